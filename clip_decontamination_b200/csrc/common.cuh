@@ -1,0 +1,78 @@
+// Shared helpers for the libclipseg kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+
+#include "../../include/clipseg.h"
+
+typedef __nv_bfloat16 bf16;
+
+extern thread_local char g_cseg_err[512];
+extern std::atomic<long long> g_cseg_launches;
+
+#define CSEG_FAIL(code, ...)                                   \
+  do {                                                         \
+    snprintf(g_cseg_err, sizeof(g_cseg_err), __VA_ARGS__);     \
+    return (code);                                             \
+  } while (0)
+
+#define CSEG_REQUIRE(cond, ...)                                \
+  do {                                                         \
+    if (!(cond)) CSEG_FAIL(CSEG_EINVAL, __VA_ARGS__);          \
+  } while (0)
+
+// every launcher ends with this: counts the launch and surfaces launch-time errors
+#define CSEG_LAUNCH_CHECK(name)                                                         \
+  do {                                                                                  \
+    g_cseg_launches.fetch_add(1, std::memory_order_relaxed);                            \
+    cudaError_t e_ = cudaGetLastError();                                                \
+    if (e_ != cudaSuccess) CSEG_FAIL(CSEG_ECUDA, "%s: %s", name, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define CSEG_CUDA(call)                                                                  \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) CSEG_FAIL(CSEG_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// exact-erf GELU (nn.GELU default) and QuickGELU (open_clip/transformer.py:35-38)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == CSEG_ACT_GELU) return gelu_erf(x);
+  if (act == CSEG_ACT_QUICKGELU) return quick_gelu(x);
+  return x;
+}
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}

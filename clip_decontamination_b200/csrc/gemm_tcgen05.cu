@@ -1,0 +1,324 @@
+// bf16 GEMM on the 5th-gen tensor cores: TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared memory
+// -> tcgen05.mma (cta_group::1, kind::f16, M=128) -> fp32 accumulator in TMEM -> tcgen05.ld epilogue.
+//
+// C[M,N] = residual + alpha * act(A[M,K] . B[N,K]^T + bias)      A, B bf16 K-major (row-major).
+//
+// Replaces the cuBLAS/cuDNN calls behind nn.Linear / nn.MultiheadAttention in/out projections /
+// the 1x1 convolutions of the reference (open_clip/transformer.py:204,211-215,560,770;
+// simfeatup_dev/upsamplers.py:218-223,325).
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
+// (one lane), warps 2..5 = epilogue (TMEM lane group = warp % 4).  One output tile per CTA; two CTAs
+// are resident per SM (<= 100 KB shared memory, <= 256 TMEM columns each) so that one CTA's epilogue
+// overlaps the other CTA's main loop.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (tcgen05): rows are 128 B, 8-row groups are
+// 1024 B apart (SBO); LBO unused for swizzled K-major; bits 46-47 = descriptor version 1;
+// bits 61-63 = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor, kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7,10), both K-major, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+struct EpiParams {
+  const float* bias;
+  const float* residual;
+  int ldr;
+  float alpha;
+  int act;
+  int out_bf16;
+  void* C;
+  int ldc;
+  int M, N;
+};
+
+template <int BN, int STAGES>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192) gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                int K, EpiParams ep) {
+  using C = Cfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + C::BAR_OFF);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + STAGES * 8, tfull = empty0 + STAGES * 8;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int num_kb = K / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + s * 8, 1);
+      mbar_init(empty0 + s * 8, 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty0 + s * 8, ph ^ 1);
+        mbar_expect_tx(full0 + s * 8, C::STAGE_BYTES);
+        const uint32_t a_dst = smem_base + s * C::STAGE_BYTES;
+        tma_load_2d(a_dst, &tmA, full0 + s * 8, kb * BK, m0);
+        tma_load_2d(a_dst + C::A_BYTES, &tmB, full0 + s * 8, kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full0 + s * 8, ph);
+        tc_fence_after();
+        const uint64_t adesc = make_sdesc(smem_base + s * C::STAGE_BYTES);
+        const uint64_t bdesc = make_sdesc(smem_base + s * C::STAGE_BYTES + C::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // +32 B per K=16 step inside the 128 B swizzle row -> +2 in the (addr >> 4) field
+          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty0 + s * 8);  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tfull);  // accumulator complete
+    }
+  } else {
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int lg = warp & 3;  // TMEM lane group this warp may read
+    const int row = m0 + lg * 32 + lane;
+    const bool row_ok = row < ep.M;
+    const bool vec_ok = ((ep.ldc & 7) == 0) && (ep.residual == nullptr || (ep.ldr & 3) == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, r);
+      const int col0 = n0 + c;
+      if (!row_ok || col0 >= ep.N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      const bool full = (col0 + 32 <= ep.N) && vec_ok;
+      if (full) {
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg((const float4*)(ep.bias + col0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (ep.act != CSEG_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+        }
+        if (ep.alpha != 1.0f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+        }
+        if (ep.residual) {
+          const float* rp = ep.residual + (size_t)row * ep.ldr + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 q = *(const float4*)(rp + j);
+            v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+          }
+        }
+        if (ep.out_bf16) {
+          bf16* cp = (bf16*)ep.C + (size_t)row * ep.ldc + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 pk;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+            pk.x = *(uint32_t*)&t0; pk.y = *(uint32_t*)&t1; pk.z = *(uint32_t*)&t2; pk.w = *(uint32_t*)&t3;
+            *(uint4*)(cp + j) = pk;
+          }
+        } else {
+          float* cp = (float*)ep.C + (size_t)row * ep.ldc + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *(float4*)(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          if (col >= ep.N) break;
+          float x = v[j];
+          if (ep.bias) x += ep.bias[col];
+          x = apply_act(x, ep.act) * ep.alpha;
+          if (ep.residual) x += ep.residual[(size_t)row * ep.ldr + col];
+          if (ep.out_bf16) ((bf16*)ep.C)[(size_t)row * ep.ldc + col] = __float2bfloat16_rn(x);
+          else ((float*)ep.C)[(size_t)row * ep.ldc + col] = x;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2D bf16 K-major tensor map: dims {K, rows}, box {64, box_rows}, 128B swizzle, zero OOB fill
+int make_map(CUtensorMap* m, const void* base, int rows, int K, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) CSEG_FAIL(CSEG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) CSEG_FAIL(CSEG_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld);
+  return 0;
+}
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+  using C = Cfg<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CSEG_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   C::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(N, BN), cdiv(M, BM));
+  gemm_bf16_tcgen05_kernel<BN, STAGES><<<grid, 192, C::SMEM_BYTES, st>>>(ta, tb, K, ep);
+  CSEG_LAUNCH_CHECK("gemm_bf16_tcgen05");
+  return 0;
+}
+
+}  // namespace
+
+int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
+                      const float* residual, int ldr, float alpha, int act, int out_dtype, void* C, int ldc,
+                      cudaStream_t st) {
+  CSEG_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  CSEG_REQUIRE(K % BK == 0, "gemm(bf16): K=%d must be a multiple of %d (pad the operands)", K, BK);
+  CSEG_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm(bf16): lda=%d, ldb=%d must be multiples of 8", lda, ldb);
+  CSEG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm(bf16): operands must be 16-byte aligned");
+  int bn = (N <= 64 || (long long)cdiv(M, BM) * cdiv(N, 128) < 2LL * sm_count()) ? 64 : 128;
+  CUtensorMap ta, tb;
+  int rc = make_map(&ta, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_map(&tb, B, N, K, ldb, bn);
+  if (rc) return rc;
+  EpiParams ep{bias, residual, ldr, alpha, act, out_dtype == CSEG_BF16, C, ldc, M, N};
+  if (bn == 64) return launch<64, 4>(ta, tb, M, N, K, ep, st);
+  return launch<128, 3>(ta, tb, M, N, K, ep, st);
+}

@@ -1,0 +1,340 @@
+// SimFeatUp joint-bilateral upsampler (simfeatup_dev/upsamplers.py:202-325), channel-last layout.
+//   guidance  : adaptive_avg_pool2d of the crop                           (:316)
+//   range_proj: conv1x1(3->32) . GELU . conv1x1(32->32)                    (:209-214)
+//   range_kernel: (2r+1)^2 reflect-padded key.query logits -> softmax * Gaussian, renormalised
+//                                                                          (:230-251,258-262)
+//   [fixup_proj: two 1x1 convs = two cseg_gemm calls with GELU / residual epilogues, :264]
+//   apply     : bicubic x2 + reflect pad + adaptive conv                   (:268-274, :14-25)
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {  // F.pad(mode='reflect'), single bounce
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void guidance_kernel(const float* __restrict__ img, int H, int W, const int32_t* __restrict__ wins,
+                                int n_crops, int crop_h, int crop_w, int pad_top, int pad_left, int gh, int gw,
+                                float4* __restrict__ guid) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_crops * gh * gw) return;
+  const int gx = idx % gw, gy = (idx / gw) % gh, crop = idx / (gw * gh);
+  const int y1 = wins[crop * 4], x1 = wins[crop * 4 + 1], wh = wins[crop * 4 + 2], ww = wins[crop * 4 + 3];
+  // adaptive pooling window: [floor(i*in/out), ceil((i+1)*in/out))
+  const int ys = (gy * crop_h) / gh, ye = ((gy + 1) * crop_h + gh - 1) / gh;
+  const int xs = (gx * crop_w) / gw, xe = ((gx + 1) * crop_w + gw - 1) / gw;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int c = 0; c < 3; ++c)
+    for (int y = ys; y < ye; ++y)
+      for (int x = xs; x < xe; ++x) {
+        const int cy = y - pad_top, cx = x - pad_left;
+        if (cy >= 0 && cy < wh && cx >= 0 && cx < ww) acc[c] += img[((size_t)c * H + y1 + cy) * W + x1 + cx];
+      }
+  const float inv = 1.0f / (float)((ye - ys) * (xe - xs));
+  guid[idx] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int KD>
+__global__ void __launch_bounds__(256) range_proj_kernel(const float4* __restrict__ guid, int n_pix,
+                                                         const float* __restrict__ w0, const float* __restrict__ b0,
+                                                         const float* __restrict__ w3, const float* __restrict__ b3,
+                                                         float* __restrict__ proj) {
+  __shared__ float sw0[KD * 3], sb0[KD], sw3[KD * KD], sb3[KD];
+  for (int i = threadIdx.x; i < KD * 3; i += blockDim.x) sw0[i] = w0[i];
+  for (int i = threadIdx.x; i < KD * KD; i += blockDim.x) sw3[i] = w3[i];
+  for (int i = threadIdx.x; i < KD; i += blockDim.x) { sb0[i] = b0[i]; sb3[i] = b3[i]; }
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= n_pix) return;
+  const float4 g = guid[pix];
+  float h[KD];
+#pragma unroll
+  for (int k = 0; k < KD; ++k) h[k] = gelu_erf(sw0[k * 3] * g.x + sw0[k * 3 + 1] * g.y + sw0[k * 3 + 2] * g.z + sb0[k]);
+  float* o = proj + (size_t)pix * KD;
+#pragma unroll 4
+  for (int k = 0; k < KD; ++k) {
+    float a = sb3[k];
+#pragma unroll
+    for (int j = 0; j < KD; ++j) a = fmaf(sw3[k * KD + j], h[j], a);
+    o[k] = a;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One thread per pixel; a 16x16 pixel tile's (16+2R)^2 halo of projections is staged in shared memory
+// as channel planes (conflict-free for x-adjacent lanes).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int R, int KD>
+__global__ void __launch_bounds__(256) range_kernel_kernel(const float* __restrict__ proj,
+                                                           const float4* __restrict__ guid, int gh, int gw,
+                                                           float pos_temp, float inv2s2, T* __restrict__ kern,
+                                                           int ldk) {
+  constexpr int DIA = 2 * R + 1, D2 = DIA * DIA, TS = 16, HS = TS + 2 * R;
+  extern __shared__ float sp[];  // [KD][HS*HS]
+  const int crop = blockIdx.z, ty0 = blockIdx.y * TS, tx0 = blockIdx.x * TS;
+  const float* pc = proj + (size_t)crop * gh * gw * KD;
+  for (int e = threadIdx.x; e < HS * HS * KD; e += blockDim.x) {
+    const int k = e % KD, pos = e / KD;
+    const int hy = pos / HS, hx = pos % HS;
+    const int y = reflect_idx(min(ty0 + hy - R, gh - 1 + R), gh), x = reflect_idx(min(tx0 + hx - R, gw - 1 + R), gw);
+    sp[k * (HS * HS) + pos] = pc[((size_t)y * gw + x) * KD + k];
+  }
+  __syncthreads();
+  const int lx = threadIdx.x % TS, ly = threadIdx.x / TS;
+  const int y = ty0 + ly, x = tx0 + lx;
+  if (y >= gh || x >= gw) return;
+  float q[KD];
+#pragma unroll
+  for (int k = 0; k < KD; ++k) q[k] = sp[k * (HS * HS) + (ly + R) * HS + lx + R];
+  float lg[D2];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < DIA; ++i)
+#pragma unroll
+    for (int j = 0; j < DIA; ++j) {
+      float a = 0.f;
+      const int pos = (ly + i) * HS + lx + j;
+#pragma unroll
+      for (int k = 0; k < KD; ++k) a = fmaf(sp[k * (HS * HS) + pos], q[k], a);
+      a *= pos_temp;
+      lg[i * DIA + j] = a;
+      m = fmaxf(m, a);
+    }
+  float se = 0.f;
+#pragma unroll
+  for (int t = 0; t < D2; ++t) {
+    lg[t] = __expf(lg[t] - m);
+    se += lg[t];
+  }
+  const float inv_se = 1.0f / se;
+  float sc = 0.f;
+#pragma unroll
+  for (int i = 0; i < DIA; ++i)
+#pragma unroll
+    for (int j = 0; j < DIA; ++j) {
+      // get_spatial_kernel: coordinates linspace(-1, 1, DIA) on both axes
+      const float dy = -1.f + 2.f * i / (DIA - 1), dx = -1.f + 2.f * j / (DIA - 1);
+      const float g = __expf(-(dy * dy + dx * dx) * inv2s2);
+      lg[i * DIA + j] = lg[i * DIA + j] * inv_se * g;
+      sc += lg[i * DIA + j];
+    }
+  const float inv_sc = 1.0f / fmaxf(sc, 1e-7f);
+  const size_t pix = ((size_t)crop * gh + y) * gw + x;
+  T* o = kern + pix * ldk;
+#pragma unroll
+  for (int t = 0; t < D2; ++t) o[t] = from_f32<T>(lg[t] * inv_sc);
+  const float4 g = guid[pix];
+  o[D2] = from_f32<T>(g.x);
+  o[D2 + 1] = from_f32<T>(g.y);
+  o[D2 + 2] = from_f32<T>(g.z);
+  for (int t = D2 + 3; t < ldk; ++t) o[t] = from_f32<T>(0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// bicubic x2 upsample, align_corners=False, A=-0.75 (torch upsample_bicubic2d), channel-last
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  c[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  c[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  c[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bicubic2x_kernel(const T* __restrict__ src, int n_crops, int h, int w, int C,
+                                                        T* __restrict__ dst) {
+  const int H2 = 2 * h, W2 = 2 * w;
+  const long long total = (long long)n_crops * H2 * W2 * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    long long r = idx / C;
+    const int X = (int)(r % W2);
+    r /= W2;
+    const int Y = (int)(r % H2), crop = (int)(r / H2);
+    const float sy = ((float)Y + 0.5f) * 0.5f - 0.5f, sx = ((float)X + 0.5f) * 0.5f - 0.5f;
+    const int iy = (int)floorf(sy), ix = (int)floorf(sx);
+    float cy[4], cx[4];
+    cubic_coeffs(sy - (float)iy, cy);
+    cubic_coeffs(sx - (float)ix, cx);
+    const T* sb = src + (size_t)crop * h * w * C + c;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), h - 1);
+      float row = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int xx = min(max(ix - 1 + b, 0), w - 1);
+        row = fmaf(cx[b], to_f32(sb[((size_t)yy * w + xx) * C]), row);
+      }
+      acc = fmaf(cy[a], row, acc);
+    }
+    dst[idx] = from_f32<T>(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// adaptive conv over the (virtually) reflect-padded high-res source:
+//   out[p, c] = sum_t hr[reflect(p + t)][c] * kern[p][t]
+// One thread per (pixel, 8-channel group); threads of a warp share the pixel's weights through L1.
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct V8;
+template <> struct V8<bf16> {
+  static __device__ __forceinline__ void ld(const bf16* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void st(bf16* p, const float (&v)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <> struct V8<float> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+
+template <typename T, int R>
+__global__ void __launch_bounds__(256) adaptive_conv_kernel(const T* __restrict__ hr, int n_crops, int H2, int W2, int C,
+                                                            const T* __restrict__ kern, int ldk, T* __restrict__ dst) {
+  constexpr int DIA = 2 * R + 1;
+  const int cg = C / 8;
+  const long long total = (long long)n_crops * H2 * W2 * cg;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % cg);
+    const long long pix = idx / cg;
+    const int X = (int)(pix % W2), Y = (int)((pix / W2) % H2), crop = (int)(pix / ((long long)W2 * H2));
+    const T* kp = kern + pix * ldk;
+    const T* hb = hr + (size_t)crop * H2 * W2 * C + g * 8;
+    float acc[8] = {};
+#pragma unroll 1
+    for (int i = 0; i < DIA; ++i) {
+      const int yy = reflect_idx(Y + i - R, H2);
+#pragma unroll
+      for (int j = 0; j < DIA; ++j) {
+        const int xx = reflect_idx(X + j - R, W2);
+        const float wv = to_f32(kp[i * DIA + j]);
+        float v[8];
+        V8<T>::ld(hb + ((size_t)yy * W2 + xx) * C, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[e], wv, acc[e]);
+      }
+    }
+    V8<T>::st(dst + pix * C + g * 8, acc);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int cseg_jbu_guidance(const float* img, int H, int W, const int32_t* windows, int n_crops, int crop_h, int crop_w,
+                      int pad_top, int pad_left, int gh, int gw, float* guid, void* stream) {
+  CSEG_REQUIRE(n_crops > 0 && gh > 0 && gw > 0 && gh <= crop_h && gw <= crop_w, "jbu_guidance: bad shape");
+  const int n = n_crops * gh * gw;
+  guidance_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(img, H, W, windows, n_crops, crop_h, crop_w, pad_top,
+                                                                  pad_left, gh, gw, (float4*)guid);
+  CSEG_LAUNCH_CHECK("jbu_guidance");
+  return 0;
+}
+
+int cseg_jbu_range_proj(const float* guid, int n_pix, int key_dim, const float* w0, const float* b0, const float* w3,
+                        const float* b3, float* proj, void* stream) {
+  CSEG_REQUIRE(n_pix > 0, "jbu_range_proj: empty");
+  CSEG_REQUIRE(key_dim == 32, "jbu_range_proj: key_dim=%d (only 32, simfeatup_dev/upsamplers.py:282-308)", key_dim);
+  range_proj_kernel<32><<<cdiv(n_pix, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)guid, n_pix, w0, b0, w3, b3,
+                                                                            proj);
+  CSEG_LAUNCH_CHECK("jbu_range_proj");
+  return 0;
+}
+
+}  // extern "C"
+
+template <typename T, int R>
+static int launch_range_kernel(const float* proj, const float* guid, int n_crops, int gh, int gw, float pos_temp,
+                               float inv2s2, void* kern, int ldk, cudaStream_t st) {
+  constexpr int HS = 16 + 2 * R;
+  const size_t smem = (size_t)32 * HS * HS * sizeof(float);
+  CSEG_CUDA(cudaFuncSetAttribute(range_kernel_kernel<T, R, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(gw, 16), cdiv(gh, 16), n_crops);
+  range_kernel_kernel<T, R, 32><<<grid, 256, smem, st>>>(proj, (const float4*)guid, gh, gw, pos_temp, inv2s2, (T*)kern,
+                                                         ldk);
+  CSEG_LAUNCH_CHECK("jbu_range_kernel");
+  return 0;
+}
+
+template <typename T>
+static int launch_apply(const void* src, int n_crops, int h, int w, int C, const void* kern, int ldk, int radius,
+                        void* dst, void* hr_scratch, cudaStream_t st) {
+  const int H2 = 2 * h, W2 = 2 * w;
+  const long long tot_b = (long long)n_crops * H2 * W2 * C;
+  bicubic2x_kernel<T><<<(int)std::min<long long>((tot_b + 255) / 256, (long long)sm_count() * 32), 256, 0, st>>>(
+      (const T*)src, n_crops, h, w, C, (T*)hr_scratch);
+  CSEG_LAUNCH_CHECK("jbu_bicubic2x");
+  const long long tot = (long long)n_crops * H2 * W2 * (C / 8);
+  const int blocks = (int)std::min<long long>((tot + 255) / 256, (long long)sm_count() * 64);
+  if (radius == 5)
+    adaptive_conv_kernel<T, 5><<<blocks, 256, 0, st>>>((const T*)hr_scratch, n_crops, H2, W2, C, (const T*)kern, ldk,
+                                                       (T*)dst);
+  else
+    adaptive_conv_kernel<T, 3><<<blocks, 256, 0, st>>>((const T*)hr_scratch, n_crops, H2, W2, C, (const T*)kern, ldk,
+                                                       (T*)dst);
+  CSEG_LAUNCH_CHECK("jbu_adaptive_conv");
+  return 0;
+}
+
+extern "C" {
+
+int cseg_jbu_range_kernel(const float* proj, const float* guid, int n_crops, int gh, int gw, int key_dim, int radius,
+                          float range_temp, float sigma_spatial, int out_dtype, void* kern, int ldk, void* stream) {
+  CSEG_REQUIRE(n_crops > 0 && gh > radius && gw > radius, "jbu_range_kernel: grid %dx%d too small for radius %d", gh, gw, radius);
+  CSEG_REQUIRE(key_dim == 32, "jbu_range_kernel: key_dim=%d (only 32)", key_dim);
+  CSEG_REQUIRE(radius == 3 || radius == 5, "jbu_range_kernel: radius=%d (3 = jbu_stack, 5 = jbu_one)", radius);
+  const int d2 = (2 * radius + 1) * (2 * radius + 1);
+  CSEG_REQUIRE(ldk >= d2 + 3, "jbu_range_kernel: ldk=%d < %d", ldk, d2 + 3);
+  // pos_temp = exp(range_temp).clamp(1e-4, 1e4)   (simfeatup_dev/upsamplers.py:237)
+  const float pos_temp = fminf(fmaxf(expf(range_temp), 1e-4f), 1e4f);
+  const float inv2s2 = 1.0f / (2.0f * sigma_spatial * sigma_spatial);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == CSEG_BF16) {
+    if (radius == 5) return launch_range_kernel<bf16, 5>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, ldk, st);
+    return launch_range_kernel<bf16, 3>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, ldk, st);
+  }
+  if (radius == 5) return launch_range_kernel<float, 5>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, ldk, st);
+  return launch_range_kernel<float, 3>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, ldk, st);
+}
+
+int cseg_jbu_apply(int dtype, const void* src, int n_crops, int h, int w, int C, const void* kern, int ldk, int radius,
+                   void* dst, void* hr_scratch, void* stream) {
+  CSEG_REQUIRE(n_crops > 0 && h > 0 && w > 0 && C % 8 == 0, "jbu_apply: C=%d must be a multiple of 8", C);
+  CSEG_REQUIRE(radius == 3 || radius == 5, "jbu_apply: radius=%d (3 or 5)", radius);
+  CSEG_REQUIRE(2 * h > radius && 2 * w > radius, "jbu_apply: source too small for reflect padding");
+  CSEG_REQUIRE(hr_scratch != nullptr, "jbu_apply: hr_scratch (n*2h*2w*C elements) required");
+  if (dtype == CSEG_BF16) return launch_apply<bf16>(src, n_crops, h, w, C, kern, ldk, radius, dst, hr_scratch, (cudaStream_t)stream);
+  return launch_apply<float>(src, n_crops, h, w, C, kern, ldk, radius, dst, hr_scratch, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,286 @@
+// Segmentor-side kernels: per-pixel L2-normalise + cosine logits (segmentor.py:374-375), the fused
+// sliding-window accumulate -> count-normalise -> resize -> softmax -> synonym max -> argmax ->
+// background threshold (segmentor.py:413-449,475-489) and the IoU histograms of mmseg's IoUMetric.
+#include "common.cuh"
+
+namespace {
+
+constexpr int QMAX = 32;  // queries per class file (largest shipped: iSAID 16, OpenEarthMap 8+)
+
+// ---------------------------------------------------------------------------------------------
+// A10: logits[crop][q][pix] = <f/|f|, t_q> (+ cls bias).  8 lanes per feature row, 16-byte loads.
+// HBM-bound: reads rows*D*sizeof(T), writes rows*Q*4.
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Vec8;
+template <> struct Vec8<bf16> {
+  static __device__ __forceinline__ void ld(const bf16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+};
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
+template <typename T, int QT>
+__global__ void __launch_bounds__(256) norm_sim_kernel(const T* __restrict__ feats, int ldf, long long rows, int hw,
+                                                       int D, const float* __restrict__ text, int Q,
+                                                       const float* __restrict__ cls_bias,
+                                                       float* __restrict__ logits) {
+  extern __shared__ float ts[];  // [Q][D]
+  for (int i = threadIdx.x; i < Q * D; i += blockDim.x) ts[i] = text[i];
+  __syncthreads();
+  const int sub = threadIdx.x & 7;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; row < rows;
+       row += ((long long)gridDim.x * blockDim.x) >> 3) {
+    const T* f = feats + row * ldf;
+    float ss = 0.f, dot[QT];
+#pragma unroll
+    for (int q = 0; q < QT; ++q) dot[q] = 0.f;
+    for (int c = sub * 8; c < D; c += 64) {
+      float v[8];
+      Vec8<T>::ld(f + c, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss = fmaf(v[e], v[e], ss);
+#pragma unroll
+      for (int q = 0; q < QT; ++q)
+        if (q < Q) {
+          const float* t = ts + q * D + c;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dot[q] = fmaf(v[e], t[e], dot[q]);
+        }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+#pragma unroll
+      for (int q = 0; q < QT; ++q) dot[q] += __shfl_xor_sync(0xffffffffu, dot[q], o);
+    }
+    const float inv = 1.0f / sqrtf(ss);
+    const long long crop = row / hw, pix = row % hw;
+#pragma unroll
+    for (int q = 0; q < QT; ++q)
+      if (q < Q && (q & 7) == sub) {
+        float v = dot[q] * inv;
+        if (cls_bias) v += cls_bias[crop * Q + q];
+        logits[(crop * Q + q) * hw + pix] = v;
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A11 + A12 fused.  One thread per output pixel; every crop logit is read exactly once when
+// (out_h,out_w) == (H,W); labels are the only mandatory write.
+// ---------------------------------------------------------------------------------------------
+struct AccumParams {
+  const float* crop_logits;
+  int n_crops, Q, lh, lw, crop_h, crop_w, pad_top, pad_left;
+  const int32_t* windows;
+  int H, W, out_h, out_w;
+  const int32_t* query_idx;
+  int K;
+  float logit_scale, prob_thd;
+  int bg_idx;
+  uint8_t* labels;
+  float* probs;
+  float* avg_logits;
+};
+
+// torch upsample_bilinear2d, align_corners=False: src = max(scale*(dst+0.5)-0.5, 0)
+__device__ __forceinline__ void bilin_coord(int dst, int in_size, int out_size, int& i0, int& i1, float& l1) {
+  const float scale = (float)in_size / (float)out_size;
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = src - (float)i0;
+}
+
+// value of crop `cr`, query q at canvas-crop coordinate (cy, cx) in [0,crop_h) x [0,crop_w)
+__device__ __forceinline__ float crop_value(const AccumParams& p, int cr, int q, int cy, int cx) {
+  const float* base = p.crop_logits + ((size_t)cr * p.Q + q) * p.lh * p.lw;
+  if (p.lh == p.crop_h && p.lw == p.crop_w) return base[cy * p.lw + cx];
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilin_coord(cy, p.lh, p.crop_h, y0, y1, ly);
+  bilin_coord(cx, p.lw, p.crop_w, x0, x1, lx);
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  return hy * (hx * base[y0 * p.lw + x0] + lx * base[y0 * p.lw + x1]) +
+         ly * (hx * base[y1 * p.lw + x0] + lx * base[y1 * p.lw + x1]);
+}
+
+// averaged logits of canvas pixel (y, x): windows visited in forward_slide order (segmentor.py:416-444)
+__device__ __forceinline__ void canvas_avg(const AccumParams& p, const int4* wins, int y, int x, float (&acc)[QMAX]) {
+#pragma unroll
+  for (int q = 0; q < QMAX; ++q) acc[q] = 0.f;
+  int count = 0;
+  for (int cr = 0; cr < p.n_crops; ++cr) {
+    const int4 w = wins[cr];  // y1, x1, h, w
+    const int ly = y - w.x, lx = x - w.y;
+    if (ly < 0 || ly >= w.z || lx < 0 || lx >= w.w) continue;
+    ++count;
+#pragma unroll
+    for (int q = 0; q < QMAX; ++q)
+      if (q < p.Q) acc[q] += crop_value(p, cr, q, ly + p.pad_top, lx + p.pad_left);
+  }
+  const float cnt = (float)count;
+#pragma unroll
+  for (int q = 0; q < QMAX; ++q)
+    if (q < p.Q) acc[q] = acc[q] / cnt;
+}
+
+__global__ void __launch_bounds__(256) accum_argmax_kernel(const AccumParams p) {
+  extern __shared__ int4 s_wins[];
+  for (int i = threadIdx.x; i < p.n_crops; i += blockDim.x)
+    s_wins[i] = make_int4(p.windows[4 * i], p.windows[4 * i + 1], p.windows[4 * i + 2], p.windows[4 * i + 3]);
+  __syncthreads();
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
+  if (ox >= p.out_w) return;
+  float v[QMAX];
+  if (p.out_h == p.H && p.out_w == p.W) {
+    canvas_avg(p, s_wins, oy, ox, v);
+    if (p.avg_logits) {
+#pragma unroll
+      for (int q = 0; q < QMAX; ++q)
+        if (q < p.Q) p.avg_logits[((size_t)q * p.H + oy) * p.W + ox] = v[q];
+    }
+  } else {  // bilinear resize of the averaged canvas to ori_shape (segmentor.py:448-449)
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilin_coord(oy, p.H, p.out_h, y0, y1, ly);
+    bilin_coord(ox, p.W, p.out_w, x0, x1, lx);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    float a[QMAX], b[QMAX];
+    canvas_avg(p, s_wins, y0, x0, a);
+    canvas_avg(p, s_wins, y0, x1, b);
+#pragma unroll
+    for (int q = 0; q < QMAX; ++q) v[q] = hy * (hx * a[q] + lx * b[q]);
+    canvas_avg(p, s_wins, y1, x0, a);
+    canvas_avg(p, s_wins, y1, x1, b);
+#pragma unroll
+    for (int q = 0; q < QMAX; ++q) v[q] += ly * (hx * a[q] + lx * b[q]);
+  }
+  // x logit_scale, softmax over Q (segmentor.py:478-479)
+  float m = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < QMAX; ++q)
+    if (q < p.Q) {
+      v[q] *= p.logit_scale;
+      m = fmaxf(m, v[q]);
+    }
+  float sum = 0.f;
+#pragma unroll
+  for (int q = 0; q < QMAX; ++q)
+    if (q < p.Q) sum += expf(v[q] - m);
+  // per-class max over its synonym queries, argmax with lowest-index ties (segmentor.py:481-488);
+  // ordering is decided on the scaled logits (softmax is monotone), probabilities only feed the
+  // threshold and the optional probs output.
+  float best = -INFINITY;
+  int best_k = 0;
+  for (int k = 0; k < p.K; ++k) {
+    float ck = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < QMAX; ++q)
+      if (q < p.Q && p.query_idx[q] == k) ck = fmaxf(ck, v[q]);
+    if (p.probs) p.probs[((size_t)k * p.out_h + oy) * p.out_w + ox] = expf(ck - m) / sum;
+    if (ck > best) {
+      best = ck;
+      best_k = k;
+    }
+  }
+  const float pmax = expf(best - m) / sum;
+  if (pmax < p.prob_thd) best_k = p.bg_idx;  // segmentor.py:489
+  p.labels[(size_t)oy * p.out_w + ox] = (uint8_t)best_k;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K17: per-class intersect / pred / label counts (mmseg IoUMetric.intersect_and_union)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) iou_hist_kernel(const uint8_t* __restrict__ pred,
+                                                       const uint8_t* __restrict__ label, long long n, int K,
+                                                       int ignore, unsigned long long* __restrict__ hist) {
+  extern __shared__ unsigned int sh[];  // [3][K]
+  for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int l = label[i], pr = pred[i];
+    if (l == ignore) continue;
+    if (pr < K) atomicAdd(&sh[K + pr], 1u);
+    if (l < K) atomicAdd(&sh[2 * K + l], 1u);
+    if (pr == l && pr < K) atomicAdd(&sh[pr], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * K; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
+}  // namespace
+
+template <typename T>
+static int launch_norm_sim(const void* feats, int ldf, int n_crops, int hw, int D, const float* text, int Q,
+                           const float* cls_bias, float* logits, cudaStream_t st) {
+  const long long rows = (long long)n_crops * hw;
+  const size_t smem = (size_t)Q * D * sizeof(float);
+  const int blocks = (int)std::min<long long>((rows * 8 + 255) / 256, (long long)sm_count() * 8);
+#define NS_LAUNCH(QT)                                                                                          \
+  do {                                                                                                         \
+    CSEG_CUDA(cudaFuncSetAttribute(norm_sim_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    norm_sim_kernel<T, QT><<<blocks, 256, smem, st>>>((const T*)feats, ldf, rows, hw, D, text, Q, cls_bias, logits); \
+  } while (0)
+  if (Q <= 8) NS_LAUNCH(8);
+  else if (Q <= 16) NS_LAUNCH(16);
+  else NS_LAUNCH(32);
+#undef NS_LAUNCH
+  CSEG_LAUNCH_CHECK("norm_sim");
+  return 0;
+}
+
+extern "C" {
+
+int cseg_norm_sim(int dtype, const void* feats, int ldf, int n_crops, int hw, int D, const float* text, int Q,
+                  const float* cls_logit_bias, float* logits, void* stream) {
+  CSEG_REQUIRE(n_crops > 0 && hw > 0 && D > 0 && D % 8 == 0 && ldf % 8 == 0, "norm_sim: D=%d, ldf=%d must be multiples of 8", D, ldf);
+  CSEG_REQUIRE(Q >= 1 && Q <= QMAX, "norm_sim: Q=%d outside [1, %d]", Q, QMAX);
+  CSEG_REQUIRE((size_t)Q * D * 4 <= 200 * 1024, "norm_sim: text table too large for shared memory");
+  if (dtype == CSEG_BF16)
+    return launch_norm_sim<bf16>(feats, ldf, n_crops, hw, D, text, Q, cls_logit_bias, logits, (cudaStream_t)stream);
+  return launch_norm_sim<float>(feats, ldf, n_crops, hw, D, text, Q, cls_logit_bias, logits, (cudaStream_t)stream);
+}
+
+int cseg_accum_argmax(const float* crop_logits, int n_crops, int Q, int lh, int lw, int crop_h, int crop_w,
+                      int pad_top, int pad_left, const int32_t* windows, int H, int W, int out_h, int out_w,
+                      const int32_t* query_idx, int K, float logit_scale, float prob_thd, int bg_idx,
+                      uint8_t* labels, float* probs, float* avg_logits, void* stream) {
+  CSEG_REQUIRE(n_crops > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0, "accum_argmax: empty problem");
+  CSEG_REQUIRE(Q >= 1 && Q <= QMAX, "accum_argmax: Q=%d outside [1, %d]", Q, QMAX);
+  CSEG_REQUIRE(K >= 1 && K <= 256 && bg_idx >= 0 && bg_idx < 256, "accum_argmax: K=%d / bg_idx=%d do not fit uint8 labels", K, bg_idx);
+  CSEG_REQUIRE(avg_logits == nullptr || (out_h == H && out_w == W), "accum_argmax: avg_logits needs out size == canvas size");
+  AccumParams p{crop_logits, n_crops, Q, lh, lw, crop_h, crop_w, pad_top, pad_left, windows, H, W, out_h, out_w,
+                query_idx, K, logit_scale, prob_thd, bg_idx, labels, probs, avg_logits};
+  dim3 grid(cdiv(out_w, 256), out_h);
+  accum_argmax_kernel<<<grid, 256, (size_t)n_crops * sizeof(int4), (cudaStream_t)stream>>>(p);
+  CSEG_LAUNCH_CHECK("accum_argmax");
+  return 0;
+}
+
+int cseg_iou_hist(const uint8_t* pred, const uint8_t* label, long long n, int K, int ignore_index, long long* hist,
+                  void* stream) {
+  CSEG_REQUIRE(n > 0 && K >= 1 && K <= 256, "iou_hist: bad arguments");
+  const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
+  iou_hist_kernel<<<blocks, 256, (size_t)3 * K * sizeof(unsigned int), (cudaStream_t)stream>>>(
+      pred, label, n, K, ignore_index, (unsigned long long*)hist);
+  CSEG_LAUNCH_CHECK("iou_hist");
+  return 0;
+}
+
+}  // extern "C"

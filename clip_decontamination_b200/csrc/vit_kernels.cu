@@ -1,0 +1,612 @@
+// ViT-side kernels that are not GEMMs: input preprocessing, crop -> patch matrix, token assembly,
+// LayerNorm, attention (standard and the modified final-block variants), similarity map, outlier
+// suppression, CLS normalise + global debias.  Reference: open_clip/transformer.py,
+// similarity_enhancement.py, outlier_suppression.py, segmentor.py (cited per kernel).
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// segmentor.py:64-67 (mmseg SegDataPreProcessor): uint8 HWC BGR -> fp32 CHW RGB, (x-mean)/std
+// ---------------------------------------------------------------------------------------------
+__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ img, int HW, float m0, float m1, float m2, float s0,
+                                     float s1, float s2, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  const float b = img[3 * i + 0], g = img[3 * i + 1], r = img[3 * i + 2];
+  out[i] = (r - m0) / s0;
+  out[HW + i] = (g - m1) / s1;
+  out[2 * HW + i] = (b - m2) / s2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// open_clip/transformer.py:560-562 as an im2col gather (the conv has stride == kernel, no bias)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void patchify_kernel(const float* __restrict__ img, int H, int W, const int32_t* __restrict__ wins,
+                                int n_crops, int gh, int gw, int pad_top, int pad_left, int ps, T* __restrict__ out,
+                                int ldo) {
+  const long long total = (long long)n_crops * gh * gw * ldo;
+  const int kk = 3 * ps * ps;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % ldo);
+    const long long row = idx / ldo;
+    float v = 0.f;
+    if (col < kk) {
+      const int p = (int)(row % (gh * gw));
+      const int crop = (int)(row / (gh * gw));
+      const int c = col / (ps * ps), ky = (col / ps) % ps, kx = col % ps;
+      const int cy = (p / gw) * ps + ky - pad_top, cx = (p % gw) * ps + kx - pad_left;
+      const int y1 = wins[crop * 4 + 0], x1 = wins[crop * 4 + 1], wh = wins[crop * 4 + 2], ww = wins[crop * 4 + 3];
+      if (cy >= 0 && cy < wh && cx >= 0 && cx < ww) v = img[((size_t)c * H + (y1 + cy)) * W + (x1 + cx)];
+    }
+    out[idx] = from_f32<T>(v);
+  }
+}
+
+// open_clip/transformer.py:565-571
+__global__ void embed_tokens_kernel(const float* __restrict__ pe, const float* __restrict__ cls,
+                                    const float* __restrict__ pos, int n_crops, int L, int width,
+                                    float* __restrict__ x) {
+  const long long total = (long long)n_crops * L * width;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % width);
+    const long long row = idx / width;
+    const int t = (int)(row % L);
+    const int crop = (int)(row / L);
+    const float v = (t == 0) ? cls[c] : pe[((size_t)crop * (L - 1) + (t - 1)) * width + c];
+    x[idx] = v + pos[(size_t)t * width + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNormFp32, open_clip/transformer.py:17-23.  One warp per row, two-pass statistics.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void layernorm_kernel(const float* x, int rows, int width, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, T* out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (size_t)warp * width;
+  float s = 0.f;
+  for (int c = lane; c < width; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / width;
+  float v = 0.f;
+  for (int c = lane; c < width; c += 32) {
+    const float d = xr[c] - mean;
+    v += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(v) / width + eps);
+  T* orow = out + (size_t)warp * width;
+  for (int c = lane; c < width; c += 32) orow[c] = from_f32<T>((xr[c] - mean) * rstd * gamma[c] + beta[c]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Attention.  One CTA per (crop, head); Q, K, V of the head live in shared memory (type T); each warp
+// owns query rows i = warp, warp+8, ...; a lane owns keys j = lane + 32 t.  All softmax arithmetic
+// is fp32.  Reference: nn.MultiheadAttention (open_clip/transformer.py:204,218-232) for mode STD and
+// VisionTransformer.custom_attn (:822-940) for the others.
+// ---------------------------------------------------------------------------------------------
+constexpr int ATT_WARPS = 8;
+constexpr int ATT_JMAX = 10;  // L <= 320
+
+template <typename T> struct Pair;
+template <> struct Pair<float> {
+  static __device__ __forceinline__ float2 ld(const float* p) { return make_float2(p[0], p[1]); }
+  static __device__ __forceinline__ void st(float* p, float a, float b) { p[0] = a; p[1] = b; }
+};
+template <> struct Pair<bf16> {
+  static __device__ __forceinline__ float2 ld(const bf16* p) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+  }
+  static __device__ __forceinline__ void st(bf16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+  }
+};
+
+template <typename T, int HD>
+__device__ __forceinline__ float dot_row(const float (&r)[HD], const T* row) {
+  float acc = 0.f;
+#pragma unroll
+  for (int d = 0; d < HD; d += 2) {
+    const float2 v = Pair<T>::ld(row + d);
+    acc = fmaf(r[d], v.x, acc);
+    acc = fmaf(r[d + 1], v.y, acc);
+  }
+  return acc;
+}
+
+template <typename T, int HD>
+__device__ __forceinline__ void load_row(float (&r)[HD], const T* row) {
+#pragma unroll
+  for (int d = 0; d < HD; d += 2) {
+    const float2 v = Pair<T>::ld(row + d);
+    r[d] = v.x;
+    r[d + 1] = v.y;
+  }
+}
+
+// softmax over the keys a warp holds (s[t] for key lane+32t, invalid keys hold -inf)
+__device__ __forceinline__ void warp_softmax(float (&s)[ATT_JMAX], int nj) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < ATT_JMAX; ++t)
+    if (t < nj) m = fmaxf(m, s[t]);
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < ATT_JMAX; ++t)
+    if (t < nj) {
+      s[t] = __expf(s[t] - m);
+      sum += s[t];
+    }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int t = 0; t < ATT_JMAX; ++t)
+    if (t < nj) s[t] *= inv;
+}
+
+template <typename T, int HD>
+__global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const T* __restrict__ qkv, int L, int heads,
+                                                                   int mode, const float* __restrict__ simmap,
+                                                                   float simw, T* __restrict__ out,
+                                                                   float* __restrict__ stats) {
+  constexpr int LDS = HD + (sizeof(T) == 2 ? 2 : 1);
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  T* Qs = reinterpret_cast<T*>(att_smem);
+  T* Ks = Qs + (size_t)L * LDS;
+  T* Vs = Ks + (size_t)L * LDS;
+  float* Pb = reinterpret_cast<float*>(att_smem + (((size_t)3 * L * LDS * sizeof(T) + 15) & ~(size_t)15));
+  const int crop = blockIdx.x / heads, head = blockIdx.x % heads;
+  const int width = heads * HD;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float scale = rsqrtf((float)HD);
+  const int P = L - 1;
+
+  for (int idx = tid; idx < L * (HD / 2); idx += blockDim.x) {
+    const int row = idx / (HD / 2), c = (idx % (HD / 2)) * 2;
+    const T* src = qkv + ((size_t)crop * L + row) * 3 * width + head * HD + c;
+    const float2 q = Pair<T>::ld(src), k = Pair<T>::ld(src + width), v = Pair<T>::ld(src + 2 * width);
+    Pair<T>::st(Qs + row * LDS + c, q.x, q.y);
+    Pair<T>::st(Ks + row * LDS + c, k.x, k.y);
+    Pair<T>::st(Vs + row * LDS + c, v.x, v.y);
+  }
+  __syncthreads();
+
+  const int nj = (L + 31) / 32;
+  float* pb = Pb + warp * (ATT_JMAX * 32);
+  for (int i = warp; i < L; i += ATT_WARPS) {
+    float p[ATT_JMAX];
+    if (mode == CSEG_ATTN_MASKCLIP) {
+#pragma unroll
+      for (int t = 0; t < ATT_JMAX; ++t) p[t] = (lane + 32 * t == i) ? 1.f : 0.f;
+    } else {
+      float qi[HD], ki[HD];
+      load_row<T, HD>(qi, Qs + i * LDS);
+      const bool need_k = (mode == CSEG_ATTN_EXPERIMENTAL || mode == CSEG_ATTN_SCLIP || mode == CSEG_ATTN_SFP ||
+                           mode == CSEG_ATTN_SEGEARTH);
+      if (need_k) load_row<T, HD>(ki, Ks + i * LDS);
+      // similarity-map row (zero CLS row / column), similarity_enhancement.py:104-122
+      float madd[ATT_JMAX];
+#pragma unroll
+      for (int t = 0; t < ATT_JMAX; ++t) {
+        const int j = lane + 32 * t;
+        madd[t] = (simmap != nullptr && i >= 1 && j >= 1 && j < L)
+                      ? simw * simmap[((size_t)crop * P + (i - 1)) * P + (j - 1)]
+                      : 0.f;
+      }
+      float s1[ATT_JMAX], s2[ATT_JMAX];
+#pragma unroll
+      for (int t = 0; t < ATT_JMAX; ++t) {
+        const int j = lane + 32 * t;
+        s1[t] = -INFINITY;
+        s2[t] = -INFINITY;
+        if (t < nj && j < L) {
+          if (mode == CSEG_ATTN_STD || mode == CSEG_ATTN_VANILLA) {
+            s1[t] = dot_row<T, HD>(qi, Ks + j * LDS) * scale;
+          } else {
+            s1[t] = dot_row<T, HD>(qi, Qs + j * LDS) * scale;
+            if (need_k) s2[t] = dot_row<T, HD>(ki, Ks + j * LDS) * scale;
+          }
+        }
+      }
+      if (mode == CSEG_ATTN_STD) {
+        warp_softmax(s1, nj);
+      } else if (mode == CSEG_ATTN_VANILLA || mode == CSEG_ATTN_CLEARCLIP) {
+#pragma unroll
+        for (int t = 0; t < ATT_JMAX; ++t) s1[t] += madd[t];
+        warp_softmax(s1, nj);
+      } else if (mode == CSEG_ATTN_SFP) {
+#pragma unroll
+        for (int t = 0; t < ATT_JMAX; ++t) s1[t] = 0.5f * (s1[t] + s2[t]) + madd[t];
+        warp_softmax(s1, nj);
+      } else if (mode == CSEG_ATTN_EXPERIMENTAL) {
+#pragma unroll
+        for (int t = 0; t < ATT_JMAX; ++t) s1[t] = s2[t] + s1[t];  // kk + qq, :899
+        warp_softmax(s1, nj);
+#pragma unroll
+        for (int t = 0; t < ATT_JMAX; ++t)
+          if (lane + 32 * t < L) s1[t] += madd[t];  // enhance_attention on the probabilities, :901
+        warp_softmax(s1, nj);                       // second softmax is unconditional, :902
+      } else {                                      // SCLIP / SEGEARTH
+#pragma unroll
+        for (int t = 0; t < ATT_JMAX; ++t) {
+          s1[t] += madd[t];
+          s2[t] += madd[t];
+        }
+        warp_softmax(s1, nj);
+        warp_softmax(s2, nj);
+#pragma unroll
+        for (int t = 0; t < ATT_JMAX; ++t) s1[t] += s2[t];
+        if (mode == CSEG_ATTN_SEGEARTH) {
+          load_row<T, HD>(ki, Vs + i * LDS);
+#pragma unroll
+          for (int t = 0; t < ATT_JMAX; ++t) {
+            const int j = lane + 32 * t;
+            s2[t] = (t < nj && j < L) ? dot_row<T, HD>(ki, Vs + j * LDS) * scale + madd[t] : -INFINITY;
+          }
+          warp_softmax(s2, nj);
+#pragma unroll
+          for (int t = 0; t < ATT_JMAX; ++t) s1[t] += s2[t];
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < ATT_JMAX; ++t) p[t] = (lane + 32 * t < L) ? s1[t] : 0.f;
+    }
+    if (stats != nullptr) {  // outlier_suppression.py:46-49: only P[0,1+i] and P[1+i,1+i] are consumed
+      float* st = stats + ((size_t)(crop * heads + head) * 2) * P;
+#pragma unroll
+      for (int t = 0; t < ATT_JMAX; ++t) {
+        const int j = lane + 32 * t;
+        if (j >= 1 && j < L) {
+          if (i == 0) st[j - 1] = p[t];
+          if (j == i) st[P + i - 1] = p[t];
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < ATT_JMAX; ++t)
+      if (t < nj) pb[lane + 32 * t] = p[t];
+    __syncwarp();
+    for (int dp = lane; dp < HD / 2; dp += 32) {
+      float a0 = 0.f, a1 = 0.f;
+      for (int j = 0; j < L; ++j) {
+        const float pj = pb[j];
+        const float2 v = Pair<T>::ld(Vs + j * LDS + 2 * dp);
+        a0 = fmaf(pj, v.x, a0);
+        a1 = fmaf(pj, v.y, a1);
+      }
+      Pair<T>::st(out + ((size_t)crop * L + i) * width + head * HD + 2 * dp, a0, a1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// similarity_enhancement.py:37-66.  inv_norm then a 32x32-tiled fp32 dot-product kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) simmap_kernel(const float* __restrict__ x, int L, int width, float inv_temp,
+                                                     int keep_diag, float* __restrict__ sim) {
+  __shared__ float As[32][33], Bs[32][33];
+  const int P = L - 1, crop = blockIdx.z;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const float* xb = x + ((size_t)crop * L + 1) * width;  // skip CLS
+  float acc[2][2] = {};
+  float na[2] = {}, nb[2] = {};   // squared norms of the rows this thread touches (F.normalize)
+  for (int k0 = 0; k0 < width; k0 += 32) {
+    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+      const int r = e >> 5, k = e & 31;
+      As[r][k] = (i0 + r < P && k0 + k < width) ? xb[(size_t)(i0 + r) * width + k0 + k] : 0.f;
+      Bs[r][k] = (j0 + r < P && k0 + k < width) ? xb[(size_t)(j0 + r) * width + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float a0 = As[ty * 2][k], a1 = As[ty * 2 + 1][k];
+      const float b0 = Bs[tx * 2][k], b1 = Bs[tx * 2 + 1][k];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]);
+      acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]);
+      acc[1][1] = fmaf(a1, b1, acc[1][1]);
+      na[0] = fmaf(a0, a0, na[0]); na[1] = fmaf(a1, a1, na[1]);
+      nb[0] = fmaf(b0, b0, nb[0]); nb[1] = fmaf(b1, b1, nb[1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int i = i0 + ty * 2 + a, j = j0 + tx * 2 + b;
+      if (i < P && j < P) {
+        const float ia = 1.0f / fmaxf(sqrtf(na[a]), 1e-12f), ib = 1.0f / fmaxf(sqrtf(nb[b]), 1e-12f);
+        float v = acc[a][b] * ia * ib * inv_temp;
+        if (!keep_diag && i == j) v = 0.f;
+        sim[((size_t)crop * P + i) * P + j] = v;
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// outlier_suppression.py:15-61,115-214.  One CTA per crop, zero host syncs.
+//   1. ratio_i = mean_h P[0,1+i] / (mean_h P[1+i,1+i] + 1e-8); top-k by repeated argmax
+//      (ties -> lowest index).
+//   2. per (outlier, neighbour): cosine on the ORIGINAL map; replacement and decontaminated
+//      neighbour rows go to scratch.
+//   3. ordered write-back: neighbours in (i, j) order (last writer wins, cells equal to the outlier
+//      skipped), then the outliers.
+// ---------------------------------------------------------------------------------------------
+constexpr int OS_THREADS = 256;
+constexpr int OS_MAXK = 64;
+
+__global__ void __launch_bounds__(OS_THREADS) outlier_kernel(float* __restrict__ y, int L, int width, int grid,
+                                                             const float* __restrict__ stats, int heads, int top_k,
+                                                             float ctemp, float* __restrict__ scratch,
+                                                             int32_t* __restrict__ idx_out) {
+  extern __shared__ float os_smem[];
+  const int P = L - 1, crop = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* ratio = os_smem;                       // [P]
+  __shared__ int s_idx[OS_MAXK];
+  __shared__ float s_sim[OS_MAXK][8];
+  __shared__ float s_w[OS_MAXK][8];
+  __shared__ int s_nb[OS_MAXK][8];
+  __shared__ float red_v[OS_THREADS / 32];
+  __shared__ int red_i[OS_THREADS / 32];
+
+  for (int i = tid; i < P; i += OS_THREADS) {
+    float c = 0.f, d = 0.f;
+    for (int h = 0; h < heads; ++h) {
+      const float* st = stats + ((size_t)(crop * heads + h) * 2) * P;
+      c += st[i];
+      d += st[P + i];
+    }
+    ratio[i] = (c / heads) / (d / heads + 1e-8f);
+  }
+  __syncthreads();
+  const int k = min(top_k, P);
+  for (int r = 0; r < k; ++r) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < P; i += OS_THREADS) {
+      const float v = ratio[i];
+      if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < OS_THREADS / 32; ++w)
+        if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
+      s_idx[r] = bi;
+      ratio[bi] = -INFINITY;
+      if (idx_out) idx_out[crop * top_k + r] = bi;
+    }
+    __syncthreads();
+  }
+  float* yb = y + ((size_t)crop * L + 1) * width;  // patch rows
+  // cosine similarities, one warp per (outlier, neighbour)
+  const int offs_y[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+  const int offs_x[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+  for (int pr = warp; pr < k * 8; pr += OS_THREADS / 32) {
+    const int i = pr >> 3, j = pr & 7;
+    const int oy = s_idx[i] / grid, ox = s_idx[i] % grid;
+    const int ny = min(max(oy + offs_y[j], 0), grid - 1), nx = min(max(ox + offs_x[j], 0), grid - 1);
+    const float* o = yb + (size_t)s_idx[i] * width;
+    const float* nb = yb + (size_t)(ny * grid + nx) * width;
+    float dot = 0.f, no = 0.f, nn = 0.f;
+    for (int c = lane; c < width; c += 32) {
+      const float a = o[c], b = nb[c];
+      dot = fmaf(a, b, dot);
+      no = fmaf(a, a, no);
+      nn = fmaf(b, b, nn);
+    }
+    dot = warp_sum(dot); no = warp_sum(no); nn = warp_sum(nn);
+    if (lane == 0) {
+      s_sim[i][j] = dot / (fmaxf(sqrtf(no), 1e-12f) * fmaxf(sqrtf(nn), 1e-12f));
+      s_nb[i][j] = ny * grid + nx;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < k; i += OS_THREADS) {   // softmax(clamp(1 - sim, 0)) over the 8 neighbours
+    float w[8], m = -INFINITY, s = 0.f;
+    for (int j = 0; j < 8; ++j) { w[j] = fmaxf(1.0f - s_sim[i][j], 0.f); m = fmaxf(m, w[j]); }
+    for (int j = 0; j < 8; ++j) { w[j] = expf(w[j] - m); s += w[j]; }
+    for (int j = 0; j < 8; ++j) s_w[i][j] = w[j] / s;
+  }
+  __syncthreads();
+  float* sc = scratch + (size_t)crop * top_k * 9 * width;
+  for (int e = tid; e < k * width; e += OS_THREADS) {
+    const int i = e / width, c = e % width;
+    const float o = yb[(size_t)s_idx[i] * width + c];
+    float rep = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      const float nbv = yb[(size_t)s_nb[i][j] * width + c];
+      rep = fmaf(nbv, s_w[i][j], rep);
+      const float strength = fminf(fmaxf(s_sim[i][j] * ctemp, 0.f), 1.f);
+      sc[((size_t)i * 9 + 1 + j) * width + c] = nbv - o * strength;
+    }
+    sc[((size_t)i * 9) * width + c] = rep;
+  }
+  __syncthreads();  // every read of the original map is done
+  for (int c = tid; c < width; c += OS_THREADS) {   // a channel is owned by one thread: writes stay ordered
+    for (int i = 0; i < k; ++i)
+      for (int j = 0; j < 8; ++j)
+        if (s_nb[i][j] != s_idx[i]) yb[(size_t)s_nb[i][j] * width + c] = sc[((size_t)i * 9 + 1 + j) * width + c];
+    for (int i = 0; i < k; ++i) yb[(size_t)s_idx[i] * width + c] = sc[((size_t)i * 9) * width + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// segmentor.py:309-336: CLS L2-normalise (in place in the reference) + similarity-weighted debias
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void cls_debias_kernel(const float* __restrict__ tok, int n_crops, int L, int D, float factor,
+                                  T* __restrict__ feats, int ldf, float* __restrict__ cls_unit) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int P = L - 1;
+  if (gw >= n_crops * L) return;
+  const int crop = gw / L, t = gw % L;
+  const float* cls = tok + (size_t)crop * L * D;
+  float cs = 0.f;
+  for (int c = lane; c < D; c += 32) cs = fmaf(cls[c], cls[c], cs);
+  const float cinv = 1.0f / sqrtf(warp_sum(cs));
+  if (t == 0) {
+    if (cls_unit)
+      for (int c = lane; c < D; c += 32) cls_unit[(size_t)crop * D + c] = cls[c] * cinv;
+    return;
+  }
+  const float* f = tok + ((size_t)crop * L + t) * D;
+  T* o = feats + ((size_t)crop * P + (t - 1)) * ldf;
+  if (factor == 0.f) {
+    for (int c = lane; c < D; c += 32) o[c] = from_f32<T>(f[c]);
+    return;
+  }
+  // cls_unit is re-normalised in the reference (segmentor.py:325); |cls_unit| = 1 up to rounding
+  float fs = 0.f, dot = 0.f, c2 = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float cu = cls[c] * cinv;
+    fs = fmaf(f[c], f[c], fs);
+    dot = fmaf(f[c], cu, dot);
+    c2 = fmaf(cu, cu, c2);
+  }
+  fs = warp_sum(fs); dot = warp_sum(dot); c2 = warp_sum(c2);
+  const float sim = dot / (sqrtf(fs) * sqrtf(c2));
+  const float wf = sim * factor;
+  for (int c = lane; c < D; c += 32) o[c] = from_f32<T>(f[c] - cls[c] * cinv * wf);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cseg_preprocess_u8(const uint8_t* img, int H, int W, const float mean[3], const float std_[3], float* out,
+                       void* stream) {
+  CSEG_REQUIRE(H > 0 && W > 0, "preprocess: empty image");
+  const int HW = H * W;
+  preprocess_u8_kernel<<<cdiv(HW, 256), 256, 0, (cudaStream_t)stream>>>(img, HW, mean[0], mean[1], mean[2], std_[0],
+                                                                        std_[1], std_[2], out);
+  CSEG_LAUNCH_CHECK("preprocess_u8");
+  return 0;
+}
+
+int cseg_patchify(const float* img, int H, int W, const int32_t* windows, int n_crops, int crop_h, int crop_w,
+                  int pad_top, int pad_left, int ps, int out_dtype, void* out, int ldo, void* stream) {
+  CSEG_REQUIRE(n_crops > 0 && ps > 0 && crop_h % ps == 0 && crop_w % ps == 0,
+               "patchify: crop %dx%d must be a multiple of the patch size %d", crop_h, crop_w, ps);
+  CSEG_REQUIRE(ldo >= 3 * ps * ps, "patchify: ldo=%d < %d", ldo, 3 * ps * ps);
+  const int gh = crop_h / ps, gw = crop_w / ps;
+  const long long total = (long long)n_crops * gh * gw * ldo;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
+  if (out_dtype == CSEG_BF16)
+    patchify_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(img, H, W, windows, n_crops, gh, gw, pad_top,
+                                                                    pad_left, ps, (bf16*)out, ldo);
+  else
+    patchify_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(img, H, W, windows, n_crops, gh, gw, pad_top,
+                                                                     pad_left, ps, (float*)out, ldo);
+  CSEG_LAUNCH_CHECK("patchify");
+  return 0;
+}
+
+int cseg_embed_tokens(const float* pe, const float* cls, const float* pos, int n_crops, int L, int width, float* x,
+                      void* stream) {
+  CSEG_REQUIRE(n_crops > 0 && L > 1 && width > 0, "embed_tokens: bad shape");
+  const long long total = (long long)n_crops * L * width;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
+  embed_tokens_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pe, cls, pos, n_crops, L, width, x);
+  CSEG_LAUNCH_CHECK("embed_tokens");
+  return 0;
+}
+
+int cseg_layernorm(const float* x, int rows, int width, const float* gamma, const float* beta, float eps,
+                   int out_dtype, void* out, void* stream) {
+  CSEG_REQUIRE(rows > 0 && width > 0, "layernorm: bad shape");
+  const int blocks = cdiv((long long)rows * 32, 256);
+  if (out_dtype == CSEG_BF16)
+    layernorm_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, width, gamma, beta, eps, (bf16*)out);
+  else
+    layernorm_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, width, gamma, beta, eps, (float*)out);
+  CSEG_LAUNCH_CHECK("layernorm");
+  return 0;
+}
+
+}  // extern "C"
+
+template <typename T, int HD>
+static int launch_attention(const void* qkv, int n_crops, int L, int heads, int mode, const float* simmap,
+                            float simw, void* out, float* stats, cudaStream_t st) {
+  constexpr int LDS = HD + (sizeof(T) == 2 ? 2 : 1);
+  const size_t smem = (((size_t)3 * L * LDS * sizeof(T) + 15) & ~(size_t)15) + (size_t)ATT_WARPS * ATT_JMAX * 32 * 4;
+  CSEG_REQUIRE(smem <= 227 * 1024, "attention: L=%d head_dim=%d needs %zu B shared memory", L, HD, smem);
+  CSEG_CUDA(cudaFuncSetAttribute(attention_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_kernel<T, HD><<<n_crops * heads, ATT_WARPS * 32, smem, st>>>((const T*)qkv, L, heads, mode, simmap, simw,
+                                                                         (T*)out, stats);
+  CSEG_LAUNCH_CHECK("attention");
+  return 0;
+}
+
+extern "C" {
+
+int cseg_attention(int dtype, const void* qkv, int n_crops, int L, int heads, int head_dim, int mode,
+                   const float* simmap, float sim_weight, void* out, float* stats, void* stream) {
+  CSEG_REQUIRE(n_crops > 0 && heads > 0, "attention: bad shape");
+  CSEG_REQUIRE(L >= 2 && L <= ATT_JMAX * 32, "attention: L=%d outside [2, %d]", L, ATT_JMAX * 32);
+  CSEG_REQUIRE(mode >= CSEG_ATTN_STD && mode <= CSEG_ATTN_MASKCLIP, "attention: unknown mode %d", mode);
+  CSEG_REQUIRE(stats == nullptr || mode == CSEG_ATTN_STD, "attention: stats only with CSEG_ATTN_STD");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == CSEG_BF16 && head_dim == 64)
+    return launch_attention<bf16, 64>(qkv, n_crops, L, heads, mode, simmap, sim_weight, out, stats, st);
+  if (dtype == CSEG_F32 && head_dim == 64)
+    return launch_attention<float, 64>(qkv, n_crops, L, heads, mode, simmap, sim_weight, out, stats, st);
+  if (dtype == CSEG_BF16 && head_dim == 80)
+    return launch_attention<bf16, 80>(qkv, n_crops, L, heads, mode, simmap, sim_weight, out, stats, st);
+  if (dtype == CSEG_F32 && head_dim == 80)
+    return launch_attention<float, 80>(qkv, n_crops, L, heads, mode, simmap, sim_weight, out, stats, st);
+  CSEG_FAIL(CSEG_EUNSUPPORTED, "attention: head_dim=%d dtype=%d not supported (64 or 80)", head_dim, dtype);
+}
+
+int cseg_simmap(const float* x, int n_crops, int L, int width, float temperature, int add_self_similarity,
+                float* simmap, void* stream) {
+  CSEG_REQUIRE(n_crops > 0 && L >= 2 && width > 0 && temperature != 0.f, "simmap: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = L - 1;
+  dim3 grid(cdiv(P, 32), cdiv(P, 32), n_crops);
+  simmap_kernel<<<grid, 256, 0, st>>>(x, L, width, 1.0f / temperature, add_self_similarity, simmap);
+  CSEG_LAUNCH_CHECK("simmap");
+  return 0;
+}
+
+int cseg_outlier_suppress(float* y, int n_crops, int L, int width, int grid, const float* stats, int heads,
+                          int top_k, float contamination_temp, float* scratch, int32_t* outlier_idx, void* stream) {
+  CSEG_REQUIRE(n_crops > 0 && grid * grid == L - 1, "outlier_suppress: grid %d^2 != L-1 = %d", grid, L - 1);
+  CSEG_REQUIRE(top_k > 0 && top_k <= OS_MAXK, "outlier_suppress: top_k=%d outside [1, %d]", top_k, OS_MAXK);
+  const size_t smem = (size_t)(L - 1) * sizeof(float);
+  outlier_kernel<<<n_crops, OS_THREADS, smem, (cudaStream_t)stream>>>(y, L, width, grid, stats, heads, top_k,
+                                                                      contamination_temp, scratch, outlier_idx);
+  CSEG_LAUNCH_CHECK("outlier_suppress");
+  return 0;
+}
+
+int cseg_cls_debias(const float* tok, int n_crops, int L, int D, float factor, int out_dtype, void* feats, int ldf,
+                    float* cls_unit, void* stream) {
+  CSEG_REQUIRE(n_crops > 0 && L >= 2 && D > 0 && ldf >= D, "cls_debias: bad shape");
+  const int blocks = cdiv((long long)n_crops * L * 32, 256);
+  if (out_dtype == CSEG_BF16)
+    cls_debias_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(tok, n_crops, L, D, factor, (bf16*)feats, ldf,
+                                                                      cls_unit);
+  else
+    cls_debias_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(tok, n_crops, L, D, factor, (float*)feats, ldf,
+                                                                       cls_unit);
+  CSEG_LAUNCH_CHECK("cls_debias");
+  return 0;
+}
+
+}  // extern "C"

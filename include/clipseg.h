@@ -1,0 +1,170 @@
+/*
+ * clipseg.h -- C ABI of libclipseg.so, the B200 (sm_100a) kernels behind the dense CLIP
+ * segmentation hot path of UserNameUnavailableIsUnavailable/CLIP-Decontamination.
+ *
+ * The reference is pure Python and has no FFI; each entry point below names the reference
+ * function (file:line, relative to the reference root) whose arithmetic it replaces.  The
+ * reference-side binding is a ctypes stub; the package's own binding is
+ * clip_decontamination_b200/_lib.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative CSEG_E* code on failure; the message is
+ *     available through cseg_last_error() (thread-local).  No exception crosses the boundary.
+ *   - all pointers are DEVICE pointers unless the name ends in _host; nothing is allocated
+ *     inside; every launcher takes the CUDA stream (a cudaStream_t passed as void*).
+ *   - dtype arguments are CSEG_F32 / CSEG_BF16; "T" in a comment means that dtype.
+ *   - matrices are row-major; "ld*" are leading dimensions in ELEMENTS.
+ *   - token tensors are crop-major: row = crop * L + token.
+ */
+#ifndef CLIPSEG_H_
+#define CLIPSEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSEG_VERSION 100
+
+#if defined(__GNUC__)
+#define CSEG_API __attribute__((visibility("default")))
+#else
+#define CSEG_API
+#endif
+
+enum { CSEG_F32 = 0, CSEG_BF16 = 1 };
+enum { CSEG_OK = 0, CSEG_EINVAL = -1, CSEG_ECUDA = -2, CSEG_EUNSUPPORTED = -3 };
+/* epilogue activations of cseg_gemm */
+enum { CSEG_ACT_NONE = 0, CSEG_ACT_GELU = 1, CSEG_ACT_QUICKGELU = 2 };
+/* attention modes of cseg_attention: open_clip/transformer.py:858-908 */
+enum {
+  CSEG_ATTN_STD = 0,          /* softmax(q k^T * s) v           nn.MultiheadAttention, :204,218-232 */
+  CSEG_ATTN_EXPERIMENTAL = 1, /* softmax(softmax((kk+qq) s) + M) v                        :896-902 */
+  CSEG_ATTN_SCLIP = 2,        /* softmax(qq s + M) + softmax(kk s + M)                    :870-877 */
+  CSEG_ATTN_CLEARCLIP = 3,    /* softmax(qq s + M)                                        :903-908 */
+  CSEG_ATTN_SFP = 4,          /* softmax(0.5 (qq+kk) s + M)                               :888-895 */
+  CSEG_ATTN_VANILLA = 5,      /* softmax(qk s + M)                                        :858-863 */
+  CSEG_ATTN_SEGEARTH = 6,     /* SCLIP + softmax(vv s + M)                                :878-887 */
+  CSEG_ATTN_MASKCLIP = 7      /* identity attention                                       :864-869 */
+};
+
+CSEG_API int cseg_version(void);
+/* copies the calling thread's last error message into buf (NUL terminated); returns its length */
+CSEG_API int cseg_last_error(char* buf, size_t n);
+/* number of kernel launches issued through this library by the calling process so far */
+CSEG_API long long cseg_launch_count(void);
+
+/* ---- input side (N1): mmseg SegDataPreProcessor arithmetic, segmentor.py:64-67 -------------
+ * uint8 HWC BGR image -> float32 [3,H,W] RGB, (x - mean) / std. */
+CSEG_API int cseg_preprocess_u8(const uint8_t* img_hwc_bgr, int H, int W, const float mean_rgb_host[3],
+                       const float std_rgb_host[3], float* out_chw, void* stream);
+
+/* ---- A2 stem: open_clip/transformer.py:559-576 ------------------------------------------------
+ * windows: int32 [n_crops][4] = {y1, x1, h, w} of forward_slide (segmentor.py:418-424); each window
+ * is placed at (pad_top, pad_left) inside a zero canvas of crop_h x crop_w (compute_padsize,
+ * segmentor.py:427-431,534-546).  out: T [n_crops*gh*gw, ldo], column = c*ps*ps + ky*ps + kx
+ * (the flattened conv1.weight order), columns >= 3*ps*ps are written as zero up to ldo. */
+CSEG_API int cseg_patchify(const float* img_chw, int H, int W, const int32_t* windows, int n_crops,
+                  int crop_h, int crop_w, int pad_top, int pad_left, int ps, int out_dtype,
+                  void* out, int ldo, void* stream);
+/* x[crop*L + t] = (t == 0 ? class_embedding : patch_embed[crop*P + t-1]) + pos[t]   (:565-571) */
+CSEG_API int cseg_embed_tokens(const float* patch_embed, const float* class_embedding, const float* pos,
+                      int n_crops, int L, int width, float* x, void* stream);
+/* LayerNormFp32 (open_clip/transformer.py:17-23): fp32 statistics, output in out_dtype.
+ * `x` and `out` may alias when out_dtype == CSEG_F32. */
+CSEG_API int cseg_layernorm(const float* x, int rows, int width, const float* gamma, const float* beta,
+                   float eps, int out_dtype, void* out, void* stream);
+
+/* ---- GEMM (K1,K3,K4,K9,K12 of SURVEY 2.2): nn.Linear / 1x1 conv -------------------------------
+ * C[M,N] = residual + alpha * act(A[M,K] . B[N,K]^T + bias)      (residual, bias optional)
+ * in_dtype CSEG_BF16 -> TMA-fed tcgen05 kernel (fp32 accumulate in TMEM); A,B bf16, K % 64 == 0,
+ * lda,ldb % 8 == 0, 16-byte aligned bases.  in_dtype CSEG_F32 -> CUDA-core fp32 verification
+ * kernel.  bias fp32 [N]; residual fp32 [M, ldr]; C in out_dtype (may alias residual when fp32). */
+CSEG_API int cseg_gemm(int in_dtype, const void* A, int lda, const void* B, int ldb, int M, int N, int K,
+              const float* bias, const float* residual, int ldr, float alpha, int act,
+              int out_dtype, void* C, int ldc, void* stream);
+/* same contract on the CUDA-core kernel for either operand dtype: the on-device cross-check of the
+ * tensor-core path used by the tests (never called by the product path). */
+CSEG_API int cseg_gemm_reference(int in_dtype, const void* A, int lda, const void* B, int ldb, int M, int N,
+                        int K, const float* bias, const float* residual, int ldr, float alpha,
+                        int act, int out_dtype, void* C, int ldc, void* stream);
+
+/* ---- attention (K3, K5, K7) ---------------------------------------------------------------------
+ * qkv: T [n_crops*L, 3*width] (= F.linear(x, in_proj_weight, in_proj_bias), :841); heads split as
+ * :842-844.  mode selects the weight formula; simmap (fp32 [n_crops, L-1, L-1], may be NULL) is the
+ * SimilarityEnhancementModule map added with weight sim_weight and a zero CLS row/column
+ * (similarity_enhancement.py:78-124).  out: T [n_crops*L, width] (before out_proj).
+ * stats (may be NULL; CSEG_ATTN_STD only): fp32 [n_crops][heads][2][L-1] receiving P[0,1+i] and
+ * P[1+i,1+i] per head -- the only entries of the need_weights=True matrix that
+ * detect_outliers_by_attention consumes (outlier_suppression.py:46-53). */
+CSEG_API int cseg_attention(int dtype, const void* qkv, int n_crops, int L, int heads, int head_dim, int mode,
+                   const float* simmap, float sim_weight, void* out, float* stats, void* stream);
+/* SimilarityEnhancementModule.compute_similarity_map (similarity_enhancement.py:37-66) on the fp32
+ * residual stream x [n_crops*L, width] (CLS row skipped): M [n_crops, L-1, L-1] fp32. */
+CSEG_API int cseg_simmap(const float* x, int n_crops, int L, int width, float temperature,
+                int add_self_similarity, float* simmap, void* stream);
+/* detect_outliers_by_attention + OutlierSuppressionModule.mean_interpolation
+ * (outlier_suppression.py:15-61,115-214) on y [n_crops*L, width] fp32 (CLS row untouched), in place.
+ * grid x grid patches, stats from cseg_attention.  scratch: >= n_crops * top_k * 9 * width floats
+ * + n_crops*top_k ints.  outlier_idx (int32 [n_crops, top_k], may be NULL) receives the top-k order. */
+CSEG_API int cseg_outlier_suppress(float* y, int n_crops, int L, int width, int grid, const float* stats,
+                          int heads, int top_k, float contamination_temp, float* scratch,
+                          int32_t* outlier_idx, void* stream);
+/* forward_feature head (segmentor.py:309-336): tok fp32 [n_crops*L, D] = ln_post(x) @ proj.
+ * cls_unit[crop] = tok[crop*L] / |.|;  feats[crop, p] = f - factor * cos(f, cls) * cls_unit
+ * written as T [n_crops*(L-1), ldf] (channel-last patch grid). */
+CSEG_API int cseg_cls_debias(const float* tok, int n_crops, int L, int D, float factor, int out_dtype,
+                    void* feats, int ldf, float* cls_unit, void* stream);
+
+/* ---- JBU upsampler (K11): simfeatup_dev/upsamplers.py:202-325 ---------------------------------
+ * guidance for one stage: adaptive_avg_pool2d of each crop to (gh, gw) (:316) -> fp32 [n,gh,gw,4]
+ * (RGB + 0 pad). */
+CSEG_API int cseg_jbu_guidance(const float* img_chw, int H, int W, const int32_t* windows, int n_crops,
+                      int crop_h, int crop_w, int pad_top, int pad_left, int gh, int gw,
+                      float* guid, void* stream);
+/* range_proj (:209-214): conv1x1(3->kd) . GELU . conv1x1(kd->kd); proj fp32 [n,gh,gw,kd] */
+CSEG_API int cseg_jbu_range_proj(const float* guid, int n_pix, int key_dim, const float* w0, const float* b0,
+                        const float* w3, const float* b3, float* proj, void* stream);
+/* get_range_kernel x get_spatial_kernel, renormalised (:230-251,258-262).  kern: T [n*gh*gw, ldk]
+ * with columns [0,d*d) = combined kernel, [d*d, d*d+3) = guidance RGB (the fixup_proj input order,
+ * :264), rest zero. */
+CSEG_API int cseg_jbu_range_kernel(const float* proj, const float* guid, int n_crops, int gh, int gw,
+                          int key_dim, int radius, float range_temp, float sigma_spatial,
+                          int out_dtype, void* kern, int ldk, void* stream);
+/* bicubic x2 (align_corners=False, a=-0.75) + reflect pad + adaptive conv (:268-274, semantics of
+ * adaptive_conv_py_simple :14-25).  src T [n, h, w, C] channel-last -> dst T [n, 2h, 2w, C];
+ * kern T [n*2h*2w, ldk] (first d*d columns used); hr_scratch: T [n*2h*2w*C] workspace. */
+CSEG_API int cseg_jbu_apply(int dtype, const void* src, int n_crops, int h, int w, int C, const void* kern,
+                   int ldk, int radius, void* dst, void* hr_scratch, void* stream);
+
+/* ---- A10: L2-normalise + cosine logits, segmentor.py:374-375,378-379 --------------------------
+ * feats T [rows, ldf] (D used) ; text fp32 [Q, D] ; logits fp32 [n_crops, Q, hw] with rows =
+ * n_crops*hw.  cls_logit_bias (fp32 [n_crops, Q], may be NULL) is added (cls_token_lambda term). */
+CSEG_API int cseg_norm_sim(int dtype, const void* feats, int ldf, int n_crops, int hw, int D,
+                  const float* text, int Q, const float* cls_logit_bias, float* logits, void* stream);
+
+/* ---- A11 + A12: forward_slide accumulation + postprocess_result, segmentor.py:413-449,475-499 --
+ * crop_logits fp32 [n_crops, Q, lh, lw]; when (lh,lw) != (crop_h,crop_w) each crop is first
+ * resized bilinearly (align_corners=False) to crop_h x crop_w (segmentor.py:388-391).  The window
+ * of crop i covers rows [y1, y1+h), cols [x1, x1+w) of the H x W canvas and reads the crop at offset
+ * (pad_top, pad_left).  Sums over covering windows, divides by the count, resizes to out_h x out_w
+ * (:448-449), then x logit_scale, softmax over Q, per-class max over synonym queries
+ * (query_idx int32 [Q]), argmax (lowest index wins ties), prob < prob_thd -> bg_idx.
+ * labels uint8 [out_h,out_w]; probs (fp32 [K,out_h,out_w]) and avg_logits (fp32 [Q,H,W]) optional. */
+CSEG_API int cseg_accum_argmax(const float* crop_logits, int n_crops, int Q, int lh, int lw, int crop_h,
+                      int crop_w, int pad_top, int pad_left, const int32_t* windows, int H, int W,
+                      int out_h, int out_w, const int32_t* query_idx, int K, float logit_scale,
+                      float prob_thd, int bg_idx, uint8_t* labels, float* probs, float* avg_logits,
+                      void* stream);
+
+/* ---- K17: mmseg IoUMetric.intersect_and_union (mmsegmentation 1.2.2, external) -----------------
+ * hist int64 [3][K] += {intersect, pred, label} pixel counts; label == ignore_index skipped. */
+CSEG_API int cseg_iou_hist(const uint8_t* pred, const uint8_t* label, long long n, int K, int ignore_index,
+                  long long* hist, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPSEG_H_ */
