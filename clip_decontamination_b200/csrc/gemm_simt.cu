@@ -12,8 +12,8 @@ constexpr int TM = 64, TN = 64, TK = 16;
 template <typename TI>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const TI* __restrict__ A, int lda, const TI* __restrict__ B,
                                                         int ldb, int M, int N, int K, const float* __restrict__ bias,
-                                                        const float* residual, int ldr, float alpha, int act,
-                                                        int out_bf16, void* C, int ldc) {
+                                                        const void* residual, int ldr, int res_bf16, float alpha,
+                                                        int act, int out_bf16, void* C, int ldc) {
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -55,7 +55,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TI* __restrict__ A
       float x = acc[i][j];
       if (bias) x += bias[col];
       x = apply_act(x, act) * alpha;
-      if (residual) x += residual[(size_t)row * ldr + col];
+      if (residual)
+        x += res_bf16 ? __bfloat162float(((const bf16*)residual)[(size_t)row * ldr + col])
+                      : ((const float*)residual)[(size_t)row * ldr + col];
       if (out_bf16) ((bf16*)C)[(size_t)row * ldc + col] = __float2bfloat16_rn(x);
       else ((float*)C)[(size_t)row * ldc + col] = x;
     }
@@ -65,16 +67,16 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TI* __restrict__ A
 }  // namespace
 
 int cseg_gemm_simt(int in_dtype, const void* A, int lda, const void* B, int ldb, int M, int N, int K,
-                   const float* bias, const float* residual, int ldr, float alpha, int act, int out_dtype, void* C,
-                   int ldc, cudaStream_t st) {
+                   const float* bias, const void* residual, int ldr, int res_dtype, float alpha, int act, int out_dtype,
+                   void* C, int ldc, cudaStream_t st) {
   CSEG_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   dim3 grid(cdiv(N, TN), cdiv(M, TM));
   if (in_dtype == CSEG_F32)
     gemm_simt_kernel<float><<<grid, 256, 0, st>>>((const float*)A, lda, (const float*)B, ldb, M, N, K, bias, residual,
-                                                  ldr, alpha, act, out_dtype == CSEG_BF16, C, ldc);
+                                                  ldr, res_dtype == CSEG_BF16, alpha, act, out_dtype == CSEG_BF16, C, ldc);
   else
     gemm_simt_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, bias, residual, ldr,
-                                                 alpha, act, out_dtype == CSEG_BF16, C, ldc);
+                                                 res_dtype == CSEG_BF16, alpha, act, out_dtype == CSEG_BF16, C, ldc);
   CSEG_LAUNCH_CHECK("gemm_simt");
   return 0;
 }

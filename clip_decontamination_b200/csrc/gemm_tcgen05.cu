@@ -91,8 +91,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 struct EpiParams {
   const float* bias;
-  const float* residual;
+  const void* residual;
   int ldr;
+  int res_bf16;
   float alpha;
   int act;
   int out_bf16;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05_kernel(const __grid_con
     const int lg = warp & 3;  // TMEM lane group this warp may read
     const int row = m0 + lg * 32 + lane;
     const bool row_ok = row < ep.M;
-    const bool vec_ok = ((ep.ldc & 7) == 0) && (ep.residual == nullptr || (ep.ldr & 3) == 0);
+    const bool vec_ok = ((ep.ldc & 7) == 0) && (ep.residual == nullptr || (ep.ldr & 7) == 0);
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t r[32];
@@ -211,11 +212,26 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05_kernel(const __grid_con
           for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
         }
         if (ep.residual) {
-          const float* rp = ep.residual + (size_t)row * ep.ldr + col0;
+          if (ep.res_bf16) {
+            const bf16* rp = (const bf16*)ep.residual + (size_t)row * ep.ldr + col0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 q = *(const float4*)(rp + j);
-            v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 u = *(const uint4*)(rp + j);
+              const __nv_bfloat162* h = (const __nv_bfloat162*)&u;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+                v[j + 2 * e] += f.x;
+                v[j + 2 * e + 1] += f.y;
+              }
+            }
+          } else {
+            const float* rp = (const float*)ep.residual + (size_t)row * ep.ldr + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 q = *(const float4*)(rp + j);
+              v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+            }
           }
         }
         if (ep.out_bf16) {
@@ -243,7 +259,9 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05_kernel(const __grid_con
           float x = v[j];
           if (ep.bias) x += ep.bias[col];
           x = apply_act(x, ep.act) * ep.alpha;
-          if (ep.residual) x += ep.residual[(size_t)row * ep.ldr + col];
+          if (ep.residual)
+            x += ep.res_bf16 ? __bfloat162float(((const bf16*)ep.residual)[(size_t)row * ep.ldr + col])
+                             : ((const float*)ep.residual)[(size_t)row * ep.ldr + col];
           if (ep.out_bf16) ((bf16*)ep.C)[(size_t)row * ep.ldc + col] = __float2bfloat16_rn(x);
           else ((float*)ep.C)[(size_t)row * ep.ldc + col] = x;
         }
@@ -306,8 +324,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
 }  // namespace
 
 int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
-                      const float* residual, int ldr, float alpha, int act, int out_dtype, void* C, int ldc,
-                      cudaStream_t st) {
+                      const void* residual, int ldr, int res_dtype, float alpha, int act, int out_dtype, void* C,
+                      int ldc, cudaStream_t st) {
   CSEG_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   CSEG_REQUIRE(K % BK == 0, "gemm(bf16): K=%d must be a multiple of %d (pad the operands)", K, BK);
   CSEG_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm(bf16): lda=%d, ldb=%d must be multiples of 8", lda, ldb);
@@ -318,7 +336,7 @@ int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int
   if (rc) return rc;
   rc = make_map(&tb, B, N, K, ldb, bn);
   if (rc) return rc;
-  EpiParams ep{bias, residual, ldr, alpha, act, out_dtype == CSEG_BF16, C, ldc, M, N};
+  EpiParams ep{bias, residual, ldr, res_dtype == CSEG_BF16, alpha, act, out_dtype == CSEG_BF16, C, ldc, M, N};
   if (bn == 64) return launch<64, 4>(ta, tb, M, N, K, ep, st);
   return launch<128, 3>(ta, tb, M, N, K, ep, st);
 }

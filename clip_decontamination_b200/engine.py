@@ -1,0 +1,400 @@
+"""Host-side driver of the dense CLIP segmentation hot path on one B200.
+
+Three engines, each a sequence of libclipseg kernel launches on the current CUDA stream:
+
+* ``VisualEngine``  -- open_clip ViT dense patch-feature pass (open_clip/transformer.py:538-775)
+* ``JBUEngine``     -- SimFeatUp JBUOne / JBUStack upsampler (simfeatup_dev/upsamplers.py:278-325)
+* ``SegEngine``     -- forward_slide + forward_feature head + postprocess_result
+                       (segmentor.py:286-392,394-451,475-499)
+
+All crops of an image are batched into the M dimension of the GEMMs (the reference runs them one
+at a time).  Activations feeding GEMMs are bf16 (``precision='bf16'``, tcgen05 path) or fp32
+(``precision='fp32'``, CUDA-core verification mode); the residual stream, LayerNorm statistics,
+softmax, similarity map and logits are fp32 in both modes.  PyTorch supplies device memory and
+streams only -- there is no torch compute on the per-image path and no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from ._lib import ATTN, ACT_NONE, ACT_GELU, ACT_QUICKGELU
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+class Workspace:
+    """Grow-only named device buffers (no allocation on the steady-state path)."""
+
+    def __init__(self, device):
+        self.device = device
+        self._bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, shape: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        buf = self._bufs.get(name)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+            self._bufs[name] = buf
+        return buf[:nbytes].view(dtype).view(*shape)
+
+    def nbytes(self) -> int:
+        return sum(b.numel() for b in self._bufs.values())
+
+
+def slide_windows(h_img: int, w_img: int, stride: int, crop: int) -> List[Tuple[int, int, int, int]]:
+    """forward_slide window enumeration, segmentor.py:411-423: (y1, x1, h, w), last window snapped back."""
+    hg = max(h_img - crop + stride - 1, 0) // stride + 1
+    wg = max(w_img - crop + stride - 1, 0) // stride + 1
+    out = []
+    for hi in range(hg):
+        for wi in range(wg):
+            y1, x1 = hi * stride, wi * stride
+            y2, x2 = min(y1 + crop, h_img), min(x1 + crop, w_img)
+            y1, x1 = max(y2 - crop, 0), max(x2 - crop, 0)
+            out.append((y1, x1, y2 - y1, x2 - x1))
+    return out
+
+
+def compute_padsize(H: int, W: int, patch: int):
+    """segmentor.py:534-546 -> (left, right, top, bottom)."""
+    l = r = t = b = 0
+    if W % patch:
+        lr = patch - (W % patch)
+        l = lr // 2
+        r = lr - l
+    if H % patch:
+        tb = patch - (H % patch)
+        t = tb // 2
+        b = tb - t
+    return l, r, t, b
+
+
+class VisualEngine:
+    """ViT image tower.  ``sd``: visual-tower weights keyed relative to ``visual.``
+    (conv1.weight, class_embedding, positional_embedding, ln_pre.*, transformer.resblocks.N.*, ln_post.*,
+    proj), any float dtype; repacked once to kernel layouts."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], *, width: int, layers: int, heads: int, patch_size: int,
+                 image_size: int, embed_dim: int, quick_gelu: bool = False, precision: str = 'bf16',
+                 device='cuda'):
+        assert precision in ('bf16', 'fp32')
+        self.device = torch.device(device)
+        self.cdt = torch.bfloat16 if precision == 'bf16' else torch.float32
+        self.precision = precision
+        self.width, self.layers, self.heads, self.ps = width, layers, heads, patch_size
+        self.head_dim = width // heads
+        self.grid0 = image_size // patch_size
+        self.D = embed_dim
+        self.act = ACT_QUICKGELU if quick_gelu else ACT_GELU
+        f32 = lambda t: t.detach().to(self.device, torch.float32).contiguous()
+        cd = lambda t: t.detach().to(self.device, torch.float32).to(self.cdt).contiguous()
+        kk = 3 * patch_size * patch_size
+        self.Kp = _round_up(kk, 64)
+        wc = torch.zeros(width, self.Kp, dtype=torch.float32, device=self.device)
+        wc[:, :kk] = f32(sd['conv1.weight']).reshape(width, kk)
+        self.w_conv = wc.to(self.cdt).contiguous()
+        self.cls_emb = f32(sd['class_embedding'])
+        self.pos = f32(sd['positional_embedding'])
+        self._pos_cache: Dict[Tuple[int, int], torch.Tensor] = {}
+        self.ln_pre = (f32(sd['ln_pre.weight']), f32(sd['ln_pre.bias']))
+        self.ln_post = (f32(sd['ln_post.weight']), f32(sd['ln_post.bias']))
+        self.projT = cd(sd['proj'].t())                                  # [D, width] = B operand [N, K]
+        self.blocks = []
+        for i in range(layers):
+            p = f'transformer.resblocks.{i}.'
+            self.blocks.append(dict(
+                ln1=(f32(sd[p + 'ln_1.weight']), f32(sd[p + 'ln_1.bias'])),
+                ln2=(f32(sd[p + 'ln_2.weight']), f32(sd[p + 'ln_2.bias'])),
+                w_in=cd(sd[p + 'attn.in_proj_weight']), b_in=f32(sd[p + 'attn.in_proj_bias']),
+                w_out=cd(sd[p + 'attn.out_proj.weight']), b_out=f32(sd[p + 'attn.out_proj.bias']),
+                w_fc=cd(sd[p + 'mlp.c_fc.weight']), b_fc=f32(sd[p + 'mlp.c_fc.bias']),
+                w_pr=cd(sd[p + 'mlp.c_proj.weight']), b_pr=f32(sd[p + 'mlp.c_proj.bias'])))
+        self.mlp = self.blocks[0]['w_fc'].shape[0]
+        self.ws = Workspace(self.device)
+
+    def _pos_for(self, gh: int, gw: int, crop_h: int, crop_w: int) -> torch.Tensor:
+        """positional embedding for a gh x gw grid; interpolate_pos_encoding
+        (open_clip/transformer.py:777-795) when the token count differs from the pretraining grid.
+        One-time parameter transform per grid shape (cached), not on the per-image path."""
+        if gh * gw + 1 == self.pos.shape[0]:
+            return self.pos
+        key = (gh, gw)
+        if key not in self._pos_cache:
+            N = self.pos.shape[0] - 1
+            g = int(math.sqrt(N))
+            w0, h0 = crop_h // self.ps + 0.1, crop_w // self.ps + 0.1
+            pp = F.interpolate(self.pos[1:].reshape(1, g, g, -1).permute(0, 3, 1, 2),
+                               scale_factor=(w0 / math.sqrt(N), h0 / math.sqrt(N)), mode='bicubic')
+            assert int(w0) == pp.shape[-2] and int(h0) == pp.shape[-1]
+            pp = pp.permute(0, 2, 3, 1).reshape(-1, self.width)
+            self._pos_cache[key] = torch.cat([self.pos[:1], pp], 0).contiguous()
+        return self._pos_cache[key]
+
+    def encode(self, img: torch.Tensor, windows: torch.Tensor, crop_h: int, crop_w: int, pad_top: int = 0,
+               pad_left: int = 0, model_type: str = 'Experimental', ignore_residual: bool = True,
+               sim_cfg: Optional[dict] = None, outlier_cfg: Optional[dict] = None,
+               taps: Optional[dict] = None) -> Tuple[torch.Tensor, int]:
+        """img fp32 [3,H,W] (normalised), windows int32 [n,4] (y1,x1,h,w) on the device.
+        Returns (tok fp32 [n*L, D] = ln_post(.) @ proj for CLS + patches, L)."""
+        if model_type not in ATTN or model_type == 'STD':
+            raise NotImplementedError(f'model_type {model_type!r} is not supported by the CUDA path')
+        ws, n, width, cdt = self.ws, windows.shape[0], self.width, self.cdt
+        ps = self.ps
+        gh, gw = crop_h // ps, crop_w // ps
+        P = gh * gw
+        L = P + 1
+        M = n * L
+        f32 = torch.float32
+        patches = ws.get('patches', (n * P, self.Kp), cdt)
+        ops.patchify(img, windows, crop_h, crop_w, pad_top, pad_left, ps, patches)
+        pe = ws.get('pe', (n * P, width), f32)
+        ops.gemm(patches, self.w_conv, pe)
+        x = ws.get('x', (M, width), f32)
+        ops.embed_tokens(pe, self.cls_emb, self._pos_for(gh, gw, crop_h, crop_w), n, L, width, x)
+        ops.layernorm(x, *self.ln_pre, out=x)
+        if taps is not None:
+            taps['ln_pre'] = x.clone()
+        h = ws.get('h', (M, width), cdt)
+        qkv = ws.get('qkv', (M, 3 * width), cdt)
+        att = ws.get('att', (M, width), cdt)
+        g = ws.get('mlp', (M, self.mlp), cdt)
+        use_sim = sim_cfg is not None
+        use_out = outlier_cfg is not None
+        mid_idx = (self.layers - 1) // 2                                   # transformer.py:593
+        simmap = ws.get('simmap', (n, P, P), f32) if use_sim else None
+        stats = ws.get('stats', (n, self.heads, 2, P), f32) if use_out else None
+        have_sim = False
+        for idx in range(self.layers - 1):
+            b = self.blocks[idx]
+            if idx == mid_idx and use_sim:
+                ops.simmap(x, n, L, width, simmap, sim_cfg.get('temperature', 1.0),
+                           sim_cfg.get('add_self_similarity', True))
+                have_sim = True
+            ops.layernorm(x, *b['ln1'], out=h)
+            ops.gemm(h, b['w_in'], qkv, bias=b['b_in'])
+            ops.attention(qkv, n, L, self.heads, self.head_dim, ATTN['STD'], att,
+                          stats=stats if (use_out and idx == self.layers - 2) else None)
+            ops.gemm(att, b['w_out'], x, bias=b['b_out'], residual=x)
+            ops.layernorm(x, *b['ln2'], out=h)
+            ops.gemm(h, b['w_fc'], g, bias=b['b_fc'], act=self.act)
+            ops.gemm(g, b['w_pr'], x, bias=b['b_pr'], residual=x)
+            if taps is not None:
+                taps[f'block{idx}'] = x.clone()
+        if taps is not None and have_sim:
+            taps['simmap'] = simmap.clone()
+        b = self.blocks[-1]
+        ops.layernorm(x, *b['ln1'], out=h)
+        ops.gemm(h, b['w_in'], qkv, bias=b['b_in'])
+        ops.attention(qkv, n, L, self.heads, self.head_dim, ATTN[model_type], att,
+                      simmap=simmap if have_sim else None,
+                      sim_weight=(sim_cfg or {}).get('similarity_weight', 1.0))
+        y = ws.get('y', (M, width), f32)
+        if ignore_residual:                                                # transformer.py:627-628
+            ops.gemm(att, b['w_out'], y, bias=b['b_out'])
+        else:                                                              # transformer.py:641-643
+            ops.gemm(att, b['w_out'], y, bias=b['b_out'], residual=x)
+            ops.layernorm(y, *b['ln2'], out=h)
+            ops.gemm(h, b['w_fc'], g, bias=b['b_fc'], act=self.act)
+            ops.gemm(g, b['w_pr'], y, bias=b['b_pr'], residual=y)
+        if taps is not None:
+            taps['final_attn'] = y.clone()
+            if use_out and self.layers >= 2:
+                taps['stats'] = stats.clone()
+        if use_out and self.layers >= 2:                                   # transformer.py:721-742
+            if gh != gw:
+                raise NotImplementedError('outlier suppression assumes square crops (transformer.py:583)')
+            k = int(outlier_cfg.get('top_k', 10))
+            scratch = ws.get('outlier_scratch', (n * k * 9 * width,), f32)
+            oidx = ws.get('outlier_idx', (n, k), torch.int32)
+            ops.outlier_suppress(y, n, L, width, gh, stats, self.heads, k,
+                                 float(outlier_cfg.get('contamination_temp', 0.1)), scratch, oidx)
+            if taps is not None:
+                taps['outlier_idx'] = oidx.clone()
+                taps['suppressed'] = y.clone()
+        ops.layernorm(y, *self.ln_post, out=h)
+        tok = ws.get('tok', (M, self.D), f32)
+        ops.gemm(h, self.projT, tok)
+        return tok, L
+
+
+class JBUEngine:
+    """JBUOne ('up.*', radius 5, one module reused 4x) / JBUStack ('up1..4.*', radius 3)."""
+
+    def __init__(self, name: str, sd: Dict[str, torch.Tensor], feat_dim: int, precision: str = 'bf16',
+                 device='cuda'):
+        if name == 'jbu_one':
+            mods = [('up.', 5)] * 4
+        elif name == 'jbu_stack':
+            mods = [(f'up{i}.', 3) for i in range(1, 5)]
+        else:
+            raise ValueError(f"Unknown upsampler {name}")
+        self.name, self.C = name, feat_dim
+        self.device = torch.device(device)
+        self.cdt = torch.bfloat16 if precision == 'bf16' else torch.float32
+        f32 = lambda t: t.detach().to(self.device, torch.float32).contiguous()
+        self.stages = []
+        cache = {}
+        for pre, r in mods:
+            if pre not in cache:
+                d2 = (2 * r + 1) ** 2
+                ldk = _round_up(d2 + 3, 64)
+                w0 = torch.zeros(ldk, ldk, device=self.device)
+                w0[:d2, :d2 + 3] = f32(sd[pre + 'fixup_proj.0.weight']).reshape(d2, d2 + 3)
+                b0 = torch.zeros(ldk, device=self.device)
+                b0[:d2] = f32(sd[pre + 'fixup_proj.0.bias'])
+                w3 = torch.zeros(ldk, ldk, device=self.device)
+                w3[:d2, :d2] = f32(sd[pre + 'fixup_proj.3.weight']).reshape(d2, d2)
+                b3 = torch.zeros(ldk, device=self.device)
+                b3[:d2] = f32(sd[pre + 'fixup_proj.3.bias'])
+                cache[pre] = dict(
+                    radius=r, ldk=ldk,
+                    range_temp=float(sd[pre + 'range_temp']), sigma=float(sd[pre + 'sigma_spatial']),
+                    rp_w0=f32(sd[pre + 'range_proj.0.weight']).reshape(32, 3).contiguous(),
+                    rp_b0=f32(sd[pre + 'range_proj.0.bias']),
+                    rp_w3=f32(sd[pre + 'range_proj.3.weight']).reshape(32, 32).contiguous(),
+                    rp_b3=f32(sd[pre + 'range_proj.3.bias']),
+                    fx_w0=w0.to(self.cdt).contiguous(), fx_b0=b0, fx_w3=w3.to(self.cdt).contiguous(), fx_b3=b3)
+            self.stages.append(cache[pre])
+        self.w_fin = f32(sd['fixup_proj.1.weight']).reshape(feat_dim, feat_dim).to(self.cdt).contiguous()
+        self.b_fin = f32(sd['fixup_proj.1.bias'])
+        self.ws = Workspace(self.device)
+
+    def upsample(self, feats: torch.Tensor, gh: int, gw: int, img: torch.Tensor, windows: torch.Tensor,
+                 crop_h: int, crop_w: int, pad_top: int = 0, pad_left: int = 0,
+                 taps: Optional[dict] = None) -> torch.Tensor:
+        """feats T [n*gh*gw, C] channel-last; returns T [n*(16gh)*(16gw), C] after the final fix-up
+        (upsamplers.py:320-325)."""
+        ws, n, C, cdt = self.ws, windows.shape[0], self.C, self.cdt
+        f32 = torch.float32
+        s, h, w = feats, gh, gw
+        for si, st in enumerate(self.stages):
+            GH, GW = 2 * h, 2 * w
+            npix = n * GH * GW
+            guid = ws.get('guid', (npix, 4), f32)
+            ops.jbu_guidance(img, windows, crop_h, crop_w, pad_top, pad_left, GH, GW, guid)
+            proj = ws.get('proj', (npix, 32), f32)
+            ops.jbu_range_proj(guid, npix, st['rp_w0'], st['rp_b0'], st['rp_w3'], st['rp_b3'], proj)
+            kern = ws.get('kern', (npix, st['ldk']), cdt)
+            ops.jbu_range_kernel(proj, guid, n, GH, GW, st['radius'], st['range_temp'], st['sigma'], kern)
+            hid = ws.get('hid', (npix, st['ldk']), cdt)
+            ops.gemm(kern, st['fx_w0'], hid, bias=st['fx_b0'], act=ACT_GELU)          # fixup_proj.0 + GELU
+            ops.gemm(hid, st['fx_w3'], kern, bias=st['fx_b3'], residual=kern, alpha=0.1)  # kernel += .1 * fixup
+            if taps is not None:
+                taps.setdefault('jbu_kernels', []).append(kern.clone())
+            hr = ws.get('hr', (npix, C), cdt)
+            dst = ws.get(f'up{si % 2}', (npix, C), cdt)
+            ops.jbu_apply(s, n, h, w, C, kern, st['radius'], dst, hr)
+            if taps is not None:
+                taps.setdefault('jbu_stages', []).append(dst.clone())
+            s, h, w = dst, GH, GW
+        out = ws.get('fin', (n * h * w, C), cdt)
+        ops.gemm(s, self.w_fin, out, bias=self.b_fin, residual=s, alpha=0.1)
+        return out
+
+
+class SegEngine:
+    """forward_slide + forward_feature head + postprocess_result for one image at a time."""
+
+    def __init__(self, visual: VisualEngine, query_features: torch.Tensor, query_idx: Sequence[int], *,
+                 model_type: str = 'Experimental', ignore_residual: bool = True, prob_thd: float = 0.0,
+                 logit_scale: float = 50.0, slide_stride: int = 112, slide_crop: int = 224,
+                 cls_token_lambda: float = 0.0, global_debias_factor: float = 0.0, bg_idx: int = 0,
+                 upsampler: Optional[JBUEngine] = None, sim_cfg: Optional[dict] = None,
+                 outlier_cfg: Optional[dict] = None, jbu_chunk: int = 16):
+        self.v = visual
+        self.device = visual.device
+        self.text = query_features.detach().to(self.device, torch.float32).contiguous()
+        self.query_idx_list = [int(i) for i in query_idx]
+        self.query_idx = torch.tensor(self.query_idx_list, dtype=torch.int32, device=self.device)
+        self.Q = len(self.query_idx_list)
+        self.K = max(self.query_idx_list) + 1
+        self.model_type, self.ignore_residual = model_type, ignore_residual
+        self.prob_thd, self.logit_scale = float(prob_thd), float(logit_scale)
+        self.stride, self.crop = slide_stride, slide_crop
+        self.cls_token_lambda, self.debias, self.bg_idx = float(cls_token_lambda), float(global_debias_factor), int(bg_idx)
+        self.up = upsampler
+        self.sim_cfg, self.outlier_cfg = sim_cfg, outlier_cfg
+        self.jbu_chunk = jbu_chunk
+        self.ws = Workspace(self.device)
+        self._win_cache: Dict[Tuple[int, int], Tuple[torch.Tensor, list]] = {}
+
+    def _windows(self, H: int, W: int):
+        key = (H, W)
+        if key not in self._win_cache:
+            if self.crop > 0:
+                wl = slide_windows(H, W, self.stride, self.crop)
+            else:                                                   # whole-image path, segmentor.py:470-471
+                wl = [(0, 0, H, W)]
+            self._win_cache[key] = (torch.tensor(wl, dtype=torch.int32, device=self.device), wl)
+        return self._win_cache[key]
+
+    def crop_logits(self, img: torch.Tensor, taps: Optional[dict] = None):
+        """Per-crop cosine logits (forward_feature, segmentor.py:286-392) for every window of `img`
+        (fp32 [3,H,W] normalised, on the device).  Returns (logits fp32 [n,Q,lh,lw], geometry)."""
+        _, H, W = img.shape
+        win_dev, wl = self._windows(H, W)
+        n = len(wl)
+        wh, ww = wl[0][2], wl[0][3]
+        ps = self.v.ps
+        if self.crop > 0:
+            pl, pr, pt, pb = compute_padsize(wh, ww, ps)
+        else:
+            pl = pr = pt = pb = 0
+            wh, ww = (wh // ps) * ps, (ww // ps) * ps                # conv stride drops the remainder
+        crop_h, crop_w = wh + pt + pb, ww + pl + pr
+        gh, gw = crop_h // ps, crop_w // ps
+        P = gh * gw
+        tok, L = self.v.encode(img, win_dev, crop_h, crop_w, pt, pl, self.model_type, self.ignore_residual,
+                               self.sim_cfg, self.outlier_cfg, taps)
+        D, cdt, ws = self.v.D, self.v.cdt, self.ws
+        feats = ws.get('feats', (n * P, D), cdt)
+        cls_unit = ws.get('cls_unit', (n, D), torch.float32)
+        ops.cls_debias(tok, n, L, D, self.debias, feats, cls_unit)
+        if taps is not None:
+            taps['tok'] = tok.clone()
+            taps['patch_feats'] = feats.clone()
+        cls_bias = None
+        if self.cls_token_lambda != 0:                              # segmentor.py:311,378-379
+            cls_bias = ws.get('cls_bias', (n, self.Q), torch.float32)
+            ops.gemm(cls_unit, self.text, cls_bias, alpha=self.cls_token_lambda)
+        if self.up is not None:
+            if ps != 16:
+                raise ValueError('JBU upsamples x16 and only matches patch size 16 (segmentor.py:372)')
+            logits = ws.get('logits', (n, self.Q, crop_h, crop_w), torch.float32)
+            for c0 in range(0, n, self.jbu_chunk):
+                c1 = min(n, c0 + self.jbu_chunk)
+                y = self.up.upsample(feats[c0 * P:c1 * P], gh, gw, img, win_dev[c0:c1], crop_h, crop_w, pt, pl,
+                                     taps if c0 == 0 else None)
+                ops.norm_sim(y, D, c1 - c0, crop_h * crop_w, D, self.text, logits[c0:c1],
+                             cls_bias[c0:c1] if cls_bias is not None else None)
+        else:
+            logits = ws.get('logits', (n, self.Q, gh, gw), torch.float32)
+            ops.norm_sim(feats, D, n, P, D, self.text, logits, cls_bias)
+        geom = dict(windows=win_dev, crop_h=crop_h, crop_w=crop_w, pad_top=pt, pad_left=pl, H=H, W=W, n=n)
+        return logits, geom
+
+    def segment(self, img: torch.Tensor, ori_shape: Optional[Tuple[int, int]] = None, *, labels=None,
+                want_probs: bool = False, want_logits: bool = False, taps: Optional[dict] = None):
+        """predict() for one image: labels uint8 [out_h,out_w] (+ probs [K,..] / averaged logits [Q,H,W])."""
+        logits, g = self.crop_logits(img, taps)
+        H, W = g['H'], g['W']
+        out_h, out_w = (H, W) if ori_shape is None else (int(ori_shape[0]), int(ori_shape[1]))
+        if labels is None:
+            labels = torch.empty((out_h, out_w), dtype=torch.uint8, device=self.device)
+        probs = torch.empty((self.K, out_h, out_w), dtype=torch.float32, device=self.device) if want_probs else None
+        avg = torch.empty((self.Q, H, W), dtype=torch.float32, device=self.device) \
+            if (want_logits and (out_h, out_w) == (H, W)) else None
+        ops.accum_argmax(logits, g['windows'], g['crop_h'], g['crop_w'], g['pad_top'], g['pad_left'], H, W,
+                         out_h, out_w, self.query_idx, self.K, self.logit_scale, self.prob_thd, self.bg_idx,
+                         labels, probs, avg)
+        return labels, probs, avg

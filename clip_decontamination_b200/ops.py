@@ -1,0 +1,161 @@
+"""Thin torch-tensor wrappers over the C ABI (pointers + sizes; no torch types cross the boundary).
+
+PyTorch is used here for device memory and streams only.  Every wrapper validates device /
+dtype / contiguity, then forwards ``tensor.data_ptr()`` and the current CUDA stream.
+"""
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, F32, BF16
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.ClipSegError('libclipseg needs CUDA tensors (there is no CPU path)')
+    if not t.is_contiguous():
+        raise _lib.ClipSegError('libclipseg needs contiguous tensors')
+    return C.c_void_p(t.data_ptr())
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise _lib.ClipSegError(f'unsupported dtype {t.dtype} (float32 / bfloat16)')
+
+
+def preprocess_u8(img_hwc_bgr: torch.Tensor, mean, std, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    H, W, _ = img_hwc_bgr.shape
+    assert img_hwc_bgr.dtype == torch.uint8
+    if out is None:
+        out = torch.empty((3, H, W), dtype=torch.float32, device=img_hwc_bgr.device)
+    check(lib.cseg_preprocess_u8(_ptr(img_hwc_bgr), H, W, (C.c_float * 3)(*mean), (C.c_float * 3)(*std),
+                                 _ptr(out), _stream()))
+    return out
+
+
+def patchify(img: torch.Tensor, windows: torch.Tensor, crop_h: int, crop_w: int, pad_top: int, pad_left: int,
+             ps: int, out: torch.Tensor):
+    _, H, W = img.shape
+    assert img.dtype == torch.float32 and windows.dtype == torch.int32
+    check(lib.cseg_patchify(_ptr(img), H, W, _ptr(windows), windows.shape[0], crop_h, crop_w, pad_top, pad_left,
+                            ps, _dt(out), _ptr(out), out.shape[1], _stream()))
+    return out
+
+
+def embed_tokens(pe, cls_emb, pos, n_crops, L, width, x):
+    check(lib.cseg_embed_tokens(_ptr(pe), _ptr(cls_emb), _ptr(pos), n_crops, L, width, _ptr(x), _stream()))
+    return x
+
+
+def layernorm(x: torch.Tensor, gamma, beta, out: torch.Tensor, eps: float = 1e-5):
+    assert x.dtype == torch.float32
+    rows, width = x.shape
+    check(lib.cseg_layernorm(_ptr(x), rows, width, _ptr(gamma), _ptr(beta), eps, _dt(out), _ptr(out), _stream()))
+    return out
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, bias=None, residual=None, alpha: float = 1.0,
+         act: int = 0, M: Optional[int] = None, N: Optional[int] = None, K: Optional[int] = None,
+         reference: bool = False):
+    """out[M,N] = residual + alpha * act(A[M,K] @ B[N,K]^T + bias).  2-D row-major views; strides taken
+    from the tensors, so column-padded buffers work."""
+    assert A.dim() == 2 and B.dim() == 2 and out.dim() == 2 and A.dtype == B.dtype
+    assert A.stride(1) == 1 and B.stride(1) == 1 and out.stride(1) == 1
+    M = A.shape[0] if M is None else M
+    N = B.shape[0] if N is None else N
+    K = A.shape[1] if K is None else K
+    fn = lib.cseg_gemm_reference if reference else lib.cseg_gemm
+    ldr = residual.stride(0) if residual is not None else 0
+    rdt = _dt(residual) if residual is not None else F32
+    if residual is not None:
+        assert residual.stride(1) == 1
+    if bias is not None:
+        assert bias.dtype == torch.float32
+    check(fn(_dt(A), C.c_void_p(A.data_ptr()), A.stride(0), C.c_void_p(B.data_ptr()), B.stride(0), M, N, K,
+             _ptr(bias), C.c_void_p(residual.data_ptr()) if residual is not None else None, ldr, rdt, alpha, act,
+             _dt(out), C.c_void_p(out.data_ptr()), out.stride(0), _stream()))
+    return out
+
+
+def attention(qkv: torch.Tensor, n_crops: int, L: int, heads: int, head_dim: int, mode: int, out: torch.Tensor,
+              simmap=None, sim_weight: float = 1.0, stats=None):
+    check(lib.cseg_attention(_dt(qkv), _ptr(qkv), n_crops, L, heads, head_dim, mode, _ptr(simmap), sim_weight,
+                             _ptr(out), _ptr(stats), _stream()))
+    return out
+
+
+def simmap(x: torch.Tensor, n_crops: int, L: int, width: int, out: torch.Tensor, temperature: float = 1.0,
+           add_self_similarity: bool = True):
+    assert x.dtype == torch.float32 and out.dtype == torch.float32
+    check(lib.cseg_simmap(_ptr(x), n_crops, L, width, temperature, int(add_self_similarity), _ptr(out), _stream()))
+    return out
+
+
+def outlier_suppress(y, n_crops, L, width, grid, stats, heads, top_k, contamination_temp, scratch, outlier_idx=None):
+    check(lib.cseg_outlier_suppress(_ptr(y), n_crops, L, width, grid, _ptr(stats), heads, top_k, contamination_temp,
+                                    _ptr(scratch), _ptr(outlier_idx), _stream()))
+    return y
+
+
+def cls_debias(tok, n_crops, L, D, factor, feats, cls_unit=None):
+    check(lib.cseg_cls_debias(_ptr(tok), n_crops, L, D, factor, _dt(feats), _ptr(feats), feats.shape[-1],
+                              _ptr(cls_unit), _stream()))
+    return feats
+
+
+def jbu_guidance(img, windows, crop_h, crop_w, pad_top, pad_left, gh, gw, out):
+    _, H, W = img.shape
+    check(lib.cseg_jbu_guidance(_ptr(img), H, W, _ptr(windows), windows.shape[0], crop_h, crop_w, pad_top, pad_left,
+                                gh, gw, _ptr(out), _stream()))
+    return out
+
+
+def jbu_range_proj(guid, n_pix, w0, b0, w3, b3, proj):
+    check(lib.cseg_jbu_range_proj(_ptr(guid), n_pix, 32, _ptr(w0), _ptr(b0), _ptr(w3), _ptr(b3), _ptr(proj), _stream()))
+    return proj
+
+
+def jbu_range_kernel(proj, guid, n_crops, gh, gw, radius, range_temp, sigma_spatial, kern):
+    check(lib.cseg_jbu_range_kernel(_ptr(proj), _ptr(guid), n_crops, gh, gw, 32, radius, range_temp, sigma_spatial,
+                                    _dt(kern), _ptr(kern), kern.shape[-1], _stream()))
+    return kern
+
+
+def jbu_apply(src, n_crops, h, w, Cc, kern, radius, dst, hr_scratch):
+    check(lib.cseg_jbu_apply(_dt(src), _ptr(src), n_crops, h, w, Cc, _ptr(kern), kern.shape[-1], radius, _ptr(dst),
+                             _ptr(hr_scratch), _stream()))
+    return dst
+
+
+def norm_sim(feats, ldf, n_crops, hw, D, text, logits, cls_logit_bias=None):
+    check(lib.cseg_norm_sim(_dt(feats), _ptr(feats), ldf, n_crops, hw, D, _ptr(text), text.shape[0],
+                            _ptr(cls_logit_bias), _ptr(logits), _stream()))
+    return logits
+
+
+def accum_argmax(crop_logits, windows, crop_h, crop_w, pad_top, pad_left, H, W, out_h, out_w, query_idx, K,
+                 logit_scale, prob_thd, bg_idx, labels, probs=None, avg_logits=None):
+    n, Q, lh, lw = crop_logits.shape
+    assert crop_logits.dtype == torch.float32 and labels.dtype == torch.uint8
+    check(lib.cseg_accum_argmax(_ptr(crop_logits), n, Q, lh, lw, crop_h, crop_w, pad_top, pad_left, _ptr(windows),
+                                H, W, out_h, out_w, _ptr(query_idx), K, logit_scale, prob_thd, bg_idx,
+                                _ptr(labels), _ptr(probs), _ptr(avg_logits), _stream()))
+    return labels
+
+
+def iou_hist(pred, label, K, hist, ignore_index=255):
+    assert pred.dtype == torch.uint8 and label.dtype == torch.uint8 and hist.dtype == torch.int64
+    check(lib.cseg_iou_hist(_ptr(pred), _ptr(label), pred.numel(), K, ignore_index, _ptr(hist), _stream()))
+    return hist

@@ -81,15 +81,16 @@ CSEG_API int cseg_layernorm(const float* x, int rows, int width, const float* ga
  * C[M,N] = residual + alpha * act(A[M,K] . B[N,K]^T + bias)      (residual, bias optional)
  * in_dtype CSEG_BF16 -> TMA-fed tcgen05 kernel (fp32 accumulate in TMEM); A,B bf16, K % 64 == 0,
  * lda,ldb % 8 == 0, 16-byte aligned bases.  in_dtype CSEG_F32 -> CUDA-core fp32 verification
- * kernel.  bias fp32 [N]; residual fp32 [M, ldr]; C in out_dtype (may alias residual when fp32). */
+ * kernel.  bias fp32 [N]; residual [M, ldr] in res_dtype; C in out_dtype (may alias residual when both
+ * have the same dtype). */
 CSEG_API int cseg_gemm(int in_dtype, const void* A, int lda, const void* B, int ldb, int M, int N, int K,
-              const float* bias, const float* residual, int ldr, float alpha, int act,
+              const float* bias, const void* residual, int ldr, int res_dtype, float alpha, int act,
               int out_dtype, void* C, int ldc, void* stream);
 /* same contract on the CUDA-core kernel for either operand dtype: the on-device cross-check of the
  * tensor-core path used by the tests (never called by the product path). */
 CSEG_API int cseg_gemm_reference(int in_dtype, const void* A, int lda, const void* B, int ldb, int M, int N,
-                        int K, const float* bias, const float* residual, int ldr, float alpha,
-                        int act, int out_dtype, void* C, int ldc, void* stream);
+                        int K, const float* bias, const void* residual, int ldr, int res_dtype,
+                        float alpha, int act, int out_dtype, void* C, int ldc, void* stream);
 
 /* ---- attention (K3, K5, K7) ---------------------------------------------------------------------
  * qkv: T [n_crops*L, 3*width] (= F.linear(x, in_proj_weight, in_proj_bias), :841); heads split as

@@ -1,0 +1,350 @@
+"""Per-kernel parity of libclipseg (called through the C ABI via clip_decontamination_b200.ops) against
+the CPU oracle / plain torch fp32 on the same seeded inputs.  Integer outputs must be bit-exact;
+floating-point tolerances are stated per test."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import clipseg_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from clip_decontamination_b200 import ops as _ops
+    return _ops
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def cuda(t, dtype=None):
+    t = t.cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+# ------------------------------------------------------------------ GEMM --------------------------
+GEMM_SHAPES = [(128, 128, 64), (128, 64, 128), (256, 128, 192), (300, 200, 192), (77, 121, 128), (1000, 48, 64),
+               (3152, 2304, 768), (3152, 768, 3072), (3136, 768, 768), (3152, 512, 768), (9000, 128, 128)]
+
+
+@pytest.mark.parametrize('M,N,K', GEMM_SHAPES)
+def test_gemm_bf16_tcgen05_plain(ops, M, N, K):
+    """bf16 x bf16 -> fp32 accumulate; tolerance 2e-3 * sqrt(K/64) abs on O(1) products (fp32 accumulation
+    order differs from torch), compared with an fp32 matmul of the same bf16-rounded operands."""
+    A = (torch.randn(M, K, generator=_g(1)) * 0.5).bfloat16()
+    B = (torch.randn(N, K, generator=_g(2)) * 0.5).bfloat16()
+    ref = A.float() @ B.float().t()
+    out = torch.full((M, N), float('nan'), device='cuda')
+    ops.gemm(A.cuda(), B.cuda(), out)
+    torch.cuda.synchronize()
+    err = (out.cpu() - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, (K / 64) ** 0.5), err
+
+
+@pytest.mark.parametrize('act', [0, 1, 2])
+@pytest.mark.parametrize('out_dtype', [torch.float32, torch.bfloat16])
+def test_gemm_bf16_epilogue(ops, act, out_dtype):
+    M, N, K = 333, 200, 256
+    A = (torch.randn(M, K, generator=_g(1)) * 0.3).bfloat16()
+    B = (torch.randn(N, K, generator=_g(2)) * 0.3).bfloat16()
+    bias = torch.randn(N, generator=_g(3))
+    res = torch.randn(M, N, generator=_g(4))
+    z = A.float() @ B.float().t() + bias
+    z = F.gelu(z) if act == 1 else (z * torch.sigmoid(1.702 * z) if act == 2 else z)
+    ref = res + 0.1 * z
+    out = torch.zeros((M, N), device='cuda', dtype=out_dtype)
+    ops.gemm(A.cuda(), B.cuda(), out, bias=bias.cuda(), residual=res.cuda(), alpha=0.1, act=act)
+    tol = 2e-3 if out_dtype == torch.float32 else 3e-2
+    assert (out.float().cpu() - ref).abs().max().item() < tol
+    # bf16 residual, in place (the JBU kernel fix-up and the final 1x1 conv use this form)
+    r16 = res.bfloat16().cuda()
+    ref2 = r16.float().cpu() + 0.1 * z
+    ops.gemm(A.cuda(), B.cuda(), r16, bias=bias.cuda(), residual=r16, alpha=0.1, act=act)
+    assert (r16.float().cpu() - ref2).abs().max().item() < 3e-2
+
+
+def test_gemm_bf16_matches_cuda_core_reference(ops):
+    M, N, K = 1500, 384, 512
+    A = (torch.randn(M, K, generator=_g(5))).bfloat16().cuda()
+    B = (torch.randn(N, K, generator=_g(6))).bfloat16().cuda()
+    o1 = torch.empty((M, N), device='cuda')
+    o2 = torch.empty((M, N), device='cuda')
+    ops.gemm(A, B, o1)
+    ops.gemm(A, B, o2, reference=True)
+    assert (o1 - o2).abs().max().item() < 5e-3
+
+
+def test_gemm_strided_views(ops):
+    """operands / outputs that are column-padded views (lda != K, ldc != N)."""
+    M, N, K = 200, 121, 128
+    Abuf = torch.zeros(M, 192).bfloat16()
+    Abuf[:, :K] = (torch.randn(M, K, generator=_g(7)) * 0.5).bfloat16()
+    B = (torch.randn(N, K, generator=_g(8)) * 0.5).bfloat16()
+    Cbuf = torch.zeros(M, 128, device='cuda')
+    Ad = Abuf.cuda()
+    ops.gemm(Ad[:, :K], B.cuda(), Cbuf[:, :N], M=M, N=N, K=K)
+    ref = Abuf[:, :K].float() @ B.float().t()
+    assert (Cbuf[:, :N].cpu() - ref).abs().max().item() < 3e-3
+    assert Cbuf[:, N:].abs().max().item() == 0
+
+
+def test_gemm_fp32_mode(ops):
+    """fp32 verification GEMM: 1e-5 relative to the fp32 torch matmul."""
+    M, N, K = 257, 130, 300
+    A = torch.randn(M, K, generator=_g(1))
+    B = torch.randn(N, K, generator=_g(2))
+    bias = torch.randn(N, generator=_g(3))
+    out = torch.empty((M, N), device='cuda')
+    ops.gemm(A.cuda(), B.cuda(), out, bias=bias.cuda(), act=1)
+    ref = F.gelu(A @ B.t() + bias)
+    assert (out.cpu() - ref).abs().max().item() < 1e-4
+
+
+def test_gemm_rejects_bad_k(ops):
+    from clip_decontamination_b200._lib import ClipSegError
+    A = torch.zeros(128, 72, dtype=torch.bfloat16, device='cuda')
+    B = torch.zeros(64, 72, dtype=torch.bfloat16, device='cuda')
+    with pytest.raises(ClipSegError):
+        ops.gemm(A, B, torch.empty(128, 64, device='cuda'))
+
+
+# ------------------------------------------------------------------ stem / LN ---------------------
+def test_preprocess_u8(ops):
+    from clip_decontamination_b200 import synth
+    img = synth.voronoi_scene(100, 130, 3)
+    ref = synth.preprocess(img)
+    out = ops.preprocess_u8(torch.from_numpy(img).cuda(), synth.MEAN.tolist(), synth.STD.tolist())
+    assert np.abs(out.cpu().numpy() - ref).max() < 1e-6
+
+
+@pytest.mark.parametrize('ps,ch,cw,pt,pl', [(16, 224, 224, 0, 0), (14, 224, 224, 0, 0), (16, 208, 160, 4, 3)])
+def test_patchify_matches_conv(ops, ps, ch, cw, pt, pl):
+    """patches @ W^T == conv2d(stride=ps) of the zero-padded crops (open_clip/transformer.py:560)."""
+    H, W = 300, 280
+    img = torch.randn(3, H, W, generator=_g(1))
+    wh, ww = ch - 2 * pt - (1 if pt else 0), cw - 2 * pl
+    wins = [(0, 0, wh, ww), (H - wh, W - ww, wh, ww), (17, 31, wh, ww)]
+    width = 32
+    Wc = torch.randn(width, 3, ps, ps, generator=_g(2))
+    crops = []
+    for (y, x, h, w) in wins:
+        c = torch.zeros(3, ch, cw)
+        c[:, pt:pt + h, pl:pl + w] = img[:, y:y + h, x:x + w]
+        crops.append(c)
+    ref = F.conv2d(torch.stack(crops), Wc, stride=ps)
+    ref = ref.reshape(3, width, -1).permute(0, 2, 1).reshape(-1, width)
+    Kp = (3 * ps * ps + 63) // 64 * 64
+    out = torch.empty((3 * (ch // ps) * (cw // ps), Kp), device='cuda')
+    ops.patchify(img.cuda(), torch.tensor(wins, dtype=torch.int32).cuda(), ch, cw, pt, pl, ps, out)
+    got = out.cpu()[:, :3 * ps * ps] @ Wc.reshape(width, -1).t()
+    assert (got - ref).abs().max().item() < 1e-3
+    assert out[:, 3 * ps * ps:].abs().max().item() == 0
+
+
+def test_layernorm_and_embed(ops):
+    n, L, w = 3, 50, 96
+    pe = torch.randn(n * (L - 1), w, generator=_g(1))
+    cls, pos = torch.randn(w, generator=_g(2)), torch.randn(L, w, generator=_g(3))
+    x = torch.empty((n * L, w), device='cuda')
+    ops.embed_tokens(pe.cuda(), cls.cuda(), pos.cuda(), n, L, w, x)
+    ref = torch.cat([cls.expand(n, 1, w), pe.view(n, L - 1, w)], 1) + pos
+    assert (x.cpu().view(n, L, w) - ref).abs().max().item() == 0
+    gam, bet = torch.randn(w, generator=_g(4)), torch.randn(w, generator=_g(5))
+    refln = F.layer_norm(ref, (w,), gam, bet, 1e-5).view(-1, w)
+    o16 = torch.empty((n * L, w), device='cuda', dtype=torch.bfloat16)
+    ops.layernorm(x, gam.cuda(), bet.cuda(), o16)
+    assert (o16.float().cpu() - refln).abs().max().item() < 3e-2
+    ops.layernorm(x, gam.cuda(), bet.cuda(), x)          # in place, fp32: 1e-5
+    assert (x.cpu() - refln).abs().max().item() < 1e-5
+
+
+# ------------------------------------------------------------------ attention ---------------------
+def _attn_ref(qkv, n, L, heads, mode, sim, w):
+    d = qkv.shape[1] // 3
+    hd = d // heads
+    q, k, v = [O._split_heads(t.reshape(n, L, d), heads) for t in qkv.chunk(3, dim=-1)]
+    scale = hd ** -0.5
+    add = O._pad_simmap(sim, heads, w, q.dtype) if sim is not None else 0
+    T = lambda a: a.transpose(-1, -2)
+    if mode == 'STD':
+        wgt = (q @ T(k) * scale).softmax(-1)
+    elif mode == 'vanilla':
+        wgt = (q @ T(k) * scale + add).softmax(-1)
+    elif mode == 'ClearCLIP':
+        wgt = (q @ T(q) * scale + add).softmax(-1)
+    elif mode == 'SFP':
+        wgt = (0.5 * (q @ T(q) + k @ T(k)) * scale + add).softmax(-1)
+    elif mode == 'Experimental':
+        wgt = ((k @ T(k) + q @ T(q)) * scale).softmax(-1)
+        wgt = (wgt + add).softmax(-1)
+    elif mode == 'SCLIP':
+        wgt = (q @ T(q) * scale + add).softmax(-1) + (k @ T(k) * scale + add).softmax(-1)
+    elif mode == 'SegEarth':
+        wgt = (q @ T(q) * scale + add).softmax(-1) + (k @ T(k) * scale + add).softmax(-1) + \
+              (v @ T(v) * scale + add).softmax(-1)
+    elif mode == 'MaskCLIP':
+        wgt = torch.eye(L).expand(n, heads, L, L)
+    return (wgt @ v).permute(0, 2, 1, 3).reshape(n * L, d), wgt
+
+
+@pytest.mark.parametrize('mode', ['STD', 'Experimental', 'SCLIP', 'ClearCLIP', 'SFP', 'vanilla', 'SegEarth', 'MaskCLIP'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('L,hd', [(197, 64), (257, 64), (50, 80)])
+def test_attention_modes(ops, mode, dtype, L, hd):
+    """fp32: 2e-5 abs vs the torch formula of custom_attn; bf16 storage: 2e-2."""
+    from clip_decontamination_b200._lib import ATTN
+    if dtype == torch.bfloat16 and (L, hd) != (197, 64) and mode not in ('STD', 'Experimental'):
+        pytest.skip('bf16 covered on the main shape')
+    n, heads = 2, 3
+    d = heads * hd
+    qkv = (torch.randn(n * L, 3 * d, generator=_g(1)) * 0.8).to(dtype)
+    sim = None
+    if mode not in ('STD', 'MaskCLIP'):
+        f = F.normalize(torch.randn(n, L - 1, 24, generator=_g(2)), dim=-1)
+        sim = f @ f.transpose(1, 2)
+    ref, wgt = _attn_ref(qkv.float(), n, L, heads, mode, sim, 0.7)
+    out = torch.empty((n * L, d), device='cuda', dtype=dtype)
+    stats = torch.zeros((n, heads, 2, L - 1), device='cuda') if mode == 'STD' else None
+    ops.attention(qkv.cuda(), n, L, heads, hd, ATTN[mode], out, simmap=sim.cuda() if sim is not None else None,
+                  sim_weight=0.7, stats=stats)
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    assert (out.float().cpu() - ref).abs().max().item() < tol
+    if stats is not None:
+        s = stats.cpu()
+        assert (s[:, :, 0] - wgt[:, :, 0, 1:]).abs().max().item() < 1e-6
+        assert (s[:, :, 1] - torch.diagonal(wgt, dim1=2, dim2=3)[:, :, 1:]).abs().max().item() < 1e-6
+
+
+def test_simmap(ops):
+    n, L, w = 3, 197, 200
+    x = torch.randn(n * L, w, generator=_g(1))
+    ref = O.similarity_map(x.view(n, L, w)[:, 1:])
+    out = torch.empty((n, L - 1, L - 1), device='cuda')
+    ops.simmap(x.cuda(), n, L, w, out)
+    assert (out.cpu() - ref).abs().max().item() < 2e-6
+    ops.simmap(x.cuda(), n, L, w, out, temperature=2.0, add_self_similarity=False)
+    ref2 = O.similarity_map(x.view(n, L, w)[:, 1:], 2.0, False)
+    assert (out.cpu() - ref2).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize('grid,top_k', [(14, 30), (16, 10), (5, 25)])
+def test_outlier_suppression(ops, grid, top_k):
+    """indices bit-exact (ratios separated in the fixture); features 1e-5 abs."""
+    n, heads, w = 3, 4, 72
+    P = grid * grid
+    L = P + 1
+    y = torch.randn(n * L, w, generator=_g(1))
+    stats = torch.rand(n, heads, 2, P, generator=_g(2)) * 0.1 + 0.01
+    attn = torch.zeros(n, L, L)
+    attn[:, 0, 1:] = stats[:, :, 0].mean(1)
+    attn[:, torch.arange(1, L), torch.arange(1, L)] = stats[:, :, 1].mean(1)
+    oi = O.detect_outliers(attn, P, top_k)
+    fmap = y.view(n, L, w)[:, 1:].permute(0, 2, 1).reshape(n, w, grid, grid)
+    ref = O.outlier_mean_interpolation(fmap, oi, 0.1).reshape(n, w, P).permute(0, 2, 1)
+    yd = y.cuda()
+    k = min(top_k, P)
+    scratch = torch.empty(n * top_k * 9 * w, device='cuda')
+    idx = torch.full((n, top_k), -1, dtype=torch.int32, device='cuda')
+    ops.outlier_suppress(yd, n, L, w, grid, stats.cuda(), heads, top_k, 0.1, scratch, idx)
+    assert torch.equal(idx.cpu()[:, :k].long(), oi)
+    got = yd.cpu().view(n, L, w)
+    assert torch.equal(got[:, 0], y.view(n, L, w)[:, 0])
+    assert (got[:, 1:] - ref).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize('factor', [0.0, 0.2])
+def test_cls_debias(ops, factor):
+    n, L, D = 3, 30, 64
+    tok = torch.randn(n * L, D, generator=_g(1))
+    t = tok.view(n, L, D)
+    cls = t[:, 0] / t[:, 0].norm(dim=-1, keepdim=True)
+    f = t[:, 1:]
+    if factor:
+        fn = f / f.norm(dim=-1, keepdim=True)
+        cn = cls / cls.norm(dim=-1, keepdim=True)
+        s = (fn * cn.unsqueeze(1)).sum(-1)
+        f = f - cls.unsqueeze(1) * (s.unsqueeze(-1) * factor)
+    feats = torch.empty((n * (L - 1), D), device='cuda')
+    cu = torch.empty((n, D), device='cuda')
+    ops.cls_debias(tok.cuda(), n, L, D, factor, feats, cu)
+    assert (feats.cpu().view(n, L - 1, D) - f).abs().max().item() < 2e-6
+    assert (cu.cpu() - cls).abs().max().item() < 2e-6
+
+
+# ------------------------------------------------------------------ segmentor tail ----------------
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('Q', [2, 8, 16, 20])
+def test_norm_sim(ops, dtype, Q):
+    n, hw, D = 3, 101, 64
+    f = torch.randn(n * hw, D, generator=_g(1)).to(dtype)
+    text = F.normalize(torch.randn(Q, D, generator=_g(2)), dim=-1)
+    bias = torch.randn(n, Q, generator=_g(3)) * 0.1
+    ff = f.float()
+    ref = (ff / ff.norm(dim=-1, keepdim=True)) @ text.t()
+    ref = ref.view(n, hw, Q).permute(0, 2, 1) + bias[:, :, None]
+    out = torch.empty((n, Q, hw), device='cuda')
+    ops.norm_sim(f.cuda(), D, n, hw, D, text.cuda(), out, bias.cuda())
+    assert (out.cpu() - ref).abs().max().item() < 2e-6
+
+
+def _accum_case(ops, crop_logits, H, W, stride, crop, qidx, thd, bg, out_size=None, want=False):
+    wins = O.slide_windows(H, W, stride, crop)
+    wl = torch.tensor([(y1, x1, y2 - y1, x2 - x1) for (y1, y2, x1, x2) in wins], dtype=torch.int32).cuda()
+    K = max(qidx) + 1
+    oh, ow = out_size or (H, W)
+    labels = torch.empty((oh, ow), dtype=torch.uint8, device='cuda')
+    probs = torch.empty((K, oh, ow), device='cuda') if want else None
+    avg = torch.empty((len(qidx), H, W), device='cuda') if (want and out_size is None) else None
+    ch, cw = min(crop, H), min(crop, W)
+    ops.accum_argmax(crop_logits.cuda(), wl, ch, cw, 0, 0, H, W, oh, ow,
+                     torch.tensor(qidx, dtype=torch.int32).cuda(), K, 50.0, thd, bg, labels, probs, avg)
+    return wins, labels, probs, avg
+
+
+def test_accum_argmax_golden(ops, gold):
+    """labels bit-exact vs the reference's forward_slide + postprocess_result on stored crop logits."""
+    g = gold('postproc')
+    for tag in ('potsdam', 'loveda', 'road'):
+        H, W, thd, bg, stride, crop = g[f'{tag}_meta']
+        cl = torch.from_numpy(g[f'{tag}_crop_logits']).float()
+        qidx = g[f'{tag}_query_idx'].tolist()
+        wins, labels, probs, avg = _accum_case(ops, cl, int(H), int(W), int(stride), int(crop), qidx, float(thd),
+                                               int(bg), want=True)
+        assert np.array_equal(labels.cpu().numpy(), g[f'{tag}_labels'])
+        ravg, rpr, rpred = O.postprocess_from_crop_logits(cl, wins, int(H), int(W), qidx, 50, float(thd), int(bg))
+        assert torch.equal(avg.cpu(), ravg)                         # same summation order: bit-exact
+        assert (probs.cpu() - rpr).abs().max().item() < 1e-6
+
+
+def test_accum_argmax_resize_and_lowres(ops):
+    """ori_shape resize (segmentor.py:448-449) and low-res logits (no upsampler, :388-391): 1e-5 on probs,
+    labels equal wherever the oracle's top-2 probability margin exceeds 1e-4."""
+    H, W, stride, crop = 90, 120, 32, 64
+    qidx = [0, 0, 1, 2, 3, 3]
+    wins = O.slide_windows(H, W, stride, crop)
+    lo = torch.randn(len(wins), 6, 4, 4, generator=_g(3)) * 0.03
+    full = F.interpolate(lo, size=(crop, crop), mode='bilinear')
+    for out_size in (None, (131, 77)):
+        _, labels, probs, _ = _accum_case(ops, lo, H, W, stride, crop, qidx, 0.3, 1, out_size, want=True)
+        _, rpr, rpred = O.postprocess_from_crop_logits(full, wins, H, W, qidx, 50, 0.3, 1, out_size)
+        assert (probs.cpu() - rpr).abs().max().item() < 1e-5
+        s = torch.sort(rpr, dim=0, descending=True)[0]
+        safe = ((s[0] - s[1]) > 1e-4) & ((s[0] - 0.3).abs() > 1e-4)
+        assert torch.equal(labels.cpu().long()[safe], rpred[0][safe])
+
+
+def test_iou_hist(ops):
+    from clip_decontamination_b200 import synth
+    K = 6
+    pred = torch.from_numpy(synth.synthetic_labels(300, 200, K, 4))
+    pred[pred == 255] = 0
+    lab = torch.from_numpy(synth.synthetic_labels(300, 200, K, 5))
+    hist = torch.zeros((3, K), dtype=torch.int64, device='cuda')
+    ops.iou_hist(pred.cuda(), lab.cuda(), K, hist)
+    ops.iou_hist(pred.cuda(), lab.cuda(), K, hist)          # accumulates
+    ai, ap, al = O.intersect_and_union(pred.long(), lab.long(), K)
+    assert torch.equal(hist.cpu(), torch.stack([ai, ap, al]) * 2)
