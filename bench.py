@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the dense CLIP segmentation hot path (BASELINE.json metric: megapixels/sec segmented).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): Vaihingen-shaped 512x512 synthetic tiles, ViT-B/16 (synthetic
+"random-init" weights), jbu_one upsampler (C=512, radius 5), cls_vaihingen.txt (Q=K=6), prob_thd 0.1,
+bg_idx 5, slide 224/112 (16 crops per tile), base_config.py extras ON, bf16.  A step = `--tiles` tiles
+through preprocess -> ViT -> JBU -> logits -> accumulate/argmax -> IoU histogram (+ one all-reduce of
+the [3,K] int64 histogram per step when N > 1).  Every rank processes its own tiles (weak scaling).
+
+value : tiles already resident in HBM as uint8 (device-timed, CUDA events, max over ranks)
+e2e   : the same through SegmentorEx.predict_u8 from pinned HOST uint8 buffers, labels copied back
+roofline / cpu_baseline : see DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H = W = 512
+CROPS = 16
+WORKLOAD = ('Vaihingen-shaped 512x512 synthetic tile, ViT-B/16 + jbu_one (C=512, r=5), Q=K=6, slide 224/112 '
+            '(16 crops), base_config extras ON')
+METRIC = 'megapixels/sec segmented (ViT-B/16, 512x512 tiles, jbu_one)'
+
+
+def _peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sust=d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                    src='measured (MEASURED_PEAKS.json)')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback (B200_PROFILING.md)')
+
+
+# ---- algorithmic work per launch of each kernel class (DESIGN.md "Kernels and their rooflines") -------
+def _work_jbu_apply(n, h, w, C, radius, esize):
+    """adaptive conv at the reference op boundary: padded source + kernel + output."""
+    d = 2 * radius + 1
+    H2, W2 = 2 * h, 2 * w
+    return n * (C * (H2 + 2 * radius) * (W2 + 2 * radius) * esize + H2 * W2 * d * d * esize + C * H2 * W2 * esize)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == 'Active' for r in self.rows)]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+def build_model(device, precision='bf16'):
+    from clip_decontamination_b200.open_clip import create_model
+    from clip_decontamination_b200.open_clip.synthetic import synthetic_jbu_state_dict
+    from clip_decontamination_b200.segmentor import SegmentorEx
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'bench_text.npz'))
+    net = create_model('ViT-B/16', pretrained=None, precision='fp32' if precision == 'fp32' else 'fp16')
+    return SegmentorEx(clip_type='CLIP', vit_type='ViT-B/16', model_type='Experimental',
+                       name_path=os.path.join(ROOT, 'configs', 'cls_vaihingen.txt'), device=device,
+                       prob_thd=0.1, bg_idx=5, apply_sim_feat_up=True, global_debias_factor=0.2,
+                       apply_outlier_suppression=True, outlier_suppression_cfg=dict(top_k=30),
+                       apply_similarity_enhancement=True,
+                       similarity_enhancement_cfg=dict(similarity_weight=1.0, temperature=1.0, add_self_similarity=True),
+                       sim_feat_up_cfg=dict(model_name='jbu_one', model_path=None), precision=precision, net=net,
+                       query_features=torch.from_numpy(gold['vaihingen_query_features']),
+                       upsampler_state_dict=synthetic_jbu_state_dict('jbu_one', 512, 1))
+
+
+def cpu_baseline_crop_seconds(threads):
+    """Oracle (CPU restatement of the reference, fp32) on ONE 224 crop of the workload: ViT-B/16 with the
+    extras + jbu_one + cosine logits.  Returns seconds per crop."""
+    from oracle import clipseg_oracle as O
+    from clip_decontamination_b200 import synth
+    from clip_decontamination_b200.open_clip.model_configs import get_model_config
+    from clip_decontamination_b200.open_clip.synthetic import synthetic_clip_state_dict, synthetic_jbu_state_dict
+    torch.set_num_threads(threads)
+    cfg = get_model_config('ViT-B-16')
+    v = cfg['vision_cfg']
+    sd = synthetic_clip_state_dict(cfg, 0, text_tower=False)
+    vis = {k[len('visual.'):]: t for k, t in sd.items() if k.startswith('visual.')}
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'bench_text.npz'))
+    orc = O.SegOracle(vis, torch.from_numpy(gold['vaihingen_query_features']), list(range(6)), layers=v['layers'],
+                      heads=v['heads'], patch=16, prob_thd=0.1, bg_idx=5, global_debias_factor=0.2,
+                      upsampler=('jbu_one', synthetic_jbu_state_dict('jbu_one', 512, 1)), sim_cfg={},
+                      outlier_cfg={'top_k': 30})
+    img = torch.from_numpy(synth.preprocess(synth.voronoi_scene(H, W, 100)))[None]
+    crop = img[:, :, :224, :224]
+    with torch.no_grad():
+        t0 = time.time()
+        orc.forward_feature(crop)
+        return time.time() - t0
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU implementation of the path on the host cores (the oracle port: the
+    reference is Python and cannot travel to the GPU box).  A step = one crop of one tile, scaled to the
+    tile (16 crops); all host threads."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_baseline_crop_seconds(threads)
+    ts = [cpu_baseline_crop_seconds(threads) for _ in range(max(1, min(args.steps, 3)))]
+    sec_tile = float(np.mean(ts)) * CROPS
+    mps = H * W / 1e6 / sec_tile
+    line = dict(metric=METRIC, value=mps, unit='MP/s', n_gpus=args.gpus, steps=len(ts), warmup=1,
+                ms_per_step=sec_tile * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                data='synthetic', impl='reference', config=dict(workload=WORKLOAD),
+                cpu_baseline=dict(value=mps, unit='MP/s', cores=threads, kind='port',
+                                  sample='1 of the 16 crops of one 512x512 tile per step (ViT-B/16 + extras + '
+                                         'jbu_one + logits), time x16'),
+                e2e=dict(value=mps, unit='MP/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--tiles', type=int, default=4, help='tiles per step per GPU')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        return run_reference(args, rank)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    from clip_decontamination_b200 import ops, synth
+    from clip_decontamination_b200 import _lib
+    from clip_decontamination_b200.dist import allreduce_hist
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    model = build_model(device, args.precision)
+    eng = model.engine
+    K = model.num_classes
+    T = args.tiles
+    # synthetic tiles (different per rank / tile) + synthetic ground truth for the histogram
+    host_imgs = [torch.from_numpy(synth.voronoi_scene(H, W, 1000 + rank * 64 + t)).pin_memory() for t in range(T)]
+    host_gt = [torch.from_numpy(synth.synthetic_labels(H, W, K, 2000 + rank * 64 + t)) for t in range(T)]
+    dev_imgs = [x.to(device) for x in host_imgs]
+    dev_gt = [x.to(device) for x in host_gt]
+    hist = torch.zeros((3, K), dtype=torch.int64, device=device)
+    labels = [torch.empty((H, W), dtype=torch.uint8, device=device) for _ in range(T)]
+    host_labels = [torch.empty((H, W), dtype=torch.uint8).pin_memory() for _ in range(T)]
+    mean, std = synth.MEAN.tolist(), synth.STD.tolist()
+    img_f32 = torch.empty((3, H, W), dtype=torch.float32, device=device)
+
+    def step_resident():
+        for t in range(T):
+            ops.preprocess_u8(dev_imgs[t], mean, std, img_f32)
+            eng.segment(img_f32, None, labels=labels[t])
+            ops.iou_hist(labels[t].view(-1), dev_gt[t].view(-1), K, hist)
+        allreduce_hist(hist)
+
+    def step_e2e():
+        for t in range(T):
+            lab = model.predict_u8(host_imgs[t], labels_out=labels[t])       # H2D inside
+            ops.iou_hist(lab.view(-1), dev_gt[t].view(-1), K, hist)
+            host_labels[t].copy_(lab, non_blocking=True)                      # D2H of the step's result
+        allreduce_hist(hist)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up; find the dominant kernel with a fully instrumented step -------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    records = {}
+    orig = {}
+    work = {}
+
+    def wrap(name, fn, workfn=None):
+        def inner(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*a, **k)
+            e.record()
+            records.setdefault(name, []).append((s, e, workfn(*a, **k) if workfn else None))
+            return r
+        return inner
+
+    esize = 2 if args.precision == 'bf16' else 4
+
+    def gemm_work(A, B, out, **k):
+        return ('tensor', 2.0 * (k.get('M') or A.shape[0]) * (k.get('N') or B.shape[0]) * (k.get('K') or A.shape[1]))
+
+    def apply_work(src, n, h, w, C, kern, radius, dst, hr):
+        return ('hbm', float(_work_jbu_apply(n, h, w, C, radius, esize)))
+
+    def attn_work(qkv, n, L, heads, hd, mode, out, **k):
+        return ('tensor', (4.0 if mode == 0 else 6.0) * n * heads * L * L * hd)
+
+    def nsim_work(feats, ldf, n, hw, D, text, logits, cls_logit_bias=None):
+        return ('hbm', float(n * hw * (D * esize + text.shape[0] * 4)))
+
+    def accum_work(cl, *a, **k):
+        return ('hbm', float(cl.numel() * 4 + H * W))
+
+    def rk_work(proj, guid, n, gh, gw, radius, rt, ss, kern):
+        return ('hbm', float(n * gh * gw * (32 * 4 + 16 + kern.shape[-1] * esize)))
+
+    workfns = dict(gemm=gemm_work, jbu_apply=apply_work, attention=attn_work, norm_sim=nsim_work,
+                   accum_argmax=accum_work, jbu_range_kernel=rk_work)
+    names = ['preprocess_u8', 'patchify', 'embed_tokens', 'layernorm', 'gemm', 'attention', 'simmap', 'outlier_suppress',
+             'cls_debias', 'jbu_guidance', 'jbu_range_proj', 'jbu_range_kernel', 'jbu_apply', 'norm_sim',
+             'accum_argmax', 'iou_hist']
+    for nm in names:
+        orig[nm] = getattr(ops, nm)
+        setattr(ops, nm, wrap(nm, orig[nm], workfns.get(nm)))
+    step_resident()
+    torch.cuda.synchronize()
+    for nm in names:
+        setattr(ops, nm, orig[nm])
+    totals = {nm: sum(s.elapsed_time(e) for s, e, _ in recs) for nm, recs in records.items()}
+    breakdown = {nm: round(v / T, 4) for nm, v in sorted(totals.items(), key=lambda kv: -kv[1])}
+    dominant = max((nm for nm in totals if nm in workfns), key=lambda nm: totals[nm])
+    records.clear()
+    # only the dominant kernel stays wrapped during the timed region (2 events per launch)
+    setattr(ops, dominant, wrap(dominant, orig[dominant], workfns[dominant]))
+
+    # ---- timed region: value (inputs resident in HBM) ----------------------------------------------
+    clk = ClockSampler(local_rank)
+    clk.start()
+    l0 = _lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - l0
+    clocks = clk.stop()
+    setattr(ops, dominant, orig[dominant])
+    dom = records.get(dominant, [])
+    dom_ms = [s.elapsed_time(e) for s, e, _ in dom]
+    dom_work = [w[1] for _, _, w in dom]
+    bound = dom[0][2][0] if dom else 'hbm'
+    peaks = _peaks()
+    avg_ms = float(np.mean(dom_ms)) if dom_ms else float('nan')
+    avg_work = float(np.mean(dom_work)) if dom_work else 0.0
+    if bound == 'hbm':
+        achieved, peak, runit = avg_work / avg_ms / 1e6, peaks['hbm'], 'GB/s'
+    else:
+        achieved, peak, runit = avg_work / avg_ms / 1e9, peaks['tf_sust'], 'TFLOP/s'
+    roofline = dict(kernel=dominant, bound=bound, achieved=achieved, peak=peak, unit=runit, frac=achieved / peak,
+                    traffic=None, launches_timed=len(dom_ms), avg_launch_ms=avg_ms, share_of_step=sum(dom_ms) / ms,
+                    peak_source=peaks['src'], per_tile_ms_by_kernel=breakdown)
+
+    # ---- e2e: host buffers in, labels out, through the segmentor API -------------------------------
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    mp_step = T * H * W / 1e6 * world
+    value = mp_step * args.steps / (ms / 1e3)
+    e2e = mp_step * args.steps / (ms_e2e / 1e3)
+    line = dict(metric=METRIC, value=value, unit='MP/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype=args.precision, data='synthetic',
+                config=dict(workload=WORKLOAD, tiles_per_step_per_gpu=T, crops_per_tile=CROPS,
+                            l2='per-tile working set (JBU stages, ~3 GB) far exceeds the 126 MB L2; inputs rotate '
+                               'over %d tiles' % T, parallelism=f'image-sharded x{world}'),
+                clocks=clocks, gpu_launches=int(launches),
+                e2e=dict(value=e2e, unit='MP/s', h2d_bytes_per_step=T * H * W * 3, d2h_bytes_per_step=T * H * W,
+                         ms_per_step=ms_e2e / args.steps),
+                roofline=roofline)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sec = cpu_baseline_crop_seconds(threads)
+        line['cpu_baseline'] = dict(value=H * W / 1e6 / (sec * CROPS), unit='MP/s', cores=threads, kind='port',
+                                    sample='1 of the 16 crops of one 512x512 tile (ViT-B/16 + extras + jbu_one + '
+                                           'logits) through the oracle, time x16')
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

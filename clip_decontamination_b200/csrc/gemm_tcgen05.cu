@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int num_kb = K / BK;
+  const int num_kb = (K + BK - 1) / BK;  // a K tail is zero-filled by TMA (OOB fill) in both operands
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -327,7 +327,7 @@ int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int
                       const void* residual, int ldr, int res_dtype, float alpha, int act, int out_dtype, void* C,
                       int ldc, cudaStream_t st) {
   CSEG_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  CSEG_REQUIRE(K % BK == 0, "gemm(bf16): K=%d must be a multiple of %d (pad the operands)", K, BK);
+  CSEG_REQUIRE(K % 8 == 0, "gemm(bf16): K=%d must be a multiple of 8 (16-byte rows for TMA)", K);
   CSEG_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm(bf16): lda=%d, ldb=%d must be multiples of 8", lda, ldb);
   CSEG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm(bf16): operands must be 16-byte aligned");
   int bn = (N <= 64 || (long long)cdiv(M, BM) * cdiv(N, 128) < 2LL * sm_count()) ? 64 : 128;

@@ -228,8 +228,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const T* __re
         for (int t = 0; t < ATT_JMAX; ++t) s1[t] = s2[t] + s1[t];  // kk + qq, :899
         warp_softmax(s1, nj);
 #pragma unroll
-        for (int t = 0; t < ATT_JMAX; ++t)
-          if (lane + 32 * t < L) s1[t] += madd[t];  // enhance_attention on the probabilities, :901
+        for (int t = 0; t < ATT_JMAX; ++t)  // enhance_attention on the probabilities, :901
+          s1[t] = (lane + 32 * t < L) ? s1[t] + madd[t] : -INFINITY;
         warp_softmax(s1, nj);                       // second softmax is unconditional, :902
       } else {                                      // SCLIP / SEGEARTH
 #pragma unroll

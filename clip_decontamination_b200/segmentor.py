@@ -1,0 +1,352 @@
+"""``SegmentorEx`` -- drop-in for the reference's mmseg segmentor (segmentor.py:25-622).
+
+Same registry name, constructor kwargs, methods (``predict``, ``forward_slide``, ``forward_feature``,
+``postprocess_result``, ``compute_padsize``) and attributes (``net``, ``query_features``, ``query_idx``,
+``num_queries``, ``num_classes``, ``data_preprocessor``) as the reference, so the reference's ``eval.py``
+/ ``cfg_*.py`` / ``cls_*.txt`` work unchanged when this module is importable as ``segmentor``
+(see INTEGRATION.md).  The arithmetic runs in libclipseg (sm_100a); nothing here falls back to the CPU.
+
+Differences that are visible to a caller (all documented in INTEGRATION.md):
+* compute is bf16 (tcgen05) with fp32 residual stream / softmax / logits where the reference is fp16;
+  ``precision='fp32'`` selects the CUDA-core verification mode;
+* all crops of an image are processed as one batch;
+* ``seg_logits`` (class probabilities) is only attached to the data samples when
+  ``output_seg_logits=True`` -- the fused accumulate->argmax kernel does not write them otherwise.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .compat import BaseSegmentor, SegDataPreProcessor, PixelData, MODELS
+from .engine import SegEngine, compute_padsize as _compute_padsize, slide_windows
+from .open_clip import create_model, tokenizer
+from .outlier_suppression import OutlierSuppressionModule
+from .prompts.imagenet_template import openai_imagenet_template
+from .similarity_enhancement import SimilarityEnhancementModule
+from .simfeatup_dev.upsamplers import get_upsampler
+
+_CLIP_TABLE = {       # segmentor.py:69-112 (clip_type, 'B'/'L'/'H' in vit_type) -> (model name, pretrained)
+    ('CLIP', 'B'): ('ViT-B/16', 'openai'), ('CLIP', 'L'): ('ViT-L-14', 'openai'),
+    ('RemoteCLIP', 'B'): ('ViT-B/32', 'checkpoint/RemoteCLIP-ViT-B-32.pt'),
+    ('RemoteCLIP', 'L'): ('ViT-L-14', 'checkpoint/RemoteCLIP-ViT-L-14.pt'),
+    ('GeoRSCLIP', 'B'): ('ViT-B/32', 'checkpoint/RS5M_ViT-B-32.pt'),
+    ('GeoRSCLIP', 'L'): ('ViT-L-14', 'checkpoint/RS5M_ViT-L-14.pt'),
+    ('GeoRSCLIP', 'H'): ('ViT-H-14', 'checkpoint/RS5M_ViT-H-14.pt'),
+    ('SkyCLIP', 'B'): ('ViT-B/32', 'checkpoint/SkyCLIP_ViT_B32_top50pct/epoch_20.pt'),
+    ('SkyCLIP', 'L'): ('ViT-L-14', 'checkpoint/SkyCLIP_ViT_L14_top30pct_filtered_by_CLIP_laion_RS/epoch_20.pt'),
+    ('OpenCLIP', 'B'): ('ViT-B/16', 'laion2b_s34b_b88k'), ('OpenCLIP', 'L'): ('ViT-L-14', 'laion2b_s32b_b82k'),
+    ('MetaCLIP', 'B'): ('ViT-B-16-quickgelu', 'metaclip_fullcc'),
+    ('MetaCLIP', 'L'): ('ViT-L/14-quickgelu', 'metaclip_fullcc'),
+    ('ALIP', 'B'): ('ViT-B/32', 'checkpoint/ALIP_YFCC15M_B32.pt'),
+}
+
+
+def get_cls_idx(path):
+    """segmentor.py:611-622 -- one class per line, ',' separates synonyms, only the newline is stripped."""
+    with open(path, 'r') as f:
+        name_sets = f.readlines()
+    class_names, class_indices = [], []
+    for idx, line in enumerate(name_sets):
+        names_i = line.split(',')
+        class_names += names_i
+        class_indices += [idx for _ in range(len(names_i))]
+    class_names = [item.replace('\n', '') for item in class_names]
+    return class_names, class_indices
+
+
+def _vit_key(vit_type: str) -> str:
+    for k in ('B', 'L', 'H'):
+        if k in vit_type:
+            return k
+    raise ValueError(f'cannot parse vit_type {vit_type!r}')
+
+
+@MODELS.register_module()
+class SegmentorEx(BaseSegmentor):
+    def __init__(self,
+                 clip_type,
+                 vit_type,
+                 model_type,
+                 name_path,
+                 device=torch.device('cuda'),
+                 ignore_residual=True,
+                 prob_thd=0.0,
+                 logit_scale=50,
+                 slide_stride=112,
+                 slide_crop=224,
+                 cls_token_lambda=0.0,
+                 global_debias_factor=0.0,
+                 bg_idx=0,
+                 apply_sim_feat_up=False,
+                 sim_feat_up_cfg=dict(model_name='jbu_one', model_path='your/model/path'),
+                 apply_ctd=False,
+                 apply_outlier_suppression=False,
+                 outlier_suppression_cfg=None,
+                 apply_self_attn_enhancement=False,
+                 self_attn_enhancement_cfg=None,
+                 apply_layer_fusion=False,
+                 layer_fusion_lambda=0.5,
+                 layer_fusion_threshold=0.7,
+                 apply_similarity_enhancement=False,
+                 similarity_enhancement_cfg=None,
+                 result_dir=None,
+                 heatmap_dir=None,
+                 # ---- extensions (not in the reference) ----
+                 precision='bf16',
+                 output_seg_logits=False,
+                 query_features=None,
+                 net=None,
+                 upsampler_state_dict=None,
+                 ):
+        data_preprocessor = SegDataPreProcessor(
+            mean=[122.771, 116.746, 104.094],
+            std=[68.501, 66.632, 70.323],
+            bgr_to_rgb=True)
+        super().__init__(data_preprocessor=data_preprocessor)
+        # switches that are outside the CUDA hot path: accepted when off, refused when on
+        for flag, name in ((apply_ctd, 'apply_ctd'), (apply_self_attn_enhancement, 'apply_self_attn_enhancement'),
+                           (apply_layer_fusion, 'apply_layer_fusion')):
+            if flag:
+                raise NotImplementedError(f'{name}=True is not part of the B200 hot path (default off in the '
+                                          f'reference, enabled by no config)')
+        if clip_type == 'BLIP' or model_type == 'GEM':
+            raise NotImplementedError('BLIP / GEM backbones are not part of the B200 hot path')
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise RuntimeError('SegmentorEx runs on CUDA only (there is no CPU fallback)')
+        if device.index is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        if net is None:
+            key = (clip_type, _vit_key(vit_type))
+            if key not in _CLIP_TABLE:
+                raise ValueError(f'unknown clip_type / vit_type {clip_type!r} / {vit_type!r}')
+            name, pretrained = _CLIP_TABLE[key]
+            net = create_model(name, pretrained=pretrained, precision='fp32' if precision == 'fp32' else 'fp16')
+        self.net = net
+        self.net.precision = 'fp32' if precision == 'fp32' else 'bf16'
+        self.net.eval().to(device)
+        self.tokenizer = tokenizer.tokenize
+        self.clip_type, self.vit_type, self.model_type = clip_type, vit_type, model_type
+        self.apply_sim_feat_up = apply_sim_feat_up
+        self.cls_token_lambda = cls_token_lambda
+        self.global_debias_factor = global_debias_factor
+        self.bg_idx = bg_idx
+        self.patch_size = self.net.visual.patch_size
+
+        query_words, query_idx = get_cls_idx(name_path)
+        self.num_queries = len(query_words)
+        self.num_classes = max(query_idx) + 1
+        self.query_idx = torch.Tensor(query_idx).to(torch.int64).to(device)
+        if query_features is None:                                   # segmentor.py:157-174 (init-time, PyTorch)
+            feats = []
+            with torch.no_grad():
+                for qw in query_words:
+                    query = self.tokenizer([temp(qw) for temp in openai_imagenet_template]).to(device)
+                    feature = self.net.encode_text(query)
+                    feature /= feature.norm(dim=-1, keepdim=True)
+                    feature = feature.mean(dim=0)
+                    feature /= feature.norm()
+                    feats.append(feature.unsqueeze(0))
+            query_features = torch.cat(feats, dim=0)
+        self.query_features = query_features.to(device).float()
+        assert self.query_features.shape[0] == self.num_queries
+        self.dtype = self.query_features.dtype
+        self.ignore_residual = ignore_residual
+        self.logit_scale, self.prob_thd = logit_scale, prob_thd
+        self.slide_stride, self.slide_crop = slide_stride, slide_crop
+        self.apply_ctd = apply_ctd
+        self.apply_layer_fusion = apply_layer_fusion
+        self.layer_fusion_lambda, self.layer_fusion_threshold = layer_fusion_lambda, layer_fusion_threshold
+        self.apply_self_attn_enhancement = apply_self_attn_enhancement
+
+        self.apply_similarity_enhancement = apply_similarity_enhancement
+        sim_cfg = None
+        if apply_similarity_enhancement:                             # segmentor.py:196-220
+            sim_cfg = dict(similarity_weight=1.0, temperature=1.0, add_self_similarity=True)
+            if similarity_enhancement_cfg:
+                sim_cfg.update(similarity_enhancement_cfg)
+            self.net.visual.similarity_enhancer = SimilarityEnhancementModule(**sim_cfg)
+        self.apply_outlier_suppression = apply_outlier_suppression
+        out_cfg = None
+        if apply_outlier_suppression:                                # segmentor.py:252-274
+            out_cfg = dict(top_k=10)
+            if outlier_suppression_cfg:
+                out_cfg.update(outlier_suppression_cfg)
+            self.net.visual.outlier_suppressor = OutlierSuppressionModule(top_k=out_cfg['top_k'])
+            out_cfg['contamination_temp'] = self.net.visual.outlier_suppressor.contamination_temp
+        self.result_dir, self.heatmap_dir = result_dir, heatmap_dir
+        self.output_seg_logits = output_seg_logits or bool(heatmap_dir)
+
+        up_engine = None
+        if self.apply_sim_feat_up:                                   # segmentor.py:278-284
+            self.feat_dim = self.query_features.shape[-1]
+            self.upsampler = get_upsampler(sim_feat_up_cfg['model_name'], self.feat_dim)
+            if upsampler_state_dict is None:
+                ckpt = torch.load(sim_feat_up_cfg['model_path'], map_location='cpu', weights_only=False)['state_dict']
+                upsampler_state_dict = {k[10:]: v for k, v in ckpt.items()}
+            self.upsampler.load_state_dict(upsampler_state_dict, strict=True)
+            self.upsampler.precision = self.net.precision
+            self.upsampler.to(device)
+            up_engine = self.upsampler.engine(device, self.net.precision)
+        self._device = device
+        self.engine = SegEngine(self.net.visual_engine(device), self.query_features, query_idx,
+                                model_type=model_type, ignore_residual=ignore_residual, prob_thd=prob_thd,
+                                logit_scale=logit_scale, slide_stride=slide_stride, slide_crop=slide_crop,
+                                cls_token_lambda=cls_token_lambda, global_debias_factor=global_debias_factor,
+                                bg_idx=bg_idx, upsampler=up_engine, sim_cfg=sim_cfg, outlier_cfg=out_cfg)
+
+    # ------------------------------------------------------------------------------------------
+    def _img3(self, img):
+        if type(img) == list:
+            img = img[0]
+        if img.dim() == 4:
+            if img.shape[0] != 1:
+                raise ValueError('forward_feature / forward_slide take one image (the reference views with batch 1, '
+                                 'segmentor.py:369,372); use predict() for batches')
+            img = img[0]
+        return img.to(self._device, torch.float32).contiguous()
+
+    def forward_feature(self, img, logit_size=None, tile_h_idx=None, tile_w_idx=None):
+        """Cosine logits of ONE crop [1,Q,h,w] resized to `logit_size` / the crop size (segmentor.py:286-392)."""
+        img3 = self._img3(img)
+        _, H, W = img3.shape
+        saved = self.engine.crop, self.engine._win_cache
+        self.engine.crop, self.engine._win_cache = 0, {}
+        try:
+            logits, g = self.engine.crop_logits(img3)
+        finally:
+            self.engine.crop, self.engine._win_cache = saved
+        size = (H, W) if logit_size is None else tuple(logit_size)
+        return nn.functional.interpolate(logits, size=size, mode='bilinear')
+
+    def forward_slide(self, img, img_metas, stride=112, crop_size=224):
+        """Averaged cosine logits [1,Q,H0,W0] (segmentor.py:394-451)."""
+        img3 = self._img3(img)
+        eng = self.engine
+        saved = eng.stride, eng.crop, eng._win_cache
+        stride = stride[0] if isinstance(stride, (tuple, list)) else stride
+        crop_size = crop_size[0] if isinstance(crop_size, (tuple, list)) else crop_size
+        if (stride, crop_size) != (eng.stride, eng.crop):
+            eng.stride, eng.crop, eng._win_cache = stride, crop_size, {}
+        try:
+            _, _, avg = eng.segment(img3, None, want_logits=True)
+        finally:
+            eng.stride, eng.crop, eng._win_cache = saved
+        logits = avg.unsqueeze(0)
+        img_size = tuple(img_metas[0]['ori_shape'][:2])
+        if img_size != tuple(logits.shape[-2:]):
+            logits = nn.functional.interpolate(logits, size=img_size, mode='bilinear')
+        return logits
+
+    @torch.no_grad()
+    def predict(self, inputs, data_samples):
+        """segmentor.py:453-473.  inputs [B,3,H,W] normalised floats (any float dtype, any device)."""
+        if data_samples is not None:
+            batch_img_metas = [ds.metainfo for ds in data_samples]
+        else:
+            batch_img_metas = [dict(ori_shape=inputs.shape[2:], img_shape=inputs.shape[2:],
+                                    pad_shape=inputs.shape[2:], padding_size=[0, 0, 0, 0])] * inputs.shape[0]
+        preds = []
+        for i in range(inputs.shape[0]):
+            img = inputs[i].to(self._device, torch.float32).contiguous()
+            ori = tuple(batch_img_metas[i]['ori_shape'][:2])
+            labels, probs, _ = self.engine.segment(img, ori, want_probs=self.output_seg_logits)
+            seg_pred = labels.to(torch.int64).unsqueeze(0)
+            if data_samples is None:
+                preds.append(seg_pred)
+                continue
+            d = {'pred_sem_seg': PixelData(**{'data': seg_pred})}
+            if probs is not None:
+                d['seg_logits'] = PixelData(**{'data': probs})
+            data_samples[i].set_data(d)
+            if self.result_dir or self.heatmap_dir:
+                self._dump(i, data_samples[i], seg_pred, probs)
+        if data_samples is None:
+            return preds[0] if len(preds) == 1 else torch.stack(preds)   # reference returns image 0 (batch 1)
+        return data_samples
+
+    @torch.no_grad()
+    def predict_u8(self, img_hwc_bgr_u8, labels_out=None):
+        """Input side fused (N1): uint8 HWC BGR image (host or device) -> uint8 labels [H,W] on the device.
+        Equivalent to data_preprocessor + predict for one image."""
+        from . import ops
+        x = img_hwc_bgr_u8
+        if not x.is_cuda:
+            x = x.to(self._device, non_blocking=True)
+        pp = self.data_preprocessor
+        mean = [122.771, 116.746, 104.094]
+        std = [68.501, 66.632, 70.323]
+        img = ops.preprocess_u8(x.contiguous(), mean, std)
+        labels, _, _ = self.engine.segment(img, None, labels=labels_out)
+        return labels
+
+    def postprocess_result(self, seg_logits, data_samples):
+        """segmentor.py:475-499 on given averaged logits [B,Q,H,W] (runs the fused kernel with one
+        full-size window per image)."""
+        from . import ops
+        B, Q, H, W = seg_logits.shape
+        out = []
+        for i in range(B):
+            lg = seg_logits[i].to(self._device, torch.float32).contiguous().unsqueeze(0)
+            win = torch.tensor([(0, 0, H, W)], dtype=torch.int32, device=self._device)
+            labels = torch.empty((H, W), dtype=torch.uint8, device=self._device)
+            probs = torch.empty((self.num_classes, H, W), dtype=torch.float32, device=self._device)
+            ops.accum_argmax(lg, win, H, W, 0, 0, H, W, H, W, self.engine.query_idx, self.num_classes,
+                             float(self.logit_scale), float(self.prob_thd), int(self.bg_idx), labels, probs)
+            seg_pred = labels.to(torch.int64).unsqueeze(0)
+            if data_samples is None:
+                return seg_pred
+            data_samples[i].set_data({'seg_logits': PixelData(**{'data': probs}),
+                                      'pred_sem_seg': PixelData(**{'data': seg_pred})})
+        return data_samples
+
+    def compute_padsize(self, H: int, W: int, patch_size: int):
+        return _compute_padsize(H, W, patch_size)
+
+    # ---- optional PNG dumps (segmentor.py:501-531,568-608); host-side, off the hot path ---------
+    def _dump(self, i, sample, seg_pred, probs):
+        import colorsys
+        import cv2
+        meta = getattr(sample, 'metainfo', {}) or {}
+        stem = next((os.path.splitext(os.path.basename(meta[k]))[0] for k in
+                     ('img_path', 'ori_path', 'filename', 'ori_filename') if meta.get(k)), f'sample_{i}')
+        if self.result_dir:
+            os.makedirs(self.result_dir, exist_ok=True)
+            n = int(self.num_classes)
+            pal = []
+            for idx in range(n):
+                r, g, b = colorsys.hsv_to_rgb((idx / max(1, n)) % 1.0, 0.75, 1.0 if idx != self.bg_idx else 0.2)
+                pal.append([int(r * 255), int(g * 255), int(b * 255)])
+            pal = np.array(pal, dtype=np.uint8)
+            mask = seg_pred.squeeze(0).cpu().numpy().astype(np.int32)
+            cv2.imwrite(os.path.join(self.result_dir, f'{stem}.png'), pal[np.clip(mask, 0, n - 1)][:, :, ::-1])
+        if self.heatmap_dir and probs is not None:
+            os.makedirs(self.heatmap_dir, exist_ok=True)
+            conf = np.clip(np.nan_to_num(probs.max(dim=0)[0].cpu().numpy(), nan=0.0), 0.0, 1.0)
+            heat = cv2.applyColorMap((conf * 255.0).astype(np.uint8), cv2.COLORMAP_JET)
+            cv2.imwrite(os.path.join(self.heatmap_dir, f'{stem}.png'), heat)
+
+    # mmseg abstract methods (unused, as in the reference segmentor.py:548-566)
+    def _forward(self, *a, **k):
+        pass
+
+    def inference(self, img, batch_img_metas):
+        pass
+
+    def encode_decode(self, inputs, batch_img_metas):
+        pass
+
+    def extract_feat(self, inputs):
+        pass
+
+    def loss(self, inputs, data_samples):
+        pass
+
+    # aliases named in BASELINE.json's north_star
+    slide_inference = forward_slide
+
+
+SegEarthSegmentation = SegmentorEx

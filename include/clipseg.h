@@ -79,7 +79,7 @@ CSEG_API int cseg_layernorm(const float* x, int rows, int width, const float* ga
 
 /* ---- GEMM (K1,K3,K4,K9,K12 of SURVEY 2.2): nn.Linear / 1x1 conv -------------------------------
  * C[M,N] = residual + alpha * act(A[M,K] . B[N,K]^T + bias)      (residual, bias optional)
- * in_dtype CSEG_BF16 -> TMA-fed tcgen05 kernel (fp32 accumulate in TMEM); A,B bf16, K % 64 == 0,
+ * in_dtype CSEG_BF16 -> TMA-fed tcgen05 kernel (fp32 accumulate in TMEM); A,B bf16, K % 8 == 0,
  * lda,ldb % 8 == 0, 16-byte aligned bases.  in_dtype CSEG_F32 -> CUDA-core fp32 verification
  * kernel.  bias fp32 [N]; residual [M, ldr] in res_dtype; C in out_dtype (may alias residual when both
  * have the same dtype). */

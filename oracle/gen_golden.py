@@ -254,7 +254,22 @@ def seg_group(out_name, model_name, cls, H, W, thd, bg, upsampler=None, extras=T
           hist=torch.bincount(pred.flatten(), minlength=seg.num_classes))
 
 
+@torch.no_grad()
+def bench_text():
+    """prompt-ensembled class text embeddings (segmentor.py:157-174) of the benchmark configs, produced by
+    the reference's tokenizer + text tower on the synthetic ViT-B/16 weights."""
+    cfg = get_model_config('ViT-B-16')
+    sd = synthetic_clip_state_dict(cfg, 0)
+    arrs = {}
+    for cls in ('vaihingen', 'potsdam', 'isaid', 'roadval'):
+        seg = rh.build_ref_segmentor(cfg, sd, os.path.join(ROOT, 'configs', f'cls_{cls}.txt'), model_type='Experimental')
+        arrs[f'{cls}_query_features'] = seg.query_features
+        arrs[f'{cls}_query_idx'] = seg.query_idx
+    _save('bench_text', **arrs)
+
+
 GROUPS = {
+    'bench_text': bench_text,
     'vit_tiny': lambda: vit_group('ViT-tiny-16', 'vit_tiny',
                                   ['Experimental', 'SCLIP', 'ClearCLIP', 'SFP', 'vanilla', 'SegEarth', 'MaskCLIP']),
     'vit_b16': lambda: vit_group('ViT-B-16', 'vit_b16_crop', ['Experimental']),

@@ -1,0 +1,116 @@
+"""The reference-facing API on the GPU: SegmentorEx / Segmentor (predict, forward_slide, predict_u8,
+postprocess_result), create_model().encode_image, get_upsampler().forward and the sharded evaluator."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import clipseg_oracle as O  # noqa: E402
+from clip_decontamination_b200 import synth  # noqa: E402
+from clip_decontamination_b200.open_clip.model_configs import get_model_config  # noqa: E402
+from clip_decontamination_b200.open_clip.synthetic import synthetic_clip_state_dict, synthetic_jbu_state_dict  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXTRAS = dict(global_debias_factor=0.2, apply_outlier_suppression=True, outlier_suppression_cfg=dict(top_k=30),
+              apply_similarity_enhancement=True,
+              similarity_enhancement_cfg=dict(similarity_weight=1.0, temperature=1.0, add_self_similarity=True))
+
+
+def _segmentor(gold, precision='fp32', cls_name='Ex', **kw):
+    from clip_decontamination_b200.open_clip import create_model
+    from clip_decontamination_b200.segmentor import SegmentorEx
+    from clip_decontamination_b200.segearth_segmentor import Segmentor
+    g = gold('seg_tiny_jbu')
+    net = create_model('ViT-tiny-16', pretrained=None, precision='fp32' if precision == 'fp32' else 'fp16')
+    cls = SegmentorEx if cls_name == 'Ex' else Segmentor
+    base = dict(clip_type='CLIP', vit_type='ViT-B/16', model_type='Experimental',
+                name_path=os.path.join(ROOT, 'configs', 'cls_potsdam.txt'), prob_thd=0.1, bg_idx=5,
+                apply_sim_feat_up=True, sim_feat_up_cfg=dict(model_name='jbu_one', model_path=None),
+                precision=precision, net=net, query_features=torch.from_numpy(g['query_features']),
+                upsampler_state_dict=synthetic_jbu_state_dict('jbu_one', 64, 1))
+    base.update(kw)
+    return cls(**base), g
+
+
+def test_segmentor_ex_predict_matches_reference_golden(gold):
+    seg, g = _segmentor(gold, **EXTRAS)
+    H, W, seed = int(g['meta'][0]), int(g['meta'][1]), int(g['meta'][4])
+    u8 = synth.voronoi_scene(H, W, seed)
+    x = torch.from_numpy(synth.preprocess(u8))[None]
+    pred = seg.predict(x.cuda(), None)                                    # demo.py:42 call form
+    assert pred.shape == (1, H, W) and pred.dtype == torch.int64
+    assert (pred[0].cpu().numpy() == g['labels']).mean() >= 0.999
+    lg = seg.forward_slide(x.cuda(), [dict(ori_shape=(H, W))], 112, 224)
+    assert np.abs(lg[0].cpu().numpy()[:, ::4, ::4] - g['logits_sub']).max() < 1e-4
+    assert seg.slide_inference.__func__ is seg.forward_slide.__func__
+    lab = seg.predict_u8(torch.from_numpy(u8))                            # host uint8 HWC BGR in
+    assert (lab.cpu().numpy() == g['labels']).mean() >= 0.999
+    # data_samples form: pred_sem_seg PixelData int64 [1,H,W]; seg_logits only on request
+    from clip_decontamination_b200.compat import HAVE_MMSEG
+    if not HAVE_MMSEG:
+        from clip_decontamination_b200.compat import SegDataSample
+        ds = [SegDataSample(dict(ori_shape=(H, W)))]
+        out = seg.predict(x.cuda(), ds)
+        assert torch.equal(out[0].pred_sem_seg.data, pred) and not hasattr(out[0], 'seg_logits')
+        batch = dict(inputs=[torch.from_numpy(np.ascontiguousarray(u8.transpose(2, 0, 1)))],
+                     data_samples=[SegDataSample(dict(ori_shape=(H, W)))])
+        out = seg.test_step(batch)                                        # data_preprocessor + predict
+        assert (out[0].pred_sem_seg.data[0].cpu().numpy() == g['labels']).mean() >= 0.999
+    pp = seg.postprocess_result(lg, None)
+    assert (pp[0].cpu().numpy() == g['labels']).mean() >= 0.999
+    assert seg.num_queries == 8 and seg.num_classes == 6 and seg.net.visual.patch_size == (16, 16)
+    assert seg.net.visual.outlier_suppressor.top_k == 30                  # test_outlier_attr.py:19-22
+
+
+def test_segmentor_cls_token_lambda_and_resize(gold):
+    """segearth_segmentor.Segmentor (demo.py) with the cls_token_lambda bias, and an ori_shape resize."""
+    seg, g = _segmentor(gold, cls_name='Seg', cls_token_lambda=-0.3, model_type='SegEarth')
+    cfg = get_model_config('ViT-tiny-16')
+    v = cfg['vision_cfg']
+    vis = {k[len('visual.'):]: t for k, t in synthetic_clip_state_dict(cfg, 0, text_tower=False).items()
+           if k.startswith('visual.')}
+    orc = O.SegOracle(vis, torch.from_numpy(g['query_features']), g['query_idx'].tolist(), layers=v['layers'],
+                      heads=v['heads'], patch=16, prob_thd=0.1, bg_idx=5, cls_token_lambda=-0.3, model_type='SegEarth',
+                      upsampler=('jbu_one', synthetic_jbu_state_dict('jbu_one', 64, 1)))
+    x = torch.from_numpy(synth.preprocess(synth.voronoi_scene(224, 250, 9)))[None]
+    with torch.no_grad():
+        ref = orc.forward_slide(x)
+        ref_small = orc.forward_slide(x, ori_shape=(150, 170))
+    lg = seg.forward_slide(x.cuda(), [dict(ori_shape=(224, 250))])
+    assert (lg.cpu() - ref).abs().max().item() < 1e-4
+    lg2 = seg.forward_slide(x.cuda(), [dict(ori_shape=(150, 170))])
+    assert (lg2.cpu() - ref_small).abs().max().item() < 1e-4
+
+
+def test_encode_image_and_upsampler_modules(gold):
+    """open_clip.create_model(...).encode_image and get_upsampler(...).forward with the reference call forms."""
+    from clip_decontamination_b200.open_clip import create_model
+    from clip_decontamination_b200.simfeatup_dev.upsamplers import get_upsampler
+    g = gold('vit_tiny')
+    net = create_model('ViT-tiny-16', pretrained=None, precision='fp32').cuda()
+    img = torch.from_numpy(synth.preprocess(synth.voronoi_scene(224, 448, 5)))
+    x = torch.stack([img[:, :, :224], img[:, :, 224:]]).cuda()
+    cls, tok = net.encode_image(x, 'Experimental', True, output_cls_token=True)
+    assert np.abs(tok.cpu().numpy() - g['plain_tokens']).max() < 2e-4
+    gj = gold('jbu_one_c32')
+    up = get_upsampler('jbu_one', 32)
+    up.load_state_dict(synthetic_jbu_state_dict('jbu_one', 32, 1), strict=True)
+    up.precision = 'fp32'
+    guid = torch.from_numpy(synth.preprocess(synth.voronoi_scene(224, 224, 5)))[None].cuda()
+    out = up.cuda()(torch.from_numpy(gj['source']).cuda(), guid)
+    assert out.shape == (1, 32, 224, 224)
+    assert np.abs(out.cpu().numpy()[:, :, ::4, ::4] - gj['out']).max() < 1e-4
+
+
+def test_sharded_evaluate_single_rank(gold):
+    from clip_decontamination_b200.dist import evaluate
+    K = 6
+    preds = [torch.from_numpy(synth.synthetic_labels(80, 60, K, 30 + i) % K) for i in range(3)]
+    gts = [torch.from_numpy(synth.synthetic_labels(80, 60, K, 40 + i)) for i in range(3)]
+    res = evaluate(lambda p: p.cuda(), preds, gts, K, torch.device('cuda'))
+    ref = sum(torch.stack(O.intersect_and_union(p.long(), g.long(), K)) for p, g in zip(preds, gts))
+    assert torch.equal(res['hist'].cpu(), ref)
+    assert abs(res['mIoU'] - O.iou_metrics(*ref)['mIoU']) < 1e-9

@@ -27,7 +27,7 @@ def cuda(t, dtype=None):
 
 
 # ------------------------------------------------------------------ GEMM --------------------------
-GEMM_SHAPES = [(128, 128, 64), (128, 64, 128), (256, 128, 192), (300, 200, 192), (77, 121, 128), (1000, 48, 64),
+GEMM_SHAPES = [(128, 128, 64), (200, 96, 32), (130, 64, 88), (128, 64, 128), (256, 128, 192), (300, 200, 192), (77, 121, 128), (1000, 48, 64),
                (3152, 2304, 768), (3152, 768, 3072), (3136, 768, 768), (3152, 512, 768), (9000, 128, 128)]
 
 
@@ -106,8 +106,8 @@ def test_gemm_fp32_mode(ops):
 
 def test_gemm_rejects_bad_k(ops):
     from clip_decontamination_b200._lib import ClipSegError
-    A = torch.zeros(128, 72, dtype=torch.bfloat16, device='cuda')
-    B = torch.zeros(64, 72, dtype=torch.bfloat16, device='cuda')
+    A = torch.zeros(128, 68, dtype=torch.bfloat16, device='cuda')
+    B = torch.zeros(64, 68, dtype=torch.bfloat16, device='cuda')
     with pytest.raises(ClipSegError):
         ops.gemm(A, B, torch.empty(128, 64, device='cuda'))
 
@@ -142,7 +142,8 @@ def test_patchify_matches_conv(ops, ps, ch, cw, pt, pl):
     ops.patchify(img.cuda(), torch.tensor(wins, dtype=torch.int32).cuda(), ch, cw, pt, pl, ps, out)
     got = out.cpu()[:, :3 * ps * ps] @ Wc.reshape(width, -1).t()
     assert (got - ref).abs().max().item() < 1e-3
-    assert out[:, 3 * ps * ps:].abs().max().item() == 0
+    if Kp > 3 * ps * ps:
+        assert out[:, 3 * ps * ps:].abs().max().item() == 0
 
 
 def test_layernorm_and_embed(ops):
