@@ -117,7 +117,7 @@ def test_jbu_small(gold, name, precision, tol):
     d2 = g['kernel0'].shape[1]
     k0 = taps['jbu_kernels'][0].float().cpu().view(1, 28, 28, -1)[..., :d2].permute(0, 3, 1, 2)
     print(f'[{name} {precision}] kernel0 max|d|={np.abs(k0.numpy() - g["kernel0"]).max():.3e}')
-    assert np.abs(k0.numpy() - g['kernel0']).max() < (1e-5 if precision == 'fp32' else 3e-3)
+    assert np.abs(k0.numpy() - g['kernel0']).max() < (1e-5 if precision == "fp32" else 6e-3)
     errs = [np.abs(nchw(taps['jbu_stages'][0], 28).numpy() - g['stage0']).max(),
             np.abs(nchw(taps['jbu_stages'][1], 56).numpy() - g['stage1']).max(),
             np.abs(nchw(taps['jbu_stages'][2], 112).numpy()[:, :, ::2, ::2] - g['stage2']).max(),
