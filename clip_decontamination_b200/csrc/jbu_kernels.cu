@@ -286,6 +286,9 @@ static int launch_range_kernel(const float* proj, const float* guid, int n_crops
   return 0;
 }
 
+int cseg_jbu_adaptive_conv_mma(const bf16* hr, int n_crops, int H2, int W2, int C, const bf16* kern, int ldk,
+                               int radius, bf16* dst, cudaStream_t st);
+
 template <typename T>
 static int launch_apply(const void* src, int n_crops, int h, int w, int C, const void* kern, int ldk, int radius,
                         void* dst, void* hr_scratch, cudaStream_t st) {
@@ -294,6 +297,9 @@ static int launch_apply(const void* src, int n_crops, int h, int w, int C, const
   bicubic2x_kernel<T><<<(int)std::min<long long>((tot_b + 255) / 256, (long long)sm_count() * 32), 256, 0, st>>>(
       (const T*)src, n_crops, h, w, C, (T*)hr_scratch);
   CSEG_LAUNCH_CHECK("jbu_bicubic2x");
+  if (sizeof(T) == 2 && C % 128 == 0 && ldk % 8 == 0 && ldk <= 128)   // tensor-core banded GEMM path
+    return cseg_jbu_adaptive_conv_mma((const bf16*)hr_scratch, n_crops, H2, W2, C, (const bf16*)kern, ldk, radius,
+                                      (bf16*)dst, st);
   const long long tot = (long long)n_crops * H2 * W2 * (C / 8);
   const int blocks = (int)std::min<long long>((tot + 255) / 256, (long long)sm_count() * 64);
   if (radius == 5)

@@ -486,6 +486,9 @@ __global__ void cls_debias_kernel(const float* __restrict__ tok, int n_crops, in
 
 }  // namespace
 
+int cseg_attention_mma(const bf16* qkv, int n_crops, int L, int heads, int head_dim, int mode, const float* simmap,
+                       float simw, bf16* out, float* stats, cudaStream_t st);
+
 extern "C" {
 
 int cseg_preprocess_u8(const uint8_t* img, int H, int W, const float mean[3], const float std_[3], float* out,
@@ -562,6 +565,11 @@ int cseg_attention(int dtype, const void* qkv, int n_crops, int L, int heads, in
   CSEG_REQUIRE(mode >= CSEG_ATTN_STD && mode <= CSEG_ATTN_MASKCLIP, "attention: unknown mode %d", mode);
   CSEG_REQUIRE(stats == nullptr || mode == CSEG_ATTN_STD, "attention: stats only with CSEG_ATTN_STD");
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == CSEG_BF16) {   // tensor-core kernel; returns 1 for shapes it does not cover
+    const int rc = cseg_attention_mma((const bf16*)qkv, n_crops, L, heads, head_dim, mode, simmap, sim_weight, (bf16*)out,
+                                      stats, st);
+    if (rc <= 0) return rc;
+  }
   if (dtype == CSEG_BF16 && head_dim == 64)
     return launch_attention<bf16, 64>(qkv, n_crops, L, heads, mode, simmap, sim_weight, out, stats, st);
   if (dtype == CSEG_F32 && head_dim == 64)

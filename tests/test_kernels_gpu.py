@@ -276,6 +276,33 @@ def test_cls_debias(ops, factor):
     assert (cu.cpu() - cls).abs().max().item() < 2e-6
 
 
+@pytest.mark.parametrize('dtype,C,radius,h', [(torch.bfloat16, 128, 5, 14), (torch.bfloat16, 256, 3, 20),
+                                              (torch.bfloat16, 128, 5, 56), (torch.float32, 16, 5, 14),
+                                              (torch.bfloat16, 64, 3, 14)])
+def test_jbu_apply(ops, dtype, C, radius, h):
+    """bicubic x2 + reflect pad + adaptive conv (upsamplers.py:268-274) on random sources / kernels.
+    C % 128 == 0 in bf16 takes the tensor-core banded-GEMM kernel, the rest the CUDA-core kernel."""
+    n, w = 2, h + 3
+    d = 2 * radius + 1
+    ldk = 128 if radius == 5 else 64
+    src = torch.randn(n, C, h, w, generator=_g(1)).to(dtype)
+    kern = torch.zeros(n, 2 * h, 2 * w, ldk)
+    kern[..., :d * d] = torch.softmax(torch.randn(n, 2 * h, 2 * w, d * d, generator=_g(2)), -1)
+    kern = kern.to(dtype)
+    hr = F.interpolate(src.float(), size=(2 * h, 2 * w), mode='bicubic', align_corners=False)
+    if dtype == torch.bfloat16:
+        hr = hr.bfloat16().float()          # the kernel stores the high-res source in the storage dtype
+    ref = O.adaptive_conv(F.pad(hr, [radius] * 4, mode='reflect'),
+                          kern.float()[..., :d * d].reshape(n, 2 * h, 2 * w, d, d))
+    s_cl = src.permute(0, 2, 3, 1).contiguous().cuda()
+    dst = torch.empty((n, 2 * h, 2 * w, C), device='cuda', dtype=dtype)
+    hrs = torch.empty_like(dst)
+    ops.jbu_apply(s_cl, n, h, w, C, kern.reshape(-1, ldk).cuda(), radius, dst, hrs)
+    got = dst.float().cpu().permute(0, 3, 1, 2)
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert (got - ref).abs().max().item() < tol
+
+
 # ------------------------------------------------------------------ segmentor tail ----------------
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('Q', [2, 8, 16, 20])
