@@ -238,7 +238,7 @@ template <int NKB>
 int launch(const bf16* qkv, int n_crops, int L, int heads, int mode, const float* simmap, float simw, bf16* out,
            float* stats, cudaStream_t st) {
   const int smem = 3 * NKB * 8 * RSTRIDE;
-  CSEG_CUDA(cudaFuncSetAttribute(attention_mma_kernel<NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CSEG_SET_SMEM(attention_mma_kernel<NKB>, smem);
   attention_mma_kernel<NKB><<<n_crops * heads, AWARPS * 32, smem, st>>>(qkv, L, heads, mode, simmap, simw, out, stats);
   CSEG_LAUNCH_CHECK("attention_mma");
   return 0;

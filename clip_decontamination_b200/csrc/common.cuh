@@ -39,6 +39,17 @@ extern std::atomic<long long> g_cseg_launches;
     if (e_ != cudaSuccess) CSEG_FAIL(CSEG_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
 
+// raise a kernel's dynamic shared-memory limit only when needed (no runtime call on the steady-state
+// path, so launch sequences can be captured into CUDA graphs)
+#define CSEG_SET_SMEM(kernel, bytes)                                                                      \
+  do {                                                                                                    \
+    static int cur_ = 0;                                                                                  \
+    if ((int)(bytes) > cur_) {                                                                            \
+      CSEG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      cur_ = (int)(bytes);                                                                                \
+    }                                                                                                     \
+  } while (0)
+
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);

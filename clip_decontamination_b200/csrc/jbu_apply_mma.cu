@@ -163,10 +163,10 @@ int cseg_jbu_adaptive_conv_mma(const bf16* hr, int n_crops, int H2, int W2, int 
   dim3 grid(cdiv(W2, TX), cdiv(H2, RW), n_crops * (C / CS));
   CSEG_REQUIRE(grid.z <= 65535, "jbu_apply(bf16): too many crop x channel slabs (%u)", grid.z);
   if (radius == 5) {
-    CSEG_CUDA(cudaFuncSetAttribute(adaptive_conv_mma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CSEG_SET_SMEM(adaptive_conv_mma_kernel<5>, SMEM_BYTES);
     adaptive_conv_mma_kernel<5><<<grid, 128, SMEM_BYTES, st>>>(hr, H2, W2, C, kern, ldk, dst);
   } else {
-    CSEG_CUDA(cudaFuncSetAttribute(adaptive_conv_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CSEG_SET_SMEM(adaptive_conv_mma_kernel<3>, SMEM_BYTES);
     adaptive_conv_mma_kernel<3><<<grid, 128, SMEM_BYTES, st>>>(hr, H2, W2, C, kern, ldk, dst);
   }
   CSEG_LAUNCH_CHECK("jbu_adaptive_conv_mma");

@@ -146,45 +146,7 @@ __device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
   c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) bicubic2x_kernel(const T* __restrict__ src, int n_crops, int h, int w, int C,
-                                                        T* __restrict__ dst) {
-  const int H2 = 2 * h, W2 = 2 * w;
-  const long long total = (long long)n_crops * H2 * W2 * C;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C);
-    long long r = idx / C;
-    const int X = (int)(r % W2);
-    r /= W2;
-    const int Y = (int)(r % H2), crop = (int)(r / H2);
-    const float sy = ((float)Y + 0.5f) * 0.5f - 0.5f, sx = ((float)X + 0.5f) * 0.5f - 0.5f;
-    const int iy = (int)floorf(sy), ix = (int)floorf(sx);
-    float cy[4], cx[4];
-    cubic_coeffs(sy - (float)iy, cy);
-    cubic_coeffs(sx - (float)ix, cx);
-    const T* sb = src + (size_t)crop * h * w * C + c;
-    float acc = 0.f;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int yy = min(max(iy - 1 + a, 0), h - 1);
-      float row = 0.f;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int xx = min(max(ix - 1 + b, 0), w - 1);
-        row = fmaf(cx[b], to_f32(sb[((size_t)yy * w + xx) * C]), row);
-      }
-      acc = fmaf(cy[a], row, acc);
-    }
-    dst[idx] = from_f32<T>(acc);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// adaptive conv over the (virtually) reflect-padded high-res source:
-//   out[p, c] = sum_t hr[reflect(p + t)][c] * kern[p][t]
-// One thread per (pixel, 8-channel group); threads of a warp share the pixel's weights through L1.
-// ---------------------------------------------------------------------------------------------
+// 8-channel vector load/store helpers (16 B for bf16, 2 x 16 B for fp32)
 template <typename T> struct V8;
 template <> struct V8<bf16> {
   static __device__ __forceinline__ void ld(const bf16* p, float (&v)[8]) {
@@ -216,6 +178,82 @@ template <> struct V8<float> {
   }
 };
 
+// One thread = one source pixel (y, x) x 8 channels -> the 2x2 output block (2y..2y+1, 2x..2x+1).
+// Output row 2y samples source rows y-2..y+1 with t = 0.75, row 2y+1 samples y-1..y+2 with t = 0.25
+// (src = (dst + 0.5) / 2 - 0.5), so the block needs a clamped 5x5 neighbourhood: 25 16-byte loads for
+// 4 outputs instead of 16 scalar loads per output.  Horizontal pass first, then vertical (torch order).
+template <typename T>
+__global__ void __launch_bounds__(256) bicubic2x_kernel(const T* __restrict__ src, int n_crops, int h, int w, int C,
+                                                        T* __restrict__ dst) {
+  const int cg = C / 8;
+  const long long total = (long long)n_crops * h * w * cg;
+  float cA[4], cB[4];
+  cubic_coeffs(0.75f, cA);   // even output index
+  cubic_coeffs(0.25f, cB);   // odd output index
+  const int W2 = 2 * w;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % cg);
+    long long r = idx / cg;
+    const int x = (int)(r % w);
+    r /= w;
+    const int y = (int)(r % h), crop = (int)(r / h);
+    const T* sb = src + (size_t)crop * h * w * C + g * 8;
+    float o[2][2][8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[a][b][e] = 0.f;
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy) {
+      const int yy = min(max(y + dy, 0), h - 1);
+      float he[8], ho[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { he[e] = 0.f; ho[e] = 0.f; }
+#pragma unroll
+      for (int dx = -2; dx <= 2; ++dx) {
+        const int xx = min(max(x + dx, 0), w - 1);
+        float v[8];
+        V8<T>::ld(sb + ((size_t)yy * w + xx) * C, v);
+        if (dx <= 1) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) he[e] = fmaf(cA[dx + 2], v[e], he[e]);
+        }
+        if (dx >= -1) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ho[e] = fmaf(cB[dx + 1], v[e], ho[e]);
+        }
+      }
+      if (dy <= 1) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          o[0][0][e] = fmaf(cA[dy + 2], he[e], o[0][0][e]);
+          o[0][1][e] = fmaf(cA[dy + 2], ho[e], o[0][1][e]);
+        }
+      }
+      if (dy >= -1) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          o[1][0][e] = fmaf(cB[dy + 1], he[e], o[1][0][e]);
+          o[1][1][e] = fmaf(cB[dy + 1], ho[e], o[1][1][e]);
+        }
+      }
+    }
+    T* ob = dst + (size_t)crop * 4 * h * w * C + g * 8;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) V8<T>::st(ob + ((size_t)(2 * y + a) * W2 + 2 * x + b) * C, o[a][b]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// adaptive conv over the (virtually) reflect-padded high-res source:
+//   out[p, c] = sum_t hr[reflect(p + t)][c] * kern[p][t]
+// One thread per (pixel, 8-channel group); threads of a warp share the pixel's weights through L1.
+// ---------------------------------------------------------------------------------------------
 template <typename T, int R>
 __global__ void __launch_bounds__(256) adaptive_conv_kernel(const T* __restrict__ hr, int n_crops, int H2, int W2, int C,
                                                             const T* __restrict__ kern, int ldk, T* __restrict__ dst) {
@@ -278,7 +316,7 @@ static int launch_range_kernel(const float* proj, const float* guid, int n_crops
                                float inv2s2, void* kern, int ldk, cudaStream_t st) {
   constexpr int HS = 16 + 2 * R;
   const size_t smem = (size_t)32 * HS * HS * sizeof(float);
-  CSEG_CUDA(cudaFuncSetAttribute(range_kernel_kernel<T, R, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CSEG_SET_SMEM((range_kernel_kernel<T, R, 32>), smem);
   dim3 grid(cdiv(gw, 16), cdiv(gh, 16), n_crops);
   range_kernel_kernel<T, R, 32><<<grid, 256, smem, st>>>(proj, (const float4*)guid, gh, gw, pos_temp, inv2s2, (T*)kern,
                                                          ldk);
@@ -293,7 +331,7 @@ template <typename T>
 static int launch_apply(const void* src, int n_crops, int h, int w, int C, const void* kern, int ldk, int radius,
                         void* dst, void* hr_scratch, cudaStream_t st) {
   const int H2 = 2 * h, W2 = 2 * w;
-  const long long tot_b = (long long)n_crops * H2 * W2 * C;
+  const long long tot_b = (long long)n_crops * h * w * (C / 8);
   bicubic2x_kernel<T><<<(int)std::min<long long>((tot_b + 255) / 256, (long long)sm_count() * 32), 256, 0, st>>>(
       (const T*)src, n_crops, h, w, C, (T*)hr_scratch);
   CSEG_LAUNCH_CHECK("jbu_bicubic2x");

@@ -234,7 +234,7 @@ static int launch_norm_sim(const void* feats, int ldf, int n_crops, int hw, int 
   const int blocks = (int)std::min<long long>((rows * 8 + 255) / 256, (long long)sm_count() * 8);
 #define NS_LAUNCH(QT)                                                                                          \
   do {                                                                                                         \
-    CSEG_CUDA(cudaFuncSetAttribute(norm_sim_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    CSEG_SET_SMEM((norm_sim_kernel<T, QT>), smem);                                                              \
     norm_sim_kernel<T, QT><<<blocks, 256, smem, st>>>((const T*)feats, ldf, rows, hw, D, text, Q, cls_bias, logits); \
   } while (0)
   if (Q <= 8) NS_LAUNCH(8);

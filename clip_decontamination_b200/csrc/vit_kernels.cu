@@ -549,7 +549,7 @@ static int launch_attention(const void* qkv, int n_crops, int L, int heads, int 
   constexpr int LDS = HD + (sizeof(T) == 2 ? 2 : 1);
   const size_t smem = (((size_t)3 * L * LDS * sizeof(T) + 15) & ~(size_t)15) + (size_t)ATT_WARPS * ATT_JMAX * 32 * 4;
   CSEG_REQUIRE(smem <= 227 * 1024, "attention: L=%d head_dim=%d needs %zu B shared memory", L, HD, smem);
-  CSEG_CUDA(cudaFuncSetAttribute(attention_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CSEG_SET_SMEM((attention_kernel<T, HD>), smem);
   attention_kernel<T, HD><<<n_crops * heads, ATT_WARPS * 32, smem, st>>>((const T*)qkv, L, heads, mode, simmap, simw,
                                                                          (T*)out, stats);
   CSEG_LAUNCH_CHECK("attention");

@@ -327,6 +327,9 @@ class SegEngine:
         self.jbu_chunk = jbu_chunk
         self.ws = Workspace(self.device)
         self._win_cache: Dict[Tuple[int, int], Tuple[torch.Tensor, list]] = {}
+        self._graphs: Dict[Tuple[int, int], dict] = {}
+        self.mean = [122.771, 116.746, 104.094]          # segmentor.py:64-67 (RGB)
+        self.std = [68.501, 66.632, 70.323]
 
     def _windows(self, H: int, W: int):
         key = (H, W)
@@ -398,3 +401,50 @@ class SegEngine:
                          out_h, out_w, self.query_idx, self.K, self.logit_scale, self.prob_thd, self.bg_idx,
                          labels, probs, avg)
         return labels, probs, avg
+
+    # ---- CUDA-graph replay of the whole per-image launch sequence --------------------------------
+    def graph(self, H: int, W: int) -> dict:
+        """Capture preprocess_u8 -> segment for an H x W uint8 image once (a few hundred launches) and
+        replay it afterwards: the per-launch host cost (Python, ctypes, tensor-map encodes) is paid at
+        capture time only.  Static buffers: 'u8' [H,W,3] uint8 BGR in, 'labels' [H,W] uint8 out."""
+        key = (H, W)
+        if key in self._graphs:
+            return self._graphs[key]
+        st = dict(u8=torch.zeros((H, W, 3), dtype=torch.uint8, device=self.device),
+                  img=torch.empty((3, H, W), dtype=torch.float32, device=self.device),
+                  labels=torch.empty((H, W), dtype=torch.uint8, device=self.device))
+
+        def run():
+            ops.preprocess_u8(st['u8'], self.mean, self.std, st['img'])
+            self.segment(st['img'], None, labels=st['labels'])
+
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            run()                                    # warm-up: sizes every workspace before the capture
+            run()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            run()
+        st['graph'] = g
+        self._graphs[key] = st
+        return st
+
+    def segment_u8(self, img_hwc_bgr_u8: torch.Tensor, labels_out: Optional[torch.Tensor] = None,
+                   use_graph: bool = True) -> torch.Tensor:
+        """uint8 HWC BGR image (host pinned or device) -> uint8 labels [H,W] on the device."""
+        H, W, _ = img_hwc_bgr_u8.shape
+        if not use_graph:
+            x = img_hwc_bgr_u8.to(self.device, non_blocking=True)
+            img = ops.preprocess_u8(x.contiguous(), self.mean, self.std)
+            return self.segment(img, None, labels=labels_out)[0]
+        st = self.graph(H, W)
+        st['u8'].copy_(img_hwc_bgr_u8, non_blocking=True)        # H2D (or D2D) into the static input
+        st['graph'].replay()
+        if labels_out is not None:
+            labels_out.copy_(st['labels'], non_blocking=True)
+            return labels_out
+        return st['labels']

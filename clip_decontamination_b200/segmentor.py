@@ -269,19 +269,11 @@ class SegmentorEx(BaseSegmentor):
         return data_samples
 
     @torch.no_grad()
-    def predict_u8(self, img_hwc_bgr_u8, labels_out=None):
-        """Input side fused (N1): uint8 HWC BGR image (host or device) -> uint8 labels [H,W] on the device.
-        Equivalent to data_preprocessor + predict for one image."""
-        from . import ops
-        x = img_hwc_bgr_u8
-        if not x.is_cuda:
-            x = x.to(self._device, non_blocking=True)
-        pp = self.data_preprocessor
-        mean = [122.771, 116.746, 104.094]
-        std = [68.501, 66.632, 70.323]
-        img = ops.preprocess_u8(x.contiguous(), mean, std)
-        labels, _, _ = self.engine.segment(img, None, labels=labels_out)
-        return labels
+    def predict_u8(self, img_hwc_bgr_u8, labels_out=None, use_graph=True):
+        """Input side fused (N1): uint8 HWC BGR image (pinned host or device) -> uint8 labels [H,W] on the
+        device.  Equivalent to data_preprocessor + predict for one image; the launch sequence is replayed
+        from a CUDA graph captured on first use of each image shape."""
+        return self.engine.segment_u8(img_hwc_bgr_u8, labels_out, use_graph)
 
     def postprocess_result(self, seg_logits, data_samples):
         """segmentor.py:475-499 on given averaged logits [B,Q,H,W] (runs the fused kernel with one

@@ -212,7 +212,8 @@ def test_attention_modes(ops, mode, dtype, L, hd):
     stats = torch.zeros((n, heads, 2, L - 1), device='cuda') if mode == 'STD' else None
     ops.attention(qkv.cuda(), n, L, heads, hd, ATTN[mode], out, simmap=sim.cuda() if sim is not None else None,
                   sim_weight=0.7, stats=stats)
-    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    # bf16: P is rounded to bf16 before P.V; SCLIP / SegEarth sum 2-3 softmaxes (row sums 2-3)
+    tol = 2e-5 if dtype == torch.float32 else (2e-2 if mode not in ('SCLIP', 'SegEarth') else 5e-2)
     assert (out.float().cpu() - ref).abs().max().item() < tol
     if stats is not None:
         s = stats.cpu()
