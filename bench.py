@@ -241,6 +241,7 @@ def main():
     step_eager()
     launches_per_step = _lib.launch_count() - l0       # kernels per step (a graph replay issues the same set)
     records = {}
+    shape_records = {}
     orig = {}
     work = {}
 
@@ -251,6 +252,10 @@ def main():
             r = fn(*a, **k)
             e.record()
             records.setdefault(name, []).append((s, e, workfn(*a, **k) if workfn else None))
+            if name == 'gemm':      # per-shape split of the GEMM class (diagnostic)
+                A, B = a[0], a[1]
+                key = 'gemm[M%dxN%dxK%d]' % (k.get('M') or A.shape[0], k.get('N') or B.shape[0], k.get('K') or A.shape[1])
+                shape_records.setdefault(key, []).append((s, e))
             return r
         return inner
 
@@ -288,6 +293,8 @@ def main():
         setattr(ops, nm, orig[nm])
     totals = {nm: sum(s.elapsed_time(e) for s, e, _ in recs) for nm, recs in records.items()}
     breakdown = {nm: round(v / T, 4) for nm, v in sorted(totals.items(), key=lambda kv: -kv[1])}
+    gemm_shapes = {k: [len(v) // T, round(sum(s.elapsed_time(e) for s, e in v) / T, 4)] for k, v in shape_records.items()}
+    shape_records.clear()
     dominant = max((nm for nm in totals if nm in workfns), key=lambda nm: totals[nm])
     records.clear()
     # ---- timed region: value (inputs resident in HBM, CUDA-graph replay of the launch sequence) -----
@@ -315,7 +322,8 @@ def main():
     roofline = dict(kernel=dominant, bound=bound, achieved=achieved, peak=peak, unit=runit, frac=achieved / peak,
                     traffic=None, launches_timed=len(dom_ms), avg_launch_ms=tot_ms / max(1, len(dom_ms)),
                     share_of_step=tot_ms / ms_eager, eager_ms_per_step=ms_eager / args.steps,
-                    peak_source=peaks['src'], per_tile_ms_by_kernel=breakdown)
+                    peak_source=peaks['src'], per_tile_ms_by_kernel=breakdown,
+                    gemm_calls_and_ms_per_tile_by_shape=gemm_shapes)
 
     # ---- e2e: host buffers in, labels out, through the segmentor API -------------------------------
     for _ in range(2):
