@@ -277,7 +277,7 @@ def main():
         return ('hbm', float(cl.numel() * 4 + H * W))
 
     def rk_work(proj, guid, n, gh, gw, radius, rt, ss, kern):
-        return ('hbm', float(n * gh * gw * (32 * 4 + 16 + kern.shape[-1] * esize)))
+        return ('hbm', float(n * gh * gw * (32 * proj.element_size() + 16 + kern.shape[-1] * esize)))
 
     workfns = dict(gemm=gemm_work, jbu_apply=apply_work, attention=attn_work, norm_sim=nsim_work,
                    accum_argmax=accum_work, jbu_range_kernel=rk_work)

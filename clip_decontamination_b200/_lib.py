@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libclipseg.so')
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_QUICKGELU = 0, 1, 2
 ATTN = dict(STD=0, Experimental=1, SCLIP=2, ClearCLIP=3, SFP=4, vanilla=5, SegEarth=6, MaskCLIP=7)
 
@@ -39,8 +39,8 @@ SIGNATURES = {
     'cseg_outlier_suppress': (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _f, _p, _p, _p]),
     'cseg_cls_debias': (_i, [_p, _i, _i, _i, _f, _i, _p, _i, _p, _p]),
     'cseg_jbu_guidance': (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
-    'cseg_jbu_range_proj': (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p]),
-    'cseg_jbu_range_kernel': (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _f, _i, _p, _i, _p]),
+    'cseg_jbu_range_proj': (_i, [_p, _i, _i, _p, _p, _p, _p, _i, _p, _p]),
+    'cseg_jbu_range_kernel': (_i, [_i, _p, _p, _i, _i, _i, _i, _i, _f, _f, _i, _p, _i, _p]),
     'cseg_jbu_apply': (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
     'cseg_norm_sim': (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
     'cseg_accum_argmax': (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i, _f, _f, _i,

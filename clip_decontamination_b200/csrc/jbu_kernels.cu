@@ -287,6 +287,11 @@ __global__ void __launch_bounds__(256) adaptive_conv_kernel(const T* __restrict_
 
 }  // namespace
 
+int cseg_jbu_range_proj_f16(const float* guid, int n_pix, const float* w0, const float* b0, const float* w3,
+                            const float* b3, void* proj, cudaStream_t st);
+int cseg_jbu_range_kernel_mma(const void* proj_f16, const float* guid, int n_crops, int gh, int gw, int radius,
+                              float pos_temp, float inv2s2, void* kern, int ldk, cudaStream_t st);
+
 extern "C" {
 
 int cseg_jbu_guidance(const float* img, int H, int W, const int32_t* windows, int n_crops, int crop_h, int crop_w,
@@ -300,11 +305,13 @@ int cseg_jbu_guidance(const float* img, int H, int W, const int32_t* windows, in
 }
 
 int cseg_jbu_range_proj(const float* guid, int n_pix, int key_dim, const float* w0, const float* b0, const float* w3,
-                        const float* b3, float* proj, void* stream) {
+                        const float* b3, int proj_dtype, void* proj, void* stream) {
   CSEG_REQUIRE(n_pix > 0, "jbu_range_proj: empty");
   CSEG_REQUIRE(key_dim == 32, "jbu_range_proj: key_dim=%d (only 32, simfeatup_dev/upsamplers.py:282-308)", key_dim);
+  if (proj_dtype == CSEG_F16) return cseg_jbu_range_proj_f16(guid, n_pix, w0, b0, w3, b3, proj, (cudaStream_t)stream);
+  CSEG_REQUIRE(proj_dtype == CSEG_F32, "jbu_range_proj: proj_dtype must be CSEG_F32 or CSEG_F16");
   range_proj_kernel<32><<<cdiv(n_pix, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)guid, n_pix, w0, b0, w3, b3,
-                                                                            proj);
+                                                                            (float*)proj);
   CSEG_LAUNCH_CHECK("jbu_range_proj");
   return 0;
 }
@@ -352,8 +359,9 @@ static int launch_apply(const void* src, int n_crops, int h, int w, int C, const
 
 extern "C" {
 
-int cseg_jbu_range_kernel(const float* proj, const float* guid, int n_crops, int gh, int gw, int key_dim, int radius,
-                          float range_temp, float sigma_spatial, int out_dtype, void* kern, int ldk, void* stream) {
+int cseg_jbu_range_kernel(int proj_dtype, const void* proj_v, const float* guid, int n_crops, int gh, int gw, int key_dim,
+                          int radius, float range_temp, float sigma_spatial, int out_dtype, void* kern, int ldk,
+                          void* stream) {
   CSEG_REQUIRE(n_crops > 0 && gh > radius && gw > radius, "jbu_range_kernel: grid %dx%d too small for radius %d", gh, gw, radius);
   CSEG_REQUIRE(key_dim == 32, "jbu_range_kernel: key_dim=%d (only 32)", key_dim);
   CSEG_REQUIRE(radius == 3 || radius == 5, "jbu_range_kernel: radius=%d (3 = jbu_stack, 5 = jbu_one)", radius);
@@ -363,6 +371,14 @@ int cseg_jbu_range_kernel(const float* proj, const float* guid, int n_crops, int
   const float pos_temp = fminf(fmaxf(expf(range_temp), 1e-4f), 1e4f);
   const float inv2s2 = 1.0f / (2.0f * sigma_spatial * sigma_spatial);
   cudaStream_t st = (cudaStream_t)stream;
+  if (proj_dtype == CSEG_F16) {   // tensor-core path
+    CSEG_REQUIRE(out_dtype == CSEG_BF16, "jbu_range_kernel: fp16 projections go with bf16 kernels");
+    const int rc = cseg_jbu_range_kernel_mma(proj_v, guid, n_crops, gh, gw, radius, pos_temp, inv2s2, kern, ldk, st);
+    if (rc == 1) CSEG_FAIL(CSEG_EUNSUPPORTED, "jbu_range_kernel(f16): radius=%d ldk=%d not covered (5/128, 3/64)", radius, ldk);
+    return rc;
+  }
+  CSEG_REQUIRE(proj_dtype == CSEG_F32, "jbu_range_kernel: proj_dtype must be CSEG_F32 or CSEG_F16");
+  const float* proj = (const float*)proj_v;
   if (out_dtype == CSEG_BF16) {
     if (radius == 5) return launch_range_kernel<bf16, 5>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, ldk, st);
     return launch_range_kernel<bf16, 3>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, ldk, st);

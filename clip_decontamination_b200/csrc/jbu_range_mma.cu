@@ -1,0 +1,216 @@
+// JBU range kernel on tensor cores (bf16 path of cseg_jbu_range_kernel).
+//
+//   logit[p][t=(i,j)] = pos_temp * <proj(reflect(p + t - R)), proj(p)>            (upsamplers.py:230-238)
+//   kern[p][t] = softmax_t(logit) * gauss(t) / max(sum_t softmax*gauss, 1e-7)    (:240-251,258-262)
+//
+// For 16 query pixels of one image row and one tap row i, the 16 x (16+2R) key.query products are a small
+// GEMM: S[16 queries, 8-position blocks] = Q[16, 32] . K[positions, 32]^T  -> mma.sync m16n8k16 with fp16
+// operands (the reference computes these projections in fp16 under autocast, segmentor.py:370) and fp32
+// accumulation.  Only the band 0 <= pos - query < D of each block is used.  The MMAs are so cheap that the
+// softmax is done in three passes over recomputed logits (max; sums; normalised write) instead of keeping
+// D*D values per pixel in registers.  Results are staged per warp in shared memory and written as full
+// 16-byte-vector rows of the [pixels, ldk] kernel matrix (taps, then the 3 guidance channels, then zeros).
+#include "common.cuh"
+#include <cuda_fp16.h>
+
+namespace {
+
+constexpr int TXR = 32, TYR = 8;   // CTA tile: 32 x 8 query pixels, one warp per row
+constexpr int KD = 32;             // projection width
+constexpr int PROW = KD * 2 + 16;  // bytes per staged position (padded: conflict-free ldmatrix)
+
+__device__ __forceinline__ int reflect1(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int R, int LDK>
+__global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __restrict__ proj,
+                                                             const float4* __restrict__ guid, int gh, int gw,
+                                                             float pos_temp, float inv2s2, bf16* __restrict__ kern) {
+  constexpr int D = 2 * R + 1, D2 = D * D;
+  constexpr int NB = (16 + 2 * R + 7) / 8;       // 8-position blocks per 16-query block
+  constexpr int HR = TYR + 2 * R;                // halo rows
+  constexpr int NPOS = 16 + NB * 8;              // staged positions per halo row
+  extern __shared__ __align__(16) uint8_t rsm[];
+  const uint32_t psm = (uint32_t)__cvta_generic_to_shared(rsm);
+  float* gauss = reinterpret_cast<float*>(rsm + HR * NPOS * PROW);
+  bf16* stage = reinterpret_cast<bf16*>(rsm + HR * NPOS * PROW + ((D2 * 4 + 15) & ~15));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+  const int crop = blockIdx.z, y0 = blockIdx.y * TYR, x0 = blockIdx.x * TXR;
+  const __half* pc = proj + (size_t)crop * gh * gw * KD;
+
+  for (int e = tid; e < HR * NPOS * 4; e += TYR * 32) {      // 4 x 16 B per position
+    const int ch = e & 3, pos = (e >> 2) % NPOS, hy = (e >> 2) / NPOS;
+    const int yy = reflect1(min(y0 - R + hy, gh - 1 + R), gh), xx = reflect1(min(x0 - R + pos, gw - 1 + R), gw);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(pc + ((size_t)yy * gw + xx) * KD + ch * 8));
+    *reinterpret_cast<uint4*>(rsm + (hy * NPOS + pos) * PROW + ch * 16) = v;
+  }
+  for (int t = tid; t < D2; t += TYR * 32) {                 // get_spatial_kernel: linspace(-1, 1, D)^2
+    const float dy = -1.f + 2.f * (t / D) / (D - 1), dx = -1.f + 2.f * (t % D) / (D - 1);
+    gauss[t] = __expf(-(dy * dy + dx * dx) * inv2s2);
+  }
+  __syncthreads();
+
+  const int y = y0 + warp;
+  bf16* st = stage + warp * 16 * LDK;
+  const int q = lane >> 3, rr = lane & 7;
+#pragma unroll 1
+  for (int xb = 0; xb < TXR / 16; ++xb) {
+    const int xq0 = x0 + xb * 16;
+    if (y >= gh || xq0 >= gw) break;                         // warp-uniform
+    uint32_t a[2][4];
+    {
+      const uint32_t base = psm + (uint32_t)(((warp + R) * NPOS + xb * 16 + R + (q & 1) * 8 + rr) * PROW + (q >> 1) * 16);
+      ldsm4(base, a[0]);
+      ldsm4(base + 32, a[1]);
+    }
+    float mx[2] = {-INFINITY, -INFINITY}, se[2] = {0.f, 0.f}, sg[2] = {0.f, 0.f}, inv[2] = {0.f, 0.f};
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll 1
+      for (int i = 0; i < D; ++i) {
+        const uint32_t rowb = psm + (uint32_t)(((warp + i) * NPOS + xb * 16 + rr) * PROW + q * 16);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          uint32_t b[4];
+          ldsm4(rowb + nb * 8 * PROW, b);
+          float S[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_f16(S, a[0], b[0], b[1]);
+          mma_f16(S, a[1], b[2], b[3]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int h = e >> 1, m = g + h * 8, j = nb * 8 + 2 * tig + (e & 1) - m;
+            if (j < 0 || j >= D) continue;
+            const float lg = S[e] * pos_temp;
+            if (pass == 0) {
+              mx[h] = fmaxf(mx[h], lg);
+            } else {
+              const float ex = __expf(lg - mx[h]);
+              const float gz = gauss[i * D + j];
+              if (pass == 1) {
+                se[h] += ex;
+                sg[h] = fmaf(ex, gz, sg[h]);
+              } else {
+                st[m * LDK + i * D + j] = __float2bfloat16_rn(ex * gz * inv[h]);
+              }
+            }
+          }
+        }
+      }
+      if (pass == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+          mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+        }
+      } else if (pass == 1) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          se[h] += __shfl_xor_sync(0xffffffffu, se[h], 1);
+          se[h] += __shfl_xor_sync(0xffffffffu, se[h], 2);
+          sg[h] += __shfl_xor_sync(0xffffffffu, sg[h], 1);
+          sg[h] += __shfl_xor_sync(0xffffffffu, sg[h], 2);
+          const float ise = 1.0f / se[h];
+          inv[h] = ise / fmaxf(sg[h] * ise, 1e-7f);           // softmax, then / sum(softmax*gauss).clamp(1e-7)
+        }
+      }
+    }
+    // guidance channels + zero padding (columns D2 .. LDK-1), then coalesced row stores
+    if (lane < 16) {
+      const int x = min(xq0 + lane, gw - 1);
+      const float4 gv = guid[((size_t)crop * gh + y) * gw + x];
+      bf16* o = st + lane * LDK + D2;
+      o[0] = __float2bfloat16_rn(gv.x);
+      o[1] = __float2bfloat16_rn(gv.y);
+      o[2] = __float2bfloat16_rn(gv.z);
+      for (int t = D2 + 3; t < LDK; ++t) st[lane * LDK + t] = __float2bfloat16_rn(0.f);
+    }
+    __syncwarp();
+    for (int e = lane; e < 16 * (LDK / 8); e += 32) {
+      const int px = e / (LDK / 8), v = e % (LDK / 8);
+      if (xq0 + px < gw)
+        *reinterpret_cast<uint4*>(kern + (((size_t)crop * gh + y) * gw + xq0 + px) * LDK + v * 8) =
+            *reinterpret_cast<const uint4*>(st + px * LDK + v * 8);
+    }
+    __syncwarp();
+  }
+}
+
+// range_proj (upsamplers.py:209-214) with fp16 output for the tensor-core range kernel
+__global__ void __launch_bounds__(256) range_proj_f16_kernel(const float4* __restrict__ guid, int n_pix,
+                                                             const float* __restrict__ w0, const float* __restrict__ b0,
+                                                             const float* __restrict__ w3, const float* __restrict__ b3,
+                                                             __half* __restrict__ proj) {
+  __shared__ float sw0[KD * 3], sb0[KD], sw3[KD * KD], sb3[KD];
+  for (int i = threadIdx.x; i < KD * 3; i += blockDim.x) sw0[i] = w0[i];
+  for (int i = threadIdx.x; i < KD * KD; i += blockDim.x) sw3[i] = w3[i];
+  for (int i = threadIdx.x; i < KD; i += blockDim.x) { sb0[i] = b0[i]; sb3[i] = b3[i]; }
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= n_pix) return;
+  const float4 gq = guid[pix];
+  float h[KD];
+#pragma unroll
+  for (int k = 0; k < KD; ++k) h[k] = gelu_erf(sw0[k * 3] * gq.x + sw0[k * 3 + 1] * gq.y + sw0[k * 3 + 2] * gq.z + sb0[k]);
+  uint4* o = reinterpret_cast<uint4*>(proj + (size_t)pix * KD);
+#pragma unroll
+  for (int k8 = 0; k8 < KD / 8; ++k8) {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float a = sb3[k8 * 8 + e];
+#pragma unroll
+      for (int j = 0; j < KD; ++j) a = fmaf(sw3[(k8 * 8 + e) * KD + j], h[j], a);
+      acc[e] = a;
+    }
+    uint4 u;
+    __half2* hp = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) hp[e] = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
+    o[k8] = u;
+  }
+}
+
+template <int R, int LDK>
+int launch(const __half* proj, const float* guid, int n_crops, int gh, int gw, float pos_temp, float inv2s2, bf16* kern,
+           cudaStream_t st) {
+  constexpr int D2 = (2 * R + 1) * (2 * R + 1), NB = (16 + 2 * R + 7) / 8, HR = TYR + 2 * R, NPOS = 16 + NB * 8;
+  const int smem = HR * NPOS * PROW + ((D2 * 4 + 15) & ~15) + TYR * 16 * LDK * 2;
+  CSEG_SET_SMEM((range_kernel_mma<R, LDK>), smem);
+  dim3 grid(cdiv(gw, TXR), cdiv(gh, TYR), n_crops);
+  range_kernel_mma<R, LDK><<<grid, TYR * 32, smem, st>>>(proj, (const float4*)guid, gh, gw, pos_temp, inv2s2, kern);
+  CSEG_LAUNCH_CHECK("jbu_range_kernel_mma");
+  return 0;
+}
+
+}  // namespace
+
+int cseg_jbu_range_proj_f16(const float* guid, int n_pix, const float* w0, const float* b0, const float* w3,
+                            const float* b3, void* proj, cudaStream_t st) {
+  range_proj_f16_kernel<<<cdiv(n_pix, 256), 256, 0, st>>>((const float4*)guid, n_pix, w0, b0, w3, b3, (__half*)proj);
+  CSEG_LAUNCH_CHECK("jbu_range_proj_f16");
+  return 0;
+}
+
+// returns 1 when (radius, ldk) is not covered
+int cseg_jbu_range_kernel_mma(const void* proj_f16, const float* guid, int n_crops, int gh, int gw, int radius,
+                              float pos_temp, float inv2s2, void* kern, int ldk, cudaStream_t st) {
+  if (radius == 5 && ldk == 128)
+    return launch<5, 128>((const __half*)proj_f16, guid, n_crops, gh, gw, pos_temp, inv2s2, (bf16*)kern, st);
+  if (radius == 3 && ldk == 64)
+    return launch<3, 64>((const __half*)proj_f16, guid, n_crops, gh, gw, pos_temp, inv2s2, (bf16*)kern, st);
+  return 1;
+}

@@ -282,7 +282,7 @@ class JBUEngine:
             npix = n * GH * GW
             guid = ws.get('guid', (npix, 4), f32)
             ops.jbu_guidance(img, windows, crop_h, crop_w, pad_top, pad_left, GH, GW, guid)
-            proj = ws.get('proj', (npix, 32), f32)
+            proj = ws.get('proj', (npix, 32), torch.float16 if cdt == torch.bfloat16 else f32)
             ops.jbu_range_proj(guid, npix, st['rp_w0'], st['rp_b0'], st['rp_w3'], st['rp_b3'], proj)
             kern = ws.get('kern', (npix, st['ldk']), cdt)
             ops.jbu_range_kernel(proj, guid, n, GH, GW, st['radius'], st['range_temp'], st['sigma'], kern)

@@ -9,9 +9,9 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import lib, check, F32, BF16
+from ._lib import lib, check, F32, BF16, F16
 
-_DT = {torch.float32: F32, torch.bfloat16: BF16}
+_DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 
 def _stream():
@@ -123,12 +123,13 @@ def jbu_guidance(img, windows, crop_h, crop_w, pad_top, pad_left, gh, gw, out):
 
 
 def jbu_range_proj(guid, n_pix, w0, b0, w3, b3, proj):
-    check(lib.cseg_jbu_range_proj(_ptr(guid), n_pix, 32, _ptr(w0), _ptr(b0), _ptr(w3), _ptr(b3), _ptr(proj), _stream()))
+    check(lib.cseg_jbu_range_proj(_ptr(guid), n_pix, 32, _ptr(w0), _ptr(b0), _ptr(w3), _ptr(b3), _dt(proj), _ptr(proj),
+                                  _stream()))
     return proj
 
 
 def jbu_range_kernel(proj, guid, n_crops, gh, gw, radius, range_temp, sigma_spatial, kern):
-    check(lib.cseg_jbu_range_kernel(_ptr(proj), _ptr(guid), n_crops, gh, gw, 32, radius, range_temp, sigma_spatial,
+    check(lib.cseg_jbu_range_kernel(_dt(proj), _ptr(proj), _ptr(guid), n_crops, gh, gw, 32, radius, range_temp, sigma_spatial,
                                     _dt(kern), _ptr(kern), kern.shape[-1], _stream()))
     return kern
 

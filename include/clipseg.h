@@ -34,7 +34,7 @@ extern "C" {
 #define CSEG_API
 #endif
 
-enum { CSEG_F32 = 0, CSEG_BF16 = 1 };
+enum { CSEG_F32 = 0, CSEG_BF16 = 1, CSEG_F16 = 2 /* JBU range projections only */ };
 enum { CSEG_OK = 0, CSEG_EINVAL = -1, CSEG_ECUDA = -2, CSEG_EUNSUPPORTED = -3 };
 /* epilogue activations of cseg_gemm */
 enum { CSEG_ACT_NONE = 0, CSEG_ACT_GELU = 1, CSEG_ACT_QUICKGELU = 2 };
@@ -125,14 +125,16 @@ CSEG_API int cseg_cls_debias(const float* tok, int n_crops, int L, int D, float 
 CSEG_API int cseg_jbu_guidance(const float* img_chw, int H, int W, const int32_t* windows, int n_crops,
                       int crop_h, int crop_w, int pad_top, int pad_left, int gh, int gw,
                       float* guid, void* stream);
-/* range_proj (:209-214): conv1x1(3->kd) . GELU . conv1x1(kd->kd); proj fp32 [n,gh,gw,kd] */
+/* range_proj (:209-214): conv1x1(3->kd) . GELU . conv1x1(kd->kd); proj [n,gh,gw,kd] in proj_dtype:
+ * CSEG_F32 (verification mode) or CSEG_F16 (tensor-core range kernel; the reference computes these in
+ * fp16 under autocast, segmentor.py:370). */
 CSEG_API int cseg_jbu_range_proj(const float* guid, int n_pix, int key_dim, const float* w0, const float* b0,
-                        const float* w3, const float* b3, float* proj, void* stream);
+                        const float* w3, const float* b3, int proj_dtype, void* proj, void* stream);
 /* get_range_kernel x get_spatial_kernel, renormalised (:230-251,258-262).  kern: T [n*gh*gw, ldk]
  * with columns [0,d*d) = combined kernel, [d*d, d*d+3) = guidance RGB (the fixup_proj input order,
  * :264), rest zero. */
-CSEG_API int cseg_jbu_range_kernel(const float* proj, const float* guid, int n_crops, int gh, int gw,
-                          int key_dim, int radius, float range_temp, float sigma_spatial,
+CSEG_API int cseg_jbu_range_kernel(int proj_dtype, const void* proj, const float* guid, int n_crops, int gh,
+                          int gw, int key_dim, int radius, float range_temp, float sigma_spatial,
                           int out_dtype, void* kern, int ldk, void* stream);
 /* bicubic x2 (align_corners=False, a=-0.75) + reflect pad + adaptive conv (:268-274, semantics of
  * adaptive_conv_py_simple :14-25).  src T [n, h, w, C] channel-last -> dst T [n, 2h, 2w, C];

@@ -8,7 +8,7 @@ src = torch.randn(n * 112 * 112, C, device=dev).bfloat16()
 kern = torch.rand(n * 224 * 224, 128, device=dev).bfloat16()
 dst = torch.empty(n * 224 * 224, C, device=dev, dtype=torch.bfloat16)
 hr = torch.empty_like(dst)
-proj = torch.randn(n * 224 * 224, 32, device=dev)
+proj = torch.randn(n * 224 * 224, 32, device=dev).half()
 guid = torch.randn(n * 224 * 224, 4, device=dev)
 text = torch.randn(6, C, device=dev)
 lg = torch.empty(n, 6, 224 * 224, device=dev)

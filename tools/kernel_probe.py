@@ -58,7 +58,7 @@ def main():
     hr = torch.empty_like(dst)
     ms = timeit(lambda: ops.jbu_apply(src, n, 112, 112, C, kern, 5, dst, hr), iters=3, warm=1)
     print(f'jbu_apply 112->224 n={n} C={C}: {ms:.3f} ms ({n * 224 * 224 * C * 121 * 2 / ms / 1e9:.1f} TFLOP/s fp32 FMA)')
-    proj = torch.randn(n * 224 * 224, 32, device=dev)
+    proj = torch.randn(n * 224 * 224, 32, device=dev).half()
     guid = torch.randn(n * 224 * 224, 4, device=dev)
     ms = timeit(lambda: ops.jbu_range_kernel(proj, guid, n, 224, 224, 5, 0.3, 1.0, kern), iters=3, warm=1)
     print(f'jbu_range_kernel 224 n={n}: {ms:.3f} ms')
