@@ -69,6 +69,18 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // exact-erf GELU (nn.GELU default) and QuickGELU (open_clip/transformer.py:35-38)
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 instead of
+// erff's branchy polynomial; used by the tensor-core GEMM epilogue, whose outputs are rounded to bf16.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == CSEG_ACT_GELU) return gelu_erf(x);

@@ -7,8 +7,8 @@
 // the 1x1 convolutions of the reference (open_clip/transformer.py:204,211-215,560,770;
 // simfeatup_dev/upsamplers.py:218-223,325).
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
-// (one lane), warps 2..5 = epilogue (TMEM lane group = warp % 4).  One output tile per CTA; two CTAs
+// Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
+// (one lane), warps 2..9 = epilogue (TMEM lane quadrant = warp % 4, column half = (warp-2) / 4).  One output tile per CTA; two CTAs
 // are resident per SM (<= 100 KB shared memory, <= 256 TMEM columns each) so that one CTA's epilogue
 // overlaps the other CTA's main loop.
 #include "common.cuh"
@@ -112,7 +112,7 @@ struct Cfg {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192) gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(320) gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 int K, EpiParams ep) {
   using C = Cfg<BN, STAGES>;
@@ -178,92 +178,46 @@ __global__ void __launch_bounds__(192) gemm_bf16_tcgen05_kernel(const __grid_con
       umma_commit(tfull);  // accumulator complete
     }
   } else {
+    // ===== epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves =====
+    // TMEM -> registers (row per lane) -> shared memory (the operand ring is free once the accumulator is
+    // complete) -> row-coalesced global access: lane l owns column c0+l, so every load of the residual and
+    // every store of C touches one contiguous 128 B (fp32) / 64 B (bf16) segment per row.
     mbar_wait(tfull, 0);
     tc_fence_after();
-    const int lg = warp & 3;  // TMEM lane group this warp may read
-    const int row = m0 + lg * 32 + lane;
-    const bool row_ok = row < ep.M;
-    const bool vec_ok = ((ep.ldc & 7) == 0) && (ep.residual == nullptr || (ep.ldr & 7) == 0);
+    const int ew = warp - 2;
+    const int lg = warp & 3;            // TMEM lane quadrant this warp may read (= warp id % 4)
+    const int chalf = ew >> 2;          // which half of the tile's columns
+    constexpr int SST = 36;             // staging row stride in floats (36/4 odd: conflict-free STS.128)
+    float* stg = reinterpret_cast<float*>(smem) + ew * 32 * SST;
+    const int rbase = m0 + lg * 32;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
       uint32_t r[32];
       __syncwarp();
       tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, r);
       const int col0 = n0 + c;
-      if (!row_ok || col0 >= ep.N) continue;
-      float v[32];
+      if (col0 >= ep.N || rbase >= ep.M) continue;   // warp-uniform
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      const bool full = (col0 + 32 <= ep.N) && vec_ok;
-      if (full) {
-        if (ep.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg((const float4*)(ep.bias + col0 + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        if (ep.act != CSEG_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
-        }
-        if (ep.alpha != 1.0f) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
-        }
-        if (ep.residual) {
-          if (ep.res_bf16) {
-            const bf16* rp = (const bf16*)ep.residual + (size_t)row * ep.ldr + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 u = *(const uint4*)(rp + j);
-              const __nv_bfloat162* h = (const __nv_bfloat162*)&u;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h[e]);
-                v[j + 2 * e] += f.x;
-                v[j + 2 * e + 1] += f.y;
-              }
-            }
-          } else {
-            const float* rp = (const float*)ep.residual + (size_t)row * ep.ldr + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 q = *(const float4*)(rp + j);
-              v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
-            }
-          }
-        }
-        if (ep.out_bf16) {
-          bf16* cp = (bf16*)ep.C + (size_t)row * ep.ldc + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-            pk.x = *(uint32_t*)&t0; pk.y = *(uint32_t*)&t1; pk.z = *(uint32_t*)&t2; pk.w = *(uint32_t*)&t3;
-            *(uint4*)(cp + j) = pk;
-          }
-        } else {
-          float* cp = (float*)ep.C + (size_t)row * ep.ldc + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *(float4*)(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-      } else {
-#pragma unroll 1
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          if (col >= ep.N) break;
-          float x = v[j];
-          if (ep.bias) x += ep.bias[col];
-          x = apply_act(x, ep.act) * ep.alpha;
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<uint4*>(stg + lane * SST + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      __syncwarp();
+      const int col = col0 + lane;
+      const bool col_ok = col < ep.N;
+      const float bv = (ep.bias != nullptr && col_ok) ? __ldg(ep.bias + col) : 0.f;
+      const int nrows = min(32, ep.M - rbase);
+      if (col_ok) {
+#pragma unroll 4
+        for (int rr = 0; rr < nrows; ++rr) {
+          float x = stg[rr * SST + lane] + bv;
+          if (ep.act == CSEG_ACT_GELU) x = gelu_fast(x);
+          else if (ep.act == CSEG_ACT_QUICKGELU) x = quick_gelu(x);
+          x *= ep.alpha;
+          const size_t row = (size_t)(rbase + rr);
           if (ep.residual)
-            x += ep.res_bf16 ? __bfloat162float(((const bf16*)ep.residual)[(size_t)row * ep.ldr + col])
-                             : ((const float*)ep.residual)[(size_t)row * ep.ldr + col];
-          if (ep.out_bf16) ((bf16*)ep.C)[(size_t)row * ep.ldc + col] = __float2bfloat16_rn(x);
-          else ((float*)ep.C)[(size_t)row * ep.ldc + col] = x;
+            x += ep.res_bf16 ? __bfloat162float(((const bf16*)ep.residual)[row * ep.ldr + col])
+                             : ((const float*)ep.residual)[row * ep.ldr + col];
+          if (ep.out_bf16) ((bf16*)ep.C)[row * ep.ldc + col] = __float2bfloat16_rn(x);
+          else ((float*)ep.C)[row * ep.ldc + col] = x;
         }
       }
     }
@@ -316,7 +270,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
     attr_set = true;
   }
   dim3 grid(cdiv(N, BN), cdiv(M, BM));
-  gemm_bf16_tcgen05_kernel<BN, STAGES><<<grid, 192, C::SMEM_BYTES, st>>>(ta, tb, K, ep);
+  gemm_bf16_tcgen05_kernel<BN, STAGES><<<grid, 320, C::SMEM_BYTES, st>>>(ta, tb, K, ep);
   CSEG_LAUNCH_CHECK("gemm_bf16_tcgen05");
   return 0;
 }
