@@ -7,10 +7,7 @@
 // the 1x1 convolutions of the reference (open_clip/transformer.py:204,211-215,560,770;
 // simfeatup_dev/upsamplers.py:218-223,325).
 //
-// Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
-// (one lane), warps 2..9 = epilogue (TMEM lane quadrant = warp % 4, column half = (warp-2) / 4).  One output tile per CTA; two CTAs
-// are resident per SM (<= 100 KB shared memory, <= 256 TMEM columns each) so that one CTA's epilogue
-// overlaps the other CTA's main loop.
+// Kernel structure: see the comment above gemm_bf16_tcgen05_kernel (persistent, warp-specialised).
 #include "common.cuh"
 #include <cuda.h>
 
@@ -102,29 +99,51 @@ struct EpiParams {
   int M, N;
 };
 
+// Persistent, warp-specialised kernel.  One CTA per SM loops over output tiles (tile id -> (m, n) with m
+// fastest, so concurrently running CTAs share the B tile in L2):
+//   warp 0      TMA producer      smem ring of STAGES x (A 128x64 + B BNx64), full/empty mbarriers
+//   warp 1      TMEM allocator + MMA issuer; ACC accumulator stages of BN columns in TMEM
+//   warps 2..   epilogue: 4 TMEM lane quadrants (= warp id % 4) x BN/32 column chunks; each warp drains
+//               one 32x32 chunk per tile: tcgen05.ld -> release the accumulator stage -> stage through
+//               shared memory -> row-coalesced residual loads / C stores.
+// The epilogue of tile i overlaps the loads and MMAs of tiles i+1.. (ACC up to 4), which is what the
+// skinny-K GEMMs of the JBU (K = 128) and the GELU epilogues need: they are epilogue-bound.
 template <int BN, int STAGES>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int ACC = (512 / BN) < 4 ? (512 / BN) : 4;   // accumulator stages in TMEM
+  static constexpr int TMEM_COLS = ACC * BN;                     // 256 or 512 (power of two)
+  static constexpr int EPI_WARPS = 4 * (BN / 32);
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int SST = 36;                                 // staging row stride (floats); 36/4 odd
+  static constexpr int STG_OFF = STAGES * STAGE_BYTES;
+  static constexpr int STG_BYTES = EPI_WARPS * 32 * SST * 4;
+  static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
+  static constexpr int NBARS = 2 * STAGES + 2 * ACC;
+  static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;  // + alignment slack
 };
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(320) gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                const __grid_constant__ CUtensorMap tmB,
-                                                                int K, EpiParams ep) {
+__global__ void __launch_bounds__(Cfg<BN, STAGES>::THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K,
+                         int m_tiles, int num_tiles, EpiParams ep) {
   using C = Cfg<BN, STAGES>;
+  constexpr int ACC = C::ACC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + C::BAR_OFF);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
+  uint32_t* tmem_slot = (uint32_t*)(bars + C::NBARS);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t full0 = smem_u32(bars), empty0 = full0 + STAGES * 8, tfull = empty0 + STAGES * 8;
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + STAGES * 8;
+  const uint32_t tfull0 = empty0 + STAGES * 8, tempty0 = tfull0 + ACC * 8;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int num_kb = (K + BK - 1) / BK;  // a K tail is zero-filled by TMA (OOB fill) in both operands
 
   if (warp == 0 && lane == 0) {
@@ -134,11 +153,14 @@ __global__ void __launch_bounds__(320) gemm_bf16_tcgen05_kernel(const __grid_con
       mbar_init(full0 + s * 8, 1);
       mbar_init(empty0 + s * 8, 1);
     }
-    mbar_init(tfull, 1);
+    for (int s = 0; s < ACC; ++s) {
+      mbar_init(tfull0 + s * 8, 1);
+      mbar_init(tempty0 + s * 8, C::EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -148,55 +170,64 @@ __global__ void __launch_bounds__(320) gemm_bf16_tcgen05_kernel(const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(empty0 + s * 8, ph ^ 1);
-        mbar_expect_tx(full0 + s * 8, C::STAGE_BYTES);
-        const uint32_t a_dst = smem_base + s * C::STAGE_BYTES;
-        tma_load_2d(a_dst, &tmA, full0 + s * 8, kb * BK, m0);
-        tma_load_2d(a_dst + C::A_BYTES, &tmB, full0 + s * 8, kb * BK, n0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(empty0 + s * 8, ph ^ 1);
+          mbar_expect_tx(full0 + s * 8, C::STAGE_BYTES);
+          const uint32_t a_dst = smem_base + s * C::STAGE_BYTES;
+          tma_load_2d(a_dst, &tmA, full0 + s * 8, kb * BK, m0);
+          tma_load_2d(a_dst + C::A_BYTES, &tmB, full0 + s * 8, kb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(full0 + s * 8, ph);
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
+        mbar_wait(tempty0 + as * 8, aph ^ 1);      // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint64_t adesc = make_sdesc(smem_base + s * C::STAGE_BYTES);
-        const uint64_t bdesc = make_sdesc(smem_base + s * C::STAGE_BYTES + C::A_BYTES);
+        const uint32_t tacc = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(full0 + s * 8, ph);
+          tc_fence_after();
+          const uint64_t adesc = make_sdesc(smem_base + s * C::STAGE_BYTES);
+          const uint64_t bdesc = make_sdesc(smem_base + s * C::STAGE_BYTES + C::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // +32 B per K=16 step inside the 128 B swizzle row -> +2 in the (addr >> 4) field
-          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 B per K=16 step inside the 128 B swizzle row -> +2 in the (addr >> 4) field
+            umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty0 + s * 8);  // frees the smem stage once these MMAs have read it
         }
-        umma_commit(empty0 + s * 8);  // frees the smem stage once these MMAs have read it
+        umma_commit(tfull0 + as * 8);   // accumulator complete
       }
-      umma_commit(tfull);  // accumulator complete
     }
   } else {
-    // ===== epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves =====
-    // TMEM -> registers (row per lane) -> shared memory (the operand ring is free once the accumulator is
-    // complete) -> row-coalesced global access: lane l owns column c0+l, so every load of the residual and
-    // every store of C touches one contiguous 128 B (fp32) / 64 B (bf16) segment per row.
-    mbar_wait(tfull, 0);
-    tc_fence_after();
     const int ew = warp - 2;
     const int lg = warp & 3;            // TMEM lane quadrant this warp may read (= warp id % 4)
-    const int chalf = ew >> 2;          // which half of the tile's columns
-    constexpr int SST = 36;             // staging row stride in floats (36/4 odd: conflict-free STS.128)
-    float* stg = reinterpret_cast<float*>(smem) + ew * 32 * SST;
-    const int rbase = m0 + lg * 32;
-#pragma unroll 1
-    for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
+    const int cchunk = ew >> 2;         // which 32-column chunk of the tile
+    constexpr int SST = C::SST;
+    float* stg = reinterpret_cast<float*>(smem + C::STG_OFF) + ew * 32 * SST;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+      const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
+      mbar_wait(tfull0 + as * 8, aph);
+      tc_fence_after();
       uint32_t r[32];
       __syncwarp();
-      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, r);
-      const int col0 = n0 + c;
-      if (col0 >= ep.N || rbase >= ep.M) continue;   // warp-uniform
+      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + cchunk * 32), r);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + as * 8);   // this warp's part of the accumulator is in registers
+      const int rbase = m0 + lg * 32, col0 = n0 + cchunk * 32;
+      if (col0 >= ep.N || rbase >= ep.M) continue;    // warp-uniform
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<uint4*>(stg + lane * SST + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
@@ -220,12 +251,13 @@ __global__ void __launch_bounds__(320) gemm_bf16_tcgen05_kernel(const __grid_con
           else ((float*)ep.C)[row * ep.ldc + col] = x;
         }
       }
+      __syncwarp();   // staging buffer is reused by this warp's next tile
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
   }
 }
 
@@ -263,14 +295,10 @@ int make_map(CUtensorMap* m, const void* base, int rows, int K, int ld, int box_
 template <int BN, int STAGES>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
   using C = Cfg<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CSEG_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   C::SMEM_BYTES));
-    attr_set = true;
-  }
-  dim3 grid(cdiv(N, BN), cdiv(M, BM));
-  gemm_bf16_tcgen05_kernel<BN, STAGES><<<grid, 320, C::SMEM_BYTES, st>>>(ta, tb, K, ep);
+  CSEG_SET_SMEM((gemm_bf16_tcgen05_kernel<BN, STAGES>), C::SMEM_BYTES);
+  const int m_tiles = cdiv(M, BM), num_tiles = m_tiles * cdiv(N, BN);
+  const int grid = std::min(num_tiles, sm_count());
+  gemm_bf16_tcgen05_kernel<BN, STAGES><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, K, m_tiles, num_tiles, ep);
   CSEG_LAUNCH_CHECK("gemm_bf16_tcgen05");
   return 0;
 }
@@ -284,13 +312,14 @@ int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int
   CSEG_REQUIRE(K % 8 == 0, "gemm(bf16): K=%d must be a multiple of 8 (16-byte rows for TMA)", K);
   CSEG_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm(bf16): lda=%d, ldb=%d must be multiples of 8", lda, ldb);
   CSEG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm(bf16): operands must be 16-byte aligned");
-  int bn = (N <= 64 || (long long)cdiv(M, BM) * cdiv(N, 128) < 2LL * sm_count()) ? 64 : 128;
+  // BN = 64 when 128-wide tiles would leave SMs idle (fewer than ~1.5 tiles per SM)
+  int bn = (N <= 64 || (long long)cdiv(M, BM) * cdiv(N, 128) * 2 < 3LL * sm_count()) ? 64 : 128;
   CUtensorMap ta, tb;
   int rc = make_map(&ta, A, M, K, lda, BM);
   if (rc) return rc;
   rc = make_map(&tb, B, N, K, ldb, bn);
   if (rc) return rc;
   EpiParams ep{bias, residual, ldr, res_dtype == CSEG_BF16, alpha, act, out_dtype == CSEG_BF16, C, ldc, M, N};
-  if (bn == 64) return launch<64, 4>(ta, tb, M, N, K, ep, st);
-  return launch<128, 3>(ta, tb, M, N, K, ep, st);
+  if (bn == 64) return launch<64, 6>(ta, tb, M, N, K, ep, st);
+  return launch<128, 4>(ta, tb, M, N, K, ep, st);
 }
