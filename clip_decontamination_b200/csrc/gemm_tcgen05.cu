@@ -218,6 +218,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
       const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
+      const int rbase = m0 + lg * 32, col0 = n0 + cchunk * 32;
+      const int col = col0 + lane;
+      const bool col_ok = col < ep.N;
+      const int nrows = min(32, ep.M - rbase);
+      // residual + bias for this warp's 32x32 chunk are fetched BEFORE waiting for the accumulator: they do
+      // not depend on the MMA, so their latency hides behind the main loop of this tile.
+      float res[32];
+      if (ep.residual != nullptr && col_ok) {
+        if (ep.res_bf16) {
+          const bf16* rp = (const bf16*)ep.residual + (size_t)rbase * ep.ldr + col;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) res[rr] = (rr < nrows) ? __bfloat162float(rp[(size_t)rr * ep.ldr]) : 0.f;
+        } else {
+          const float* rp = (const float*)ep.residual + (size_t)rbase * ep.ldr + col;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) res[rr] = (rr < nrows) ? rp[(size_t)rr * ep.ldr] : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) res[rr] = 0.f;
+      }
+      const float bv = (ep.bias != nullptr && col_ok) ? __ldg(ep.bias + col) : 0.f;
       mbar_wait(tfull0 + as * 8, aph);
       tc_fence_after();
       uint32_t r[32];
@@ -226,29 +248,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + as * 8);   // this warp's part of the accumulator is in registers
-      const int rbase = m0 + lg * 32, col0 = n0 + cchunk * 32;
       if (col0 >= ep.N || rbase >= ep.M) continue;    // warp-uniform
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<uint4*>(stg + lane * SST + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
       __syncwarp();
-      const int col = col0 + lane;
-      const bool col_ok = col < ep.N;
-      const float bv = (ep.bias != nullptr && col_ok) ? __ldg(ep.bias + col) : 0.f;
-      const int nrows = min(32, ep.M - rbase);
       if (col_ok) {
-#pragma unroll 4
-        for (int rr = 0; rr < nrows; ++rr) {
-          float x = stg[rr * SST + lane] + bv;
-          if (ep.act == CSEG_ACT_GELU) x = gelu_fast(x);
-          else if (ep.act == CSEG_ACT_QUICKGELU) x = quick_gelu(x);
-          x *= ep.alpha;
-          const size_t row = (size_t)(rbase + rr);
-          if (ep.residual)
-            x += ep.res_bf16 ? __bfloat162float(((const bf16*)ep.residual)[row * ep.ldr + col])
-                             : ((const float*)ep.residual)[row * ep.ldr + col];
-          if (ep.out_bf16) ((bf16*)ep.C)[row * ep.ldc + col] = __float2bfloat16_rn(x);
-          else ((float*)ep.C)[row * ep.ldc + col] = x;
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          if (rr < nrows) {
+            float x = stg[rr * SST + lane] + bv;
+            if (ep.act == CSEG_ACT_GELU) x = gelu_fast(x);
+            else if (ep.act == CSEG_ACT_QUICKGELU) x = quick_gelu(x);
+            x = fmaf(x, ep.alpha, res[rr]);
+            const size_t row = (size_t)(rbase + rr);
+            if (ep.out_bf16) ((bf16*)ep.C)[row * ep.ldc + col] = __float2bfloat16_rn(x);
+            else ((float*)ep.C)[row * ep.ldc + col] = x;
+          }
         }
       }
       __syncwarp();   // staging buffer is reused by this warp's next tile
