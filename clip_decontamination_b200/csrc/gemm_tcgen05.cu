@@ -129,7 +129,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BN, int STAGES>
+// ACT: CSEG_ACT_*; OUTB: C is bf16; RES: 0 none, 1 fp32 residual, 2 bf16 residual (compile-time so the
+// per-element epilogue is ~10 instructions: the skinny-K GEMMs are bound by epilogue instruction issue)
+template <int BN, int STAGES, int ACT, int OUTB, int RES>
 __global__ void __launch_bounds__(Cfg<BN, STAGES>::THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K,
                          int m_tiles, int num_tiles, EpiParams ep) {
@@ -145,6 +147,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (K + BK - 1) / BK;  // a K tail is zero-filled by TMA (OOB fill) in both operands
+  // tile order: the n-tiles of one m-panel run back to back when A is the big operand (m_tiles >= n_tiles:
+  // the A panel is fetched from HBM once and re-read from L2), otherwise m fastest (B panel shared).
+  const int n_tiles = num_tiles / m_tiles;
+  const bool n_fast = m_tiles >= n_tiles;
+#define TILE_M(t) (n_fast ? (t) / n_tiles : (t) % m_tiles)
+#define TILE_N(t) (n_fast ? (t) % n_tiles : (t) / m_tiles)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -172,7 +180,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+        const int m0 = TILE_M(tile) * BM, n0 = TILE_N(tile) * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(empty0 + s * 8, ph ^ 1);
@@ -216,7 +224,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     float* stg = reinterpret_cast<float*>(smem + C::STG_OFF) + ew * 32 * SST;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-      const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+      const int m0 = TILE_M(tile) * BM, n0 = TILE_N(tile) * BN;
       const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
       const int rbase = m0 + lg * 32, col0 = n0 + cchunk * 32;
       const int col = col0 + lane;
@@ -225,8 +233,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       // residual + bias for this warp's 32x32 chunk are fetched BEFORE waiting for the accumulator: they do
       // not depend on the MMA, so their latency hides behind the main loop of this tile.
       float res[32];
-      if (ep.residual != nullptr && col_ok) {
-        if (ep.res_bf16) {
+      if (RES != 0 && col_ok) {
+        if (RES == 2) {
           const bf16* rp = (const bf16*)ep.residual + (size_t)rbase * ep.ldr + col;
 #pragma unroll
           for (int rr = 0; rr < 32; ++rr) res[rr] = (rr < nrows) ? __bfloat162float(rp[(size_t)rr * ep.ldr]) : 0.f;
@@ -235,9 +243,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int rr = 0; rr < 32; ++rr) res[rr] = (rr < nrows) ? rp[(size_t)rr * ep.ldr] : 0.f;
         }
-      } else {
-#pragma unroll
-        for (int rr = 0; rr < 32; ++rr) res[rr] = 0.f;
       }
       const float bv = (ep.bias != nullptr && col_ok) ? __ldg(ep.bias + col) : 0.f;
       mbar_wait(tfull0 + as * 8, aph);
@@ -254,16 +259,32 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         *reinterpret_cast<uint4*>(stg + lane * SST + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
       __syncwarp();
       if (col_ok) {
+        const float alpha = ep.alpha;
+        auto finish = [&](int rr) -> float {
+          float x = stg[rr * SST + lane] + bv;
+          if (ACT == CSEG_ACT_GELU) x = gelu_fast(x);
+          else if (ACT == CSEG_ACT_QUICKGELU) x = quick_gelu(x);
+          return RES != 0 ? fmaf(x, alpha, res[rr]) : x * alpha;
+        };
+        if (OUTB) {
+          bf16* cp = (bf16*)ep.C + (size_t)rbase * ep.ldc + col;
+          if (nrows == 32) {
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
-          if (rr < nrows) {
-            float x = stg[rr * SST + lane] + bv;
-            if (ep.act == CSEG_ACT_GELU) x = gelu_fast(x);
-            else if (ep.act == CSEG_ACT_QUICKGELU) x = quick_gelu(x);
-            x = fmaf(x, ep.alpha, res[rr]);
-            const size_t row = (size_t)(rbase + rr);
-            if (ep.out_bf16) ((bf16*)ep.C)[row * ep.ldc + col] = __float2bfloat16_rn(x);
-            else ((float*)ep.C)[row * ep.ldc + col] = x;
+            for (int rr = 0; rr < 32; ++rr) cp[(size_t)rr * ep.ldc] = __float2bfloat16_rn(finish(rr));
+          } else {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              if (rr < nrows) cp[(size_t)rr * ep.ldc] = __float2bfloat16_rn(finish(rr));
+          }
+        } else {
+          float* cp = (float*)ep.C + (size_t)rbase * ep.ldc + col;
+          if (nrows == 32) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) cp[(size_t)rr * ep.ldc] = finish(rr);
+          } else {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              if (rr < nrows) cp[(size_t)rr * ep.ldc] = finish(rr);
           }
         }
       }
@@ -308,15 +329,33 @@ int make_map(CUtensorMap* m, const void* base, int rows, int K, int ld, int box_
   return 0;
 }
 
-template <int BN, int STAGES>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+template <int BN, int STAGES, int ACT, int OUTB, int RES>
+int launch3(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
   using C = Cfg<BN, STAGES>;
-  CSEG_SET_SMEM((gemm_bf16_tcgen05_kernel<BN, STAGES>), C::SMEM_BYTES);
+  CSEG_SET_SMEM((gemm_bf16_tcgen05_kernel<BN, STAGES, ACT, OUTB, RES>), C::SMEM_BYTES);
   const int m_tiles = cdiv(M, BM), num_tiles = m_tiles * cdiv(N, BN);
   const int grid = std::min(num_tiles, sm_count());
-  gemm_bf16_tcgen05_kernel<BN, STAGES><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, K, m_tiles, num_tiles, ep);
+  gemm_bf16_tcgen05_kernel<BN, STAGES, ACT, OUTB, RES><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, K, m_tiles,
+                                                                                              num_tiles, ep);
   CSEG_LAUNCH_CHECK("gemm_bf16_tcgen05");
   return 0;
+}
+template <int BN, int STAGES, int ACT, int OUTB>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+  if (ep.residual == nullptr) return launch3<BN, STAGES, ACT, OUTB, 0>(ta, tb, M, N, K, ep, st);
+  if (ep.res_bf16) return launch3<BN, STAGES, ACT, OUTB, 2>(ta, tb, M, N, K, ep, st);
+  return launch3<BN, STAGES, ACT, OUTB, 1>(ta, tb, M, N, K, ep, st);
+}
+template <int BN, int STAGES, int ACT>
+int launch1(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+  if (ep.out_bf16) return launch2<BN, STAGES, ACT, 1>(ta, tb, M, N, K, ep, st);
+  return launch2<BN, STAGES, ACT, 0>(ta, tb, M, N, K, ep, st);
+}
+template <int BN, int STAGES>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+  if (ep.act == CSEG_ACT_GELU) return launch1<BN, STAGES, CSEG_ACT_GELU>(ta, tb, M, N, K, ep, st);
+  if (ep.act == CSEG_ACT_QUICKGELU) return launch1<BN, STAGES, CSEG_ACT_QUICKGELU>(ta, tb, M, N, K, ep, st);
+  return launch1<BN, STAGES, CSEG_ACT_NONE>(ta, tb, M, N, K, ep, st);
 }
 
 }  // namespace
