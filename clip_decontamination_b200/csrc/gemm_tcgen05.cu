@@ -227,48 +227,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int m0 = TILE_M(tile) * BM, n0 = TILE_N(tile) * BN;
       const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
       const int rbase = m0 + lg * 32, col0 = n0 + cchunk * 32;
-      // lane -> (row parity p, column pair cp): rows 2i+p, columns 2cp and 2cp+1 of the 32x32 chunk, so
-      // residual loads and C stores are 4-byte (bf16x2) / 8-byte (float2) accesses, two rows per instruction
-      const int p = lane >> 4, cp = lane & 15;
-      const int col = col0 + 2 * cp;
-      const bool c0ok = col < ep.N, c1ok = col + 1 < ep.N;
+      const int col = col0 + lane;
+      const bool col_ok = col < ep.N;
       const int nrows = min(32, ep.M - rbase);
-      const bool vec = c1ok && ((ep.ldc & 1) == 0) && (RES == 0 || (ep.ldr & 1) == 0);   // 2-element accesses legal
-      // residual + bias are fetched BEFORE waiting for the accumulator: they do not depend on the MMA, so
-      // their latency hides behind the main loop of this tile.
-      float res0[16], res1[16];
-      if (RES != 0) {
+      // residual + bias for this warp's 32x32 chunk are fetched BEFORE waiting for the accumulator: they do
+      // not depend on the MMA, so their latency hides behind the main loop of this tile.
+      float res[32];
+      if (RES != 0 && col_ok) {
+        if (RES == 2) {
+          const bf16* rp = (const bf16*)ep.residual + (size_t)rbase * ep.ldr + col;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int rr = 2 * i + p;
-          res0[i] = 0.f;
-          res1[i] = 0.f;
-          if (rr < nrows && c0ok) {
-            const size_t off = (size_t)(rbase + rr) * ep.ldr + col;
-            if (RES == 2) {
-              const bf16* rp = (const bf16*)ep.residual + off;
-              if (vec) {
-                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rp));
-                res0[i] = f.x; res1[i] = f.y;
-              } else {
-                res0[i] = __bfloat162float(rp[0]);
-                if (c1ok) res1[i] = __bfloat162float(rp[1]);
-              }
-            } else {
-              const float* rp = (const float*)ep.residual + off;
-              if (vec) {
-                const float2 f = *reinterpret_cast<const float2*>(rp);
-                res0[i] = f.x; res1[i] = f.y;
-              } else {
-                res0[i] = rp[0];
-                if (c1ok) res1[i] = rp[1];
-              }
-            }
-          }
+          for (int rr = 0; rr < 32; ++rr) res[rr] = (rr < nrows) ? __bfloat162float(rp[(size_t)rr * ep.ldr]) : 0.f;
+        } else {
+          const float* rp = (const float*)ep.residual + (size_t)rbase * ep.ldr + col;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) res[rr] = (rr < nrows) ? rp[(size_t)rr * ep.ldr] : 0.f;
         }
       }
-      const float bv0 = (ep.bias != nullptr && c0ok) ? __ldg(ep.bias + col) : 0.f;
-      const float bv1 = (ep.bias != nullptr && c1ok) ? __ldg(ep.bias + col + 1) : 0.f;
+      const float bv = (ep.bias != nullptr && col_ok) ? __ldg(ep.bias + col) : 0.f;
       mbar_wait(tfull0 + as * 8, aph);
       tc_fence_after();
       uint32_t r[32];
@@ -282,28 +258,33 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<uint4*>(stg + lane * SST + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
       __syncwarp();
-      if (c0ok) {
+      if (col_ok) {
         const float alpha = ep.alpha;
+        auto finish = [&](int rr) -> float {
+          float x = stg[rr * SST + lane] + bv;
+          if (ACT == CSEG_ACT_GELU) x = gelu_fast(x);
+          else if (ACT == CSEG_ACT_QUICKGELU) x = quick_gelu(x);
+          return RES != 0 ? fmaf(x, alpha, res[rr]) : x * alpha;
+        };
+        if (OUTB) {
+          bf16* cp = (bf16*)ep.C + (size_t)rbase * ep.ldc + col;
+          if (nrows == 32) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int rr = 2 * i + p;
-          if (rr < nrows) {
-            const float2 a2 = *reinterpret_cast<const float2*>(stg + rr * SST + 2 * cp);
-            float x0 = a2.x + bv0, x1 = a2.y + bv1;
-            if (ACT == CSEG_ACT_GELU) { x0 = gelu_fast(x0); x1 = gelu_fast(x1); }
-            else if (ACT == CSEG_ACT_QUICKGELU) { x0 = quick_gelu(x0); x1 = quick_gelu(x1); }
-            if (RES != 0) { x0 = fmaf(x0, alpha, res0[i]); x1 = fmaf(x1, alpha, res1[i]); }
-            else { x0 *= alpha; x1 *= alpha; }
-            const size_t off = (size_t)(rbase + rr) * ep.ldc + col;
-            if (OUTB) {
-              bf16* cp_ = (bf16*)ep.C + off;
-              if (vec) *reinterpret_cast<__nv_bfloat162*>(cp_) = __floats2bfloat162_rn(x0, x1);
-              else { cp_[0] = __float2bfloat16_rn(x0); if (c1ok) cp_[1] = __float2bfloat16_rn(x1); }
-            } else {
-              float* cp_ = (float*)ep.C + off;
-              if (vec) *reinterpret_cast<float2*>(cp_) = make_float2(x0, x1);
-              else { cp_[0] = x0; if (c1ok) cp_[1] = x1; }
-            }
+            for (int rr = 0; rr < 32; ++rr) cp[(size_t)rr * ep.ldc] = __float2bfloat16_rn(finish(rr));
+          } else {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              if (rr < nrows) cp[(size_t)rr * ep.ldc] = __float2bfloat16_rn(finish(rr));
+          }
+        } else {
+          float* cp = (float*)ep.C + (size_t)rbase * ep.ldc + col;
+          if (nrows == 32) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) cp[(size_t)rr * ep.ldc] = finish(rr);
+          } else {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              if (rr < nrows) cp[(size_t)rr * ep.ldc] = finish(rr);
           }
         }
       }
