@@ -19,13 +19,14 @@ namespace {
 
 constexpr int RW = 4;      // output rows per CTA
 constexpr int TX = 32;     // output pixels per CTA (2 MMA pixel blocks)
-constexpr int CS = 128;    // channels per CTA
+constexpr int CS = 256;    // channels per CTA (4 warps x 64)
 constexpr int NPOS = TX + 16;                 // source positions per row buffer (x0-R .. incl. K padding)
 constexpr int PSTRIDE = CS * 2 + 16;          // bytes per position in the ring (padded)
-constexpr int NST = 4;                        // ring stages
-constexpr int WSTRIDE = 136;                  // bf16 elements per staged kernel row (128 + 8 pad)
+constexpr int NST = 3;                        // ring stages
 constexpr int ROW_BYTES = NPOS * PSTRIDE;
-constexpr int SMEM_BYTES = NST * ROW_BYTES + RW * TX * WSTRIDE * 2;
+constexpr int ASTRIDE = 80;                   // bytes per row of a band tile (32 bf16 + pad: conflict-free ldmatrix)
+constexpr int ATILE = 16 * ASTRIDE;           // one 16 x 32 band tile
+constexpr int NTHREADS = 256;
 
 __device__ __forceinline__ int reflect1(int i, int n) {
   if (i < 0) i = -i;
@@ -39,6 +40,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -51,29 +57,38 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// CTA = RW output rows x 32 pixels x 256 channels; 8 warps = 2 pixel blocks x 4 channel quarters (8 n-blocks
+// of 8 channels each).  The kernel weights of the tile are expanded ONCE into band tiles in shared memory
+// (Wband[r][i][xb][m][k] = kern[px(m)][i*D + k - m] for 0 <= k-m < D, zero elsewhere), so an A fragment is
+// two ldmatrix.x4 instead of a predicated gather, and it is shared by the four channel-quarter warps.
 template <int R>
-__global__ void __launch_bounds__(128, 2) adaptive_conv_mma_kernel(const bf16* __restrict__ hr, int H2, int W2, int C,
-                                                                   const bf16* __restrict__ kern, int ldk,
-                                                                   bf16* __restrict__ dst) {
+__global__ void __launch_bounds__(NTHREADS, 1) adaptive_conv_mma_kernel(const bf16* __restrict__ hr, int H2, int W2, int C,
+                                                                        const bf16* __restrict__ kern, int ldk,
+                                                                        bf16* __restrict__ dst) {
   constexpr int D = 2 * R + 1;
   constexpr int NSRC = RW + 2 * R;  // source rows per tile
+  constexpr int WB_BYTES = RW * D * 2 * ATILE;
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem);
-  bf16* Ws = reinterpret_cast<bf16*>(smem + NST * ROW_BYTES);
+  uint8_t* wb = smem + NST * ROW_BYTES;
+  const uint32_t wband = ring + NST * ROW_BYTES;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int xb = warp & 1, chalf = warp >> 1;
+  const int xb = warp & 1, cq = warp >> 1;
   const int g = lane >> 2, tig = lane & 3;
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * RW;
-  const int nslab = C / CS;
+  const int nslab = (C + CS - 1) / CS;
   const int crop = blockIdx.z / nslab, c0 = (blockIdx.z % nslab) * CS;
+  const int cvalid = min(CS, C - c0);            // channels of this slab that exist
+  const bool warp_on = cq * 64 < cvalid;         // warp-uniform: this channel quarter exists
   const bf16* hrc = hr + (size_t)crop * H2 * W2 * C + c0;
 
   auto load_row = [&](int sr) {
     const int yy = reflect1(min(y0 + sr - R, H2 - 1 + R), H2);
     const uint32_t base = ring + (sr % NST) * ROW_BYTES;
-    for (int e = tid; e < NPOS * (CS / 8); e += 128) {
+    for (int e = tid; e < NPOS * (CS / 8); e += NTHREADS) {
       const int p = e / (CS / 8), ch = (e % (CS / 8)) * 8;
+      if (ch >= cvalid) continue;
       const int xx = reflect1(min(x0 - R + p, W2 - 1 + R), W2);
       cp_async16(base + p * PSTRIDE + ch * 2, hrc + ((size_t)yy * W2 + xx) * C + ch);
     }
@@ -83,13 +98,23 @@ __global__ void __launch_bounds__(128, 2) adaptive_conv_mma_kernel(const bf16* _
     if (s < NSRC) load_row(s);
     cp_async_commit();
   }
-  // stage the kernel weights of the tile: RW x TX rows of ldk bf16 (zero rows outside the image)
-  for (int e = tid; e < RW * TX * (128 / 8); e += 128) {
+  // ---- expand the kernel weights of the tile into band tiles ----
+  for (int e = tid; e < WB_BYTES / 16; e += NTHREADS) reinterpret_cast<uint4*>(wb)[e] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int e = tid; e < RW * TX * (128 / 8); e += NTHREADS) {
     const int v = e % 16, px = (e / 16) % TX, r = e / (16 * TX);
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (y0 + r < H2 && x0 + px < W2 && v * 8 < ldk)
-      val = __ldg(reinterpret_cast<const uint4*>(kern + (((size_t)crop * H2 + y0 + r) * W2 + x0 + px) * ldk + v * 8));
-    *reinterpret_cast<uint4*>(Ws + (r * TX + px) * WSTRIDE + v * 8) = val;
+    if (y0 + r >= H2 || x0 + px >= W2 || v * 8 >= ldk) continue;
+    const uint4 val = __ldg(reinterpret_cast<const uint4*>(kern + (((size_t)crop * H2 + y0 + r) * W2 + x0 + px) * ldk + v * 8));
+    const unsigned short* hv = reinterpret_cast<const unsigned short*>(&val);
+    const int m = px & 15, pxb = px >> 4;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = v * 8 + q;
+      if (t < D * D) {
+        const int i = t / D, j = t - i * D;
+        *reinterpret_cast<unsigned short*>(wb + ((r * D + i) * 2 + pxb) * ATILE + m * ASTRIDE + (j + m) * 2) = hv[q];
+      }
+    }
   }
 
   float acc[RW][8][4];
@@ -101,15 +126,18 @@ __global__ void __launch_bounds__(128, 2) adaptive_conv_mma_kernel(const bf16* _
       for (int e = 0; e < 4; ++e) acc[r][nb][e] = 0.f;
 
   const int lrow = lane & 7, lq = lane >> 3;
-  const uint32_t b_lane_off = (uint32_t)(((lq & 1) * 8 + lrow) * PSTRIDE + (chalf * 64 + (lq >> 1) * 8) * 2);
-  const unsigned short* Wu = reinterpret_cast<const unsigned short*>(Ws);
+  const uint32_t b_lane_off = (uint32_t)(((lq & 1) * 8 + lrow) * PSTRIDE + (cq * 64 + (lq >> 1) * 8) * 2);
+  // A fragment lanes: matrices (rows 0-7, k 0-7) (rows 8-15, k 0-7) (rows 0-7, k 8-15) (rows 8-15, k 8-15)
+  const uint32_t a_lane_off = (uint32_t)(((lq & 1) * 8 + lrow) * ASTRIDE + (lq >> 1) * 16);
 
 #pragma unroll 1
   for (int sr = 0; sr < NSRC; ++sr) {
     cp_async_wait<NST - 2>();
-    __syncthreads();  // row sr has landed for everyone; slot (sr-1)%NST is free again
+    __syncthreads();  // row sr has landed for everyone (and, at sr = 0, the band tiles are complete);
+                      // slot (sr-1)%NST is free again
     if (sr + NST - 1 < NSRC) load_row(sr + NST - 1);
     cp_async_commit();
+    if (!warp_on) continue;
     const uint32_t rowbase = ring + (sr % NST) * ROW_BYTES;
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
@@ -121,22 +149,15 @@ __global__ void __launch_bounds__(128, 2) adaptive_conv_mma_kernel(const bf16* _
       for (int r = 0; r < RW; ++r) {
         const int i = sr - r;  // tap row of output row r fed by this source row
         if (i < 0 || i >= D) continue;
-        // A fragment of the band: A[m][k] = w[px(m)][i*D + k + 16 ks - m]
         uint32_t a[4];
-        const unsigned short* w0 = Wu + (r * TX + xb * 16 + g) * WSTRIDE + i * D;
-        const unsigned short* w1 = w0 + 8 * WSTRIDE;
-        const int jb = 2 * tig + 16 * ks;
-        auto wv = [&](const unsigned short* w, int j) -> uint32_t { return (j >= 0 && j < D) ? (uint32_t)w[j] : 0u; };
-        a[0] = wv(w0, jb - g) | (wv(w0, jb + 1 - g) << 16);
-        a[1] = wv(w1, jb - g - 8) | (wv(w1, jb + 1 - g - 8) << 16);
-        a[2] = wv(w0, jb + 8 - g) | (wv(w0, jb + 9 - g) << 16);
-        a[3] = wv(w1, jb - g) | (wv(w1, jb + 1 - g) << 16);
+        ldsm_x4(wband + (uint32_t)(((r * D + i) * 2 + xb) * ATILE + ks * 32) + a_lane_off, a);
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) mma_bf16(acc[r][nb], a, bfr[nb >> 1][(nb & 1) * 2], bfr[nb >> 1][(nb & 1) * 2 + 1]);
       }
     }
   }
   cp_async_wait<0>();
+  if (!warp_on) return;
   // epilogue: c0,c1 -> (px g, ch 2tig,2tig+1); c2,c3 -> (px g+8, ...)
 #pragma unroll
   for (int r = 0; r < RW; ++r) {
@@ -146,29 +167,33 @@ __global__ void __launch_bounds__(128, 2) adaptive_conv_mma_kernel(const bf16* _
     for (int hm = 0; hm < 2; ++hm) {
       const int x = x0 + xb * 16 + g + hm * 8;
       if (x >= W2) continue;
-      bf16* o = dst + (((size_t)crop * H2 + y) * W2 + x) * C + c0 + chalf * 64 + 2 * tig;
+      bf16* o = dst + (((size_t)crop * H2 + y) * W2 + x) * C + c0 + cq * 64 + 2 * tig;
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb)
-        *reinterpret_cast<__nv_bfloat162*>(o + nb * 8) = __floats2bfloat162_rn(acc[r][nb][hm * 2], acc[r][nb][hm * 2 + 1]);
+        if (cq * 64 + nb * 8 < cvalid)
+          *reinterpret_cast<__nv_bfloat162*>(o + nb * 8) = __floats2bfloat162_rn(acc[r][nb][hm * 2], acc[r][nb][hm * 2 + 1]);
     }
   }
+}
+
+template <int R>
+int launch_conv(const bf16* hr, int n_crops, int H2, int W2, int C, const bf16* kern, int ldk, bf16* dst, cudaStream_t st) {
+  constexpr int D = 2 * R + 1;
+  const int smem = NST * ROW_BYTES + RW * D * 2 * ATILE;
+  CSEG_SET_SMEM(adaptive_conv_mma_kernel<R>, smem);
+  dim3 grid(cdiv(W2, TX), cdiv(H2, RW), n_crops * cdiv(C, CS));
+  CSEG_REQUIRE(grid.z <= 65535, "jbu_apply(bf16): too many crop x channel slabs (%u)", grid.z);
+  adaptive_conv_mma_kernel<R><<<grid, NTHREADS, smem, st>>>(hr, H2, W2, C, kern, ldk, dst);
+  CSEG_LAUNCH_CHECK("jbu_adaptive_conv_mma");
+  return 0;
 }
 
 }  // namespace
 
 int cseg_jbu_adaptive_conv_mma(const bf16* hr, int n_crops, int H2, int W2, int C, const bf16* kern, int ldk,
                                int radius, bf16* dst, cudaStream_t st) {
-  CSEG_REQUIRE(C % CS == 0, "jbu_apply(bf16): C=%d must be a multiple of %d", C, CS);
+  CSEG_REQUIRE(C % 64 == 0, "jbu_apply(bf16): C=%d must be a multiple of 64", C);
   CSEG_REQUIRE(ldk % 8 == 0 && ldk <= 128, "jbu_apply(bf16): ldk=%d must be a multiple of 8 and <= 128", ldk);
-  dim3 grid(cdiv(W2, TX), cdiv(H2, RW), n_crops * (C / CS));
-  CSEG_REQUIRE(grid.z <= 65535, "jbu_apply(bf16): too many crop x channel slabs (%u)", grid.z);
-  if (radius == 5) {
-    CSEG_SET_SMEM(adaptive_conv_mma_kernel<5>, SMEM_BYTES);
-    adaptive_conv_mma_kernel<5><<<grid, 128, SMEM_BYTES, st>>>(hr, H2, W2, C, kern, ldk, dst);
-  } else {
-    CSEG_SET_SMEM(adaptive_conv_mma_kernel<3>, SMEM_BYTES);
-    adaptive_conv_mma_kernel<3><<<grid, 128, SMEM_BYTES, st>>>(hr, H2, W2, C, kern, ldk, dst);
-  }
-  CSEG_LAUNCH_CHECK("jbu_adaptive_conv_mma");
-  return 0;
+  if (radius == 5) return launch_conv<5>(hr, n_crops, H2, W2, C, kern, ldk, dst, st);
+  return launch_conv<3>(hr, n_crops, H2, W2, C, kern, ldk, dst, st);
 }

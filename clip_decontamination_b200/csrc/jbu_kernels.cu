@@ -342,7 +342,7 @@ static int launch_apply(const void* src, int n_crops, int h, int w, int C, const
   bicubic2x_kernel<T><<<(int)std::min<long long>((tot_b + 255) / 256, (long long)sm_count() * 32), 256, 0, st>>>(
       (const T*)src, n_crops, h, w, C, (T*)hr_scratch);
   CSEG_LAUNCH_CHECK("jbu_bicubic2x");
-  if (sizeof(T) == 2 && C % 128 == 0 && ldk % 8 == 0 && ldk <= 128)   // tensor-core banded GEMM path
+  if (sizeof(T) == 2 && C % 64 == 0 && C >= 128 && ldk % 8 == 0 && ldk <= 128)   // tensor-core banded GEMM path
     return cseg_jbu_adaptive_conv_mma((const bf16*)hr_scratch, n_crops, H2, W2, C, (const bf16*)kern, ldk, radius,
                                       (bf16*)dst, st);
   const long long tot = (long long)n_crops * H2 * W2 * (C / 8);
