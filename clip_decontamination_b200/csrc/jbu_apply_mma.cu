@@ -83,15 +83,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) adaptive_conv_mma_kernel(const bf
   const bool warp_on = cq * 64 < cvalid;         // warp-uniform: this channel quarter exists
   const bf16* hrc = hr + (size_t)crop * H2 * W2 * C + c0;
 
+  // per-thread copy plan of a source row: the (position, channel chunk) pairs a thread moves are the same for
+  // every row, so the reflect / index arithmetic is done once and a row costs LPT cp.async per thread
+  constexpr int LPT = NPOS * (CS / 8) / NTHREADS;   // 6
+  int src_off[LPT];                                  // element offset inside one source row, -1 = nothing to copy
+  uint32_t dst_off[LPT];
+#pragma unroll
+  for (int k = 0; k < LPT; ++k) {
+    const int e = tid + k * NTHREADS;
+    const int p = e / (CS / 8), ch = (e % (CS / 8)) * 8;
+    const int xx = reflect1(min(x0 - R + p, W2 - 1 + R), W2);
+    src_off[k] = (ch < cvalid) ? xx * C + ch : -1;
+    dst_off[k] = (uint32_t)(p * PSTRIDE + ch * 2);
+  }
   auto load_row = [&](int sr) {
     const int yy = reflect1(min(y0 + sr - R, H2 - 1 + R), H2);
     const uint32_t base = ring + (sr % NST) * ROW_BYTES;
-    for (int e = tid; e < NPOS * (CS / 8); e += NTHREADS) {
-      const int p = e / (CS / 8), ch = (e % (CS / 8)) * 8;
-      if (ch >= cvalid) continue;
-      const int xx = reflect1(min(x0 - R + p, W2 - 1 + R), W2);
-      cp_async16(base + p * PSTRIDE + ch * 2, hrc + ((size_t)yy * W2 + xx) * C + ch);
-    }
+    const bf16* rowp = hrc + (size_t)yy * W2 * C;
+#pragma unroll
+    for (int k = 0; k < LPT; ++k)
+      if (src_off[k] >= 0) cp_async16(base + dst_off[k], rowp + src_off[k]);
   };
 #pragma unroll
   for (int s = 0; s < NST - 1; ++s) {
@@ -99,13 +110,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) adaptive_conv_mma_kernel(const bf
     cp_async_commit();
   }
   // ---- expand the kernel weights of the tile into band tiles ----
+  // the global loads are issued first so that their latency overlaps the zero fill
+  constexpr int WPT = RW * TX * 16 / NTHREADS;       // 8 x 16-byte weight chunks per thread
+  uint4 wv[WPT];
+#pragma unroll
+  for (int k = 0; k < WPT; ++k) {
+    const int e = tid + k * NTHREADS;
+    const int v = e % 16, px = (e / 16) % TX, r = e / (16 * TX);
+    wv[k] = make_uint4(0, 0, 0, 0);
+    if (y0 + r < H2 && x0 + px < W2 && v * 8 < ldk)
+      wv[k] = __ldg(reinterpret_cast<const uint4*>(kern + (((size_t)crop * H2 + y0 + r) * W2 + x0 + px) * ldk + v * 8));
+  }
   for (int e = tid; e < WB_BYTES / 16; e += NTHREADS) reinterpret_cast<uint4*>(wb)[e] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  for (int e = tid; e < RW * TX * (128 / 8); e += NTHREADS) {
+#pragma unroll
+  for (int k = 0; k < WPT; ++k) {
+    const int e = tid + k * NTHREADS;
     const int v = e % 16, px = (e / 16) % TX, r = e / (16 * TX);
-    if (y0 + r >= H2 || x0 + px >= W2 || v * 8 >= ldk) continue;
-    const uint4 val = __ldg(reinterpret_cast<const uint4*>(kern + (((size_t)crop * H2 + y0 + r) * W2 + x0 + px) * ldk + v * 8));
-    const unsigned short* hv = reinterpret_cast<const unsigned short*>(&val);
+    const unsigned short* hv = reinterpret_cast<const unsigned short*>(&wv[k]);
     const int m = px & 15, pxb = px >> 4;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {

@@ -83,6 +83,60 @@ __global__ void layernorm_kernel(const float* x, int rows, int width, const floa
   for (int c = lane; c < width; c += 32) orow[c] = from_f32<T>((xr[c] - mean) * rstd * gamma[c] + beta[c]);
 }
 
+// single pass: the row lives in registers (float4 x LNV per lane), for width % 4 == 0 and width <= 128*LNV
+constexpr int LNV = 10;
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_reg_kernel(const float* x, int rows, int width,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, T* out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nv = width >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * width);
+  float4 buf[LNV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < LNV; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nv) {
+      buf[k] = xr[v];
+      s += (buf[k].x + buf[k].y) + (buf[k].z + buf[k].w);
+    }
+  }
+  const float mean = warp_sum(s) / width;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < LNV; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nv) {
+      const float a = buf[k].x - mean, b = buf[k].y - mean, c = buf[k].z - mean, d = buf[k].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / width + eps);
+  T* orow = out + (size_t)warp * width;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int k = 0; k < LNV; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nv) {
+      const float4 g = __ldg(g4 + v), b = __ldg(b4 + v);
+      const float o0 = (buf[k].x - mean) * rstd * g.x + b.x, o1 = (buf[k].y - mean) * rstd * g.y + b.y;
+      const float o2 = (buf[k].z - mean) * rstd * g.z + b.z, o3 = (buf[k].w - mean) * rstd * g.w + b.w;
+      if (sizeof(T) == 4) {
+        reinterpret_cast<float4*>(orow)[v] = make_float4(o0, o1, o2, o3);
+      } else {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&lo);
+        u.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(orow)[v] = u;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Attention.  One CTA per (crop, head); Q, K, V of the head live in shared memory (type T); each warp
 // owns query rows i = warp, warp+8, ...; a lane owns keys j = lane + 32 t.  All softmax arithmetic
@@ -332,30 +386,37 @@ __global__ void __launch_bounds__(256) simmap_kernel(const float* __restrict__ x
 }
 
 // ---------------------------------------------------------------------------------------------
-// outlier_suppression.py:15-61,115-214.  One CTA per crop, zero host syncs.
-//   1. ratio_i = mean_h P[0,1+i] / (mean_h P[1+i,1+i] + 1e-8); top-k by repeated argmax
-//      (ties -> lowest index).
-//   2. per (outlier, neighbour): cosine on the ORIGINAL map; replacement and decontaminated
-//      neighbour rows go to scratch.
-//   3. ordered write-back: neighbours in (i, j) order (last writer wins, cells equal to the outlier
-//      skipped), then the outliers.
+// outlier_suppression.py:15-61,115-214, zero host syncs, two kernels:
+//   plan  (one CTA per crop): ratio_i = mean_h P[0,1+i] / (mean_h P[1+i,1+i] + 1e-8); top-k by repeated
+//          argmax (ties -> lowest index); per (outlier, neighbour) cosine on the ORIGINAL map; softmax
+//          weights; and the "owner" of every cell under the reference's sequential write order
+//          (neighbours in (i, j) order, last writer wins, cells equal to the outlier skipped; outliers last).
+//   apply (one CTA per cell): writes the output row from the ORIGINAL map and the plan -- out of place, so no
+//          ordering between CTAs is needed:  none -> copy;  neighbour (i,j) -> nb - clamp(sim*temp,0,1) * o_i;
+//          outlier i -> sum_j w_ij * nb_ij.
+// plan layout per crop (32-bit words): idx[k] | nb[8k] | sim[8k] | w[8k] | owner[P]
 // ---------------------------------------------------------------------------------------------
 constexpr int OS_THREADS = 256;
 constexpr int OS_MAXK = 64;
 
-__global__ void __launch_bounds__(OS_THREADS) outlier_kernel(float* __restrict__ y, int L, int width, int grid,
-                                                             const float* __restrict__ stats, int heads, int top_k,
-                                                             float ctemp, float* __restrict__ scratch,
-                                                             int32_t* __restrict__ idx_out) {
+__global__ void __launch_bounds__(OS_THREADS) outlier_plan_kernel(const float* __restrict__ y, int L, int width, int grid,
+                                                                  const float* __restrict__ stats, int heads, int top_k,
+                                                                  int* __restrict__ plan, int32_t* __restrict__ idx_out) {
   extern __shared__ float os_smem[];
   const int P = L - 1, crop = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* ratio = os_smem;                       // [P]
   __shared__ int s_idx[OS_MAXK];
   __shared__ float s_sim[OS_MAXK][8];
-  __shared__ float s_w[OS_MAXK][8];
   __shared__ int s_nb[OS_MAXK][8];
   __shared__ float red_v[OS_THREADS / 32];
   __shared__ int red_i[OS_THREADS / 32];
+  const int k = min(top_k, P);
+  int* pl = plan + (size_t)crop * (25 * top_k + P);
+  int* p_idx = pl;
+  int* p_nb = pl + top_k;
+  float* p_sim = reinterpret_cast<float*>(pl + 9 * top_k);
+  float* p_w = reinterpret_cast<float*>(pl + 17 * top_k);
+  int* p_owner = pl + 25 * top_k;
 
   for (int i = tid; i < P; i += OS_THREADS) {
     float c = 0.f, d = 0.f;
@@ -365,9 +426,9 @@ __global__ void __launch_bounds__(OS_THREADS) outlier_kernel(float* __restrict__
       d += st[P + i];
     }
     ratio[i] = (c / heads) / (d / heads + 1e-8f);
+    p_owner[i] = -1;
   }
   __syncthreads();
-  const int k = min(top_k, P);
   for (int r = 0; r < k; ++r) {
     float bv = -INFINITY;
     int bi = 0x7fffffff;
@@ -388,15 +449,15 @@ __global__ void __launch_bounds__(OS_THREADS) outlier_kernel(float* __restrict__
         if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
       s_idx[r] = bi;
       ratio[bi] = -INFINITY;
+      p_idx[r] = bi;
       if (idx_out) idx_out[crop * top_k + r] = bi;
     }
     __syncthreads();
   }
-  float* yb = y + ((size_t)crop * L + 1) * width;  // patch rows
-  // cosine similarities, one warp per (outlier, neighbour)
+  const float* yb = y + ((size_t)crop * L + 1) * width;  // patch rows
   const int offs_y[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
   const int offs_x[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
-  for (int pr = warp; pr < k * 8; pr += OS_THREADS / 32) {
+  for (int pr = warp; pr < k * 8; pr += OS_THREADS / 32) {   // one warp per (outlier, neighbour)
     const int i = pr >> 3, j = pr & 7;
     const int oy = s_idx[i] / grid, ox = s_idx[i] % grid;
     const int ny = min(max(oy + offs_y[j], 0), grid - 1), nx = min(max(ox + offs_x[j], 0), grid - 1);
@@ -417,31 +478,55 @@ __global__ void __launch_bounds__(OS_THREADS) outlier_kernel(float* __restrict__
   }
   __syncthreads();
   for (int i = tid; i < k; i += OS_THREADS) {   // softmax(clamp(1 - sim, 0)) over the 8 neighbours
-    float w[8], m = -INFINITY, s = 0.f;
+    float w[8], m = -INFINITY, sm = 0.f;
     for (int j = 0; j < 8; ++j) { w[j] = fmaxf(1.0f - s_sim[i][j], 0.f); m = fmaxf(m, w[j]); }
-    for (int j = 0; j < 8; ++j) { w[j] = expf(w[j] - m); s += w[j]; }
-    for (int j = 0; j < 8; ++j) s_w[i][j] = w[j] / s;
-  }
-  __syncthreads();
-  float* sc = scratch + (size_t)crop * top_k * 9 * width;
-  for (int e = tid; e < k * width; e += OS_THREADS) {
-    const int i = e / width, c = e % width;
-    const float o = yb[(size_t)s_idx[i] * width + c];
-    float rep = 0.f;
+    for (int j = 0; j < 8; ++j) { w[j] = expf(w[j] - m); sm += w[j]; }
     for (int j = 0; j < 8; ++j) {
-      const float nbv = yb[(size_t)s_nb[i][j] * width + c];
-      rep = fmaf(nbv, s_w[i][j], rep);
-      const float strength = fminf(fmaxf(s_sim[i][j] * ctemp, 0.f), 1.f);
-      sc[((size_t)i * 9 + 1 + j) * width + c] = nbv - o * strength;
+      p_w[i * 8 + j] = w[j] / sm;
+      p_sim[i * 8 + j] = s_sim[i][j];
+      p_nb[i * 8 + j] = s_nb[i][j];
     }
-    sc[((size_t)i * 9) * width + c] = rep;
   }
-  __syncthreads();  // every read of the original map is done
-  for (int c = tid; c < width; c += OS_THREADS) {   // a channel is owned by one thread: writes stay ordered
+  if (tid == 0) {                                // sequential write order of the reference (:204-212)
     for (int i = 0; i < k; ++i)
       for (int j = 0; j < 8; ++j)
-        if (s_nb[i][j] != s_idx[i]) yb[(size_t)s_nb[i][j] * width + c] = sc[((size_t)i * 9 + 1 + j) * width + c];
-    for (int i = 0; i < k; ++i) yb[(size_t)s_idx[i] * width + c] = sc[((size_t)i * 9) * width + c];
+        if (s_nb[i][j] != s_idx[i]) p_owner[s_nb[i][j]] = 1000 + i * 8 + j;
+    for (int i = 0; i < k; ++i) p_owner[s_idx[i]] = i;
+  }
+}
+
+__global__ void __launch_bounds__(128) outlier_apply_kernel(const float* __restrict__ y, float* __restrict__ out, int L,
+                                                            int width, int top_k, float ctemp,
+                                                            const int* __restrict__ plan) {
+  const int P = L - 1, crop = blockIdx.x / L, t = blockIdx.x % L;
+  const float* src = y + ((size_t)crop * L + t) * width;
+  float* dst = out + ((size_t)crop * L + t) * width;
+  if (t == 0) {                                  // CLS token bypasses the module (transformer.py:727,741)
+    for (int c = threadIdx.x; c < width; c += 128) dst[c] = src[c];
+    return;
+  }
+  const int* pl = plan + (size_t)crop * (25 * top_k + P);
+  const int* p_idx = pl;
+  const int* p_nb = pl + top_k;
+  const float* p_sim = reinterpret_cast<const float*>(pl + 9 * top_k);
+  const float* p_w = reinterpret_cast<const float*>(pl + 17 * top_k);
+  const int owner = pl[25 * top_k + (t - 1)];
+  const float* yb = y + ((size_t)crop * L + 1) * width;
+  if (owner < 0) {
+    for (int c = threadIdx.x; c < width; c += 128) dst[c] = src[c];
+  } else if (owner >= 1000) {
+    const int ij = owner - 1000, i = ij >> 3;
+    const float strength = fminf(fmaxf(p_sim[ij] * ctemp, 0.f), 1.f);
+    const float* o = yb + (size_t)p_idx[i] * width;
+    for (int c = threadIdx.x; c < width; c += 128) dst[c] = src[c] - o[c] * strength;
+  } else {
+    const int i = owner;
+    for (int c = threadIdx.x; c < width; c += 128) {
+      float rep = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rep = fmaf(yb[(size_t)p_nb[i * 8 + j] * width + c], p_w[i * 8 + j], rep);
+      dst[c] = rep;
+    }
   }
 }
 
@@ -533,7 +618,13 @@ int cseg_layernorm(const float* x, int rows, int width, const float* gamma, cons
                    int out_dtype, void* out, void* stream) {
   CSEG_REQUIRE(rows > 0 && width > 0, "layernorm: bad shape");
   const int blocks = cdiv((long long)rows * 32, 256);
-  if (out_dtype == CSEG_BF16)
+  const bool reg_path = (width % 4 == 0) && width <= 128 * LNV && (((uintptr_t)x | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0;
+  if (reg_path) {
+    if (out_dtype == CSEG_BF16)
+      layernorm_reg_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, width, gamma, beta, eps, (bf16*)out);
+    else
+      layernorm_reg_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, width, gamma, beta, eps, (float*)out);
+  } else if (out_dtype == CSEG_BF16)
     layernorm_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, width, gamma, beta, eps, (bf16*)out);
   else
     layernorm_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, width, gamma, beta, eps, (float*)out);
@@ -592,14 +683,18 @@ int cseg_simmap(const float* x, int n_crops, int L, int width, float temperature
   return 0;
 }
 
-int cseg_outlier_suppress(float* y, int n_crops, int L, int width, int grid, const float* stats, int heads,
-                          int top_k, float contamination_temp, float* scratch, int32_t* outlier_idx, void* stream) {
+int cseg_outlier_suppress(const float* y, float* y_out, int n_crops, int L, int width, int grid, const float* stats,
+                          int heads, int top_k, float contamination_temp, int32_t* plan, int32_t* outlier_idx,
+                          void* stream) {
   CSEG_REQUIRE(n_crops > 0 && grid * grid == L - 1, "outlier_suppress: grid %d^2 != L-1 = %d", grid, L - 1);
   CSEG_REQUIRE(top_k > 0 && top_k <= OS_MAXK, "outlier_suppress: top_k=%d outside [1, %d]", top_k, OS_MAXK);
+  CSEG_REQUIRE(y != y_out, "outlier_suppress: runs out of place (y_out must differ from y)");
   const size_t smem = (size_t)(L - 1) * sizeof(float);
-  outlier_kernel<<<n_crops, OS_THREADS, smem, (cudaStream_t)stream>>>(y, L, width, grid, stats, heads, top_k,
-                                                                      contamination_temp, scratch, outlier_idx);
-  CSEG_LAUNCH_CHECK("outlier_suppress");
+  cudaStream_t st = (cudaStream_t)stream;
+  outlier_plan_kernel<<<n_crops, OS_THREADS, smem, st>>>(y, L, width, grid, stats, heads, top_k, plan, outlier_idx);
+  CSEG_LAUNCH_CHECK("outlier_plan");
+  outlier_apply_kernel<<<n_crops * L, 128, 0, st>>>(y, y_out, L, width, top_k, contamination_temp, plan);
+  CSEG_LAUNCH_CHECK("outlier_apply");
   return 0;
 }
 

@@ -214,10 +214,12 @@ class VisualEngine:
             if gh != gw:
                 raise NotImplementedError('outlier suppression assumes square crops (transformer.py:583)')
             k = int(outlier_cfg.get('top_k', 10))
-            scratch = ws.get('outlier_scratch', (n * k * 9 * width,), f32)
+            plan = ws.get('outlier_plan', (n * (25 * k + P),), torch.int32)
             oidx = ws.get('outlier_idx', (n, k), torch.int32)
-            ops.outlier_suppress(y, n, L, width, gh, stats, self.heads, k,
-                                 float(outlier_cfg.get('contamination_temp', 0.1)), scratch, oidx)
+            y2 = ws.get('y2', (M, width), f32)
+            ops.outlier_suppress(y, y2, n, L, width, gh, stats, self.heads, k,
+                                 float(outlier_cfg.get('contamination_temp', 0.1)), plan, oidx)
+            y = y2
             if taps is not None:
                 taps['outlier_idx'] = oidx.clone()
                 taps['suppressed'] = y.clone()

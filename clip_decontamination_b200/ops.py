@@ -103,10 +103,11 @@ def simmap(x: torch.Tensor, n_crops: int, L: int, width: int, out: torch.Tensor,
     return out
 
 
-def outlier_suppress(y, n_crops, L, width, grid, stats, heads, top_k, contamination_temp, scratch, outlier_idx=None):
-    check(lib.cseg_outlier_suppress(_ptr(y), n_crops, L, width, grid, _ptr(stats), heads, top_k, contamination_temp,
-                                    _ptr(scratch), _ptr(outlier_idx), _stream()))
-    return y
+def outlier_suppress(y, y_out, n_crops, L, width, grid, stats, heads, top_k, contamination_temp, plan, outlier_idx=None):
+    assert plan.dtype == torch.int32 and plan.numel() >= n_crops * (25 * top_k + L - 1)
+    check(lib.cseg_outlier_suppress(_ptr(y), _ptr(y_out), n_crops, L, width, grid, _ptr(stats), heads, top_k,
+                                    contamination_temp, _ptr(plan), _ptr(outlier_idx), _stream()))
+    return y_out
 
 
 def cls_debias(tok, n_crops, L, D, factor, feats, cls_unit=None):

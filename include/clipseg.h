@@ -107,12 +107,13 @@ CSEG_API int cseg_attention(int dtype, const void* qkv, int n_crops, int L, int 
 CSEG_API int cseg_simmap(const float* x, int n_crops, int L, int width, float temperature,
                 int add_self_similarity, float* simmap, void* stream);
 /* detect_outliers_by_attention + OutlierSuppressionModule.mean_interpolation
- * (outlier_suppression.py:15-61,115-214) on y [n_crops*L, width] fp32 (CLS row untouched), in place.
- * grid x grid patches, stats from cseg_attention.  scratch: >= n_crops * top_k * 9 * width floats
- * + n_crops*top_k ints.  outlier_idx (int32 [n_crops, top_k], may be NULL) receives the top-k order. */
-CSEG_API int cseg_outlier_suppress(float* y, int n_crops, int L, int width, int grid, const float* stats,
-                          int heads, int top_k, float contamination_temp, float* scratch,
-                          int32_t* outlier_idx, void* stream);
+ * (outlier_suppression.py:15-61,115-214): y [n_crops*L, width] fp32 -> y_out (same shape, OUT OF PLACE,
+ * CLS row copied).  grid x grid patches, stats from cseg_attention.  plan: int32 workspace of
+ * n_crops * (25*top_k + L-1) words.  outlier_idx (int32 [n_crops, top_k], may be NULL) receives the
+ * top-k order. */
+CSEG_API int cseg_outlier_suppress(const float* y, float* y_out, int n_crops, int L, int width, int grid,
+                          const float* stats, int heads, int top_k, float contamination_temp,
+                          int32_t* plan, int32_t* outlier_idx, void* stream);
 /* forward_feature head (segmentor.py:309-336): tok fp32 [n_crops*L, D] = ln_post(x) @ proj.
  * cls_unit[crop] = tok[crop*L] / |.|;  feats[crop, p] = f - factor * cos(f, cls) * cls_unit
  * written as T [n_crops*(L-1), ldf] (channel-last patch grid). */

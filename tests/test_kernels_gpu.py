@@ -249,11 +249,13 @@ def test_outlier_suppression(ops, grid, top_k):
     ref = O.outlier_mean_interpolation(fmap, oi, 0.1).reshape(n, w, P).permute(0, 2, 1)
     yd = y.cuda()
     k = min(top_k, P)
-    scratch = torch.empty(n * top_k * 9 * w, device='cuda')
+    plan = torch.empty(n * (25 * top_k + P), dtype=torch.int32, device='cuda')
     idx = torch.full((n, top_k), -1, dtype=torch.int32, device='cuda')
-    ops.outlier_suppress(yd, n, L, w, grid, stats.cuda(), heads, top_k, 0.1, scratch, idx)
+    yo = torch.full_like(yd, float('nan'))
+    ops.outlier_suppress(yd, yo, n, L, w, grid, stats.cuda(), heads, top_k, 0.1, plan, idx)
+    assert torch.equal(yd.cpu(), y)                     # input untouched (out of place)
     assert torch.equal(idx.cpu()[:, :k].long(), oi)
-    got = yd.cpu().view(n, L, w)
+    got = yo.cpu().view(n, L, w)
     assert torch.equal(got[:, 0], y.view(n, L, w)[:, 0])
     assert (got[:, 1:] - ref).abs().max().item() < 1e-5
 
