@@ -279,10 +279,13 @@ def main():
     def rk_work(proj, guid, n, gh, gw, radius, rt, ss, kern):
         return ('hbm', float(n * gh * gw * (32 * proj.element_size() + 16 + kern.shape[-1] * esize)))
 
-    workfns = dict(gemm=gemm_work, jbu_apply=apply_work, attention=attn_work, norm_sim=nsim_work,
+    def fns_work(y, Wt, n, hw, Cc, bias, alpha, text, logits, cls_logit_bias=None, scratch=None):
+        return ('tensor', 2.0 * n * hw * Cc * (Cc + text.shape[0]))
+
+    workfns = dict(fixup_norm_sim=fns_work, gemm=gemm_work, jbu_apply=apply_work, attention=attn_work, norm_sim=nsim_work,
                    accum_argmax=accum_work, jbu_range_kernel=rk_work)
     names = ['preprocess_u8', 'patchify', 'embed_tokens', 'layernorm', 'gemm', 'attention', 'simmap', 'outlier_suppress',
-             'cls_debias', 'jbu_guidance', 'jbu_range_proj', 'jbu_range_kernel', 'jbu_apply', 'norm_sim',
+             'cls_debias', 'jbu_guidance', 'jbu_range_proj', 'jbu_range_kernel', 'jbu_apply', 'norm_sim', 'fixup_norm_sim',
              'accum_argmax', 'iou_hist']
     for nm in names:
         orig[nm] = getattr(ops, nm)

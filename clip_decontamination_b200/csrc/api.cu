@@ -11,6 +11,9 @@ int cseg_gemm_simt(int in_dtype, const void* A, int lda, const void* B, int ldb,
                    const float* bias, const void* residual, int ldr, int res_dtype, float alpha, int act, int out_dtype, void* C,
                    int ldc, cudaStream_t st);
 
+int cseg_fixup_norm_sim_tc(const void* y, int ldy, const void* W, int ldw, int M, int C, const float* bias, float alpha,
+                           const float* text, int Q, const float* cls_bias, int hw, float* logits, cudaStream_t st);
+
 extern "C" {
 
 int cseg_version(void) { return CSEG_VERSION; }
@@ -32,6 +35,25 @@ int cseg_gemm(int in_dtype, const void* A, int lda, const void* B, int ldb, int 
   if (in_dtype == CSEG_F32)
     return cseg_gemm_simt(CSEG_F32, A, lda, B, ldb, M, N, K, bias, residual, ldr, res_dtype, alpha, act, out_dtype, C, ldc, st);
   CSEG_FAIL(CSEG_EINVAL, "gemm: unknown dtype %d", in_dtype);
+}
+
+int cseg_fixup_norm_sim(int dtype, const void* y, int ldy, const void* W, int ldw, int n_crops, int hw, int C,
+                        const float* bias, float alpha, const float* text, int Q, const float* cls_logit_bias,
+                        float* logits, void* scratch, void* stream) {
+  CSEG_REQUIRE(n_crops > 0 && hw > 0 && C > 0 && Q > 0, "fixup_norm_sim: empty problem");
+  const long long M = (long long)n_crops * hw;
+  CSEG_REQUIRE(M < (1LL << 31), "fixup_norm_sim: too many rows");
+  if (dtype == CSEG_BF16) {
+    const int rc = cseg_fixup_norm_sim_tc(y, ldy, W, ldw, (int)M, C, bias, alpha, text, Q, cls_logit_bias, hw, logits,
+                                          (cudaStream_t)stream);
+    if (rc <= 0) return rc;
+  }
+  // unfused form (fp32 verification mode, or shapes the fused kernel does not cover)
+  CSEG_REQUIRE(scratch != nullptr, "fixup_norm_sim: scratch (n_crops*hw*C elements) required for the unfused path");
+  int rc = cseg_gemm(dtype, y, ldy, W, ldw, (int)M, C, C, bias, y, ldy, dtype, alpha, CSEG_ACT_NONE, dtype, scratch, C,
+                     stream);
+  if (rc) return rc;
+  return cseg_norm_sim(dtype, scratch, C, n_crops, hw, C, text, Q, cls_logit_bias, logits, stream);
 }
 
 // test hook: CUDA-core GEMM on bf16 operands (on-device cross-check of the tcgen05 kernel)

@@ -358,7 +358,228 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
   return launch1<BN, STAGES, CSEG_ACT_NONE>(ta, tb, M, N, K, ep, st);
 }
 
+// =====================================================================================================
+// Fused final 1x1 conv + L2-normalise + cosine logits (K12 + K13 of SURVEY 2.2):
+//   out[p, :] = y[p, :] + alpha * (y[p, :] . W^T + b)        (simfeatup_dev/upsamplers.py:325)
+//   logits[crop, q, pix] = <out[p] / |out[p]|, T[q]> (+ cls bias)   (segmentor.py:374-375,378-379)
+// The C x 224^2 feature map `out` never reaches HBM: the GEMM epilogue accumulates |out|^2 and the Q dot
+// products per pixel.  Same persistent TMA / tcgen05 / TMEM pipeline as the generic kernel, but the unit of
+// scheduling is an M-panel: the NT = C/128 n-tiles of a panel go to the same CTA (one TMEM accumulator stage
+// each), so the per-row partial sums stay in registers across n-tiles.  Epilogue warps use the native TMEM
+// layout (lane = row), which makes the per-row reductions thread-local.
+// =====================================================================================================
+template <int QT>
+struct NsCfg {
+  static constexpr int BN = 128, STAGES = 3, NT_MAX = 4;
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_WARPS = 16, THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int TXT_OFF = STAGES * STAGE_BYTES;               // text  [C_MAX][QT] fp32
+  static constexpr int C_MAX = 512;
+  static constexpr int TXT_BYTES = C_MAX * QT * 4;
+  static constexpr int BIAS_OFF = TXT_OFF + TXT_BYTES;               // bias  [C_MAX] fp32
+  static constexpr int PART_OFF = BIAS_OFF + C_MAX * 4;              // part  [2][4 chunks][128 rows][QT+1]
+  static constexpr int PART_BYTES = 2 * 4 * 128 * (QT + 1) * 4;
+  static constexpr int BAR_OFF = PART_OFF + PART_BYTES;
+  static constexpr int NBARS = 2 * STAGES + 2 * NT_MAX;
+  static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
+};
+
+template <int QT>
+__global__ void __launch_bounds__(NsCfg<QT>::THREADS, 1)
+gemm_normsim_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int C,
+                    const bf16* __restrict__ y, int ldy, const float* __restrict__ bias, float alpha,
+                    const float* __restrict__ text, int Q, const float* __restrict__ cls_bias, int hw,
+                    float* __restrict__ logits) {
+  using Cf = NsCfg<QT>;
+  constexpr int BN = Cf::BN, STAGES = Cf::STAGES, ACC = Cf::NT_MAX;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + Cf::BAR_OFF);
+  uint32_t* tmem_slot = (uint32_t*)(bars + Cf::NBARS);
+  float* txt = reinterpret_cast<float*>(smem + Cf::TXT_OFF);
+  float* bs = reinterpret_cast<float*>(smem + Cf::BIAS_OFF);
+  float* part = reinterpret_cast<float*>(smem + Cf::PART_OFF);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + STAGES * 8;
+  const uint32_t tfull0 = empty0 + STAGES * 8, tempty0 = tfull0 + ACC * 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = C / BK, NT = C / BN, panels = (M + BM - 1) / BM;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + s * 8, 1);
+      mbar_init(empty0 + s * 8, 1);
+    }
+    for (int s = 0; s < ACC; ++s) {
+      mbar_init(tfull0 + s * 8, 1);
+      mbar_init(tempty0 + s * 8, Cf::EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // text (transposed to [c][QT], zero padded) and bias into shared memory
+  for (int e = threadIdx.x; e < C * QT; e += Cf::THREADS) {
+    const int c = e / QT, q = e % QT;
+    txt[e] = (q < Q) ? text[(size_t)q * C + c] : 0.f;
+  }
+  for (int c = threadIdx.x; c < C; c += Cf::THREADS) bs[c] = bias ? bias[c] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int panel = blockIdx.x; panel < panels; panel += gridDim.x)
+        for (int nt = 0; nt < NT; ++nt)
+          for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(empty0 + s * 8, ph ^ 1);
+            mbar_expect_tx(full0 + s * 8, Cf::STAGE_BYTES);
+            const uint32_t a_dst = smem_base + s * Cf::STAGE_BYTES;
+            tma_load_2d(a_dst, &tmA, full0 + s * 8, kb * BK, panel * BM);
+            tma_load_2d(a_dst + Cf::A_BYTES, &tmB, full0 + s * 8, kb * BK, nt * BN);
+          }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      uint32_t it = 0, tl = 0;
+      for (int panel = blockIdx.x; panel < panels; panel += gridDim.x)
+        for (int nt = 0; nt < NT; ++nt, ++tl) {
+          const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
+          mbar_wait(tempty0 + as * 8, aph ^ 1);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + as * BN;
+          for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(full0 + s * 8, ph);
+            tc_fence_after();
+            const uint64_t adesc = make_sdesc(smem_base + s * Cf::STAGE_BYTES);
+            const uint64_t bdesc = make_sdesc(smem_base + s * Cf::STAGE_BYTES + Cf::A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(empty0 + s * 8);
+          }
+          umma_commit(tfull0 + as * 8);
+        }
+    }
+  } else {
+    const int ew = warp - 2, lg = warp & 3, cchunk = ew >> 2;
+    uint32_t tl = 0, pi = 0;
+    for (int panel = blockIdx.x; panel < panels; panel += gridDim.x, ++pi) {
+      const int row = panel * BM + lg * 32 + lane;
+      const bool row_ok = row < M;
+      float ss = 0.f, dot[QT];
+#pragma unroll
+      for (int q = 0; q < QT; ++q) dot[q] = 0.f;
+      for (int nt = 0; nt < NT; ++nt, ++tl) {
+        const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
+        const int col0 = nt * BN + cchunk * 32;
+        // residual y[row, col0 .. col0+31] (64 B per lane), prefetched before the accumulator is ready
+        uint4 yv[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          yv[v] = row_ok ? *reinterpret_cast<const uint4*>(y + (size_t)row * ldy + col0 + v * 8) : make_uint4(0, 0, 0, 0);
+        mbar_wait(tfull0 + as * 8, aph);
+        tc_fence_after();
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + cchunk * 32), r);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + as * 8);
+        const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(yv);
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float2 yr = __bfloat1622float2(yh[j >> 1]);
+          const float o0 = fmaf(alpha, __uint_as_float(r[j]) + bs[col0 + j], yr.x);
+          const float o1 = fmaf(alpha, __uint_as_float(r[j + 1]) + bs[col0 + j + 1], yr.y);
+          ss = fmaf(o0, o0, ss);
+          ss = fmaf(o1, o1, ss);
+          const float4* t0 = reinterpret_cast<const float4*>(txt + (col0 + j) * QT);
+          const float4* t1 = reinterpret_cast<const float4*>(txt + (col0 + j + 1) * QT);
+#pragma unroll
+          for (int q4 = 0; q4 < QT / 4; ++q4) {
+            const float4 a = t0[q4], b = t1[q4];
+            dot[q4 * 4 + 0] = fmaf(o0, a.x, dot[q4 * 4 + 0]); dot[q4 * 4 + 1] = fmaf(o0, a.y, dot[q4 * 4 + 1]);
+            dot[q4 * 4 + 2] = fmaf(o0, a.z, dot[q4 * 4 + 2]); dot[q4 * 4 + 3] = fmaf(o0, a.w, dot[q4 * 4 + 3]);
+            dot[q4 * 4 + 0] = fmaf(o1, b.x, dot[q4 * 4 + 0]); dot[q4 * 4 + 1] = fmaf(o1, b.y, dot[q4 * 4 + 1]);
+            dot[q4 * 4 + 2] = fmaf(o1, b.z, dot[q4 * 4 + 2]); dot[q4 * 4 + 3] = fmaf(o1, b.w, dot[q4 * 4 + 3]);
+          }
+        }
+      }
+      // combine the four column chunks of every row in a fixed order (deterministic), then finalise
+      float* pb = part + (size_t)(pi & 1) * 4 * 128 * (QT + 1);
+      float* mine = pb + ((size_t)cchunk * 128 + lg * 32 + lane) * (QT + 1);
+      mine[0] = ss;
+#pragma unroll
+      for (int q = 0; q < QT; ++q) mine[1 + q] = dot[q];
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * NsCfg<QT>::EPI_WARPS) : "memory");   // epilogue warps only
+      if (cchunk == 0 && row_ok) {
+        float tot[QT + 1];
+#pragma unroll
+        for (int q = 0; q <= QT; ++q) tot[q] = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const float* pp = pb + ((size_t)ch * 128 + lg * 32 + lane) * (QT + 1);
+#pragma unroll
+          for (int q = 0; q <= QT; ++q) tot[q] += pp[q];
+        }
+        const float inv = 1.0f / sqrtf(tot[0]);
+        const long long crop = row / hw, pix = row % hw;
+#pragma unroll
+        for (int q = 0; q < QT; ++q)
+          if (q < Q) {
+            float v = tot[1 + q] * inv;
+            if (cls_bias) v += cls_bias[crop * Q + q];
+            logits[(crop * Q + q) * hw + pix] = v;
+          }
+      }
+      // the part buffer alternates per panel; a buffer is rewritten two panels later, after another bar.sync
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+template <int QT>
+int launch_normsim(const CUtensorMap& ta, const CUtensorMap& tb, int M, int C, const bf16* y, int ldy, const float* bias,
+                   float alpha, const float* text, int Q, const float* cls_bias, int hw, float* logits, cudaStream_t st) {
+  using Cf = NsCfg<QT>;
+  CSEG_SET_SMEM(gemm_normsim_kernel<QT>, Cf::SMEM_BYTES);
+  const int panels = cdiv(M, BM);
+  gemm_normsim_kernel<QT><<<std::min(panels, sm_count()), Cf::THREADS, Cf::SMEM_BYTES, st>>>(
+      ta, tb, M, C, y, ldy, bias, alpha, text, Q, cls_bias, hw, logits);
+  CSEG_LAUNCH_CHECK("gemm_normsim");
+  return 0;
+}
+
 }  // namespace
+
+// returns 1 when the shape is not covered by the fused kernel (caller runs cseg_gemm + cseg_norm_sim instead)
+int cseg_fixup_norm_sim_tc(const void* y, int ldy, const void* W, int ldw, int M, int C, const float* bias, float alpha,
+                           const float* text, int Q, const float* cls_bias, int hw, float* logits, cudaStream_t st) {
+  if (C % 128 != 0 || C > 512 || Q > 16 || ldy % 8 != 0 || ldw % 8 != 0) return 1;
+  CUtensorMap ta, tb;
+  int rc = make_map(&ta, y, M, C, ldy, BM);
+  if (rc) return rc;
+  rc = make_map(&tb, W, C, C, ldw, 128);
+  if (rc) return rc;
+  if (Q <= 8)
+    return launch_normsim<8>(ta, tb, M, C, (const bf16*)y, ldy, bias, alpha, text, Q, cls_bias, hw, logits, st);
+  return launch_normsim<16>(ta, tb, M, C, (const bf16*)y, ldy, bias, alpha, text, Q, cls_bias, hw, logits, st);
+}
 
 int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
                       const void* residual, int ldr, int res_dtype, float alpha, int act, int out_dtype, void* C,

@@ -273,9 +273,10 @@ class JBUEngine:
 
     def upsample(self, feats: torch.Tensor, gh: int, gw: int, img: torch.Tensor, windows: torch.Tensor,
                  crop_h: int, crop_w: int, pad_top: int = 0, pad_left: int = 0,
-                 taps: Optional[dict] = None) -> torch.Tensor:
+                 taps: Optional[dict] = None, final_conv: bool = True) -> torch.Tensor:
         """feats T [n*gh*gw, C] channel-last; returns T [n*(16gh)*(16gw), C] after the final fix-up
-        (upsamplers.py:320-325)."""
+        (upsamplers.py:320-325); with final_conv=False the output of the fourth stage (the caller fuses the
+        1x1 conv with the normalise + similarity, ``ops.fixup_norm_sim``)."""
         ws, n, C, cdt = self.ws, windows.shape[0], self.C, self.cdt
         f32 = torch.float32
         s, h, w = feats, gh, gw
@@ -299,6 +300,8 @@ class JBUEngine:
             if taps is not None:
                 taps.setdefault('jbu_stages', []).append(dst.clone())
             s, h, w = dst, GH, GW
+        if not final_conv:
+            return s
         out = ws.get('fin', (n * h * w, C), cdt)
         ops.gemm(s, self.w_fin, out, bias=self.b_fin, residual=s, alpha=0.1)
         return out
@@ -379,9 +382,11 @@ class SegEngine:
             for c0 in range(0, n, self.jbu_chunk):
                 c1 = min(n, c0 + self.jbu_chunk)
                 y = self.up.upsample(feats[c0 * P:c1 * P], gh, gw, img, win_dev[c0:c1], crop_h, crop_w, pt, pl,
-                                     taps if c0 == 0 else None)
-                ops.norm_sim(y, D, c1 - c0, crop_h * crop_w, D, self.text, logits[c0:c1],
-                             cls_bias[c0:c1] if cls_bias is not None else None)
+                                     taps if c0 == 0 else None, final_conv=False)
+                fused = (cdt == torch.bfloat16 and D % 128 == 0 and D <= 512 and self.Q <= 16)
+                scratch = None if fused else self.up.ws.get('fin', ((c1 - c0) * crop_h * crop_w, D), cdt)
+                ops.fixup_norm_sim(y, self.up.w_fin, c1 - c0, crop_h * crop_w, D, self.up.b_fin, 0.1, self.text,
+                                   logits[c0:c1], cls_bias[c0:c1] if cls_bias is not None else None, scratch)
         else:
             logits = ws.get('logits', (n, self.Q, gh, gw), torch.float32)
             ops.norm_sim(feats, D, n, P, D, self.text, logits, cls_bias)

@@ -147,6 +147,12 @@ def norm_sim(feats, ldf, n_crops, hw, D, text, logits, cls_logit_bias=None):
     return logits
 
 
+def fixup_norm_sim(y, W, n_crops, hw, Cc, bias, alpha, text, logits, cls_logit_bias=None, scratch=None):
+    check(lib.cseg_fixup_norm_sim(_dt(y), _ptr(y), y.stride(0), _ptr(W), W.stride(0), n_crops, hw, Cc, _ptr(bias), alpha,
+                                  _ptr(text), text.shape[0], _ptr(cls_logit_bias), _ptr(logits), _ptr(scratch), _stream()))
+    return logits
+
+
 def accum_argmax(crop_logits, windows, crop_h, crop_w, pad_top, pad_left, H, W, out_h, out_w, query_idx, K,
                  logit_scale, prob_thd, bg_idx, labels, probs=None, avg_logits=None):
     n, Q, lh, lw = crop_logits.shape

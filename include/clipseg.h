@@ -149,6 +149,15 @@ CSEG_API int cseg_jbu_apply(int dtype, const void* src, int n_crops, int h, int 
 CSEG_API int cseg_norm_sim(int dtype, const void* feats, int ldf, int n_crops, int hw, int D,
                   const float* text, int Q, const float* cls_logit_bias, float* logits, void* stream);
 
+/* K12 + K13 fused: final 1x1 conv of the upsampler (upsamplers.py:325) + normalise + cosine logits:
+ *   out = y + alpha * (y . W^T + bias);  logits[crop, q, pix] = <out/|out|, text[q]> (+ cls bias).
+ * y T [n_crops*hw, ldy] channel-last, W T [C, ldw].  In bf16 (C % 128 == 0, C <= 512, Q <= 16) this is ONE
+ * tcgen05 kernel whose epilogue keeps `out` on chip; otherwise cseg_gemm + cseg_norm_sim through `scratch`
+ * (T [n_crops*hw*C], may be NULL when the fused kernel applies). */
+CSEG_API int cseg_fixup_norm_sim(int dtype, const void* y, int ldy, const void* W, int ldw, int n_crops, int hw,
+                        int C, const float* bias, float alpha, const float* text, int Q,
+                        const float* cls_logit_bias, float* logits, void* scratch, void* stream);
+
 /* ---- A11 + A12: forward_slide accumulation + postprocess_result, segmentor.py:413-449,475-499 --
  * crop_logits fp32 [n_crops, Q, lh, lw]; when (lh,lw) != (crop_h,crop_w) each crop is first
  * resized bilinearly (align_corners=False) to crop_h x crop_w (segmentor.py:388-391).  The window

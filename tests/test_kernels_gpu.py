@@ -379,3 +379,24 @@ def test_iou_hist(ops):
     ops.iou_hist(pred.cuda(), lab.cuda(), K, hist)          # accumulates
     ai, ap, al = O.intersect_and_union(pred.long(), lab.long(), K)
     assert torch.equal(hist.cpu(), torch.stack([ai, ap, al]) * 2)
+
+
+@pytest.mark.parametrize('dtype,C,Q', [(torch.bfloat16, 512, 6), (torch.bfloat16, 256, 16), (torch.bfloat16, 128, 2),
+                                        (torch.float32, 64, 8), (torch.bfloat16, 64, 8)])
+def test_fixup_norm_sim(ops, dtype, C, Q):
+    """final 1x1 conv + normalise + cosine logits: fused tcgen05 epilogue (bf16, C % 128 == 0) and the
+    unfused path give the logits of upsamplers.py:325 + segmentor.py:374-375.  fp32: 2e-5; bf16: 3e-3."""
+    n, hw = 3, 333
+    y = (torch.randn(n * hw, C, generator=_g(1)) * 0.5).to(dtype)
+    W = (torch.randn(C, C, generator=_g(2)) * C ** -0.5).to(dtype)
+    b = torch.randn(C, generator=_g(3)) * 0.1
+    text = F.normalize(torch.randn(Q, C, generator=_g(4)), dim=-1)
+    cb = torch.randn(n, Q, generator=_g(5)) * 0.1
+    out = y.float() + 0.1 * (y.float() @ W.float().t() + b)
+    ref = (out / out.norm(dim=-1, keepdim=True)) @ text.t()
+    ref = ref.view(n, hw, Q).permute(0, 2, 1) + cb[:, :, None]
+    lg = torch.full((n, Q, hw), float('nan'), device='cuda')
+    scratch = torch.empty(n * hw * C, device='cuda', dtype=dtype)
+    ops.fixup_norm_sim(y.cuda(), W.cuda(), n, hw, C, b.cuda(), 0.1, text.cuda(), lg, cb.cuda(), scratch)
+    tol = 2e-5 if dtype == torch.float32 else 3e-3
+    assert (lg.cpu() - ref).abs().max().item() < tol
