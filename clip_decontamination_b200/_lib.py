@@ -40,7 +40,7 @@ SIGNATURES = {
     'cseg_cls_debias': (_i, [_p, _i, _i, _i, _f, _i, _p, _i, _p, _p]),
     'cseg_jbu_guidance': (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     'cseg_jbu_range_proj': (_i, [_p, _i, _i, _p, _p, _p, _p, _i, _p, _p]),
-    'cseg_jbu_range_kernel': (_i, [_i, _p, _p, _i, _i, _i, _i, _i, _f, _f, _i, _p, _i, _p]),
+    'cseg_jbu_range_kernel': (_i, [_i, _p, _p, _i, _i, _i, _i, _i, _f, _f, _i, _p, _i, _i, _p]),
     'cseg_jbu_apply': (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
     'cseg_norm_sim': (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
     'cseg_fixup_norm_sim': (_i, [_i, _p, _i, _p, _i, _i, _i, _i, _p, _f, _p, _i, _p, _p, _p, _p]),

@@ -72,7 +72,7 @@ template <typename T, int R, int KD>
 __global__ void __launch_bounds__(256) range_kernel_kernel(const float* __restrict__ proj,
                                                            const float4* __restrict__ guid, int gh, int gw,
                                                            float pos_temp, float inv2s2, T* __restrict__ kern,
-                                                           int ldk) {
+                                                           int kwidth, int ldk) {
   constexpr int DIA = 2 * R + 1, D2 = DIA * DIA, TS = 16, HS = TS + 2 * R;
   extern __shared__ float sp[];  // [KD][HS*HS]
   const int crop = blockIdx.z, ty0 = blockIdx.y * TS, tx0 = blockIdx.x * TS;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) range_kernel_kernel(const float* __restri
   o[D2] = from_f32<T>(g.x);
   o[D2 + 1] = from_f32<T>(g.y);
   o[D2 + 2] = from_f32<T>(g.z);
-  for (int t = D2 + 3; t < ldk; ++t) o[t] = from_f32<T>(0.f);
+  for (int t = D2 + 3; t < kwidth; ++t) o[t] = from_f32<T>(0.f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(256) adaptive_conv_kernel(const T* __restrict_
 int cseg_jbu_range_proj_f16(const float* guid, int n_pix, const float* w0, const float* b0, const float* w3,
                             const float* b3, void* proj, cudaStream_t st);
 int cseg_jbu_range_kernel_mma(const void* proj_f16, const float* guid, int n_crops, int gh, int gw, int radius,
-                              float pos_temp, float inv2s2, void* kern, int ldk, cudaStream_t st);
+                              float pos_temp, float inv2s2, void* kern, int kwidth, int ldk, cudaStream_t st);
 
 extern "C" {
 
@@ -320,13 +320,13 @@ int cseg_jbu_range_proj(const float* guid, int n_pix, int key_dim, const float* 
 
 template <typename T, int R>
 static int launch_range_kernel(const float* proj, const float* guid, int n_crops, int gh, int gw, float pos_temp,
-                               float inv2s2, void* kern, int ldk, cudaStream_t st) {
+                               float inv2s2, void* kern, int kwidth, int ldk, cudaStream_t st) {
   constexpr int HS = 16 + 2 * R;
   const size_t smem = (size_t)32 * HS * HS * sizeof(float);
   CSEG_SET_SMEM((range_kernel_kernel<T, R, 32>), smem);
   dim3 grid(cdiv(gw, 16), cdiv(gh, 16), n_crops);
   range_kernel_kernel<T, R, 32><<<grid, 256, smem, st>>>(proj, (const float4*)guid, gh, gw, pos_temp, inv2s2, (T*)kern,
-                                                         ldk);
+                                                         kwidth, ldk);
   CSEG_LAUNCH_CHECK("jbu_range_kernel");
   return 0;
 }
@@ -360,31 +360,31 @@ static int launch_apply(const void* src, int n_crops, int h, int w, int C, const
 extern "C" {
 
 int cseg_jbu_range_kernel(int proj_dtype, const void* proj_v, const float* guid, int n_crops, int gh, int gw, int key_dim,
-                          int radius, float range_temp, float sigma_spatial, int out_dtype, void* kern, int ldk,
-                          void* stream) {
+                          int radius, float range_temp, float sigma_spatial, int out_dtype, void* kern, int kwidth,
+                          int ldk, void* stream) {
   CSEG_REQUIRE(n_crops > 0 && gh > radius && gw > radius, "jbu_range_kernel: grid %dx%d too small for radius %d", gh, gw, radius);
   CSEG_REQUIRE(key_dim == 32, "jbu_range_kernel: key_dim=%d (only 32)", key_dim);
   CSEG_REQUIRE(radius == 3 || radius == 5, "jbu_range_kernel: radius=%d (3 = jbu_stack, 5 = jbu_one)", radius);
   const int d2 = (2 * radius + 1) * (2 * radius + 1);
-  CSEG_REQUIRE(ldk >= d2 + 3, "jbu_range_kernel: ldk=%d < %d", ldk, d2 + 3);
+  CSEG_REQUIRE(kwidth >= d2 + 3 && ldk >= kwidth, "jbu_range_kernel: kwidth=%d (>= %d), ldk=%d (>= kwidth)", kwidth, d2 + 3, ldk);
   // pos_temp = exp(range_temp).clamp(1e-4, 1e4)   (simfeatup_dev/upsamplers.py:237)
   const float pos_temp = fminf(fmaxf(expf(range_temp), 1e-4f), 1e4f);
   const float inv2s2 = 1.0f / (2.0f * sigma_spatial * sigma_spatial);
   cudaStream_t st = (cudaStream_t)stream;
   if (proj_dtype == CSEG_F16) {   // tensor-core path
     CSEG_REQUIRE(out_dtype == CSEG_BF16, "jbu_range_kernel: fp16 projections go with bf16 kernels");
-    const int rc = cseg_jbu_range_kernel_mma(proj_v, guid, n_crops, gh, gw, radius, pos_temp, inv2s2, kern, ldk, st);
-    if (rc == 1) CSEG_FAIL(CSEG_EUNSUPPORTED, "jbu_range_kernel(f16): radius=%d ldk=%d not covered (5/128, 3/64)", radius, ldk);
+    const int rc = cseg_jbu_range_kernel_mma(proj_v, guid, n_crops, gh, gw, radius, pos_temp, inv2s2, kern, kwidth, ldk, st);
+    if (rc == 1) CSEG_FAIL(CSEG_EUNSUPPORTED, "jbu_range_kernel(f16): radius=%d kwidth=%d not covered (5/128, 3/64)", radius, kwidth);
     return rc;
   }
   CSEG_REQUIRE(proj_dtype == CSEG_F32, "jbu_range_kernel: proj_dtype must be CSEG_F32 or CSEG_F16");
   const float* proj = (const float*)proj_v;
   if (out_dtype == CSEG_BF16) {
-    if (radius == 5) return launch_range_kernel<bf16, 5>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, ldk, st);
-    return launch_range_kernel<bf16, 3>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, ldk, st);
+    if (radius == 5) return launch_range_kernel<bf16, 5>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, kwidth, ldk, st);
+    return launch_range_kernel<bf16, 3>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, kwidth, ldk, st);
   }
-  if (radius == 5) return launch_range_kernel<float, 5>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, ldk, st);
-  return launch_range_kernel<float, 3>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, ldk, st);
+  if (radius == 5) return launch_range_kernel<float, 5>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, kwidth, ldk, st);
+  return launch_range_kernel<float, 3>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, kwidth, ldk, st);
 }
 
 int cseg_jbu_apply(int dtype, const void* src, int n_crops, int h, int w, int C, const void* kern, int ldk, int radius,

@@ -38,7 +38,8 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], u
 template <int R, int LDK>
 __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __restrict__ proj,
                                                              const float4* __restrict__ guid, int gh, int gw,
-                                                             float pos_temp, float inv2s2, bf16* __restrict__ kern) {
+                                                             float pos_temp, float inv2s2, bf16* __restrict__ kern,
+                                                             int ldk) {
   constexpr int D = 2 * R + 1, D2 = D * D;
   constexpr int NB = (16 + 2 * R + 7) / 8;       // 8-position blocks per 16-query block
   constexpr int HR = TYR + 2 * R;                // halo rows
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
     for (int e = lane; e < 16 * (LDK / 8); e += 32) {
       const int px = e / (LDK / 8), v = e % (LDK / 8);
       if (xq0 + px < gw)
-        *reinterpret_cast<uint4*>(kern + (((size_t)crop * gh + y) * gw + xq0 + px) * LDK + v * 8) =
+        *reinterpret_cast<uint4*>(kern + (((size_t)crop * gh + y) * gw + xq0 + px) * ldk + v * 8) =
             *reinterpret_cast<const uint4*>(st + px * LDK + v * 8);
     }
     __syncwarp();
@@ -186,12 +187,12 @@ __global__ void __launch_bounds__(256) range_proj_f16_kernel(const float4* __res
 
 template <int R, int LDK>
 int launch(const __half* proj, const float* guid, int n_crops, int gh, int gw, float pos_temp, float inv2s2, bf16* kern,
-           cudaStream_t st) {
+           int ldk, cudaStream_t st) {
   constexpr int D2 = (2 * R + 1) * (2 * R + 1), NB = (16 + 2 * R + 7) / 8, HR = TYR + 2 * R, NPOS = 16 + NB * 8;
   const int smem = HR * NPOS * PROW + ((D2 * 4 + 15) & ~15) + TYR * 16 * LDK * 2;
   CSEG_SET_SMEM((range_kernel_mma<R, LDK>), smem);
   dim3 grid(cdiv(gw, TXR), cdiv(gh, TYR), n_crops);
-  range_kernel_mma<R, LDK><<<grid, TYR * 32, smem, st>>>(proj, (const float4*)guid, gh, gw, pos_temp, inv2s2, kern);
+  range_kernel_mma<R, LDK><<<grid, TYR * 32, smem, st>>>(proj, (const float4*)guid, gh, gw, pos_temp, inv2s2, kern, ldk);
   CSEG_LAUNCH_CHECK("jbu_range_kernel_mma");
   return 0;
 }
@@ -207,10 +208,11 @@ int cseg_jbu_range_proj_f16(const float* guid, int n_pix, const float* w0, const
 
 // returns 1 when (radius, ldk) is not covered
 int cseg_jbu_range_kernel_mma(const void* proj_f16, const float* guid, int n_crops, int gh, int gw, int radius,
-                              float pos_temp, float inv2s2, void* kern, int ldk, cudaStream_t st) {
-  if (radius == 5 && ldk == 128)
-    return launch<5, 128>((const __half*)proj_f16, guid, n_crops, gh, gw, pos_temp, inv2s2, (bf16*)kern, st);
-  if (radius == 3 && ldk == 64)
-    return launch<3, 64>((const __half*)proj_f16, guid, n_crops, gh, gw, pos_temp, inv2s2, (bf16*)kern, st);
+                              float pos_temp, float inv2s2, void* kern, int kwidth, int ldk, cudaStream_t st) {
+  if (ldk % 8 != 0 || ((uintptr_t)kern & 15) != 0) return 1;
+  if (radius == 5 && kwidth == 128)
+    return launch<5, 128>((const __half*)proj_f16, guid, n_crops, gh, gw, pos_temp, inv2s2, (bf16*)kern, ldk, st);
+  if (radius == 3 && kwidth == 64)
+    return launch<3, 64>((const __half*)proj_f16, guid, n_crops, gh, gw, pos_temp, inv2s2, (bf16*)kern, ldk, st);
   return 1;
 }

@@ -254,10 +254,13 @@ class JBUEngine:
                 w0[:d2, :d2 + 3] = f32(sd[pre + 'fixup_proj.0.weight']).reshape(d2, d2 + 3)
                 b0 = torch.zeros(ldk, device=self.device)
                 b0[:d2] = f32(sd[pre + 'fixup_proj.0.bias'])
-                w3 = torch.zeros(ldk, ldk, device=self.device)
-                w3[:d2, :d2] = f32(sd[pre + 'fixup_proj.3.weight']).reshape(d2, d2)
+                # second fix-up conv as ONE GEMM without a residual read: kernel += 0.1 * (W3 . hidden + b3) is
+                # [hidden | kernel] . [0.1 W3 | I]^T + 0.1 b3  (the identity block passes the bf16 kernel exactly)
+                w3 = torch.zeros(ldk, 2 * ldk, device=self.device)
+                w3[:d2, :d2] = 0.1 * f32(sd[pre + 'fixup_proj.3.weight']).reshape(d2, d2)
+                w3[:, ldk:] = torch.eye(ldk, device=self.device)
                 b3 = torch.zeros(ldk, device=self.device)
-                b3[:d2] = f32(sd[pre + 'fixup_proj.3.bias'])
+                b3[:d2] = 0.1 * f32(sd[pre + 'fixup_proj.3.bias'])
                 cache[pre] = dict(
                     radius=r, ldk=ldk,
                     range_temp=float(sd[pre + 'range_temp']), sigma=float(sd[pre + 'sigma_spatial']),
@@ -287,11 +290,12 @@ class JBUEngine:
             ops.jbu_guidance(img, windows, crop_h, crop_w, pad_top, pad_left, GH, GW, guid)
             proj = ws.get('proj', (npix, 32), torch.float16 if cdt == torch.bfloat16 else f32)
             ops.jbu_range_proj(guid, npix, st['rp_w0'], st['rp_b0'], st['rp_w3'], st['rp_b3'], proj)
-            kern = ws.get('kern', (npix, st['ldk']), cdt)
-            ops.jbu_range_kernel(proj, guid, n, GH, GW, st['radius'], st['range_temp'], st['sigma'], kern)
-            hid = ws.get('hid', (npix, st['ldk']), cdt)
-            ops.gemm(kern, st['fx_w0'], hid, bias=st['fx_b0'], act=ACT_GELU)          # fixup_proj.0 + GELU
-            ops.gemm(hid, st['fx_w3'], kern, bias=st['fx_b3'], residual=kern, alpha=0.1)  # kernel += .1 * fixup
+            kw = st['ldk']
+            hk = ws.get('hidkern', (npix, 2 * kw), cdt)                                # [hidden | kernel] rows
+            ops.jbu_range_kernel(proj, guid, n, GH, GW, st['radius'], st['range_temp'], st['sigma'], hk[:, kw:])
+            ops.gemm(hk[:, kw:], st['fx_w0'], hk[:, :kw], bias=st['fx_b0'], act=ACT_GELU)   # fixup_proj.0 + GELU
+            kern = ws.get('kern', (npix, kw), cdt)
+            ops.gemm(hk, st['fx_w3'], kern, bias=st['fx_b3'])                          # kernel + .1 * fixup_proj.3
             if taps is not None:
                 taps.setdefault('jbu_kernels', []).append(kern.clone())
             hr = ws.get('hr', (npix, C), cdt)

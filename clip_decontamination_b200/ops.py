@@ -130,8 +130,10 @@ def jbu_range_proj(guid, n_pix, w0, b0, w3, b3, proj):
 
 
 def jbu_range_kernel(proj, guid, n_crops, gh, gw, radius, range_temp, sigma_spatial, kern):
+    """kern: 2-D (possibly column-sliced) view [n*gh*gw, kwidth]; its row stride is passed as ldk."""
+    assert kern.dim() == 2 and kern.stride(1) == 1
     check(lib.cseg_jbu_range_kernel(_dt(proj), _ptr(proj), _ptr(guid), n_crops, gh, gw, 32, radius, range_temp, sigma_spatial,
-                                    _dt(kern), _ptr(kern), kern.shape[-1], _stream()))
+                                    _dt(kern), C.c_void_p(kern.data_ptr()), kern.shape[1], kern.stride(0), _stream()))
     return kern
 
 

@@ -131,12 +131,13 @@ CSEG_API int cseg_jbu_guidance(const float* img_chw, int H, int W, const int32_t
  * fp16 under autocast, segmentor.py:370). */
 CSEG_API int cseg_jbu_range_proj(const float* guid, int n_pix, int key_dim, const float* w0, const float* b0,
                         const float* w3, const float* b3, int proj_dtype, void* proj, void* stream);
-/* get_range_kernel x get_spatial_kernel, renormalised (:230-251,258-262).  kern: T [n*gh*gw, ldk]
- * with columns [0,d*d) = combined kernel, [d*d, d*d+3) = guidance RGB (the fixup_proj input order,
- * :264), rest zero. */
+/* get_range_kernel x get_spatial_kernel, renormalised (:230-251,258-262).  kern: T rows of stride ldk;
+ * columns [0,d*d) = combined kernel, [d*d, d*d+3) = guidance RGB (the fixup_proj input order, :264),
+ * [d*d+3, kwidth) = zero; columns >= kwidth are not touched (the engine keeps the fix-up hidden layer in
+ * the other half of the same rows). */
 CSEG_API int cseg_jbu_range_kernel(int proj_dtype, const void* proj, const float* guid, int n_crops, int gh,
                           int gw, int key_dim, int radius, float range_temp, float sigma_spatial,
-                          int out_dtype, void* kern, int ldk, void* stream);
+                          int out_dtype, void* kern, int kwidth, int ldk, void* stream);
 /* bicubic x2 (align_corners=False, a=-0.75) + reflect pad + adaptive conv (:268-274, semantics of
  * adaptive_conv_py_simple :14-25).  src T [n, h, w, C] channel-last -> dst T [n, 2h, 2w, C];
  * kern T [n*2h*2w, ldk] (first d*d columns used); hr_scratch: T [n*2h*2w*C] workspace. */
