@@ -18,7 +18,7 @@
 namespace {
 
 constexpr int RW = 4;      // output rows per CTA
-constexpr int TX = 32;     // output pixels per CTA (2 MMA pixel blocks)
+constexpr int TX = 16;     // output pixels per CTA (one MMA pixel block; two CTAs are resident per SM)
 constexpr int CS = 256;    // channels per CTA (4 warps x 64)
 constexpr int NPOS = TX + 16;                 // source positions per row buffer (x0-R .. incl. K padding)
 constexpr int PSTRIDE = CS * 2 + 16;          // bytes per position in the ring (padded)
@@ -26,7 +26,8 @@ constexpr int NST = 3;                        // ring stages
 constexpr int ROW_BYTES = NPOS * PSTRIDE;
 constexpr int ASTRIDE = 80;                   // bytes per row of a band tile (32 bf16 + pad: conflict-free ldmatrix)
 constexpr int ATILE = 16 * ASTRIDE;           // one 16 x 32 band tile
-constexpr int NTHREADS = 256;
+constexpr int XB = TX / 16;                   // MMA pixel blocks per CTA
+constexpr int NTHREADS = 128 * XB;
 
 __device__ __forceinline__ int reflect1(int i, int n) {
   if (i < 0) i = -i;
@@ -57,24 +58,24 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// CTA = RW output rows x 32 pixels x 256 channels; 8 warps = 2 pixel blocks x 4 channel quarters (8 n-blocks
+// CTA = RW output rows x TX pixels x 256 channels; warps = TX/16 pixel blocks x 4 channel quarters (8 n-blocks
 // of 8 channels each).  The kernel weights of the tile are expanded ONCE into band tiles in shared memory
 // (Wband[r][i][xb][m][k] = kern[px(m)][i*D + k - m] for 0 <= k-m < D, zero elsewhere), so an A fragment is
 // two ldmatrix.x4 instead of a predicated gather, and it is shared by the four channel-quarter warps.
 template <int R>
-__global__ void __launch_bounds__(NTHREADS, 1) adaptive_conv_mma_kernel(const bf16* __restrict__ hr, int H2, int W2, int C,
+__global__ void __launch_bounds__(NTHREADS, 2 / XB) adaptive_conv_mma_kernel(const bf16* __restrict__ hr, int H2, int W2, int C,
                                                                         const bf16* __restrict__ kern, int ldk,
                                                                         bf16* __restrict__ dst) {
   constexpr int D = 2 * R + 1;
   constexpr int NSRC = RW + 2 * R;  // source rows per tile
-  constexpr int WB_BYTES = RW * D * 2 * ATILE;
+  constexpr int WB_BYTES = RW * D * XB * ATILE;
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem);
   uint8_t* wb = smem + NST * ROW_BYTES;
   const uint32_t wband = ring + NST * ROW_BYTES;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int xb = warp & 1, cq = warp >> 1;
+  const int xb = warp % XB, cq = warp / XB;
   const int g = lane >> 2, tig = lane & 3;
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * RW;
   const int nslab = (C + CS - 1) / CS;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) adaptive_conv_mma_kernel(const bf
       const int t = v * 8 + q;
       if (t < D * D) {
         const int i = t / D, j = t - i * D;
-        *reinterpret_cast<unsigned short*>(wb + ((r * D + i) * 2 + pxb) * ATILE + m * ASTRIDE + (j + m) * 2) = hv[q];
+        *reinterpret_cast<unsigned short*>(wb + ((r * D + i) * XB + pxb) * ATILE + m * ASTRIDE + (j + m) * 2) = hv[q];
       }
     }
   }
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) adaptive_conv_mma_kernel(const bf
         const int i = sr - r;  // tap row of output row r fed by this source row
         if (i < 0 || i >= D) continue;
         uint32_t a[4];
-        ldsm_x4(wband + (uint32_t)(((r * D + i) * 2 + xb) * ATILE + ks * 32) + a_lane_off, a);
+        ldsm_x4(wband + (uint32_t)(((r * D + i) * XB + xb) * ATILE + ks * 32) + a_lane_off, a);
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) mma_bf16(acc[r][nb], a, bfr[nb >> 1][(nb & 1) * 2], bfr[nb >> 1][(nb & 1) * 2 + 1]);
       }
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) adaptive_conv_mma_kernel(const bf
 template <int R>
 int launch_conv(const bf16* hr, int n_crops, int H2, int W2, int C, const bf16* kern, int ldk, bf16* dst, cudaStream_t st) {
   constexpr int D = 2 * R + 1;
-  const int smem = NST * ROW_BYTES + RW * D * 2 * ATILE;
+  const int smem = NST * ROW_BYTES + RW * D * XB * ATILE;
   CSEG_SET_SMEM(adaptive_conv_mma_kernel<R>, smem);
   dim3 grid(cdiv(W2, TX), cdiv(H2, RW), n_crops * cdiv(C, CS));
   CSEG_REQUIRE(grid.z <= 65535, "jbu_apply(bf16): too many crop x channel slabs (%u)", grid.z);

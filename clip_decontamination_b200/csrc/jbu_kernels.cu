@@ -178,74 +178,113 @@ template <> struct V8<float> {
   }
 };
 
-// One thread = one source pixel (y, x) x 8 channels -> the 2x2 output block (2y..2y+1, 2x..2x+1).
+// One thread = a 2x2 block of source pixels x 4 channels -> the 4x4 output block (4y0..4y0+3, 4x0..4x0+3).
 // Output row 2y samples source rows y-2..y+1 with t = 0.75, row 2y+1 samples y-1..y+2 with t = 0.25
-// (src = (dst + 0.5) / 2 - 0.5), so the block needs a clamped 5x5 neighbourhood: 25 16-byte loads for
-// 4 outputs instead of 16 scalar loads per output.  Horizontal pass first, then vertical (torch order).
+// (src = (dst + 0.5) / 2 - 0.5), so the block needs a clamped 6x6 neighbourhood: 36 loads for 16 outputs
+// (2.25 per output; the one-output-per-thread form needs 16).  Horizontal pass first, then vertical
+// (torch order).  4 channels per thread keep the 16 x 4 accumulators in registers.
+template <typename T> struct V4;
+template <> struct V4<bf16> {
+  static __device__ __forceinline__ void ld(const bf16* p, float (&v)[4]) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void st(bf16* p, const float (&v)[4]) {
+    uint2 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+    h[0] = __floats2bfloat162_rn(v[0], v[1]);
+    h[1] = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+template <> struct V4<float> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256) bicubic2x_kernel(const T* __restrict__ src, int n_crops, int h, int w, int C,
                                                         T* __restrict__ dst) {
-  const int cg = C / 8;
-  const long long total = (long long)n_crops * h * w * cg;
+  const int cg = C / 4, hb = (h + 1) / 2, wb = (w + 1) / 2;
+  const long long total = (long long)n_crops * hb * wb * cg;
   float cA[4], cB[4];
   cubic_coeffs(0.75f, cA);   // even output index
   cubic_coeffs(0.25f, cB);   // odd output index
-  const int W2 = 2 * w;
+  const int W2 = 2 * w, H2 = 2 * h;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(idx % cg);
     long long r = idx / cg;
-    const int x = (int)(r % w);
-    r /= w;
-    const int y = (int)(r % h), crop = (int)(r / h);
-    const T* sb = src + (size_t)crop * h * w * C + g * 8;
-    float o[2][2][8];
+    const int bx = (int)(r % wb);
+    r /= wb;
+    const int by = (int)(r % hb), crop = (int)(r / hb);
+    const int y0 = 2 * by, x0 = 2 * bx;                 // source block origin
+    const T* sb = src + (size_t)crop * h * w * C + g * 4;
+    float o[4][4][4];                                   // [out row][out col][channel]
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 2; ++b)
+      for (int b = 0; b < 4; ++b)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[a][b][e] = 0.f;
+        for (int e = 0; e < 4; ++e) o[a][b][e] = 0.f;
 #pragma unroll
-    for (int dy = -2; dy <= 2; ++dy) {
-      const int yy = min(max(y + dy, 0), h - 1);
-      float he[8], ho[8];
+    for (int dy = -2; dy <= 3; ++dy) {                  // source rows y0-2 .. y0+3
+      const int yy = min(max(y0 + dy, 0), h - 1);
+      float hz[4][4];                                   // horizontally interpolated, 4 output columns
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { he[e] = 0.f; ho[e] = 0.f; }
+      for (int b = 0; b < 4; ++b)
 #pragma unroll
-      for (int dx = -2; dx <= 2; ++dx) {
-        const int xx = min(max(x + dx, 0), w - 1);
-        float v[8];
-        V8<T>::ld(sb + ((size_t)yy * w + xx) * C, v);
+        for (int e = 0; e < 4; ++e) hz[b][e] = 0.f;
+#pragma unroll
+      for (int dx = -2; dx <= 3; ++dx) {                // source cols x0-2 .. x0+3
+        const int xx = min(max(x0 + dx, 0), w - 1);
+        float v[4];
+        V4<T>::ld(sb + ((size_t)yy * w + xx) * C, v);
+        // output col 0 (= 2*x0):   src x0-2..x0+1 (cA);  col 1 (2*x0+1): x0-1..x0+2 (cB)
+        // output col 2 (= 2*x0+2): src x0-1..x0+2 (cA);  col 3:           x0..x0+3   (cB)
         if (dx <= 1) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) he[e] = fmaf(cA[dx + 2], v[e], he[e]);
+          for (int e = 0; e < 4; ++e) hz[0][e] = fmaf(cA[dx + 2], v[e], hz[0][e]);
         }
-        if (dx >= -1) {
+        if (dx >= -1 && dx <= 2) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) ho[e] = fmaf(cB[dx + 1], v[e], ho[e]);
+          for (int e = 0; e < 4; ++e) {
+            hz[1][e] = fmaf(cB[dx + 1], v[e], hz[1][e]);
+            hz[2][e] = fmaf(cA[dx + 1], v[e], hz[2][e]);
+          }
+        }
+        if (dx >= 0) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) hz[3][e] = fmaf(cB[dx], v[e], hz[3][e]);
         }
       }
-      if (dy <= 1) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          o[0][0][e] = fmaf(cA[dy + 2], he[e], o[0][0][e]);
-          o[0][1][e] = fmaf(cA[dy + 2], ho[e], o[0][1][e]);
-        }
-      }
-      if (dy >= -1) {
+      for (int b = 0; b < 4; ++b)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          o[1][0][e] = fmaf(cB[dy + 1], he[e], o[1][0][e]);
-          o[1][1][e] = fmaf(cB[dy + 1], ho[e], o[1][1][e]);
+        for (int e = 0; e < 4; ++e) {
+          if (dy <= 1) o[0][b][e] = fmaf(cA[dy + 2], hz[b][e], o[0][b][e]);
+          if (dy >= -1 && dy <= 2) {
+            o[1][b][e] = fmaf(cB[dy + 1], hz[b][e], o[1][b][e]);
+            o[2][b][e] = fmaf(cA[dy + 1], hz[b][e], o[2][b][e]);
+          }
+          if (dy >= 0) o[3][b][e] = fmaf(cB[dy], hz[b][e], o[3][b][e]);
         }
-      }
     }
-    T* ob = dst + (size_t)crop * 4 * h * w * C + g * 8;
+    T* ob = dst + (size_t)crop * H2 * W2 * C + g * 4;
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 2; ++b) V8<T>::st(ob + ((size_t)(2 * y + a) * W2 + 2 * x + b) * C, o[a][b]);
+      for (int b = 0; b < 4; ++b) {
+        const int Y = 2 * y0 + a, X = 2 * x0 + b;
+        if (Y < H2 && X < W2) V4<T>::st(ob + ((size_t)Y * W2 + X) * C, o[a][b]);
+      }
   }
 }
 
@@ -338,7 +377,7 @@ template <typename T>
 static int launch_apply(const void* src, int n_crops, int h, int w, int C, const void* kern, int ldk, int radius,
                         void* dst, void* hr_scratch, cudaStream_t st) {
   const int H2 = 2 * h, W2 = 2 * w;
-  const long long tot_b = (long long)n_crops * h * w * (C / 8);
+  const long long tot_b = (long long)n_crops * ((h + 1) / 2) * ((w + 1) / 2) * (C / 4);
   bicubic2x_kernel<T><<<(int)std::min<long long>((tot_b + 255) / 256, (long long)sm_count() * 32), 256, 0, st>>>(
       (const T*)src, n_crops, h, w, C, (T*)hr_scratch);
   CSEG_LAUNCH_CHECK("jbu_bicubic2x");
