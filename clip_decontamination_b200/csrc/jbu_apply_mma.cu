@@ -124,19 +124,26 @@ __global__ void __launch_bounds__(NTHREADS, 2 / XB) adaptive_conv_mma_kernel(con
   }
   for (int e = tid; e < WB_BYTES / 16; e += NTHREADS) reinterpret_cast<uint4*>(wb)[e] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-#pragma unroll
-  for (int k = 0; k < WPT; ++k) {
-    const int e = tid + k * NTHREADS;
-    const int v = e % 16, px = (e / 16) % TX, r = e / (16 * TX);
-    const unsigned short* hv = reinterpret_cast<const unsigned short*>(&wv[k]);
-    const int m = px & 15, pxb = px >> 4;
+  {
+    // NTHREADS % 16 == 0, so the 16-byte chunk index v = tid & 15 (hence the 8 taps a thread scatters) is the
+    // same for all of its chunks: the tap -> (i, j) split is done once per thread
+    const int v = tid & 15;
+    int toff[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int t = v * 8 + q;
-      if (t < D * D) {
-        const int i = t / D, j = t - i * D;
-        *reinterpret_cast<unsigned short*>(wb + ((r * D + i) * XB + pxb) * ATILE + m * ASTRIDE + (j + m) * 2) = hv[q];
-      }
+      const int t = v * 8 + q, i = t / D, j = t - i * D;
+      toff[q] = (t < D * D) ? i * XB * ATILE + j * 2 : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) {
+      const int e = tid + k * NTHREADS;
+      const int px = (e / 16) % TX, r = e / (16 * TX);
+      const unsigned short* hv = reinterpret_cast<const unsigned short*>(&wv[k]);
+      const int m = px & 15, pxb = px >> 4;
+      uint8_t* base = wb + (r * D * XB + pxb) * ATILE + m * (ASTRIDE + 2);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (toff[q] >= 0) *reinterpret_cast<unsigned short*>(base + toff[q]) = hv[q];
     }
   }
 
@@ -162,20 +169,42 @@ __global__ void __launch_bounds__(NTHREADS, 2 / XB) adaptive_conv_mma_kernel(con
     cp_async_commit();
     if (!warp_on) continue;
     const uint32_t rowbase = ring + (sr % NST) * ROW_BYTES;
+    if (sr >= RW - 1 && sr < D) {
+      // interior source row: it feeds all RW output rows (tap rows i = sr - r).  Branch-free, so all sixteen
+      // fragment loads are issued before the 64 MMAs and their latency overlaps the tensor pipe.
+      uint32_t bfr[2][4][4], a[2][RW][4];
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      uint32_t bfr[4][4];
-      const uint32_t baddr = rowbase + (uint32_t)((xb * 16 + ks * 16) * PSTRIDE) + b_lane_off;
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t baddr = rowbase + (uint32_t)((xb * 16 + ks * 16) * PSTRIDE) + b_lane_off;
 #pragma unroll
-      for (int j2 = 0; j2 < 4; ++j2) ldsm_x4_trans(baddr + j2 * 32, bfr[j2]);
+        for (int j2 = 0; j2 < 4; ++j2) ldsm_x4_trans(baddr + j2 * 32, bfr[ks][j2]);
 #pragma unroll
-      for (int r = 0; r < RW; ++r) {
-        const int i = sr - r;  // tap row of output row r fed by this source row
-        if (i < 0 || i >= D) continue;
-        uint32_t a[4];
-        ldsm_x4(wband + (uint32_t)(((r * D + i) * XB + xb) * ATILE + ks * 32) + a_lane_off, a);
+        for (int r = 0; r < RW; ++r)
+          ldsm_x4(wband + (uint32_t)(((r * D + (sr - r)) * XB + xb) * ATILE + ks * 32) + a_lane_off, a[ks][r]);
+      }
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb) mma_bf16(acc[r][nb], a, bfr[nb >> 1][(nb & 1) * 2], bfr[nb >> 1][(nb & 1) * 2 + 1]);
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int r = 0; r < RW; ++r)
+#pragma unroll
+          for (int nb = 0; nb < 8; ++nb)
+            mma_bf16(acc[r][nb], a[ks][r], bfr[ks][nb >> 1][(nb & 1) * 2], bfr[ks][nb >> 1][(nb & 1) * 2 + 1]);
+    } else {
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t bfr[4][4];
+        const uint32_t baddr = rowbase + (uint32_t)((xb * 16 + ks * 16) * PSTRIDE) + b_lane_off;
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) ldsm_x4_trans(baddr + j2 * 32, bfr[j2]);
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+          const int i = sr - r;  // tap row of output row r fed by this source row
+          if (i < 0 || i >= D) continue;
+          uint32_t a[4];
+          ldsm_x4(wband + (uint32_t)(((r * D + i) * XB + xb) * ATILE + ks * 32) + a_lane_off, a);
+#pragma unroll
+          for (int nb = 0; nb < 8; ++nb) mma_bf16(acc[r][nb], a, bfr[nb >> 1][(nb & 1) * 2], bfr[nb >> 1][(nb & 1) * 2 + 1]);
+        }
       }
     }
   }
