@@ -79,54 +79,88 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
       ldsm4(base + 32, a[1]);
     }
     float mx[2] = {-INFINITY, -INFINITY}, se[2] = {0.f, 0.f}, sg[2] = {0.f, 0.f}, inv[2] = {0.f, 0.f};
-#pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {
-#pragma unroll 1
-      for (int i = 0; i < D; ++i) {
-        const uint32_t rowb = psm + (uint32_t)(((warp + i) * NPOS + xb * 16 + rr) * PROW + q * 16);
+    // tap column j of fragment element (nb, e) does not depend on the tap row i: hoist it (and its validity)
+    int jj[NB][4];
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-          uint32_t b[4];
-          ldsm4(rowb + nb * 8 * PROW, b);
-          float S[4] = {0.f, 0.f, 0.f, 0.f};
-          mma_f16(S, a[0], b[0], b[1]);
-          mma_f16(S, a[1], b[2], b[3]);
+    for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int h = e >> 1, m = g + h * 8, j = nb * 8 + 2 * tig + (e & 1) - m;
-            if (j < 0 || j >= D) continue;
-            const float lg = S[e] * pos_temp;
-            if (pass == 0) {
-              mx[h] = fmaxf(mx[h], lg);
-            } else {
-              const float ex = __expf(lg - mx[h]);
-              const float gz = gauss[i * D + j];
-              if (pass == 1) {
-                se[h] += ex;
-                sg[h] = fmaf(ex, gz, sg[h]);
-              } else {
-                st[m * LDK + i * D + j] = __float2bfloat16_rn(ex * gz * inv[h]);
-              }
-            }
-          }
-        }
+      for (int e = 0; e < 4; ++e) {
+        const int j = nb * 8 + 2 * tig + (e & 1) - (g + (e >> 1) * 8);
+        jj[nb][e] = (j >= 0 && j < D) ? j : -1;
       }
-      if (pass == 0) {
+    const uint32_t rowb0 = psm + (uint32_t)((warp * NPOS + xb * 16 + rr) * PROW + q * 16);
+    // ---- pass 0: row maxima ----
+#pragma unroll 1
+    for (int i = 0; i < D; ++i) {
+      const uint32_t rowb = rowb0 + (uint32_t)(i * NPOS * PROW);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
-          mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
-        }
-      } else if (pass == 1) {
+      for (int nb = 0; nb < NB; ++nb) {
+        uint32_t b[4];
+        ldsm4(rowb + nb * 8 * PROW, b);
+        float S[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16(S, a[0], b[0], b[1]);
+        mma_f16(S, a[1], b[2], b[3]);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          se[h] += __shfl_xor_sync(0xffffffffu, se[h], 1);
-          se[h] += __shfl_xor_sync(0xffffffffu, se[h], 2);
-          sg[h] += __shfl_xor_sync(0xffffffffu, sg[h], 1);
-          sg[h] += __shfl_xor_sync(0xffffffffu, sg[h], 2);
-          const float ise = 1.0f / se[h];
-          inv[h] = ise / fmaxf(sg[h] * ise, 1e-7f);           // softmax, then / sum(softmax*gauss).clamp(1e-7)
-        }
+        for (int e = 0; e < 4; ++e)
+          if (jj[nb][e] >= 0) mx[e >> 1] = fmaxf(mx[e >> 1], S[e]);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+      mx[h] *= pos_temp;                                       // pos_temp > 0: max commutes with the scaling
+    }
+    // ---- pass 1: sum exp, sum exp * gauss ----
+#pragma unroll 1
+    for (int i = 0; i < D; ++i) {
+      const uint32_t rowb = rowb0 + (uint32_t)(i * NPOS * PROW);
+      const float* gi = gauss + i * D;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        uint32_t b[4];
+        ldsm4(rowb + nb * 8 * PROW, b);
+        float S[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16(S, a[0], b[0], b[1]);
+        mma_f16(S, a[1], b[2], b[3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (jj[nb][e] >= 0) {
+            const float ex = __expf(fmaf(S[e], pos_temp, -mx[e >> 1]));
+            se[e >> 1] += ex;
+            sg[e >> 1] = fmaf(ex, gi[jj[nb][e]], sg[e >> 1]);
+          }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      se[h] += __shfl_xor_sync(0xffffffffu, se[h], 1);
+      se[h] += __shfl_xor_sync(0xffffffffu, se[h], 2);
+      sg[h] += __shfl_xor_sync(0xffffffffu, sg[h], 1);
+      sg[h] += __shfl_xor_sync(0xffffffffu, sg[h], 2);
+      const float ise = 1.0f / se[h];
+      inv[h] = ise / fmaxf(sg[h] * ise, 1e-7f);               // softmax, then / sum(softmax*gauss).clamp(1e-7)
+    }
+    // ---- pass 2: normalised kernel values into the staging rows ----
+#pragma unroll 1
+    for (int i = 0; i < D; ++i) {
+      const uint32_t rowb = rowb0 + (uint32_t)(i * NPOS * PROW);
+      const float* gi = gauss + i * D;
+      bf16* sti = st + i * D;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        uint32_t b[4];
+        ldsm4(rowb + nb * 8 * PROW, b);
+        float S[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_f16(S, a[0], b[0], b[1]);
+        mma_f16(S, a[1], b[2], b[3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (jj[nb][e] >= 0) {
+            const int h = e >> 1;
+            const float ex = __expf(fmaf(S[e], pos_temp, -mx[h]));
+            sti[(g + h * 8) * LDK + jj[nb][e]] = __float2bfloat16_rn(ex * gi[jj[nb][e]] * inv[h]);
+          }
       }
     }
     // guidance channels + zero padding (columns D2 .. LDK-1), then coalesced row stores
