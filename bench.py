@@ -32,6 +32,14 @@ CROPS = 16
 WORKLOAD = ('Vaihingen-shaped 512x512 synthetic tile, ViT-B/16 + jbu_one (C=512, r=5), Q=K=6, slide 224/112 '
             '(16 crops), base_config extras ON')
 METRIC = 'megapixels/sec segmented (ViT-B/16, 512x512 tiles, jbu_one)'
+# other BASELINE.json configs, selectable with --workload (the default above is the benchmark line)
+WORKLOADS = {
+    'vaihingen512': dict(H=512, W=512, model='ViT-B/16', cls='vaihingen', thd=0.1, bg=5, up=True),
+    'potsdam512': dict(H=512, W=512, model='ViT-B/16', cls='potsdam', thd=0.1, bg=5, up=True),
+    'isaid896': dict(H=896, W=896, model='ViT-B/16', cls='isaid', thd=0.4, bg=0, up=True),
+    'road1024': dict(H=1024, W=1024, model='ViT-B/16', cls='roadval', thd=0.7, bg=0, up=True),
+    'vaihingen512_noup': dict(H=512, W=512, model='ViT-B/16', cls='vaihingen', thd=0.1, bg=5, up=False),
+}
 
 
 def _peaks():
@@ -87,20 +95,21 @@ class ClockSampler:
                     reasons=reasons, samples=len(sm))
 
 
-def build_model(device, precision='bf16'):
+def build_model(device, precision='bf16', wl=None):
     from clip_decontamination_b200.open_clip import create_model
     from clip_decontamination_b200.open_clip.synthetic import synthetic_jbu_state_dict
     from clip_decontamination_b200.segmentor import SegmentorEx
+    wl = wl or WORKLOADS['vaihingen512']
     gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'bench_text.npz'))
-    net = create_model('ViT-B/16', pretrained=None, precision='fp32' if precision == 'fp32' else 'fp16')
-    return SegmentorEx(clip_type='CLIP', vit_type='ViT-B/16', model_type='Experimental',
-                       name_path=os.path.join(ROOT, 'configs', 'cls_vaihingen.txt'), device=device,
-                       prob_thd=0.1, bg_idx=5, apply_sim_feat_up=True, global_debias_factor=0.2,
+    net = create_model(wl['model'], pretrained=None, precision='fp32' if precision == 'fp32' else 'fp16')
+    return SegmentorEx(clip_type='CLIP', vit_type=wl['model'], model_type='Experimental',
+                       name_path=os.path.join(ROOT, 'configs', f"cls_{wl['cls']}.txt"), device=device,
+                       prob_thd=wl['thd'], bg_idx=wl['bg'], apply_sim_feat_up=wl['up'], global_debias_factor=0.2,
                        apply_outlier_suppression=True, outlier_suppression_cfg=dict(top_k=30),
                        apply_similarity_enhancement=True,
                        similarity_enhancement_cfg=dict(similarity_weight=1.0, temperature=1.0, add_self_similarity=True),
                        sim_feat_up_cfg=dict(model_name='jbu_one', model_path=None), precision=precision, net=net,
-                       query_features=torch.from_numpy(gold['vaihingen_query_features']),
+                       query_features=torch.from_numpy(gold[f"{wl['cls']}_query_features"]),
                        upsampler_state_dict=synthetic_jbu_state_dict('jbu_one', 512, 1))
 
 
@@ -160,6 +169,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='vaihingen512', choices=sorted(WORKLOADS))
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -177,7 +187,15 @@ def main():
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=device)
-    model = build_model(device, args.precision)
+    global H, W, CROPS, WORKLOAD
+    wl = WORKLOADS[args.workload]
+    if args.workload != 'vaihingen512':
+        from clip_decontamination_b200.engine import slide_windows
+        H, W = wl['H'], wl['W']
+        CROPS = len(slide_windows(H, W, 112, 224))
+        WORKLOAD = f"{args.workload}: {H}x{W} synthetic tile, {wl['model']}, cls_{wl['cls']}.txt, jbu_one={wl['up']}, {CROPS} crops, extras ON"
+        args.no_cpu_baseline = True
+    model = build_model(device, args.precision, wl)
     eng = model.engine
     K = model.num_classes
     T = args.tiles
