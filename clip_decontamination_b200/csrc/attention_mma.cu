@@ -16,7 +16,7 @@ namespace {
 
 constexpr int HD = 64;
 constexpr int RSTRIDE = HD * 2 + 16;  // bytes per staged row (padded: conflict-free ldmatrix)
-constexpr int AWARPS = 8;
+constexpr int AWARPS = 4;            // one 16-row block per warp; ceil(L/64) CTAs per (crop, head), 2 CTAs per SM
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -123,7 +123,7 @@ __device__ __forceinline__ void add_simmap(float (&S)[NKB][4], const float* __re
 }
 
 template <int NKB>
-__global__ void __launch_bounds__(AWARPS * 32, 1) attention_mma_kernel(const bf16* __restrict__ qkv, int L, int heads,
+__global__ void __launch_bounds__(AWARPS * 32, 2) attention_mma_kernel(const bf16* __restrict__ qkv, int L, int heads,
                                                                        int mode, const float* __restrict__ simmap,
                                                                        float simw, bf16* __restrict__ out,
                                                                        float* __restrict__ stats) {
@@ -131,16 +131,18 @@ __global__ void __launch_bounds__(AWARPS * 32, 1) attention_mma_kernel(const bf1
   extern __shared__ __align__(16) uint8_t asmem[];
   const uint32_t qt = (uint32_t)__cvta_generic_to_shared(asmem);
   const uint32_t kt = qt + LP * RSTRIDE, vt = kt + LP * RSTRIDE;
-  const int crop = blockIdx.x / heads, head = blockIdx.x % heads;
+  const int nsplit = (L + 16 * AWARPS - 1) / (16 * AWARPS);
+  const int split = blockIdx.x % nsplit, ch = blockIdx.x / nsplit;
+  const int crop = ch / heads, head = ch % heads;
   const int width = heads * HD;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
   const int P = L - 1;
 
   for (int e = tid; e < LP * 8 * 3; e += AWARPS * 32) {  // 16-byte chunks: 8 per row per matrix
-    const int ch = e & 7, row = (e >> 3) % LP, mat = e / (8 * LP);
+    const int c8 = e & 7, row = (e >> 3) % LP, mat = e / (8 * LP);
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < L) v = __ldg(reinterpret_cast<const uint4*>(qkv + ((size_t)crop * L + row) * 3 * width + mat * width + head * HD + ch * 8));
-    *reinterpret_cast<uint4*>(asmem + (size_t)mat * LP * RSTRIDE + row * RSTRIDE + ch * 16) = v;
+    if (row < L) v = __ldg(reinterpret_cast<const uint4*>(qkv + ((size_t)crop * L + row) * 3 * width + mat * width + head * HD + c8 * 8));
+    *reinterpret_cast<uint4*>(asmem + (size_t)mat * LP * RSTRIDE + row * RSTRIDE + c8 * 16) = v;
   }
   __syncthreads();
 
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(AWARPS * 32, 1) attention_mma_kernel(const bf1
   if (mode == CSEG_ATTN_SCLIP) npass = 2;
   if (mode == CSEG_ATTN_SEGEARTH) npass = 3;
 
-  for (int rb = warp; rb * 16 < L; rb += AWARPS) {
+  for (int rb = split * AWARPS + warp; rb * 16 < L; rb += AWARPS * nsplit) {
     const int r0 = rb * 16, row0 = r0 + g, row1 = r0 + g + 8;
     float O[8][4];
 #pragma unroll
@@ -239,7 +241,8 @@ int launch(const bf16* qkv, int n_crops, int L, int heads, int mode, const float
            float* stats, cudaStream_t st) {
   const int smem = 3 * NKB * 8 * RSTRIDE;
   CSEG_SET_SMEM(attention_mma_kernel<NKB>, smem);
-  attention_mma_kernel<NKB><<<n_crops * heads, AWARPS * 32, smem, st>>>(qkv, L, heads, mode, simmap, simw, out, stats);
+  const int nsplit = (L + 16 * AWARPS - 1) / (16 * AWARPS);
+  attention_mma_kernel<NKB><<<n_crops * heads * nsplit, AWARPS * 32, smem, st>>>(qkv, L, heads, mode, simmap, simw, out, stats);
   CSEG_LAUNCH_CHECK("attention_mma");
   return 0;
 }

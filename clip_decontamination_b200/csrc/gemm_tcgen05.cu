@@ -370,7 +370,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
 // =====================================================================================================
 template <int QT>
 struct NsCfg {
-  static constexpr int BN = 128, STAGES = 3, NT_MAX = 4;
+  static constexpr int BN = 128, STAGES = (QT <= 8 ? 4 : 3), NT_MAX = 4;
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_WARPS = 16, THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int TXT_OFF = STAGES * STAGE_BYTES;               // text  [C_MAX][QT] fp32

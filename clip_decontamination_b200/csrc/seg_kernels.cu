@@ -120,9 +120,10 @@ __device__ __forceinline__ float crop_value(const AccumParams& p, int cr, int q,
 }
 
 // averaged logits of canvas pixel (y, x): windows visited in forward_slide order (segmentor.py:416-444)
-__device__ __forceinline__ void canvas_avg(const AccumParams& p, const int4* wins, int y, int x, float (&acc)[QMAX]) {
+template <int QT>
+__device__ __forceinline__ void canvas_avg(const AccumParams& p, const int4* wins, int y, int x, float (&acc)[QT]) {
 #pragma unroll
-  for (int q = 0; q < QMAX; ++q) acc[q] = 0.f;
+  for (int q = 0; q < QT; ++q) acc[q] = 0.f;
   int count = 0;
   for (int cr = 0; cr < p.n_crops; ++cr) {
     const int4 w = wins[cr];  // y1, x1, h, w
@@ -130,15 +131,16 @@ __device__ __forceinline__ void canvas_avg(const AccumParams& p, const int4* win
     if (ly < 0 || ly >= w.z || lx < 0 || lx >= w.w) continue;
     ++count;
 #pragma unroll
-    for (int q = 0; q < QMAX; ++q)
+    for (int q = 0; q < QT; ++q)
       if (q < p.Q) acc[q] += crop_value(p, cr, q, ly + p.pad_top, lx + p.pad_left);
   }
   const float cnt = (float)count;
 #pragma unroll
-  for (int q = 0; q < QMAX; ++q)
+  for (int q = 0; q < QT; ++q)
     if (q < p.Q) acc[q] = acc[q] / cnt;
 }
 
+template <int QT>
 __global__ void __launch_bounds__(256) accum_argmax_kernel(const AccumParams p) {
   extern __shared__ int4 s_wins[];
   for (int i = threadIdx.x; i < p.n_crops; i += blockDim.x)
@@ -146,12 +148,12 @@ __global__ void __launch_bounds__(256) accum_argmax_kernel(const AccumParams p) 
   __syncthreads();
   const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
   if (ox >= p.out_w) return;
-  float v[QMAX];
+  float v[QT];
   if (p.out_h == p.H && p.out_w == p.W) {
-    canvas_avg(p, s_wins, oy, ox, v);
+    canvas_avg<QT>(p, s_wins, oy, ox, v);
     if (p.avg_logits) {
 #pragma unroll
-      for (int q = 0; q < QMAX; ++q)
+      for (int q = 0; q < QT; ++q)
         if (q < p.Q) p.avg_logits[((size_t)q * p.H + oy) * p.W + ox] = v[q];
     }
   } else {  // bilinear resize of the averaged canvas to ori_shape (segmentor.py:448-449)
@@ -160,27 +162,27 @@ __global__ void __launch_bounds__(256) accum_argmax_kernel(const AccumParams p) 
     bilin_coord(oy, p.H, p.out_h, y0, y1, ly);
     bilin_coord(ox, p.W, p.out_w, x0, x1, lx);
     const float hy = 1.f - ly, hx = 1.f - lx;
-    float a[QMAX], b[QMAX];
-    canvas_avg(p, s_wins, y0, x0, a);
-    canvas_avg(p, s_wins, y0, x1, b);
+    float a[QT], b[QT];
+    canvas_avg<QT>(p, s_wins, y0, x0, a);
+    canvas_avg<QT>(p, s_wins, y0, x1, b);
 #pragma unroll
-    for (int q = 0; q < QMAX; ++q) v[q] = hy * (hx * a[q] + lx * b[q]);
-    canvas_avg(p, s_wins, y1, x0, a);
-    canvas_avg(p, s_wins, y1, x1, b);
+    for (int q = 0; q < QT; ++q) v[q] = hy * (hx * a[q] + lx * b[q]);
+    canvas_avg<QT>(p, s_wins, y1, x0, a);
+    canvas_avg<QT>(p, s_wins, y1, x1, b);
 #pragma unroll
-    for (int q = 0; q < QMAX; ++q) v[q] += ly * (hx * a[q] + lx * b[q]);
+    for (int q = 0; q < QT; ++q) v[q] += ly * (hx * a[q] + lx * b[q]);
   }
   // x logit_scale, softmax over Q (segmentor.py:478-479)
   float m = -INFINITY;
 #pragma unroll
-  for (int q = 0; q < QMAX; ++q)
+  for (int q = 0; q < QT; ++q)
     if (q < p.Q) {
       v[q] *= p.logit_scale;
       m = fmaxf(m, v[q]);
     }
   float sum = 0.f;
 #pragma unroll
-  for (int q = 0; q < QMAX; ++q)
+  for (int q = 0; q < QT; ++q)
     if (q < p.Q) sum += expf(v[q] - m);
   // per-class max over its synonym queries, argmax with lowest-index ties (segmentor.py:481-488);
   // ordering is decided on the scaled logits (softmax is monotone), probabilities only feed the
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(256) accum_argmax_kernel(const AccumParams p) 
   for (int k = 0; k < p.K; ++k) {
     float ck = -INFINITY;
 #pragma unroll
-    for (int q = 0; q < QMAX; ++q)
+    for (int q = 0; q < QT; ++q)
       if (q < p.Q && p.query_idx[q] == k) ck = fmaxf(ck, v[q]);
     if (p.probs) p.probs[((size_t)k * p.out_h + oy) * p.out_w + ox] = expf(ck - m) / sum;
     if (ck > best) {
@@ -268,7 +270,10 @@ int cseg_accum_argmax(const float* crop_logits, int n_crops, int Q, int lh, int 
   AccumParams p{crop_logits, n_crops, Q, lh, lw, crop_h, crop_w, pad_top, pad_left, windows, H, W, out_h, out_w,
                 query_idx, K, logit_scale, prob_thd, bg_idx, labels, probs, avg_logits};
   dim3 grid(cdiv(out_w, 256), out_h);
-  accum_argmax_kernel<<<grid, 256, (size_t)n_crops * sizeof(int4), (cudaStream_t)stream>>>(p);
+  const size_t smem = (size_t)n_crops * sizeof(int4);
+  if (Q <= 8) accum_argmax_kernel<8><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  else if (Q <= 16) accum_argmax_kernel<16><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  else accum_argmax_kernel<32><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
   CSEG_LAUNCH_CHECK("accum_argmax");
   return 0;
 }
