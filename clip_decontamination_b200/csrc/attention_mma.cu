@@ -138,12 +138,19 @@ __global__ void __launch_bounds__(AWARPS * 32, 2) attention_mma_kernel(const bf1
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
   const int P = L - 1;
 
+  // stage Q, K, V of this head with cp.async (all copies in flight at once; padding rows are zeroed)
   for (int e = tid; e < LP * 8 * 3; e += AWARPS * 32) {  // 16-byte chunks: 8 per row per matrix
     const int c8 = e & 7, row = (e >> 3) % LP, mat = e / (8 * LP);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < L) v = __ldg(reinterpret_cast<const uint4*>(qkv + ((size_t)crop * L + row) * 3 * width + mat * width + head * HD + c8 * 8));
-    *reinterpret_cast<uint4*>(asmem + (size_t)mat * LP * RSTRIDE + row * RSTRIDE + c8 * 16) = v;
+    const uint32_t dst = qt + (uint32_t)(mat * LP * RSTRIDE + row * RSTRIDE + c8 * 16);
+    if (row < L) {
+      const bf16* src = qkv + ((size_t)crop * L + row) * 3 * width + mat * width + head * HD + c8 * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(asmem + (size_t)mat * LP * RSTRIDE + row * RSTRIDE + c8 * 16) = make_uint4(0, 0, 0, 0);
+    }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   const float scale = 0.125f;  // 64^-0.5

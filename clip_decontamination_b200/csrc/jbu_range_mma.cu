@@ -53,16 +53,19 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
   const int crop = blockIdx.z, y0 = blockIdx.y * TYR, x0 = blockIdx.x * TXR;
   const __half* pc = proj + (size_t)crop * gh * gw * KD;
 
-  for (int e = tid; e < HR * NPOS * 4; e += TYR * 32) {      // 4 x 16 B per position
+  for (int e = tid; e < HR * NPOS * 4; e += TYR * 32) {      // 4 x 16 B per position, all in flight (cp.async)
     const int ch = e & 3, pos = (e >> 2) % NPOS, hy = (e >> 2) / NPOS;
     const int yy = reflect1(min(y0 - R + hy, gh - 1 + R), gh), xx = reflect1(min(x0 - R + pos, gw - 1 + R), gw);
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(pc + ((size_t)yy * gw + xx) * KD + ch * 8));
-    *reinterpret_cast<uint4*>(rsm + (hy * NPOS + pos) * PROW + ch * 16) = v;
+    const uint32_t dst = psm + (uint32_t)((hy * NPOS + pos) * PROW + ch * 16);
+    const __half* src = pc + ((size_t)yy * gw + xx) * KD + ch * 8;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int t = tid; t < D2; t += TYR * 32) {                 // get_spatial_kernel: linspace(-1, 1, D)^2
     const float dy = -1.f + 2.f * (t / D) / (D - 1), dx = -1.f + 2.f * (t % D) / (D - 1);
     gauss[t] = __expf(-(dy * dy + dx * dx) * inv2s2);
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   const int y = y0 + warp;
