@@ -103,9 +103,12 @@ struct EpiParams {
 // fastest, so concurrently running CTAs share the B tile in L2):
 //   warp 0      TMA producer      smem ring of STAGES x (A 128x64 + B BNx64), full/empty mbarriers
 //   warp 1      TMEM allocator + MMA issuer; ACC accumulator stages of BN columns in TMEM
-//   warps 2..   epilogue: 4 TMEM lane quadrants (= warp id % 4) x BN/32 column chunks; each warp drains
-//               one 32x32 chunk per tile: tcgen05.ld -> release the accumulator stage -> stage through
-//               shared memory -> row-coalesced residual loads / C stores.
+//   warps 2..   epilogue: 4 TMEM lane quadrants (= warp id % 4) x column groups; each warp drains one or
+//               two 32x32 chunks per tile: tcgen05.ld -> (after its last chunk) release the accumulator
+//               stage -> stage through shared memory -> row-coalesced residual loads / C stores.
+// Tile widths: BN = 64 / 128 (4 accumulator stages) and 192 / 256 (2 stages).  The L2 -> SM feed saturates
+// at roughly 50-60 B/clk/SM with the ring depth that fits in shared memory, so wide tiles (fewer operand bytes
+// per flop) are what lifts the large-N GEMMs; BN = 192 gives N = 768 exactly 100 tiles on 148 SMs.
 // The epilogue of tile i overlaps the loads and MMAs of tiles i+1.. (ACC up to 4), which is what the
 // skinny-K GEMMs of the JBU (K = 128) and the GELU epilogues need: they are epilogue-bound.
 template <int BN, int STAGES>
@@ -114,8 +117,10 @@ struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int ACC = (512 / BN) < 4 ? (512 / BN) : 4;   // accumulator stages in TMEM
-  static constexpr int TMEM_COLS = ACC * BN;                     // 256 or 512 (power of two)
-  static constexpr int EPI_WARPS = 4 * (BN / 32);
+  static constexpr int TMEM_COLS = (ACC * BN <= 256) ? 256 : 512; // allocation must be a power of two
+  static constexpr int NCHUNK = BN / 32;                          // 32-column chunks per tile
+  static constexpr int CGROUPS = NCHUNK <= 4 ? NCHUNK : (NCHUNK % 3 == 0 ? 3 : 4);  // column groups of warps
+  static constexpr int EPI_WARPS = 4 * CGROUPS;                   // each warp drains NCHUNK / CGROUPS chunks
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int SST = 36;                                 // staging row stride (floats); 36/4 odd
   static constexpr int STG_OFF = STAGES * STAGE_BYTES;
@@ -219,76 +224,85 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else {
     const int ew = warp - 2;
     const int lg = warp & 3;            // TMEM lane quadrant this warp may read (= warp id % 4)
-    const int cchunk = ew >> 2;         // which 32-column chunk of the tile
-    constexpr int SST = C::SST;
+    const int cg = ew >> 2;             // column group: chunks cg, cg + CGROUPS, ...
+    constexpr int SST = C::SST, CPW = C::NCHUNK / C::CGROUPS;
     float* stg = reinterpret_cast<float*>(smem + C::STG_OFF) + ew * 32 * SST;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       const int m0 = TILE_M(tile) * BM, n0 = TILE_N(tile) * BN;
       const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
-      const int rbase = m0 + lg * 32, col0 = n0 + cchunk * 32;
-      const int col = col0 + lane;
-      const bool col_ok = col < ep.N;
+      const int rbase = m0 + lg * 32;
       const int nrows = min(32, ep.M - rbase);
-      // residual + bias for this warp's 32x32 chunk are fetched BEFORE waiting for the accumulator: they do
-      // not depend on the MMA, so their latency hides behind the main loop of this tile.
-      float res[32];
-      if (RES != 0 && col_ok) {
-        if (RES == 2) {
-          const bf16* rp = (const bf16*)ep.residual + (size_t)rbase * ep.ldr + col;
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) res[rr] = (rr < nrows) ? __bfloat162float(rp[(size_t)rr * ep.ldr]) : 0.f;
-        } else {
-          const float* rp = (const float*)ep.residual + (size_t)rbase * ep.ldr + col;
+      for (int ci = 0; ci < CPW; ++ci) {
+        const int cchunk = cg + ci * C::CGROUPS;
+        const int col0 = n0 + cchunk * 32;
+        const int col = col0 + lane;
+        const bool col_ok = col < ep.N;
+        // residual + bias of the chunk are fetched BEFORE the accumulator is read (for the first chunk:
+        // before waiting for it), so their latency hides behind the main loop / the previous chunk.
+        float res[32];
+        if (RES != 0 && col_ok && nrows > 0) {
+          if (RES == 2) {
+            const bf16* rp = (const bf16*)ep.residual + (size_t)rbase * ep.ldr + col;
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) res[rr] = (rr < nrows) ? rp[(size_t)rr * ep.ldr] : 0.f;
-        }
-      }
-      const float bv = (ep.bias != nullptr && col_ok) ? __ldg(ep.bias + col) : 0.f;
-      mbar_wait(tfull0 + as * 8, aph);
-      tc_fence_after();
-      uint32_t r[32];
-      __syncwarp();
-      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + cchunk * 32), r);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + as * 8);   // this warp's part of the accumulator is in registers
-      if (col0 >= ep.N || rbase >= ep.M) continue;    // warp-uniform
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<uint4*>(stg + lane * SST + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-      __syncwarp();
-      if (col_ok) {
-        const float alpha = ep.alpha;
-        auto finish = [&](int rr) -> float {
-          float x = stg[rr * SST + lane] + bv;
-          if (ACT == CSEG_ACT_GELU) x = gelu_fast(x);
-          else if (ACT == CSEG_ACT_QUICKGELU) x = quick_gelu(x);
-          return RES != 0 ? fmaf(x, alpha, res[rr]) : x * alpha;
-        };
-        if (OUTB) {
-          bf16* cp = (bf16*)ep.C + (size_t)rbase * ep.ldc + col;
-          if (nrows == 32) {
-#pragma unroll
-            for (int rr = 0; rr < 32; ++rr) cp[(size_t)rr * ep.ldc] = __float2bfloat16_rn(finish(rr));
+            for (int rr = 0; rr < 32; ++rr) res[rr] = (rr < nrows) ? __bfloat162float(rp[(size_t)rr * ep.ldr]) : 0.f;
           } else {
+            const float* rp = (const float*)ep.residual + (size_t)rbase * ep.ldr + col;
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr)
-              if (rr < nrows) cp[(size_t)rr * ep.ldc] = __float2bfloat16_rn(finish(rr));
-          }
-        } else {
-          float* cp = (float*)ep.C + (size_t)rbase * ep.ldc + col;
-          if (nrows == 32) {
-#pragma unroll
-            for (int rr = 0; rr < 32; ++rr) cp[(size_t)rr * ep.ldc] = finish(rr);
-          } else {
-#pragma unroll
-            for (int rr = 0; rr < 32; ++rr)
-              if (rr < nrows) cp[(size_t)rr * ep.ldc] = finish(rr);
+            for (int rr = 0; rr < 32; ++rr) res[rr] = (rr < nrows) ? rp[(size_t)rr * ep.ldr] : 0.f;
           }
         }
+        const float bv = (ep.bias != nullptr && col_ok) ? __ldg(ep.bias + col) : 0.f;
+        if (ci == 0) {
+          mbar_wait(tfull0 + as * 8, aph);
+          tc_fence_after();
+        }
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + cchunk * 32), r);
+        if (ci == CPW - 1) {            // last chunk of this warp: its part of the accumulator is in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + as * 8);
+        }
+        if (col0 >= ep.N || nrows <= 0) continue;    // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(stg + lane * SST + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        __syncwarp();
+        if (col_ok) {
+          const float alpha = ep.alpha;
+          auto finish = [&](int rr) -> float {
+            float x = stg[rr * SST + lane] + bv;
+            if (ACT == CSEG_ACT_GELU) x = gelu_fast(x);
+            else if (ACT == CSEG_ACT_QUICKGELU) x = quick_gelu(x);
+            return RES != 0 ? fmaf(x, alpha, res[rr]) : x * alpha;
+          };
+          if (OUTB) {
+            bf16* cp = (bf16*)ep.C + (size_t)rbase * ep.ldc + col;
+            if (nrows == 32) {
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) cp[(size_t)rr * ep.ldc] = __float2bfloat16_rn(finish(rr));
+            } else {
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr)
+                if (rr < nrows) cp[(size_t)rr * ep.ldc] = __float2bfloat16_rn(finish(rr));
+            }
+          } else {
+            float* cp = (float*)ep.C + (size_t)rbase * ep.ldc + col;
+            if (nrows == 32) {
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) cp[(size_t)rr * ep.ldc] = finish(rr);
+            } else {
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr)
+                if (rr < nrows) cp[(size_t)rr * ep.ldc] = finish(rr);
+            }
+          }
+        }
+        __syncwarp();   // staging buffer is reused by this warp's next chunk / tile
       }
-      __syncwarp();   // staging buffer is reused by this warp's next tile
     }
   }
   tc_fence_before();
@@ -588,8 +602,24 @@ int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int
   CSEG_REQUIRE(K % 8 == 0, "gemm(bf16): K=%d must be a multiple of 8 (16-byte rows for TMA)", K);
   CSEG_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm(bf16): lda=%d, ldb=%d must be multiples of 8", lda, ldb);
   CSEG_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm(bf16): operands must be 16-byte aligned");
-  // BN = 64 when 128-wide tiles would leave SMs idle (fewer than ~1.5 tiles per SM)
-  int bn = (N <= 64 || (long long)cdiv(M, BM) * cdiv(N, 128) * 2 < 3LL * sm_count()) ? 64 : 128;
+  // Tile width: the widest BN whose tile count still gives every SM work; ties broken by the makespan
+  // (rounds x tile width).  BN = 192 / 256 halve the operand traffic per flop of the large-N GEMMs.
+  const int m_tiles = cdiv(M, BM), sms = sm_count();
+  int bn = 64;
+  {
+    double best = 1e30;
+    const int cands[4] = {256, 192, 128, 64};
+    for (int ci = 0; ci < 4; ++ci) {
+      const int c = cands[ci];
+      if (c > 64 && N < c) continue;
+      const long long tiles = (long long)m_tiles * cdiv(N, c);
+      const long long rounds = (tiles + sms - 1) / sms;
+      // cost model: rounds x (tile MMA time + feed penalty for narrow tiles)
+      const double feed = (c == 64) ? 1.6 : (c == 128 ? 1.25 : 1.0);
+      const double cost = (double)rounds * c * feed;
+      if (cost < best - 1e-9) { best = cost; bn = c; }
+    }
+  }
   CUtensorMap ta, tb;
   int rc = make_map(&ta, A, M, K, lda, BM);
   if (rc) return rc;
@@ -597,5 +627,7 @@ int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int
   if (rc) return rc;
   EpiParams ep{bias, residual, ldr, res_dtype == CSEG_BF16, alpha, act, out_dtype == CSEG_BF16, C, ldc, M, N};
   if (bn == 64) return launch<64, 6>(ta, tb, M, N, K, ep, st);
+  if (bn == 192) return launch<192, 4>(ta, tb, M, N, K, ep, st);
+  if (bn == 256) return launch<256, 3>(ta, tb, M, N, K, ep, st);
   return launch<128, 4>(ta, tb, M, N, K, ep, st);
 }
