@@ -69,16 +69,20 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // exact-erf GELU (nn.GELU default) and QuickGELU (open_clip/transformer.py:35-38)
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-// GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 instead of
-// erff's branchy polynomial; used by the tensor-core GEMM epilogue, whose outputs are rounded to bf16.
+// GELU with erf from Abramowitz-Stegun 7.1.28 (|err| <= 3e-7):  erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16.
+// One MUFU.RCP and ~16 FMA-pipe instructions; erff() costs a branchy polynomial plus MUFU.EX2 and the
+// 7.1.26 form two MUFU ops -- the GELU epilogues of the tensor-core GEMMs are MUFU/issue bound.
 __device__ __forceinline__ float gelu_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-z * z);
+  float p = fmaf(0.0000430638f, z, 0.0002765672f);
+  p = fmaf(p, z, 0.0001520143f);
+  p = fmaf(p, z, 0.0092705272f);
+  p = fmaf(p, z, 0.0422820123f);
+  p = fmaf(p, z, 0.0705230784f);
+  p = fmaf(p, z, 1.0f);
+  float r = __frcp_rn(p);
+  r *= r; r *= r; r *= r; r *= r;          // p^-16
+  const float e = 1.0f - r;                 // erf(|x| / sqrt 2)
   return 0.5f * x * (1.0f + copysignf(e, x));
 }
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
