@@ -13,6 +13,11 @@
 
 namespace {
 
+#ifndef CSEG_EPI_DIRECT
+#define CSEG_EPI_DIRECT 0   /* measured slower than the staged epilogue on every pipeline shape */
+#endif
+constexpr bool EPI_DIRECT = CSEG_EPI_DIRECT != 0;   // row-per-lane epilogue (no smem staging) for full, aligned chunks
+
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 
@@ -242,7 +247,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // residual + bias of the chunk are fetched BEFORE the accumulator is read (for the first chunk:
         // before waiting for it), so their latency hides behind the main loop / the previous chunk.
         float res[32];
-        if (RES != 0 && col_ok && nrows > 0) {
+        const bool direct = EPI_DIRECT && col0 + 32 <= ep.N && (ep.ldc & 7) == 0 && (RES == 0 || (ep.ldr & 7) == 0);
+        if (RES != 0 && col_ok && nrows > 0 && !direct) {
           if (RES == 2) {
             const bf16* rp = (const bf16*)ep.residual + (size_t)rbase * ep.ldr + col;
 #pragma unroll
@@ -267,6 +273,73 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           if (lane == 0) mbar_arrive(tempty0 + as * 8);
         }
         if (col0 >= ep.N || nrows <= 0) continue;    // warp-uniform
+        if (direct) {
+          // row-per-lane epilogue straight from the TMEM layout: lane = row, 32 consecutive columns.  Each lane
+          // writes one contiguous 64 B (bf16) / 128 B (fp32) segment with 16-byte stores; bias is a broadcast load.
+          const int row = rbase + lane;
+          if (lane < nrows) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (ep.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
+            }
+            if (ACT == CSEG_ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+            } else if (ACT == CSEG_ACT_QUICKGELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+            }
+            const float alpha = ep.alpha;
+            if (RES == 1) {
+              const float4* rp = reinterpret_cast<const float4*>((const float*)ep.residual + (size_t)row * ep.ldr + col0);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 q4 = rp[j >> 2];
+                v[j] = fmaf(v[j], alpha, q4.x); v[j + 1] = fmaf(v[j + 1], alpha, q4.y);
+                v[j + 2] = fmaf(v[j + 2], alpha, q4.z); v[j + 3] = fmaf(v[j + 3], alpha, q4.w);
+              }
+            } else if (RES == 2) {
+              const uint4* rp = reinterpret_cast<const uint4*>((const bf16*)ep.residual + (size_t)row * ep.ldr + col0);
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 u = rp[j >> 3];
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(h[e]);
+                  v[j + 2 * e] = fmaf(v[j + 2 * e], alpha, f.x);
+                  v[j + 2 * e + 1] = fmaf(v[j + 2 * e + 1], alpha, f.y);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= alpha;
+            }
+            if (OUTB) {
+              uint4* cp = reinterpret_cast<uint4*>((bf16*)ep.C + (size_t)row * ep.ldc + col0);
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                cp[j >> 3] = pk;
+              }
+            } else {
+              float4* cp = reinterpret_cast<float4*>((float*)ep.C + (size_t)row * ep.ldc + col0);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) cp[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<uint4*>(stg + lane * SST + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
@@ -616,7 +689,9 @@ int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int
       const long long rounds = (tiles + sms - 1) / sms;
       // cost model: rounds x (tile MMA time + feed penalty for narrow tiles)
       const double feed = (c == 64) ? 1.6 : (c == 128 ? 1.25 : 1.0);
-      const double cost = (double)rounds * c * feed;
+      // BN = 192 has 12 epilogue warps for 6 chunks: activation epilogues (MUFU / issue bound) pace its tiles
+      const double epi = (c == 192 && act != CSEG_ACT_NONE) ? 1.45 : 1.0;
+      const double cost = (double)rounds * c * feed * epi;
       if (cost < best - 1e-9) { best = cost; bn = c; }
     }
   }
