@@ -65,8 +65,7 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
 template <int R>
 __global__ void __launch_bounds__(NTHREADS, 2 / XB) adaptive_conv_mma_kernel(const bf16* __restrict__ hr, int H2, int W2, int C,
                                                                         const bf16* __restrict__ kern, int ldk,
-                                                                        bf16* __restrict__ dst, int nx, int ny,
-                                                                        int total_tiles) {
+                                                                        bf16* __restrict__ dst) {
   constexpr int D = 2 * R + 1;
   constexpr int NSRC = RW + 2 * R;  // source rows per tile
   constexpr int WB_BYTES = RW * D * XB * ATILE;
@@ -78,86 +77,63 @@ __global__ void __launch_bounds__(NTHREADS, 2 / XB) adaptive_conv_mma_kernel(con
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int xb = warp % XB, cq = warp / XB;
   const int g = lane >> 2, tig = lane & 3;
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * RW;
   const int nslab = (C + CS - 1) / CS;
-  const int lrow = lane & 7, lq = lane >> 3;
-  const uint32_t b_lane_off = (uint32_t)(((lq & 1) * 8 + lrow) * PSTRIDE + (cq * 64 + (lq >> 1) * 8) * 2);
-  // A fragment lanes: matrices (rows 0-7, k 0-7) (rows 8-15, k 0-7) (rows 0-7, k 8-15) (rows 8-15, k 8-15)
-  const uint32_t a_lane_off = (uint32_t)(((lq & 1) * 8 + lrow) * ASTRIDE + (lq >> 1) * 16);
+  const int crop = blockIdx.z / nslab, c0 = (blockIdx.z % nslab) * CS;
+  const int cvalid = min(CS, C - c0);            // channels of this slab that exist
+  const bool warp_on = cq * 64 < cvalid;         // warp-uniform: this channel quarter exists
+  const bf16* hrc = hr + (size_t)crop * H2 * W2 * C + c0;
 
-  // Persistent CTA: the band tiles are zero-filled ONCE (the non-zero slots are the same for every tile and are
-  // all rewritten by each tile's scatter); the kernel weights of the NEXT tile are fetched into registers
-  // while the current tile runs its main loop.
-  for (int e = tid; e < WB_BYTES / 16; e += NTHREADS) reinterpret_cast<uint4*>(wb)[e] = make_uint4(0, 0, 0, 0);
-
-  constexpr int WPT = RW * TX * 16 / NTHREADS;       // 8 x 16-byte weight chunks per thread
-  constexpr int LPT = NPOS * (CS / 8) / NTHREADS;    // cp.async per thread per source row
-  auto tile_coords = [&](int tile, int& x0, int& y0, int& crop, int& c0) {
-    x0 = (tile % nx) * TX;
-    y0 = ((tile / nx) % ny) * RW;
-    const int z = tile / (nx * ny);
-    crop = z / nslab;
-    c0 = (z % nslab) * CS;
-  };
-  auto load_weights = [&](int tile, uint4 (&wv)[WPT]) {
-    int x0, y0, crop, c0;
-    tile_coords(tile, x0, y0, crop, c0);
+  // per-thread copy plan of a source row: the (position, channel chunk) pairs a thread moves are the same for
+  // every row, so the reflect / index arithmetic is done once and a row costs LPT cp.async per thread
+  constexpr int LPT = NPOS * (CS / 8) / NTHREADS;   // 6
+  int src_off[LPT];                                  // element offset inside one source row, -1 = nothing to copy
+  uint32_t dst_off[LPT];
 #pragma unroll
-    for (int k = 0; k < WPT; ++k) {
-      const int e = tid + k * NTHREADS;
-      const int v = e % 16, px = (e / 16) % TX, r = e / (16 * TX);
-      wv[k] = make_uint4(0, 0, 0, 0);
-      if (y0 + r < H2 && x0 + px < W2 && v * 8 < ldk)
-        wv[k] = __ldg(reinterpret_cast<const uint4*>(kern + (((size_t)crop * H2 + y0 + r) * W2 + x0 + px) * ldk + v * 8));
-    }
-  };
-  // NTHREADS % 16 == 0, so the 16-byte chunk index v = tid & 15 (hence the 8 taps a thread scatters) is the
-  // same for all of its chunks: the tap -> (i, j) split is done once per thread
-  int toff[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int t = (tid & 15) * 8 + q, i = t / D, j = t - i * D;
-    toff[q] = (t < D * D) ? i * XB * ATILE + j * 2 : -1;
+  for (int k = 0; k < LPT; ++k) {
+    const int e = tid + k * NTHREADS;
+    const int p = e / (CS / 8), ch = (e % (CS / 8)) * 8;
+    const int xx = reflect1(min(x0 - R + p, W2 - 1 + R), W2);
+    src_off[k] = (ch < cvalid) ? xx * C + ch : -1;
+    dst_off[k] = (uint32_t)(p * PSTRIDE + ch * 2);
   }
-
+  auto load_row = [&](int sr) {
+    const int yy = reflect1(min(y0 + sr - R, H2 - 1 + R), H2);
+    const uint32_t base = ring + (sr % NST) * ROW_BYTES;
+    const bf16* rowp = hrc + (size_t)yy * W2 * C;
+#pragma unroll
+    for (int k = 0; k < LPT; ++k)
+      if (src_off[k] >= 0) cp_async16(base + dst_off[k], rowp + src_off[k]);
+  };
+#pragma unroll
+  for (int s = 0; s < NST - 1; ++s) {
+    if (s < NSRC) load_row(s);
+    cp_async_commit();
+  }
+  // ---- expand the kernel weights of the tile into band tiles ----
+  // the global loads are issued first so that their latency overlaps the zero fill
+  constexpr int WPT = RW * TX * 16 / NTHREADS;       // 8 x 16-byte weight chunks per thread
   uint4 wv[WPT];
-  if ((int)blockIdx.x < total_tiles) load_weights(blockIdx.x, wv);
-
-#pragma unroll 1
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    int x0, y0, crop, c0;
-    tile_coords(tile, x0, y0, crop, c0);
-    const int cvalid = min(CS, C - c0);            // channels of this slab that exist
-    const bool warp_on = cq * 64 < cvalid;         // warp-uniform: this channel quarter exists
-    const bf16* hrc = hr + (size_t)crop * H2 * W2 * C + c0;
-
-    // per-thread copy plan of a source row: the (position, channel chunk) pairs a thread moves are the same
-    // for every row, so the reflect / index arithmetic is done once and a row costs LPT cp.async per thread
-    int src_off[LPT];                                // element offset inside one source row, -1 = nothing to copy
-    uint32_t dst_off[LPT];
 #pragma unroll
-    for (int k = 0; k < LPT; ++k) {
-      const int e = tid + k * NTHREADS;
-      const int p = e / (CS / 8), ch = (e % (CS / 8)) * 8;
-      const int xx = reflect1(min(x0 - R + p, W2 - 1 + R), W2);
-      src_off[k] = (ch < cvalid) ? xx * C + ch : -1;
-      dst_off[k] = (uint32_t)(p * PSTRIDE + ch * 2);
+  for (int k = 0; k < WPT; ++k) {
+    const int e = tid + k * NTHREADS;
+    const int v = e % 16, px = (e / 16) % TX, r = e / (16 * TX);
+    wv[k] = make_uint4(0, 0, 0, 0);
+    if (y0 + r < H2 && x0 + px < W2 && v * 8 < ldk)
+      wv[k] = __ldg(reinterpret_cast<const uint4*>(kern + (((size_t)crop * H2 + y0 + r) * W2 + x0 + px) * ldk + v * 8));
+  }
+  for (int e = tid; e < WB_BYTES / 16; e += NTHREADS) reinterpret_cast<uint4*>(wb)[e] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  {
+    // NTHREADS % 16 == 0, so the 16-byte chunk index v = tid & 15 (hence the 8 taps a thread scatters) is the
+    // same for all of its chunks: the tap -> (i, j) split is done once per thread
+    const int v = tid & 15;
+    int toff[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = v * 8 + q, i = t / D, j = t - i * D;
+      toff[q] = (t < D * D) ? i * XB * ATILE + j * 2 : -1;
     }
-    auto load_row = [&](int sr) {
-      const int yy = reflect1(min(y0 + sr - R, H2 - 1 + R), H2);
-      const uint32_t base = ring + (sr % NST) * ROW_BYTES;
-      const bf16* rowp = hrc + (size_t)yy * W2 * C;
-#pragma unroll
-      for (int k = 0; k < LPT; ++k)
-        if (src_off[k] >= 0) cp_async16(base + dst_off[k], rowp + src_off[k]);
-    };
-    __syncthreads();   // every warp is done with the previous tile's ring slots and band tiles (and, for the
-                       // first tile, the zero fill is complete)
-#pragma unroll
-    for (int s = 0; s < NST - 1; ++s) {
-      if (s < NSRC) load_row(s);
-      cp_async_commit();
-    }
-    // ---- expand the kernel weights of the tile into band tiles ----
 #pragma unroll
     for (int k = 0; k < WPT; ++k) {
       const int e = tid + k * NTHREADS;
@@ -169,82 +145,85 @@ __global__ void __launch_bounds__(NTHREADS, 2 / XB) adaptive_conv_mma_kernel(con
       for (int q = 0; q < 8; ++q)
         if (toff[q] >= 0) *reinterpret_cast<unsigned short*>(base + toff[q]) = hv[q];
     }
-    if (tile + (int)gridDim.x < total_tiles) load_weights(tile + gridDim.x, wv);   // prefetch for the next tile
+  }
 
-    float acc[RW][8][4];
+  float acc[RW][8][4];
 #pragma unroll
-    for (int r = 0; r < RW; ++r)
+  for (int r = 0; r < RW; ++r)
 #pragma unroll
-      for (int nb = 0; nb < 8; ++nb)
+    for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[r][nb][e] = 0.f;
+      for (int e = 0; e < 4; ++e) acc[r][nb][e] = 0.f;
+
+  const int lrow = lane & 7, lq = lane >> 3;
+  const uint32_t b_lane_off = (uint32_t)(((lq & 1) * 8 + lrow) * PSTRIDE + (cq * 64 + (lq >> 1) * 8) * 2);
+  // A fragment lanes: matrices (rows 0-7, k 0-7) (rows 8-15, k 0-7) (rows 0-7, k 8-15) (rows 8-15, k 8-15)
+  const uint32_t a_lane_off = (uint32_t)(((lq & 1) * 8 + lrow) * ASTRIDE + (lq >> 1) * 16);
 
 #pragma unroll 1
-    for (int sr = 0; sr < NSRC; ++sr) {
-      cp_async_wait<NST - 2>();
-      __syncthreads();  // row sr has landed for everyone (and, at sr = 0, the band tiles are complete);
-                        // slot (sr-1)%NST is free again
-      if (sr + NST - 1 < NSRC) load_row(sr + NST - 1);
-      cp_async_commit();
-      if (!warp_on) continue;
-      const uint32_t rowbase = ring + (sr % NST) * ROW_BYTES;
-      if (sr >= RW - 1 && sr < D) {
-        // interior source row: it feeds all RW output rows (tap rows i = sr - r).  Branch-free, so all sixteen
-        // fragment loads are issued before the 64 MMAs and their latency overlaps the tensor pipe.
-        uint32_t bfr[2][4][4], a[2][RW][4];
+  for (int sr = 0; sr < NSRC; ++sr) {
+    cp_async_wait<NST - 2>();
+    __syncthreads();  // row sr has landed for everyone (and, at sr = 0, the band tiles are complete);
+                      // slot (sr-1)%NST is free again
+    if (sr + NST - 1 < NSRC) load_row(sr + NST - 1);
+    cp_async_commit();
+    if (!warp_on) continue;
+    const uint32_t rowbase = ring + (sr % NST) * ROW_BYTES;
+    if (sr >= RW - 1 && sr < D) {
+      // interior source row: it feeds all RW output rows (tap rows i = sr - r).  Branch-free, so all sixteen
+      // fragment loads are issued before the 64 MMAs and their latency overlaps the tensor pipe.
+      uint32_t bfr[2][4][4], a[2][RW][4];
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint32_t baddr = rowbase + (uint32_t)((xb * 16 + ks * 16) * PSTRIDE) + b_lane_off;
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t baddr = rowbase + (uint32_t)((xb * 16 + ks * 16) * PSTRIDE) + b_lane_off;
 #pragma unroll
-          for (int j2 = 0; j2 < 4; ++j2) ldsm_x4_trans(baddr + j2 * 32, bfr[ks][j2]);
+        for (int j2 = 0; j2 < 4; ++j2) ldsm_x4_trans(baddr + j2 * 32, bfr[ks][j2]);
 #pragma unroll
-          for (int r = 0; r < RW; ++r)
-            ldsm_x4(wband + (uint32_t)(((r * D + (sr - r)) * XB + xb) * ATILE + ks * 32) + a_lane_off, a[ks][r]);
-        }
+        for (int r = 0; r < RW; ++r)
+          ldsm_x4(wband + (uint32_t)(((r * D + (sr - r)) * XB + xb) * ATILE + ks * 32) + a_lane_off, a[ks][r]);
+      }
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
+      for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-          for (int r = 0; r < RW; ++r)
+        for (int r = 0; r < RW; ++r)
 #pragma unroll
-            for (int nb = 0; nb < 8; ++nb)
-              mma_bf16(acc[r][nb], a[ks][r], bfr[ks][nb >> 1][(nb & 1) * 2], bfr[ks][nb >> 1][(nb & 1) * 2 + 1]);
-      } else {
+          for (int nb = 0; nb < 8; ++nb)
+            mma_bf16(acc[r][nb], a[ks][r], bfr[ks][nb >> 1][(nb & 1) * 2], bfr[ks][nb >> 1][(nb & 1) * 2 + 1]);
+    } else {
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          uint32_t bfr[4][4];
-          const uint32_t baddr = rowbase + (uint32_t)((xb * 16 + ks * 16) * PSTRIDE) + b_lane_off;
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t bfr[4][4];
+        const uint32_t baddr = rowbase + (uint32_t)((xb * 16 + ks * 16) * PSTRIDE) + b_lane_off;
 #pragma unroll
-          for (int j2 = 0; j2 < 4; ++j2) ldsm_x4_trans(baddr + j2 * 32, bfr[j2]);
+        for (int j2 = 0; j2 < 4; ++j2) ldsm_x4_trans(baddr + j2 * 32, bfr[j2]);
 #pragma unroll
-          for (int r = 0; r < RW; ++r) {
-            const int i = sr - r;  // tap row of output row r fed by this source row
-            if (i < 0 || i >= D) continue;
-            uint32_t a[4];
-            ldsm_x4(wband + (uint32_t)(((r * D + i) * XB + xb) * ATILE + ks * 32) + a_lane_off, a);
+        for (int r = 0; r < RW; ++r) {
+          const int i = sr - r;  // tap row of output row r fed by this source row
+          if (i < 0 || i >= D) continue;
+          uint32_t a[4];
+          ldsm_x4(wband + (uint32_t)(((r * D + i) * XB + xb) * ATILE + ks * 32) + a_lane_off, a);
 #pragma unroll
-            for (int nb = 0; nb < 8; ++nb) mma_bf16(acc[r][nb], a, bfr[nb >> 1][(nb & 1) * 2], bfr[nb >> 1][(nb & 1) * 2 + 1]);
-          }
+          for (int nb = 0; nb < 8; ++nb) mma_bf16(acc[r][nb], a, bfr[nb >> 1][(nb & 1) * 2], bfr[nb >> 1][(nb & 1) * 2 + 1]);
         }
       }
     }
-    cp_async_wait<0>();
-    if (warp_on) {
-      // epilogue: c0,c1 -> (px g, ch 2tig,2tig+1); c2,c3 -> (px g+8, ...)
+  }
+  cp_async_wait<0>();
+  if (!warp_on) return;
+  // epilogue: c0,c1 -> (px g, ch 2tig,2tig+1); c2,c3 -> (px g+8, ...)
 #pragma unroll
-      for (int r = 0; r < RW; ++r) {
-        const int y = y0 + r;
-        if (y >= H2) continue;
+  for (int r = 0; r < RW; ++r) {
+    const int y = y0 + r;
+    if (y >= H2) continue;
 #pragma unroll
-        for (int hm = 0; hm < 2; ++hm) {
-          const int x = x0 + xb * 16 + g + hm * 8;
-          if (x >= W2) continue;
-          bf16* o = dst + (((size_t)crop * H2 + y) * W2 + x) * C + c0 + cq * 64 + 2 * tig;
+    for (int hm = 0; hm < 2; ++hm) {
+      const int x = x0 + xb * 16 + g + hm * 8;
+      if (x >= W2) continue;
+      bf16* o = dst + (((size_t)crop * H2 + y) * W2 + x) * C + c0 + cq * 64 + 2 * tig;
 #pragma unroll
-          for (int nb = 0; nb < 8; ++nb)
-            if (cq * 64 + nb * 8 < cvalid)
-              *reinterpret_cast<__nv_bfloat162*>(o + nb * 8) = __floats2bfloat162_rn(acc[r][nb][hm * 2], acc[r][nb][hm * 2 + 1]);
-        }
-      }
+      for (int nb = 0; nb < 8; ++nb)
+        if (cq * 64 + nb * 8 < cvalid)
+          *reinterpret_cast<__nv_bfloat162*>(o + nb * 8) = __floats2bfloat162_rn(acc[r][nb][hm * 2], acc[r][nb][hm * 2 + 1]);
     }
   }
 }
@@ -254,11 +233,9 @@ int launch_conv(const bf16* hr, int n_crops, int H2, int W2, int C, const bf16* 
   constexpr int D = 2 * R + 1;
   const int smem = NST * ROW_BYTES + RW * D * XB * ATILE;
   CSEG_SET_SMEM(adaptive_conv_mma_kernel<R>, smem);
-  const int nx = cdiv(W2, TX), ny = cdiv(H2, RW);
-  const long long total = (long long)nx * ny * n_crops * cdiv(C, CS);
-  CSEG_REQUIRE(total < (1LL << 31), "jbu_apply(bf16): too many tiles");
-  const int grid = (int)std::min<long long>(total, (long long)sm_count() * (2 / XB));
-  adaptive_conv_mma_kernel<R><<<grid, NTHREADS, smem, st>>>(hr, H2, W2, C, kern, ldk, dst, nx, ny, (int)total);
+  dim3 grid(cdiv(W2, TX), cdiv(H2, RW), n_crops * cdiv(C, CS));
+  CSEG_REQUIRE(grid.z <= 65535, "jbu_apply(bf16): too many crop x channel slabs (%u)", grid.z);
+  adaptive_conv_mma_kernel<R><<<grid, NTHREADS, smem, st>>>(hr, H2, W2, C, kern, ldk, dst);
   CSEG_LAUNCH_CHECK("jbu_adaptive_conv_mma");
   return 0;
 }
