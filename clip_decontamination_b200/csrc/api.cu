@@ -14,6 +14,10 @@ int cseg_gemm_simt(int in_dtype, const void* A, int lda, const void* B, int ldb,
 int cseg_fixup_norm_sim_tc(const void* y, int ldy, const void* W, int ldw, int M, int C, const float* bias, float alpha,
                            const float* text, int Q, const float* cls_bias, int hw, float* logits, cudaStream_t st);
 
+int cseg_basis_logits_tc(const void* s, int lds, int Cb, int n_crops, int hw, int T, int tstride, const void* gram,
+                         const void* aux, int ldg, const float* consts, int Q, const float* cls_bias, float* logits,
+                         cudaStream_t st);
+
 extern "C" {
 
 int cseg_version(void) { return CSEG_VERSION; }
@@ -54,6 +58,15 @@ int cseg_fixup_norm_sim(int dtype, const void* y, int ldy, const void* W, int ld
                      stream);
   if (rc) return rc;
   return cseg_norm_sim(dtype, scratch, C, n_crops, hw, C, text, Q, cls_logit_bias, logits, stream);
+}
+
+int cseg_basis_logits(int dtype, const void* s, int lds, int Cb, int n_crops, int hw, int T, int tstride,
+                      const void* gram, const void* aux, int ldg, const float* consts, int Q,
+                      const float* cls_logit_bias, float* logits, void* stream) {
+  CSEG_REQUIRE(dtype == CSEG_BF16, "basis_logits: bf16 only (the fp32 verification mode upsamples the features directly)");
+  CSEG_REQUIRE(s && gram && aux && consts && logits, "basis_logits: null operand");
+  return cseg_basis_logits_tc(s, lds, Cb, n_crops, hw, T, tstride, gram, aux, ldg, consts, Q, cls_logit_bias, logits,
+                              (cudaStream_t)stream);
 }
 
 // test hook: CUDA-core GEMM on bf16 operands (on-device cross-check of the tcgen05 kernel)

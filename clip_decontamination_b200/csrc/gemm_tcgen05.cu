@@ -652,6 +652,206 @@ int launch_normsim(const CUtensorMap& ta, const CUtensorMap& tb, int M, int C, c
   return 0;
 }
 
+
+// =====================================================================================================
+// Cosine logits from basis coefficients (the "basis path" of the JBU head).
+// The JBU stack is linear in its source and acts on every channel alike, so upsampling the identity (one
+// channel per low-resolution token) yields coefficients s[p, k] with
+//   feature[p] = sum_k s[p, k] * g[k] + b            g = per-crop token features after the final 1x1 conv
+// and the normalise + similarity of segmentor.py:374-379 becomes, per pixel p of a crop,
+//   |feature|^2 = s^T (g g^T) s + 2 s.(g b) + b.b     <feature, t_q> = s.(g t_q) + b.t_q
+// i.e. one GEMM  D = S . [Gram | Aux]^T  with N = T + 16 columns instead of C, whose epilogue needs one
+// multiply-add per Gram column (sum_j D[p, j] s[p, j]).  K = T (tokens per crop, <= 256) instead of C.
+// Same TMA / tcgen05 / TMEM pipeline as above; one M-panel (128 pixels of one crop) per accumulator stage.
+// =====================================================================================================
+struct BlCfg {
+  static constexpr int STAGES = 4, N1_MAX = 256, N2 = 16;
+  static constexpr int A_BYTES = BM * BK * 2, B1_BYTES = N1_MAX * BK * 2, B2_BYTES = N2 * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B1_BYTES + B2_BYTES;      // 50 KB, a multiple of 1024
+  static constexpr int EPI_WARPS = 16, THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int PART_OFF = STAGES * STAGE_BYTES;                  // part [2][4 column groups][128 rows]
+  static constexpr int PART_BYTES = 2 * 4 * 128 * 4;
+  static constexpr int BAR_OFF = PART_OFF + PART_BYTES;
+  static constexpr int NBARS = 2 * STAGES + 4;
+  static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// KS = ceil(T / 16) K-steps (and Gram column groups); panels never straddle crops (hw % 128 == 0).
+__global__ void __launch_bounds__(BlCfg::THREADS, 1)
+basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
+                    const __grid_constant__ CUtensorMap tmB2, int panels, int hw, int tstride, int KS,
+                    const bf16* __restrict__ s, int lds, const float* __restrict__ consts, int Q,
+                    const float* __restrict__ cls_bias, float* __restrict__ logits) {
+  using Cf = BlCfg;
+  constexpr int STAGES = Cf::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + Cf::BAR_OFF);
+  uint32_t* tmem_slot = (uint32_t*)(bars + Cf::NBARS);
+  float* part = reinterpret_cast<float*>(smem + Cf::PART_OFF);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + STAGES * 8;
+  const uint32_t tfull0 = empty0 + STAGES * 8, tempty0 = tfull0 + 2 * 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N1 = KS * 16, num_kb = (KS + 3) / 4;
+  const uint32_t ACC = (N1 + Cf::N2 <= 256) ? 2u : 1u;      // accumulator stages of 256 TMEM columns
+  const int panels_per_crop = hw / BM;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full0 + i * 8, 1);
+      mbar_init(empty0 + i * 8, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull0 + i * 8, 1);
+      mbar_init(tempty0 + i * 8, Cf::EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t stage_tx = (uint32_t)(Cf::A_BYTES + N1 * BK * 2 + Cf::B2_BYTES);
+      uint32_t it = 0;
+      for (int panel = blockIdx.x; panel < panels; panel += gridDim.x) {
+        const int kcrop = (panel / panels_per_crop) * tstride;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(empty0 + st * 8, ph ^ 1);
+          mbar_expect_tx(full0 + st * 8, stage_tx);
+          const uint32_t a_dst = smem_base + st * Cf::STAGE_BYTES;
+          tma_load_2d(a_dst, &tmA, full0 + st * 8, kb * BK, panel * BM);
+          tma_load_2d(a_dst + Cf::A_BYTES, &tmB1, full0 + st * 8, kcrop + kb * BK, 0);
+          tma_load_2d(a_dst + Cf::A_BYTES + Cf::B1_BYTES, &tmB2, full0 + st * 8, kcrop + kb * BK, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc(BM, N1), idesc2 = make_idesc(BM, Cf::N2);
+      uint32_t it = 0, tl = 0;
+      for (int panel = blockIdx.x; panel < panels; panel += gridDim.x, ++tl) {
+        const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
+        mbar_wait(tempty0 + as * 8, aph ^ 1);
+        tc_fence_after();
+        const uint32_t tacc1 = tmem_base + as * 256, tacc2 = tacc1 + (uint32_t)N1;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(full0 + st * 8, ph);
+          tc_fence_after();
+          const uint32_t a_src = smem_base + st * Cf::STAGE_BYTES;
+          const uint64_t adesc = make_sdesc(a_src);
+          const uint64_t b1desc = make_sdesc(a_src + Cf::A_BYTES);
+          const uint64_t b2desc = make_sdesc(a_src + Cf::A_BYTES + Cf::B1_BYTES);
+          const int ksteps = min(4, KS - kb * 4);
+          for (int k = 0; k < ksteps; ++k) {
+            const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_f16(tacc1, adesc + 2 * k, b1desc + 2 * k, idesc1, accum);
+            umma_f16(tacc2, adesc + 2 * k, b2desc + 2 * k, idesc2, accum);
+          }
+          umma_commit(empty0 + st * 8);
+        }
+        umma_commit(tfull0 + as * 8);
+      }
+    }
+  } else {
+    const int ew = warp - 2, lg = warp & 3, cg = ew >> 2;
+    uint32_t tl = 0;
+    for (int panel = blockIdx.x; panel < panels; panel += gridDim.x, ++tl) {
+      const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
+      const size_t row = (size_t)panel * BM + lg * 32 + lane;
+      // this lane's coefficients of the Gram column groups cg, cg+4, ... (32 B each), fetched before the
+      // accumulator is ready
+      uint4 sv[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int g = cg + 4 * i;
+        if (g < KS) {
+          const uint4* sp = reinterpret_cast<const uint4*>(s + row * lds + g * 16);
+          sv[i][0] = sp[0];
+          sv[i][1] = sp[1];
+        }
+      }
+      mbar_wait(tfull0 + as * 8, aph);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(lg * 32) << 16) + as * 256;
+      float den = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int g = cg + 4 * i;
+        if (g < KS) {                                      // warp-uniform
+          uint32_t r[16];
+          __syncwarp();
+          tmem_ld16(trow + (uint32_t)(g * 16), r);
+          const __nv_bfloat162* sh = reinterpret_cast<const __nv_bfloat162*>(&sv[i][0]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 f = __bfloat1622float2(sh[j]);
+            den = fmaf(__uint_as_float(r[2 * j]), f.x, den);
+            den = fmaf(__uint_as_float(r[2 * j + 1]), f.y, den);
+          }
+        }
+      }
+      uint32_t nr[16];
+      if (cg == 3) {
+        __syncwarp();
+        tmem_ld16(trow + (uint32_t)N1, nr);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + as * 8);
+      float* pb = part + (size_t)(tl & 1) * 4 * 128;
+      pb[cg * 128 + lg * 32 + lane] = den;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * BlCfg::EPI_WARPS) : "memory");   // epilogue warps only
+      if (cg == 3) {
+        const int r128 = lg * 32 + lane;
+        float hb = 0.f;                                    // D2 column Q = s . (g b); select keeps nr[] in registers
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          if (q == Q) hb = __uint_as_float(nr[q]);
+        const float d2 = pb[r128] + pb[128 + r128] + pb[256 + r128] + pb[384 + r128] + 2.f * hb + __ldg(consts + Q);
+        const float inv = 1.0f / sqrtf(fmaxf(d2, 1e-30f));
+        const size_t crop = row / hw, pix = row % hw;
+#pragma unroll
+        for (int q = 0; q < 15; ++q)
+          if (q < Q) {
+            float v = (__uint_as_float(nr[q]) + __ldg(consts + q)) * inv;
+            if (cls_bias) v += cls_bias[crop * Q + q];
+            logits[(crop * Q + q) * hw + pix] = v;
+          }
+      }
+      // the part buffer alternates per panel; a buffer is rewritten two panels later, after another bar.sync
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 }  // namespace
 
 // returns 1 when the shape is not covered by the fused kernel (caller runs cseg_gemm + cseg_norm_sim instead)
@@ -666,6 +866,34 @@ int cseg_fixup_norm_sim_tc(const void* y, int ldy, const void* W, int ldw, int M
   if (Q <= 8)
     return launch_normsim<8>(ta, tb, M, C, (const bf16*)y, ldy, bias, alpha, text, Q, cls_bias, hw, logits, st);
   return launch_normsim<16>(ta, tb, M, C, (const bf16*)y, ldy, bias, alpha, text, Q, cls_bias, hw, logits, st);
+}
+
+int cseg_basis_logits_tc(const void* s, int lds, int Cb, int n_crops, int hw, int T, int tstride, const void* gram,
+                         const void* aux, int ldg, const float* consts, int Q, const float* cls_bias, float* logits,
+                         cudaStream_t st) {
+  CSEG_REQUIRE(n_crops > 0 && hw > 0 && hw % BM == 0, "basis_logits: hw=%d must be a positive multiple of %d", hw, BM);
+  CSEG_REQUIRE(T > 0 && T <= 256 && tstride >= T, "basis_logits: T=%d (tokens per crop) must be in 1..256, tstride=%d >= T", T, tstride);
+  CSEG_REQUIRE(Q > 0 && Q <= 15, "basis_logits: Q=%d must be in 1..15", Q);
+  const int KS = cdiv(T, 16);
+  CSEG_REQUIRE(Cb >= KS * 16 && lds >= Cb, "basis_logits: coefficient rows need >= %d columns (Cb=%d, lds=%d)", KS * 16, Cb, lds);
+  CSEG_REQUIRE(lds % 8 == 0 && ldg % 8 == 0, "basis_logits: lds=%d, ldg=%d must be multiples of 8", lds, ldg);
+  CSEG_REQUIRE(((uintptr_t)s & 15) == 0 && ((uintptr_t)gram & 15) == 0 && ((uintptr_t)aux & 15) == 0,
+               "basis_logits: operands must be 16-byte aligned");
+  const long long M = (long long)n_crops * hw;
+  CSEG_REQUIRE(M < (1ll << 31), "basis_logits: too many pixels");
+  CUtensorMap ta, tb1, tb2;
+  int rc = make_map(&ta, s, (int)M, Cb, lds, BM);
+  if (rc) return rc;
+  rc = make_map(&tb1, gram, KS * 16, ldg, ldg, KS * 16);
+  if (rc) return rc;
+  rc = make_map(&tb2, aux, BlCfg::N2, ldg, ldg, BlCfg::N2);
+  if (rc) return rc;
+  CSEG_SET_SMEM(basis_logits_kernel, BlCfg::SMEM_BYTES);
+  const int panels = (int)(M / BM);
+  basis_logits_kernel<<<std::min(panels, sm_count()), BlCfg::THREADS, BlCfg::SMEM_BYTES, st>>>(
+      ta, tb1, tb2, panels, hw, tstride, KS, (const bf16*)s, lds, consts, Q, cls_bias, logits);
+  CSEG_LAUNCH_CHECK("basis_logits");
+  return 0;
 }
 
 int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,

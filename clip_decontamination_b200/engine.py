@@ -280,7 +280,7 @@ class JBUEngine:
         """feats T [n*gh*gw, C] channel-last; returns T [n*(16gh)*(16gw), C] after the final fix-up
         (upsamplers.py:320-325); with final_conv=False the output of the fourth stage (the caller fuses the
         1x1 conv with the normalise + similarity, ``ops.fixup_norm_sim``)."""
-        ws, n, C, cdt = self.ws, windows.shape[0], self.C, self.cdt
+        ws, n, C, cdt = self.ws, windows.shape[0], feats.shape[1], self.cdt     # C = self.C, or the basis width
         f32 = torch.float32
         s, h, w = feats, gh, gw
         for si, st in enumerate(self.stages):
@@ -310,6 +310,53 @@ class JBUEngine:
         ops.gemm(s, self.w_fin, out, bias=self.b_fin, residual=s, alpha=0.1)
         return out
 
+    # ---- basis form: upsample the identity instead of the features (cseg_basis_logits) ----------------
+    def basis_ok(self, P: int, hw: int, Q: int) -> bool:
+        """The stack is linear in its source and treats all channels alike, so for P tokens per crop < C it is
+        cheaper to upsample one-hot token indicators (width round_up(P, 64)) and contract with the P x P Gram
+        matrix of the token features afterwards.  bf16 only; fp32 stays on the literal path."""
+        return (self.cdt == torch.bfloat16 and P <= 256 and max(128, _round_up(P, 64)) < self.C
+                and hw % 128 == 0 and Q <= 15 and self.C % 8 == 0)
+
+    def _basis_state(self, n: int, P: int, text: torch.Tensor) -> dict:
+        key = (n, P, text.data_ptr())
+        st = getattr(self, '_basis', {}).get(key)
+        if st is None:
+            dev, C, Q = self.device, self.C, text.shape[0]
+            Cb = max(128, _round_up(P, 64))
+            eye = torch.zeros(n, P, Cb, device=dev, dtype=self.cdt)
+            eye[:, torch.arange(P), torch.arange(P)] = 1
+            ldg = _round_up(n * P + 8, 8)
+            b = 0.1 * self.b_fin                                   # bias of the final fix-up, upsamplers.py:325
+            tb = torch.zeros(16, C, device=dev, dtype=torch.float32)
+            tb[:Q] = text
+            tb[Q] = b
+            consts = torch.cat([text @ b, (b @ b).reshape(1)]).contiguous()
+            st = dict(Cb=Cb, ldg=ldg, eye=eye.reshape(n * P, Cb), tb=tb.to(self.cdt).contiguous(), consts=consts,
+                      g=torch.zeros(n * P, C, device=dev, dtype=self.cdt),
+                      gram=torch.zeros(_round_up(P, 16), ldg, device=dev, dtype=self.cdt),
+                      aux=torch.zeros(16, ldg, device=dev, dtype=self.cdt))
+            if not hasattr(self, '_basis'):
+                self._basis = {}
+            self._basis[key] = st
+        return st
+
+    def basis_logits(self, feats: torch.Tensor, gh: int, gw: int, img: torch.Tensor, windows: torch.Tensor,
+                     crop_h: int, crop_w: int, pad_top: int, pad_left: int, text: torch.Tensor,
+                     logits: torch.Tensor, cls_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Same result as upsample(final_conv=False) + ops.fixup_norm_sim: logits fp32 [n, Q, crop_h*crop_w]."""
+        n, P, Q = windows.shape[0], gh * gw, text.shape[0]
+        st = self._basis_state(n, P, text)
+        g, gram, aux = st['g'], st['gram'], st['aux']
+        # token features after the final 1x1 conv (without its bias): g = x + 0.1 * x . W^T
+        ops.gemm(feats, self.w_fin, g, residual=feats, alpha=0.1)
+        for c in range(n):                                          # P x P Gram matrix of every crop
+            gc = g[c * P:(c + 1) * P]
+            ops.gemm(gc, gc, gram[:P, c * P:(c + 1) * P])
+        ops.gemm(st['tb'], g, aux[:, :n * P])                       # <g, text[q]> and <g, b>
+        s = self.upsample(st['eye'], gh, gw, img, windows, crop_h, crop_w, pad_top, pad_left, None, final_conv=False)
+        return ops.basis_logits(s, st['Cb'], n, crop_h * crop_w, P, P, gram, aux, st['consts'], Q, logits, cls_bias)
+
 
 class SegEngine:
     """forward_slide + forward_feature head + postprocess_result for one image at a time."""
@@ -319,7 +366,7 @@ class SegEngine:
                  logit_scale: float = 50.0, slide_stride: int = 112, slide_crop: int = 224,
                  cls_token_lambda: float = 0.0, global_debias_factor: float = 0.0, bg_idx: int = 0,
                  upsampler: Optional[JBUEngine] = None, sim_cfg: Optional[dict] = None,
-                 outlier_cfg: Optional[dict] = None, jbu_chunk: int = 16):
+                 outlier_cfg: Optional[dict] = None, jbu_chunk: int = 16, basis: bool = True):
         self.v = visual
         self.device = visual.device
         self.text = query_features.detach().to(self.device, torch.float32).contiguous()
@@ -334,6 +381,7 @@ class SegEngine:
         self.up = upsampler
         self.sim_cfg, self.outlier_cfg = sim_cfg, outlier_cfg
         self.jbu_chunk = jbu_chunk
+        self.basis = basis          # bf16: upsample token indicators instead of features when that is cheaper
         self.ws = Workspace(self.device)
         self._win_cache: Dict[Tuple[int, int], Tuple[torch.Tensor, list]] = {}
         self._graphs: Dict[Tuple[int, int], dict] = {}
@@ -383,8 +431,13 @@ class SegEngine:
             if ps != 16:
                 raise ValueError('JBU upsamples x16 and only matches patch size 16 (segmentor.py:372)')
             logits = ws.get('logits', (n, self.Q, crop_h, crop_w), torch.float32)
+            basis = self.basis and taps is None and self.up.basis_ok(P, crop_h * crop_w, self.Q)
             for c0 in range(0, n, self.jbu_chunk):
                 c1 = min(n, c0 + self.jbu_chunk)
+                if basis:
+                    self.up.basis_logits(feats[c0 * P:c1 * P], gh, gw, img, win_dev[c0:c1], crop_h, crop_w, pt, pl,
+                                         self.text, logits[c0:c1], cls_bias[c0:c1] if cls_bias is not None else None)
+                    continue
                 y = self.up.upsample(feats[c0 * P:c1 * P], gh, gw, img, win_dev[c0:c1], crop_h, crop_w, pt, pl,
                                      taps if c0 == 0 else None, final_conv=False)
                 fused = (cdt == torch.bfloat16 and D % 128 == 0 and D <= 512 and self.Q <= 16)

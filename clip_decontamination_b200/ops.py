@@ -155,6 +155,14 @@ def fixup_norm_sim(y, W, n_crops, hw, Cc, bias, alpha, text, logits, cls_logit_b
     return logits
 
 
+def basis_logits(s, Cb, n_crops, hw, T, tstride, gram, aux, consts, Q, logits, cls_logit_bias=None):
+    """Cosine logits from JBU basis coefficients (include/clipseg.h: cseg_basis_logits)."""
+    assert gram.stride(0) == aux.stride(0)
+    check(lib.cseg_basis_logits(_dt(s), _ptr(s), s.stride(0), Cb, n_crops, hw, T, tstride, _ptr(gram), _ptr(aux),
+                                gram.stride(0), _ptr(consts), Q, _ptr(cls_logit_bias), _ptr(logits), _stream()))
+    return logits
+
+
 def accum_argmax(crop_logits, windows, crop_h, crop_w, pad_top, pad_left, H, W, out_h, out_w, query_idx, K,
                  logit_scale, prob_thd, bg_idx, labels, probs=None, avg_logits=None):
     n, Q, lh, lw = crop_logits.shape

@@ -159,6 +159,20 @@ CSEG_API int cseg_fixup_norm_sim(int dtype, const void* y, int ldy, const void* 
                         int C, const float* bias, float alpha, const float* text, int Q,
                         const float* cls_logit_bias, float* logits, void* scratch, void* stream);
 
+/* K11..K13 in basis form (bf16 fast path; same result as cseg_jbu_apply x4 + cseg_fixup_norm_sim).
+ * The JBU stack (upsamplers.py:269-274,320-325) is linear in its source and treats every channel alike, so
+ * upsampling the identity (one channel per low-resolution token: src[crop, k, :] = e_k) gives coefficients
+ * s[p, k] with  out[p] = sum_k s[p, k] g[crop, k] + b,  g = tokens after the final 1x1 conv, and
+ *   |out|^2 = s^T (g g^T) s + 2 s.(g b) + b.b        <out, text[q]> = s.(g text[q]) + b.text[q].
+ * s    bf16 [n_crops*hw, lds], Cb valid columns (>= 16*ceil(T/16); columns >= T are zero), hw % 128 == 0
+ * gram bf16 [16*ceil(T/16), ldg]: gram[j, crop*tstride + k] = <g[crop, j], g[crop, k]>, rows >= T zero
+ * aux  bf16 [16, ldg]: aux[q, crop*tstride + k] = <g[crop, k], text[q]> (q < Q), row Q = <g[crop, k], b>
+ * consts fp32 [Q+1]: <b, text[q]>, then <b, b>.    T <= 256 tokens per crop, Q <= 15.
+ * logits fp32 [n_crops, Q, hw] = cosine (+ cls_logit_bias[crop, q], segmentor.py:378-379). */
+CSEG_API int cseg_basis_logits(int dtype, const void* s, int lds, int Cb, int n_crops, int hw, int T, int tstride,
+                      const void* gram, const void* aux, int ldg, const float* consts, int Q,
+                      const float* cls_logit_bias, float* logits, void* stream);
+
 /* ---- A11 + A12: forward_slide accumulation + postprocess_result, segmentor.py:413-449,475-499 --
  * crop_logits fp32 [n_crops, Q, lh, lw]; when (lh,lw) != (crop_h,crop_w) each crop is first
  * resized bilinearly (align_corners=False) to crop_h x crop_w (segmentor.py:388-391).  The window

@@ -211,6 +211,24 @@ def test_seg_potsdam_jbu(gold, precision, tol):
     _check_seg('seg_potsdam_jbu', seg, g, precision, tol)
 
 
+def test_seg_potsdam_jbu_basis_vs_literal(gold):
+    """bf16 head in basis form (upsample token indicators, Gram contraction: cseg_basis_logits) against the
+    literal form (upsample 512 channels, fused 1x1 conv + normalise: cseg_fixup_norm_sim) on the same crops:
+    per-crop cosine logits agree to 5e-3 and both stay within the 1e-2 bar of the fp32 reference."""
+    g = gold('seg_potsdam_jbu')
+    seg = _seg_engine('ViT-B-16', 'potsdam', 'bf16', g, upsampler='jbu_one')
+    assert seg.basis and seg.up.basis_ok(196, 224 * 224, seg.Q)
+    H, W, seed = int(g['meta'][0]), int(g['meta'][1]), int(g['meta'][4])
+    img = torch.from_numpy(synth.preprocess(synth.voronoi_scene(H, W, seed))).cuda()
+    lb = seg.crop_logits(img)[0].clone()
+    seg.basis = False
+    ll = seg.crop_logits(img)[0].clone()
+    torch.cuda.synchronize()
+    d = (lb - ll).abs().max().item()
+    print(f'[basis vs literal] max|dlogit| per crop = {d:.3e}')
+    assert torch.isfinite(lb).all() and d < 5e-3
+
+
 @pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('bf16', 1e-2)])
 def test_seg_loveda_vitl(gold, precision, tol):
     """BASELINE config 3 shape: ViT-L/14 (L=257, 24 layers), no upsampler, 448x448 (9 crops), Q=9 -> K=7."""

@@ -381,6 +381,38 @@ def test_iou_hist(ops):
     assert torch.equal(hist.cpu(), torch.stack([ai, ap, al]) * 2)
 
 
+@pytest.mark.parametrize('T,Cb,Q,n,hw', [(196, 256, 6, 3, 384), (256, 256, 15, 2, 256), (16, 128, 1, 2, 128),
+                                          (49, 128, 7, 5, 640)])
+def test_basis_logits(ops, T, Cb, Q, n, hw):
+    """cosine logits from basis coefficients == normalise(S . g + b) . text^T (segmentor.py:374-379) for the same
+    bf16 operands; tolerance 2e-3 (bf16 Gram / aux rounding).  T = 256 exercises the single-stage TMEM layout."""
+    C = 512
+    S = torch.rand(n * hw, Cb, generator=_g(1)) ** 4
+    S[:, T:] = 0
+    S = (S / S.sum(-1, keepdim=True)).bfloat16()
+    g = (torch.randn(n, T, C, generator=_g(2)) * 0.3 + torch.randn(1, 1, C, generator=_g(3)) * 0.5).bfloat16()
+    b = torch.randn(C, generator=_g(4)) * 0.05
+    text = F.normalize(torch.randn(Q, C, generator=_g(5)), dim=-1)
+    cb = torch.randn(n, Q, generator=_g(6)) * 0.1
+    feat = torch.einsum('npk,nkc->npc', S.float().view(n, hw, Cb)[:, :, :T], g.float()) + b
+    ref = (F.normalize(feat, dim=-1) @ text.t()).permute(0, 2, 1) + cb[:, :, None]
+    ldg = (n * T + 15) // 8 * 8
+    gram = torch.zeros((T + 15) // 16 * 16, ldg)
+    aux = torch.zeros(16, ldg)
+    for c in range(n):
+        gf = g[c].float()
+        gram[:T, c * T:(c + 1) * T] = gf @ gf.t()
+        aux[:Q, c * T:(c + 1) * T] = text @ gf.t()
+        aux[Q, c * T:(c + 1) * T] = gf @ b
+    consts = torch.cat([text @ b, (b @ b).reshape(1)])
+    lg = torch.full((n, Q, hw), float('nan'), device='cuda')
+    ops.basis_logits(S.cuda(), Cb, n, hw, T, T, gram.bfloat16().cuda(), aux.bfloat16().cuda(), consts.cuda(), Q, lg,
+                     cb.cuda())
+    err = (lg.cpu() - ref).abs().max().item()
+    print(f'basis_logits T={T} max|d|={err:.3e}')
+    assert err < 2e-3
+
+
 @pytest.mark.parametrize('dtype,C,Q', [(torch.bfloat16, 512, 6), (torch.bfloat16, 256, 16), (torch.bfloat16, 128, 2),
                                         (torch.float32, 64, 8), (torch.bfloat16, 64, 8)])
 def test_fixup_norm_sim(ops, dtype, C, Q):
