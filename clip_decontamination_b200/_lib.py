@@ -37,7 +37,7 @@ SIGNATURES = {
     'cseg_attention': (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _f, _p, _p, _p]),
     'cseg_simmap': (_i, [_p, _i, _i, _i, _f, _i, _p, _p]),
     'cseg_outlier_suppress': (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _i, _f, _p, _p, _p]),
-    'cseg_cls_debias': (_i, [_p, _i, _i, _i, _f, _i, _p, _i, _p, _p]),
+    'cseg_cls_debias': (_i, [_p, _i, _i, _i, _f, _i, _p, _i, _i, _p, _p]),
     'cseg_jbu_guidance': (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     'cseg_jbu_range_proj': (_i, [_p, _i, _i, _p, _p, _p, _p, _i, _p, _p]),
     'cseg_jbu_range_kernel': (_i, [_i, _p, _p, _i, _i, _i, _i, _i, _f, _f, _i, _p, _i, _i, _p]),

@@ -665,11 +665,11 @@ int launch_normsim(const CUtensorMap& ta, const CUtensorMap& tb, int M, int C, c
 // Same TMA / tcgen05 / TMEM pipeline as above; one M-panel (128 pixels of one crop) per accumulator stage.
 // =====================================================================================================
 struct BlCfg {
-  static constexpr int STAGES = 4, N1_MAX = 256, N2 = 16;
-  static constexpr int A_BYTES = BM * BK * 2, B1_BYTES = N1_MAX * BK * 2, B2_BYTES = N2 * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B1_BYTES + B2_BYTES;      // 50 KB, a multiple of 1024
+  static constexpr int STAGES = 4, N_MAX = 256, N2 = 16;              // N = Gram columns + N2 aux columns
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = N_MAX * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;                 // 48 KB
   static constexpr int EPI_WARPS = 16, THREADS = 64 + 32 * EPI_WARPS;
-  static constexpr int PART_OFF = STAGES * STAGE_BYTES;                  // part [2][4 column groups][128 rows]
+  static constexpr int PART_OFF = STAGES * STAGE_BYTES;                 // part [2][4 column groups][128 rows]
   static constexpr int PART_BYTES = 2 * 4 * 128 * 4;
   static constexpr int BAR_OFF = PART_OFF + PART_BYTES;
   static constexpr int NBARS = 2 * STAGES + 4;
@@ -687,7 +687,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
-// KS = ceil(T / 16) K-steps (and Gram column groups); panels never straddle crops (hw % 128 == 0).
+// KS = ceil(T / 16) K-steps (and Gram column groups of 16); panels never straddle crops (hw % 128 == 0).
+// The B tile of a stage is the Gram rows followed by the 16 aux rows (two TMA loads into adjacent 8-row groups
+// of the SWIZZLE_128B layout), so one MMA of N = 16 KS + 16 <= 256 produces both; two accumulator stages.
 __global__ void __launch_bounds__(BlCfg::THREADS, 1)
 basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
                     const __grid_constant__ CUtensorMap tmB2, int panels, int hw, int tstride, int KS,
@@ -695,6 +697,7 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const float* __restrict__ cls_bias, float* __restrict__ logits) {
   using Cf = BlCfg;
   constexpr int STAGES = Cf::STAGES;
+  constexpr uint32_t ACC = 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + Cf::BAR_OFF);
@@ -702,10 +705,9 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   float* part = reinterpret_cast<float*>(smem + Cf::PART_OFF);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + STAGES * 8;
-  const uint32_t tfull0 = empty0 + STAGES * 8, tempty0 = tfull0 + 2 * 8;
+  const uint32_t tfull0 = empty0 + STAGES * 8, tempty0 = tfull0 + ACC * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N1 = KS * 16, num_kb = (KS + 3) / 4;
-  const uint32_t ACC = (N1 + Cf::N2 <= 256) ? 2u : 1u;      // accumulator stages of 256 TMEM columns
   const int panels_per_crop = hw / BM;
 
   if (warp == 0 && lane == 0) {
@@ -716,7 +718,7 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(full0 + i * 8, 1);
       mbar_init(empty0 + i * 8, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < (int)ACC; ++i) {
       mbar_init(tfull0 + i * 8, 1);
       mbar_init(tempty0 + i * 8, Cf::EPI_WARPS);
     }
@@ -733,7 +735,8 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t stage_tx = (uint32_t)(Cf::A_BYTES + N1 * BK * 2 + Cf::B2_BYTES);
+      const uint32_t b1_bytes = (uint32_t)(N1 * BK * 2);
+      const uint32_t stage_tx = (uint32_t)Cf::A_BYTES + b1_bytes + (uint32_t)(Cf::N2 * BK * 2);
       uint32_t it = 0;
       for (int panel = blockIdx.x; panel < panels; panel += gridDim.x) {
         const int kcrop = (panel / panels_per_crop) * tstride;
@@ -744,33 +747,29 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t a_dst = smem_base + st * Cf::STAGE_BYTES;
           tma_load_2d(a_dst, &tmA, full0 + st * 8, kb * BK, panel * BM);
           tma_load_2d(a_dst + Cf::A_BYTES, &tmB1, full0 + st * 8, kcrop + kb * BK, 0);
-          tma_load_2d(a_dst + Cf::A_BYTES + Cf::B1_BYTES, &tmB2, full0 + st * 8, kcrop + kb * BK, 0);
+          tma_load_2d(a_dst + Cf::A_BYTES + b1_bytes, &tmB2, full0 + st * 8, kcrop + kb * BK, 0);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc1 = make_idesc(BM, N1), idesc2 = make_idesc(BM, Cf::N2);
+      const uint32_t idesc = make_idesc(BM, N1 + Cf::N2);
       uint32_t it = 0, tl = 0;
       for (int panel = blockIdx.x; panel < panels; panel += gridDim.x, ++tl) {
         const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
         mbar_wait(tempty0 + as * 8, aph ^ 1);
         tc_fence_after();
-        const uint32_t tacc1 = tmem_base + as * 256, tacc2 = tacc1 + (uint32_t)N1;
+        const uint32_t tacc = tmem_base + as * 256;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(full0 + st * 8, ph);
           tc_fence_after();
           const uint32_t a_src = smem_base + st * Cf::STAGE_BYTES;
           const uint64_t adesc = make_sdesc(a_src);
-          const uint64_t b1desc = make_sdesc(a_src + Cf::A_BYTES);
-          const uint64_t b2desc = make_sdesc(a_src + Cf::A_BYTES + Cf::B1_BYTES);
+          const uint64_t bdesc = make_sdesc(a_src + Cf::A_BYTES);
           const int ksteps = min(4, KS - kb * 4);
-          for (int k = 0; k < ksteps; ++k) {
-            const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
-            umma_f16(tacc1, adesc + 2 * k, b1desc + 2 * k, idesc1, accum);
-            umma_f16(tacc2, adesc + 2 * k, b2desc + 2 * k, idesc2, accum);
-          }
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(empty0 + st * 8);
         }
         umma_commit(tfull0 + as * 8);
@@ -827,7 +826,7 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       asm volatile("bar.sync 1, %0;" ::"n"(32 * BlCfg::EPI_WARPS) : "memory");   // epilogue warps only
       if (cg == 3) {
         const int r128 = lg * 32 + lane;
-        float hb = 0.f;                                    // D2 column Q = s . (g b); select keeps nr[] in registers
+        float hb = 0.f;                                    // aux column Q = s . (g b); select keeps nr[] in registers
 #pragma unroll
         for (int q = 0; q < 16; ++q)
           if (q == Q) hb = __uint_as_float(nr[q]);
@@ -872,7 +871,8 @@ int cseg_basis_logits_tc(const void* s, int lds, int Cb, int n_crops, int hw, in
                          const void* aux, int ldg, const float* consts, int Q, const float* cls_bias, float* logits,
                          cudaStream_t st) {
   CSEG_REQUIRE(n_crops > 0 && hw > 0 && hw % BM == 0, "basis_logits: hw=%d must be a positive multiple of %d", hw, BM);
-  CSEG_REQUIRE(T > 0 && T <= 256 && tstride >= T, "basis_logits: T=%d (tokens per crop) must be in 1..256, tstride=%d >= T", T, tstride);
+  CSEG_REQUIRE(T > 0 && T <= 240 && tstride >= T && tstride % 8 == 0,
+               "basis_logits: T=%d (tokens per crop) must be in 1..240, tstride=%d >= T and a multiple of 8 (TMA)", T, tstride);
   CSEG_REQUIRE(Q > 0 && Q <= 15, "basis_logits: Q=%d must be in 1..15", Q);
   const int KS = cdiv(T, 16);
   CSEG_REQUIRE(Cb >= KS * 16 && lds >= Cb, "basis_logits: coefficient rows need >= %d columns (Cb=%d, lds=%d)", KS * 16, Cb, lds);

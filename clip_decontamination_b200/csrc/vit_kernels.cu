@@ -535,11 +535,16 @@ __global__ void __launch_bounds__(128) outlier_apply_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void cls_debias_kernel(const float* __restrict__ tok, int n_crops, int L, int D, float factor,
-                                  T* __restrict__ feats, int ldf, float* __restrict__ cls_unit) {
+                                  T* __restrict__ feats, int ldf, int rows, float* __restrict__ cls_unit) {
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int P = L - 1;
-  if (gw >= n_crops * L) return;
-  const int crop = gw / L, t = gw % L;
+  const int P = rows;                       // output rows per crop: L-1 patch tokens, then zero padding
+  if (gw >= n_crops * (rows + 1)) return;
+  const int crop = gw / (rows + 1), t = gw % (rows + 1);
+  if (t >= L) {                             // padding row
+    T* o = feats + ((size_t)crop * P + (t - 1)) * ldf;
+    for (int c = lane; c < D; c += 32) o[c] = from_f32<T>(0.f);
+    return;
+  }
   const float* cls = tok + (size_t)crop * L * D;
   float cs = 0.f;
   for (int c = lane; c < D; c += 32) cs = fmaf(cls[c], cls[c], cs);
@@ -699,15 +704,17 @@ int cseg_outlier_suppress(const float* y, float* y_out, int n_crops, int L, int 
 }
 
 int cseg_cls_debias(const float* tok, int n_crops, int L, int D, float factor, int out_dtype, void* feats, int ldf,
-                    float* cls_unit, void* stream) {
+                    int rows_per_crop, float* cls_unit, void* stream) {
   CSEG_REQUIRE(n_crops > 0 && L >= 2 && D > 0 && ldf >= D, "cls_debias: bad shape");
-  const int blocks = cdiv((long long)n_crops * L * 32, 256);
+  const int rows = rows_per_crop > 0 ? rows_per_crop : L - 1;
+  CSEG_REQUIRE(rows >= L - 1, "cls_debias: rows_per_crop=%d < %d patch tokens", rows, L - 1);
+  const int blocks = cdiv((long long)n_crops * (rows + 1) * 32, 256);
   if (out_dtype == CSEG_BF16)
     cls_debias_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(tok, n_crops, L, D, factor, (bf16*)feats, ldf,
-                                                                      cls_unit);
+                                                                      rows, cls_unit);
   else
     cls_debias_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(tok, n_crops, L, D, factor, (float*)feats, ldf,
-                                                                       cls_unit);
+                                                                       rows, cls_unit);
   CSEG_LAUNCH_CHECK("cls_debias");
   return 0;
 }

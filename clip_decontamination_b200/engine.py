@@ -315,7 +315,7 @@ class JBUEngine:
         """The stack is linear in its source and treats all channels alike, so for P tokens per crop < C it is
         cheaper to upsample one-hot token indicators (width round_up(P, 64)) and contract with the P x P Gram
         matrix of the token features afterwards.  bf16 only; fp32 stays on the literal path."""
-        return (self.cdt == torch.bfloat16 and P <= 256 and max(128, _round_up(P, 64)) < self.C
+        return (self.cdt == torch.bfloat16 and P <= 240 and max(128, _round_up(P, 64)) < self.C
                 and hw % 128 == 0 and Q <= 15 and self.C % 8 == 0)
 
     def _basis_state(self, n: int, P: int, text: torch.Tensor) -> dict:
@@ -323,17 +323,17 @@ class JBUEngine:
         st = getattr(self, '_basis', {}).get(key)
         if st is None:
             dev, C, Q = self.device, self.C, text.shape[0]
-            Cb = max(128, _round_up(P, 64))
+            Cb, Tp = max(128, _round_up(P, 64)), _round_up(P, 8)
             eye = torch.zeros(n, P, Cb, device=dev, dtype=self.cdt)
             eye[:, torch.arange(P), torch.arange(P)] = 1
-            ldg = _round_up(n * P + 8, 8)
+            ldg = _round_up(n * Tp + 8, 8)
             b = 0.1 * self.b_fin                                   # bias of the final fix-up, upsamplers.py:325
             tb = torch.zeros(16, C, device=dev, dtype=torch.float32)
             tb[:Q] = text
             tb[Q] = b
             consts = torch.cat([text @ b, (b @ b).reshape(1)]).contiguous()
-            st = dict(Cb=Cb, ldg=ldg, eye=eye.reshape(n * P, Cb), tb=tb.to(self.cdt).contiguous(), consts=consts,
-                      g=torch.zeros(n * P, C, device=dev, dtype=self.cdt),
+            st = dict(Cb=Cb, Tp=Tp, ldg=ldg, eye=eye.reshape(n * P, Cb), tb=tb.to(self.cdt).contiguous(), consts=consts,
+                      g=torch.zeros(n * Tp, C, device=dev, dtype=self.cdt),
                       gram=torch.zeros(_round_up(P, 16), ldg, device=dev, dtype=self.cdt),
                       aux=torch.zeros(16, ldg, device=dev, dtype=self.cdt))
             if not hasattr(self, '_basis'):
@@ -344,18 +344,21 @@ class JBUEngine:
     def basis_logits(self, feats: torch.Tensor, gh: int, gw: int, img: torch.Tensor, windows: torch.Tensor,
                      crop_h: int, crop_w: int, pad_top: int, pad_left: int, text: torch.Tensor,
                      logits: torch.Tensor, cls_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Same result as upsample(final_conv=False) + ops.fixup_norm_sim: logits fp32 [n, Q, crop_h*crop_w]."""
+        """Same result as upsample(final_conv=False) + ops.fixup_norm_sim: logits fp32 [n, Q, crop_h*crop_w].
+        feats: [n * round_up(P, 8), C], every crop's P tokens followed by zero rows (ops.cls_debias rows_per_crop):
+        the per-crop column blocks of gram / aux then start on 16-byte boundaries, which TMA requires."""
         n, P, Q = windows.shape[0], gh * gw, text.shape[0]
         st = self._basis_state(n, P, text)
-        g, gram, aux = st['g'], st['gram'], st['aux']
+        g, gram, aux, Tp = st['g'], st['gram'], st['aux'], st['Tp']
+        assert feats.shape[0] == n * Tp
         # token features after the final 1x1 conv (without its bias): g = x + 0.1 * x . W^T
         ops.gemm(feats, self.w_fin, g, residual=feats, alpha=0.1)
         for c in range(n):                                          # P x P Gram matrix of every crop
-            gc = g[c * P:(c + 1) * P]
-            ops.gemm(gc, gc, gram[:P, c * P:(c + 1) * P])
-        ops.gemm(st['tb'], g, aux[:, :n * P])                       # <g, text[q]> and <g, b>
+            gc = g[c * Tp:c * Tp + P]
+            ops.gemm(gc, gc, gram[:P, c * Tp:c * Tp + P])
+        ops.gemm(st['tb'], g, aux[:, :n * Tp])                      # <g, text[q]> and <g, b>
         s = self.upsample(st['eye'], gh, gw, img, windows, crop_h, crop_w, pad_top, pad_left, None, final_conv=False)
-        return ops.basis_logits(s, st['Cb'], n, crop_h * crop_w, P, P, gram, aux, st['consts'], Q, logits, cls_bias)
+        return ops.basis_logits(s, st['Cb'], n, crop_h * crop_w, P, Tp, gram, aux, st['consts'], Q, logits, cls_bias)
 
 
 class SegEngine:
@@ -417,9 +420,12 @@ class SegEngine:
         tok, L = self.v.encode(img, win_dev, crop_h, crop_w, pt, pl, self.model_type, self.ignore_residual,
                                self.sim_cfg, self.outlier_cfg, taps)
         D, cdt, ws = self.v.D, self.v.cdt, self.ws
-        feats = ws.get('feats', (n * P, D), cdt)
+        basis = (self.up is not None and self.basis and taps is None and ps == 16
+                 and self.up.basis_ok(P, crop_h * crop_w, self.Q))
+        Pp = _round_up(P, 8) if basis else P                       # basis form: zero rows pad every crop to 16 bytes
+        feats = ws.get('feats', (n * Pp, D), cdt)
         cls_unit = ws.get('cls_unit', (n, D), torch.float32)
-        ops.cls_debias(tok, n, L, D, self.debias, feats, cls_unit)
+        ops.cls_debias(tok, n, L, D, self.debias, feats, cls_unit, rows_per_crop=Pp)
         if taps is not None:
             taps['tok'] = tok.clone()
             taps['patch_feats'] = feats.clone()
@@ -431,11 +437,10 @@ class SegEngine:
             if ps != 16:
                 raise ValueError('JBU upsamples x16 and only matches patch size 16 (segmentor.py:372)')
             logits = ws.get('logits', (n, self.Q, crop_h, crop_w), torch.float32)
-            basis = self.basis and taps is None and self.up.basis_ok(P, crop_h * crop_w, self.Q)
             for c0 in range(0, n, self.jbu_chunk):
                 c1 = min(n, c0 + self.jbu_chunk)
                 if basis:
-                    self.up.basis_logits(feats[c0 * P:c1 * P], gh, gw, img, win_dev[c0:c1], crop_h, crop_w, pt, pl,
+                    self.up.basis_logits(feats[c0 * Pp:c1 * Pp], gh, gw, img, win_dev[c0:c1], crop_h, crop_w, pt, pl,
                                          self.text, logits[c0:c1], cls_bias[c0:c1] if cls_bias is not None else None)
                     continue
                 y = self.up.upsample(feats[c0 * P:c1 * P], gh, gw, img, win_dev[c0:c1], crop_h, crop_w, pt, pl,

@@ -110,9 +110,9 @@ def outlier_suppress(y, y_out, n_crops, L, width, grid, stats, heads, top_k, con
     return y_out
 
 
-def cls_debias(tok, n_crops, L, D, factor, feats, cls_unit=None):
+def cls_debias(tok, n_crops, L, D, factor, feats, cls_unit=None, rows_per_crop=0):
     check(lib.cseg_cls_debias(_ptr(tok), n_crops, L, D, factor, _dt(feats), _ptr(feats), feats.shape[-1],
-                              _ptr(cls_unit), _stream()))
+                              rows_per_crop, _ptr(cls_unit), _stream()))
     return feats
 
 

@@ -116,9 +116,10 @@ CSEG_API int cseg_outlier_suppress(const float* y, float* y_out, int n_crops, in
                           int32_t* plan, int32_t* outlier_idx, void* stream);
 /* forward_feature head (segmentor.py:309-336): tok fp32 [n_crops*L, D] = ln_post(x) @ proj.
  * cls_unit[crop] = tok[crop*L] / |.|;  feats[crop, p] = f - factor * cos(f, cls) * cls_unit
- * written as T [n_crops*(L-1), ldf] (channel-last patch grid). */
+ * written as T [n_crops*rows_per_crop, ldf] (channel-last patch grid); rows_per_crop = 0 means L-1, a larger
+ * value appends zero rows to every crop (16-byte aligned per-crop blocks for cseg_basis_logits). */
 CSEG_API int cseg_cls_debias(const float* tok, int n_crops, int L, int D, float factor, int out_dtype,
-                    void* feats, int ldf, float* cls_unit, void* stream);
+                    void* feats, int ldf, int rows_per_crop, float* cls_unit, void* stream);
 
 /* ---- JBU upsampler (K11): simfeatup_dev/upsamplers.py:202-325 ---------------------------------
  * guidance for one stage: adaptive_avg_pool2d of each crop to (gh, gw) (:316) -> fp32 [n,gh,gw,4]
@@ -167,7 +168,8 @@ CSEG_API int cseg_fixup_norm_sim(int dtype, const void* y, int ldy, const void* 
  * s    bf16 [n_crops*hw, lds], Cb valid columns (>= 16*ceil(T/16); columns >= T are zero), hw % 128 == 0
  * gram bf16 [16*ceil(T/16), ldg]: gram[j, crop*tstride + k] = <g[crop, j], g[crop, k]>, rows >= T zero
  * aux  bf16 [16, ldg]: aux[q, crop*tstride + k] = <g[crop, k], text[q]> (q < Q), row Q = <g[crop, k], b>
- * consts fp32 [Q+1]: <b, text[q]>, then <b, b>.    T <= 256 tokens per crop, Q <= 15.
+ * consts fp32 [Q+1]: <b, text[q]>, then <b, b>.    T <= 240 tokens per crop, Q <= 15, tstride % 8 == 0
+ * (TMA box origins must be 16-byte aligned).
  * logits fp32 [n_crops, Q, hw] = cosine (+ cls_logit_bias[crop, q], segmentor.py:378-379). */
 CSEG_API int cseg_basis_logits(int dtype, const void* s, int lds, int Cb, int n_crops, int hw, int T, int tstride,
                       const void* gram, const void* aux, int ldg, const float* consts, int Q,

@@ -277,6 +277,12 @@ def test_cls_debias(ops, factor):
     ops.cls_debias(tok.cuda(), n, L, D, factor, feats, cu)
     assert (feats.cpu().view(n, L - 1, D) - f).abs().max().item() < 2e-6
     assert (cu.cpu() - cls).abs().max().item() < 2e-6
+    # padded form: rows_per_crop > L-1 appends zero rows to every crop
+    rows = 32
+    fp = torch.full((n * rows, D), float('nan'), device='cuda')
+    ops.cls_debias(tok.cuda(), n, L, D, factor, fp, cu, rows_per_crop=rows)
+    fp = fp.cpu().view(n, rows, D)
+    assert torch.equal(fp[:, :L - 1], feats.cpu().view(n, L - 1, D)) and (fp[:, L - 1:] == 0).all()
 
 
 @pytest.mark.parametrize('dtype,C,radius,h', [(torch.bfloat16, 128, 5, 14), (torch.bfloat16, 256, 3, 20),
@@ -381,11 +387,11 @@ def test_iou_hist(ops):
     assert torch.equal(hist.cpu(), torch.stack([ai, ap, al]) * 2)
 
 
-@pytest.mark.parametrize('T,Cb,Q,n,hw', [(196, 256, 6, 3, 384), (256, 256, 15, 2, 256), (16, 128, 1, 2, 128),
+@pytest.mark.parametrize('T,Cb,Q,n,hw', [(196, 256, 6, 3, 384), (240, 256, 15, 2, 256), (16, 128, 1, 2, 128),
                                           (49, 128, 7, 5, 640)])
 def test_basis_logits(ops, T, Cb, Q, n, hw):
     """cosine logits from basis coefficients == normalise(S . g + b) . text^T (segmentor.py:374-379) for the same
-    bf16 operands; tolerance 2e-3 (bf16 Gram / aux rounding).  T = 256 exercises the single-stage TMEM layout."""
+    bf16 operands; tolerance 2e-3 (bf16 Gram / aux rounding).  T = 240 is the widest tile (N = 256)."""
     C = 512
     S = torch.rand(n * hw, Cb, generator=_g(1)) ** 4
     S[:, T:] = 0
@@ -396,17 +402,18 @@ def test_basis_logits(ops, T, Cb, Q, n, hw):
     cb = torch.randn(n, Q, generator=_g(6)) * 0.1
     feat = torch.einsum('npk,nkc->npc', S.float().view(n, hw, Cb)[:, :, :T], g.float()) + b
     ref = (F.normalize(feat, dim=-1) @ text.t()).permute(0, 2, 1) + cb[:, :, None]
-    ldg = (n * T + 15) // 8 * 8
+    Tp = (T + 7) // 8 * 8                       # per-crop column blocks start on 16-byte boundaries (TMA)
+    ldg = (n * Tp + 15) // 8 * 8
     gram = torch.zeros((T + 15) // 16 * 16, ldg)
     aux = torch.zeros(16, ldg)
     for c in range(n):
         gf = g[c].float()
-        gram[:T, c * T:(c + 1) * T] = gf @ gf.t()
-        aux[:Q, c * T:(c + 1) * T] = text @ gf.t()
-        aux[Q, c * T:(c + 1) * T] = gf @ b
+        gram[:T, c * Tp:c * Tp + T] = gf @ gf.t()
+        aux[:Q, c * Tp:c * Tp + T] = text @ gf.t()
+        aux[Q, c * Tp:c * Tp + T] = gf @ b
     consts = torch.cat([text @ b, (b @ b).reshape(1)])
     lg = torch.full((n, Q, hw), float('nan'), device='cuda')
-    ops.basis_logits(S.cuda(), Cb, n, hw, T, T, gram.bfloat16().cuda(), aux.bfloat16().cuda(), consts.cuda(), Q, lg,
+    ops.basis_logits(S.cuda(), Cb, n, hw, T, Tp, gram.bfloat16().cuda(), aux.bfloat16().cuda(), consts.cuda(), Q, lg,
                      cb.cuda())
     err = (lg.cpu() - ref).abs().max().item()
     print(f'basis_logits T={T} max|d|={err:.3e}')
