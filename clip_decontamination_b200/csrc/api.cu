@@ -1,8 +1,18 @@
 // extern "C" entry points that are not tied to one kernel file (error state, version, GEMM dispatch).
 #include "common.cuh"
+#include <stdlib.h>
 
 thread_local char g_cseg_err[512] = {0};
 std::atomic<long long> g_cseg_launches{0};
+
+bool cseg_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CSEG_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
 
 int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
                       const void* residual, int ldr, int res_dtype, float alpha, int act, int out_dtype, void* C, int ldc,

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(AWARPS * 32, 2) attention_mma_kernel(const bf1
                                                                        int mode, const float* __restrict__ simmap,
                                                                        float simw, bf16* __restrict__ out,
                                                                        float* __restrict__ stats) {
+  pdl_grid_sync();
   constexpr int LP = NKB * 8;  // padded key count (multiple of 16)
   extern __shared__ __align__(16) uint8_t asmem[];
   const uint32_t qt = (uint32_t)__cvta_generic_to_shared(asmem);
@@ -249,7 +250,7 @@ int launch(const bf16* qkv, int n_crops, int L, int heads, int mode, const float
   const int smem = 3 * NKB * 8 * RSTRIDE;
   CSEG_SET_SMEM(attention_mma_kernel<NKB>, smem);
   const int nsplit = (L + 16 * AWARPS - 1) / (16 * AWARPS);
-  attention_mma_kernel<NKB><<<n_crops * heads * nsplit, AWARPS * 32, smem, st>>>(qkv, L, heads, mode, simmap, simw, out, stats);
+  cseg_launch(attention_mma_kernel<NKB>, dim3(n_crops * heads * nsplit), dim3(AWARPS * 32), smem, st, qkv, L, heads, mode, simmap, simw, out, stats);
   CSEG_LAUNCH_CHECK("attention_mma");
   return 0;
 }

@@ -50,6 +50,33 @@ extern std::atomic<long long> g_cseg_launches;
     }                                                                                                     \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
+// Every kernel of the library is launched with programmatic stream serialisation allowed and starts with
+// pdl_grid_sync(): the next kernel of the stream (or of a captured graph) may be scheduled while the tail of the
+// previous one drains, runs its input-independent prologue (barrier init, TMEM allocation, tensor-map prefetch),
+// and blocks in griddepcontrol.wait until the previous grid has completed and its writes are visible.  Memory
+// ordering between consecutive kernels is therefore exactly that of a plain stream; only launch latency and
+// prologues overlap.  CSEG_PDL=0 in the environment restores plain launches.
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool cseg_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void cseg_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cseg_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in CSEG_LAUNCH_CHECK
+}
+
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);

@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TI* __restrict__ A
                                                         int ldb, int M, int N, int K, const float* __restrict__ bias,
                                                         const void* residual, int ldr, int res_bf16, float alpha,
                                                         int act, int out_bf16, void* C, int ldc) {
+  pdl_grid_sync();
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -72,10 +73,10 @@ int cseg_gemm_simt(int in_dtype, const void* A, int lda, const void* B, int ldb,
   CSEG_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   dim3 grid(cdiv(N, TN), cdiv(M, TM));
   if (in_dtype == CSEG_F32)
-    gemm_simt_kernel<float><<<grid, 256, 0, st>>>((const float*)A, lda, (const float*)B, ldb, M, N, K, bias, residual,
+    cseg_launch(gemm_simt_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)A, lda, (const float*)B, ldb, M, N, K, bias, residual,
                                                   ldr, res_dtype == CSEG_BF16, alpha, act, out_dtype == CSEG_BF16, C, ldc);
   else
-    gemm_simt_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, bias, residual, ldr,
+    cseg_launch(gemm_simt_kernel<bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)A, lda, (const bf16*)B, ldb, M, N, K, bias, residual, ldr,
                                                  res_dtype == CSEG_BF16, alpha, act, out_dtype == CSEG_BF16, C, ldc);
   CSEG_LAUNCH_CHECK("gemm_simt");
   return 0;

@@ -181,6 +181,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_grid_sync();   // everything above is input-independent and overlaps the tail of the previous kernel
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -422,7 +423,7 @@ int launch3(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, c
   CSEG_SET_SMEM((gemm_bf16_tcgen05_kernel<BN, STAGES, ACT, OUTB, RES>), C::SMEM_BYTES);
   const int m_tiles = cdiv(M, BM), num_tiles = m_tiles * cdiv(N, BN);
   const int grid = std::min(num_tiles, sm_count());
-  gemm_bf16_tcgen05_kernel<BN, STAGES, ACT, OUTB, RES><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, K, m_tiles,
+  cseg_launch(gemm_bf16_tcgen05_kernel<BN, STAGES, ACT, OUTB, RES>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, K, m_tiles,
                                                                                               num_tiles, ep);
   CSEG_LAUNCH_CHECK("gemm_bf16_tcgen05");
   return 0;
@@ -509,6 +510,7 @@ gemm_normsim_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_grid_sync();   // everything above is input-independent and overlaps the tail of the previous kernel
   // text (transposed to [c][QT], zero padded) and bias into shared memory
   for (int e = threadIdx.x; e < C * QT; e += Cf::THREADS) {
     const int c = e / QT, q = e % QT;
@@ -646,7 +648,7 @@ int launch_normsim(const CUtensorMap& ta, const CUtensorMap& tb, int M, int C, c
   using Cf = NsCfg<QT>;
   CSEG_SET_SMEM(gemm_normsim_kernel<QT>, Cf::SMEM_BYTES);
   const int panels = cdiv(M, BM);
-  gemm_normsim_kernel<QT><<<std::min(panels, sm_count()), Cf::THREADS, Cf::SMEM_BYTES, st>>>(
+  cseg_launch(gemm_normsim_kernel<QT>, dim3(std::min(panels, sm_count())), dim3(Cf::THREADS), Cf::SMEM_BYTES, st, 
       ta, tb, M, C, y, ldy, bias, alpha, text, Q, cls_bias, hw, logits);
   CSEG_LAUNCH_CHECK("gemm_normsim");
   return 0;
@@ -688,6 +690,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 
 // KS = ceil(T / 16) K-steps (and Gram column groups of 16); panels never straddle crops (hw % 128 == 0).
+// gram is the full (n_crops*tstride)^2 product g g^T; the tile of a crop is its diagonal block (rows and columns
+// crop*tstride ..; rows / columns past the crop's T tokens meet zero coefficients and never contribute).
 // The B tile of a stage is the Gram rows followed by the 16 aux rows (two TMA loads into adjacent 8-row groups
 // of the SWIZZLE_128B layout), so one MMA of N = 16 KS + 16 <= 256 produces both; two accumulator stages.
 __global__ void __launch_bounds__(BlCfg::THREADS, 1)
@@ -728,6 +732,7 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_grid_sync();   // everything above is input-independent and overlaps the tail of the previous kernel
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -746,7 +751,7 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_expect_tx(full0 + st * 8, stage_tx);
           const uint32_t a_dst = smem_base + st * Cf::STAGE_BYTES;
           tma_load_2d(a_dst, &tmA, full0 + st * 8, kb * BK, panel * BM);
-          tma_load_2d(a_dst + Cf::A_BYTES, &tmB1, full0 + st * 8, kcrop + kb * BK, 0);
+          tma_load_2d(a_dst + Cf::A_BYTES, &tmB1, full0 + st * 8, kcrop + kb * BK, kcrop);
           tma_load_2d(a_dst + Cf::A_BYTES + b1_bytes, &tmB2, full0 + st * 8, kcrop + kb * BK, 0);
         }
       }
@@ -884,13 +889,13 @@ int cseg_basis_logits_tc(const void* s, int lds, int Cb, int n_crops, int hw, in
   CUtensorMap ta, tb1, tb2;
   int rc = make_map(&ta, s, (int)M, Cb, lds, BM);
   if (rc) return rc;
-  rc = make_map(&tb1, gram, KS * 16, ldg, ldg, KS * 16);
+  rc = make_map(&tb1, gram, n_crops * tstride, ldg, ldg, KS * 16);
   if (rc) return rc;
   rc = make_map(&tb2, aux, BlCfg::N2, ldg, ldg, BlCfg::N2);
   if (rc) return rc;
   CSEG_SET_SMEM(basis_logits_kernel, BlCfg::SMEM_BYTES);
   const int panels = (int)(M / BM);
-  basis_logits_kernel<<<std::min(panels, sm_count()), BlCfg::THREADS, BlCfg::SMEM_BYTES, st>>>(
+  cseg_launch(basis_logits_kernel, dim3(std::min(panels, sm_count())), dim3(BlCfg::THREADS), BlCfg::SMEM_BYTES, st, 
       ta, tb1, tb2, panels, hw, tstride, KS, (const bf16*)s, lds, consts, Q, cls_bias, logits);
   CSEG_LAUNCH_CHECK("basis_logits");
   return 0;

@@ -66,6 +66,7 @@ template <int R>
 __global__ void __launch_bounds__(NTHREADS, 2 / XB) adaptive_conv_mma_kernel(const bf16* __restrict__ hr, int H2, int W2, int C,
                                                                         const bf16* __restrict__ kern, int ldk,
                                                                         bf16* __restrict__ dst) {
+  pdl_grid_sync();
   constexpr int D = 2 * R + 1;
   constexpr int NSRC = RW + 2 * R;  // source rows per tile
   constexpr int WB_BYTES = RW * D * XB * ATILE;
@@ -235,7 +236,7 @@ int launch_conv(const bf16* hr, int n_crops, int H2, int W2, int C, const bf16* 
   CSEG_SET_SMEM(adaptive_conv_mma_kernel<R>, smem);
   dim3 grid(cdiv(W2, TX), cdiv(H2, RW), n_crops * cdiv(C, CS));
   CSEG_REQUIRE(grid.z <= 65535, "jbu_apply(bf16): too many crop x channel slabs (%u)", grid.z);
-  adaptive_conv_mma_kernel<R><<<grid, NTHREADS, smem, st>>>(hr, H2, W2, C, kern, ldk, dst);
+  cseg_launch(adaptive_conv_mma_kernel<R>, dim3(grid), dim3(NTHREADS), smem, st, hr, H2, W2, C, kern, ldk, dst);
   CSEG_LAUNCH_CHECK("jbu_adaptive_conv_mma");
   return 0;
 }

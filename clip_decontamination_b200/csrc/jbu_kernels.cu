@@ -19,6 +19,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {  // F.pad(mode='refle
 __global__ void guidance_kernel(const float* __restrict__ img, int H, int W, const int32_t* __restrict__ wins,
                                 int n_crops, int crop_h, int crop_w, int pad_top, int pad_left, int gh, int gw,
                                 float4* __restrict__ guid) {
+  pdl_grid_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_crops * gh * gw) return;
   const int gx = idx % gw, gy = (idx / gw) % gh, crop = idx / (gw * gh);
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(256) range_proj_kernel(const float4* __restric
                                                          const float* __restrict__ w0, const float* __restrict__ b0,
                                                          const float* __restrict__ w3, const float* __restrict__ b3,
                                                          float* __restrict__ proj) {
+  pdl_grid_sync();
   __shared__ float sw0[KD * 3], sb0[KD], sw3[KD * KD], sb3[KD];
   for (int i = threadIdx.x; i < KD * 3; i += blockDim.x) sw0[i] = w0[i];
   for (int i = threadIdx.x; i < KD * KD; i += blockDim.x) sw3[i] = w3[i];
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(256) range_kernel_kernel(const float* __restri
                                                            const float4* __restrict__ guid, int gh, int gw,
                                                            float pos_temp, float inv2s2, T* __restrict__ kern,
                                                            int kwidth, int ldk) {
+  pdl_grid_sync();
   constexpr int DIA = 2 * R + 1, D2 = DIA * DIA, TS = 16, HS = TS + 2 * R;
   extern __shared__ float sp[];  // [KD][HS*HS]
   const int crop = blockIdx.z, ty0 = blockIdx.y * TS, tx0 = blockIdx.x * TS;
@@ -212,6 +215,7 @@ template <> struct V4<float> {
 template <typename T>
 __global__ void __launch_bounds__(256) bicubic2x_kernel(const T* __restrict__ src, int n_crops, int h, int w, int C,
                                                         T* __restrict__ dst) {
+  pdl_grid_sync();
   const int cg = C / 4, hb = (h + 1) / 2, wb = (w + 1) / 2;
   const long long total = (long long)n_crops * hb * wb * cg;
   float cA[4], cB[4];
@@ -296,6 +300,7 @@ __global__ void __launch_bounds__(256) bicubic2x_kernel(const T* __restrict__ sr
 template <typename T, int R>
 __global__ void __launch_bounds__(256) adaptive_conv_kernel(const T* __restrict__ hr, int n_crops, int H2, int W2, int C,
                                                             const T* __restrict__ kern, int ldk, T* __restrict__ dst) {
+  pdl_grid_sync();
   constexpr int DIA = 2 * R + 1;
   const int cg = C / 8;
   const long long total = (long long)n_crops * H2 * W2 * cg;
@@ -337,7 +342,7 @@ int cseg_jbu_guidance(const float* img, int H, int W, const int32_t* windows, in
                       int pad_top, int pad_left, int gh, int gw, float* guid, void* stream) {
   CSEG_REQUIRE(n_crops > 0 && gh > 0 && gw > 0 && gh <= crop_h && gw <= crop_w, "jbu_guidance: bad shape");
   const int n = n_crops * gh * gw;
-  guidance_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(img, H, W, windows, n_crops, crop_h, crop_w, pad_top,
+  cseg_launch(guidance_kernel, dim3(cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, img, H, W, windows, n_crops, crop_h, crop_w, pad_top,
                                                                   pad_left, gh, gw, (float4*)guid);
   CSEG_LAUNCH_CHECK("jbu_guidance");
   return 0;
@@ -349,7 +354,7 @@ int cseg_jbu_range_proj(const float* guid, int n_pix, int key_dim, const float* 
   CSEG_REQUIRE(key_dim == 32, "jbu_range_proj: key_dim=%d (only 32, simfeatup_dev/upsamplers.py:282-308)", key_dim);
   if (proj_dtype == CSEG_F16) return cseg_jbu_range_proj_f16(guid, n_pix, w0, b0, w3, b3, proj, (cudaStream_t)stream);
   CSEG_REQUIRE(proj_dtype == CSEG_F32, "jbu_range_proj: proj_dtype must be CSEG_F32 or CSEG_F16");
-  range_proj_kernel<32><<<cdiv(n_pix, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)guid, n_pix, w0, b0, w3, b3,
+  cseg_launch(range_proj_kernel<32>, dim3(cdiv(n_pix, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)guid, n_pix, w0, b0, w3, b3,
                                                                             (float*)proj);
   CSEG_LAUNCH_CHECK("jbu_range_proj");
   return 0;
@@ -364,7 +369,7 @@ static int launch_range_kernel(const float* proj, const float* guid, int n_crops
   const size_t smem = (size_t)32 * HS * HS * sizeof(float);
   CSEG_SET_SMEM((range_kernel_kernel<T, R, 32>), smem);
   dim3 grid(cdiv(gw, 16), cdiv(gh, 16), n_crops);
-  range_kernel_kernel<T, R, 32><<<grid, 256, smem, st>>>(proj, (const float4*)guid, gh, gw, pos_temp, inv2s2, (T*)kern,
+  cseg_launch(range_kernel_kernel<T, R, 32>, dim3(grid), dim3(256), smem, st, proj, (const float4*)guid, gh, gw, pos_temp, inv2s2, (T*)kern,
                                                          kwidth, ldk);
   CSEG_LAUNCH_CHECK("jbu_range_kernel");
   return 0;
@@ -378,7 +383,7 @@ static int launch_apply(const void* src, int n_crops, int h, int w, int C, const
                         void* dst, void* hr_scratch, cudaStream_t st) {
   const int H2 = 2 * h, W2 = 2 * w;
   const long long tot_b = (long long)n_crops * ((h + 1) / 2) * ((w + 1) / 2) * (C / 4);
-  bicubic2x_kernel<T><<<(int)std::min<long long>((tot_b + 255) / 256, (long long)sm_count() * 32), 256, 0, st>>>(
+  cseg_launch(bicubic2x_kernel<T>, dim3((int)std::min<long long>((tot_b + 255) / 256, (long long)sm_count() * 32)), dim3(256), 0, st, 
       (const T*)src, n_crops, h, w, C, (T*)hr_scratch);
   CSEG_LAUNCH_CHECK("jbu_bicubic2x");
   if (sizeof(T) == 2 && C % 64 == 0 && C >= 128 && ldk % 8 == 0 && ldk <= 128)   // tensor-core banded GEMM path
@@ -387,10 +392,10 @@ static int launch_apply(const void* src, int n_crops, int h, int w, int C, const
   const long long tot = (long long)n_crops * H2 * W2 * (C / 8);
   const int blocks = (int)std::min<long long>((tot + 255) / 256, (long long)sm_count() * 64);
   if (radius == 5)
-    adaptive_conv_kernel<T, 5><<<blocks, 256, 0, st>>>((const T*)hr_scratch, n_crops, H2, W2, C, (const T*)kern, ldk,
+    cseg_launch(adaptive_conv_kernel<T, 5>, dim3(blocks), dim3(256), 0, st, (const T*)hr_scratch, n_crops, H2, W2, C, (const T*)kern, ldk,
                                                        (T*)dst);
   else
-    adaptive_conv_kernel<T, 3><<<blocks, 256, 0, st>>>((const T*)hr_scratch, n_crops, H2, W2, C, (const T*)kern, ldk,
+    cseg_launch(adaptive_conv_kernel<T, 3>, dim3(blocks), dim3(256), 0, st, (const T*)hr_scratch, n_crops, H2, W2, C, (const T*)kern, ldk,
                                                        (T*)dst);
   CSEG_LAUNCH_CHECK("jbu_adaptive_conv");
   return 0;

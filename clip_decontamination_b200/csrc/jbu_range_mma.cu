@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
                                                              const float4* __restrict__ guid, int gh, int gw,
                                                              float pos_temp, float inv2s2, bf16* __restrict__ kern,
                                                              int ldk) {
+  pdl_grid_sync();
   constexpr int D = 2 * R + 1, D2 = D * D;
   constexpr int NB = (16 + 2 * R + 7) / 8;       // 8-position blocks per 16-query block
   constexpr int HR = TYR + 2 * R;                // halo rows
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(256) range_proj_f16_kernel(const float4* __res
                                                              const float* __restrict__ w0, const float* __restrict__ b0,
                                                              const float* __restrict__ w3, const float* __restrict__ b3,
                                                              __half* __restrict__ proj) {
+  pdl_grid_sync();
   __shared__ float sw0[KD * 3], sb0[KD], sw3[KD * KD], sb3[KD];
   for (int i = threadIdx.x; i < KD * 3; i += blockDim.x) sw0[i] = w0[i];
   for (int i = threadIdx.x; i < KD * KD; i += blockDim.x) sw3[i] = w3[i];
@@ -229,7 +231,7 @@ int launch(const __half* proj, const float* guid, int n_crops, int gh, int gw, f
   const int smem = HR * NPOS * PROW + ((D2 * 4 + 15) & ~15) + TYR * 16 * LDK * 2;
   CSEG_SET_SMEM((range_kernel_mma<R, LDK>), smem);
   dim3 grid(cdiv(gw, TXR), cdiv(gh, TYR), n_crops);
-  range_kernel_mma<R, LDK><<<grid, TYR * 32, smem, st>>>(proj, (const float4*)guid, gh, gw, pos_temp, inv2s2, kern, ldk);
+  cseg_launch(range_kernel_mma<R, LDK>, dim3(grid), dim3(TYR * 32), smem, st, proj, (const float4*)guid, gh, gw, pos_temp, inv2s2, kern, ldk);
   CSEG_LAUNCH_CHECK("jbu_range_kernel_mma");
   return 0;
 }
@@ -238,7 +240,7 @@ int launch(const __half* proj, const float* guid, int n_crops, int gh, int gw, f
 
 int cseg_jbu_range_proj_f16(const float* guid, int n_pix, const float* w0, const float* b0, const float* w3,
                             const float* b3, void* proj, cudaStream_t st) {
-  range_proj_f16_kernel<<<cdiv(n_pix, 256), 256, 0, st>>>((const float4*)guid, n_pix, w0, b0, w3, b3, (__half*)proj);
+  cseg_launch(range_proj_f16_kernel, dim3(cdiv(n_pix, 256)), dim3(256), 0, st, (const float4*)guid, n_pix, w0, b0, w3, b3, (__half*)proj);
   CSEG_LAUNCH_CHECK("jbu_range_proj_f16");
   return 0;
 }

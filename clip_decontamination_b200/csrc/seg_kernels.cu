@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256) norm_sim_kernel(const T* __restrict__ fea
                                                        int D, const float* __restrict__ text, int Q,
                                                        const float* __restrict__ cls_bias,
                                                        float* __restrict__ logits) {
+  pdl_grid_sync();
   extern __shared__ float ts[];  // [Q][D]
   for (int i = threadIdx.x; i < Q * D; i += blockDim.x) ts[i] = text[i];
   __syncthreads();
@@ -142,6 +143,7 @@ __device__ __forceinline__ void canvas_avg(const AccumParams& p, const int4* win
 
 template <int QT>
 __global__ void __launch_bounds__(256) accum_argmax_kernel(const AccumParams p) {
+  pdl_grid_sync();
   extern __shared__ int4 s_wins[];
   for (int i = threadIdx.x; i < p.n_crops; i += blockDim.x)
     s_wins[i] = make_int4(p.windows[4 * i], p.windows[4 * i + 1], p.windows[4 * i + 2], p.windows[4 * i + 3]);
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(256) accum_argmax_kernel(const AccumParams p) 
 __global__ void __launch_bounds__(256) iou_hist_kernel(const uint8_t* __restrict__ pred,
                                                        const uint8_t* __restrict__ label, long long n, int K,
                                                        int ignore, unsigned long long* __restrict__ hist) {
+  pdl_grid_sync();
   extern __shared__ unsigned int sh[];  // [3][K]
   for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) sh[i] = 0;
   __syncthreads();
@@ -237,7 +240,7 @@ static int launch_norm_sim(const void* feats, int ldf, int n_crops, int hw, int 
 #define NS_LAUNCH(QT)                                                                                          \
   do {                                                                                                         \
     CSEG_SET_SMEM((norm_sim_kernel<T, QT>), smem);                                                              \
-    norm_sim_kernel<T, QT><<<blocks, 256, smem, st>>>((const T*)feats, ldf, rows, hw, D, text, Q, cls_bias, logits); \
+    cseg_launch(norm_sim_kernel<T, QT>, dim3(blocks), dim3(256), smem, st, (const T*)feats, ldf, rows, hw, D, text, Q, cls_bias, logits); \
   } while (0)
   if (Q <= 8) NS_LAUNCH(8);
   else if (Q <= 16) NS_LAUNCH(16);
@@ -271,9 +274,9 @@ int cseg_accum_argmax(const float* crop_logits, int n_crops, int Q, int lh, int 
                 query_idx, K, logit_scale, prob_thd, bg_idx, labels, probs, avg_logits};
   dim3 grid(cdiv(out_w, 256), out_h);
   const size_t smem = (size_t)n_crops * sizeof(int4);
-  if (Q <= 8) accum_argmax_kernel<8><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
-  else if (Q <= 16) accum_argmax_kernel<16><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
-  else accum_argmax_kernel<32><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  if (Q <= 8) cseg_launch(accum_argmax_kernel<8>, grid, dim3(256), smem, (cudaStream_t)stream, p);
+  else if (Q <= 16) cseg_launch(accum_argmax_kernel<16>, grid, dim3(256), smem, (cudaStream_t)stream, p);
+  else cseg_launch(accum_argmax_kernel<32>, grid, dim3(256), smem, (cudaStream_t)stream, p);
   CSEG_LAUNCH_CHECK("accum_argmax");
   return 0;
 }
@@ -282,8 +285,8 @@ int cseg_iou_hist(const uint8_t* pred, const uint8_t* label, long long n, int K,
                   void* stream) {
   CSEG_REQUIRE(n > 0 && K >= 1 && K <= 256, "iou_hist: bad arguments");
   const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
-  iou_hist_kernel<<<blocks, 256, (size_t)3 * K * sizeof(unsigned int), (cudaStream_t)stream>>>(
-      pred, label, n, K, ignore_index, (unsigned long long*)hist);
+  cseg_launch(iou_hist_kernel, dim3(blocks), dim3(256), (size_t)3 * K * sizeof(unsigned int), (cudaStream_t)stream,
+              pred, label, n, K, ignore_index, (unsigned long long*)hist);
   CSEG_LAUNCH_CHECK("iou_hist");
   return 0;
 }

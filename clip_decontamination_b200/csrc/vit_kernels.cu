@@ -11,6 +11,7 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ img, int HW, float m0, float m1, float m2, float s0,
                                      float s1, float s2, float* __restrict__ out) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= HW) return;
   const float b = img[3 * i + 0], g = img[3 * i + 1], r = img[3 * i + 2];
@@ -26,6 +27,7 @@ template <typename T>
 __global__ void patchify_kernel(const float* __restrict__ img, int H, int W, const int32_t* __restrict__ wins,
                                 int n_crops, int gh, int gw, int pad_top, int pad_left, int ps, T* __restrict__ out,
                                 int ldo) {
+  pdl_grid_sync();
   const long long total = (long long)n_crops * gh * gw * ldo;
   const int kk = 3 * ps * ps;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -49,6 +51,7 @@ __global__ void patchify_kernel(const float* __restrict__ img, int H, int W, con
 __global__ void embed_tokens_kernel(const float* __restrict__ pe, const float* __restrict__ cls,
                                     const float* __restrict__ pos, int n_crops, int L, int width,
                                     float* __restrict__ x) {
+  pdl_grid_sync();
   const long long total = (long long)n_crops * L * width;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -67,6 +70,7 @@ __global__ void embed_tokens_kernel(const float* __restrict__ pe, const float* _
 template <typename T>
 __global__ void layernorm_kernel(const float* x, int rows, int width, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, T* out) {
+  pdl_grid_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float* xr = x + (size_t)warp * width;
@@ -89,6 +93,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) layernorm_reg_kernel(const float* x, int rows, int width,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, T* out) {
+  pdl_grid_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int nv = width >> 2;
@@ -208,6 +213,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const T* __re
                                                                    int mode, const float* __restrict__ simmap,
                                                                    float simw, T* __restrict__ out,
                                                                    float* __restrict__ stats) {
+  pdl_grid_sync();
   constexpr int LDS = HD + (sizeof(T) == 2 ? 2 : 1);
   extern __shared__ __align__(16) uint8_t att_smem[];
   T* Qs = reinterpret_cast<T*>(att_smem);
@@ -344,6 +350,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const T* __re
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) simmap_kernel(const float* __restrict__ x, int L, int width, float inv_temp,
                                                      int keep_diag, float* __restrict__ sim) {
+  pdl_grid_sync();
   __shared__ float As[32][33], Bs[32][33];
   const int P = L - 1, crop = blockIdx.z;
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
@@ -402,6 +409,7 @@ constexpr int OS_MAXK = 64;
 __global__ void __launch_bounds__(OS_THREADS) outlier_plan_kernel(const float* __restrict__ y, int L, int width, int grid,
                                                                   const float* __restrict__ stats, int heads, int top_k,
                                                                   int* __restrict__ plan, int32_t* __restrict__ idx_out) {
+  pdl_grid_sync();
   extern __shared__ float os_smem[];
   const int P = L - 1, crop = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* ratio = os_smem;                       // [P]
@@ -498,6 +506,7 @@ __global__ void __launch_bounds__(OS_THREADS) outlier_plan_kernel(const float* _
 __global__ void __launch_bounds__(128) outlier_apply_kernel(const float* __restrict__ y, float* __restrict__ out, int L,
                                                             int width, int top_k, float ctemp,
                                                             const int* __restrict__ plan) {
+  pdl_grid_sync();
   const int P = L - 1, crop = blockIdx.x / L, t = blockIdx.x % L;
   const float* src = y + ((size_t)crop * L + t) * width;
   float* dst = out + ((size_t)crop * L + t) * width;
@@ -536,6 +545,7 @@ __global__ void __launch_bounds__(128) outlier_apply_kernel(const float* __restr
 template <typename T>
 __global__ void cls_debias_kernel(const float* __restrict__ tok, int n_crops, int L, int D, float factor,
                                   T* __restrict__ feats, int ldf, int rows, float* __restrict__ cls_unit) {
+  pdl_grid_sync();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int P = rows;                       // output rows per crop: L-1 patch tokens, then zero padding
   if (gw >= n_crops * (rows + 1)) return;
@@ -585,7 +595,7 @@ int cseg_preprocess_u8(const uint8_t* img, int H, int W, const float mean[3], co
                        void* stream) {
   CSEG_REQUIRE(H > 0 && W > 0, "preprocess: empty image");
   const int HW = H * W;
-  preprocess_u8_kernel<<<cdiv(HW, 256), 256, 0, (cudaStream_t)stream>>>(img, HW, mean[0], mean[1], mean[2], std_[0],
+  cseg_launch(preprocess_u8_kernel, dim3(cdiv(HW, 256)), dim3(256), 0, (cudaStream_t)stream, img, HW, mean[0], mean[1], mean[2], std_[0],
                                                                         std_[1], std_[2], out);
   CSEG_LAUNCH_CHECK("preprocess_u8");
   return 0;
@@ -600,10 +610,10 @@ int cseg_patchify(const float* img, int H, int W, const int32_t* windows, int n_
   const long long total = (long long)n_crops * gh * gw * ldo;
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
   if (out_dtype == CSEG_BF16)
-    patchify_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(img, H, W, windows, n_crops, gh, gw, pad_top,
+    cseg_launch(patchify_kernel<bf16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, img, H, W, windows, n_crops, gh, gw, pad_top,
                                                                     pad_left, ps, (bf16*)out, ldo);
   else
-    patchify_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(img, H, W, windows, n_crops, gh, gw, pad_top,
+    cseg_launch(patchify_kernel<float>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, img, H, W, windows, n_crops, gh, gw, pad_top,
                                                                      pad_left, ps, (float*)out, ldo);
   CSEG_LAUNCH_CHECK("patchify");
   return 0;
@@ -614,7 +624,7 @@ int cseg_embed_tokens(const float* pe, const float* cls, const float* pos, int n
   CSEG_REQUIRE(n_crops > 0 && L > 1 && width > 0, "embed_tokens: bad shape");
   const long long total = (long long)n_crops * L * width;
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
-  embed_tokens_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pe, cls, pos, n_crops, L, width, x);
+  cseg_launch(embed_tokens_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, pe, cls, pos, n_crops, L, width, x);
   CSEG_LAUNCH_CHECK("embed_tokens");
   return 0;
 }
@@ -626,13 +636,13 @@ int cseg_layernorm(const float* x, int rows, int width, const float* gamma, cons
   const bool reg_path = (width % 4 == 0) && width <= 128 * LNV && (((uintptr_t)x | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0;
   if (reg_path) {
     if (out_dtype == CSEG_BF16)
-      layernorm_reg_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, width, gamma, beta, eps, (bf16*)out);
+      cseg_launch(layernorm_reg_kernel<bf16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, rows, width, gamma, beta, eps, (bf16*)out);
     else
-      layernorm_reg_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, width, gamma, beta, eps, (float*)out);
+      cseg_launch(layernorm_reg_kernel<float>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, rows, width, gamma, beta, eps, (float*)out);
   } else if (out_dtype == CSEG_BF16)
-    layernorm_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, width, gamma, beta, eps, (bf16*)out);
+    cseg_launch(layernorm_kernel<bf16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, rows, width, gamma, beta, eps, (bf16*)out);
   else
-    layernorm_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, width, gamma, beta, eps, (float*)out);
+    cseg_launch(layernorm_kernel<float>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, rows, width, gamma, beta, eps, (float*)out);
   CSEG_LAUNCH_CHECK("layernorm");
   return 0;
 }
@@ -646,7 +656,7 @@ static int launch_attention(const void* qkv, int n_crops, int L, int heads, int 
   const size_t smem = (((size_t)3 * L * LDS * sizeof(T) + 15) & ~(size_t)15) + (size_t)ATT_WARPS * ATT_JMAX * 32 * 4;
   CSEG_REQUIRE(smem <= 227 * 1024, "attention: L=%d head_dim=%d needs %zu B shared memory", L, HD, smem);
   CSEG_SET_SMEM((attention_kernel<T, HD>), smem);
-  attention_kernel<T, HD><<<n_crops * heads, ATT_WARPS * 32, smem, st>>>((const T*)qkv, L, heads, mode, simmap, simw,
+  cseg_launch(attention_kernel<T, HD>, dim3(n_crops * heads), dim3(ATT_WARPS * 32), smem, st, (const T*)qkv, L, heads, mode, simmap, simw,
                                                                          (T*)out, stats);
   CSEG_LAUNCH_CHECK("attention");
   return 0;
@@ -683,7 +693,7 @@ int cseg_simmap(const float* x, int n_crops, int L, int width, float temperature
   cudaStream_t st = (cudaStream_t)stream;
   const int P = L - 1;
   dim3 grid(cdiv(P, 32), cdiv(P, 32), n_crops);
-  simmap_kernel<<<grid, 256, 0, st>>>(x, L, width, 1.0f / temperature, add_self_similarity, simmap);
+  cseg_launch(simmap_kernel, dim3(grid), dim3(256), 0, st, x, L, width, 1.0f / temperature, add_self_similarity, simmap);
   CSEG_LAUNCH_CHECK("simmap");
   return 0;
 }
@@ -696,9 +706,9 @@ int cseg_outlier_suppress(const float* y, float* y_out, int n_crops, int L, int 
   CSEG_REQUIRE(y != y_out, "outlier_suppress: runs out of place (y_out must differ from y)");
   const size_t smem = (size_t)(L - 1) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  outlier_plan_kernel<<<n_crops, OS_THREADS, smem, st>>>(y, L, width, grid, stats, heads, top_k, plan, outlier_idx);
+  cseg_launch(outlier_plan_kernel, dim3(n_crops), dim3(OS_THREADS), smem, st, y, L, width, grid, stats, heads, top_k, plan, outlier_idx);
   CSEG_LAUNCH_CHECK("outlier_plan");
-  outlier_apply_kernel<<<n_crops * L, 128, 0, st>>>(y, y_out, L, width, top_k, contamination_temp, plan);
+  cseg_launch(outlier_apply_kernel, dim3(n_crops * L), dim3(128), 0, st, y, y_out, L, width, top_k, contamination_temp, plan);
   CSEG_LAUNCH_CHECK("outlier_apply");
   return 0;
 }
@@ -710,10 +720,10 @@ int cseg_cls_debias(const float* tok, int n_crops, int L, int D, float factor, i
   CSEG_REQUIRE(rows >= L - 1, "cls_debias: rows_per_crop=%d < %d patch tokens", rows, L - 1);
   const int blocks = cdiv((long long)n_crops * (rows + 1) * 32, 256);
   if (out_dtype == CSEG_BF16)
-    cls_debias_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>(tok, n_crops, L, D, factor, (bf16*)feats, ldf,
+    cseg_launch(cls_debias_kernel<bf16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, tok, n_crops, L, D, factor, (bf16*)feats, ldf,
                                                                       rows, cls_unit);
   else
-    cls_debias_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(tok, n_crops, L, D, factor, (float*)feats, ldf,
+    cseg_launch(cls_debias_kernel<float>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, tok, n_crops, L, D, factor, (float*)feats, ldf,
                                                                        rows, cls_unit);
   CSEG_LAUNCH_CHECK("cls_debias");
   return 0;

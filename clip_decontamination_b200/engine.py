@@ -334,7 +334,7 @@ class JBUEngine:
             consts = torch.cat([text @ b, (b @ b).reshape(1)]).contiguous()
             st = dict(Cb=Cb, Tp=Tp, ldg=ldg, eye=eye.reshape(n * P, Cb), tb=tb.to(self.cdt).contiguous(), consts=consts,
                       g=torch.zeros(n * Tp, C, device=dev, dtype=self.cdt),
-                      gram=torch.zeros(_round_up(P, 16), ldg, device=dev, dtype=self.cdt),
+                      gram=torch.zeros(n * Tp, ldg, device=dev, dtype=self.cdt),
                       aux=torch.zeros(16, ldg, device=dev, dtype=self.cdt))
             if not hasattr(self, '_basis'):
                 self._basis = {}
@@ -353,9 +353,7 @@ class JBUEngine:
         assert feats.shape[0] == n * Tp
         # token features after the final 1x1 conv (without its bias): g = x + 0.1 * x . W^T
         ops.gemm(feats, self.w_fin, g, residual=feats, alpha=0.1)
-        for c in range(n):                                          # P x P Gram matrix of every crop
-            gc = g[c * Tp:c * Tp + P]
-            ops.gemm(gc, gc, gram[:P, c * Tp:c * Tp + P])
+        ops.gemm(g, g, gram[:, :n * Tp])          # Gram matrix; one launch, the diagonal blocks are what is used
         ops.gemm(st['tb'], g, aux[:, :n * Tp])                      # <g, text[q]> and <g, b>
         s = self.upsample(st['eye'], gh, gw, img, windows, crop_h, crop_w, pad_top, pad_left, None, final_conv=False)
         return ops.basis_logits(s, st['Cb'], n, crop_h * crop_w, P, Tp, gram, aux, st['consts'], Q, logits, cls_bias)

@@ -166,7 +166,8 @@ CSEG_API int cseg_fixup_norm_sim(int dtype, const void* y, int ldy, const void* 
  * s[p, k] with  out[p] = sum_k s[p, k] g[crop, k] + b,  g = tokens after the final 1x1 conv, and
  *   |out|^2 = s^T (g g^T) s + 2 s.(g b) + b.b        <out, text[q]> = s.(g text[q]) + b.text[q].
  * s    bf16 [n_crops*hw, lds], Cb valid columns (>= 16*ceil(T/16); columns >= T are zero), hw % 128 == 0
- * gram bf16 [16*ceil(T/16), ldg]: gram[j, crop*tstride + k] = <g[crop, j], g[crop, k]>, rows >= T zero
+ * gram bf16 [n_crops*tstride, ldg]: gram[crop*tstride + j, crop*tstride + k] = <g[crop, j], g[crop, k]> (only the
+ *      diagonal blocks are read; entries that pair a token with padding or with another crop may hold anything finite)
  * aux  bf16 [16, ldg]: aux[q, crop*tstride + k] = <g[crop, k], text[q]> (q < Q), row Q = <g[crop, k], b>
  * consts fp32 [Q+1]: <b, text[q]>, then <b, b>.    T <= 240 tokens per crop, Q <= 15, tstride % 8 == 0
  * (TMA box origins must be 16-byte aligned).

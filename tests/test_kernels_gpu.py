@@ -404,11 +404,11 @@ def test_basis_logits(ops, T, Cb, Q, n, hw):
     ref = (F.normalize(feat, dim=-1) @ text.t()).permute(0, 2, 1) + cb[:, :, None]
     Tp = (T + 7) // 8 * 8                       # per-crop column blocks start on 16-byte boundaries (TMA)
     ldg = (n * Tp + 15) // 8 * 8
-    gram = torch.zeros((T + 15) // 16 * 16, ldg)
+    gram = torch.randn(n * Tp, ldg, generator=_g(7))        # off-diagonal blocks / padding: finite garbage
     aux = torch.zeros(16, ldg)
     for c in range(n):
         gf = g[c].float()
-        gram[:T, c * Tp:c * Tp + T] = gf @ gf.t()
+        gram[c * Tp:c * Tp + T, c * Tp:c * Tp + T] = gf @ gf.t()
         aux[:Q, c * Tp:c * Tp + T] = text @ gf.t()
         aux[Q, c * Tp:c * Tp + T] = gf @ b
     consts = torch.cat([text @ b, (b @ b).reshape(1)])
