@@ -200,34 +200,33 @@ def main():
     K = model.num_classes
     T = args.tiles
     # synthetic tiles (different per rank / tile) + synthetic ground truth for the histogram
-    host_imgs = [torch.from_numpy(synth.voronoi_scene(H, W, 1000 + rank * 64 + t)).pin_memory() for t in range(T)]
-    host_gt = [torch.from_numpy(synth.synthetic_labels(H, W, K, 2000 + rank * 64 + t)) for t in range(T)]
-    dev_imgs = [x.to(device) for x in host_imgs]
-    dev_gt = [x.to(device) for x in host_gt]
+    host_imgs = torch.stack([torch.from_numpy(synth.voronoi_scene(H, W, 1000 + rank * 64 + t)) for t in range(T)]).pin_memory()
+    host_gt = torch.stack([torch.from_numpy(synth.synthetic_labels(H, W, K, 2000 + rank * 64 + t)) for t in range(T)])
+    dev_imgs = host_imgs.to(device)                     # [T,H,W,3] uint8 BGR
+    dev_gt = host_gt.to(device)
     hist = torch.zeros((3, K), dtype=torch.int64, device=device)
-    labels = [torch.empty((H, W), dtype=torch.uint8, device=device) for _ in range(T)]
-    host_labels = [torch.empty((H, W), dtype=torch.uint8).pin_memory() for _ in range(T)]
+    labels = torch.empty((T, H, W), dtype=torch.uint8, device=device)
+    host_labels = torch.empty((T, H, W), dtype=torch.uint8).pin_memory()
     mean, std = synth.MEAN.tolist(), synth.STD.tolist()
-    img_f32 = torch.empty((3, H, W), dtype=torch.float32, device=device)
+    img_f32 = torch.empty((3, T * H, W), dtype=torch.float32, device=device)
 
+    # One step = one pass of the hot path over one batch of T tiles: the T images go through every kernel together
+    # (T x 16 crops per launch), as the reference's slide_inference does with a batched input.
     def step_eager():          # un-graphed launch sequence (used for the instrumented breakdown)
-        for t in range(T):
-            ops.preprocess_u8(dev_imgs[t], mean, std, img_f32)
-            eng.segment(img_f32, None, labels=labels[t])
-            ops.iou_hist(labels[t].view(-1), dev_gt[t].view(-1), K, hist)
+        ops.preprocess_u8(dev_imgs.view(T * H, W, 3), mean, std, img_f32)
+        eng.segment(img_f32, None, labels=labels.view(T * H, W), batch=T)
+        ops.iou_hist(labels.view(-1), dev_gt.view(-1), K, hist)
         allreduce_hist(hist)
 
-    def step_resident():       # the product path: CUDA-graph replay per tile, inputs resident in HBM
-        for t in range(T):
-            lab = eng.segment_u8(dev_imgs[t])
-            ops.iou_hist(lab.view(-1), dev_gt[t].view(-1), K, hist)
+    def step_resident():       # the product path: CUDA-graph replay, inputs resident in HBM
+        lab = eng.segment_u8(dev_imgs)
+        ops.iou_hist(lab.view(-1), dev_gt.view(-1), K, hist)
         allreduce_hist(hist)
 
     def step_e2e():
-        for t in range(T):
-            lab = model.predict_u8(host_imgs[t])                              # H2D inside
-            ops.iou_hist(lab.view(-1), dev_gt[t].view(-1), K, hist)
-            host_labels[t].copy_(lab, non_blocking=True)                      # D2H of the step's result
+        lab = model.predict_u8(host_imgs)                                     # H2D inside
+        ops.iou_hist(lab.view(-1), dev_gt.view(-1), K, hist)
+        host_labels.copy_(lab, non_blocking=True)                             # D2H of the step's result
         allreduce_hist(hist)
         torch.cuda.current_stream().synchronize()
 

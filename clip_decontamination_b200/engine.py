@@ -389,21 +389,27 @@ class SegEngine:
         self.mean = [122.771, 116.746, 104.094]          # segmentor.py:64-67 (RGB)
         self.std = [68.501, 66.632, 70.323]
 
-    def _windows(self, H: int, W: int):
-        key = (H, W)
+    def _windows(self, H: int, W: int, B: int = 1):
+        """Windows of B equally sized images stacked vertically into one [3, B*H, W] canvas: the batch dimension of
+        slide_inference (segmentor.py:413-449 crops all B images per window) becomes B times as many crops, and no
+        window straddles two images."""
+        key = (H, W, B)
         if key not in self._win_cache:
             if self.crop > 0:
                 wl = slide_windows(H, W, self.stride, self.crop)
             else:                                                   # whole-image path, segmentor.py:470-471
                 wl = [(0, 0, H, W)]
+            wl = [(y1 + b * H, x1, h, w) for b in range(B) for (y1, x1, h, w) in wl]
             self._win_cache[key] = (torch.tensor(wl, dtype=torch.int32, device=self.device), wl)
         return self._win_cache[key]
 
-    def crop_logits(self, img: torch.Tensor, taps: Optional[dict] = None):
+    def crop_logits(self, img: torch.Tensor, taps: Optional[dict] = None, batch: int = 1):
         """Per-crop cosine logits (forward_feature, segmentor.py:286-392) for every window of `img`
-        (fp32 [3,H,W] normalised, on the device).  Returns (logits fp32 [n,Q,lh,lw], geometry)."""
+        (fp32 [3,H,W] normalised, on the device; with batch = B > 1, B images stacked to [3, B*H, W]).
+        Returns (logits fp32 [n,Q,lh,lw], geometry)."""
         _, H, W = img.shape
-        win_dev, wl = self._windows(H, W)
+        assert H % batch == 0
+        win_dev, wl = self._windows(H // batch, W, batch)
         n = len(wl)
         wh, ww = wl[0][2], wl[0][3]
         ps = self.v.ps
@@ -454,9 +460,12 @@ class SegEngine:
         return logits, geom
 
     def segment(self, img: torch.Tensor, ori_shape: Optional[Tuple[int, int]] = None, *, labels=None,
-                want_probs: bool = False, want_logits: bool = False, taps: Optional[dict] = None):
-        """predict() for one image: labels uint8 [out_h,out_w] (+ probs [K,..] / averaged logits [Q,H,W])."""
-        logits, g = self.crop_logits(img, taps)
+                want_probs: bool = False, want_logits: bool = False, taps: Optional[dict] = None, batch: int = 1):
+        """predict() for one image: labels uint8 [out_h,out_w] (+ probs [K,..] / averaged logits [Q,H,W]).
+        batch = B > 1: `img` holds B images stacked vertically ([3, B*H, W]) and so do the outputs; every crop-level
+        kernel then works on B times as many crops per launch (ori_shape must be None)."""
+        assert batch == 1 or ori_shape is None
+        logits, g = self.crop_logits(img, taps, batch)
         H, W = g['H'], g['W']
         out_h, out_w = (H, W) if ori_shape is None else (int(ori_shape[0]), int(ori_shape[1]))
         if labels is None:
@@ -470,20 +479,20 @@ class SegEngine:
         return labels, probs, avg
 
     # ---- CUDA-graph replay of the whole per-image launch sequence --------------------------------
-    def graph(self, H: int, W: int) -> dict:
-        """Capture preprocess_u8 -> segment for an H x W uint8 image once (a few hundred launches) and
+    def graph(self, H: int, W: int, B: int = 1) -> dict:
+        """Capture preprocess_u8 -> segment for B uint8 images of H x W once (a few hundred launches) and
         replay it afterwards: the per-launch host cost (Python, ctypes, tensor-map encodes) is paid at
-        capture time only.  Static buffers: 'u8' [H,W,3] uint8 BGR in, 'labels' [H,W] uint8 out."""
-        key = (H, W)
+        capture time only.  Static buffers: 'u8' [B,H,W,3] uint8 BGR in, 'labels' [B,H,W] uint8 out."""
+        key = (H, W, B)
         if key in self._graphs:
             return self._graphs[key]
-        st = dict(u8=torch.zeros((H, W, 3), dtype=torch.uint8, device=self.device),
-                  img=torch.empty((3, H, W), dtype=torch.float32, device=self.device),
-                  labels=torch.empty((H, W), dtype=torch.uint8, device=self.device))
+        st = dict(u8=torch.zeros((B, H, W, 3), dtype=torch.uint8, device=self.device),
+                  img=torch.empty((3, B * H, W), dtype=torch.float32, device=self.device),
+                  labels=torch.empty((B, H, W), dtype=torch.uint8, device=self.device))
 
         def run():
-            ops.preprocess_u8(st['u8'], self.mean, self.std, st['img'])
-            self.segment(st['img'], None, labels=st['labels'])
+            ops.preprocess_u8(st['u8'].view(B * H, W, 3), self.mean, self.std, st['img'])
+            self.segment(st['img'], None, labels=st['labels'].view(B * H, W), batch=B)
 
         cur = torch.cuda.current_stream(self.device)
         side = torch.cuda.Stream(self.device)
@@ -502,16 +511,23 @@ class SegEngine:
 
     def segment_u8(self, img_hwc_bgr_u8: torch.Tensor, labels_out: Optional[torch.Tensor] = None,
                    use_graph: bool = True) -> torch.Tensor:
-        """uint8 HWC BGR image (host pinned or device) -> uint8 labels [H,W] on the device."""
-        H, W, _ = img_hwc_bgr_u8.shape
+        """uint8 HWC BGR image [H,W,3] -> uint8 labels [H,W] on the device, or a batch [B,H,W,3] -> [B,H,W]
+        (host pinned or device input).  A batch runs as ONE launch sequence over B times as many crops."""
+        batched = img_hwc_bgr_u8.dim() == 4
+        B = img_hwc_bgr_u8.shape[0] if batched else 1
+        H, W = img_hwc_bgr_u8.shape[-3], img_hwc_bgr_u8.shape[-2]
         if not use_graph:
-            x = img_hwc_bgr_u8.to(self.device, non_blocking=True)
-            img = ops.preprocess_u8(x.contiguous(), self.mean, self.std)
-            return self.segment(img, None, labels=labels_out)[0]
-        st = self.graph(H, W)
-        st['u8'].copy_(img_hwc_bgr_u8, non_blocking=True)        # H2D (or D2D) into the static input
-        st['graph'].replay()
-        if labels_out is not None:
-            labels_out.copy_(st['labels'], non_blocking=True)
+            x = img_hwc_bgr_u8.to(self.device, non_blocking=True).contiguous()
+            img = ops.preprocess_u8(x.view(B * H, W, 3), self.mean, self.std)
+            if labels_out is None:
+                labels_out = torch.empty((B, H, W) if batched else (H, W), dtype=torch.uint8, device=self.device)
+            self.segment(img, None, labels=labels_out.view(B * H, W), batch=B)
             return labels_out
-        return st['labels']
+        st = self.graph(H, W, B)
+        st['u8'].copy_(img_hwc_bgr_u8.view(B, H, W, 3), non_blocking=True)   # H2D (or D2D) into the static input
+        st['graph'].replay()
+        out = st['labels'] if batched else st['labels'][0]
+        if labels_out is not None:
+            labels_out.copy_(out, non_blocking=True)
+            return labels_out
+        return out

@@ -229,6 +229,24 @@ def test_seg_potsdam_jbu_basis_vs_literal(gold):
     assert torch.isfinite(lb).all() and d < 5e-3
 
 
+@pytest.mark.parametrize('upsampler', [None, 'jbu_one'])
+def test_batched_equals_per_image(gold, upsampler):
+    """A batch [B,H,W,3] goes through every kernel as B x 16 crops (stacked canvas); crop-level work is independent,
+    so the labels equal those of B single-image calls (slide_inference with a batched input, segmentor.py:413-449)."""
+    g = gold('seg_potsdam_jbu')
+    seg = _seg_engine('ViT-B-16', 'potsdam', 'bf16', g, upsampler=upsampler)
+    B, H, W = 3, 512, 512
+    u8 = torch.stack([torch.from_numpy(synth.voronoi_scene(H, W, 70 + b)) for b in range(B)]).cuda()
+    single = torch.stack([seg.segment_u8(u8[b], use_graph=False).clone() for b in range(B)])
+    batched = seg.segment_u8(u8, use_graph=False)
+    graphed = seg.segment_u8(u8, use_graph=True).clone()
+    torch.cuda.synchronize()
+    same = (single == batched).float().mean().item()
+    print(f'[batched vs single, up={upsampler}] label agreement {same * 100:.4f}%')
+    assert same >= 0.9999
+    assert torch.equal(batched, graphed)
+
+
 @pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('bf16', 1e-2)])
 def test_seg_loveda_vitl(gold, precision, tol):
     """BASELINE config 3 shape: ViT-L/14 (L=257, 24 layers), no upsampler, 448x448 (9 crops), Q=9 -> K=7."""
