@@ -291,7 +291,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             if (ACT == CSEG_ACT_GELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+              for (int j = 0; j < 32; ++j) v[j] = OUTB ? gelu_tanh(v[j]) : gelu_fast(v[j]);
             } else if (ACT == CSEG_ACT_QUICKGELU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
@@ -349,7 +349,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const float alpha = ep.alpha;
           auto finish = [&](int rr) -> float {
             float x = stg[rr * SST + lane] + bv;
-            if (ACT == CSEG_ACT_GELU) x = gelu_fast(x);
+            if (ACT == CSEG_ACT_GELU) x = OUTB ? gelu_tanh(x) : gelu_fast(x);
             else if (ACT == CSEG_ACT_QUICKGELU) x = quick_gelu(x);
             return RES != 0 ? fmaf(x, alpha, res[rr]) : x * alpha;
           };

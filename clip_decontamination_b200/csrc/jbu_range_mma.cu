@@ -7,9 +7,10 @@
 // GEMM: S[16 queries, 8-position blocks] = Q[16, 32] . K[positions, 32]^T  -> mma.sync m16n8k16 with fp16
 // operands (the reference computes these projections in fp16 under autocast, segmentor.py:370) and fp32
 // accumulation.  Only the band 0 <= pos - query < D of each block is used.  The MMAs are so cheap that the
-// softmax is done in three passes over recomputed logits (max; sums; normalised write) instead of keeping
-// D*D values per pixel in registers.  Results are staged per warp in shared memory and written as full
-// 16-byte-vector rows of the [pixels, ldk] kernel matrix (taps, then the 3 guidance channels, then zeros).
+// softmax takes two passes over recomputed logits instead of keeping D*D values per pixel in registers:
+// (0) row maxima, (1) exp, both sums, and exp * gauss staged per warp in shared memory as fp16 (values <= 1).
+// The normalisation is applied while the staged rows are copied out as full 16-byte vectors of the
+// [pixels, ldk] kernel matrix (taps, then the 3 guidance channels, then zeros).
 #include "common.cuh"
 #include <cuda_fp16.h>
 
@@ -115,11 +116,15 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
       mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
       mx[h] *= pos_temp;                                       // pos_temp > 0: max commutes with the scaling
     }
-    // ---- pass 1: sum exp, sum exp * gauss ----
+    // ---- pass 1: exp, sums, and the unnormalised exp * gauss (fp16, <= 1) into the staging rows ----
+    const float pt2 = pos_temp * 1.4426950408889634f;          // exp(x) = 2^(x log2 e): one FFMA + MUFU.EX2 per tap
+    const float mx2[2] = {mx[0] * 1.4426950408889634f, mx[1] * 1.4426950408889634f};
+    __half* sth = reinterpret_cast<__half*>(st);
 #pragma unroll 1
     for (int i = 0; i < D; ++i) {
       const uint32_t rowb = rowb0 + (uint32_t)(i * NPOS * PROW);
       const float* gi = gauss + i * D;
+      __half* sti = sth + i * D;
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
         uint32_t b[4];
@@ -130,9 +135,13 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
 #pragma unroll
         for (int e = 0; e < 4; ++e)
           if (jj[nb][e] >= 0) {
-            const float ex = __expf(fmaf(S[e], pos_temp, -mx[e >> 1]));
-            se[e >> 1] += ex;
-            sg[e >> 1] = fmaf(ex, gi[jj[nb][e]], sg[e >> 1]);
+            const int h = e >> 1;
+            float ex;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(S[e], pt2, -mx2[h])));
+            const float w = ex * gi[jj[nb][e]];
+            se[h] += ex;
+            sg[h] += w;
+            sti[(g + h * 8) * LDK + jj[nb][e]] = __float2half_rn(w);
           }
       }
     }
@@ -145,44 +154,38 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
       const float ise = 1.0f / se[h];
       inv[h] = ise / fmaxf(sg[h] * ise, 1e-7f);               // softmax, then / sum(softmax*gauss).clamp(1e-7)
     }
-    // ---- pass 2: normalised kernel values into the staging rows ----
-#pragma unroll 1
-    for (int i = 0; i < D; ++i) {
-      const uint32_t rowb = rowb0 + (uint32_t)(i * NPOS * PROW);
-      const float* gi = gauss + i * D;
-      bf16* sti = st + i * D;
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        uint32_t b[4];
-        ldsm4(rowb + nb * 8 * PROW, b);
-        float S[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_f16(S, a[0], b[0], b[1]);
-        mma_f16(S, a[1], b[2], b[3]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (jj[nb][e] >= 0) {
-            const int h = e >> 1;
-            const float ex = __expf(fmaf(S[e], pos_temp, -mx[h]));
-            sti[(g + h * 8) * LDK + jj[nb][e]] = __float2bfloat16_rn(ex * gi[jj[nb][e]] * inv[h]);
-          }
-      }
-    }
-    // guidance channels + zero padding (columns D2 .. LDK-1), then coalesced row stores
-    if (lane < 16) {
-      const int x = min(xq0 + lane, gw - 1);
-      const float4 gv = guid[((size_t)crop * gh + y) * gw + x];
-      bf16* o = st + lane * LDK + D2;
-      o[0] = __float2bfloat16_rn(gv.x);
-      o[1] = __float2bfloat16_rn(gv.y);
-      o[2] = __float2bfloat16_rn(gv.z);
-      for (int t = D2 + 3; t < LDK; ++t) st[lane * LDK + t] = __float2bfloat16_rn(0.f);
-    }
     __syncwarp();
-    for (int e = lane; e < 16 * (LDK / 8); e += 32) {
+    // ---- normalise while copying out: taps * inv[row], then the 3 guidance channels, then zeros; coalesced
+    //      16-byte row stores of the [pixels, ldk] kernel matrix ----
+#pragma unroll
+    for (int e = lane; e < 16 * (LDK / 8); e += 32) {          // uniform trip count: the shuffles stay convergent
       const int px = e / (LDK / 8), v = e % (LDK / 8);
-      if (xq0 + px < gw)
-        *reinterpret_cast<uint4*>(kern + (((size_t)crop * gh + y) * gw + xq0 + px) * ldk + v * 8) =
-            *reinterpret_cast<const uint4*>(st + px * LDK + v * 8);
+      const float i0 = __shfl_sync(0xffffffffu, inv[0], (px & 7) * 4);
+      const float i1 = __shfl_sync(0xffffffffu, inv[1], (px & 7) * 4);
+      const float sc = px < 8 ? i0 : i1;
+      const uint4 raw = *reinterpret_cast<const uint4*>(sth + px * LDK + v * 8);
+      const __half2* hp = reinterpret_cast<const __half2*>(&raw);
+      float f[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 t2 = __half22float2(hp[k]);
+        f[2 * k] = (v * 8 + 2 * k < D2) ? t2.x * sc : 0.f;
+        f[2 * k + 1] = (v * 8 + 2 * k + 1 < D2) ? t2.y * sc : 0.f;
+      }
+      if (v == D2 / 8) {                                       // columns D2 .. D2+2: guidance (RGB) of this pixel
+        const int x = min(xq0 + px, gw - 1);
+        const float4 gv = guid[((size_t)crop * gh + y) * gw + x];
+        f[D2 % 8] = gv.x;
+        f[D2 % 8 + 1] = gv.y;
+        f[D2 % 8 + 2] = gv.z;
+      }
+      if (xq0 + px < gw) {
+        uint4 o;
+        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) op[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+        *reinterpret_cast<uint4*>(kern + (((size_t)crop * gh + y) * gw + xq0 + px) * ldk + v * 8) = o;
+      }
     }
     __syncwarp();
   }
