@@ -6,6 +6,7 @@
 //   [fixup_proj: two 1x1 convs = two cseg_gemm calls with GELU / residual epilogues, :264]
 //   apply     : bicubic x2 + reflect pad + adaptive conv                   (:268-274, :14-25)
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -375,6 +376,16 @@ static int launch_range_kernel(const float* proj, const float* guid, int n_crops
   return 0;
 }
 
+int cseg_jbu_adaptive_conv_tc(const bf16* hr, int n_crops, int H2, int W2, int C, const bf16* kern, int ldk, int radius,
+                              bf16* dst, cudaStream_t st);
+static bool conv_tc_enabled() {      // CSEG_CONV_TC=0 selects the mma.sync kernel (A/B measurements)
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CSEG_CONV_TC");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
 int cseg_jbu_adaptive_conv_mma(const bf16* hr, int n_crops, int H2, int W2, int C, const bf16* kern, int ldk,
                                int radius, bf16* dst, cudaStream_t st);
 
@@ -386,7 +397,12 @@ static int launch_apply(const void* src, int n_crops, int h, int w, int C, const
   cseg_launch(bicubic2x_kernel<T>, dim3((int)std::min<long long>((tot_b + 255) / 256, (long long)sm_count() * 32)), dim3(256), 0, st, 
       (const T*)src, n_crops, h, w, C, (T*)hr_scratch);
   CSEG_LAUNCH_CHECK("jbu_bicubic2x");
-  if (sizeof(T) == 2 && C % 64 == 0 && C >= 128 && ldk % 8 == 0 && ldk <= 128)   // tensor-core banded GEMM path
+  if (sizeof(T) == 2 && conv_tc_enabled()) {                                      // tcgen05 banded GEMM (C % 128 == 0)
+    const int rc = cseg_jbu_adaptive_conv_tc((const bf16*)hr_scratch, n_crops, H2, W2, C, (const bf16*)kern, ldk, radius,
+                                             (bf16*)dst, st);
+    if (rc <= 0) return rc;
+  }
+  if (sizeof(T) == 2 && C % 64 == 0 && C >= 128 && ldk % 8 == 0 && ldk <= 128)   // mma.sync banded GEMM path
     return cseg_jbu_adaptive_conv_mma((const bf16*)hr_scratch, n_crops, H2, W2, C, (const bf16*)kern, ldk, radius,
                                       (bf16*)dst, st);
   const long long tot = (long long)n_crops * H2 * W2 * (C / 8);
