@@ -595,14 +595,14 @@ int launch_normsim(const CUtensorMap& ta, const CUtensorMap& tb, int M, int C, c
 // Same TMA / tcgen05 / TMEM pipeline as above; one M-panel (128 pixels of one crop) per accumulator stage.
 // =====================================================================================================
 struct BlCfg {
-  static constexpr int STAGES = 4, N_MAX = 256, N2 = 16;              // N = Gram columns + N2 aux columns
-  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = N_MAX * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;                 // 48 KB
+  static constexpr int STAGES = 5, N_MAX = 256, N2 = 16, KB_MAX = 4;   // N = Gram columns + N2 aux columns, K <= 256
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = N_MAX * BK * 2; // A ring stage 16 KB; one B k-block 32 KB
+  static constexpr int B_OFF = STAGES * A_BYTES;                        // B of the current crop stays resident
   static constexpr int EPI_WARPS = 16, THREADS = 64 + 32 * EPI_WARPS;
-  static constexpr int PART_OFF = STAGES * STAGE_BYTES;                 // part [2][4 column groups][128 rows]
+  static constexpr int PART_OFF = B_OFF + KB_MAX * B_BYTES;             // part [2][4 column groups][128 rows]
   static constexpr int PART_BYTES = 2 * 4 * 128 * 4;
   static constexpr int BAR_OFF = PART_OFF + PART_BYTES;
-  static constexpr int NBARS = 2 * STAGES + 4;
+  static constexpr int NBARS = 2 * STAGES + 6;
   static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
 };
 
@@ -620,8 +620,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 // KS = ceil(T / 16) K-steps (and Gram column groups of 16); panels never straddle crops (hw % 128 == 0).
 // gram is the full (n_crops*tstride)^2 product g g^T; the tile of a crop is its diagonal block (rows and columns
 // crop*tstride ..; rows / columns past the crop's T tokens meet zero coefficients and never contribute).
-// The B tile of a stage is the Gram rows followed by the 16 aux rows (two TMA loads into adjacent 8-row groups
+// The B tile of a k-block is the Gram rows followed by the 16 aux rows (two TMA loads into adjacent 8-row groups
 // of the SWIZZLE_128B layout), so one MMA of N = 16 KS + 16 <= 256 produces both; two accumulator stages.
+// Every CTA takes a contiguous range of panels; the B tile of the current crop (all k-blocks, <= 128 KB) stays
+// resident in shared memory and only the coefficient panels stream through the TMA ring.
 __global__ void __launch_bounds__(BlCfg::THREADS, 1)
 basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
                     const __grid_constant__ CUtensorMap tmB2, int panels, int hw, int tstride, int KS,
@@ -638,9 +640,13 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + STAGES * 8;
   const uint32_t tfull0 = empty0 + STAGES * 8, tempty0 = tfull0 + ACC * 8;
+  const uint32_t bfull = tempty0 + ACC * 8, bfree = bfull + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N1 = KS * 16, num_kb = (KS + 3) / 4;
   const int panels_per_crop = hw / BM;
+  // contiguous panel range per CTA: consecutive panels share the crop, whose Gram / aux tile stays in shared memory
+  const int ppc = (panels + gridDim.x - 1) / gridDim.x;
+  const int p_begin = blockIdx.x * ppc, p_end = min(panels, p_begin + ppc);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -654,6 +660,8 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(tfull0 + i * 8, 1);
       mbar_init(tempty0 + i * 8, Cf::EPI_WARPS);
     }
+    mbar_init(bfull, 1);
+    mbar_init(bfree, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -669,27 +677,43 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t b1_bytes = (uint32_t)(N1 * BK * 2);
-      const uint32_t stage_tx = (uint32_t)Cf::A_BYTES + b1_bytes + (uint32_t)(Cf::N2 * BK * 2);
-      uint32_t it = 0;
-      for (int panel = blockIdx.x; panel < panels; panel += gridDim.x) {
-        const int kcrop = (panel / panels_per_crop) * tstride;
+      const uint32_t b_tx = (uint32_t)num_kb * (b1_bytes + (uint32_t)(Cf::N2 * BK * 2));
+      uint32_t it = 0, nb = 0, np = 0;
+      int cur_crop = -1;
+      for (int panel = p_begin; panel < p_end; ++panel, ++np) {
+        const int crop = panel / panels_per_crop;
+        if (crop != cur_crop) {                       // new crop: reload the resident B once the MMAs that read the old one are done
+          if (np > 0) mbar_wait(bfree, (np - 1) & 1);
+          mbar_expect_tx(bfull, b_tx);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            const uint32_t b_dst = smem_base + Cf::B_OFF + kb * Cf::B_BYTES;
+            tma_load_2d(b_dst, &tmB1, bfull, crop * tstride + kb * BK, crop * tstride);
+            tma_load_2d(b_dst + b1_bytes, &tmB2, bfull, crop * tstride + kb * BK, 0);
+          }
+          cur_crop = crop;
+          ++nb;
+        }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(empty0 + st * 8, ph ^ 1);
-          mbar_expect_tx(full0 + st * 8, stage_tx);
-          const uint32_t a_dst = smem_base + st * Cf::STAGE_BYTES;
-          tma_load_2d(a_dst, &tmA, full0 + st * 8, kb * BK, panel * BM);
-          tma_load_2d(a_dst + Cf::A_BYTES, &tmB1, full0 + st * 8, kcrop + kb * BK, kcrop);
-          tma_load_2d(a_dst + Cf::A_BYTES + b1_bytes, &tmB2, full0 + st * 8, kcrop + kb * BK, 0);
+          mbar_expect_tx(full0 + st * 8, Cf::A_BYTES);
+          tma_load_2d(smem_base + st * Cf::A_BYTES, &tmA, full0 + st * 8, kb * BK, panel * BM);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BM, N1 + Cf::N2);
-      uint32_t it = 0, tl = 0;
-      for (int panel = blockIdx.x; panel < panels; panel += gridDim.x, ++tl) {
+      uint32_t it = 0, tl = 0, nb = 0;
+      int cur_crop = -1;
+      for (int panel = p_begin; panel < p_end; ++panel, ++tl) {
         const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
+        const int crop = panel / panels_per_crop;
+        if (crop != cur_crop) {
+          mbar_wait(bfull, nb & 1);
+          cur_crop = crop;
+          ++nb;
+        }
         mbar_wait(tempty0 + as * 8, aph ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * 256;
@@ -697,21 +721,21 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(full0 + st * 8, ph);
           tc_fence_after();
-          const uint32_t a_src = smem_base + st * Cf::STAGE_BYTES;
-          const uint64_t adesc = make_sdesc(a_src);
-          const uint64_t bdesc = make_sdesc(a_src + Cf::A_BYTES);
+          const uint64_t adesc = make_sdesc(smem_base + st * Cf::A_BYTES);
+          const uint64_t bdesc = make_sdesc(smem_base + Cf::B_OFF + kb * Cf::B_BYTES);
           const int ksteps = min(4, KS - kb * 4);
           for (int k = 0; k < ksteps; ++k)
             umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(empty0 + st * 8);
         }
         umma_commit(tfull0 + as * 8);
+        umma_commit(bfree);                            // one phase per panel: everything up to this panel has read B
       }
     }
   } else {
     const int ew = warp - 2, lg = warp & 3, cg = ew >> 2;
     uint32_t tl = 0;
-    for (int panel = blockIdx.x; panel < panels; panel += gridDim.x, ++tl) {
+    for (int panel = p_begin; panel < p_end; ++panel, ++tl) {
       const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
       const size_t row = (size_t)panel * BM + lg * 32 + lane;
       // this lane's coefficients of the Gram column groups cg, cg+4, ... (32 B each), fetched before the

@@ -28,7 +28,8 @@ namespace {
 
 constexpr int CV_RW = 4, CV_TX = 16, CV_NPX = CV_RW * CV_TX;   // 64 pixels per tile = N of the MMA
 constexpr int CV_NPOS = 32;                                    // source positions per strip (K per source row)
-constexpr int CV_NSTG = 4;                                     // A ring stages
+constexpr int CV_NSTG = 6;                                     // A ring stages
+constexpr int CV_INFL = 4;                                     // source strips in flight per loader thread
 constexpr int CV_EPI_WARPS = 4, CV_LD_WARPS = 4, CV_BB_WARPS = 4;
 constexpr int CV_THREADS = 32 * (CV_EPI_WARPS + 1 + CV_LD_WARPS + CV_BB_WARPS);
 constexpr int CV_LD_T0 = 32 * (CV_EPI_WARPS + 1), CV_BB_T0 = CV_LD_T0 + 32 * CV_LD_WARPS;
@@ -193,8 +194,7 @@ adaptive_conv_tc_kernel(const bf16* __restrict__ hr, int H2, int W2, int C, cons
     const int lt = tid - CV_LD_T0;                               // 0..127
     constexpr int CPR = Cf::CH / 8;                              // 16-byte chunks per position
     constexpr int LPT = CV_NPOS * CPR / (32 * CV_LD_WARPS);      // chunks per thread per strip (4 / 8)
-    uint32_t it = 0;
-    int pending = -1;                                            // stage whose copies are in flight
+    uint32_t it = 0;                                             // strips issued so far; strip j lives in stage j % NSTG
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int x0, y0, crop, c0;
       tile_coords(tile, x0, y0, crop, c0);
@@ -219,19 +219,17 @@ adaptive_conv_tc_kernel(const bf16* __restrict__ hr, int H2, int W2, int C, cons
         for (int k = 0; k < LPT; ++k)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + dst_off[k]), "l"(rowp + src_off[k]) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
-        if (pending >= 0) {                                      // the previous strip has landed: publish it
-          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (it >= CV_INFL - 1) {                                 // strip it-(INFL-1) has landed: publish it
+          asm volatile("cp.async.wait_group %0;" ::"n"(CV_INFL - 1) : "memory");
           fence_proxy_async();
-          mbar_arrive(a_full0 + pending * 8);
+          mbar_arrive(a_full0 + ((it - (CV_INFL - 1)) % CV_NSTG) * 8);
         }
-        pending = (int)st;
       }
     }
-    if (pending >= 0) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      fence_proxy_async();
-      mbar_arrive(a_full0 + pending * 8);
-    }
+    // drain: the last INFL-1 strips, oldest first
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    fence_proxy_async();
+    for (uint32_t j = (it >= CV_INFL - 1 ? it - (CV_INFL - 1) : 0); j < it; ++j) mbar_arrive(a_full0 + (j % CV_NSTG) * 8);
   } else {
     // ---------------- B builders: banded weight tiles ----------------
     const int bt = tid - CV_BB_T0;                               // 0..127

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) range_proj_f16_kernel(const float4* __res
                                                              const float* __restrict__ w3, const float* __restrict__ b3,
                                                              __half* __restrict__ proj) {
   pdl_grid_sync();
-  __shared__ float sw0[KD * 3], sb0[KD], sw3[KD * KD], sb3[KD];
+  __shared__ __align__(16) float sw0[KD * 3], sb0[KD], sw3[KD * KD], sb3[KD];
   for (int i = threadIdx.x; i < KD * 3; i += blockDim.x) sw0[i] = w0[i];
   for (int i = threadIdx.x; i < KD * KD; i += blockDim.x) sw3[i] = w3[i];
   for (int i = threadIdx.x; i < KD; i += blockDim.x) { sb0[i] = b0[i]; sb3[i] = b3[i]; }
@@ -215,8 +215,15 @@ __global__ void __launch_bounds__(256) range_proj_f16_kernel(const float4* __res
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float a = sb3[k8 * 8 + e];
+      const float4* wr = reinterpret_cast<const float4*>(sw3 + (k8 * 8 + e) * KD);   // broadcast LDS.128: 4 weights per load
 #pragma unroll
-      for (int j = 0; j < KD; ++j) a = fmaf(sw3[(k8 * 8 + e) * KD + j], h[j], a);
+      for (int j4 = 0; j4 < KD / 4; ++j4) {
+        const float4 w = wr[j4];
+        a = fmaf(w.x, h[4 * j4], a);
+        a = fmaf(w.y, h[4 * j4 + 1], a);
+        a = fmaf(w.z, h[4 * j4 + 2], a);
+        a = fmaf(w.w, h[4 * j4 + 3], a);
+      }
       acc[e] = a;
     }
     uint4 u;
