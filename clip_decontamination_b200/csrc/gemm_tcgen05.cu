@@ -640,7 +640,7 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + STAGES * 8;
   const uint32_t tfull0 = empty0 + STAGES * 8, tempty0 = tfull0 + ACC * 8;
-  const uint32_t bfull = tempty0 + ACC * 8, bfree = bfull + 8;
+  const uint32_t bfull = tempty0 + ACC * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N1 = KS * 16, num_kb = (KS + 3) / 4;
   const int panels_per_crop = hw / BM;
@@ -661,7 +661,6 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(tempty0 + i * 8, Cf::EPI_WARPS);
     }
     mbar_init(bfull, 1);
-    mbar_init(bfree, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -678,12 +677,14 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       const uint32_t b1_bytes = (uint32_t)(N1 * BK * 2);
       const uint32_t b_tx = (uint32_t)num_kb * (b1_bytes + (uint32_t)(Cf::N2 * BK * 2));
-      uint32_t it = 0, nb = 0, np = 0;
+      uint32_t it = 0;
       int cur_crop = -1;
-      for (int panel = p_begin; panel < p_end; ++panel, ++np) {
+      for (int panel = p_begin; panel < p_end; ++panel) {
         const int crop = panel / panels_per_crop;
         if (crop != cur_crop) {                       // new crop: reload the resident B once the MMAs that read the old one are done
-          if (np > 0) mbar_wait(bfree, (np - 1) & 1);
+          // the commit that frees the most recently filled A stage covers every MMA issued before it; the producer
+          // has observed all earlier phases of that barrier, so the parity wait cannot alias
+          if (it > 0) mbar_wait(empty0 + ((it - 1) % STAGES) * 8, ((it - 1) / STAGES) & 1);
           mbar_expect_tx(bfull, b_tx);
           for (int kb = 0; kb < num_kb; ++kb) {
             const uint32_t b_dst = smem_base + Cf::B_OFF + kb * Cf::B_BYTES;
@@ -691,7 +692,6 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_2d(b_dst + b1_bytes, &tmB2, bfull, crop * tstride + kb * BK, 0);
           }
           cur_crop = crop;
-          ++nb;
         }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
@@ -729,7 +729,6 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           umma_commit(empty0 + st * 8);
         }
         umma_commit(tfull0 + as * 8);
-        umma_commit(bfree);                            // one phase per panel: everything up to this panel has read B
       }
     }
   } else {
