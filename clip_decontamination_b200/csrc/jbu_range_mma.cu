@@ -19,6 +19,7 @@ namespace {
 constexpr int TXR = 32, TYR = 8;   // CTA tile: 32 x 8 query pixels, one warp per row
 constexpr int KD = 32;             // projection width
 constexpr int PROW = KD * 2 + 16;  // bytes per staged position (padded: conflict-free ldmatrix)
+constexpr int SPAD = 8;            // staging row padding (halves): rows 4 banks apart, 16-byte aligned
 
 __device__ __forceinline__ int reflect1(int i, int n) {
   if (i < 0) i = -i;
@@ -63,15 +64,17 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int t = tid; t < D2; t += TYR * 32) {                 // get_spatial_kernel: linspace(-1, 1, D)^2
-    const float dy = -1.f + 2.f * (t / D) / (D - 1), dx = -1.f + 2.f * (t % D) / (D - 1);
-    gauss[t] = __expf(-(dy * dy + dx * dx) * inv2s2);
+  // get_spatial_kernel: exp(-(dy^2 + dx^2) / 2 sigma^2) on linspace(-1, 1, D)^2 is separable: gauss[i] holds the
+  // 1-D factor; the column factors of a thread's fragment elements live in registers
+  for (int t = tid; t < D; t += TYR * 32) {
+    const float d1 = -1.f + 2.f * t / (D - 1);
+    gauss[t] = __expf(-(d1 * d1) * inv2s2);
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   const int y = y0 + warp;
-  bf16* st = stage + warp * 16 * LDK;
+  bf16* st = stage + warp * 16 * (LDK + SPAD);
   const int q = lane >> 3, rr = lane & 7;
 #pragma unroll 1
   for (int xb = 0; xb < TXR / 16; ++xb) {
@@ -93,6 +96,11 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
         const int j = nb * 8 + 2 * tig + (e & 1) - (g + (e >> 1) * 8);
         jj[nb][e] = (j >= 0 && j < D) ? j : -1;
       }
+    float gx[NB][4];                                           // column factor of the spatial Gaussian per element
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) gx[nb][e] = jj[nb][e] >= 0 ? gauss[jj[nb][e]] : 0.f;
     const uint32_t rowb0 = psm + (uint32_t)((warp * NPOS + xb * 16 + rr) * PROW + q * 16);
     // ---- pass 0: row maxima ----
 #pragma unroll 1
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
 #pragma unroll 1
     for (int i = 0; i < D; ++i) {
       const uint32_t rowb = rowb0 + (uint32_t)(i * NPOS * PROW);
-      const float* gi = gauss + i * D;
+      const float gy = gauss[i];
       __half* sti = sth + i * D;
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
@@ -138,10 +146,10 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
             const int h = e >> 1;
             float ex;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(S[e], pt2, -mx2[h])));
-            const float w = ex * gi[jj[nb][e]];
+            const float w = ex * (gy * gx[nb][e]);
             se[h] += ex;
             sg[h] += w;
-            sti[(g + h * 8) * LDK + jj[nb][e]] = __float2half_rn(w);
+            sti[(g + h * 8) * (LDK + SPAD) + jj[nb][e]] = __float2half_rn(w);
           }
       }
     }
@@ -163,7 +171,7 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
       const float i0 = __shfl_sync(0xffffffffu, inv[0], (px & 7) * 4);
       const float i1 = __shfl_sync(0xffffffffu, inv[1], (px & 7) * 4);
       const float sc = px < 8 ? i0 : i1;
-      const uint4 raw = *reinterpret_cast<const uint4*>(sth + px * LDK + v * 8);
+      const uint4 raw = *reinterpret_cast<const uint4*>(sth + px * (LDK + SPAD) + v * 8);
       const __half2* hp = reinterpret_cast<const __half2*>(&raw);
       float f[8];
 #pragma unroll
@@ -238,7 +246,7 @@ template <int R, int LDK>
 int launch(const __half* proj, const float* guid, int n_crops, int gh, int gw, float pos_temp, float inv2s2, bf16* kern,
            int ldk, cudaStream_t st) {
   constexpr int D2 = (2 * R + 1) * (2 * R + 1), NB = (16 + 2 * R + 7) / 8, HR = TYR + 2 * R, NPOS = 16 + NB * 8;
-  const int smem = HR * NPOS * PROW + ((D2 * 4 + 15) & ~15) + TYR * 16 * LDK * 2;
+  const int smem = HR * NPOS * PROW + ((D2 * 4 + 15) & ~15) + TYR * 16 * (LDK + SPAD) * 2;
   CSEG_SET_SMEM((range_kernel_mma<R, LDK>), smem);
   dim3 grid(cdiv(gw, TXR), cdiv(gh, TYR), n_crops);
   cseg_launch(range_kernel_mma<R, LDK>, dim3(grid), dim3(TYR * 32), smem, st, proj, (const float4*)guid, gh, gw, pos_temp, inv2s2, kern, ldk);
