@@ -199,46 +199,90 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
   }
 }
 
-// range_proj (upsamplers.py:209-214) with fp16 output for the tensor-core range kernel
+// range_proj (upsamplers.py:209-214) with fp16 output for the tensor-core range kernel:
+//   proj[p] = W3 . gelu(W0 . rgb[p] + b0) + b3        (two 1x1 convs, 3 -> 32 -> 32)
+// One warp per 16 pixels.  The hidden layer is evaluated directly in the mma.sync A-fragment layout (16 GELUs per
+// thread, erf form to 3e-7), the 32x32 second layer runs on the tensor cores with both operands split into
+// fp16 hi + lo parts (hi.hi + hi.lo + lo.hi: products carry ~21 bits, accumulation is fp32), so the result equals
+// the fp32 evaluation to ~1e-6 before the final fp16 rounding.
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  __half2 h = __halves2half2(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 __global__ void __launch_bounds__(256) range_proj_f16_kernel(const float4* __restrict__ guid, int n_pix,
                                                              const float* __restrict__ w0, const float* __restrict__ b0,
                                                              const float* __restrict__ w3, const float* __restrict__ b3,
                                                              __half* __restrict__ proj) {
   pdl_grid_sync();
-  __shared__ __align__(16) float sw0[KD * 3], sb0[KD], sw3[KD * KD], sb3[KD];
-  for (int i = threadIdx.x; i < KD * 3; i += blockDim.x) sw0[i] = w0[i];
-  for (int i = threadIdx.x; i < KD * KD; i += blockDim.x) sw3[i] = w3[i];
-  for (int i = threadIdx.x; i < KD; i += blockDim.x) { sb0[i] = b0[i]; sb3[i] = b3[i]; }
-  __syncthreads();
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= n_pix) return;
-  const float4 gq = guid[pix];
-  float h[KD];
+  const int lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  // per-thread constants: the 8 hidden units (k = ks*16 + 2 tig + {0, 1, 8, 9}) of the A fragments ...
+  float wa[2][4][4];
 #pragma unroll
-  for (int k = 0; k < KD; ++k) h[k] = gelu_erf(sw0[k * 3] * gq.x + sw0[k * 3 + 1] * gq.y + sw0[k * 3 + 2] * gq.z + sb0[k]);
-  uint4* o = reinterpret_cast<uint4*>(proj + (size_t)pix * KD);
+  for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-  for (int k8 = 0; k8 < KD / 8; ++k8) {
-    float acc[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float a = sb3[k8 * 8 + e];
-      const float4* wr = reinterpret_cast<const float4*>(sw3 + (k8 * 8 + e) * KD);   // broadcast LDS.128: 4 weights per load
-#pragma unroll
-      for (int j4 = 0; j4 < KD / 4; ++j4) {
-        const float4 w = wr[j4];
-        a = fmaf(w.x, h[4 * j4], a);
-        a = fmaf(w.y, h[4 * j4 + 1], a);
-        a = fmaf(w.z, h[4 * j4 + 2], a);
-        a = fmaf(w.w, h[4 * j4 + 3], a);
-      }
-      acc[e] = a;
+    for (int q = 0; q < 4; ++q) {
+      const int k = ks * 16 + 2 * tig + (q & 1) + (q >> 1) * 8;
+      wa[ks][q][0] = w0[k * 3];
+      wa[ks][q][1] = w0[k * 3 + 1];
+      wa[ks][q][2] = w0[k * 3 + 2];
+      wa[ks][q][3] = b0[k];
     }
-    uint4 u;
-    __half2* hp = reinterpret_cast<__half2*>(&u);
+  // ... and the B fragments of W3 (B[k][n] = w3[n][k]), hi and lo halves
+  uint32_t bh[4][2][2], bl[4][2][2];
+  float bias[4][2];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) hp[e] = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
-    o[k8] = u;
+  for (int nb = 0; nb < 4; ++nb) {
+    const int n = nb * 8 + g;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int k = ks * 16 + 2 * tig + r * 8;
+        const float v0 = w3[n * KD + k], v1 = w3[n * KD + k + 1];
+        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+        bh[nb][ks][r] = pack_h2(h0, h1);
+        bl[nb][ks][r] = pack_h2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+      }
+    bias[nb][0] = b3[nb * 8 + 2 * tig];
+    bias[nb][1] = b3[nb * 8 + 2 * tig + 1];
+  }
+  const int n_tiles = (n_pix + 15) / 16;
+  for (int tile = warp_global; tile < n_tiles; tile += n_warps) {
+    const int p0 = tile * 16 + g, p1 = p0 + 8;
+    const float4 g0 = guid[min(p0, n_pix - 1)], g1 = guid[min(p1, n_pix - 1)];
+    uint32_t ah[2][4], al[2][4];                       // A fragments: (row g | g+8) x (k pair | k pair + 8)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {                    // r: k pair (0,1) or (8,9)
+        float h[2][2];                                 // [row][element of the pair]
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float* w = wa[ks][r * 2 + e];
+          h[0][e] = gelu_fast(fmaf(w[0], g0.x, fmaf(w[1], g0.y, fmaf(w[2], g0.z, w[3]))));
+          h[1][e] = gelu_fast(fmaf(w[0], g1.x, fmaf(w[1], g1.y, fmaf(w[2], g1.z, w[3]))));
+        }
+#pragma unroll
+        for (int row = 0; row < 2; ++row) {
+          const __half x0 = __float2half_rn(h[row][0]), x1 = __float2half_rn(h[row][1]);
+          ah[ks][r * 2 + row] = pack_h2(x0, x1);
+          al[ks][r * 2 + row] = pack_h2(__float2half_rn(h[row][0] - __half2float(x0)),
+                                        __float2half_rn(h[row][1] - __half2float(x1)));
+        }
+      }
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      float d[4] = {bias[nb][0], bias[nb][1], bias[nb][0], bias[nb][1]};
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        mma_f16(d, al[ks], bh[nb][ks][0], bh[nb][ks][1]);
+        mma_f16(d, ah[ks], bl[nb][ks][0], bl[nb][ks][1]);
+        mma_f16(d, ah[ks], bh[nb][ks][0], bh[nb][ks][1]);
+      }
+      if (p0 < n_pix) *reinterpret_cast<__half2*>(proj + (size_t)p0 * KD + nb * 8 + 2 * tig) = __floats2half2_rn(d[0], d[1]);
+      if (p1 < n_pix) *reinterpret_cast<__half2*>(proj + (size_t)p1 * KD + nb * 8 + 2 * tig) = __floats2half2_rn(d[2], d[3]);
+    }
   }
 }
 
@@ -258,7 +302,8 @@ int launch(const __half* proj, const float* guid, int n_crops, int gh, int gw, f
 
 int cseg_jbu_range_proj_f16(const float* guid, int n_pix, const float* w0, const float* b0, const float* w3,
                             const float* b3, void* proj, cudaStream_t st) {
-  cseg_launch(range_proj_f16_kernel, dim3(cdiv(n_pix, 256)), dim3(256), 0, st, (const float4*)guid, n_pix, w0, b0, w3, b3, (__half*)proj);
+  const int blocks = (int)std::min<long long>(cdiv(cdiv(n_pix, 16), 8), (long long)sm_count() * 8);
+  cseg_launch(range_proj_f16_kernel, dim3(blocks), dim3(256), 0, st, (const float4*)guid, n_pix, w0, b0, w3, b3, (__half*)proj);
   CSEG_LAUNCH_CHECK("jbu_range_proj_f16");
   return 0;
 }
