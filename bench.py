@@ -302,10 +302,13 @@ def main():
     def basis_work(s, Cb, n, hw, Tk, ts, gram, aux, consts, Q, logits, cls_logit_bias=None):
         return ('hbm', float(n * hw * (Cb * esize + Q * 4)))
 
-    workfns = dict(basis_logits=basis_work, fixup_norm_sim=fns_work, gemm=gemm_work, jbu_apply=apply_work, attention=attn_work, norm_sim=nsim_work,
+    def kfix_work(k, W0, b0, W3s, b3s, out):
+        return ('hbm', float(2 * k.shape[0] * k.shape[1] * esize))
+
+    workfns = dict(jbu_kernel_fixup=kfix_work, basis_logits=basis_work, fixup_norm_sim=fns_work, gemm=gemm_work, jbu_apply=apply_work, attention=attn_work, norm_sim=nsim_work,
                    accum_argmax=accum_work, jbu_range_kernel=rk_work)
     names = ['preprocess_u8', 'patchify', 'embed_tokens', 'layernorm', 'gemm', 'attention', 'simmap', 'outlier_suppress',
-             'cls_debias', 'jbu_guidance', 'jbu_range_proj', 'jbu_range_kernel', 'jbu_apply', 'norm_sim', 'fixup_norm_sim', 'basis_logits',
+             'cls_debias', 'jbu_guidance', 'jbu_range_proj', 'jbu_range_kernel', 'jbu_kernel_fixup', 'jbu_apply', 'norm_sim', 'fixup_norm_sim', 'basis_logits',
              'accum_argmax', 'iou_hist']
     for nm in names:
         orig[nm] = getattr(ops, nm)

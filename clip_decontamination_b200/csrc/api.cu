@@ -28,6 +28,9 @@ int cseg_basis_logits_tc(const void* s, int lds, int Cb, int n_crops, int hw, in
                          const void* aux, int ldg, const float* consts, int Q, const float* cls_bias, float* logits,
                          cudaStream_t st);
 
+int cseg_jbu_kernel_fixup_tc(const void* k, int lda, const void* W0, int ldw0, const float* b0, const void* W3, int ldw3,
+                             const float* b3, int M, int ldk, void* out, int ldo, cudaStream_t st);
+
 extern "C" {
 
 int cseg_version(void) { return CSEG_VERSION; }
@@ -77,6 +80,15 @@ int cseg_basis_logits(int dtype, const void* s, int lds, int Cb, int n_crops, in
   CSEG_REQUIRE(s && gram && aux && consts && logits, "basis_logits: null operand");
   return cseg_basis_logits_tc(s, lds, Cb, n_crops, hw, T, tstride, gram, aux, ldg, consts, Q, cls_logit_bias, logits,
                               (cudaStream_t)stream);
+}
+
+int cseg_jbu_kernel_fixup(int dtype, const void* k, int lda, const void* W0, int ldw0, const float* b0, const void* W3s,
+                          int ldw3, const float* b3s, int M, int ldk, void* out, int ldo, void* stream) {
+  CSEG_REQUIRE(dtype == CSEG_BF16, "jbu_kernel_fixup: bf16 only (fp32 mode issues the two GEMMs through cseg_gemm)");
+  CSEG_REQUIRE(k && W0 && W3s && out && M > 0, "jbu_kernel_fixup: null operand / empty problem");
+  const int rc = cseg_jbu_kernel_fixup_tc(k, lda, W0, ldw0, b0, W3s, ldw3, b3s, M, ldk, out, ldo, (cudaStream_t)stream);
+  if (rc == 1) CSEG_FAIL(CSEG_EINVAL, "jbu_kernel_fixup: ldk=%d must be 64 or 128, strides multiples of 8, 16-byte aligned operands", ldk);
+  return rc;
 }
 
 // test hook: CUDA-core GEMM on bf16 operands (on-device cross-check of the tcgen05 kernel)

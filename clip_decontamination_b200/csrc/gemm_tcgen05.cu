@@ -807,6 +807,250 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+
+// =====================================================================================================
+// JBU kernel fix-up in one pass (simfeatup_dev/upsamplers.py:218-223,258-262):
+//   out[p, :] = k[p, :] + 0.1 * (W3 . gelu(W0 . k[p, :] + b0) + b3)            k = range x spatial kernel, LDK wide
+// Two chained tcgen05 GEMMs per 128-row panel.  The hidden activations never leave the SM: the first epilogue
+// writes gelu(.) as bf16 straight into the SWIZZLE_128B K-major layout the second MMA reads; the residual is read
+// back from the TMA-loaded k tile in shared memory.  HBM traffic = read k once + write out once.
+//   warp 0 TMA producer (W0, W3 once; k panels, 2-stage ring)     warp 1 MMA issuer (MMA1 of panel i+1 before
+//   MMA2 of panel i)     warps 2-5 epilogue 1 (D1 -> gelu -> H tile)     warps 6-9 epilogue 2 (D2 + k + b3 -> out)
+// =====================================================================================================
+template <int LDK>
+struct FxCfg {
+  static constexpr int NKB = LDK / BK;
+  static constexpr int W_BYTES = LDK * LDK * 2, P_BYTES = BM * LDK * 2, KB_W = LDK * 128, KB_P = BM * 128;
+  static constexpr int W0_OFF = 0, W3_OFF = W_BYTES, A_OFF = 2 * W_BYTES, H_OFF = A_OFF + 2 * P_BYTES;
+  static constexpr int BIAS_OFF = H_OFF + 2 * P_BYTES;             // b0[LDK], b3[LDK] fp32
+  static constexpr int BAR_OFF = BIAS_OFF + 2 * LDK * 4;
+  static constexpr int NBARS = 17;
+  static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
+  static constexpr int THREADS = 320, TMEM_COLS = 4 * LDK;
+};
+
+template <int LDK>
+__global__ void __launch_bounds__(FxCfg<LDK>::THREADS, 1)
+kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
+                    const __grid_constant__ CUtensorMap tmW3, int M, const float* __restrict__ b0,
+                    const float* __restrict__ b3, bf16* __restrict__ out, int ldo) {
+  using Cf = FxCfg<LDK>;
+  constexpr int NKB = Cf::NKB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + Cf::BAR_OFF);
+  uint32_t* tmem_slot = (uint32_t*)(bars + Cf::NBARS);
+  float* bs0 = reinterpret_cast<float*>(smem + Cf::BIAS_OFF);
+  float* bs3 = bs0 + LDK;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t w_full = smem_u32(bars);
+  const uint32_t a_full0 = w_full + 8, a_empty0 = a_full0 + 16, d1_full0 = a_empty0 + 16, d1_empty0 = d1_full0 + 16;
+  const uint32_t h_full0 = d1_empty0 + 16, h_empty0 = h_full0 + 16, d2_full0 = h_empty0 + 16, d2_empty0 = d2_full0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int panels = (M + BM - 1) / BM;
+  const int n_my = (panels > (int)blockIdx.x) ? (panels - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW3) : "memory");
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(a_full0 + i * 8, 1);
+      mbar_init(a_empty0 + i * 8, 4);
+      mbar_init(d1_full0 + i * 8, 1);
+      mbar_init(d1_empty0 + i * 8, 4);
+      mbar_init(h_full0 + i * 8, 128);
+      mbar_init(h_empty0 + i * 8, 1);
+      mbar_init(d2_full0 + i * 8, 1);
+      mbar_init(d2_empty0 + i * 8, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cf::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_grid_sync();   // everything above is input-independent and overlaps the tail of the previous kernel
+  for (int c = threadIdx.x; c < LDK; c += Cf::THREADS) {
+    bs0[c] = b0 ? b0[c] : 0.f;
+    bs3[c] = b3 ? b3[c] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, 2 * Cf::W_BYTES);
+      for (int kb = 0; kb < NKB; ++kb) {
+        tma_load_2d(smem_base + Cf::W0_OFF + kb * Cf::KB_W, &tmW0, w_full, kb * BK, 0);
+        tma_load_2d(smem_base + Cf::W3_OFF + kb * Cf::KB_W, &tmW3, w_full, kb * BK, 0);
+      }
+      for (int i = 0; i < n_my; ++i) {
+        const uint32_t st = i & 1, u = i >> 1;
+        const int panel = blockIdx.x + i * gridDim.x;
+        mbar_wait(a_empty0 + st * 8, (u & 1) ^ 1);
+        mbar_expect_tx(a_full0 + st * 8, Cf::P_BYTES);
+        for (int kb = 0; kb < NKB; ++kb)
+          tma_load_2d(smem_base + Cf::A_OFF + st * Cf::P_BYTES + kb * Cf::KB_P, &tmA, a_full0 + st * 8, kb * BK, panel * BM);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, LDK);
+      mbar_wait(w_full, 0);
+      auto mma1 = [&](int i) {
+        const uint32_t st = i & 1, u = i >> 1;
+        mbar_wait(a_full0 + st * 8, u & 1);
+        mbar_wait(d1_empty0 + st * 8, (u & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + st * 2 * LDK;
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) {
+          const uint64_t adesc = make_sdesc(smem_base + Cf::A_OFF + st * Cf::P_BYTES + kb * Cf::KB_P);
+          const uint64_t bdesc = make_sdesc(smem_base + Cf::W0_OFF + kb * Cf::KB_W);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(d1_full0 + st * 8);
+      };
+      auto mma2 = [&](int i) {
+        const uint32_t st = i & 1, u = i >> 1;
+        mbar_wait(h_full0 + st * 8, u & 1);
+        mbar_wait(d2_empty0 + st * 8, (u & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + st * 2 * LDK + LDK;
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) {
+          const uint64_t adesc = make_sdesc(smem_base + Cf::H_OFF + st * Cf::P_BYTES + kb * Cf::KB_P);
+          const uint64_t bdesc = make_sdesc(smem_base + Cf::W3_OFF + kb * Cf::KB_W);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(d2_full0 + st * 8);
+        umma_commit(h_empty0 + st * 8);
+      };
+      if (n_my > 0) mma1(0);
+      for (int i = 0; i < n_my; ++i) {
+        if (i + 1 < n_my) mma1(i + 1);
+        mma2(i);
+      }
+    }
+  } else if (warp < 6) {
+    // ---- epilogue 1: hidden = gelu(D1 + b0) -> bf16 H tile (K-major, SWIZZLE_128B) ----
+    const int lg = warp & 3, row = lg * 32 + lane;
+    for (int i = 0; i < n_my; ++i) {
+      const uint32_t st = i & 1, u = i >> 1;
+      mbar_wait(d1_full0 + st * 8, u & 1);
+      mbar_wait(h_empty0 + st * 8, (u & 1) ^ 1);
+      tc_fence_after();
+      uint8_t* hrow = smem + Cf::H_OFF + st * Cf::P_BYTES + row * 128;
+#pragma unroll 1
+      for (int c4 = 0; c4 < LDK / 32; ++c4) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(st * 2 * LDK + c4 * 32), r);
+        if (c4 == LDK / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d1_empty0 + st * 8);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 pk;
+          uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = c4 * 32 + j * 8 + 2 * e;
+            const __nv_bfloat162 t = __floats2bfloat162_rn(gelu_tanh(__uint_as_float(r[j * 8 + 2 * e]) + bs0[col]),
+                                                          gelu_tanh(__uint_as_float(r[j * 8 + 2 * e + 1]) + bs0[col + 1]));
+            pw[e] = *reinterpret_cast<const uint32_t*>(&t);
+          }
+          const int c = c4 * 4 + j;                               // 16-byte chunk of the row
+          *reinterpret_cast<uint4*>(hrow + (c >> 3) * Cf::KB_P + (((c & 7) ^ (row & 7)) << 4)) = pk;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(h_full0 + st * 8);
+    }
+  } else {
+    // ---- epilogue 2: out = k + D2 + b3 (k read back from the TMA tile) ----
+    const int lg = warp & 3, row = lg * 32 + lane;
+    for (int i = 0; i < n_my; ++i) {
+      const uint32_t st = i & 1, u = i >> 1;
+      const int panel = blockIdx.x + i * gridDim.x;
+      const long long grow = (long long)panel * BM + row;
+      mbar_wait(d2_full0 + st * 8, u & 1);
+      tc_fence_after();
+      const uint8_t* arow = smem + Cf::A_OFF + st * Cf::P_BYTES + row * 128;
+      bf16* orow = out + grow * ldo;
+#pragma unroll 1
+      for (int c4 = 0; c4 < LDK / 32; ++c4) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(st * 2 * LDK + LDK + c4 * 32), r);
+        uint4 res[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c4 * 4 + j;
+          res[j] = *reinterpret_cast<const uint4*>(arow + (c >> 3) * Cf::KB_P + (((c & 7) ^ (row & 7)) << 4));
+        }
+        if (c4 == LDK / 32 - 1) {                                  // accumulator and k tile fully read
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(d2_empty0 + st * 8);
+            mbar_arrive(a_empty0 + st * 8);
+          }
+        }
+        if (grow < M) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&res[j]);
+            uint4 pk;
+            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int col = c4 * 32 + j * 8 + 2 * e;
+              const float2 kv = __bfloat1622float2(kh[e]);
+              const __nv_bfloat162 t = __floats2bfloat162_rn(kv.x + __uint_as_float(r[j * 8 + 2 * e]) + bs3[col],
+                                                            kv.y + __uint_as_float(r[j * 8 + 2 * e + 1]) + bs3[col + 1]);
+              pw[e] = *reinterpret_cast<const uint32_t*>(&t);
+            }
+            *reinterpret_cast<uint4*>(orow + c4 * 32 + j * 8) = pk;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cf::TMEM_COLS) : "memory");
+  }
+}
+
+template <int LDK>
+int launch_kernel_fixup(const void* k, int lda, const void* W0, int ldw0, const float* b0, const void* W3, int ldw3,
+                        const float* b3, int M, void* out, int ldo, cudaStream_t st) {
+  using Cf = FxCfg<LDK>;
+  CUtensorMap ta, tw0, tw3;
+  int rc = make_map(&ta, k, M, LDK, lda, BM);
+  if (rc) return rc;
+  rc = make_map(&tw0, W0, LDK, LDK, ldw0, LDK);
+  if (rc) return rc;
+  rc = make_map(&tw3, W3, LDK, LDK, ldw3, LDK);
+  if (rc) return rc;
+  CSEG_SET_SMEM(kernel_fixup_kernel<LDK>, Cf::SMEM_BYTES);
+  const int panels = cdiv(M, BM);
+  cseg_launch(kernel_fixup_kernel<LDK>, dim3(std::min(panels, sm_count())), dim3(Cf::THREADS), Cf::SMEM_BYTES, st, ta, tw0,
+              tw3, M, b0, b3, (bf16*)out, ldo);
+  CSEG_LAUNCH_CHECK("jbu_kernel_fixup");
+  return 0;
+}
+
 }  // namespace
 
 // returns 1 when the shape is not covered by the fused kernel (caller runs cseg_gemm + cseg_norm_sim instead)
@@ -850,6 +1094,15 @@ int cseg_basis_logits_tc(const void* s, int lds, int Cb, int n_crops, int hw, in
       ta, tb1, tb2, panels, hw, tstride, KS, (const bf16*)s, lds, consts, Q, cls_bias, logits);
   CSEG_LAUNCH_CHECK("basis_logits");
   return 0;
+}
+
+// returns 1 when the shape is not covered (caller issues the two GEMMs instead)
+int cseg_jbu_kernel_fixup_tc(const void* k, int lda, const void* W0, int ldw0, const float* b0, const void* W3, int ldw3,
+                             const float* b3, int M, int ldk, void* out, int ldo, cudaStream_t st) {
+  if ((ldk != 64 && ldk != 128) || lda % 8 || ldw0 % 8 || ldw3 % 8 || ldo % 8) return 1;
+  if ((((uintptr_t)k | (uintptr_t)W0 | (uintptr_t)W3 | (uintptr_t)out) & 15) != 0) return 1;
+  if (ldk == 128) return launch_kernel_fixup<128>(k, lda, W0, ldw0, b0, W3, ldw3, b3, M, out, ldo, st);
+  return launch_kernel_fixup<64>(k, lda, W0, ldw0, b0, W3, ldw3, b3, M, out, ldo, st);
 }
 
 int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,

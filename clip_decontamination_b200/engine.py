@@ -291,11 +291,17 @@ class JBUEngine:
             proj = ws.get('proj', (npix, 32), torch.float16 if cdt == torch.bfloat16 else f32)
             ops.jbu_range_proj(guid, npix, st['rp_w0'], st['rp_b0'], st['rp_w3'], st['rp_b3'], proj)
             kw = st['ldk']
-            hk = ws.get('hidkern', (npix, 2 * kw), cdt)                                # [hidden | kernel] rows
-            ops.jbu_range_kernel(proj, guid, n, GH, GW, st['radius'], st['range_temp'], st['sigma'], hk[:, kw:])
-            ops.gemm(hk[:, kw:], st['fx_w0'], hk[:, :kw], bias=st['fx_b0'], act=ACT_GELU)   # fixup_proj.0 + GELU
             kern = ws.get('kern', (npix, kw), cdt)
-            ops.gemm(hk, st['fx_w3'], kern, bias=st['fx_b3'])                          # kernel + .1 * fixup_proj.3
+            if cdt == torch.bfloat16 and kw in (64, 128):
+                # both fix-up convs in one kernel: hidden activations stay on chip
+                kraw = ws.get('kraw', (npix, kw), cdt)
+                ops.jbu_range_kernel(proj, guid, n, GH, GW, st['radius'], st['range_temp'], st['sigma'], kraw)
+                ops.jbu_kernel_fixup(kraw, st['fx_w0'], st['fx_b0'], st['fx_w3'][:, :kw], st['fx_b3'], kern)
+            else:
+                hk = ws.get('hidkern', (npix, 2 * kw), cdt)                            # [hidden | kernel] rows
+                ops.jbu_range_kernel(proj, guid, n, GH, GW, st['radius'], st['range_temp'], st['sigma'], hk[:, kw:])
+                ops.gemm(hk[:, kw:], st['fx_w0'], hk[:, :kw], bias=st['fx_b0'], act=ACT_GELU)   # fixup_proj.0 + GELU
+                ops.gemm(hk, st['fx_w3'], kern, bias=st['fx_b3'])                      # kernel + .1 * fixup_proj.3
             if taps is not None:
                 taps.setdefault('jbu_kernels', []).append(kern.clone())
             hr = ws.get('hr', (npix, C), cdt)

@@ -155,6 +155,18 @@ def fixup_norm_sim(y, W, n_crops, hw, Cc, bias, alpha, text, logits, cls_logit_b
     return logits
 
 
+def jbu_kernel_fixup(k, W0, b0, W3s, b3s, out):
+    """out = k + W3s . gelu(W0 . k + b0) + b3s per row (include/clipseg.h: cseg_jbu_kernel_fixup); 2-D views."""
+    M, ldk = k.shape
+    assert out.shape == k.shape and W0.shape[0] == ldk and W3s.shape[0] == ldk
+    for t in (k, W0, W3s, out):                      # row-strided 2-D views are fine (strides are passed)
+        assert t.is_cuda and t.dim() == 2 and t.stride(1) == 1 and t.dtype == k.dtype
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    check(lib.cseg_jbu_kernel_fixup(_dt(k), vp(k), k.stride(0), vp(W0), W0.stride(0), _ptr(b0), vp(W3s),
+                                    W3s.stride(0), _ptr(b3s), M, ldk, vp(out), out.stride(0), _stream()))
+    return out
+
+
 def basis_logits(s, Cb, n_crops, hw, T, tstride, gram, aux, consts, Q, logits, cls_logit_bias=None):
     """Cosine logits from JBU basis coefficients (include/clipseg.h: cseg_basis_logits)."""
     assert gram.stride(0) == aux.stride(0)

@@ -160,6 +160,15 @@ CSEG_API int cseg_fixup_norm_sim(int dtype, const void* y, int ldy, const void* 
                         int C, const float* bias, float alpha, const float* text, int Q,
                         const float* cls_logit_bias, float* logits, void* scratch, void* stream);
 
+/* JBU kernel fix-up in one pass (upsamplers.py:218-223,258-262), bf16:
+ *   out[p, :] = k[p, :] + (W3s . gelu(W0 . k[p, :] + b0) + b3s)      W3s = 0.1 * fixup_proj.3.weight, b3s = 0.1 * bias
+ * k, out bf16 [M, ldk] (row strides lda, ldo); W0, W3s bf16 [ldk, ldk] row-major (row strides ldw0, ldw3), zero padded
+ * beyond the (2r+1)^2 (+3 guidance) used entries; ldk = 64 or 128.  Two chained tcgen05 GEMMs per 128-row panel; the
+ * hidden activations stay in shared memory.  Equivalent to two cseg_gemm calls (GELU epilogue, then residual). */
+CSEG_API int cseg_jbu_kernel_fixup(int dtype, const void* k, int lda, const void* W0, int ldw0, const float* b0,
+                          const void* W3s, int ldw3, const float* b3s, int M, int ldk, void* out, int ldo,
+                          void* stream);
+
 /* K11..K13 in basis form (bf16 fast path; same result as cseg_jbu_apply x4 + cseg_fixup_norm_sim).
  * The JBU stack (upsamplers.py:269-274,320-325) is linear in its source and treats every channel alike, so
  * upsampling the identity (one channel per low-resolution token: src[crop, k, :] = e_k) gives coefficients

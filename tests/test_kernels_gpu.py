@@ -387,6 +387,25 @@ def test_iou_hist(ops):
     assert torch.equal(hist.cpu(), torch.stack([ai, ap, al]) * 2)
 
 
+@pytest.mark.parametrize('ldk,M', [(128, 1000), (64, 333), (128, 128 * 300 + 5)])
+def test_jbu_kernel_fixup(ops, ldk, M):
+    """fused kernel fix-up == k + W3s . gelu(W0 . k + b0) + b3s in fp32 on the same bf16 operands (erf GELU);
+    tolerance 6e-3: the result lies in [0, 2), where half a bf16 ulp is 3.9e-3, plus the bf16 hidden activations."""
+    k = torch.rand(M, ldk, generator=_g(1)).bfloat16()
+    W0 = (torch.randn(ldk, ldk, generator=_g(2)) * ldk ** -0.5).bfloat16()
+    W3 = (torch.randn(ldk, ldk, generator=_g(3)) * 0.1 * ldk ** -0.5).bfloat16()
+    b0, b3 = torch.randn(ldk, generator=_g(4)) * 0.1, torch.randn(ldk, generator=_g(5)) * 0.01
+    hid = F.gelu(k.float() @ W0.float().t() + b0).bfloat16().float()
+    ref = k.float() + hid @ W3.float().t() + b3
+    out = torch.full((M, ldk), float('nan'), device='cuda', dtype=torch.bfloat16)
+    w3wide = torch.zeros(ldk, 2 * ldk, dtype=torch.bfloat16)     # the engine passes a strided view of [0.1 W3 | I]
+    w3wide[:, :ldk] = W3
+    ops.jbu_kernel_fixup(k.cuda(), W0.cuda(), b0.cuda(), w3wide.cuda()[:, :ldk], b3.cuda(), out)
+    err = (out.float().cpu() - ref).abs().max().item()
+    print(f'jbu_kernel_fixup ldk={ldk} M={M} max|d|={err:.3e}')
+    assert err < 6e-3
+
+
 @pytest.mark.parametrize('T,Cb,Q,n,hw', [(196, 256, 6, 3, 384), (240, 256, 15, 2, 256), (16, 128, 1, 2, 128),
                                           (49, 128, 7, 5, 640)])
 def test_basis_logits(ops, T, Cb, Q, n, hw):
