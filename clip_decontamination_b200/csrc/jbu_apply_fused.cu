@@ -1,0 +1,433 @@
+// JBU apply = bicubic x2 upsample + reflect pad + adaptive convolution, as ONE tcgen05 kernel on the LOW-resolution
+// source (bf16 path of cseg_jbu_apply, C % 128 == 0).
+//
+//   out[y, x, c] = sum_{i,j} k[(y,x)][i*D + j] * hr[reflect(y+i-R), reflect(x+j-R), c]        D = 2R+1
+//   hr[qy, qx, c] = sum_{a,b} cy_a(qy) cx_b(qx) src[clamp(..), clamp(..), c]                  (bicubic, A = -0.75)
+//
+// (simfeatup_dev/upsamplers.py:268-274; torch upsample_bicubic2d, align_corners=False.)  Both steps are linear and
+// separable in the spatial position, so for every output pixel the D x D kernel over the high-res neighbourhood folds
+// into a composite kernel over a (2 DO + 1)^2 LOW-res neighbourhood (DO = 4 for R = 5):
+//   K'[(y,x)][dy, dx] = sum_{i,j} TY[y][i][dy] * k[(y,x)][i, j] * TX[x][j][dx]
+// where TX[x][j][dx] is the bicubic weight that tap j of column x puts on low-res column (x >> 1) + dx - DO (reflect
+// padding and border clamps are resolved when the table is built; TY likewise).  The high-res intermediate never
+// exists: HBM traffic drops from (write + re-read hr, 5 x the source) to the source itself, and the banded GEMM sees
+// 16 instead of 32 positions per source row and NLR = 10 instead of 14 rows per tile.
+//
+// Per tile of 4 rows x 16 px and 128-channel slab, every low-res row s of the (NLR x 16) source patch costs one
+// tcgen05.mma  D[128 ch, 64 px] += A_s[128 ch, 16 pos] . B_s[16 pos, 64 px]  (A: MN-major SWIZZLE_128B straight from
+// the [pos][ch] HBM layout; B: composite band tile, K-major).  Warp roles of the persistent CTA:
+//   warps 0-3   epilogue (tcgen05.ld, lane = channel)           warp 4   TMEM allocator + MMA issuer
+//   warps 5-8   strip loaders (cp.async into a 6-stage ring)
+//   warps 9-12  composite builders, one output row each: per pixel two mma.sync (fp16) compute T^T = TX^T . k^T, two
+//               more K'^T = T^T . TY (the accumulator of the first pair is the A fragment of the second), and the
+//               (2 DO + 1)^2 results are scattered into the double-buffered band tiles.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <cuda_fp16.h>
+
+namespace {
+
+constexpr int FZ_RW = 4, FZ_TX = 16, FZ_NPX = FZ_RW * FZ_TX;   // 64 pixels per tile = N of the MMA
+constexpr int FZ_NPOS = 16;                                    // low-res positions per strip = K of the MMA
+constexpr int FZ_NSTG = 6, FZ_INFL = 4;                        // strip ring stages / strips in flight per loader thread
+constexpr int FZ_EPI_WARPS = 4, FZ_LD_WARPS = 4, FZ_BB_WARPS = 4;
+constexpr int FZ_THREADS = 32 * (FZ_EPI_WARPS + 1 + FZ_LD_WARPS + FZ_BB_WARPS);
+constexpr int FZ_LD_T0 = 32 * (FZ_EPI_WARPS + 1), FZ_BB_T0 = FZ_LD_T0 + 32 * FZ_LD_WARPS;
+constexpr int FZ_TAB = 16 * 16;                                // halves per table entry: [16][16]
+
+__device__ __forceinline__ int fz_reflect(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+__device__ __forceinline__ void fz_cubic(float t, float (&c)[4]) {   // torch upsample_bicubic2d, A = -0.75
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  c[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  c[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  c[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+__device__ __forceinline__ void fz_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fz_mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t fz_pack(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Tables (fp16, one 16x16 entry per coordinate), both stored [coordinate][d][tap]:
+//   tab[c][d][t] = sum over the bicubic taps b of high-res coordinate q = reflect(c + t - R) that land on low-res
+//                  coordinate (c >> 1) + d - DO:  coeff_b(q)
+// axis 0: columns (n = W2) -> TX^T[x][dx][j];   axis 1: rows (n = H2) -> TY^T[y][dy][i]
+__global__ void fz_tables_kernel(int W2, int H2, int R, __half* __restrict__ tabx, __half* __restrict__ taby) {
+  pdl_grid_sync();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (W2 + H2) * 16) return;
+  const int t = idx & 15, cc = idx >> 4;
+  const bool rows = cc >= W2;
+  const int c = rows ? cc - W2 : cc, n = rows ? H2 : W2, nl = n >> 1, D = 2 * R + 1, DO = (R + 3) / 2;
+  __half* out = (rows ? taby : tabx) + (size_t)c * FZ_TAB;
+  float acc[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) acc[d] = 0.f;
+  if (t < D) {
+    const int q = fz_reflect(c + t - R, n), u = q >> 1, odd = q & 1;
+    float cf[4];
+    fz_cubic(odd ? 0.25f : 0.75f, cf);                 // even q = 2u: taps u-2..u+1; odd: u-1..u+2
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int l = min(max(u - 2 + odd + b, 0), nl - 1);
+      const int d = l - (c >> 1) + DO;                 // in [0, 2 DO] by construction
+#pragma unroll
+      for (int dd = 0; dd < 16; ++dd)
+        if (dd == d) acc[dd] += cf[b];
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 16; ++d) out[d * 16 + t] = __float2half_rn(acc[d]);
+}
+
+__device__ __forceinline__ uint64_t fz_adesc(uint32_t saddr, uint32_t lbo_bytes) {   // MN-major SWIZZLE_128B (jbu_apply_tc.cu)
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t fz_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(FZ_NPX >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+template <int R, int MH>
+struct FzCfg {
+  static constexpr int D = 2 * R + 1, DO = (R + 3) / 2;           // composite kernel spans 2 DO + 1 low-res taps
+  static constexpr int NLR = (FZ_RW + 2 * R) / 2 + 3;             // low-res rows per tile (10 / 8)
+  static constexpr int NQUAD = (NLR + 3) / 4;                     // four strip rows share one 128 B band-tile row
+  static constexpr int CH = 128 * MH;
+  static constexpr int CHUNK_BYTES = FZ_NPOS * 128;               // one 64-channel chunk of a strip (16 rows x 128 B)
+  static constexpr int A_STAGE = (CH / 64) * CHUNK_BYTES;         // 4 / 8 KB
+  static constexpr int B_QUAD = FZ_NPX * 128, B_BUF = NQUAD * B_QUAD;
+  static constexpr int WROW = 256 + 16;                           // staged raw weights: bytes per pixel row (padded)
+  static constexpr int W_STAGE = FZ_BB_WARPS * 16 * WROW;
+  static constexpr int A_OFF = 0, B_OFF = FZ_NSTG * A_STAGE, W_OFF = B_OFF + 2 * B_BUF, BAR_OFF = W_OFF + W_STAGE;
+  static constexpr int NBARS = 2 * FZ_NSTG + 8;
+  static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
+  static constexpr int TMEM_COLS = (2 * MH * FZ_NPX <= 128) ? 128 : 256;
+};
+
+template <int R, int MH>
+__global__ void __launch_bounds__(FZ_THREADS, 1)
+jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const bf16* __restrict__ kern, int ldk,
+                       const __half* __restrict__ tabx, const __half* __restrict__ taby, bf16* __restrict__ dst, int nx,
+                       int ny, int nslab, int total_tiles) {
+  using Cf = FzCfg<R, MH>;
+  constexpr int D = Cf::D, DO = Cf::DO, NLR = Cf::NLR;
+  const int H2 = 2 * h, W2 = 2 * w;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + Cf::BAR_OFF);
+  uint32_t* tmem_slot = (uint32_t*)(bars + Cf::NBARS);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t a_full0 = smem_u32(bars), a_empty0 = a_full0 + FZ_NSTG * 8;
+  const uint32_t b_full0 = a_empty0 + FZ_NSTG * 8, b_empty0 = b_full0 + 16;
+  const uint32_t t_full0 = b_empty0 + 16, t_empty0 = t_full0 + 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < FZ_NSTG; ++i) {
+      mbar_init(a_full0 + i * 8, 32 * FZ_LD_WARPS);
+      mbar_init(a_empty0 + i * 8, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(b_full0 + i * 8, 32 * FZ_BB_WARPS);
+      mbar_init(b_empty0 + i * 8, 1);
+      mbar_init(t_full0 + i * 8, 1);
+      mbar_init(t_empty0 + i * 8, FZ_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == FZ_EPI_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cf::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_grid_sync();   // everything above is input-independent and overlaps the tail of the previous kernel
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int tile, int& x0, int& y0, int& crop, int& c0) {
+    const int xt = tile % nx, rest = tile / nx;
+    const int yt = rest % ny, z = rest / ny;
+    x0 = xt * FZ_TX;
+    y0 = yt * FZ_RW;
+    crop = z / nslab;
+    c0 = (z % nslab) * Cf::CH;
+  };
+
+  if (warp < FZ_EPI_WARPS) {
+    // ---------------- epilogue: lane = channel, 64 pixel columns per channel slab ----------------
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      int x0, y0, crop, c0;
+      tile_coords(tile, x0, y0, crop, c0);
+      const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+      mbar_wait(t_full0 + as * 8, aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int hc = 0; hc < MH * (FZ_NPX / 32); ++hc) {          // 32 pixel columns (two output rows) per step
+        const int half = hc / (FZ_NPX / 32), cb = hc % (FZ_NPX / 32);
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((as * MH + half) * FZ_NPX + cb * 32), r);
+        bf16* obase = dst + (size_t)crop * H2 * W2 * C + c0 + half * 128 + warp * 32 + lane;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int y = y0 + cb * 2 + rr;
+          if (y >= H2) continue;
+          bf16* o = obase + ((size_t)y * W2 + x0) * C;
+          const int mmax = min(16, W2 - x0);
+          if (mmax == 16) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) o[(size_t)m * C] = __float2bfloat16_rn(__uint_as_float(r[rr * 16 + m]));
+          } else {
+#pragma unroll
+            for (int m = 0; m < 16; ++m)
+              if (m < mmax) o[(size_t)m * C] = __float2bfloat16_rn(__uint_as_float(r[rr * 16 + m]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty0 + as * 8);
+    }
+  } else if (warp == FZ_EPI_WARPS) {
+    // ---------------- MMA issuer: one MMA per low-res row and channel half ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = fz_idesc();
+      uint32_t tl = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+        mbar_wait(t_empty0 + as * 8, aph ^ 1);
+        mbar_wait(b_full0 + as * 8, aph);
+        tc_fence_after();
+        const uint32_t bbuf = smem_base + Cf::B_OFF + as * Cf::B_BUF;
+        for (int s = 0; s < NLR; ++s, ++it) {
+          const uint32_t st = it % FZ_NSTG, ph = (it / FZ_NSTG) & 1;
+          mbar_wait(a_full0 + st * 8, ph);
+          tc_fence_after();
+          const uint32_t a_src = smem_base + Cf::A_OFF + st * Cf::A_STAGE;
+          const uint64_t bdesc = make_sdesc(bbuf + (s >> 2) * Cf::B_QUAD + (s & 3) * 32);
+#pragma unroll
+          for (int half = 0; half < MH; ++half) {
+            const uint64_t adesc = fz_adesc(a_src + half * 2 * Cf::CHUNK_BYTES, Cf::CHUNK_BYTES);
+            umma_f16(tmem_base + (uint32_t)((as * MH + half) * FZ_NPX), adesc, bdesc, idesc, s > 0 ? 1u : 0u);
+          }
+          umma_commit(a_empty0 + st * 8);
+        }
+        umma_commit(t_full0 + as * 8);
+        umma_commit(b_empty0 + as * 8);
+      }
+    }
+  } else if (warp < FZ_EPI_WARPS + 1 + FZ_LD_WARPS) {
+    // ---------------- strip loaders: NLR low-res rows x 16 positions x CH channels per tile ----------------
+    const int lt = tid - FZ_LD_T0;
+    constexpr int CPR = Cf::CH / 8;                              // 16-byte chunks per position
+    constexpr int LPT = FZ_NPOS * CPR / (32 * FZ_LD_WARPS);      // chunks per thread per strip (2 / 4)
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int x0, y0, crop, c0;
+      tile_coords(tile, x0, y0, crop, c0);
+      const bf16* sc = src + (size_t)crop * h * w * C + c0;
+      const int lx0 = (x0 >> 1) - DO, ly0 = (y0 >> 1) - DO;
+      int src_off[LPT];
+      uint32_t dst_off[LPT];
+#pragma unroll
+      for (int k = 0; k < LPT; ++k) {
+        const int e = lt + k * 32 * FZ_LD_WARPS;
+        const int p = e / CPR, c8 = e % CPR;
+        const int xx = min(max(lx0 + p, 0), w - 1);              // outside the image the band weights are zero
+        src_off[k] = xx * C + c8 * 8;
+        dst_off[k] = (uint32_t)((c8 >> 3) * Cf::CHUNK_BYTES + p * 128 + (((c8 & 7) ^ (p & 7)) << 4));
+      }
+      for (int s = 0; s < NLR; ++s, ++it) {
+        const uint32_t st = it % FZ_NSTG, ph = (it / FZ_NSTG) & 1;
+        mbar_wait(a_empty0 + st * 8, ph ^ 1);
+        const int yy = min(max(ly0 + s, 0), h - 1);
+        const bf16* rowp = sc + (size_t)yy * w * C;
+        const uint32_t base = smem_base + Cf::A_OFF + st * Cf::A_STAGE;
+#pragma unroll
+        for (int k = 0; k < LPT; ++k)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + dst_off[k]), "l"(rowp + src_off[k]) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (it >= FZ_INFL - 1) {
+          asm volatile("cp.async.wait_group %0;" ::"n"(FZ_INFL - 1) : "memory");
+          fz_fence_proxy_async();
+          mbar_arrive(a_full0 + ((it - (FZ_INFL - 1)) % FZ_NSTG) * 8);
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    fz_fence_proxy_async();
+    for (uint32_t j = (it >= FZ_INFL - 1 ? it - (FZ_INFL - 1) : 0); j < it; ++j) mbar_arrive(a_full0 + (j % FZ_NSTG) * 8);
+  } else {
+    // ---------------- composite builders: warp = output row r of the tile, 16 pixels ----------------
+    const int r = warp - (FZ_EPI_WARPS + 1 + FZ_LD_WARPS);
+    const int g = lane >> 2, tig = lane & 3;
+    uint8_t* wst = smem + Cf::W_OFF + r * 16 * Cf::WROW;         // this warp's staged raw weights [16 px][WROW]
+    // B fragments of stage A: element (k = j, n = i) = k[i][j]; offsets into a pixel's weight row, -1 = padding
+    int boff[2][2][2];                                           // [n-block of i][k half of j][element]
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+      for (int kh = 0; kh < 2; ++kh)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int i = nb * 8 + g, j = kh * 8 + 2 * tig + e;
+          boff[nb][kh][e] = (i < D && j < D) ? (i * D + j) * 2 : -1;
+        }
+    uint32_t tl = 0;
+    uint4 wv[8];                                                 // next tile's weight rows (16 px x 256 B per warp)
+    auto load_weights = [&](int tile) {
+      int x0, y0, crop, c0;
+      tile_coords(tile, x0, y0, crop, c0);
+      const int y = y0 + r;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = lane + k * 32, m = e >> 4, v = e & 15, x = x0 + m;
+        wv[k] = make_uint4(0, 0, 0, 0);
+        if (y < H2 && x < W2 && v * 8 < ldk)
+          wv[k] = __ldg(reinterpret_cast<const uint4*>(kern + (((size_t)crop * H2 + y) * W2 + x) * ldk + v * 8));
+      }
+    };
+    if ((int)blockIdx.x < total_tiles) load_weights(blockIdx.x);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      int x0, y0, crop, c0;
+      tile_coords(tile, x0, y0, crop, c0);
+      const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = lane + k * 32;
+        *reinterpret_cast<uint4*>(wst + (e >> 4) * Cf::WROW + (e & 15) * 16) = wv[k];
+      }
+      __syncwarp();
+      if (tile + (int)gridDim.x < total_tiles) load_weights(tile + gridDim.x);
+      // TY^T fragments of this output row: B operand of stage B, element (k = i, n = dy) = taby[y][dy][i]
+      const int y = min(y0 + r, H2 - 1);
+      uint32_t tyb[2][2];
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh)
+          tyb[nb][kh] = __ldg(reinterpret_cast<const uint32_t*>(taby + (size_t)y * FZ_TAB + (nb * 8 + g) * 16 + kh * 8 + 2 * tig));
+      mbar_wait(b_empty0 + as * 8, aph ^ 1);
+      uint8_t* bbuf = smem + Cf::B_OFF + as * Cf::B_BUF;
+      if (tl < 2) {                                              // zero background, once per buffer
+        for (int e = tid - FZ_BB_T0; e < Cf::B_BUF / 16; e += 32 * FZ_BB_WARPS) reinterpret_cast<uint4*>(bbuf)[e] = make_uint4(0, 0, 0, 0);
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * FZ_BB_WARPS) : "memory");
+      }
+      const int sr0 = r >> 1;                                    // (y >> 1) - (y0 >> 1)
+#pragma unroll 1
+      for (int m = 0; m < 16; ++m) {
+        const int x = min(x0 + m, W2 - 1), n = r * 16 + m;
+        // stage A: T^T[dx][i] = sum_j TX^T[x][dx][j] * k[i][j]
+        uint32_t ta[4];
+        const __half* tx = tabx + (size_t)x * FZ_TAB;
+        ta[0] = __ldg(reinterpret_cast<const uint32_t*>(tx + g * 16 + 2 * tig));
+        ta[1] = __ldg(reinterpret_cast<const uint32_t*>(tx + (g + 8) * 16 + 2 * tig));
+        ta[2] = __ldg(reinterpret_cast<const uint32_t*>(tx + g * 16 + 8 + 2 * tig));
+        ta[3] = __ldg(reinterpret_cast<const uint32_t*>(tx + (g + 8) * 16 + 8 + 2 * tig));
+        const uint8_t* wrow = wst + m * Cf::WROW;
+        float tacc[2][4];
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          uint32_t kb[2];
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh) {
+            float f[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int o = boff[nb][kh][e];
+              f[e] = o >= 0 ? __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(wrow + o)) << 16) : 0.f;
+            }
+            kb[kh] = fz_pack(f[0], f[1]);
+          }
+          tacc[nb][0] = tacc[nb][1] = tacc[nb][2] = tacc[nb][3] = 0.f;
+          fz_mma_f16(tacc[nb], ta, kb[0], kb[1]);
+        }
+        // stage B: K'^T[dx][dy] = sum_i T^T[dx][i] * TY^T[y][dy][i]; the accumulators above are its A fragments
+        uint32_t a2[4] = {fz_pack(tacc[0][0], tacc[0][1]), fz_pack(tacc[0][2], tacc[0][3]),
+                          fz_pack(tacc[1][0], tacc[1][1]), fz_pack(tacc[1][2], tacc[1][3])};
+        uint8_t* rowb = bbuf + (n >> 3) * 1024 + (n & 7) * 128;
+        const int kk0 = (m >> 1);                                // (x >> 1) - (x0 >> 1)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          float kacc[4] = {0.f, 0.f, 0.f, 0.f};
+          fz_mma_f16(kacc, a2, tyb[nb][0], tyb[nb][1]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int dx = g + (e >> 1) * 8, dy = nb * 8 + 2 * tig + (e & 1);
+            if (dx <= 2 * DO && dy <= 2 * DO) {
+              const int sr = sr0 + dy, col = (sr & 3) * 16 + kk0 + dx;   // strip row, column in the 64-wide band-tile row
+              *reinterpret_cast<bf16*>(rowb + (sr >> 2) * Cf::B_QUAD + ((((col >> 3) ^ (n & 7)) << 4) | ((col & 7) << 1))) =
+                  __float2bfloat16_rn(kacc[e]);
+            }
+          }
+        }
+      }
+      fz_fence_proxy_async();
+      mbar_arrive(b_full0 + as * 8);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == FZ_EPI_WARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cf::TMEM_COLS) : "memory");
+  }
+}
+
+template <int R, int MH>
+int launch_fused(const bf16* src, int n_crops, int h, int w, int C, const bf16* kern, int ldk, bf16* dst, __half* tabs,
+                 cudaStream_t st) {
+  using Cf = FzCfg<R, MH>;
+  const int H2 = 2 * h, W2 = 2 * w;
+  __half* tabx = tabs;
+  __half* taby = tabs + (size_t)W2 * FZ_TAB;
+  cseg_launch(fz_tables_kernel, dim3(cdiv((W2 + H2) * 16, 256)), dim3(256), 0, st, W2, H2, R, tabx, taby);
+  CSEG_LAUNCH_CHECK("jbu_apply_tables");
+  CSEG_SET_SMEM((jbu_apply_fused_kernel<R, MH>), Cf::SMEM_BYTES);
+  const int nx = cdiv(W2, FZ_TX), ny = cdiv(H2, FZ_RW), nslab = C / Cf::CH;
+  const long long total = (long long)nx * ny * n_crops * nslab;
+  CSEG_REQUIRE(total < (1ll << 31), "jbu_apply(bf16): too many tiles");
+  const int grid = (int)std::min<long long>(total, sm_count());
+  cseg_launch(jbu_apply_fused_kernel<R, MH>, dim3(grid), dim3(FZ_THREADS), Cf::SMEM_BYTES, st, src, h, w, C, kern, ldk,
+              (const __half*)tabx, (const __half*)taby, dst, nx, ny, nslab, (int)total);
+  CSEG_LAUNCH_CHECK("jbu_apply_fused");
+  return 0;
+}
+
+}  // namespace
+
+// returns 1 when the shape is not covered (caller runs bicubic2x + the stand-alone adaptive conv instead).
+// scratch: the caller's hr_scratch; the first (2h + 2w) * 512 bytes hold the bicubic tables.
+int cseg_jbu_apply_fused(const bf16* src, int n_crops, int h, int w, int C, const bf16* kern, int ldk, int radius,
+                         bf16* dst, void* scratch, cudaStream_t st) {
+  if (C % 128 != 0 || ldk % 8 != 0 || (radius != 5 && radius != 3)) return 1;
+  if (h < radius + 2 || w < 12 || scratch == nullptr) return 1;          // single reflection; strips of 16 positions
+  if (((uintptr_t)src & 15) != 0 || ((uintptr_t)kern & 15) != 0 || ((uintptr_t)scratch & 15) != 0) return 1;
+  __half* tabs = (__half*)scratch;
+  if (C % 256 == 0) {
+    if (radius == 5) return launch_fused<5, 2>(src, n_crops, h, w, C, kern, ldk, dst, tabs, st);
+    return launch_fused<3, 2>(src, n_crops, h, w, C, kern, ldk, dst, tabs, st);
+  }
+  if (radius == 5) return launch_fused<5, 1>(src, n_crops, h, w, C, kern, ldk, dst, tabs, st);
+  return launch_fused<3, 1>(src, n_crops, h, w, C, kern, ldk, dst, tabs, st);
+}

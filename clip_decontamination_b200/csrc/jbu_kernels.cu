@@ -378,6 +378,16 @@ static int launch_range_kernel(const float* proj, const float* guid, int n_crops
 
 int cseg_jbu_adaptive_conv_tc(const bf16* hr, int n_crops, int H2, int W2, int C, const bf16* kern, int ldk, int radius,
                               bf16* dst, cudaStream_t st);
+int cseg_jbu_apply_fused(const bf16* src, int n_crops, int h, int w, int C, const bf16* kern, int ldk, int radius,
+                         bf16* dst, void* scratch, cudaStream_t st);
+static bool apply_fused_enabled() {  // CSEG_APPLY_FUSED=0 selects bicubic2x + the stand-alone conv (A/B measurements)
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CSEG_APPLY_FUSED");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
 static bool conv_tc_enabled() {      // CSEG_CONV_TC=0 selects the mma.sync kernel (A/B measurements)
   static int on = -1;
   if (on < 0) {
@@ -393,6 +403,11 @@ template <typename T>
 static int launch_apply(const void* src, int n_crops, int h, int w, int C, const void* kern, int ldk, int radius,
                         void* dst, void* hr_scratch, cudaStream_t st) {
   const int H2 = 2 * h, W2 = 2 * w;
+  if (sizeof(T) == 2 && apply_fused_enabled()) {   // bicubic folded into the kernel weights: one tcgen05 kernel on the low-res source
+    const int rc = cseg_jbu_apply_fused((const bf16*)src, n_crops, h, w, C, (const bf16*)kern, ldk, radius, (bf16*)dst,
+                                        hr_scratch, st);
+    if (rc <= 0) return rc;
+  }
   const long long tot_b = (long long)n_crops * ((h + 1) / 2) * ((w + 1) / 2) * (C / 4);
   cseg_launch(bicubic2x_kernel<T>, dim3((int)std::min<long long>((tot_b + 255) / 256, (long long)sm_count() * 32)), dim3(256), 0, st, 
       (const T*)src, n_crops, h, w, C, (T*)hr_scratch);
