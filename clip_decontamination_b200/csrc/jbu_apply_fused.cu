@@ -33,7 +33,6 @@ constexpr int FZ_NSTG = 6, FZ_INFL = 4;                        // strip ring sta
 constexpr int FZ_EPI_WARPS = 4, FZ_LD_WARPS = 4, FZ_BB_WARPS = 4;
 constexpr int FZ_THREADS = 32 * (FZ_EPI_WARPS + 1 + FZ_LD_WARPS + FZ_BB_WARPS);
 constexpr int FZ_LD_T0 = 32 * (FZ_EPI_WARPS + 1), FZ_BB_T0 = FZ_LD_T0 + 32 * FZ_LD_WARPS;
-constexpr int FZ_TAB = 16 * 16;                                // halves per table entry: [16][16]
 
 __device__ __forceinline__ int fz_reflect(int i, int n) {
   if (i < 0) i = -i;
@@ -60,36 +59,102 @@ __device__ __forceinline__ uint32_t fz_pack(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// Tables (fp16, one 16x16 entry per coordinate), both stored [coordinate][d][tap]:
-//   tab[c][d][t] = sum over the bicubic taps b of high-res coordinate q = reflect(c + t - R) that land on low-res
-//                  coordinate (c >> 1) + d - DO:  coeff_b(q)
-// axis 0: columns (n = W2) -> TX^T[x][dx][j];   axis 1: rows (n = H2) -> TY^T[y][dy][i]
-__global__ void fz_tables_kernel(int W2, int H2, int R, __half* __restrict__ tabx, __half* __restrict__ taby) {
+// Tables (fp16): tab(c, d, t) = sum over the bicubic taps b of high-res coordinate q = reflect(c + t - R) that land
+// on low-res coordinate (c >> 1) + d - DO of coeff_b(q); reflect padding and border clamps are resolved here.
+// Stored in mma.sync fragment order, one uint4 per (coordinate, lane):
+//   columns (n = W2): A operand of stage A, TX^T[dx][j]:  {(g, 2tig), (g+8, 2tig), (g, 2tig+8), (g+8, 2tig+8)}
+//   rows    (n = H2): B operand of stage B, TY^T[dy][i]:  {(g, 2tig), (g, 2tig+8), (g+8, 2tig), (g+8, 2tig+8)}
+// where (row, col) = (d, t) and each register packs columns col, col+1.
+__device__ __forceinline__ float fz_tab_entry(int c, int d, int t, int n, int R) {
+  const int D = 2 * R + 1, DO = (R + 3) / 2, nl = n >> 1;
+  if (t >= D) return 0.f;
+  const int q = fz_reflect(c + t - R, n), u = q >> 1, odd = q & 1;
+  float cf[4];
+  fz_cubic(odd ? 0.25f : 0.75f, cf);                   // even q = 2u: taps u-2..u+1; odd: u-1..u+2
+  float acc = 0.f;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int l = min(max(u - 2 + odd + b, 0), nl - 1);
+    if (l - (c >> 1) + DO == d) acc += cf[b];
+  }
+  return acc;
+}
+__global__ void fz_tables_kernel(int W2, int H2, int R, uint4* __restrict__ tabx, uint4* __restrict__ taby) {
   pdl_grid_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (W2 + H2) * 16) return;
-  const int t = idx & 15, cc = idx >> 4;
+  if (idx >= (W2 + H2) * 32) return;
+  const int lane = idx & 31, cc = idx >> 5, g = lane >> 2, tig = lane & 3;
   const bool rows = cc >= W2;
-  const int c = rows ? cc - W2 : cc, n = rows ? H2 : W2, nl = n >> 1, D = 2 * R + 1, DO = (R + 3) / 2;
-  __half* out = (rows ? taby : tabx) + (size_t)c * FZ_TAB;
-  float acc[16];
+  const int c = rows ? cc - W2 : cc, n = rows ? H2 : W2;
+  uint32_t r[4];
 #pragma unroll
-  for (int d = 0; d < 16; ++d) acc[d] = 0.f;
-  if (t < D) {
-    const int q = fz_reflect(c + t - R, n), u = q >> 1, odd = q & 1;
-    float cf[4];
-    fz_cubic(odd ? 0.25f : 0.75f, cf);                 // even q = 2u: taps u-2..u+1; odd: u-1..u+2
+  for (int k = 0; k < 4; ++k) {
+    const int hi_row = rows ? (k >> 1) : (k & 1), hi_col = rows ? (k & 1) : (k >> 1);
+    const int d = g + hi_row * 8, t = 2 * tig + hi_col * 8;
+    r[k] = fz_pack(fz_tab_entry(c, d, t, n, R), fz_tab_entry(c, d, t + 1, n, R));
+  }
+  (rows ? taby : tabx)[(size_t)c * 32 + lane] = make_uint4(r[0], r[1], r[2], r[3]);
+}
+
+// Composite kernels K'^T[dx][dy] of every output pixel, one warp per pixel (grid-stride):
+//   stage A  T^T[dx][i]  = sum_j TX^T[x][dx][j] * k[i][j]        (mma.sync fp16, A = table fragment, B = the weight row)
+//   stage B  K'^T[dx][dy] = sum_i T^T[dx][i] * TY^T[y][dy][i]     (the accumulators of stage A are the A fragment)
+// kc[p][dy * (2 DO + 1) + dx] (bf16, row stride 128) is what the banded GEMM scatters into its B tiles.
+template <int R>
+__global__ void __launch_bounds__(256) fz_composite_kernel(const bf16* __restrict__ kern, int ldk, long long n_px, int H2,
+                                                           int W2, const uint4* __restrict__ tabx,
+                                                           const uint4* __restrict__ taby, bf16* __restrict__ kc) {
+  pdl_grid_sync();
+  constexpr int D = 2 * R + 1, DO = (R + 3) / 2, DC = 2 * DO + 1;
+  const int lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+  int boff[2][2][2];                                           // [n-block of i][k half of j][element]; -1 = padding
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int l = min(max(u - 2 + odd + b, 0), nl - 1);
-      const int d = l - (c >> 1) + DO;                 // in [0, 2 DO] by construction
+  for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
-      for (int dd = 0; dd < 16; ++dd)
-        if (dd == d) acc[dd] += cf[b];
+    for (int kh = 0; kh < 2; ++kh)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = nb * 8 + g, j = kh * 8 + 2 * tig + e;
+        boff[nb][kh][e] = (i < D && j < D) ? i * D + j : -1;
+      }
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p = warp0; p < n_px; p += nwarps) {
+    const int x = (int)(p % W2), y = (int)((p / W2) % H2);
+    const uint4 txv = __ldg(tabx + (size_t)x * 32 + lane), tyv = __ldg(taby + (size_t)y * 32 + lane);
+    const uint32_t ta[4] = {txv.x, txv.y, txv.z, txv.w};
+    const uint32_t tyb[2][2] = {{tyv.x, tyv.y}, {tyv.z, tyv.w}};
+    const unsigned short* wrow = reinterpret_cast<const unsigned short*>(kern + p * ldk);
+    float tacc[2][4];
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb) {
+      uint32_t kb[2];
+#pragma unroll
+      for (int kh = 0; kh < 2; ++kh) {
+        float f[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int o = boff[nb][kh][e];
+          f[e] = o >= 0 ? __uint_as_float((uint32_t)__ldg(wrow + o) << 16) : 0.f;
+        }
+        kb[kh] = fz_pack(f[0], f[1]);
+      }
+      tacc[nb][0] = tacc[nb][1] = tacc[nb][2] = tacc[nb][3] = 0.f;
+      fz_mma_f16(tacc[nb], ta, kb[0], kb[1]);
+    }
+    const uint32_t a2[4] = {fz_pack(tacc[0][0], tacc[0][1]), fz_pack(tacc[0][2], tacc[0][3]),
+                            fz_pack(tacc[1][0], tacc[1][1]), fz_pack(tacc[1][2], tacc[1][3])};
+    bf16* orow = kc + p * 128;
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb) {
+      float kacc[4] = {0.f, 0.f, 0.f, 0.f};
+      fz_mma_f16(kacc, a2, tyb[nb][0], tyb[nb][1]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int dx = g + (e >> 1) * 8, dy = nb * 8 + 2 * tig + (e & 1);
+        if (dx < DC && dy < DC) orow[dy * DC + dx] = __float2bfloat16_rn(kacc[e]);
+      }
     }
   }
-#pragma unroll
-  for (int d = 0; d < 16; ++d) out[d * 16 + t] = __float2half_rn(acc[d]);
 }
 
 __device__ __forceinline__ uint64_t fz_adesc(uint32_t saddr, uint32_t lbo_bytes) {   // MN-major SWIZZLE_128B (jbu_apply_tc.cu)
@@ -114,9 +179,7 @@ struct FzCfg {
   static constexpr int CHUNK_BYTES = FZ_NPOS * 128;               // one 64-channel chunk of a strip (16 rows x 128 B)
   static constexpr int A_STAGE = (CH / 64) * CHUNK_BYTES;         // 4 / 8 KB
   static constexpr int B_QUAD = FZ_NPX * 128, B_BUF = NQUAD * B_QUAD;
-  static constexpr int WROW = 256 + 16;                           // staged raw weights: bytes per pixel row (padded)
-  static constexpr int W_STAGE = FZ_BB_WARPS * 16 * WROW;
-  static constexpr int A_OFF = 0, B_OFF = FZ_NSTG * A_STAGE, W_OFF = B_OFF + 2 * B_BUF, BAR_OFF = W_OFF + W_STAGE;
+  static constexpr int A_OFF = 0, B_OFF = FZ_NSTG * A_STAGE, BAR_OFF = B_OFF + 2 * B_BUF;
   static constexpr int NBARS = 2 * FZ_NSTG + 8;
   static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = (2 * MH * FZ_NPX <= 128) ? 128 : 256;
@@ -124,11 +187,10 @@ struct FzCfg {
 
 template <int R, int MH>
 __global__ void __launch_bounds__(FZ_THREADS, 1)
-jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const bf16* __restrict__ kern, int ldk,
-                       const __half* __restrict__ tabx, const __half* __restrict__ taby, bf16* __restrict__ dst, int nx,
-                       int ny, int nslab, int total_tiles) {
+jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const bf16* __restrict__ kc,
+                       bf16* __restrict__ dst, int nx, int ny, int nslab, int total_tiles) {
   using Cf = FzCfg<R, MH>;
-  constexpr int D = Cf::D, DO = Cf::DO, NLR = Cf::NLR;
+  constexpr int DO = Cf::DO, NLR = Cf::NLR;
   const int H2 = 2 * h, W2 = 2 * w;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -278,109 +340,46 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
     fz_fence_proxy_async();
     for (uint32_t j = (it >= FZ_INFL - 1 ? it - (FZ_INFL - 1) : 0); j < it; ++j) mbar_arrive(a_full0 + (j % FZ_NSTG) * 8);
   } else {
-    // ---------------- composite builders: warp = output row r of the tile, 16 pixels ----------------
-    const int r = warp - (FZ_EPI_WARPS + 1 + FZ_LD_WARPS);
-    const int g = lane >> 2, tig = lane & 3;
-    uint8_t* wst = smem + Cf::W_OFF + r * 16 * Cf::WROW;         // this warp's staged raw weights [16 px][WROW]
-    // B fragments of stage A: element (k = j, n = i) = k[i][j]; offsets into a pixel's weight row, -1 = padding
-    int boff[2][2][2];                                           // [n-block of i][k half of j][element]
-#pragma unroll
-    for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-      for (int kh = 0; kh < 2; ++kh)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int i = nb * 8 + g, j = kh * 8 + 2 * tig + e;
-          boff[nb][kh][e] = (i < D && j < D) ? (i * D + j) * 2 : -1;
-        }
+    // ---------------- band builders: scatter the composite kernels of the tile's 64 pixels ----------------
+    const int bt = tid - FZ_BB_T0;                               // 0..127
+    constexpr int DC = 2 * DO + 1, NCH = (DC * DC + 7) / 8;      // 16-byte chunks per composite kernel (11 / 7)
+    constexpr int WPT = (FZ_NPX * NCH + 32 * FZ_BB_WARPS - 1) / (32 * FZ_BB_WARPS);
     uint32_t tl = 0;
-    uint4 wv[8];                                                 // next tile's weight rows (16 px x 256 B per warp)
-    auto load_weights = [&](int tile) {
-      int x0, y0, crop, c0;
-      tile_coords(tile, x0, y0, crop, c0);
-      const int y = y0 + r;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int e = lane + k * 32, m = e >> 4, v = e & 15, x = x0 + m;
-        wv[k] = make_uint4(0, 0, 0, 0);
-        if (y < H2 && x < W2 && v * 8 < ldk)
-          wv[k] = __ldg(reinterpret_cast<const uint4*>(kern + (((size_t)crop * H2 + y) * W2 + x) * ldk + v * 8));
-      }
-    };
-    if ((int)blockIdx.x < total_tiles) load_weights(blockIdx.x);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
       int x0, y0, crop, c0;
       tile_coords(tile, x0, y0, crop, c0);
       const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
-      __syncwarp();
+      uint4 wv[WPT];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int e = lane + k * 32;
-        *reinterpret_cast<uint4*>(wst + (e >> 4) * Cf::WROW + (e & 15) * 16) = wv[k];
+      for (int k = 0; k < WPT; ++k) {
+        const int e = bt + k * 32 * FZ_BB_WARPS, n = e / NCH, v = e - n * NCH;
+        const int y = y0 + (n >> 4), x = x0 + (n & 15);
+        wv[k] = make_uint4(0, 0, 0, 0);                          // pixels outside the image: zero weights
+        if (n < FZ_NPX && y < H2 && x < W2)
+          wv[k] = __ldg(reinterpret_cast<const uint4*>(kc + (((size_t)crop * H2 + y) * W2 + x) * 128 + v * 8));
       }
-      __syncwarp();
-      if (tile + (int)gridDim.x < total_tiles) load_weights(tile + gridDim.x);
-      // TY^T fragments of this output row: B operand of stage B, element (k = i, n = dy) = taby[y][dy][i]
-      const int y = min(y0 + r, H2 - 1);
-      uint32_t tyb[2][2];
-#pragma unroll
-      for (int nb = 0; nb < 2; ++nb)
-#pragma unroll
-        for (int kh = 0; kh < 2; ++kh)
-          tyb[nb][kh] = __ldg(reinterpret_cast<const uint32_t*>(taby + (size_t)y * FZ_TAB + (nb * 8 + g) * 16 + kh * 8 + 2 * tig));
       mbar_wait(b_empty0 + as * 8, aph ^ 1);
       uint8_t* bbuf = smem + Cf::B_OFF + as * Cf::B_BUF;
       if (tl < 2) {                                              // zero background, once per buffer
-        for (int e = tid - FZ_BB_T0; e < Cf::B_BUF / 16; e += 32 * FZ_BB_WARPS) reinterpret_cast<uint4*>(bbuf)[e] = make_uint4(0, 0, 0, 0);
+        for (int e = bt; e < Cf::B_BUF / 16; e += 32 * FZ_BB_WARPS) reinterpret_cast<uint4*>(bbuf)[e] = make_uint4(0, 0, 0, 0);
         asm volatile("bar.sync 2, %0;" ::"n"(32 * FZ_BB_WARPS) : "memory");
       }
-      const int sr0 = r >> 1;                                    // (y >> 1) - (y0 >> 1)
-#pragma unroll 1
-      for (int m = 0; m < 16; ++m) {
-        const int x = min(x0 + m, W2 - 1), n = r * 16 + m;
-        // stage A: T^T[dx][i] = sum_j TX^T[x][dx][j] * k[i][j]
-        uint32_t ta[4];
-        const __half* tx = tabx + (size_t)x * FZ_TAB;
-        ta[0] = __ldg(reinterpret_cast<const uint32_t*>(tx + g * 16 + 2 * tig));
-        ta[1] = __ldg(reinterpret_cast<const uint32_t*>(tx + (g + 8) * 16 + 2 * tig));
-        ta[2] = __ldg(reinterpret_cast<const uint32_t*>(tx + g * 16 + 8 + 2 * tig));
-        ta[3] = __ldg(reinterpret_cast<const uint32_t*>(tx + (g + 8) * 16 + 8 + 2 * tig));
-        const uint8_t* wrow = wst + m * Cf::WROW;
-        float tacc[2][4];
 #pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
-          uint32_t kb[2];
-#pragma unroll
-          for (int kh = 0; kh < 2; ++kh) {
-            float f[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int o = boff[nb][kh][e];
-              f[e] = o >= 0 ? __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(wrow + o)) << 16) : 0.f;
-            }
-            kb[kh] = fz_pack(f[0], f[1]);
-          }
-          tacc[nb][0] = tacc[nb][1] = tacc[nb][2] = tacc[nb][3] = 0.f;
-          fz_mma_f16(tacc[nb], ta, kb[0], kb[1]);
-        }
-        // stage B: K'^T[dx][dy] = sum_i T^T[dx][i] * TY^T[y][dy][i]; the accumulators above are its A fragments
-        uint32_t a2[4] = {fz_pack(tacc[0][0], tacc[0][1]), fz_pack(tacc[0][2], tacc[0][3]),
-                          fz_pack(tacc[1][0], tacc[1][1]), fz_pack(tacc[1][2], tacc[1][3])};
+      for (int k = 0; k < WPT; ++k) {
+        const int e = bt + k * 32 * FZ_BB_WARPS, n = e / NCH, v = e - n * NCH;
+        if (n >= FZ_NPX) continue;
+        const int r = n >> 4, m = n & 15;
+        const unsigned short* hv = reinterpret_cast<const unsigned short*>(&wv[k]);
         uint8_t* rowb = bbuf + (n >> 3) * 1024 + (n & 7) * 128;
-        const int kk0 = (m >> 1);                                // (x >> 1) - (x0 >> 1)
+        const int sr0 = r >> 1, kk0 = m >> 1;                    // (y >> 1) - (y0 >> 1), (x >> 1) - (x0 >> 1)
 #pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
-          float kacc[4] = {0.f, 0.f, 0.f, 0.f};
-          fz_mma_f16(kacc, a2, tyb[nb][0], tyb[nb][1]);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int dx = g + (e >> 1) * 8, dy = nb * 8 + 2 * tig + (e & 1);
-            if (dx <= 2 * DO && dy <= 2 * DO) {
-              const int sr = sr0 + dy, col = (sr & 3) * 16 + kk0 + dx;   // strip row, column in the 64-wide band-tile row
-              *reinterpret_cast<bf16*>(rowb + (sr >> 2) * Cf::B_QUAD + ((((col >> 3) ^ (n & 7)) << 4) | ((col & 7) << 1))) =
-                  __float2bfloat16_rn(kacc[e]);
-            }
-          }
+        for (int q = 0; q < 8; ++q) {
+          const int t = v * 8 + q;
+          if (t >= DC * DC) continue;
+          const int dy = (t * 57) >> 9;                          // t / 9 for t < 128 (DC == 9); exact division below otherwise
+          const int dyy = (DC == 9) ? dy : t / DC, dx = t - dyy * DC;
+          const int sr = sr0 + dyy, col = (sr & 3) * 16 + kk0 + dx;
+          *reinterpret_cast<unsigned short*>(rowb + (sr >> 2) * Cf::B_QUAD + ((((col >> 3) ^ (n & 7)) << 4) | ((col & 7) << 1))) = hv[q];
         }
       }
       fz_fence_proxy_async();
@@ -395,21 +394,27 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
 }
 
 template <int R, int MH>
-int launch_fused(const bf16* src, int n_crops, int h, int w, int C, const bf16* kern, int ldk, bf16* dst, __half* tabs,
+int launch_fused(const bf16* src, int n_crops, int h, int w, int C, const bf16* kern, int ldk, bf16* dst, uint8_t* scratch,
                  cudaStream_t st) {
   using Cf = FzCfg<R, MH>;
   const int H2 = 2 * h, W2 = 2 * w;
-  __half* tabx = tabs;
-  __half* taby = tabs + (size_t)W2 * FZ_TAB;
-  cseg_launch(fz_tables_kernel, dim3(cdiv((W2 + H2) * 16, 256)), dim3(256), 0, st, W2, H2, R, tabx, taby);
+  const long long n_px = (long long)n_crops * H2 * W2;
+  bf16* kc = reinterpret_cast<bf16*>(scratch);                       // composite kernels [n_px, 128]
+  uint4* tabx = reinterpret_cast<uint4*>(scratch + n_px * 256);      // then the bicubic tables
+  uint4* taby = tabx + (size_t)W2 * 32;
+  cseg_launch(fz_tables_kernel, dim3(cdiv((W2 + H2) * 32, 256)), dim3(256), 0, st, W2, H2, R, tabx, taby);
   CSEG_LAUNCH_CHECK("jbu_apply_tables");
+  const int cblocks = (int)std::min<long long>(cdiv(n_px, 8), (long long)sm_count() * 8);
+  cseg_launch(fz_composite_kernel<R>, dim3(cblocks), dim3(256), 0, st, kern, ldk, n_px, H2, W2, (const uint4*)tabx,
+              (const uint4*)taby, kc);
+  CSEG_LAUNCH_CHECK("jbu_apply_composite");
   CSEG_SET_SMEM((jbu_apply_fused_kernel<R, MH>), Cf::SMEM_BYTES);
   const int nx = cdiv(W2, FZ_TX), ny = cdiv(H2, FZ_RW), nslab = C / Cf::CH;
   const long long total = (long long)nx * ny * n_crops * nslab;
   CSEG_REQUIRE(total < (1ll << 31), "jbu_apply(bf16): too many tiles");
   const int grid = (int)std::min<long long>(total, sm_count());
-  cseg_launch(jbu_apply_fused_kernel<R, MH>, dim3(grid), dim3(FZ_THREADS), Cf::SMEM_BYTES, st, src, h, w, C, kern, ldk,
-              (const __half*)tabx, (const __half*)taby, dst, nx, ny, nslab, (int)total);
+  cseg_launch(jbu_apply_fused_kernel<R, MH>, dim3(grid), dim3(FZ_THREADS), Cf::SMEM_BYTES, st, src, h, w, C, (const bf16*)kc,
+              dst, nx, ny, nslab, (int)total);
   CSEG_LAUNCH_CHECK("jbu_apply_fused");
   return 0;
 }
@@ -417,13 +422,15 @@ int launch_fused(const bf16* src, int n_crops, int h, int w, int C, const bf16* 
 }  // namespace
 
 // returns 1 when the shape is not covered (caller runs bicubic2x + the stand-alone adaptive conv instead).
-// scratch: the caller's hr_scratch; the first (2h + 2w) * 512 bytes hold the bicubic tables.
+// scratch: the caller's hr_scratch (n * 2h * 2w * C elements >= what is used here): composite kernels
+// [n * 2h * 2w, 128] bf16, then (2h + 2w) * 512 bytes of bicubic tables.
 int cseg_jbu_apply_fused(const bf16* src, int n_crops, int h, int w, int C, const bf16* kern, int ldk, int radius,
                          bf16* dst, void* scratch, cudaStream_t st) {
   if (C % 128 != 0 || ldk % 8 != 0 || (radius != 5 && radius != 3)) return 1;
   if (h < radius + 2 || w < 12 || scratch == nullptr) return 1;          // single reflection; strips of 16 positions
+  if ((long long)C * 2 < 256 + 16) return 1;                             // scratch holds 256 B per pixel + the tables
   if (((uintptr_t)src & 15) != 0 || ((uintptr_t)kern & 15) != 0 || ((uintptr_t)scratch & 15) != 0) return 1;
-  __half* tabs = (__half*)scratch;
+  uint8_t* tabs = (uint8_t*)scratch;
   if (C % 256 == 0) {
     if (radius == 5) return launch_fused<5, 2>(src, n_crops, h, w, C, kern, ldk, dst, tabs, st);
     return launch_fused<3, 2>(src, n_crops, h, w, C, kern, ldk, dst, tabs, st);
