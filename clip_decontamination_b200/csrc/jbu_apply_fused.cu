@@ -117,9 +117,15 @@ __global__ void __launch_bounds__(256) fz_composite_kernel(const bf16* __restric
         const int i = nb * 8 + g, j = kh * 8 + 2 * tig + e;
         boff[nb][kh][e] = (i < D && j < D) ? i * D + j : -1;
       }
+  // every warp takes a contiguous run of pixels, so (x, y) advance incrementally (no per-pixel divisions)
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long p = warp0; p < n_px; p += nwarps) {
-    const int x = (int)(p % W2), y = (int)((p / W2) % H2);
+  const long long per = (n_px + nwarps - 1) / nwarps, p_begin = warp0 * per, p_end = min(n_px, p_begin + per);
+  int x = (int)(p_begin % W2), y = (int)((p_begin / W2) % H2);
+  for (long long p = p_begin; p < p_end; ++p, ++x) {
+    if (x == W2) {
+      x = 0;
+      if (++y == H2) y = 0;
+    }
     const uint4 txv = __ldg(tabx + (size_t)x * 32 + lane), tyv = __ldg(taby + (size_t)y * 32 + lane);
     const uint32_t ta[4] = {txv.x, txv.y, txv.z, txv.w};
     const uint32_t tyb[2][2] = {{tyv.x, tyv.y}, {tyv.z, tyv.w}};
@@ -130,13 +136,9 @@ __global__ void __launch_bounds__(256) fz_composite_kernel(const bf16* __restric
       uint32_t kb[2];
 #pragma unroll
       for (int kh = 0; kh < 2; ++kh) {
-        float f[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int o = boff[nb][kh][e];
-          f[e] = o >= 0 ? __uint_as_float((uint32_t)__ldg(wrow + o) << 16) : 0.f;
-        }
-        kb[kh] = fz_pack(f[0], f[1]);
+        const int o0 = boff[nb][kh][0], o1 = boff[nb][kh][1];
+        const uint32_t lo = o0 >= 0 ? (uint32_t)__ldg(wrow + o0) : 0u, hi = o1 >= 0 ? (uint32_t)__ldg(wrow + o1) : 0u;
+        kb[kh] = fz_pack(__uint_as_float(lo << 16), __uint_as_float(hi << 16));
       }
       tacc[nb][0] = tacc[nb][1] = tacc[nb][2] = tacc[nb][3] = 0.f;
       fz_mma_f16(tacc[nb], ta, kb[0], kb[1]);
