@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(BlCfg::THREADS, 1)
 basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
                     const __grid_constant__ CUtensorMap tmB2, int panels, int hw, int tstride, int KS,
                     const bf16* __restrict__ s, int lds, const float* __restrict__ consts, int Q,
-                    const float* __restrict__ cls_bias, float* __restrict__ logits) {
+                    const float* __restrict__ cls_bias, float* __restrict__ logits, int n2) {
   using Cf = BlCfg;
   constexpr int STAGES = Cf::STAGES;
   constexpr uint32_t ACC = 2;
@@ -676,7 +676,7 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t b1_bytes = (uint32_t)(N1 * BK * 2);
-      const uint32_t b_tx = (uint32_t)num_kb * (b1_bytes + (uint32_t)(Cf::N2 * BK * 2));
+      const uint32_t b_tx = (uint32_t)num_kb * (b1_bytes + (uint32_t)(n2 * BK * 2));
       uint32_t it = 0;
       int cur_crop = -1;
       for (int panel = p_begin; panel < p_end; ++panel) {
@@ -703,7 +703,7 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BM, N1 + Cf::N2);
+      const uint32_t idesc = make_idesc(BM, N1 + n2);
       uint32_t it = 0, tl = 0, nb = 0;
       int cur_crop = -1;
       for (int panel = p_begin; panel < p_end; ++panel, ++tl) {
@@ -769,10 +769,14 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
-      uint32_t nr[16];
+      uint32_t nr[16], nr2[16];                            // aux columns 0..15 (and 16..31 when Q + 1 > 16)
       if (cg == 3) {
         __syncwarp();
         tmem_ld16(trow + (uint32_t)N1, nr);
+        if (n2 > 16) {
+          __syncwarp();
+          tmem_ld16(trow + (uint32_t)N1 + 16, nr2);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -784,18 +788,29 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int r128 = lg * 32 + lane;
         float hb = 0.f;                                    // aux column Q = s . (g b); select keeps nr[] in registers
 #pragma unroll
-        for (int q = 0; q < 16; ++q)
+        for (int q = 0; q < 16; ++q) {
           if (q == Q) hb = __uint_as_float(nr[q]);
+          if (n2 > 16 && q + 16 == Q) hb = __uint_as_float(nr2[q]);
+        }
         const float d2 = pb[r128] + pb[128 + r128] + pb[256 + r128] + pb[384 + r128] + 2.f * hb + __ldg(consts + Q);
         const float inv = 1.0f / sqrtf(fmaxf(d2, 1e-30f));
         const size_t crop = row / hw, pix = row % hw;
 #pragma unroll
-        for (int q = 0; q < 15; ++q)
+        for (int q = 0; q < 16; ++q)
           if (q < Q) {
             float v = (__uint_as_float(nr[q]) + __ldg(consts + q)) * inv;
             if (cls_bias) v += cls_bias[crop * Q + q];
             logits[(crop * Q + q) * hw + pix] = v;
           }
+        if (n2 > 16) {
+#pragma unroll
+          for (int q = 0; q < 15; ++q)
+            if (q + 16 < Q) {
+              float v = (__uint_as_float(nr2[q]) + __ldg(consts + q + 16)) * inv;
+              if (cls_bias) v += cls_bias[crop * Q + q + 16];
+              logits[(crop * Q + q + 16) * hw + pix] = v;
+            }
+        }
       }
       // the part buffer alternates per panel; a buffer is rewritten two panels later, after another bar.sync
     }
@@ -1071,10 +1086,12 @@ int cseg_basis_logits_tc(const void* s, int lds, int Cb, int n_crops, int hw, in
                          const void* aux, int ldg, const float* consts, int Q, const float* cls_bias, float* logits,
                          cudaStream_t st) {
   CSEG_REQUIRE(n_crops > 0 && hw > 0 && hw % BM == 0, "basis_logits: hw=%d must be a positive multiple of %d", hw, BM);
-  CSEG_REQUIRE(T > 0 && T <= 240 && tstride >= T && tstride % 8 == 0,
-               "basis_logits: T=%d (tokens per crop) must be in 1..240, tstride=%d >= T and a multiple of 8 (TMA)", T, tstride);
-  CSEG_REQUIRE(Q > 0 && Q <= 15, "basis_logits: Q=%d must be in 1..15", Q);
+  CSEG_REQUIRE(Q > 0 && Q <= 31, "basis_logits: Q=%d must be in 1..31", Q);
+  const int n2 = Q + 1 <= 16 ? 16 : 32;                 // aux rows: Q text rows + the bias row
+  CSEG_REQUIRE(T > 0 && T <= 256 - n2 && tstride >= T && tstride % 8 == 0,
+               "basis_logits: T=%d (tokens per crop) must be in 1..%d, tstride=%d >= T and a multiple of 8 (TMA)", T, 256 - n2, tstride);
   const int KS = cdiv(T, 16);
+  CSEG_REQUIRE(KS * 16 + n2 <= 256, "basis_logits: T=%d with Q=%d needs %d accumulator columns (max 256)", T, Q, KS * 16 + n2);
   CSEG_REQUIRE(Cb >= KS * 16 && lds >= Cb, "basis_logits: coefficient rows need >= %d columns (Cb=%d, lds=%d)", KS * 16, Cb, lds);
   CSEG_REQUIRE(lds % 8 == 0 && ldg % 8 == 0, "basis_logits: lds=%d, ldg=%d must be multiples of 8", lds, ldg);
   CSEG_REQUIRE(((uintptr_t)s & 15) == 0 && ((uintptr_t)gram & 15) == 0 && ((uintptr_t)aux & 15) == 0,
@@ -1086,12 +1103,12 @@ int cseg_basis_logits_tc(const void* s, int lds, int Cb, int n_crops, int hw, in
   if (rc) return rc;
   rc = make_map(&tb1, gram, n_crops * tstride, ldg, ldg, KS * 16);
   if (rc) return rc;
-  rc = make_map(&tb2, aux, BlCfg::N2, ldg, ldg, BlCfg::N2);
+  rc = make_map(&tb2, aux, n2, ldg, ldg, n2);
   if (rc) return rc;
   CSEG_SET_SMEM(basis_logits_kernel, BlCfg::SMEM_BYTES);
   const int panels = (int)(M / BM);
   cseg_launch(basis_logits_kernel, dim3(std::min(panels, sm_count())), dim3(BlCfg::THREADS), BlCfg::SMEM_BYTES, st, 
-      ta, tb1, tb2, panels, hw, tstride, KS, (const bf16*)s, lds, consts, Q, cls_bias, logits);
+      ta, tb1, tb2, panels, hw, tstride, KS, (const bf16*)s, lds, consts, Q, cls_bias, logits, n2);
   CSEG_LAUNCH_CHECK("basis_logits");
   return 0;
 }

@@ -321,8 +321,9 @@ class JBUEngine:
         """The stack is linear in its source and treats all channels alike, so for P tokens per crop < C it is
         cheaper to upsample one-hot token indicators (width round_up(P, 64)) and contract with the P x P Gram
         matrix of the token features afterwards.  bf16 only; fp32 stays on the literal path."""
-        return (self.cdt == torch.bfloat16 and P <= 240 and max(128, _round_up(P, 64)) < self.C
-                and hw % 128 == 0 and Q <= 15 and self.C % 8 == 0)
+        n2 = 16 if Q + 1 <= 16 else 32
+        return (self.cdt == torch.bfloat16 and _round_up(P, 16) + n2 <= 256 and max(128, _round_up(P, 64)) < self.C
+                and hw % 128 == 0 and Q <= 31 and self.C % 8 == 0)
 
     def _basis_state(self, n: int, P: int, text: torch.Tensor) -> dict:
         key = (n, P, text.data_ptr())
@@ -334,14 +335,15 @@ class JBUEngine:
             eye[:, torch.arange(P), torch.arange(P)] = 1
             ldg = _round_up(n * Tp + 8, 8)
             b = 0.1 * self.b_fin                                   # bias of the final fix-up, upsamplers.py:325
-            tb = torch.zeros(16, C, device=dev, dtype=torch.float32)
+            n2 = 16 if Q + 1 <= 16 else 32
+            tb = torch.zeros(n2, C, device=dev, dtype=torch.float32)
             tb[:Q] = text
             tb[Q] = b
             consts = torch.cat([text @ b, (b @ b).reshape(1)]).contiguous()
             st = dict(Cb=Cb, Tp=Tp, ldg=ldg, eye=eye.reshape(n * P, Cb), tb=tb.to(self.cdt).contiguous(), consts=consts,
                       g=torch.zeros(n * Tp, C, device=dev, dtype=self.cdt),
                       gram=torch.zeros(n * Tp, ldg, device=dev, dtype=self.cdt),
-                      aux=torch.zeros(16, ldg, device=dev, dtype=self.cdt))
+                      aux=torch.zeros(n2, ldg, device=dev, dtype=self.cdt))
             if not hasattr(self, '_basis'):
                 self._basis = {}
             self._basis[key] = st

@@ -177,8 +177,9 @@ CSEG_API int cseg_jbu_kernel_fixup(int dtype, const void* k, int lda, const void
  * s    bf16 [n_crops*hw, lds], Cb valid columns (>= 16*ceil(T/16); columns >= T are zero), hw % 128 == 0
  * gram bf16 [n_crops*tstride, ldg]: gram[crop*tstride + j, crop*tstride + k] = <g[crop, j], g[crop, k]> (only the
  *      diagonal blocks are read; entries that pair a token with padding or with another crop may hold anything finite)
- * aux  bf16 [16, ldg]: aux[q, crop*tstride + k] = <g[crop, k], text[q]> (q < Q), row Q = <g[crop, k], b>
- * consts fp32 [Q+1]: <b, text[q]>, then <b, b>.    T <= 240 tokens per crop, Q <= 15, tstride % 8 == 0
+ * aux  bf16 [16 or 32, ldg] (32 rows when Q + 1 > 16): aux[q, crop*tstride + k] = <g[crop, k], text[q]> (q < Q),
+ *      row Q = <g[crop, k], b>
+ * consts fp32 [Q+1]: <b, text[q]>, then <b, b>.    16*ceil(T/16) + (Q < 16 ? 16 : 32) <= 256, Q <= 31, tstride % 8 == 0
  * (TMA box origins must be 16-byte aligned).
  * logits fp32 [n_crops, Q, hw] = cosine (+ cls_logit_bias[crop, q], segmentor.py:378-379). */
 CSEG_API int cseg_basis_logits(int dtype, const void* s, int lds, int Cb, int n_crops, int hw, int T, int tstride,

@@ -407,7 +407,7 @@ def test_jbu_kernel_fixup(ops, ldk, M):
 
 
 @pytest.mark.parametrize('T,Cb,Q,n,hw', [(196, 256, 6, 3, 384), (240, 256, 15, 2, 256), (16, 128, 1, 2, 128),
-                                          (49, 128, 7, 5, 640)])
+                                          (49, 128, 7, 5, 640), (196, 256, 16, 2, 256), (100, 128, 31, 2, 128)])
 def test_basis_logits(ops, T, Cb, Q, n, hw):
     """cosine logits from basis coefficients == normalise(S . g + b) . text^T (segmentor.py:374-379) for the same
     bf16 operands; tolerance 2e-3 (bf16 Gram / aux rounding).  T = 240 is the widest tile (N = 256)."""
@@ -424,7 +424,7 @@ def test_basis_logits(ops, T, Cb, Q, n, hw):
     Tp = (T + 7) // 8 * 8                       # per-crop column blocks start on 16-byte boundaries (TMA)
     ldg = (n * Tp + 15) // 8 * 8
     gram = torch.randn(n * Tp, ldg, generator=_g(7))        # off-diagonal blocks / padding: finite garbage
-    aux = torch.zeros(16, ldg)
+    aux = torch.zeros(16 if Q + 1 <= 16 else 32, ldg)
     for c in range(n):
         gf = g[c].float()
         gram[c * Tp:c * Tp + T, c * Tp:c * Tp + T] = gf @ gf.t()
