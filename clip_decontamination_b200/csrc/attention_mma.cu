@@ -16,7 +16,8 @@ namespace {
 
 constexpr int HD = 64;
 constexpr int RSTRIDE = HD * 2 + 16;  // bytes per staged row (padded: conflict-free ldmatrix)
-constexpr int AWARPS = 4;            // one 16-row block per warp; ceil(L/64) CTAs per (crop, head), 2 CTAs per SM
+constexpr int AWARPS = 4;            // general modes: one 16-row block per warp, ceil(L/64) CTAs per (crop, head)
+constexpr int SWARPS = 8;            // STD layers: ONE CTA of 8 warps per (crop, head), Q/K/V staged once
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -122,17 +123,21 @@ __device__ __forceinline__ void add_simmap(float (&S)[NKB][4], const float* __re
   }
 }
 
-template <int NKB>
-__global__ void __launch_bounds__(AWARPS * 32, 2) attention_mma_kernel(const bf16* __restrict__ qkv, int L, int heads,
-                                                                       int mode, const float* __restrict__ simmap,
-                                                                       float simw, bf16* __restrict__ out,
-                                                                       float* __restrict__ stats) {
+// STD = true: compile-time plain softmax(q k^T s) v (11 of the 12 ViT-B layers): no mode branches, no similarity
+// map, one pass -- and one CTA of NW = 8 warps per (crop, head), so Q/K/V are staged once instead of once per
+// 64-row split.  STD = false: every custom_attn variant, NW = 4 warps per 64-row split.
+template <int NKB, int NW, bool STD>
+__global__ void __launch_bounds__(NW * 32, (NW * NKB > 8 * 26) ? 1 : 2) attention_mma_kernel(const bf16* __restrict__ qkv, int L, int heads,
+                                                                   int mode_rt, int nsplit, const float* __restrict__ simmap,
+                                                                   float simw, bf16* __restrict__ out,
+                                                                   float* __restrict__ stats) {
   pdl_grid_sync();
+  const int mode = STD ? (int)CSEG_ATTN_STD : mode_rt;
+  constexpr int AWARPS = NW;
   constexpr int LP = NKB * 8;  // padded key count (multiple of 16)
   extern __shared__ __align__(16) uint8_t asmem[];
   const uint32_t qt = (uint32_t)__cvta_generic_to_shared(asmem);
   const uint32_t kt = qt + LP * RSTRIDE, vt = kt + LP * RSTRIDE;
-  const int nsplit = (L + 16 * AWARPS - 1) / (16 * AWARPS);
   const int split = blockIdx.x % nsplit, ch = blockIdx.x / nsplit;
   const int crop = ch / heads, head = ch % heads;
   const int width = heads * HD;
@@ -248,9 +253,16 @@ template <int NKB>
 int launch(const bf16* qkv, int n_crops, int L, int heads, int mode, const float* simmap, float simw, bf16* out,
            float* stats, cudaStream_t st) {
   const int smem = 3 * NKB * 8 * RSTRIDE;
-  CSEG_SET_SMEM(attention_mma_kernel<NKB>, smem);
-  const int nsplit = (L + 16 * AWARPS - 1) / (16 * AWARPS);
-  cseg_launch(attention_mma_kernel<NKB>, dim3(n_crops * heads * nsplit), dim3(AWARPS * 32), smem, st, qkv, L, heads, mode, simmap, simw, out, stats);
+  if (mode == CSEG_ATTN_STD) {
+    CSEG_SET_SMEM((attention_mma_kernel<NKB, SWARPS, true>), smem);
+    cseg_launch(attention_mma_kernel<NKB, SWARPS, true>, dim3(n_crops * heads), dim3(SWARPS * 32), smem, st, qkv, L, heads, mode,
+                1, simmap, simw, out, stats);
+  } else {
+    CSEG_SET_SMEM((attention_mma_kernel<NKB, AWARPS, false>), smem);
+    const int nsplit = (L + 16 * AWARPS - 1) / (16 * AWARPS);
+    cseg_launch(attention_mma_kernel<NKB, AWARPS, false>, dim3(n_crops * heads * nsplit), dim3(AWARPS * 32), smem, st, qkv, L,
+                heads, mode, nsplit, simmap, simw, out, stats);
+  }
   CSEG_LAUNCH_CHECK("attention_mma");
   return 0;
 }
