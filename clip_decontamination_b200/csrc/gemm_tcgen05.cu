@@ -654,7 +654,7 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(full0 + i * 8, 1);
-      mbar_init(empty0 + i * 8, 1);
+      mbar_init(empty0 + i * 8, 1 + Cf::EPI_WARPS);    // the MMA commit and every epilogue warp (reads its coefficients)
     }
     for (int i = 0; i < (int)ACC; ++i) {
       mbar_init(tfull0 + i * 8, 1);
@@ -733,20 +733,28 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     const int ew = warp - 2, lg = warp & 3, cg = ew >> 2;
-    uint32_t tl = 0;
+    uint32_t tl = 0, it = 0;
+    const int r128 = lg * 32 + lane;
     for (int panel = p_begin; panel < p_end; ++panel, ++tl) {
       const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
-      const size_t row = (size_t)panel * BM + lg * 32 + lane;
-      // this lane's coefficients of the Gram column groups cg, cg+4, ... (32 B each), fetched before the
-      // accumulator is ready
+      const size_t row = (size_t)panel * BM + r128;
+      // this lane's coefficients of the Gram column groups cg, cg+4, ... (32 B each) come from the TMA tiles in shared
+      // memory: group cg + 4 i lies in k-block i, chunks 2 cg and 2 cg + 1 of the row (SWIZZLE_128B: chunk ^ (row & 7)).
+      // A row-per-lane global load would cost 32 wavefronts per instruction; these are conflict free.
       uint4 sv[4][2];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int g = cg + 4 * i;
-        if (g < KS) {
-          const uint4* sp = reinterpret_cast<const uint4*>(s + row * lds + g * 16);
-          sv[i][0] = sp[0];
-          sv[i][1] = sp[1];
+        if (i < num_kb) {                                  // warp-uniform; every epilogue warp consumes every k-block
+          const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(full0 + st * 8, ph);
+          if (cg + 4 * i < KS) {
+            const uint8_t* arow = smem + st * Cf::A_BYTES + r128 * 128;
+            sv[i][0] = *reinterpret_cast<const uint4*>(arow + (((2 * cg) ^ (r128 & 7)) << 4));
+            sv[i][1] = *reinterpret_cast<const uint4*>(arow + (((2 * cg + 1) ^ (r128 & 7)) << 4));
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty0 + st * 8);
+          ++it;
         }
       }
       mbar_wait(tfull0 + as * 8, aph);
@@ -976,11 +984,13 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int j = 0; j < 4; ++j) {
           uint4 pk;
           uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+          // bias of 8 columns as two broadcast LDS.128 (a 32-bit load per element would cost a wavefront each)
+          const float4 ba = *reinterpret_cast<const float4*>(bs0 + c4 * 32 + j * 8), bb = *reinterpret_cast<const float4*>(bs0 + c4 * 32 + j * 8 + 4);
+          const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int col = c4 * 32 + j * 8 + 2 * e;
-            const __nv_bfloat162 t = __floats2bfloat162_rn(gelu_tanh(__uint_as_float(r[j * 8 + 2 * e]) + bs0[col]),
-                                                          gelu_tanh(__uint_as_float(r[j * 8 + 2 * e + 1]) + bs0[col + 1]));
+            const __nv_bfloat162 t = __floats2bfloat162_rn(gelu_tanh(__uint_as_float(r[j * 8 + 2 * e]) + bv[2 * e]),
+                                                          gelu_tanh(__uint_as_float(r[j * 8 + 2 * e + 1]) + bv[2 * e + 1]));
             pw[e] = *reinterpret_cast<const uint32_t*>(&t);
           }
           const int c = c4 * 4 + j;                               // 16-byte chunk of the row
@@ -1026,12 +1036,13 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&res[j]);
             uint4 pk;
             uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+            const float4 ba = *reinterpret_cast<const float4*>(bs3 + c4 * 32 + j * 8), bb = *reinterpret_cast<const float4*>(bs3 + c4 * 32 + j * 8 + 4);
+            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int col = c4 * 32 + j * 8 + 2 * e;
               const float2 kv = __bfloat1622float2(kh[e]);
-              const __nv_bfloat162 t = __floats2bfloat162_rn(kv.x + __uint_as_float(r[j * 8 + 2 * e]) + bs3[col],
-                                                            kv.y + __uint_as_float(r[j * 8 + 2 * e + 1]) + bs3[col + 1]);
+              const __nv_bfloat162 t = __floats2bfloat162_rn(kv.x + __uint_as_float(r[j * 8 + 2 * e]) + bv[2 * e],
+                                                            kv.y + __uint_as_float(r[j * 8 + 2 * e + 1]) + bv[2 * e + 1]);
               pw[e] = *reinterpret_cast<const uint32_t*>(&t);
             }
             *reinterpret_cast<uint4*>(orow + c4 * 32 + j * 8) = pk;
