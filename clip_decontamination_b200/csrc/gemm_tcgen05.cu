@@ -844,10 +844,11 @@ template <int LDK>
 struct FxCfg {
   static constexpr int NKB = LDK / BK;
   static constexpr int W_BYTES = LDK * LDK * 2, P_BYTES = BM * LDK * 2, KB_W = LDK * 128, KB_P = BM * 128;
-  static constexpr int W0_OFF = 0, W3_OFF = W_BYTES, A_OFF = 2 * W_BYTES, H_OFF = A_OFF + 2 * P_BYTES;
+  static constexpr int NA = 3;                                      // k-panel ring: one stage more than accumulator stages
+  static constexpr int W0_OFF = 0, W3_OFF = W_BYTES, A_OFF = 2 * W_BYTES, H_OFF = A_OFF + NA * P_BYTES;
   static constexpr int BIAS_OFF = H_OFF + 2 * P_BYTES;             // b0[LDK], b3[LDK] fp32
   static constexpr int BAR_OFF = BIAS_OFF + 2 * LDK * 4;
-  static constexpr int NBARS = 17;
+  static constexpr int NBARS = 19;
   static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
   static constexpr int THREADS = 320, TMEM_COLS = 4 * LDK;
 };
@@ -867,7 +868,7 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   float* bs3 = bs0 + LDK;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t w_full = smem_u32(bars);
-  const uint32_t a_full0 = w_full + 8, a_empty0 = a_full0 + 16, d1_full0 = a_empty0 + 16, d1_empty0 = d1_full0 + 16;
+  const uint32_t a_full0 = w_full + 8, a_empty0 = a_full0 + 24, d1_full0 = a_empty0 + 24, d1_empty0 = d1_full0 + 16;
   const uint32_t h_full0 = d1_empty0 + 16, h_empty0 = h_full0 + 16, d2_full0 = h_empty0 + 16, d2_empty0 = d2_full0 + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int panels = (M + BM - 1) / BM;
@@ -878,9 +879,11 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW3) : "memory");
     mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < Cf::NA; ++i) {
       mbar_init(a_full0 + i * 8, 1);
       mbar_init(a_empty0 + i * 8, 4);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(d1_full0 + i * 8, 1);
       mbar_init(d1_empty0 + i * 8, 4);
       mbar_init(h_full0 + i * 8, 128);
@@ -912,12 +915,12 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_load_2d(smem_base + Cf::W3_OFF + kb * Cf::KB_W, &tmW3, w_full, kb * BK, 0);
       }
       for (int i = 0; i < n_my; ++i) {
-        const uint32_t st = i & 1, u = i >> 1;
+        const uint32_t sa = i % Cf::NA, ua = i / Cf::NA;
         const int panel = blockIdx.x + i * gridDim.x;
-        mbar_wait(a_empty0 + st * 8, (u & 1) ^ 1);
-        mbar_expect_tx(a_full0 + st * 8, Cf::P_BYTES);
+        mbar_wait(a_empty0 + sa * 8, (ua & 1) ^ 1);
+        mbar_expect_tx(a_full0 + sa * 8, Cf::P_BYTES);
         for (int kb = 0; kb < NKB; ++kb)
-          tma_load_2d(smem_base + Cf::A_OFF + st * Cf::P_BYTES + kb * Cf::KB_P, &tmA, a_full0 + st * 8, kb * BK, panel * BM);
+          tma_load_2d(smem_base + Cf::A_OFF + sa * Cf::P_BYTES + kb * Cf::KB_P, &tmA, a_full0 + sa * 8, kb * BK, panel * BM);
       }
     }
   } else if (warp == 1) {
@@ -925,14 +928,14 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr uint32_t idesc = make_idesc(BM, LDK);
       mbar_wait(w_full, 0);
       auto mma1 = [&](int i) {
-        const uint32_t st = i & 1, u = i >> 1;
-        mbar_wait(a_full0 + st * 8, u & 1);
+        const uint32_t st = i & 1, u = i >> 1, sa = i % Cf::NA, ua = i / Cf::NA;
+        mbar_wait(a_full0 + sa * 8, ua & 1);
         mbar_wait(d1_empty0 + st * 8, (u & 1) ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + st * 2 * LDK;
 #pragma unroll
         for (int kb = 0; kb < NKB; ++kb) {
-          const uint64_t adesc = make_sdesc(smem_base + Cf::A_OFF + st * Cf::P_BYTES + kb * Cf::KB_P);
+          const uint64_t adesc = make_sdesc(smem_base + Cf::A_OFF + sa * Cf::P_BYTES + kb * Cf::KB_P);
           const uint64_t bdesc = make_sdesc(smem_base + Cf::W0_OFF + kb * Cf::KB_W);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
@@ -1009,7 +1012,8 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const long long grow = (long long)panel * BM + row;
       mbar_wait(d2_full0 + st * 8, u & 1);
       tc_fence_after();
-      const uint8_t* arow = smem + Cf::A_OFF + st * Cf::P_BYTES + row * 128;
+      const uint32_t sa = i % Cf::NA;
+      const uint8_t* arow = smem + Cf::A_OFF + sa * Cf::P_BYTES + row * 128;
       bf16* orow = out + grow * ldo;
 #pragma unroll 1
       for (int c4 = 0; c4 < LDK / 32; ++c4) {
@@ -1027,7 +1031,7 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
           if (lane == 0) {
             mbar_arrive(d2_empty0 + st * 8);
-            mbar_arrive(a_empty0 + st * 8);
+            mbar_arrive(a_empty0 + sa * 8);
           }
         }
         if (grow < M) {
