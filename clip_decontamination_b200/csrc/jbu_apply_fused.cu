@@ -174,7 +174,7 @@ __host__ __device__ constexpr uint32_t fz_idesc() {
 
 template <int R, int MH>
 struct FzCfg {
-  static constexpr int D = 2 * R + 1, DO = (R + 3) / 2;           // composite kernel spans 2 DO + 1 low-res taps
+  static constexpr int DO = (R + 3) / 2;                         // composite kernel spans 2 DO + 1 low-res taps
   static constexpr int NLR = (FZ_RW + 2 * R) / 2 + 3;             // low-res rows per tile (10 / 8)
   static constexpr int NQUAD = (NLR + 3) / 4;                     // four strip rows share one 128 B band-tile row
   static constexpr int CH = 128 * MH;

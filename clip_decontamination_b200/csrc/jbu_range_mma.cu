@@ -6,10 +6,10 @@
 // For 16 query pixels of one image row and one tap row i, the 16 x (16+2R) key.query products are a small
 // GEMM: S[16 queries, 8-position blocks] = Q[16, 32] . K[positions, 32]^T  -> mma.sync m16n8k16 with fp16
 // operands (the reference computes these projections in fp16 under autocast, segmentor.py:370) and fp32
-// accumulation.  Only the band 0 <= pos - query < D of each block is used.  The MMAs are so cheap that the
-// softmax takes two passes over recomputed logits instead of keeping D*D values per pixel in registers:
-// (0) row maxima, (1) exp, both sums, and exp * gauss staged per warp in shared memory as fp16 (values <= 1).
-// The normalisation is applied while the staged rows are copied out as full 16-byte vectors of the
+// accumulation.  Only the band 0 <= pos - query < D of each block is used.  One pass over the D tap rows with a
+// running maximum (online softmax): exp, both sums, and exp * gauss staged per warp in shared memory as fp16
+// (values <= 1, relative to the running maximum of their tap row).  The normalisation -- including the factor
+// 2^(m_row - m_final) -- is applied while the staged rows are copied out as full 16-byte vectors of the
 // [pixels, ldk] kernel matrix (taps, then the 3 guidance channels, then zeros).
 #include "common.cuh"
 #include <cuda_fp16.h>
@@ -20,6 +20,7 @@ constexpr int TXR = 32, TYR = 8;   // CTA tile: 32 x 8 query pixels, one warp pe
 constexpr int KD = 32;             // projection width
 constexpr int PROW = KD * 2 + 16;  // bytes per staged position (padded: conflict-free ldmatrix)
 constexpr int SPAD = 8;            // staging row padding (halves): rows 4 banks apart, 16-byte aligned
+constexpr int MROWS = 12;          // per-pixel running maxima of the tap rows (D <= 11, padded)
 
 __device__ __forceinline__ int reflect1(int i, int n) {
   if (i < 0) i = -i;
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
   const uint32_t psm = (uint32_t)__cvta_generic_to_shared(rsm);
   float* gauss = reinterpret_cast<float*>(rsm + HR * NPOS * PROW);
   bf16* stage = reinterpret_cast<bf16*>(rsm + HR * NPOS * PROW + ((D2 * 4 + 15) & ~15));
+  float* mrow = reinterpret_cast<float*>(rsm + HR * NPOS * PROW + ((D2 * 4 + 15) & ~15) + TYR * 16 * (LDK + SPAD) * 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
   const int crop = blockIdx.z, y0 = blockIdx.y * TYR, x0 = blockIdx.x * TXR;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
       ldsm4(base, a[0]);
       ldsm4(base + 32, a[1]);
     }
-    float mx[2] = {-INFINITY, -INFINITY}, se[2] = {0.f, 0.f}, sg[2] = {0.f, 0.f}, inv[2] = {0.f, 0.f};
+    float se[2] = {0.f, 0.f}, sg[2] = {0.f, 0.f}, inv[2] = {0.f, 0.f};
     // tap column j of fragment element (nb, e) does not depend on the tap row i: hoist it (and its validity)
     int jj[NB][4];
 #pragma unroll
@@ -102,56 +104,60 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
 #pragma unroll
       for (int e = 0; e < 4; ++e) gx[nb][e] = jj[nb][e] >= 0 ? gauss[jj[nb][e]] : 0.f;
     const uint32_t rowb0 = psm + (uint32_t)((warp * NPOS + xb * 16 + rr) * PROW + q * 16);
-    // ---- pass 0: row maxima ----
-#pragma unroll 1
-    for (int i = 0; i < D; ++i) {
-      const uint32_t rowb = rowb0 + (uint32_t)(i * NPOS * PROW);
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        uint32_t b[4];
-        ldsm4(rowb + nb * 8 * PROW, b);
-        float S[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_f16(S, a[0], b[0], b[1]);
-        mma_f16(S, a[1], b[2], b[3]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (jj[nb][e] >= 0) mx[e >> 1] = fmaxf(mx[e >> 1], S[e]);
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
-      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
-      mx[h] *= pos_temp;                                       // pos_temp > 0: max commutes with the scaling
-    }
-    // ---- pass 1: exp, sums, and the unnormalised exp * gauss (fp16, <= 1) into the staging rows ----
+    // ---- single pass over the tap rows with a running maximum (online softmax): exp, both sums, and the unnormalised
+    //      exp * gauss (fp16, <= 1) into the staging rows.  Every tap row i is staged relative to the running maximum at
+    //      that time, which is kept per (pixel, i) and folded into the normalisation when the rows are copied out. ----
     const float pt2 = pos_temp * 1.4426950408889634f;          // exp(x) = 2^(x log2 e): one FFMA + MUFU.EX2 per tap
-    const float mx2[2] = {mx[0] * 1.4426950408889634f, mx[1] * 1.4426950408889634f};
+    float mrun[2] = {-INFINITY, -INFINITY};                    // running maxima of rows g, g+8 in log2 units
     __half* sth = reinterpret_cast<__half*>(st);
+    float* mrw = mrow + warp * 16 * MROWS;
 #pragma unroll 1
     for (int i = 0; i < D; ++i) {
       const uint32_t rowb = rowb0 + (uint32_t)(i * NPOS * PROW);
       const float gy = gauss[i];
       __half* sti = sth + i * D;
+      float S[NB][4];
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
         uint32_t b[4];
         ldsm4(rowb + nb * 8 * PROW, b);
-        float S[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_f16(S, a[0], b[0], b[1]);
-        mma_f16(S, a[1], b[2], b[3]);
+        S[nb][0] = S[nb][1] = S[nb][2] = S[nb][3] = 0.f;
+        mma_f16(S[nb], a[0], b[0], b[1]);
+        mma_f16(S[nb], a[1], b[2], b[3]);
+      }
+      float mi[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          S[nb][e] *= pt2;
+          if (jj[nb][e] >= 0) mi[e >> 1] = fmaxf(mi[e >> 1], S[nb][e]);
+        }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        mi[h] = fmaxf(mi[h], __shfl_xor_sync(0xffffffffu, mi[h], 1));
+        mi[h] = fmaxf(mi[h], __shfl_xor_sync(0xffffffffu, mi[h], 2));
+        const float mnew = fmaxf(mrun[h], mi[h]);
+        float corr;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(corr) : "f"(mrun[h] - mnew));   // 0 on the first row (mrun = -inf)
+        se[h] *= corr;
+        sg[h] *= corr;
+        mrun[h] = mnew;
+        if (tig == 0) mrw[(g + h * 8) * MROWS + i] = mnew;
+      }
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
         for (int e = 0; e < 4; ++e)
           if (jj[nb][e] >= 0) {
             const int h = e >> 1;
             float ex;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(S[e], pt2, -mx2[h])));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(S[nb][e] - mrun[h]));
             const float w = ex * (gy * gx[nb][e]);
             se[h] += ex;
             sg[h] += w;
             sti[(g + h * 8) * (LDK + SPAD) + jj[nb][e]] = __float2half_rn(w);
           }
-      }
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -163,22 +169,31 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
       inv[h] = ise / fmaxf(sg[h] * ise, 1e-7f);               // softmax, then / sum(softmax*gauss).clamp(1e-7)
     }
     __syncwarp();
-    // ---- normalise while copying out: taps * inv[row], then the 3 guidance channels, then zeros; coalesced
-    //      16-byte row stores of the [pixels, ldk] kernel matrix ----
+    // ---- normalise while copying out: taps * inv[row] * 2^(m_i - m_final), then the 3 guidance channels, then zeros;
+    //      coalesced 16-byte row stores of the [pixels, ldk] kernel matrix ----
 #pragma unroll
     for (int e = lane; e < 16 * (LDK / 8); e += 32) {          // uniform trip count: the shuffles stay convergent
       const int px = e / (LDK / 8), v = e % (LDK / 8);
       const float i0 = __shfl_sync(0xffffffffu, inv[0], (px & 7) * 4);
       const float i1 = __shfl_sync(0xffffffffu, inv[1], (px & 7) * 4);
-      const float sc = px < 8 ? i0 : i1;
+      const float m0 = __shfl_sync(0xffffffffu, mrun[0], (px & 7) * 4);
+      const float m1 = __shfl_sync(0xffffffffu, mrun[1], (px & 7) * 4);
+      const float sc = px < 8 ? i0 : i1, mf = px < 8 ? m0 : m1;
+      // the 8 taps of this chunk lie in tap rows ia and (from element bnd on) ia + 1
+      const int ia = (v * 8) / D, bnd = (ia + 1) * D - v * 8;
+      float fa, fb;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(fa) : "f"(mrw[px * MROWS + min(ia, D - 1)] - mf));
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(fb) : "f"(mrw[px * MROWS + min(ia + 1, D - 1)] - mf));
+      fa *= sc;
+      fb *= sc;
       const uint4 raw = *reinterpret_cast<const uint4*>(sth + px * (LDK + SPAD) + v * 8);
       const __half2* hp = reinterpret_cast<const __half2*>(&raw);
       float f[8];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 t2 = __half22float2(hp[k]);
-        f[2 * k] = (v * 8 + 2 * k < D2) ? t2.x * sc : 0.f;
-        f[2 * k + 1] = (v * 8 + 2 * k + 1 < D2) ? t2.y * sc : 0.f;
+        f[2 * k] = (v * 8 + 2 * k < D2) ? t2.x * (2 * k < bnd ? fa : fb) : 0.f;
+        f[2 * k + 1] = (v * 8 + 2 * k + 1 < D2) ? t2.y * (2 * k + 1 < bnd ? fa : fb) : 0.f;
       }
       if (v == D2 / 8) {                                       // columns D2 .. D2+2: guidance (RGB) of this pixel
         const int x = min(xq0 + px, gw - 1);
@@ -290,7 +305,7 @@ template <int R, int LDK>
 int launch(const __half* proj, const float* guid, int n_crops, int gh, int gw, float pos_temp, float inv2s2, bf16* kern,
            int ldk, cudaStream_t st) {
   constexpr int D2 = (2 * R + 1) * (2 * R + 1), NB = (16 + 2 * R + 7) / 8, HR = TYR + 2 * R, NPOS = 16 + NB * 8;
-  const int smem = HR * NPOS * PROW + ((D2 * 4 + 15) & ~15) + TYR * 16 * (LDK + SPAD) * 2;
+  const int smem = HR * NPOS * PROW + ((D2 * 4 + 15) & ~15) + TYR * 16 * (LDK + SPAD) * 2 + TYR * 16 * MROWS * 4;
   CSEG_SET_SMEM((range_kernel_mma<R, LDK>), smem);
   dim3 grid(cdiv(gw, TXR), cdiv(gh, TYR), n_crops);
   cseg_launch(range_kernel_mma<R, LDK>, dim3(grid), dim3(TYR * 32), smem, st, proj, (const float4*)guid, gh, gw, pos_temp, inv2s2, kern, ldk);
