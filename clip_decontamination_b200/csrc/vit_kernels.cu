@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(256) simmap_kernel(const float* __restrict__ x
   pdl_grid_sync();
   __shared__ float As[32][33], Bs[32][33];
   const int P = L - 1, crop = blockIdx.z;
+  if (blockIdx.x < blockIdx.y) return;                   // M is symmetric: tiles on / above the diagonal write both halves
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const float* xb = x + ((size_t)crop * L + 1) * width;  // skip CLS
@@ -385,9 +386,10 @@ __global__ void __launch_bounds__(256) simmap_kernel(const float* __restrict__ x
       const int i = i0 + ty * 2 + a, j = j0 + tx * 2 + b;
       if (i < P && j < P) {
         const float ia = 1.0f / fmaxf(sqrtf(na[a]), 1e-12f), ib = 1.0f / fmaxf(sqrtf(nb[b]), 1e-12f);
-        float v = acc[a][b] * ia * ib * inv_temp;
+        float v = acc[a][b] * (ia * ib) * inv_temp;       // (ia * ib): the same value for (i, j) and (j, i)
         if (!keep_diag && i == j) v = 0.f;
         sim[((size_t)crop * P + i) * P + j] = v;
+        if (blockIdx.x != blockIdx.y) sim[((size_t)crop * P + j) * P + i] = v;
       }
     }
 }
