@@ -274,7 +274,8 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
     }
   } else if (warp == FZ_EPI_WARPS) {
     // ---------------- MMA issuer: one MMA per low-res row and channel half ----------------
-    if (lane == 0) {
+    // the whole warp runs the loop (warp-uniform control flow); one elected lane issues the MMAs and commits
+    {
       constexpr uint32_t idesc = fz_idesc();
       uint32_t tl = 0, it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
@@ -289,15 +290,20 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
           tc_fence_after();
           const uint32_t a_src = smem_base + Cf::A_OFF + st * Cf::A_STAGE;
           const uint64_t bdesc = make_sdesc(bbuf + (s >> 2) * Cf::B_QUAD + (s & 3) * 32);
+          if (elect_one()) {
 #pragma unroll
-          for (int half = 0; half < MH; ++half) {
-            const uint64_t adesc = fz_adesc(a_src + half * 2 * Cf::CHUNK_BYTES, Cf::CHUNK_BYTES);
-            umma_f16(tmem_base + (uint32_t)((as * MH + half) * FZ_NPX), adesc, bdesc, idesc, s > 0 ? 1u : 0u);
+            for (int half = 0; half < MH; ++half) {
+              const uint64_t adesc = fz_adesc(a_src + half * 2 * Cf::CHUNK_BYTES, Cf::CHUNK_BYTES);
+              umma_f16(tmem_base + (uint32_t)((as * MH + half) * FZ_NPX), adesc, bdesc, idesc, s > 0 ? 1u : 0u);
+            }
+            umma_commit(a_empty0 + st * 8);
+            if (s == NLR - 1) {
+              umma_commit(t_full0 + as * 8);
+              umma_commit(b_empty0 + as * 8);
+            }
           }
-          umma_commit(a_empty0 + st * 8);
+          __syncwarp();
         }
-        umma_commit(t_full0 + as * 8);
-        umma_commit(b_empty0 + as * 8);
       }
     }
   } else if (warp < FZ_EPI_WARPS + 1 + FZ_LD_WARPS) {
