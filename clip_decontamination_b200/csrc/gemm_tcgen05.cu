@@ -924,7 +924,9 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // the whole warp runs this loop (warp-uniform control flow keeps descriptors in uniform registers); one elected
+    // lane issues the MMAs and commits
+    {
       constexpr uint32_t idesc = make_idesc(BM, LDK);
       mbar_wait(w_full, 0);
       auto mma1 = [&](int i) {
@@ -933,14 +935,17 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(d1_empty0 + st * 8, (u & 1) ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + st * 2 * LDK;
+        if (elect_one()) {
 #pragma unroll
-        for (int kb = 0; kb < NKB; ++kb) {
-          const uint64_t adesc = make_sdesc(smem_base + Cf::A_OFF + sa * Cf::P_BYTES + kb * Cf::KB_P);
-          const uint64_t bdesc = make_sdesc(smem_base + Cf::W0_OFF + kb * Cf::KB_W);
+          for (int kb = 0; kb < NKB; ++kb) {
+            const uint64_t adesc = make_sdesc(smem_base + Cf::A_OFF + sa * Cf::P_BYTES + kb * Cf::KB_P);
+            const uint64_t bdesc = make_sdesc(smem_base + Cf::W0_OFF + kb * Cf::KB_W);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(d1_full0 + st * 8);
         }
-        umma_commit(d1_full0 + st * 8);
+        __syncwarp();
       };
       auto mma2 = [&](int i) {
         const uint32_t st = i & 1, u = i >> 1;
@@ -948,15 +953,18 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(d2_empty0 + st * 8, (u & 1) ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + st * 2 * LDK + LDK;
+        if (elect_one()) {
 #pragma unroll
-        for (int kb = 0; kb < NKB; ++kb) {
-          const uint64_t adesc = make_sdesc(smem_base + Cf::H_OFF + st * Cf::P_BYTES + kb * Cf::KB_P);
-          const uint64_t bdesc = make_sdesc(smem_base + Cf::W3_OFF + kb * Cf::KB_W);
+          for (int kb = 0; kb < NKB; ++kb) {
+            const uint64_t adesc = make_sdesc(smem_base + Cf::H_OFF + st * Cf::P_BYTES + kb * Cf::KB_P);
+            const uint64_t bdesc = make_sdesc(smem_base + Cf::W3_OFF + kb * Cf::KB_W);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(d2_full0 + st * 8);
+          umma_commit(h_empty0 + st * 8);
         }
-        umma_commit(d2_full0 + st * 8);
-        umma_commit(h_empty0 + st * 8);
+        __syncwarp();
       };
       if (n_my > 0) mma1(0);
       for (int i = 0; i < n_my; ++i) {
