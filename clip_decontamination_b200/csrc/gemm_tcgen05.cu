@@ -131,7 +131,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // the whole warp runs this loop (warp-uniform control flow keeps descriptors and barrier addresses in uniform
+    // registers); one elected lane issues the MMAs and the commits
+    {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       uint32_t it = 0, tl = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
@@ -145,14 +147,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           tc_fence_after();
           const uint64_t adesc = make_sdesc(smem_base + s * C::STAGE_BYTES);
           const uint64_t bdesc = make_sdesc(smem_base + s * C::STAGE_BYTES + C::A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // +32 B per K=16 step inside the 128 B swizzle row -> +2 in the (addr >> 4) field
-            umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // +32 B per K=16 step inside the 128 B swizzle row -> +2 in the (addr >> 4) field
+              umma_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(empty0 + s * 8);  // frees the smem stage once these MMAs have read it
+            if (kb == num_kb - 1) umma_commit(tfull0 + as * 8);   // accumulator complete
           }
-          umma_commit(empty0 + s * 8);  // frees the smem stage once these MMAs have read it
+          __syncwarp();
         }
-        umma_commit(tfull0 + as * 8);   // accumulator complete
       }
     }
   } else {
