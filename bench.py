@@ -308,7 +308,7 @@ def main():
     workfns = dict(jbu_kernel_fixup=kfix_work, basis_logits=basis_work, fixup_norm_sim=fns_work, gemm=gemm_work, jbu_apply=apply_work, attention=attn_work, norm_sim=nsim_work,
                    accum_argmax=accum_work, jbu_range_kernel=rk_work)
     names = ['preprocess_u8', 'patchify', 'embed_tokens', 'layernorm', 'gemm', 'attention', 'simmap', 'outlier_suppress',
-             'cls_debias', 'jbu_guidance', 'jbu_range_proj', 'jbu_range_kernel', 'jbu_kernel_fixup', 'jbu_apply', 'norm_sim', 'fixup_norm_sim', 'basis_logits',
+             'cls_debias', 'jbu_guidance', 'jbu_range_proj', 'jbu_guidance_proj', 'jbu_range_kernel', 'jbu_kernel_fixup', 'jbu_apply', 'norm_sim', 'fixup_norm_sim', 'basis_logits',
              'accum_argmax', 'iou_hist']
     for nm in names:
         orig[nm] = getattr(ops, nm)

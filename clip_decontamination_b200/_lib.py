@@ -44,6 +44,7 @@ SIGNATURES = {
     'cseg_jbu_apply': (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
     'cseg_norm_sim': (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
     'cseg_fixup_norm_sim': (_i, [_i, _p, _i, _p, _i, _i, _i, _i, _p, _f, _p, _i, _p, _p, _p, _p]),
+    'cseg_jbu_guidance_proj': (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p]),
     'cseg_jbu_kernel_fixup': (_i, [_i, _p, _i, _p, _i, _p, _p, _i, _p, _i, _i, _p, _i, _p]),
     'cseg_basis_logits': (_i, [_i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p, _p]),
     'cseg_accum_argmax': (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i, _f, _f, _i,

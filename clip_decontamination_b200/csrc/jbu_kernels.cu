@@ -332,6 +332,9 @@ __global__ void __launch_bounds__(256) adaptive_conv_kernel(const T* __restrict_
 
 }  // namespace
 
+int cseg_jbu_guidance_proj_f16(const float* img, int H, int W, const int32_t* windows, int n_crops, int crop_h, int crop_w,
+                               int pad_top, int pad_left, int gh, int gw, const float* w0, const float* b0, const float* w3,
+                               const float* b3, float* guid, void* proj, cudaStream_t st);
 int cseg_jbu_range_proj_f16(const float* guid, int n_pix, const float* w0, const float* b0, const float* w3,
                             const float* b3, void* proj, cudaStream_t st);
 int cseg_jbu_range_kernel_mma(const void* proj_f16, const float* guid, int n_crops, int gh, int gw, int radius,
@@ -347,6 +350,16 @@ int cseg_jbu_guidance(const float* img, int H, int W, const int32_t* windows, in
                                                                   pad_left, gh, gw, (float4*)guid);
   CSEG_LAUNCH_CHECK("jbu_guidance");
   return 0;
+}
+
+int cseg_jbu_guidance_proj(const float* img, int H, int W, const int32_t* windows, int n_crops, int crop_h, int crop_w,
+                           int pad_top, int pad_left, int gh, int gw, int key_dim, const float* w0, const float* b0,
+                           const float* w3, const float* b3, float* guid, int proj_dtype, void* proj, void* stream) {
+  CSEG_REQUIRE(n_crops > 0 && gh > 0 && gw > 0 && gh <= crop_h && gw <= crop_w, "jbu_guidance_proj: bad shape");
+  CSEG_REQUIRE(key_dim == 32 && proj_dtype == CSEG_F16, "jbu_guidance_proj: key_dim 32 / fp16 projections only (bf16 pipeline)");
+  CSEG_REQUIRE(gw >= 16, "jbu_guidance_proj: gw=%d must be >= 16 (call cseg_jbu_guidance + cseg_jbu_range_proj instead)", gw);
+  return cseg_jbu_guidance_proj_f16(img, H, W, windows, n_crops, crop_h, crop_w, pad_top, pad_left, gh, gw, w0, b0, w3, b3, guid,
+                                    proj, (cudaStream_t)stream);
 }
 
 int cseg_jbu_range_proj(const float* guid, int n_pix, int key_dim, const float* w0, const float* b0, const float* w3,

@@ -224,7 +224,14 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   __half2 h = __halves2half2(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-__global__ void __launch_bounds__(256) range_proj_f16_kernel(const float4* __restrict__ guid, int n_pix,
+// guidance (adaptive_avg_pool2d of every crop to gh x gw, upsamplers.py:316) fused with the projection: the pooled RGB is
+// computed by the lane quad of each pixel (lane tig = channel), written out as the guidance tensor (the range kernel and
+// the kernel fix-up read it) and fed straight into the MLP.  FUSED = false is the stand-alone projection.
+template <bool FUSED>
+__global__ void __launch_bounds__(256) range_proj_f16_kernel(const float4* __restrict__ guid, float4* __restrict__ guid_out,
+                                                             const float* __restrict__ img, int H, int W,
+                                                             const int32_t* __restrict__ wins, int crop_h, int crop_w,
+                                                             int pad_top, int pad_left, int gh, int gw, int n_pix,
                                                              const float* __restrict__ w0, const float* __restrict__ b0,
                                                              const float* __restrict__ w3, const float* __restrict__ b3,
                                                              __half* __restrict__ proj) {
@@ -265,7 +272,52 @@ __global__ void __launch_bounds__(256) range_proj_f16_kernel(const float4* __res
   const int n_tiles = (n_pix + 15) / 16;
   for (int tile = warp_global; tile < n_tiles; tile += n_warps) {
     const int p0 = tile * 16 + g, p1 = p0 + 8;
-    const float4 g0 = guid[min(p0, n_pix - 1)], g1 = guid[min(p1, n_pix - 1)];
+    float4 g0, g1;
+    if (!FUSED) {
+      g0 = guid[min(p0, n_pix - 1)];
+      g1 = guid[min(p1, n_pix - 1)];
+    } else {
+      // pixel coordinates: one division per tile (warp-uniform); the 16 pixels of a tile wrap at most once (gw >= 16)
+      const int base = tile * 16, gx0 = base % gw, t0 = base / gw, gy0 = t0 % gh, crop0 = t0 / gh;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        int gx = gx0 + g + hh * 8, gy = gy0, crop = crop0;
+        if (gx >= gw) {
+          gx -= gw;
+          if (++gy == gh) { gy = 0; ++crop; }
+        }
+        if (tile * 16 + g + hh * 8 >= n_pix) { gx = 0; gy = 0; crop = 0; }   // padding pixels of the last tile: any valid cell
+        const int y1 = wins[crop * 4], x1 = wins[crop * 4 + 1], wh = wins[crop * 4 + 2], ww = wins[crop * 4 + 3];
+        // adaptive pooling window: [floor(i*in/out), ceil((i+1)*in/out))
+        const int ys = (gy * crop_h) / gh, ye = ((gy + 1) * crop_h + gh - 1) / gh;
+        const int xs = (gx * crop_w) / gw, xe = ((gx + 1) * crop_w + gw - 1) / gw;
+        // the four lanes of the quad split the window rows; all three channels per lane, then a quad reduction
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int y = ys + tig; y < ye; y += 4) {
+          const int cy = y - pad_top;
+          if (cy < 0 || cy >= wh) continue;
+          const float* r0 = img + ((size_t)(y1 + cy)) * W + x1 - pad_left;
+          for (int x = xs; x < xe; ++x) {
+            const int cx = x - pad_left;
+            if (cx >= 0 && cx < ww) {
+              a0 += r0[x];
+              a1 += r0[(size_t)H * W + x];
+              a2 += r0[(size_t)2 * H * W + x];
+            }
+          }
+        }
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
+        const float inv = 1.0f / (float)((ye - ys) * (xe - xs));
+        if (hh == 0) g0 = make_float4(a0 * inv, a1 * inv, a2 * inv, 0.f);
+        else g1 = make_float4(a0 * inv, a1 * inv, a2 * inv, 0.f);
+      }
+      if (tig == 0) {
+        if (p0 < n_pix) guid_out[p0] = g0;
+        if (p1 < n_pix) guid_out[p1] = g1;
+      }
+    }
     uint32_t ah[2][4], al[2][4];                       // A fragments: (row g | g+8) x (k pair | k pair + 8)
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
@@ -275,8 +327,10 @@ __global__ void __launch_bounds__(256) range_proj_f16_kernel(const float4* __res
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const float* w = wa[ks][r * 2 + e];
-          h[0][e] = gelu_fast(fmaf(w[0], g0.x, fmaf(w[1], g0.y, fmaf(w[2], g0.z, w[3]))));
-          h[1][e] = gelu_fast(fmaf(w[0], g1.x, fmaf(w[1], g1.y, fmaf(w[2], g1.z, w[3]))));
+          const float z0 = fmaf(w[0], g0.x, fmaf(w[1], g0.y, fmaf(w[2], g0.z, w[3])));
+          const float z1 = fmaf(w[0], g1.x, fmaf(w[1], g1.y, fmaf(w[2], g1.z, w[3])));
+          h[0][e] = FUSED ? gelu_tanh(z0) : gelu_fast(z0);   // tanh form (|err| <= 4.8e-4, the size of the fp16 rounding the
+          h[1][e] = FUSED ? gelu_tanh(z1) : gelu_fast(z1);   // reference's autocast applies to these activations)
         }
 #pragma unroll
         for (int row = 0; row < 2; ++row) {
@@ -318,8 +372,20 @@ int launch(const __half* proj, const float* guid, int n_crops, int gh, int gw, f
 int cseg_jbu_range_proj_f16(const float* guid, int n_pix, const float* w0, const float* b0, const float* w3,
                             const float* b3, void* proj, cudaStream_t st) {
   const int blocks = (int)std::min<long long>(cdiv(cdiv(n_pix, 16), 8), (long long)sm_count() * 8);
-  cseg_launch(range_proj_f16_kernel, dim3(blocks), dim3(256), 0, st, (const float4*)guid, n_pix, w0, b0, w3, b3, (__half*)proj);
+  cseg_launch(range_proj_f16_kernel<false>, dim3(blocks), dim3(256), 0, st, (const float4*)guid, (float4*)nullptr,
+              (const float*)nullptr, 0, 0, (const int32_t*)nullptr, 0, 0, 0, 0, 1, 1, n_pix, w0, b0, w3, b3, (__half*)proj);
   CSEG_LAUNCH_CHECK("jbu_range_proj_f16");
+  return 0;
+}
+
+int cseg_jbu_guidance_proj_f16(const float* img, int H, int W, const int32_t* windows, int n_crops, int crop_h, int crop_w,
+                               int pad_top, int pad_left, int gh, int gw, const float* w0, const float* b0, const float* w3,
+                               const float* b3, float* guid, void* proj, cudaStream_t st) {
+  const int n_pix = n_crops * gh * gw;
+  const int blocks = (int)std::min<long long>(cdiv(cdiv(n_pix, 16), 8), (long long)sm_count() * 8);
+  cseg_launch(range_proj_f16_kernel<true>, dim3(blocks), dim3(256), 0, st, (const float4*)nullptr, (float4*)guid, img, H, W,
+              windows, crop_h, crop_w, pad_top, pad_left, gh, gw, n_pix, w0, b0, w3, b3, (__half*)proj);
+  CSEG_LAUNCH_CHECK("jbu_guidance_proj_f16");
   return 0;
 }
 

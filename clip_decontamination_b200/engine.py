@@ -287,9 +287,13 @@ class JBUEngine:
             GH, GW = 2 * h, 2 * w
             npix = n * GH * GW
             guid = ws.get('guid', (npix, 4), f32)
-            ops.jbu_guidance(img, windows, crop_h, crop_w, pad_top, pad_left, GH, GW, guid)
             proj = ws.get('proj', (npix, 32), torch.float16 if cdt == torch.bfloat16 else f32)
-            ops.jbu_range_proj(guid, npix, st['rp_w0'], st['rp_b0'], st['rp_w3'], st['rp_b3'], proj)
+            if cdt == torch.bfloat16 and GW >= 16:    # pooling + MLP in one kernel
+                ops.jbu_guidance_proj(img, windows, crop_h, crop_w, pad_top, pad_left, GH, GW, st['rp_w0'], st['rp_b0'],
+                                      st['rp_w3'], st['rp_b3'], guid, proj)
+            else:
+                ops.jbu_guidance(img, windows, crop_h, crop_w, pad_top, pad_left, GH, GW, guid)
+                ops.jbu_range_proj(guid, npix, st['rp_w0'], st['rp_b0'], st['rp_w3'], st['rp_b3'], proj)
             kw = st['ldk']
             kern = ws.get('kern', (npix, kw), cdt)
             if cdt == torch.bfloat16 and kw in (64, 128):

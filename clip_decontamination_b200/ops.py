@@ -123,6 +123,15 @@ def jbu_guidance(img, windows, crop_h, crop_w, pad_top, pad_left, gh, gw, out):
     return out
 
 
+def jbu_guidance_proj(img, windows, crop_h, crop_w, pad_top, pad_left, gh, gw, w0, b0, w3, b3, guid, proj):
+    """guidance + range projection of one stage in one kernel (bf16 pipeline; proj fp16)."""
+    _, H, W = img.shape
+    check(lib.cseg_jbu_guidance_proj(_ptr(img), H, W, _ptr(windows), windows.shape[0], crop_h, crop_w, pad_top, pad_left,
+                                     gh, gw, 32, _ptr(w0), _ptr(b0), _ptr(w3), _ptr(b3), _ptr(guid), _dt(proj), _ptr(proj),
+                                     _stream()))
+    return guid, proj
+
+
 def jbu_range_proj(guid, n_pix, w0, b0, w3, b3, proj):
     check(lib.cseg_jbu_range_proj(_ptr(guid), n_pix, 32, _ptr(w0), _ptr(b0), _ptr(w3), _ptr(b3), _dt(proj), _ptr(proj),
                                   _stream()))

@@ -127,6 +127,13 @@ CSEG_API int cseg_cls_debias(const float* tok, int n_crops, int L, int D, float 
 CSEG_API int cseg_jbu_guidance(const float* img_chw, int H, int W, const int32_t* windows, int n_crops,
                       int crop_h, int crop_w, int pad_top, int pad_left, int gh, int gw,
                       float* guid, void* stream);
+/* the two calls above/below in one kernel for the bf16 pipeline: guid (fp32 [n,gh,gw,4]) and proj (CSEG_F16
+ * [n,gh,gw,32]) of one stage from the image; the hidden GELU uses the tanh form (|err| <= 4.8e-4, the size of the
+ * fp16 rounding the reference's autocast applies to these activations). */
+CSEG_API int cseg_jbu_guidance_proj(const float* img_chw, int H, int W, const int32_t* windows, int n_crops,
+                           int crop_h, int crop_w, int pad_top, int pad_left, int gh, int gw, int key_dim,
+                           const float* w0, const float* b0, const float* w3, const float* b3, float* guid,
+                           int proj_dtype, void* proj, void* stream);
 /* range_proj (:209-214): conv1x1(3->kd) . GELU . conv1x1(kd->kd); proj [n,gh,gw,kd] in proj_dtype:
  * CSEG_F32 (verification mode) or CSEG_F16 (tensor-core range kernel; the reference computes these in
  * fp16 under autocast, segmentor.py:370). */

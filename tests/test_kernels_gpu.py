@@ -387,6 +387,30 @@ def test_iou_hist(ops):
     assert torch.equal(hist.cpu(), torch.stack([ai, ap, al]) * 2)
 
 
+@pytest.mark.parametrize('gh', [28, 224])
+def test_jbu_guidance_proj_fused(ops, gh):
+    """pooling + projection in one kernel == cseg_jbu_guidance followed by cseg_jbu_range_proj(fp16): guidance bit-exact
+    up to the summation order (1e-6), projections within 4e-3 (tanh-form GELU on the hidden layer, |err| <= 4.8e-4,
+    times the second layer; fp16 output rounding 1e-3 at |proj| ~ 2)."""
+    n, H, W = 3, 300, 260
+    img = torch.randn(3, H, W, generator=_g(1)).cuda()
+    wins = torch.tensor([[0, 0, 224, 224], [76, 36, 224, 224], [10, 20, 224, 224]], dtype=torch.int32).cuda()
+    w0, b0 = (torch.randn(32, 3, generator=_g(2)) * 0.5).cuda(), (torch.randn(32, generator=_g(3)) * 0.1).cuda()
+    w3, b3 = (torch.randn(32, 32, generator=_g(4)) * 32 ** -0.5).cuda(), (torch.randn(32, generator=_g(5)) * 0.1).cuda()
+    npix = n * gh * gh
+    g_ref = torch.empty(npix, 4, device='cuda')
+    p_ref = torch.empty(npix, 32, device='cuda', dtype=torch.float16)
+    ops.jbu_guidance(img, wins, 224, 224, 0, 0, gh, gh, g_ref)
+    ops.jbu_range_proj(g_ref, npix, w0, b0, w3, b3, p_ref)
+    g = torch.full((npix, 4), float('nan'), device='cuda')
+    pr = torch.full((npix, 32), float('nan'), device='cuda', dtype=torch.float16)
+    ops.jbu_guidance_proj(img, wins, 224, 224, 0, 0, gh, gh, w0, b0, w3, b3, g, pr)
+    assert (g - g_ref).abs().max().item() < 1e-6
+    err = (pr.float() - p_ref.float()).abs().max().item()
+    print(f'guidance_proj gh={gh} max|dproj|={err:.3e}')
+    assert err < 4e-3
+
+
 @pytest.mark.parametrize('ldk,M', [(128, 1000), (64, 333), (128, 128 * 300 + 5)])
 def test_jbu_kernel_fixup(ops, ldk, M):
     """fused kernel fix-up == k + W3s . gelu(W0 . k + b0) + b3s in fp32 on the same bf16 operands (erf GELU);
