@@ -855,14 +855,14 @@ struct FxCfg {
   static constexpr int BAR_OFF = BIAS_OFF + 2 * LDK * 4;
   static constexpr int NBARS = 19;
   static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
-  static constexpr int THREADS = 320, TMEM_COLS = 4 * LDK;
+  static constexpr int E1W = 4, THREADS = 32 * (2 + E1W + 4), TMEM_COLS = 4 * LDK;
 };
 
 template <int LDK>
 __global__ void __launch_bounds__(FxCfg<LDK>::THREADS, 1)
 kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
-                    const __grid_constant__ CUtensorMap tmW3, int M, const float* __restrict__ b0,
-                    const float* __restrict__ b3, bf16* __restrict__ out, int ldo) {
+                    const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmOut, int M,
+                    const float* __restrict__ b0, const float* __restrict__ b3) {
   using Cf = FxCfg<LDK>;
   constexpr int NKB = Cf::NKB;
   extern __shared__ uint8_t smem_raw[];
@@ -883,10 +883,11 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW3) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
     mbar_init(w_full, 1);
     for (int i = 0; i < Cf::NA; ++i) {
       mbar_init(a_full0 + i * 8, 1);
-      mbar_init(a_empty0 + i * 8, 4);
+      mbar_init(a_empty0 + i * 8, 1);                  // the thread that issued the TMA store of the slot
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(d1_full0 + i * 8, 1);
@@ -1017,56 +1018,60 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_arrive(h_full0 + st * 8);
     }
   } else {
-    // ---- epilogue 2: out = k + D2 + b3 (k read back from the TMA tile) ----
+    // ---- epilogue 2: out = k + D2 + b3.  k is read back from the TMA tile and the result overwrites it in place (same
+    //      swizzled position, every thread owns its row); the finished tile leaves with one TMA store per k-block, so
+    //      the global writes are full lines instead of 32 row-strided 16-byte pieces per instruction ----
     const int lg = warp & 3, row = lg * 32 + lane;
     for (int i = 0; i < n_my; ++i) {
       const uint32_t st = i & 1, u = i >> 1;
       const int panel = blockIdx.x + i * gridDim.x;
-      const long long grow = (long long)panel * BM + row;
       mbar_wait(d2_full0 + st * 8, u & 1);
       tc_fence_after();
       const uint32_t sa = i % Cf::NA;
-      const uint8_t* arow = smem + Cf::A_OFF + sa * Cf::P_BYTES + row * 128;
-      bf16* orow = out + grow * ldo;
+      uint8_t* arow = smem + Cf::A_OFF + sa * Cf::P_BYTES + row * 128;
 #pragma unroll 1
       for (int c4 = 0; c4 < LDK / 32; ++c4) {
         uint32_t r[32];
         __syncwarp();
         tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(st * 2 * LDK + LDK + c4 * 32), r);
-        uint4 res[4];
+        if (c4 == LDK / 32 - 1) {                                  // accumulator fully read
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d2_empty0 + st * 8);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c = c4 * 4 + j;
-          res[j] = *reinterpret_cast<const uint4*>(arow + (c >> 3) * Cf::KB_P + (((c & 7) ^ (row & 7)) << 4));
-        }
-        if (c4 == LDK / 32 - 1) {                                  // accumulator and k tile fully read
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(d2_empty0 + st * 8);
-            mbar_arrive(a_empty0 + sa * 8);
-          }
-        }
-        if (grow < M) {
+          uint4* slot = reinterpret_cast<uint4*>(arow + (c >> 3) * Cf::KB_P + (((c & 7) ^ (row & 7)) << 4));
+          const uint4 res = *slot;
+          const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&res);
+          uint4 pk;
+          uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+          const float4 ba = *reinterpret_cast<const float4*>(bs3 + c4 * 32 + j * 8), bb = *reinterpret_cast<const float4*>(bs3 + c4 * 32 + j * 8 + 4);
+          const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&res[j]);
-            uint4 pk;
-            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
-            const float4 ba = *reinterpret_cast<const float4*>(bs3 + c4 * 32 + j * 8), bb = *reinterpret_cast<const float4*>(bs3 + c4 * 32 + j * 8 + 4);
-            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 kv = __bfloat1622float2(kh[e]);
-              const __nv_bfloat162 t = __floats2bfloat162_rn(kv.x + __uint_as_float(r[j * 8 + 2 * e]) + bv[2 * e],
-                                                            kv.y + __uint_as_float(r[j * 8 + 2 * e + 1]) + bv[2 * e + 1]);
-              pw[e] = *reinterpret_cast<const uint32_t*>(&t);
-            }
-            *reinterpret_cast<uint4*>(orow + c4 * 32 + j * 8) = pk;
+          for (int e = 0; e < 4; ++e) {
+            const float2 kv = __bfloat1622float2(kh[e]);
+            const __nv_bfloat162 t = __floats2bfloat162_rn(kv.x + __uint_as_float(r[j * 8 + 2 * e]) + bv[2 * e],
+                                                          kv.y + __uint_as_float(r[j * 8 + 2 * e + 1]) + bv[2 * e + 1]);
+            pw[e] = *reinterpret_cast<const uint32_t*>(&t);
           }
+          *slot = pk;
         }
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> visible to the TMA store
+      asm volatile("bar.sync 3, 128;" ::: "memory");                    // the four epilogue-2 warps
+      if (warp == 2 + Cf::E1W && lane == 0) {
+        for (int kb = 0; kb < NKB; ++kb)
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(&tmOut), "r"(smem_base + Cf::A_OFF + sa * Cf::P_BYTES + kb * Cf::KB_P), "r"(kb * BK), "r"(panel * BM)
+                       : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the slot has been read: the producer may refill it
+        mbar_arrive(a_empty0 + sa * 8);
+      }
     }
+    if (warp == 2 + Cf::E1W && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete
   }
   tc_fence_before();
   __syncthreads();
@@ -1086,10 +1091,13 @@ int launch_kernel_fixup(const void* k, int lda, const void* W0, int ldw0, const 
   if (rc) return rc;
   rc = make_map(&tw3, W3, LDK, LDK, ldw3, LDK);
   if (rc) return rc;
+  CUtensorMap tout;
+  rc = make_map(&tout, out, M, LDK, ldo, BM);
+  if (rc) return rc;
   CSEG_SET_SMEM(kernel_fixup_kernel<LDK>, Cf::SMEM_BYTES);
   const int panels = cdiv(M, BM);
   cseg_launch(kernel_fixup_kernel<LDK>, dim3(std::min(panels, sm_count())), dim3(Cf::THREADS), Cf::SMEM_BYTES, st, ta, tw0,
-              tw3, M, b0, b3, (bf16*)out, ldo);
+              tw3, tout, M, b0, b3);
   CSEG_LAUNCH_CHECK("jbu_kernel_fixup");
   return 0;
 }
