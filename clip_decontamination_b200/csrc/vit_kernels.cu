@@ -351,39 +351,45 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const T* __re
 __global__ void __launch_bounds__(256) simmap_kernel(const float* __restrict__ x, int L, int width, float inv_temp,
                                                      int keep_diag, float* __restrict__ sim) {
   pdl_grid_sync();
-  __shared__ float As[32][33], Bs[32][33];
-  const int P = L - 1, crop = blockIdx.z;
+  // 64 x 64 tile per CTA, 4 x 4 outputs per thread, operands staged k-major so that a thread reads its four rows /
+  // columns as one float4 (broadcast across the 16 threads that share them)
+  constexpr int TS = 64, KC = 16, LDS_ = TS + 4;
+  __shared__ __align__(16) float As[KC][LDS_], Bs[KC][LDS_];
   if (blockIdx.x < blockIdx.y) return;                   // M is symmetric: tiles on / above the diagonal write both halves
-  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int P = L - 1, crop = blockIdx.z;
+  const int i0 = blockIdx.y * TS, j0 = blockIdx.x * TS;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const float* xb = x + ((size_t)crop * L + 1) * width;  // skip CLS
-  float acc[2][2] = {};
-  float na[2] = {}, nb[2] = {};   // squared norms of the rows this thread touches (F.normalize)
-  for (int k0 = 0; k0 < width; k0 += 32) {
-    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
-      const int r = e >> 5, k = e & 31;
-      As[r][k] = (i0 + r < P && k0 + k < width) ? xb[(size_t)(i0 + r) * width + k0 + k] : 0.f;
-      Bs[r][k] = (j0 + r < P && k0 + k < width) ? xb[(size_t)(j0 + r) * width + k0 + k] : 0.f;
+  float acc[4][4] = {};
+  float na[4] = {}, nb[4] = {};   // squared norms of the rows this thread touches (F.normalize)
+  for (int k0 = 0; k0 < width; k0 += KC) {
+#pragma unroll
+    for (int n = 0; n < TS * KC / 256; ++n) {
+      const int e = threadIdx.x + n * 256, r = e / KC, k = e % KC;
+      As[k][r] = (i0 + r < P && k0 + k < width) ? xb[(size_t)(i0 + r) * width + k0 + k] : 0.f;
+      Bs[k][r] = (j0 + r < P && k0 + k < width) ? xb[(size_t)(j0 + r) * width + k0 + k] : 0.f;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float a0 = As[ty * 2][k], a1 = As[ty * 2 + 1][k];
-      const float b0 = Bs[tx * 2][k], b1 = Bs[tx * 2 + 1][k];
-      acc[0][0] = fmaf(a0, b0, acc[0][0]);
-      acc[0][1] = fmaf(a0, b1, acc[0][1]);
-      acc[1][0] = fmaf(a1, b0, acc[1][0]);
-      acc[1][1] = fmaf(a1, b1, acc[1][1]);
-      na[0] = fmaf(a0, a0, na[0]); na[1] = fmaf(a1, a1, na[1]);
-      nb[0] = fmaf(b0, b0, nb[0]); nb[1] = fmaf(b1, b1, nb[1]);
+    for (int k = 0; k < KC; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        na[u] = fmaf(a[u], a[u], na[u]);
+        nb[u] = fmaf(b[u], b[u], nb[u]);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], b[v], acc[u][v]);
+      }
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int i = i0 + ty * 2 + a, j = j0 + tx * 2 + b;
+    for (int b = 0; b < 4; ++b) {
+      const int i = i0 + ty * 4 + a, j = j0 + tx * 4 + b;
       if (i < P && j < P) {
         const float ia = 1.0f / fmaxf(sqrtf(na[a]), 1e-12f), ib = 1.0f / fmaxf(sqrtf(nb[b]), 1e-12f);
         float v = acc[a][b] * (ia * ib) * inv_temp;       // (ia * ib): the same value for (i, j) and (j, i)
@@ -694,7 +700,7 @@ int cseg_simmap(const float* x, int n_crops, int L, int width, float temperature
   CSEG_REQUIRE(n_crops > 0 && L >= 2 && width > 0 && temperature != 0.f, "simmap: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const int P = L - 1;
-  dim3 grid(cdiv(P, 32), cdiv(P, 32), n_crops);
+  dim3 grid(cdiv(P, 64), cdiv(P, 64), n_crops);
   cseg_launch(simmap_kernel, dim3(grid), dim3(256), 0, st, x, L, width, 1.0f / temperature, add_self_similarity, simmap);
   CSEG_LAUNCH_CHECK("simmap");
   return 0;
