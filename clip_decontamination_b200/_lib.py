@@ -10,9 +10,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libclipseg.so')
 
-F32, BF16, F16 = 0, 1, 2
+F32, BF16, F16, U8 = 0, 1, 2, 3
 ACT_NONE, ACT_GELU, ACT_QUICKGELU = 0, 1, 2
-ATTN = dict(STD=0, Experimental=1, SCLIP=2, ClearCLIP=3, SFP=4, vanilla=5, SegEarth=6, MaskCLIP=7)
+ATTN = dict(STD=0, Experimental=1, SCLIP=2, ClearCLIP=3, SFP=4, vanilla=5, SegEarth=6, MaskCLIP=7, CAUSAL=8)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -24,12 +24,23 @@ lib = C.CDLL(LIB_PATH)
 _p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 _f3 = C.c_float * 3
 
+
+class CsegImage(C.Structure):
+    """struct cseg_image of include/clipseg.h (host struct; `data` is a device pointer)."""
+    _fields_ = [('data', C.c_void_p), ('dtype', C.c_int), ('H', C.c_int), ('W', C.c_int), ('img_h', C.c_int),
+                ('stride_img', C.c_longlong), ('stride_c', C.c_longlong), ('stride_y', C.c_longlong),
+                ('stride_x', C.c_longlong), ('chan', C.c_int * 3), ('mean', C.c_float * 3), ('std', C.c_float * 3)]
+
+
+_img = C.POINTER(CsegImage)
+
 SIGNATURES = {
     'cseg_version': (_i, []),
     'cseg_last_error': (_i, [C.c_char_p, C.c_size_t]),
     'cseg_launch_count': (_ll, []),
     'cseg_preprocess_u8': (_i, [_p, _i, _i, _f3, _f3, _p, _p]),
-    'cseg_patchify': (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
+    'cseg_patchify': (_i, [_img, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
+    'cseg_gather_rows': (_i, [_p, _p, _p, _ll, _i, _i, _p, _p]),
     'cseg_embed_tokens': (_i, [_p, _p, _p, _i, _i, _i, _p, _p]),
     'cseg_layernorm': (_i, [_p, _i, _i, _p, _p, _f, _i, _p, _p]),
     'cseg_gemm': (_i, [_i, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _f, _i, _i, _p, _i, _p]),
@@ -38,13 +49,13 @@ SIGNATURES = {
     'cseg_simmap': (_i, [_p, _i, _i, _i, _f, _i, _p, _p]),
     'cseg_outlier_suppress': (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _i, _f, _p, _p, _p]),
     'cseg_cls_debias': (_i, [_p, _i, _i, _i, _f, _i, _p, _i, _i, _p, _p]),
-    'cseg_jbu_guidance': (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    'cseg_jbu_guidance': (_i, [_img, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     'cseg_jbu_range_proj': (_i, [_p, _i, _i, _p, _p, _p, _p, _i, _p, _p]),
     'cseg_jbu_range_kernel': (_i, [_i, _p, _p, _i, _i, _i, _i, _i, _f, _f, _i, _p, _i, _i, _p]),
     'cseg_jbu_apply': (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
     'cseg_norm_sim': (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
     'cseg_fixup_norm_sim': (_i, [_i, _p, _i, _p, _i, _i, _i, _i, _p, _f, _p, _i, _p, _p, _p, _p]),
-    'cseg_jbu_guidance_proj': (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p]),
+    'cseg_jbu_guidance_proj': (_i, [_img, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p]),
     'cseg_jbu_kernel_fixup': (_i, [_i, _p, _i, _p, _i, _p, _p, _i, _p, _i, _i, _p, _i, _p]),
     'cseg_basis_logits': (_i, [_i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p, _p]),
     'cseg_accum_argmax': (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i, _f, _f, _i,

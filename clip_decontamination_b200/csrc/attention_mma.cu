@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(NW * 32, (NW * NKB > 8 * 26) ? 1 : 2) attentio
       for (int nb = 0; nb < NKB; ++nb)
 #pragma unroll
         for (int e = 0; e < 4; ++e) S[nb][e] = 0.f;
-      if (mode == CSEG_ATTN_STD || mode == CSEG_ATTN_VANILLA) {
+      if (mode == CSEG_ATTN_STD || mode == CSEG_ATTN_VANILLA || mode == CSEG_ATTN_CAUSAL) {
         accum_scores<NKB>(S, qt, kt, r0, lane);
       } else if (mode == CSEG_ATTN_CLEARCLIP) {
         accum_scores<NKB>(S, qt, qt, r0, lane);
@@ -200,7 +200,18 @@ __global__ void __launch_bounds__(NW * 32, (NW * NKB > 8 * 26) ? 1 : 2) attentio
         add_simmap<NKB>(S, sim, simw, P, L, row0, row1, tig);   // on the probabilities (:900-901)
         frag_softmax<NKB>(S, L, tig);                           // second softmax, unconditional (:902)
       } else {
-        if (mode != CSEG_ATTN_STD) add_simmap<NKB>(S, sim, simw, P, L, row0, row1, tig);
+        if (mode == CSEG_ATTN_CAUSAL) {           // additive -inf mask above the diagonal (build_attention_mask)
+#pragma unroll
+          for (int nb = 0; nb < NKB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int j = nb * 8 + 2 * tig + e;
+              if (j > row0) S[nb][e] = -INFINITY;
+              if (j > row1) S[nb][2 + e] = -INFINITY;
+            }
+        } else if (mode != CSEG_ATTN_STD) {
+          add_simmap<NKB>(S, sim, simw, P, L, row0, row1, tig);
+        }
         frag_softmax<NKB>(S, L, tig);
       }
       if (stats != nullptr) {
@@ -273,6 +284,7 @@ int launch(const bf16* qkv, int n_crops, int L, int heads, int mode, const float
 int cseg_attention_mma(const bf16* qkv, int n_crops, int L, int heads, int head_dim, int mode, const float* simmap,
                        float simw, bf16* out, float* stats, cudaStream_t st) {
   if (head_dim != HD || mode == CSEG_ATTN_MASKCLIP || L > 272) return 1;
+  if (L <= 80 && mode != CSEG_ATTN_STD) return launch<10>(qkv, n_crops, L, heads, mode, simmap, simw, out, stats, st);
   if (L <= 208) return launch<26>(qkv, n_crops, L, heads, mode, simmap, simw, out, stats, st);
   return launch<34>(qkv, n_crops, L, heads, mode, simmap, simw, out, stats, st);
 }

@@ -77,6 +77,39 @@ inline void cseg_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t 
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in CSEG_LAUNCH_CHECK
 }
 
+// ---- input image access (cseg_image, include/clipseg.h): normalised RGB value of canvas element (c, Y, x) -----------
+struct ImgView {
+  const void* data;
+  int dtype, H, W, img_h;
+  long long stride_img, stride_c, stride_y, stride_x;
+  int chan[3];
+  float mean[3], std[3];
+};
+static inline int make_img_view(const cseg_image* d, ImgView& v) {
+  if (!d || !d->data || d->H <= 0 || d->W <= 0 || d->img_h <= 0 || d->H % d->img_h != 0) return 1;
+  if (d->dtype != CSEG_F32 && d->dtype != CSEG_U8) return 1;
+  v.data = d->data; v.dtype = d->dtype; v.H = d->H; v.W = d->W; v.img_h = d->img_h;
+  v.stride_img = d->stride_img; v.stride_c = d->stride_c; v.stride_y = d->stride_y; v.stride_x = d->stride_x;
+  for (int c = 0; c < 3; ++c) {
+    if (d->chan[c] < 0 || d->chan[c] > 2) return 1;
+    v.chan[c] = d->chan[c]; v.mean[c] = d->mean[c]; v.std[c] = d->std[c];
+    if (d->dtype == CSEG_U8 && !(d->std[c] > 0.f)) return 1;
+  }
+  return 0;
+}
+// offset of canvas row Y (image index resolved) without the channel / column terms
+__device__ __forceinline__ long long img_row_off(const ImgView& v, int Y) {
+  if (v.img_h == v.H) return (long long)Y * v.stride_y;
+  const int b = Y / v.img_h;
+  return (long long)b * v.stride_img + (long long)(Y - b * v.img_h) * v.stride_y;
+}
+__device__ __forceinline__ float img_at(const ImgView& v, int c, long long row_off, int x) {
+  const long long off = row_off + (long long)v.chan[c] * v.stride_c + (long long)x * v.stride_x;
+  if (v.dtype == CSEG_U8)      // SegDataPreProcessor: (x.float() - mean) / std, IEEE division (segmentor.py:64-67)
+    return __fdiv_rn((float)reinterpret_cast<const uint8_t*>(v.data)[off] - v.mean[c], v.std[c]);
+  return reinterpret_cast<const float*>(v.data)[off];
+}
+
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);

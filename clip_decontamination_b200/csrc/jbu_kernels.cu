@@ -17,7 +17,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {  // F.pad(mode='refle
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void guidance_kernel(const float* __restrict__ img, int H, int W, const int32_t* __restrict__ wins,
+__global__ void guidance_kernel(const ImgView img, const int32_t* __restrict__ wins,
                                 int n_crops, int crop_h, int crop_w, int pad_top, int pad_left, int gh, int gw,
                                 float4* __restrict__ guid) {
   pdl_grid_sync();
@@ -33,7 +33,7 @@ __global__ void guidance_kernel(const float* __restrict__ img, int H, int W, con
     for (int y = ys; y < ye; ++y)
       for (int x = xs; x < xe; ++x) {
         const int cy = y - pad_top, cx = x - pad_left;
-        if (cy >= 0 && cy < wh && cx >= 0 && cx < ww) acc[c] += img[((size_t)c * H + y1 + cy) * W + x1 + cx];
+        if (cy >= 0 && cy < wh && cx >= 0 && cx < ww) acc[c] += img_at(img, c, img_row_off(img, y1 + cy), x1 + cx);
       }
   const float inv = 1.0f / (float)((ye - ys) * (xe - xs));
   guid[idx] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, 0.f);
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256) adaptive_conv_kernel(const T* __restrict_
 
 }  // namespace
 
-int cseg_jbu_guidance_proj_f16(const float* img, int H, int W, const int32_t* windows, int n_crops, int crop_h, int crop_w,
+int cseg_jbu_guidance_proj_f16(const ImgView& img, const int32_t* windows, int n_crops, int crop_h, int crop_w,
                                int pad_top, int pad_left, int gh, int gw, const float* w0, const float* b0, const float* w3,
                                const float* b3, float* guid, void* proj, cudaStream_t st);
 int cseg_jbu_range_proj_f16(const float* guid, int n_pix, const float* w0, const float* b0, const float* w3,
@@ -342,23 +342,27 @@ int cseg_jbu_range_kernel_mma(const void* proj_f16, const float* guid, int n_cro
 
 extern "C" {
 
-int cseg_jbu_guidance(const float* img, int H, int W, const int32_t* windows, int n_crops, int crop_h, int crop_w,
+int cseg_jbu_guidance(const cseg_image* img_desc, const int32_t* windows, int n_crops, int crop_h, int crop_w,
                       int pad_top, int pad_left, int gh, int gw, float* guid, void* stream) {
+  ImgView img;
+  CSEG_REQUIRE(make_img_view(img_desc, img) == 0, "jbu_guidance: bad image descriptor");
   CSEG_REQUIRE(n_crops > 0 && gh > 0 && gw > 0 && gh <= crop_h && gw <= crop_w, "jbu_guidance: bad shape");
   const int n = n_crops * gh * gw;
-  cseg_launch(guidance_kernel, dim3(cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, img, H, W, windows, n_crops, crop_h, crop_w, pad_top,
+  cseg_launch(guidance_kernel, dim3(cdiv(n, 256)), dim3(256), 0, (cudaStream_t)stream, img, windows, n_crops, crop_h, crop_w, pad_top,
                                                                   pad_left, gh, gw, (float4*)guid);
   CSEG_LAUNCH_CHECK("jbu_guidance");
   return 0;
 }
 
-int cseg_jbu_guidance_proj(const float* img, int H, int W, const int32_t* windows, int n_crops, int crop_h, int crop_w,
+int cseg_jbu_guidance_proj(const cseg_image* img_desc, const int32_t* windows, int n_crops, int crop_h, int crop_w,
                            int pad_top, int pad_left, int gh, int gw, int key_dim, const float* w0, const float* b0,
                            const float* w3, const float* b3, float* guid, int proj_dtype, void* proj, void* stream) {
+  ImgView img;
+  CSEG_REQUIRE(make_img_view(img_desc, img) == 0, "jbu_guidance_proj: bad image descriptor");
   CSEG_REQUIRE(n_crops > 0 && gh > 0 && gw > 0 && gh <= crop_h && gw <= crop_w, "jbu_guidance_proj: bad shape");
   CSEG_REQUIRE(key_dim == 32 && proj_dtype == CSEG_F16, "jbu_guidance_proj: key_dim 32 / fp16 projections only (bf16 pipeline)");
   CSEG_REQUIRE(gw >= 16, "jbu_guidance_proj: gw=%d must be >= 16 (call cseg_jbu_guidance + cseg_jbu_range_proj instead)", gw);
-  return cseg_jbu_guidance_proj_f16(img, H, W, windows, n_crops, crop_h, crop_w, pad_top, pad_left, gh, gw, w0, b0, w3, b3, guid,
+  return cseg_jbu_guidance_proj_f16(img, windows, n_crops, crop_h, crop_w, pad_top, pad_left, gh, gw, w0, b0, w3, b3, guid,
                                     proj, (cudaStream_t)stream);
 }
 

@@ -229,7 +229,7 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
 // the kernel fix-up read it) and fed straight into the MLP.  FUSED = false is the stand-alone projection.
 template <bool FUSED>
 __global__ void __launch_bounds__(256) range_proj_f16_kernel(const float4* __restrict__ guid, float4* __restrict__ guid_out,
-                                                             const float* __restrict__ img, int H, int W,
+                                                             const ImgView img,
                                                              const int32_t* __restrict__ wins, int crop_h, int crop_w,
                                                              int pad_top, int pad_left, int gh, int gw, int n_pix,
                                                              const float* __restrict__ w0, const float* __restrict__ b0,
@@ -296,13 +296,13 @@ __global__ void __launch_bounds__(256) range_proj_f16_kernel(const float4* __res
         for (int y = ys + tig; y < ye; y += 4) {
           const int cy = y - pad_top;
           if (cy < 0 || cy >= wh) continue;
-          const float* r0 = img + ((size_t)(y1 + cy)) * W + x1 - pad_left;
+          const long long r0 = img_row_off(img, y1 + cy);
           for (int x = xs; x < xe; ++x) {
             const int cx = x - pad_left;
             if (cx >= 0 && cx < ww) {
-              a0 += r0[x];
-              a1 += r0[(size_t)H * W + x];
-              a2 += r0[(size_t)2 * H * W + x];
+              a0 += img_at(img, 0, r0, x1 + cx);
+              a1 += img_at(img, 1, r0, x1 + cx);
+              a2 += img_at(img, 2, r0, x1 + cx);
             }
           }
         }
@@ -372,18 +372,19 @@ int launch(const __half* proj, const float* guid, int n_crops, int gh, int gw, f
 int cseg_jbu_range_proj_f16(const float* guid, int n_pix, const float* w0, const float* b0, const float* w3,
                             const float* b3, void* proj, cudaStream_t st) {
   const int blocks = (int)std::min<long long>(cdiv(cdiv(n_pix, 16), 8), (long long)sm_count() * 8);
+  ImgView none = {};
   cseg_launch(range_proj_f16_kernel<false>, dim3(blocks), dim3(256), 0, st, (const float4*)guid, (float4*)nullptr,
-              (const float*)nullptr, 0, 0, (const int32_t*)nullptr, 0, 0, 0, 0, 1, 1, n_pix, w0, b0, w3, b3, (__half*)proj);
+              none, (const int32_t*)nullptr, 0, 0, 0, 0, 1, 1, n_pix, w0, b0, w3, b3, (__half*)proj);
   CSEG_LAUNCH_CHECK("jbu_range_proj_f16");
   return 0;
 }
 
-int cseg_jbu_guidance_proj_f16(const float* img, int H, int W, const int32_t* windows, int n_crops, int crop_h, int crop_w,
+int cseg_jbu_guidance_proj_f16(const ImgView& img, const int32_t* windows, int n_crops, int crop_h, int crop_w,
                                int pad_top, int pad_left, int gh, int gw, const float* w0, const float* b0, const float* w3,
                                const float* b3, float* guid, void* proj, cudaStream_t st) {
   const int n_pix = n_crops * gh * gw;
   const int blocks = (int)std::min<long long>(cdiv(cdiv(n_pix, 16), 8), (long long)sm_count() * 8);
-  cseg_launch(range_proj_f16_kernel<true>, dim3(blocks), dim3(256), 0, st, (const float4*)nullptr, (float4*)guid, img, H, W,
+  cseg_launch(range_proj_f16_kernel<true>, dim3(blocks), dim3(256), 0, st, (const float4*)nullptr, (float4*)guid, img,
               windows, crop_h, crop_w, pad_top, pad_left, gh, gw, n_pix, w0, b0, w3, b3, (__half*)proj);
   CSEG_LAUNCH_CHECK("jbu_guidance_proj_f16");
   return 0;

@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(256) norm_sim_kernel(const T* __restrict__ fea
 }
 
 // ---------------------------------------------------------------------------------------------
-// A11 + A12 fused.  One thread per output pixel; every crop logit is read exactly once when
-// (out_h,out_w) == (H,W); labels are the only mandatory write.
+// A11 + A12 fused.  Every crop logit is read exactly once when (out_h,out_w) == (H,W); labels are the only
+// mandatory write.
 // ---------------------------------------------------------------------------------------------
 struct AccumParams {
   const float* crop_logits;
@@ -120,14 +120,16 @@ __device__ __forceinline__ float crop_value(const AccumParams& p, int cr, int q,
          ly * (hx * base[y1 * p.lw + x0] + lx * base[y1 * p.lw + x1]);
 }
 
-// averaged logits of canvas pixel (y, x): windows visited in forward_slide order (segmentor.py:416-444)
+// averaged logits of canvas pixel (y, x): candidate windows visited in forward_slide order (segmentor.py:416-444)
 template <int QT>
-__device__ __forceinline__ void canvas_avg(const AccumParams& p, const int4* wins, int y, int x, float (&acc)[QT]) {
+__device__ __forceinline__ void canvas_avg(const AccumParams& p, const int4* wins, const int* cand, int n_cand, int y,
+                                           int x, float (&acc)[QT]) {
 #pragma unroll
   for (int q = 0; q < QT; ++q) acc[q] = 0.f;
   int count = 0;
-  for (int cr = 0; cr < p.n_crops; ++cr) {
-    const int4 w = wins[cr];  // y1, x1, h, w
+  for (int ci = 0; ci < n_cand; ++ci) {
+    const int cr = cand[ci];
+    const int4 w = wins[ci];  // y1, x1, h, w
     const int ly = y - w.x, lx = x - w.y;
     if (ly < 0 || ly >= w.z || lx < 0 || lx >= w.w) continue;
     ++count;
@@ -141,40 +143,11 @@ __device__ __forceinline__ void canvas_avg(const AccumParams& p, const int4* win
     if (q < p.Q) acc[q] = acc[q] / cnt;
 }
 
+// x logit_scale, softmax over Q, per-class max over synonym queries, argmax (lowest index wins ties), threshold
+// (segmentor.py:478-489).  Ordering is decided on the scaled logits (softmax is monotone); probabilities only feed the
+// threshold and the optional probs output.
 template <int QT>
-__global__ void __launch_bounds__(256) accum_argmax_kernel(const AccumParams p) {
-  pdl_grid_sync();
-  extern __shared__ int4 s_wins[];
-  for (int i = threadIdx.x; i < p.n_crops; i += blockDim.x)
-    s_wins[i] = make_int4(p.windows[4 * i], p.windows[4 * i + 1], p.windows[4 * i + 2], p.windows[4 * i + 3]);
-  __syncthreads();
-  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
-  if (ox >= p.out_w) return;
-  float v[QT];
-  if (p.out_h == p.H && p.out_w == p.W) {
-    canvas_avg<QT>(p, s_wins, oy, ox, v);
-    if (p.avg_logits) {
-#pragma unroll
-      for (int q = 0; q < QT; ++q)
-        if (q < p.Q) p.avg_logits[((size_t)q * p.H + oy) * p.W + ox] = v[q];
-    }
-  } else {  // bilinear resize of the averaged canvas to ori_shape (segmentor.py:448-449)
-    int y0, y1, x0, x1;
-    float ly, lx;
-    bilin_coord(oy, p.H, p.out_h, y0, y1, ly);
-    bilin_coord(ox, p.W, p.out_w, x0, x1, lx);
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    float a[QT], b[QT];
-    canvas_avg<QT>(p, s_wins, y0, x0, a);
-    canvas_avg<QT>(p, s_wins, y0, x1, b);
-#pragma unroll
-    for (int q = 0; q < QT; ++q) v[q] = hy * (hx * a[q] + lx * b[q]);
-    canvas_avg<QT>(p, s_wins, y1, x0, a);
-    canvas_avg<QT>(p, s_wins, y1, x1, b);
-#pragma unroll
-    for (int q = 0; q < QT; ++q) v[q] += ly * (hx * a[q] + lx * b[q]);
-  }
-  // x logit_scale, softmax over Q (segmentor.py:478-479)
+__device__ __forceinline__ uint8_t post_process(const AccumParams& p, const int* s_qidx, float (&v)[QT], int oy, int ox) {
   float m = -INFINITY;
 #pragma unroll
   for (int q = 0; q < QT; ++q)
@@ -186,16 +159,13 @@ __global__ void __launch_bounds__(256) accum_argmax_kernel(const AccumParams p) 
 #pragma unroll
   for (int q = 0; q < QT; ++q)
     if (q < p.Q) sum += expf(v[q] - m);
-  // per-class max over its synonym queries, argmax with lowest-index ties (segmentor.py:481-488);
-  // ordering is decided on the scaled logits (softmax is monotone), probabilities only feed the
-  // threshold and the optional probs output.
   float best = -INFINITY;
   int best_k = 0;
   for (int k = 0; k < p.K; ++k) {
     float ck = -INFINITY;
 #pragma unroll
     for (int q = 0; q < QT; ++q)
-      if (q < p.Q && p.query_idx[q] == k) ck = fmaxf(ck, v[q]);
+      if (q < p.Q && s_qidx[q] == k) ck = fmaxf(ck, v[q]);
     if (p.probs) p.probs[((size_t)k * p.out_h + oy) * p.out_w + ox] = expf(ck - m) / sum;
     if (ck > best) {
       best = ck;
@@ -204,7 +174,149 @@ __global__ void __launch_bounds__(256) accum_argmax_kernel(const AccumParams p) 
   }
   const float pmax = expf(best - m) / sum;
   if (pmax < p.prob_thd) best_k = p.bg_idx;  // segmentor.py:489
-  p.labels[(size_t)oy * p.out_w + ox] = (uint8_t)best_k;
+  return (uint8_t)best_k;
+}
+
+// One CTA per tile of (32 PX) x 8 output pixels, PX consecutive pixels per thread.  The windows that touch the tile are
+// binned once per CTA (in forward_slide order, so the fp32 sums keep the reference's order): a pixel then visits
+// <= 4..9 candidates instead of all n_crops.  When the crop logits are at crop resolution and no final resize is needed
+// (the JBU path) the PX pixels of a thread read each crop's logits with one 16-byte load per query.
+template <int QT, int PX>
+__global__ void __launch_bounds__(256) accum_argmax_kernel(const AccumParams p) {
+  pdl_grid_sync();
+  extern __shared__ int4 s_wins[];                              // [n_crops] candidate windows (compacted)
+  int* s_cand = reinterpret_cast<int*>(s_wins + p.n_crops);     // [n_crops] their crop indices
+  __shared__ int s_ncand;
+  __shared__ int s_qidx[QT];
+  const int tid = threadIdx.x;
+  const int ox0 = blockIdx.x * (32 * PX), oy0 = blockIdx.y * 8;
+  const bool direct = (p.out_h == p.H && p.out_w == p.W);
+  if (tid < QT) s_qidx[tid] = tid < p.Q ? p.query_idx[tid] : -1;
+  if (tid < 32) {
+    // canvas rectangle the tile depends on
+    int cy0 = oy0, cy1 = min(oy0 + 7, p.out_h - 1), cx0 = ox0, cx1 = min(ox0 + 32 * PX - 1, p.out_w - 1);
+    if (!direct) {
+      int a, b;
+      float l;
+      bilin_coord(cy0, p.H, p.out_h, a, b, l); cy0 = a;
+      bilin_coord(cy1, p.H, p.out_h, a, b, l); cy1 = b;
+      bilin_coord(cx0, p.W, p.out_w, a, b, l); cx0 = a;
+      bilin_coord(cx1, p.W, p.out_w, a, b, l); cx1 = b;
+    }
+    int n = 0;
+    for (int base = 0; base < p.n_crops; base += 32) {
+      const int i = base + tid;
+      int4 w = make_int4(0, 0, 0, 0);
+      bool hit = false;
+      if (i < p.n_crops) {
+        w = make_int4(p.windows[4 * i], p.windows[4 * i + 1], p.windows[4 * i + 2], p.windows[4 * i + 3]);
+        hit = (w.x <= cy1 && w.x + w.z > cy0 && w.y <= cx1 && w.y + w.w > cx0);
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int pos = n + __popc(mask & ((1u << tid) - 1u));
+        s_wins[pos] = w;
+        s_cand[pos] = i;
+      }
+      n += __popc(mask);
+    }
+    if (tid == 0) s_ncand = n;
+  }
+  __syncthreads();
+  const int n_cand = s_ncand;
+  const int oy = oy0 + (tid >> 5), oxb = ox0 + (tid & 31) * PX;
+  if (oy >= p.out_h || oxb >= p.out_w) return;
+  uint8_t lab[PX];
+  if (direct) {
+    float acc[PX][QT];
+    int cnt[PX];
+#pragma unroll
+    for (int e = 0; e < PX; ++e) {
+      cnt[e] = 0;
+#pragma unroll
+      for (int q = 0; q < QT; ++q) acc[e][q] = 0.f;
+    }
+    const bool same_res = (p.lh == p.crop_h && p.lw == p.crop_w);
+    for (int ci = 0; ci < n_cand; ++ci) {
+      const int4 w = s_wins[ci];
+      const int ly = oy - w.x;
+      if (ly < 0 || ly >= w.z) continue;
+      const int lx0 = oxb - w.y;
+      if (lx0 + PX <= 0 || lx0 >= w.w) continue;
+      const int cr = s_cand[ci];
+      const int cy = ly + p.pad_top, cx0 = lx0 + p.pad_left;
+      if (PX == 4 && same_res && lx0 >= 0 && lx0 + PX <= w.w && ((cx0 | p.lw) & 3) == 0) {
+        const float* base = p.crop_logits + (size_t)cr * p.Q * p.lh * p.lw + (size_t)cy * p.lw + cx0;
+#pragma unroll
+        for (int q = 0; q < QT; ++q)
+          if (q < p.Q) {
+            const float4 v4 = *reinterpret_cast<const float4*>(base + (size_t)q * p.lh * p.lw);
+            acc[0][q] += v4.x;
+            if (PX > 1) acc[1 % PX][q] += v4.y;
+            if (PX > 2) acc[2 % PX][q] += v4.z;
+            if (PX > 3) acc[3 % PX][q] += v4.w;
+          }
+#pragma unroll
+        for (int e = 0; e < PX; ++e) ++cnt[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < PX; ++e) {
+          const int lx = lx0 + e;
+          if (lx < 0 || lx >= w.w || oxb + e >= p.out_w) continue;
+          ++cnt[e];
+#pragma unroll
+          for (int q = 0; q < QT; ++q)
+            if (q < p.Q) acc[e][q] += crop_value(p, cr, q, cy, cx0 + e);
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < PX; ++e) {
+      const int ox = oxb + e;
+      if (ox >= p.out_w) { lab[e] = 0; continue; }
+      const float c = (float)cnt[e];
+#pragma unroll
+      for (int q = 0; q < QT; ++q)
+        if (q < p.Q) {
+          acc[e][q] = acc[e][q] / c;
+          if (p.avg_logits) p.avg_logits[((size_t)q * p.H + oy) * p.W + ox] = acc[e][q];
+        }
+      lab[e] = post_process<QT>(p, s_qidx, acc[e], oy, ox);
+    }
+  } else {  // bilinear resize of the averaged canvas to ori_shape (segmentor.py:448-449)
+    int y0, y1;
+    float ly;
+    bilin_coord(oy, p.H, p.out_h, y0, y1, ly);
+    const float hy = 1.f - ly;
+#pragma unroll 1
+    for (int e = 0; e < PX; ++e) {
+      const int ox = oxb + e;
+      if (ox >= p.out_w) { lab[e] = 0; continue; }
+      int x0, x1;
+      float lx;
+      bilin_coord(ox, p.W, p.out_w, x0, x1, lx);
+      const float hx = 1.f - lx;
+      float v[QT], a[QT], b[QT];
+      canvas_avg<QT>(p, s_wins, s_cand, n_cand, y0, x0, a);
+      canvas_avg<QT>(p, s_wins, s_cand, n_cand, y0, x1, b);
+#pragma unroll
+      for (int q = 0; q < QT; ++q) v[q] = hy * (hx * a[q] + lx * b[q]);
+      canvas_avg<QT>(p, s_wins, s_cand, n_cand, y1, x0, a);
+      canvas_avg<QT>(p, s_wins, s_cand, n_cand, y1, x1, b);
+#pragma unroll
+      for (int q = 0; q < QT; ++q) v[q] += ly * (hx * a[q] + lx * b[q]);
+      lab[e] = post_process<QT>(p, s_qidx, v, oy, ox);
+    }
+  }
+  uint8_t* lrow = p.labels + (size_t)oy * p.out_w + oxb;
+  if (PX == 4 && oxb + 4 <= p.out_w && (((size_t)oy * p.out_w + oxb) & 3) == 0 && ((uintptr_t)p.labels & 3) == 0) {
+    *reinterpret_cast<uint32_t*>(lrow) = (uint32_t)lab[0] | ((uint32_t)lab[1 % PX] << 8) | ((uint32_t)lab[2 % PX] << 16) |
+                                         ((uint32_t)lab[3 % PX] << 24);
+  } else {
+#pragma unroll
+    for (int e = 0; e < PX; ++e)
+      if (oxb + e < p.out_w) lrow[e] = lab[e];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -272,11 +384,18 @@ int cseg_accum_argmax(const float* crop_logits, int n_crops, int Q, int lh, int 
   CSEG_REQUIRE(avg_logits == nullptr || (out_h == H && out_w == W), "accum_argmax: avg_logits needs out size == canvas size");
   AccumParams p{crop_logits, n_crops, Q, lh, lw, crop_h, crop_w, pad_top, pad_left, windows, H, W, out_h, out_w,
                 query_idx, K, logit_scale, prob_thd, bg_idx, labels, probs, avg_logits};
-  dim3 grid(cdiv(out_w, 256), out_h);
-  const size_t smem = (size_t)n_crops * sizeof(int4);
-  if (Q <= 8) cseg_launch(accum_argmax_kernel<8>, grid, dim3(256), smem, (cudaStream_t)stream, p);
-  else if (Q <= 16) cseg_launch(accum_argmax_kernel<16>, grid, dim3(256), smem, (cudaStream_t)stream, p);
-  else cseg_launch(accum_argmax_kernel<32>, grid, dim3(256), smem, (cudaStream_t)stream, p);
+  const size_t smem = (size_t)n_crops * (sizeof(int4) + sizeof(int));
+  CSEG_REQUIRE(smem <= 200 * 1024, "accum_argmax: %d windows do not fit the window table in shared memory", n_crops);
+  if (Q <= 8) {
+    CSEG_SET_SMEM((accum_argmax_kernel<8, 4>), smem);
+    cseg_launch(accum_argmax_kernel<8, 4>, dim3(cdiv(out_w, 128), cdiv(out_h, 8)), dim3(256), smem, (cudaStream_t)stream, p);
+  } else if (Q <= 16) {
+    CSEG_SET_SMEM((accum_argmax_kernel<16, 4>), smem);
+    cseg_launch(accum_argmax_kernel<16, 4>, dim3(cdiv(out_w, 128), cdiv(out_h, 8)), dim3(256), smem, (cudaStream_t)stream, p);
+  } else {
+    CSEG_SET_SMEM((accum_argmax_kernel<32, 2>), smem);
+    cseg_launch(accum_argmax_kernel<32, 2>, dim3(cdiv(out_w, 64), cdiv(out_h, 8)), dim3(256), smem, (cudaStream_t)stream, p);
+  }
   CSEG_LAUNCH_CHECK("accum_argmax");
   return 0;
 }

@@ -24,7 +24,7 @@ __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ img, int HW, fl
 // open_clip/transformer.py:560-562 as an im2col gather (the conv has stride == kernel, no bias)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void patchify_kernel(const float* __restrict__ img, int H, int W, const int32_t* __restrict__ wins,
+__global__ void patchify_kernel(const ImgView img, const int32_t* __restrict__ wins,
                                 int n_crops, int gh, int gw, int pad_top, int pad_left, int ps, T* __restrict__ out,
                                 int ldo) {
   pdl_grid_sync();
@@ -41,9 +41,25 @@ __global__ void patchify_kernel(const float* __restrict__ img, int H, int W, con
       const int c = col / (ps * ps), ky = (col / ps) % ps, kx = col % ps;
       const int cy = (p / gw) * ps + ky - pad_top, cx = (p % gw) * ps + kx - pad_left;
       const int y1 = wins[crop * 4 + 0], x1 = wins[crop * 4 + 1], wh = wins[crop * 4 + 2], ww = wins[crop * 4 + 3];
-      if (cy >= 0 && cy < wh && cx >= 0 && cx < ww) v = img[((size_t)c * H + (y1 + cy)) * W + (x1 + cx)];
+      if (cy >= 0 && cy < wh && cx >= 0 && cx < ww) v = img_at(img, c, img_row_off(img, y1 + cy), x1 + cx);
     }
     out[idx] = from_f32<T>(v);
+  }
+}
+
+// text tower stem (open_clip/model.py:291-293): out[r] = table[idx[r]] + pos[r % L]; pos == nullptr: plain row gather
+// (the EOT-token pick of model.py:302-304)
+__global__ void gather_rows_kernel(const float* __restrict__ table, const long long* __restrict__ idx,
+                                   const float* __restrict__ pos, long long n_rows, int L, int width,
+                                   float* __restrict__ out) {
+  pdl_grid_sync();
+  const long long total = n_rows * width;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / width;
+    const int c = (int)(e - r * width);
+    float v = table[(size_t)idx[r] * width + c];
+    if (pos) v += pos[(size_t)(r % L) * width + c];
+    out[e] = v;
   }
 }
 
@@ -265,7 +281,9 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const T* __re
         s1[t] = -INFINITY;
         s2[t] = -INFINITY;
         if (t < nj && j < L) {
-          if (mode == CSEG_ATTN_STD || mode == CSEG_ATTN_VANILLA) {
+          if (mode == CSEG_ATTN_CAUSAL) {
+            if (j <= i) s1[t] = dot_row<T, HD>(qi, Ks + j * LDS) * scale;
+          } else if (mode == CSEG_ATTN_STD || mode == CSEG_ATTN_VANILLA) {
             s1[t] = dot_row<T, HD>(qi, Ks + j * LDS) * scale;
           } else {
             s1[t] = dot_row<T, HD>(qi, Qs + j * LDS) * scale;
@@ -273,7 +291,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const T* __re
           }
         }
       }
-      if (mode == CSEG_ATTN_STD) {
+      if (mode == CSEG_ATTN_STD || mode == CSEG_ATTN_CAUSAL) {
         warp_softmax(s1, nj);
       } else if (mode == CSEG_ATTN_VANILLA || mode == CSEG_ATTN_CLEARCLIP) {
 #pragma unroll
@@ -314,7 +332,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const T* __re
         }
       }
 #pragma unroll
-      for (int t = 0; t < ATT_JMAX; ++t) p[t] = (lane + 32 * t < L) ? s1[t] : 0.f;
+      for (int t = 0; t < ATT_JMAX; ++t)
+        p[t] = (lane + 32 * t < L && !(mode == CSEG_ATTN_CAUSAL && lane + 32 * t > i)) ? s1[t] : 0.f;
     }
     if (stats != nullptr) {  // outlier_suppression.py:46-49: only P[0,1+i] and P[1+i,1+i] are consumed
       float* st = stats + ((size_t)(crop * heads + head) * 2) * P;
@@ -609,8 +628,10 @@ int cseg_preprocess_u8(const uint8_t* img, int H, int W, const float mean[3], co
   return 0;
 }
 
-int cseg_patchify(const float* img, int H, int W, const int32_t* windows, int n_crops, int crop_h, int crop_w,
+int cseg_patchify(const cseg_image* img_desc, const int32_t* windows, int n_crops, int crop_h, int crop_w,
                   int pad_top, int pad_left, int ps, int out_dtype, void* out, int ldo, void* stream) {
+  ImgView img;
+  CSEG_REQUIRE(make_img_view(img_desc, img) == 0, "patchify: bad image descriptor");
   CSEG_REQUIRE(n_crops > 0 && ps > 0 && crop_h % ps == 0 && crop_w % ps == 0,
                "patchify: crop %dx%d must be a multiple of the patch size %d", crop_h, crop_w, ps);
   CSEG_REQUIRE(ldo >= 3 * ps * ps, "patchify: ldo=%d < %d", ldo, 3 * ps * ps);
@@ -618,12 +639,21 @@ int cseg_patchify(const float* img, int H, int W, const int32_t* windows, int n_
   const long long total = (long long)n_crops * gh * gw * ldo;
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
   if (out_dtype == CSEG_BF16)
-    cseg_launch(patchify_kernel<bf16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, img, H, W, windows, n_crops, gh, gw, pad_top,
+    cseg_launch(patchify_kernel<bf16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, img, windows, n_crops, gh, gw, pad_top,
                                                                     pad_left, ps, (bf16*)out, ldo);
   else
-    cseg_launch(patchify_kernel<float>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, img, H, W, windows, n_crops, gh, gw, pad_top,
+    cseg_launch(patchify_kernel<float>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, img, windows, n_crops, gh, gw, pad_top,
                                                                      pad_left, ps, (float*)out, ldo);
   CSEG_LAUNCH_CHECK("patchify");
+  return 0;
+}
+
+int cseg_gather_rows(const float* table, const long long* idx, const float* pos, long long n_rows, int L, int width,
+                     float* out, void* stream) {
+  CSEG_REQUIRE(table && idx && out && n_rows > 0 && width > 0 && L > 0, "gather_rows: bad arguments");
+  const int blocks = (int)std::min<long long>((n_rows * width + 255) / 256, (long long)sm_count() * 16);
+  cseg_launch(gather_rows_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, table, idx, pos, n_rows, L, width, out);
+  CSEG_LAUNCH_CHECK("gather_rows");
   return 0;
 }
 
@@ -676,7 +706,7 @@ int cseg_attention(int dtype, const void* qkv, int n_crops, int L, int heads, in
                    const float* simmap, float sim_weight, void* out, float* stats, void* stream) {
   CSEG_REQUIRE(n_crops > 0 && heads > 0, "attention: bad shape");
   CSEG_REQUIRE(L >= 2 && L <= ATT_JMAX * 32, "attention: L=%d outside [2, %d]", L, ATT_JMAX * 32);
-  CSEG_REQUIRE(mode >= CSEG_ATTN_STD && mode <= CSEG_ATTN_MASKCLIP, "attention: unknown mode %d", mode);
+  CSEG_REQUIRE(mode >= CSEG_ATTN_STD && mode <= CSEG_ATTN_CAUSAL, "attention: unknown mode %d", mode);
   CSEG_REQUIRE(stats == nullptr || mode == CSEG_ATTN_STD, "attention: stats only with CSEG_ATTN_STD");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == CSEG_BF16) {   // tensor-core kernel; returns 1 for shapes it does not cover
@@ -688,11 +718,15 @@ int cseg_attention(int dtype, const void* qkv, int n_crops, int L, int heads, in
     return launch_attention<bf16, 64>(qkv, n_crops, L, heads, mode, simmap, sim_weight, out, stats, st);
   if (dtype == CSEG_F32 && head_dim == 64)
     return launch_attention<float, 64>(qkv, n_crops, L, heads, mode, simmap, sim_weight, out, stats, st);
+  if (dtype == CSEG_BF16 && head_dim == 32)
+    return launch_attention<bf16, 32>(qkv, n_crops, L, heads, mode, simmap, sim_weight, out, stats, st);
+  if (dtype == CSEG_F32 && head_dim == 32)
+    return launch_attention<float, 32>(qkv, n_crops, L, heads, mode, simmap, sim_weight, out, stats, st);
   if (dtype == CSEG_BF16 && head_dim == 80)
     return launch_attention<bf16, 80>(qkv, n_crops, L, heads, mode, simmap, sim_weight, out, stats, st);
   if (dtype == CSEG_F32 && head_dim == 80)
     return launch_attention<float, 80>(qkv, n_crops, L, heads, mode, simmap, sim_weight, out, stats, st);
-  CSEG_FAIL(CSEG_EUNSUPPORTED, "attention: head_dim=%d dtype=%d not supported (64 or 80)", head_dim, dtype);
+  CSEG_FAIL(CSEG_EUNSUPPORTED, "attention: head_dim=%d dtype=%d not supported (32, 64 or 80)", head_dim, dtype);
 }
 
 int cseg_simmap(const float* x, int n_crops, int L, int width, float temperature, int add_self_similarity,

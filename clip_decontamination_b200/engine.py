@@ -30,11 +30,15 @@ def _round_up(v: int, m: int) -> int:
 
 
 class Workspace:
-    """Grow-only named device buffers (no allocation on the steady-state path)."""
+    """Grow-only named device buffers (no allocation on the steady-state path).
+
+    ``generation`` counts re-allocations: a CUDA graph captured while the buffers had generation g holds raw pointers
+    into them and must not be replayed once any buffer has been replaced (SegEngine.graph checks this and recaptures)."""
 
     def __init__(self, device):
         self.device = device
         self._bufs: Dict[str, torch.Tensor] = {}
+        self.generation = 0
 
     def get(self, name: str, shape: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
         n = 1
@@ -43,6 +47,8 @@ class Workspace:
         nbytes = n * torch.empty((), dtype=dtype).element_size()
         buf = self._bufs.get(name)
         if buf is None or buf.numel() < nbytes:
+            if buf is not None:
+                self.generation += 1              # an existing buffer is replaced: captured graphs are stale
             buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
             self._bufs[name] = buf
         return buf[:nbytes].view(dtype).view(*shape)
@@ -144,7 +150,7 @@ class VisualEngine:
                pad_left: int = 0, model_type: str = 'Experimental', ignore_residual: bool = True,
                sim_cfg: Optional[dict] = None, outlier_cfg: Optional[dict] = None,
                taps: Optional[dict] = None) -> Tuple[torch.Tensor, int]:
-        """img fp32 [3,H,W] (normalised), windows int32 [n,4] (y1,x1,h,w) on the device.
+        """img: ops.Image (or a normalised fp32 [3,H,W] tensor), windows int32 [n,4] (y1,x1,h,w) in canvas rows.
         Returns (tok fp32 [n*L, D] = ln_post(.) @ proj for CLS + patches, L)."""
         if model_type not in ATTN or model_type == 'STD':
             raise NotImplementedError(f'model_type {model_type!r} is not supported by the CUDA path')
@@ -227,6 +233,77 @@ class VisualEngine:
         tok = ws.get('tok', (M, self.D), f32)
         ops.gemm(h, self.projT, tok)
         return tok, L
+
+
+class TextEngine:
+    """CLIP text tower (open_clip/model.py:288-306, transformer.py:1047-1053) on the same kernels as the ViT: token +
+    positional embedding gather, 12 pre-LN blocks (tcgen05 GEMMs, causal tensor-core attention), ln_final on the EOT
+    rows, text_projection.  Init-time only (the prompt-ensembled class embeddings are cached by the segmentor).
+    ``sd``: text-side weights keyed as in the CLIP state dict (token_embedding.weight, positional_embedding,
+    transformer.resblocks.N.*, ln_final.*, text_projection)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], *, width: int, layers: int, heads: int, quick_gelu: bool = False,
+                 precision: str = 'bf16', device='cuda'):
+        assert precision in ('bf16', 'fp32')
+        self.device = torch.device(device)
+        self.cdt = torch.bfloat16 if precision == 'bf16' else torch.float32
+        self.width, self.layers, self.heads = width, layers, heads
+        self.head_dim = width // heads
+        self.act = ACT_QUICKGELU if quick_gelu else ACT_GELU
+        f32 = lambda t: t.detach().to(self.device, torch.float32).contiguous()
+        cd = lambda t: t.detach().to(self.device, torch.float32).to(self.cdt).contiguous()
+        self.tok_emb = f32(sd['token_embedding.weight'])
+        self.pos = f32(sd['positional_embedding'])
+        self.L = self.pos.shape[0]
+        self.ln_final = (f32(sd['ln_final.weight']), f32(sd['ln_final.bias']))
+        self.projT = cd(sd['text_projection'].t())                        # [D, width] = B operand [N, K]
+        self.D = self.projT.shape[0]
+        self.blocks = []
+        for i in range(layers):
+            p = f'transformer.resblocks.{i}.'
+            self.blocks.append(dict(
+                ln1=(f32(sd[p + 'ln_1.weight']), f32(sd[p + 'ln_1.bias'])),
+                ln2=(f32(sd[p + 'ln_2.weight']), f32(sd[p + 'ln_2.bias'])),
+                w_in=cd(sd[p + 'attn.in_proj_weight']), b_in=f32(sd[p + 'attn.in_proj_bias']),
+                w_out=cd(sd[p + 'attn.out_proj.weight']), b_out=f32(sd[p + 'attn.out_proj.bias']),
+                w_fc=cd(sd[p + 'mlp.c_fc.weight']), b_fc=f32(sd[p + 'mlp.c_fc.bias']),
+                w_pr=cd(sd[p + 'mlp.c_proj.weight']), b_pr=f32(sd[p + 'mlp.c_proj.bias'])))
+        self.mlp = self.blocks[0]['w_fc'].shape[0]
+        self.ws = Workspace(self.device)
+
+    def encode(self, tokens: torch.Tensor) -> torch.Tensor:
+        """tokens int64 [n, context_length] -> fp32 [n, D] (un-normalised, like CLIP.encode_text)."""
+        with torch.cuda.device(self.device):
+            tokens = tokens.to(self.device, torch.int64).contiguous()
+            n, L = tokens.shape
+            assert L == self.L
+            ws, width, cdt, f32 = self.ws, self.width, self.cdt, torch.float32
+            M = n * L
+            x = ws.get('x', (M, width), f32)
+            ops.gather_rows(self.tok_emb, tokens.view(-1), self.pos, L, x)              # model.py:291-293
+            h = ws.get('h', (M, width), cdt)
+            qkv = ws.get('qkv', (M, 3 * width), cdt)
+            att = ws.get('att', (M, width), cdt)
+            g = ws.get('mlp', (M, self.mlp), cdt)
+            for b in self.blocks:                                                       # transformer.py:234-254
+                ops.layernorm(x, *b['ln1'], out=h)
+                ops.gemm(h, b['w_in'], qkv, bias=b['b_in'])
+                ops.attention(qkv, n, L, self.heads, self.head_dim, ATTN['CAUSAL'], att)
+                ops.gemm(att, b['w_out'], x, bias=b['b_out'], residual=x)
+                ops.layernorm(x, *b['ln2'], out=h)
+                ops.gemm(h, b['w_fc'], g, bias=b['b_fc'], act=self.act)
+                ops.gemm(g, b['w_pr'], x, bias=b['b_pr'], residual=x)
+            # ln_final is row-wise, so it is applied to the n EOT rows only (EOT has the highest id: argmax, model.py:302-304)
+            rows = torch.arange(n, device=self.device, dtype=torch.int64) * L + tokens.argmax(dim=-1)
+            Mp = _round_up(n, 8)
+            xe = ws.get('xe', (Mp, width), f32)
+            xe[n:].zero_()
+            ops.gather_rows(x, rows, None, 1, xe[:n])
+            he = ws.get('he', (Mp, width), cdt)
+            ops.layernorm(xe, *self.ln_final, out=he)
+            out = torch.empty((Mp, self.D), dtype=f32, device=self.device)
+            ops.gemm(he, self.projT, out)
+            return out[:n]
 
 
 class JBUEngine:
@@ -396,16 +473,17 @@ class SegEngine:
         self.jbu_chunk = jbu_chunk
         self.basis = basis          # bf16: upsample token indicators instead of features when that is cheaper
         self.ws = Workspace(self.device)
-        self._win_cache: Dict[Tuple[int, int], Tuple[torch.Tensor, list]] = {}
-        self._graphs: Dict[Tuple[int, int], dict] = {}
+        self._win_cache: Dict[tuple, Tuple[torch.Tensor, list]] = {}
+        self._graphs: Dict[tuple, dict] = {}
+        self.max_graphs = 8
         self.mean = [122.771, 116.746, 104.094]          # segmentor.py:64-67 (RGB)
         self.std = [68.501, 66.632, 70.323]
 
     def _windows(self, H: int, W: int, B: int = 1):
-        """Windows of B equally sized images stacked vertically into one [3, B*H, W] canvas: the batch dimension of
+        """Windows of B equally sized images stacked vertically into one canvas of B*H rows: the batch dimension of
         slide_inference (segmentor.py:413-449 crops all B images per window) becomes B times as many crops, and no
         window straddles two images."""
-        key = (H, W, B)
+        key = (H, W, B, self.stride, self.crop)
         if key not in self._win_cache:
             if self.crop > 0:
                 wl = slide_windows(H, W, self.stride, self.crop)
@@ -415,12 +493,21 @@ class SegEngine:
             self._win_cache[key] = (torch.tensor(wl, dtype=torch.int32, device=self.device), wl)
         return self._win_cache[key]
 
-    def crop_logits(self, img: torch.Tensor, taps: Optional[dict] = None, batch: int = 1):
-        """Per-crop cosine logits (forward_feature, segmentor.py:286-392) for every window of `img`
-        (fp32 [3,H,W] normalised, on the device; with batch = B > 1, B images stacked to [3, B*H, W]).
-        Returns (logits fp32 [n,Q,lh,lw], geometry)."""
-        _, H, W = img.shape
-        assert H % batch == 0
+    def _as_image(self, img, batch: int = 1) -> Tuple[ops.Image, int]:
+        """(ops.Image, B).  A plain fp32 tensor [3, B*H, W] is the legacy stacked canvas (B given by `batch`)."""
+        if isinstance(img, ops.Image):
+            assert batch in (1, img.B)
+            return img, img.B
+        im = ops.Image.normalised(img)
+        assert im.H % batch == 0
+        return im, batch
+
+    def crop_logits(self, img, taps: Optional[dict] = None, batch: int = 1):
+        """Per-crop cosine logits (forward_feature, segmentor.py:286-392) for every window of `img` (an ops.Image, or
+        a normalised fp32 [3,H,W] tensor on the device; with batch = B > 1 the tensor holds B images stacked to
+        [3, B*H, W]).  Returns (logits fp32 [n,Q,lh,lw], geometry)."""
+        img, batch = self._as_image(img, batch)
+        H, W = img.H, img.W
         win_dev, wl = self._windows(H // batch, W, batch)
         n = len(wl)
         wh, ww = wl[0][2], wl[0][3]
@@ -430,6 +517,10 @@ class SegEngine:
         else:
             pl = pr = pt = pb = 0
             wh, ww = (wh // ps) * ps, (ww // ps) * ps                # conv stride drops the remainder
+            if self.up is not None and (wh, ww) != (wl[0][2], wl[0][3]):
+                # the reference's view(1, C, H*W) of the upsampled grid fails here too (segmentor.py:372)
+                raise ValueError(f'whole-image inference with the x16 upsampler needs H, W multiples of {ps}, '
+                                 f'got {wl[0][2]}x{wl[0][3]}')
         crop_h, crop_w = wh + pt + pb, ww + pl + pr
         gh, gw = crop_h // ps, crop_w // ps
         P = gh * gw
@@ -471,75 +562,136 @@ class SegEngine:
         geom = dict(windows=win_dev, crop_h=crop_h, crop_w=crop_w, pad_top=pt, pad_left=pl, H=H, W=W, n=n)
         return logits, geom
 
-    def segment(self, img: torch.Tensor, ori_shape: Optional[Tuple[int, int]] = None, *, labels=None,
+    def segment(self, img, ori_shape: Optional[Tuple[int, int]] = None, *, labels=None,
                 want_probs: bool = False, want_logits: bool = False, taps: Optional[dict] = None, batch: int = 1):
         """predict() for one image: labels uint8 [out_h,out_w] (+ probs [K,..] / averaged logits [Q,H,W]).
-        batch = B > 1: `img` holds B images stacked vertically ([3, B*H, W]) and so do the outputs; every crop-level
-        kernel then works on B times as many crops per launch (ori_shape must be None)."""
-        assert batch == 1 or ori_shape is None
-        logits, g = self.crop_logits(img, taps, batch)
-        H, W = g['H'], g['W']
-        out_h, out_w = (H, W) if ori_shape is None else (int(ori_shape[0]), int(ori_shape[1]))
-        if labels is None:
-            labels = torch.empty((out_h, out_w), dtype=torch.uint8, device=self.device)
-        probs = torch.empty((self.K, out_h, out_w), dtype=torch.float32, device=self.device) if want_probs else None
-        avg = torch.empty((self.Q, H, W), dtype=torch.float32, device=self.device) \
-            if (want_logits and (out_h, out_w) == (H, W)) else None
-        ops.accum_argmax(logits, g['windows'], g['crop_h'], g['crop_w'], g['pad_top'], g['pad_left'], H, W,
-                         out_h, out_w, self.query_idx, self.K, self.logit_scale, self.prob_thd, self.bg_idx,
-                         labels, probs, avg)
+        `img` is an ops.Image or a normalised fp32 tensor.  batch = B > 1 (or an Image of B images): every crop-level
+        kernel works on B times as many crops per launch and the outputs are the B results stacked vertically
+        (ori_shape must be None)."""
+        with torch.cuda.device(self.device):
+            img, batch = self._as_image(img, batch)
+            assert batch == 1 or ori_shape is None
+            logits, g = self.crop_logits(img, taps, batch)
+            H, W = g['H'], g['W']
+            out_h, out_w = (H, W) if ori_shape is None else (int(ori_shape[0]), int(ori_shape[1]))
+            if labels is None:
+                labels = torch.empty((out_h, out_w), dtype=torch.uint8, device=self.device)
+            probs = torch.empty((self.K, out_h, out_w), dtype=torch.float32, device=self.device) if want_probs else None
+            avg = None
+            if want_logits and self.crop <= 0:          # whole image: forward_feature's output at ori_shape
+                avg = torch.empty((self.Q, out_h, out_w), dtype=torch.float32, device=self.device)
+            elif want_logits and (out_h, out_w) == (H, W):
+                avg = torch.empty((self.Q, H, W), dtype=torch.float32, device=self.device)
+            if self.crop > 0:
+                ops.accum_argmax(logits, g['windows'], g['crop_h'], g['crop_w'], g['pad_top'], g['pad_left'], H, W,
+                                 out_h, out_w, self.query_idx, self.K, self.logit_scale, self.prob_thd, self.bg_idx,
+                                 labels, probs, avg)
+            else:
+                # whole image (segmentor.py:470-471): forward_feature interpolates the [lh, lw] logits straight to
+                # ori_shape (one bilinear resize, :388-391): a single window of the output size
+                win = self._whole_window(out_h, out_w)
+                ops.accum_argmax(logits, win, out_h, out_w, 0, 0, out_h, out_w, out_h, out_w, self.query_idx, self.K,
+                                 self.logit_scale, self.prob_thd, self.bg_idx, labels, probs, avg)
         return labels, probs, avg
 
-    # ---- CUDA-graph replay of the whole per-image launch sequence --------------------------------
-    def graph(self, H: int, W: int, B: int = 1) -> dict:
-        """Capture preprocess_u8 -> segment for B uint8 images of H x W once (a few hundred launches) and
-        replay it afterwards: the per-launch host cost (Python, ctypes, tensor-map encodes) is paid at
-        capture time only.  Static buffers: 'u8' [B,H,W,3] uint8 BGR in, 'labels' [B,H,W] uint8 out."""
-        key = (H, W, B)
-        if key in self._graphs:
-            return self._graphs[key]
-        st = dict(u8=torch.zeros((B, H, W, 3), dtype=torch.uint8, device=self.device),
-                  img=torch.empty((3, B * H, W), dtype=torch.float32, device=self.device),
-                  labels=torch.empty((B, H, W), dtype=torch.uint8, device=self.device))
+    def _whole_window(self, h: int, w: int) -> torch.Tensor:
+        key = ('whole', h, w)
+        if key not in self._win_cache:
+            self._win_cache[key] = (torch.tensor([(0, 0, h, w)], dtype=torch.int32, device=self.device), None)
+        return self._win_cache[key][0]
 
-        def run():
-            ops.preprocess_u8(st['u8'].view(B * H, W, 3), self.mean, self.std, st['img'])
-            self.segment(st['img'], None, labels=st['labels'].view(B * H, W), batch=B)
+    # ---- CUDA-graph replay of the whole per-batch launch sequence ----------------------------------
+    def _generations(self):
+        return (self.ws.generation, self.v.ws.generation, self.up.ws.generation if self.up is not None else 0)
 
-        cur = torch.cuda.current_stream(self.device)
-        side = torch.cuda.Stream(self.device)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            run()                                    # warm-up: sizes every workspace before the capture
-            run()
-        cur.wait_stream(side)
-        torch.cuda.synchronize(self.device)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            run()
-        st['graph'] = g
+    def _static_input(self, kind: str, B: int, H: int, W: int) -> torch.Tensor:
+        if kind == 'u8hwc':
+            return torch.zeros((B, H, W, 3), dtype=torch.uint8, device=self.device)
+        if kind == 'u8chw':
+            return torch.zeros((B, 3, H, W), dtype=torch.uint8, device=self.device)
+        if kind == 'f32':
+            return torch.zeros((B, 3, H, W), dtype=torch.float32, device=self.device)
+        raise ValueError(kind)
+
+    def _image_of(self, kind: str, t: torch.Tensor) -> ops.Image:
+        if kind == 'f32':
+            return ops.Image.normalised(t)
+        return ops.Image.u8(t, 'hwc' if kind == 'u8hwc' else 'chw', self.mean, self.std)
+
+    def graph(self, H: int, W: int, B: int = 1, kind: str = 'u8hwc',
+              ori_shape: Optional[Tuple[int, int]] = None) -> dict:
+        """Capture the launch sequence for B images of H x W once (a few hundred launches) and replay it afterwards:
+        the per-launch host cost (Python, ctypes, tensor-map encodes) is paid at capture time only.
+        kind: 'u8hwc' uint8 [B,H,W,3] BGR (cv2 / predict_u8), 'u8chw' uint8 [B,3,H,W] BGR (mmengine test_step),
+        'f32' normalised [B,3,H,W] (predict).  Static buffers: st['in'] and st['labels'] (uint8 [B,out_h,out_w]).
+        A graph holds raw pointers into the grow-only workspaces: it is discarded and recaptured when any of them has
+        been re-allocated since the capture (a larger problem ran in between)."""
+        key = (H, W, B, kind, ori_shape, self.stride, self.crop)
+        st = self._graphs.get(key)
+        if st is not None and st['gen'] == self._generations():
+            if next(reversed(self._graphs)) != key:      # keep the dict in least-recently-used order
+                self._graphs[key] = self._graphs.pop(key)
+            return st
+        while st is None and len(self._graphs) >= self.max_graphs:      # datasets with many image sizes: bound the cache
+            self._graphs.pop(next(iter(self._graphs)))
+        with torch.cuda.device(self.device):
+            if st is None:
+                oh, ow = (H, W) if ori_shape is None else (int(ori_shape[0]), int(ori_shape[1]))
+                st = {'in': self._static_input(kind, B, H, W),
+                      'labels': torch.empty((B, oh, ow), dtype=torch.uint8, device=self.device)}
+                st['image'] = self._image_of(kind, st['in'])
+            oh, ow = st['labels'].shape[1:]
+
+            def run():
+                self.segment(st['image'], ori_shape, labels=st['labels'].view(B * oh, ow))
+
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                run()                                    # warm-up: sizes every workspace before the capture
+                run()
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run()
+            st['graph'] = g
+            st['gen'] = self._generations()
         self._graphs[key] = st
         return st
 
+    def segment_batch(self, x: torch.Tensor, kind: str, ori_shape: Optional[Tuple[int, int]] = None,
+                      labels_out: Optional[torch.Tensor] = None, use_graph: bool = True,
+                      copy_out: bool = True) -> torch.Tensor:
+        """B equally sized images (host pinned or device tensor laid out as `kind`, see graph()) -> uint8 labels
+        [B,out_h,out_w] on the device.  The batch runs as ONE launch sequence over B times as many crops.
+        With copy_out=False the returned tensor is the graph's static output buffer, overwritten by the next call."""
+        B = x.shape[0]
+        H, W = (x.shape[1], x.shape[2]) if kind == 'u8hwc' else (x.shape[2], x.shape[3])
+        assert B == 1 or ori_shape is None
+        with torch.cuda.device(self.device):
+            if not use_graph:
+                xd = x.to(self.device, non_blocking=True).contiguous()
+                oh, ow = (H, W) if ori_shape is None else (int(ori_shape[0]), int(ori_shape[1]))
+                if labels_out is None:
+                    labels_out = torch.empty((B, oh, ow), dtype=torch.uint8, device=self.device)
+                self.segment(self._image_of(kind, xd), ori_shape, labels=labels_out.view(B * oh, ow))
+                return labels_out
+            st = self.graph(H, W, B, kind, ori_shape)
+            st['in'].copy_(x, non_blocking=True)         # H2D (or D2D) into the static input
+            st['graph'].replay()
+            if labels_out is not None:
+                labels_out.copy_(st['labels'], non_blocking=True)
+                return labels_out
+            return st['labels'].clone() if copy_out else st['labels']
+
     def segment_u8(self, img_hwc_bgr_u8: torch.Tensor, labels_out: Optional[torch.Tensor] = None,
-                   use_graph: bool = True) -> torch.Tensor:
+                   use_graph: bool = True, copy_out: bool = True) -> torch.Tensor:
         """uint8 HWC BGR image [H,W,3] -> uint8 labels [H,W] on the device, or a batch [B,H,W,3] -> [B,H,W]
-        (host pinned or device input).  A batch runs as ONE launch sequence over B times as many crops."""
+        (host pinned or device input)."""
         batched = img_hwc_bgr_u8.dim() == 4
-        B = img_hwc_bgr_u8.shape[0] if batched else 1
-        H, W = img_hwc_bgr_u8.shape[-3], img_hwc_bgr_u8.shape[-2]
-        if not use_graph:
-            x = img_hwc_bgr_u8.to(self.device, non_blocking=True).contiguous()
-            img = ops.preprocess_u8(x.view(B * H, W, 3), self.mean, self.std)
-            if labels_out is None:
-                labels_out = torch.empty((B, H, W) if batched else (H, W), dtype=torch.uint8, device=self.device)
-            self.segment(img, None, labels=labels_out.view(B * H, W), batch=B)
-            return labels_out
-        st = self.graph(H, W, B)
-        st['u8'].copy_(img_hwc_bgr_u8.view(B, H, W, 3), non_blocking=True)   # H2D (or D2D) into the static input
-        st['graph'].replay()
-        out = st['labels'] if batched else st['labels'][0]
-        if labels_out is not None:
-            labels_out.copy_(out, non_blocking=True)
-            return labels_out
-        return out
+        x = img_hwc_bgr_u8 if batched else img_hwc_bgr_u8.unsqueeze(0)
+        lo = labels_out if (labels_out is None or batched) else labels_out.unsqueeze(0)
+        out = self.segment_batch(x, 'u8hwc', None, lo, use_graph, copy_out)
+        return out if batched else out[0]

@@ -1,7 +1,9 @@
 """``CLIP`` object returned by ``create_model``: a parameter holder whose state-dict keys equal the
 reference's (open_clip/model.py:220-254, open_clip/transformer.py:338-444) so real checkpoints load
-with ``load_state_dict``; ``encode_image`` runs on the CUDA engine, ``encode_text`` (init-time prompt
-ensemble only, segmentor.py:157-174) runs the text tower in plain PyTorch.
+with ``load_state_dict``; ``encode_image`` and ``encode_text`` (init-time prompt ensemble only,
+segmentor.py:157-174) run on the CUDA engines (``VisualEngine`` / ``TextEngine``, engine.py).  A model that lives
+on the CPU can still evaluate ``encode_text`` in plain PyTorch: that form exists for the CPU test that pins the
+tokenizer + state-dict mapping against the reference golden, never for the segmentation path.
 """
 from collections import OrderedDict
 from typing import Optional
@@ -78,13 +80,28 @@ class CLIP(nn.Module):
         self.vision_cfg = dict(v)
         self.precision = precision          # 'bf16' (tcgen05 path) or 'fp32' (verification mode)
         self._engine = None
+        self._text_engine = None
         for p in self.parameters():
             p.requires_grad_(False)
 
     # ---- engine management ------------------------------------------------------------------
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         self._engine = None
+        self._text_engine = None
         return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def text_engine(self, device=None):
+        """The CUDA text tower over a snapshot of the current text-side weights (built lazily)."""
+        from ..engine import TextEngine
+        device = torch.device(device if device is not None else self.text_projection.device)
+        if device.type != 'cuda':
+            raise RuntimeError('clip_decontamination_b200 runs on CUDA only (there is no CPU fallback)')
+        if getattr(self, '_text_engine', None) is None or self._text_engine.device != device:
+            sd = {k: p.detach() for k, p in self.state_dict().items() if not k.startswith('visual.')}
+            self._text_engine = TextEngine(sd, width=self.transformer.width, layers=self.transformer.layers,
+                                           heads=self.transformer.heads, quick_gelu=self.quick_gelu,
+                                           precision=self.precision, device=device)
+        return self._text_engine
 
     def visual_engine(self, device=None):
         """The CUDA engine over a snapshot of the current ``visual.*`` weights (built lazily)."""
@@ -132,9 +149,17 @@ class CLIP(nn.Module):
             cls, feats = F.normalize(cls, dim=-1), F.normalize(feats, dim=-1)
         return (cls, feats) if output_cls_token else feats
 
-    # ---- open_clip/model.py:288-306 (init-time only; PyTorch) -------------------------------
+    # ---- open_clip/model.py:288-306 (init-time only) ------------------------------------------
     @torch.no_grad()
     def encode_text(self, text, normalize: bool = False):
+        if text.is_cuda:                                              # libclipseg kernels (TextEngine)
+            x = self.text_engine(text.device).encode(text)
+            return F.normalize(x, dim=-1) if normalize else x
+        return self.encode_text_torch(text, normalize)
+
+    @torch.no_grad()
+    def encode_text_torch(self, text, normalize: bool = False):
+        """Plain-PyTorch text tower for a model held on the CPU (CPU checker of the tokenizer / weight mapping)."""
         x = self.token_embedding(text).float() + self.positional_embedding.float()
         heads = self.transformer.heads
         mask = self.attn_mask.to(x.device)

@@ -4,10 +4,9 @@ Own implementation of the published CLIP BPE scheme (lower-case, whitespace clea
 -> unicode table, merges ranked by the vocabulary file, <start_of_text> / <end_of_text>, zero padding
 to 77) -- behaviour contract: open_clip/tokenizer.py:83-85,250-257,270 of the reference.
 
-The merges file (``bpe_simple_vocab_16e6.txt.gz``, the public OpenAI CLIP vocabulary, 1.36 MB) is data
-and is not vendored here; it is looked up in ``$CLIPSEG_BPE_VOCAB``, next to this file, in an installed
-``open_clip`` / ``clip`` package, or in the reference checkout.  Without it ``tokenize`` raises -- use
-cached ``query_features`` instead.
+The merge table is data: ``clip_bpe_merges.txt.gz`` next to this file holds the 48 894 merge rules CLIP reads from
+the public OpenAI vocabulary (``bpe_simple_vocab_16e6.txt.gz`` lines 1..48894; derived by tools/make_bpe_merges.py).
+``$CLIPSEG_BPE_VOCAB`` may point at either file instead.
 """
 import gzip
 import html
@@ -20,23 +19,13 @@ import torch
 
 CONTEXT_LENGTH = 77
 _VOCAB_NAME = 'bpe_simple_vocab_16e6.txt.gz'
+_MERGES_NAME = 'clip_bpe_merges.txt.gz'
+_N_MERGES = 49152 - 256 - 2
 
 
 def find_bpe_vocab():
-    cands = [os.environ.get('CLIPSEG_BPE_VOCAB', ''),
-             os.path.join(os.path.dirname(os.path.abspath(__file__)), _VOCAB_NAME)]
-    repo = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    cands.append(os.path.join(repo, 'baseline', '_ref', 'open_clip', _VOCAB_NAME))
-    for mod in ('open_clip', 'clip'):
-        try:
-            import importlib.util
-            spec = importlib.util.find_spec(mod)
-            if spec and spec.origin and 'clip_decontamination_b200' not in spec.origin:
-                cands.append(os.path.join(os.path.dirname(spec.origin), _VOCAB_NAME))
-        except Exception:
-            pass
-    cands.append(os.path.join(os.environ.get('CLIPSEG_REF', '/root/reference'), 'open_clip', _VOCAB_NAME))
-    for c in cands:
+    here = os.path.dirname(os.path.abspath(__file__))
+    for c in (os.environ.get('CLIPSEG_BPE_VOCAB', ''), os.path.join(here, _MERGES_NAME), os.path.join(here, _VOCAB_NAME)):
         if c and os.path.isfile(c):
             return c
     return None
@@ -57,8 +46,11 @@ def _byte_table():
 class BPETokenizer:
     def __init__(self, vocab_path: str):
         self.byte_enc = _byte_table()
-        merges = gzip.open(vocab_path).read().decode('utf-8').split('\n')
-        merges = [tuple(m.split()) for m in merges[1:49152 - 256 - 2 + 1]]
+        lines = gzip.open(vocab_path).read().decode('utf-8').split('\n')
+        if lines[0].startswith('"bpe_simple_vocab') or '#version' in lines[0]:      # the original OpenAI file: header line
+            lines = lines[1:]
+        merges = [tuple(m.split()) for m in lines[:_N_MERGES]]
+        assert len(merges) == _N_MERGES and all(len(m) == 2 for m in merges), 'truncated BPE merge table'
         vocab = list(self.byte_enc.values())
         vocab = vocab + [v + '</w>' for v in vocab] + [''.join(m) for m in merges]
         vocab += ['<start_of_text>', '<end_of_text>']
@@ -121,8 +113,6 @@ def tokenize(texts: Union[str, List[str]], context_length: int = CONTEXT_LENGTH)
     if _tok is None:
         path = find_bpe_vocab()
         if path is None:
-            raise RuntimeError(
-                f'{_VOCAB_NAME} not found (set CLIPSEG_BPE_VOCAB or install open_clip); the text cache cannot be '
-                f'built without the CLIP vocabulary -- pass precomputed query_features instead')
+            raise RuntimeError(f'{_MERGES_NAME} not found next to {__file__} (set CLIPSEG_BPE_VOCAB)')
         _tok = BPETokenizer(path)
     return _tok(texts, context_length)

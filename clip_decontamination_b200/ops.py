@@ -9,30 +9,69 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import lib, check, F32, BF16, F16
+from ._lib import lib, check, F32, BF16, F16, U8
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
+
+MEAN_RGB = (122.771, 116.746, 104.094)        # segmentor.py:64-67 (SegDataPreProcessor, after bgr_to_rgb)
+STD_RGB = (68.501, 66.632, 70.323)
 
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _ptr(t: Optional[torch.Tensor]):
-    if t is None:
-        return None
-    if not t.is_cuda:
-        raise _lib.ClipSegError('libclipseg needs CUDA tensors (there is no CPU path)')
-    if not t.is_contiguous():
-        raise _lib.ClipSegError('libclipseg needs contiguous tensors')
-    return C.c_void_p(t.data_ptr())
+class Image:
+    """``cseg_image`` over a torch tensor: how the kernels that read the input (patchify, JBU guidance) address it.
+    A batch of B equally sized images is ONE canvas of B*h rows (image b = rows [b*h, (b+1)*h)); no copy, no
+    separate preprocessing pass -- uint8 inputs are normalised on load ((x - mean) / std, segmentor.py:64-67).
 
+      Image.normalised(t)   t fp32 [3,H,W] or [B,3,H,W]: already normalised RGB (what predict() receives)
+      Image.u8(t, 'hwc')    t uint8 [H,W,3] / [B,H,W,3], BGR (cv2 / predict_u8)
+      Image.u8(t, 'chw')    t uint8 [3,H,W] / [B,3,H,W], BGR (mmengine PackSegInputs -> test_step)
+    """
 
-def _dt(t: torch.Tensor) -> int:
-    try:
-        return _DT[t.dtype]
-    except KeyError:
-        raise _lib.ClipSegError(f'unsupported dtype {t.dtype} (float32 / bfloat16)')
+    def __init__(self, t: torch.Tensor, kind: str, B: int, h: int, W: int, strides, chan=(0, 1, 2),
+                 mean=MEAN_RGB, std=STD_RGB):
+        if not t.is_cuda:
+            raise _lib.ClipSegError('libclipseg needs CUDA tensors (there is no CPU path)')
+        if not t.is_contiguous():
+            raise _lib.ClipSegError('libclipseg needs contiguous tensors')
+        self.tensor, self.kind, self.B, self.h, self.W, self.H = t, kind, B, h, W, B * h
+        d = _lib.CsegImage()
+        d.data = t.data_ptr()
+        d.dtype = U8 if t.dtype == torch.uint8 else F32
+        d.H, d.W, d.img_h = B * h, W, h
+        d.stride_img, d.stride_c, d.stride_y, d.stride_x = strides
+        d.chan = (C.c_int * 3)(*chan)
+        d.mean = (C.c_float * 3)(*mean)
+        d.std = (C.c_float * 3)(*std)
+        self.desc = d
+
+    @property
+    def device(self):
+        return self.tensor.device
+
+    @classmethod
+    def normalised(cls, t: torch.Tensor):
+        assert t.dtype == torch.float32 and t.dim() in (3, 4)
+        if t.dim() == 3:
+            _, H, W = t.shape
+            return cls(t, 'f32', 1, H, W, (0, H * W, W, 1))
+        B, _, H, W = t.shape
+        return cls(t, 'f32', B, H, W, (3 * H * W, H * W, W, 1))
+
+    @classmethod
+    def u8(cls, t: torch.Tensor, layout: str = 'hwc', mean=MEAN_RGB, std=STD_RGB, bgr_to_rgb: bool = True):
+        assert t.dtype == torch.uint8 and t.dim() in (3, 4) and layout in ('hwc', 'chw')
+        if t.dim() == 3:
+            t = t.unsqueeze(0)
+        chan = (2, 1, 0) if bgr_to_rgb else (0, 1, 2)
+        if layout == 'hwc':
+            B, H, W, _ = t.shape
+            return cls(t, 'u8hwc', B, H, W, (3 * H * W, 1, 3 * W, 3), chan, mean, std)
+        B, _, H, W = t.shape
+        return cls(t, 'u8chw', B, H, W, (3 * H * W, H * W, W, 1), chan, mean, std)
 
 
 def preprocess_u8(img_hwc_bgr: torch.Tensor, mean, std, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -45,12 +84,22 @@ def preprocess_u8(img_hwc_bgr: torch.Tensor, mean, std, out: Optional[torch.Tens
     return out
 
 
-def patchify(img: torch.Tensor, windows: torch.Tensor, crop_h: int, crop_w: int, pad_top: int, pad_left: int,
+def _image(img) -> Image:
+    return img if isinstance(img, Image) else Image.normalised(img)
+
+
+def patchify(img, windows: torch.Tensor, crop_h: int, crop_w: int, pad_top: int, pad_left: int,
              ps: int, out: torch.Tensor):
-    _, H, W = img.shape
-    assert img.dtype == torch.float32 and windows.dtype == torch.int32
-    check(lib.cseg_patchify(_ptr(img), H, W, _ptr(windows), windows.shape[0], crop_h, crop_w, pad_top, pad_left,
-                            ps, _dt(out), _ptr(out), out.shape[1], _stream()))
+    assert windows.dtype == torch.int32
+    check(lib.cseg_patchify(C.byref(_image(img).desc), _ptr(windows), windows.shape[0], crop_h, crop_w, pad_top,
+                            pad_left, ps, _dt(out), _ptr(out), out.shape[1], _stream()))
+    return out
+
+
+def gather_rows(table: torch.Tensor, idx: torch.Tensor, pos: Optional[torch.Tensor], L: int, out: torch.Tensor):
+    """out[r] = table[idx[r]] (+ pos[r % L]): token embedding + positional embedding of the text tower, and the EOT pick."""
+    assert table.dtype == torch.float32 and idx.dtype == torch.int64 and out.dtype == torch.float32
+    check(lib.cseg_gather_rows(_ptr(table), _ptr(idx), _ptr(pos), idx.numel(), L, table.shape[1], _ptr(out), _stream()))
     return out
 
 
@@ -117,18 +166,16 @@ def cls_debias(tok, n_crops, L, D, factor, feats, cls_unit=None, rows_per_crop=0
 
 
 def jbu_guidance(img, windows, crop_h, crop_w, pad_top, pad_left, gh, gw, out):
-    _, H, W = img.shape
-    check(lib.cseg_jbu_guidance(_ptr(img), H, W, _ptr(windows), windows.shape[0], crop_h, crop_w, pad_top, pad_left,
-                                gh, gw, _ptr(out), _stream()))
+    check(lib.cseg_jbu_guidance(C.byref(_image(img).desc), _ptr(windows), windows.shape[0], crop_h, crop_w, pad_top,
+                                pad_left, gh, gw, _ptr(out), _stream()))
     return out
 
 
 def jbu_guidance_proj(img, windows, crop_h, crop_w, pad_top, pad_left, gh, gw, w0, b0, w3, b3, guid, proj):
     """guidance + range projection of one stage in one kernel (bf16 pipeline; proj fp16)."""
-    _, H, W = img.shape
-    check(lib.cseg_jbu_guidance_proj(_ptr(img), H, W, _ptr(windows), windows.shape[0], crop_h, crop_w, pad_top, pad_left,
-                                     gh, gw, 32, _ptr(w0), _ptr(b0), _ptr(w3), _ptr(b3), _ptr(guid), _dt(proj), _ptr(proj),
-                                     _stream()))
+    check(lib.cseg_jbu_guidance_proj(C.byref(_image(img).desc), _ptr(windows), windows.shape[0], crop_h, crop_w, pad_top,
+                                     pad_left, gh, gw, 32, _ptr(w0), _ptr(b0), _ptr(w3), _ptr(b3), _ptr(guid), _dt(proj),
+                                     _ptr(proj), _stream()))
     return guid, proj
 
 

@@ -100,6 +100,7 @@ class SegmentorEx(BaseSegmentor):
                  query_features=None,
                  net=None,
                  upsampler_state_dict=None,
+                 use_graph=True,
                  ):
         data_preprocessor = SegDataPreProcessor(
             mean=[122.771, 116.746, 104.094],
@@ -140,17 +141,8 @@ class SegmentorEx(BaseSegmentor):
         self.num_queries = len(query_words)
         self.num_classes = max(query_idx) + 1
         self.query_idx = torch.Tensor(query_idx).to(torch.int64).to(device)
-        if query_features is None:                                   # segmentor.py:157-174 (init-time, PyTorch)
-            feats = []
-            with torch.no_grad():
-                for qw in query_words:
-                    query = self.tokenizer([temp(qw) for temp in openai_imagenet_template]).to(device)
-                    feature = self.net.encode_text(query)
-                    feature /= feature.norm(dim=-1, keepdim=True)
-                    feature = feature.mean(dim=0)
-                    feature /= feature.norm()
-                    feats.append(feature.unsqueeze(0))
-            query_features = torch.cat(feats, dim=0)
+        if query_features is None:                                   # segmentor.py:157-174 (init-time)
+            query_features = self._text_cache(query_words, device)
         self.query_features = query_features.to(device).float()
         assert self.query_features.shape[0] == self.num_queries
         self.dtype = self.query_features.dtype
@@ -179,6 +171,7 @@ class SegmentorEx(BaseSegmentor):
             out_cfg['contamination_temp'] = self.net.visual.outlier_suppressor.contamination_temp
         self.result_dir, self.heatmap_dir = result_dir, heatmap_dir
         self.output_seg_logits = output_seg_logits or bool(heatmap_dir)
+        self.use_graph = use_graph
 
         up_engine = None
         if self.apply_sim_feat_up:                                   # segmentor.py:278-284
@@ -198,6 +191,54 @@ class SegmentorEx(BaseSegmentor):
                                 cls_token_lambda=cls_token_lambda, global_debias_factor=global_debias_factor,
                                 bg_idx=bg_idx, upsampler=up_engine, sim_cfg=sim_cfg, outlier_cfg=out_cfg)
 
+    # ---- A13 / N3: prompt-ensembled class embeddings, cached on disk ------------------------------
+    def _text_cache(self, query_words, device):
+        """segmentor.py:157-174: per query word the 80 imagenet templates -> tokenizer -> text tower (TextEngine, the
+        same tcgen05 GEMM / tensor-core attention kernels as the ViT) -> unit norm -> mean -> unit norm.  The result
+        only depends on the text-side weights, the words and the templates, so it is cached under
+        $CLIPSEG_CACHE_DIR (default ~/.cache/clip_decontamination_b200) keyed by a fingerprint of those."""
+        import hashlib
+        n_t = len(openai_imagenet_template)
+        hsh = hashlib.sha1()
+        hsh.update(repr((list(query_words), [t('X') for t in openai_imagenet_template], self.net.precision,
+                         self.net.quick_gelu)).encode())
+        for k, p in sorted(self.net.state_dict().items()):
+            if k.startswith('visual.'):
+                continue
+            pf = p.detach().float().flatten()
+            step = max(1, pf.numel() // 4096)
+            hsh.update(k.encode())
+            hsh.update(np.asarray(list(p.shape) + [float(pf.double().sum()), float(pf.double().abs().sum())]).tobytes())
+            hsh.update(pf[::step].cpu().numpy().tobytes())
+        cdir = os.environ.get('CLIPSEG_CACHE_DIR', os.path.join(os.path.expanduser('~'), '.cache', 'clip_decontamination_b200'))
+        path = os.path.join(cdir, f'text_{hsh.hexdigest()}.npy')
+        if os.path.isfile(path):
+            try:
+                qf = torch.from_numpy(np.load(path))
+                if qf.shape[0] == len(query_words):
+                    return qf
+            except Exception:
+                pass
+        prompts = [temp(qw) for qw in query_words for temp in openai_imagenet_template]
+        tokens = self.tokenizer(prompts)
+        feats = []
+        with torch.no_grad():
+            for c0 in range(0, len(prompts), 4 * n_t):                # four classes (320 prompts, M = 24 640 rows) per pass
+                feats.append(self.net.encode_text(tokens[c0:c0 + 4 * n_t].to(device)))
+            f = torch.cat(feats).float().view(len(query_words), n_t, -1)
+            f = f / f.norm(dim=-1, keepdim=True)
+            f = f.mean(dim=1)
+            qf = f / f.norm(dim=-1, keepdim=True)
+        try:
+            os.makedirs(cdir, exist_ok=True)
+            tmp = path + f'.{os.getpid()}.tmp'
+            with open(tmp, 'wb') as fh:
+                np.save(fh, qf.cpu().numpy())
+            os.replace(tmp, path)
+        except OSError:
+            pass                                                     # read-only home: recompute next time
+        return qf
+
     # ------------------------------------------------------------------------------------------
     def _img3(self, img):
         if type(img) == list:
@@ -213,12 +254,12 @@ class SegmentorEx(BaseSegmentor):
         """Cosine logits of ONE crop [1,Q,h,w] resized to `logit_size` / the crop size (segmentor.py:286-392)."""
         img3 = self._img3(img)
         _, H, W = img3.shape
-        saved = self.engine.crop, self.engine._win_cache
-        self.engine.crop, self.engine._win_cache = 0, {}
+        saved = self.engine.crop
+        self.engine.crop = 0
         try:
             logits, g = self.engine.crop_logits(img3)
         finally:
-            self.engine.crop, self.engine._win_cache = saved
+            self.engine.crop = saved
         size = (H, W) if logit_size is None else tuple(logit_size)
         return nn.functional.interpolate(logits, size=size, mode='bilinear')
 
@@ -226,54 +267,99 @@ class SegmentorEx(BaseSegmentor):
         """Averaged cosine logits [1,Q,H0,W0] (segmentor.py:394-451)."""
         img3 = self._img3(img)
         eng = self.engine
-        saved = eng.stride, eng.crop, eng._win_cache
+        saved = eng.stride, eng.crop
         stride = stride[0] if isinstance(stride, (tuple, list)) else stride
         crop_size = crop_size[0] if isinstance(crop_size, (tuple, list)) else crop_size
-        if (stride, crop_size) != (eng.stride, eng.crop):
-            eng.stride, eng.crop, eng._win_cache = stride, crop_size, {}
+        eng.stride, eng.crop = stride, crop_size
         try:
             _, _, avg = eng.segment(img3, None, want_logits=True)
         finally:
-            eng.stride, eng.crop, eng._win_cache = saved
+            eng.stride, eng.crop = saved
         logits = avg.unsqueeze(0)
         img_size = tuple(img_metas[0]['ori_shape'][:2])
         if img_size != tuple(logits.shape[-2:]):
             logits = nn.functional.interpolate(logits, size=img_size, mode='bilinear')
         return logits
 
+    # ---- the fast path shared by predict / test_step / predict_u8 ---------------------------------
+    def _labels(self, x, kind, ori_shapes):
+        """x: B equally sized images laid out as `kind` (engine.graph) -> list of B uint8 label maps [oh,ow] on the
+        device.  Images that keep their size go through ONE CUDA-graph replay as a stacked batch; images that are
+        resized to a different ori_shape (Resize in the test pipeline) are replayed one by one."""
+        B = x.shape[0]
+        H, W = (x.shape[1], x.shape[2]) if kind == 'u8hwc' else (x.shape[2], x.shape[3])
+        oris = [tuple(int(v) for v in o[:2]) for o in ori_shapes]
+        if all(o == (H, W) for o in oris):
+            lab = self.engine.segment_batch(x, kind, None, use_graph=self.use_graph)
+            return [lab[i] for i in range(B)]
+        return [self.engine.segment_batch(x[i:i + 1], kind, oris[i], use_graph=self.use_graph)[0] for i in range(B)]
+
+    def _attach(self, data_samples, labels, probs_list=None):
+        out = []
+        for i, lab in enumerate(labels):
+            seg_pred = lab.to(torch.int64).unsqueeze(0)
+            if data_samples is None:
+                out.append(seg_pred)
+                continue
+            d = {'pred_sem_seg': PixelData(**{'data': seg_pred})}
+            pr = probs_list[i] if probs_list is not None else None
+            if pr is not None:
+                d['seg_logits'] = PixelData(**{'data': pr})
+            data_samples[i].set_data(d)
+            if self.result_dir or self.heatmap_dir:
+                self._dump(i, data_samples[i], lab, pr)
+        if data_samples is None:
+            return out[0] if len(out) == 1 else torch.stack(out)   # reference returns image 0 (batch 1)
+        return data_samples
+
     @torch.no_grad()
     def predict(self, inputs, data_samples):
-        """segmentor.py:453-473.  inputs [B,3,H,W] normalised floats (any float dtype, any device)."""
+        """segmentor.py:453-473.  inputs [B,3,H,W] normalised floats (any float dtype, any device).  All B images go
+        through the engine as ONE batch (B x n_crops crops per kernel launch, CUDA-graph replay per input shape)."""
         if data_samples is not None:
             batch_img_metas = [ds.metainfo for ds in data_samples]
         else:
             batch_img_metas = [dict(ori_shape=inputs.shape[2:], img_shape=inputs.shape[2:],
                                     pad_shape=inputs.shape[2:], padding_size=[0, 0, 0, 0])] * inputs.shape[0]
-        preds = []
-        for i in range(inputs.shape[0]):
-            img = inputs[i].to(self._device, torch.float32).contiguous()
-            ori = tuple(batch_img_metas[i]['ori_shape'][:2])
-            labels, probs, _ = self.engine.segment(img, ori, want_probs=self.output_seg_logits)
-            seg_pred = labels.to(torch.int64).unsqueeze(0)
-            if data_samples is None:
-                preds.append(seg_pred)
-                continue
-            d = {'pred_sem_seg': PixelData(**{'data': seg_pred})}
-            if probs is not None:
-                d['seg_logits'] = PixelData(**{'data': probs})
-            data_samples[i].set_data(d)
-            if self.result_dir or self.heatmap_dir:
-                self._dump(i, data_samples[i], seg_pred, probs)
-        if data_samples is None:
-            return preds[0] if len(preds) == 1 else torch.stack(preds)   # reference returns image 0 (batch 1)
-        return data_samples
+        oris = [m['ori_shape'] for m in batch_img_metas]
+        if self.output_seg_logits:                                   # probabilities requested: eager, per image
+            labels, probs = [], []
+            for i in range(inputs.shape[0]):
+                img = inputs[i].to(self._device, torch.float32).contiguous()
+                lab, pr, _ = self.engine.segment(img, tuple(oris[i][:2]), want_probs=True)
+                labels.append(lab)
+                probs.append(pr)
+            return self._attach(data_samples, labels, probs)
+        x = inputs if inputs.dtype == torch.float32 else inputs.float()
+        return self._attach(data_samples, self._labels(x.contiguous(), 'f32', oris))
 
     @torch.no_grad()
-    def predict_u8(self, img_hwc_bgr_u8, labels_out=None, use_graph=True):
-        """Input side fused (N1): uint8 HWC BGR image (pinned host or device) -> uint8 labels [H,W] on the
-        device.  Equivalent to data_preprocessor + predict for one image; the launch sequence is replayed
-        from a CUDA graph captured on first use of each image shape."""
-        return self.engine.segment_u8(img_hwc_bgr_u8, labels_out, use_graph)
+    def test_step(self, data):
+        """mmengine BaseModel.test_step (what Runner.test() calls, eval.py:86-87): data = dict(inputs=[uint8 CHW BGR
+        tensors], data_samples=[SegDataSample]).  The SegDataPreProcessor arithmetic (segmentor.py:64-67) is fused
+        into the kernels that read the image, so the raw bytes are uploaded as they are; anything that is not a
+        list of equally sized uint8 CHW images takes the generic data_preprocessor + predict route."""
+        inputs, samples = data['inputs'], data.get('data_samples')
+        fast = (isinstance(inputs, (list, tuple)) and len(inputs) > 0 and not self.output_seg_logits
+                and all(torch.is_tensor(t) and t.dtype == torch.uint8 and t.dim() == 3 and t.shape[0] == 3
+                        and t.shape == inputs[0].shape for t in inputs))
+        if not fast:
+            data = self.data_preprocessor(data, False)
+            return self.predict(data['inputs'], data['data_samples'])
+        x = inputs[0].unsqueeze(0) if len(inputs) == 1 else torch.stack(list(inputs))
+        if samples is not None:
+            oris = [ds.metainfo.get('ori_shape', x.shape[2:]) for ds in samples]
+        else:
+            oris = [x.shape[2:]] * x.shape[0]
+        return self._attach(samples, self._labels(x.contiguous(), 'u8chw', oris))
+
+    @torch.no_grad()
+    def predict_u8(self, img_hwc_bgr_u8, labels_out=None, use_graph=True, copy_out=True):
+        """uint8 HWC BGR image [H,W,3] or batch [B,H,W,3] (pinned host or device, as cv2.imread returns it) -> uint8
+        labels on the device.  Equivalent to data_preprocessor + predict; the launch sequence is replayed from a CUDA
+        graph captured on first use of each input shape.  copy_out=False returns the graph's static output buffer
+        (valid until the next call)."""
+        return self.engine.segment_u8(img_hwc_bgr_u8, labels_out, use_graph, copy_out)
 
     def postprocess_result(self, seg_logits, data_samples):
         """segmentor.py:475-499 on given averaged logits [B,Q,H,W] (runs the fused kernel with one
@@ -299,7 +385,7 @@ class SegmentorEx(BaseSegmentor):
         return _compute_padsize(H, W, patch_size)
 
     # ---- optional PNG dumps (segmentor.py:501-531,568-608); host-side, off the hot path ---------
-    def _dump(self, i, sample, seg_pred, probs):
+    def _dump(self, i, sample, labels_u8, probs):
         import colorsys
         import cv2
         meta = getattr(sample, 'metainfo', {}) or {}
@@ -313,7 +399,7 @@ class SegmentorEx(BaseSegmentor):
                 r, g, b = colorsys.hsv_to_rgb((idx / max(1, n)) % 1.0, 0.75, 1.0 if idx != self.bg_idx else 0.2)
                 pal.append([int(r * 255), int(g * 255), int(b * 255)])
             pal = np.array(pal, dtype=np.uint8)
-            mask = seg_pred.squeeze(0).cpu().numpy().astype(np.int32)
+            mask = labels_u8.cpu().numpy().astype(np.int32)
             cv2.imwrite(os.path.join(self.result_dir, f'{stem}.png'), pal[np.clip(mask, 0, n - 1)][:, :, ::-1])
         if self.heatmap_dir and probs is not None:
             os.makedirs(self.heatmap_dir, exist_ok=True)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CSEG_VERSION 100
+#define CSEG_VERSION 200
 
 #if defined(__GNUC__)
 #define CSEG_API __attribute__((visibility("default")))
@@ -34,7 +34,7 @@ extern "C" {
 #define CSEG_API
 #endif
 
-enum { CSEG_F32 = 0, CSEG_BF16 = 1, CSEG_F16 = 2 /* JBU range projections only */ };
+enum { CSEG_F32 = 0, CSEG_BF16 = 1, CSEG_F16 = 2 /* JBU range projections only */, CSEG_U8 = 3 /* cseg_image only */ };
 enum { CSEG_OK = 0, CSEG_EINVAL = -1, CSEG_ECUDA = -2, CSEG_EUNSUPPORTED = -3 };
 /* epilogue activations of cseg_gemm */
 enum { CSEG_ACT_NONE = 0, CSEG_ACT_GELU = 1, CSEG_ACT_QUICKGELU = 2 };
@@ -47,7 +47,8 @@ enum {
   CSEG_ATTN_SFP = 4,          /* softmax(0.5 (qq+kk) s + M)                               :888-895 */
   CSEG_ATTN_VANILLA = 5,      /* softmax(qk s + M)                                        :858-863 */
   CSEG_ATTN_SEGEARTH = 6,     /* SCLIP + softmax(vv s + M)                                :878-887 */
-  CSEG_ATTN_MASKCLIP = 7      /* identity attention                                       :864-869 */
+  CSEG_ATTN_MASKCLIP = 7,     /* identity attention                                       :864-869 */
+  CSEG_ATTN_CAUSAL = 8        /* softmax(q k^T * s + causal mask) v: text tower, transformer.py:1047-1053, model.py:295 */
 };
 
 CSEG_API int cseg_version(void);
@@ -57,7 +58,26 @@ CSEG_API int cseg_last_error(char* buf, size_t n);
 CSEG_API long long cseg_launch_count(void);
 
 /* ---- input side (N1): mmseg SegDataPreProcessor arithmetic, segmentor.py:64-67 -------------
- * uint8 HWC BGR image -> float32 [3,H,W] RGB, (x - mean) / std. */
+ * Image descriptor read by the three kernels that touch the input (cseg_patchify, cseg_jbu_guidance,
+ * cseg_jbu_guidance_proj).  A HOST struct passed by pointer; `data` is a DEVICE pointer.  The canvas has H rows
+ * and W columns and is a vertical stack of H / img_h equally sized images (img_h == H: one image); canvas row Y is
+ * row Y % img_h of image Y / img_h.  Element (c, Y, x) of the normalised RGB image the reference feeds to
+ * predict() (segmentor.py:453-468) lives at
+ *     data[(Y / img_h) * stride_img + chan[c] * stride_c + (Y % img_h) * stride_y + x * stride_x]
+ * dtype CSEG_F32: the stored value is already normalised (mean / std ignored, chan = {0,1,2});
+ * dtype CSEG_U8:  raw bytes; the value is (float(byte) - mean[c]) / std[c] in fp32 (SegDataPreProcessor with
+ *                 bgr_to_rgb: chan = {2,1,0} for BGR storage).  HWC uint8 (cv2 / predict_u8): stride_c = 1,
+ *                 stride_x = 3, stride_y = 3 W; CHW uint8 (mmengine PackSegInputs): stride_c = img_h * W, stride_x = 1. */
+typedef struct cseg_image {
+  const void* data;
+  int dtype;
+  int H, W, img_h;
+  long long stride_img, stride_c, stride_y, stride_x;
+  int chan[3];
+  float mean[3], std[3];
+} cseg_image;
+
+/* stand-alone form of the same arithmetic: uint8 HWC BGR image -> float32 [3,H,W] RGB, (x - mean) / std. */
 CSEG_API int cseg_preprocess_u8(const uint8_t* img_hwc_bgr, int H, int W, const float mean_rgb_host[3],
                        const float std_rgb_host[3], float* out_chw, void* stream);
 
@@ -66,9 +86,14 @@ CSEG_API int cseg_preprocess_u8(const uint8_t* img_hwc_bgr, int H, int W, const 
  * is placed at (pad_top, pad_left) inside a zero canvas of crop_h x crop_w (compute_padsize,
  * segmentor.py:427-431,534-546).  out: T [n_crops*gh*gw, ldo], column = c*ps*ps + ky*ps + kx
  * (the flattened conv1.weight order), columns >= 3*ps*ps are written as zero up to ldo. */
-CSEG_API int cseg_patchify(const float* img_chw, int H, int W, const int32_t* windows, int n_crops,
+CSEG_API int cseg_patchify(const cseg_image* img, const int32_t* windows, int n_crops,
                   int crop_h, int crop_w, int pad_top, int pad_left, int ps, int out_dtype,
                   void* out, int ldo, void* stream);
+/* text tower stem (A13/N3; open_clip/model.py:291-293): out[r] = table[idx[r]] + pos[r % L] for r < n_rows
+ * (table fp32 [*, width], idx int64 [n_rows], pos fp32 [L, width] or NULL = plain row gather, used for the
+ * EOT-token pick of model.py:302-304). */
+CSEG_API int cseg_gather_rows(const float* table, const long long* idx, const float* pos, long long n_rows, int L,
+                     int width, float* out, void* stream);
 /* x[crop*L + t] = (t == 0 ? class_embedding : patch_embed[crop*P + t-1]) + pos[t]   (:565-571) */
 CSEG_API int cseg_embed_tokens(const float* patch_embed, const float* class_embedding, const float* pos,
                       int n_crops, int L, int width, float* x, void* stream);
@@ -124,13 +149,13 @@ CSEG_API int cseg_cls_debias(const float* tok, int n_crops, int L, int D, float 
 /* ---- JBU upsampler (K11): simfeatup_dev/upsamplers.py:202-325 ---------------------------------
  * guidance for one stage: adaptive_avg_pool2d of each crop to (gh, gw) (:316) -> fp32 [n,gh,gw,4]
  * (RGB + 0 pad). */
-CSEG_API int cseg_jbu_guidance(const float* img_chw, int H, int W, const int32_t* windows, int n_crops,
+CSEG_API int cseg_jbu_guidance(const cseg_image* img, const int32_t* windows, int n_crops,
                       int crop_h, int crop_w, int pad_top, int pad_left, int gh, int gw,
                       float* guid, void* stream);
 /* the two calls above/below in one kernel for the bf16 pipeline: guid (fp32 [n,gh,gw,4]) and proj (CSEG_F16
  * [n,gh,gw,32]) of one stage from the image; the hidden GELU uses the tanh form (|err| <= 4.8e-4, the size of the
  * fp16 rounding the reference's autocast applies to these activations). */
-CSEG_API int cseg_jbu_guidance_proj(const float* img_chw, int H, int W, const int32_t* windows, int n_crops,
+CSEG_API int cseg_jbu_guidance_proj(const cseg_image* img, const int32_t* windows, int n_crops,
                            int crop_h, int crop_w, int pad_top, int pad_left, int gh, int gw, int key_dim,
                            const float* w0, const float* b0, const float* w3, const float* b3, float* guid,
                            int proj_dtype, void* proj, void* stream);

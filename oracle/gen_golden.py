@@ -254,6 +254,91 @@ def seg_group(out_name, model_name, cls, H, W, thd, bg, upsampler=None, extras=T
           hist=torch.bincount(pred.flatten(), minlength=seg.num_classes))
 
 
+MARGIN_Q = 2e-4          # top-2 logit margins of the full-size groups are stored as uint8 multiples of this
+
+
+@torch.no_grad()
+def seg_full(out_name, model_name, cls, H, W, thd, bg, upsampler=None, extras=True, scene_seed=2,
+             crop=224, stride=112, ori_shape=None, pin=True, sub=4):
+    """Full-size BASELINE configurations through the UNMODIFIED reference (predict's two branches,
+    segmentor.py:468-473): slide (crop > 0, optional resize to ori_shape) or whole image (crop <= 0)."""
+    cfg = get_model_config(model_name)
+    sd = synthetic_clip_state_dict(cfg, 0)
+    v = cfg['vision_cfg']
+    kw = dict(EXTRAS) if extras else {}
+    up = (upsampler, synthetic_jbu_state_dict(upsampler, cfg['embed_dim'], 1)) if upsampler else None
+    seg = rh.build_ref_segmentor(cfg, sd, os.path.join(ROOT, 'configs', f'cls_{cls}.txt'),
+                                 model_type='Experimental', prob_thd=thd, bg_idx=bg, upsampler=up, **kw)
+    img = torch.from_numpy(synth.preprocess(synth.voronoi_scene(H, W, scene_seed)))[None]
+    ori = (H, W) if ori_shape is None else tuple(ori_shape)
+    t0 = time.time()
+    if crop > 0:
+        lg = seg.forward_slide(img, [dict(ori_shape=ori)], stride, crop)
+    else:
+        lg = seg.forward_feature(img, ori)
+    pred = seg.postprocess_result(lg.clone(), None)
+    t_ref = time.time() - t0
+    print(f'  reference: {t_ref:.1f}s  label hist {torch.bincount(pred.flatten(), minlength=seg.num_classes).tolist()}')
+    if pin:
+        orc = O.SegOracle(_visual(sd), seg.query_features, seg.query_idx.tolist(), layers=v['layers'],
+                          heads=v['heads'], patch=v['patch_size'], prob_thd=thd, bg_idx=bg, slide_stride=stride,
+                          slide_crop=crop, global_debias_factor=0.2 if extras else 0.0, upsampler=up,
+                          sim_cfg={} if extras else None, outlier_cfg={'top_k': 30} if extras else None)
+        olg = orc.forward_slide(img, ori) if crop > 0 else orc.forward_feature(img, ori)
+        _, opred = orc.postprocess(olg[0])
+        _pin(f'{out_name}/logits', lg, olg, 1e-5)
+        agree = float((pred == opred).float().mean())
+        print(f'  oracle label agreement with the reference: {agree * 100:.4f}%')
+        assert agree >= 0.9999
+    s = torch.sort(lg[0], dim=0, descending=True)[0]
+    margin = (s[0] - s[1])
+    _save(out_name, query_features=seg.query_features, query_idx=seg.query_idx,
+          logits_sub=lg[0][:, ::sub, ::sub].half() if sub > 4 else lg[0][:, ::sub, ::sub],
+          labels=pred[0].to(torch.uint8),
+          margin_u8=(margin / MARGIN_Q).clamp(0, 255).to(torch.uint8),
+          meta=np.array([H, W, thd, bg, scene_seed, t_ref, crop, stride, ori[0], ori[1], sub, MARGIN_Q,
+                         1.0 if extras else 0.0], dtype=np.float64),
+          hist=torch.bincount(pred.flatten(), minlength=seg.num_classes))
+
+
+@torch.no_grad()
+def ref_bf16_yardstick():
+    """The reference's OWN reduced-precision noise floor: the unmodified reference run in bf16
+    (weights via convert_weights_to_lp, bf16 input, bf16 upsampler; the adaptive-conv shim accumulates its
+    121 taps in fp32 as a device kernel would) against the fp32 goldens of the same scenes."""
+    cfg = get_model_config('ViT-B-16')
+    sd = synthetic_clip_state_dict(cfg, 0)
+    out = {}
+    for tag, gold_name, cls, upn in (('potsdam_noup', 'seg_potsdam_noup', 'potsdam', None),
+                                     ('potsdam_jbu', 'seg_potsdam_jbu', 'potsdam', 'jbu_one'),
+                                     ('vaihingen_jbu', 'seg_vaihingen_jbu', 'vaihingen', 'jbu_one')):
+        path = os.path.join(GOLD, gold_name + '.npz')
+        if not os.path.exists(path):
+            print(f'  skip {tag}: {gold_name}.npz missing')
+            continue
+        g = np.load(path)
+        H, W, thd, bg, seed = int(g['meta'][0]), int(g['meta'][1]), float(g['meta'][2]), int(g['meta'][3]), int(g['meta'][4])
+        up = (upn, synthetic_jbu_state_dict(upn, cfg['embed_dim'], 1)) if upn else None
+        seg = rh.build_ref_segmentor(cfg, sd, os.path.join(ROOT, 'configs', f'cls_{cls}.txt'), precision='bf16',
+                                     model_type='Experimental', prob_thd=thd, bg_idx=bg, upsampler=up, **EXTRAS)
+        if up is not None:
+            seg.upsampler.bfloat16()
+        img = torch.from_numpy(synth.preprocess(synth.voronoi_scene(H, W, seed)))[None].bfloat16()
+        t0 = time.time()
+        lg = seg.forward_slide(img, [dict(ori_shape=(H, W))], 112, 224)
+        pred = seg.postprocess_result(lg.clone(), None)[0].to(torch.uint8)
+        lab32 = torch.from_numpy(g['labels'])
+        sub = lg[0][:, ::4, ::4].float()
+        dl = float((sub - torch.from_numpy(g['logits_sub']).float()).abs().max())
+        agree = float((pred == lab32).float().mean())
+        print(f'  {tag}: reference bf16 vs reference fp32: label agreement {agree * 100:.3f}%, '
+              f'max|dlogit| {dl:.2e} ({time.time() - t0:.0f}s)')
+        out[f'{tag}_agree'] = np.float64(agree)
+        out[f'{tag}_max_dlogit'] = np.float64(dl)
+        out[f'{tag}_labels_bf16'] = pred
+    _save('ref_bf16_yardstick', **out)
+
+
 @torch.no_grad()
 def bench_text():
     """prompt-ensembled class text embeddings (segmentor.py:157-174) of the benchmark configs, produced by
@@ -281,6 +366,23 @@ GROUPS = {
     'seg_noup': lambda: seg_group('seg_potsdam_noup', 'ViT-B-16', 'potsdam', 512, 512, 0.1, 5),
     'seg_jbu': lambda: seg_group('seg_potsdam_jbu', 'ViT-B-16', 'potsdam', 512, 512, 0.1, 5, upsampler='jbu_one'),
     'seg_vitl': lambda: seg_group('seg_loveda_vitl', 'ViT-L-14', 'loveda', 448, 448, 0.3, 0),
+    # ---- BASELINE.json configs at their real size + the branches of predict (round 2) ----
+    'seg_vaihingen': lambda: seg_full('seg_vaihingen_jbu', 'ViT-B-16', 'vaihingen', 512, 512, 0.1, 5, 'jbu_one'),
+    'seg_extras_off': lambda: seg_full('seg_potsdam_jbu_extras_off', 'ViT-B-16', 'potsdam', 512, 512, 0.1, 5, 'jbu_one',
+                                       extras=False),
+    'seg_whole_jbu': lambda: seg_full('seg_whole_240_jbu', 'ViT-B-16', 'potsdam', 240, 240, 0.1, 5, 'jbu_one', crop=0),
+    'seg_whole_noup': lambda: seg_full('seg_whole_250_noup', 'ViT-B-16', 'potsdam', 250, 250, 0.1, 5, None, crop=0),
+    'seg_small_side': lambda: seg_full('seg_small_200_jbu', 'ViT-B-16', 'vaihingen', 200, 200, 0.1, 5, 'jbu_one'),
+    'seg_nonsquare_off': lambda: seg_full('seg_nonsquare_200x180_off', 'ViT-B-16', 'potsdam', 200, 180, 0.1, 5, None,
+                                          extras=False),
+    'seg_road_resize': lambda: seg_full('seg_road_448to1024', 'ViT-B-16', 'roadval', 448, 448, 0.7, 0, 'jbu_one',
+                                        ori_shape=(1024, 1024), sub=8),
+    'seg_vitl_1024': lambda: seg_full('seg_loveda_vitl_1024', 'ViT-L-14', 'loveda', 1024, 1024, 0.3, 0, None, sub=8),
+    'seg_isaid': lambda: seg_full('seg_isaid_896', 'ViT-B-16', 'isaid', 896, 896, 0.4, 0, 'jbu_one', sub=8),
+    'seg_road': lambda: seg_full('seg_road_1024', 'ViT-B-16', 'roadval', 1024, 1024, 0.7, 0, 'jbu_one', sub=8),
+    'seg_road_snapped': lambda: seg_full('seg_road_1300x1100', 'ViT-B-16', 'roadval', 1300, 1100, 0.7, 0, 'jbu_one',
+                                         sub=8, pin=False),
+    'ref_bf16': ref_bf16_yardstick,
 }
 
 if __name__ == '__main__':

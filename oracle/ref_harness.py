@@ -16,7 +16,10 @@ import types
 import torch
 import torch.nn as nn
 
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get('CLIPSEG_REF', '/root/reference')
+if not os.path.isdir(os.path.join(REF, 'open_clip')) and os.path.isdir(os.path.join(_ROOT, 'baseline', '_ref', 'open_clip')):
+    REF = os.path.join(_ROOT, 'baseline', '_ref')          # staged by oracle/stage_ref.py for GPU-box runs
 
 
 def available() -> bool:
@@ -76,11 +79,13 @@ def install():
         def apply(inp, filt):
             b, c, h1, w1 = inp.shape
             _, h2, w2, f1, f2 = filt.shape
-            out = torch.zeros(b, c, h2, w2, dtype=inp.dtype)
+            # reduced-precision runs (the bf16 yardstick) accumulate the taps in fp32, as a device kernel would
+            low = inp.dtype in (torch.float16, torch.bfloat16)
+            out = torch.zeros(b, c, h2, w2, dtype=torch.float32 if low else inp.dtype, device=inp.device)
             for i in range(f1):
                 for j in range(f2):
-                    out.addcmul_(inp[:, :, i:i + h2, j:j + w2], filt[:, None, :, :, i, j])
-            return out
+                    out.addcmul_(inp[:, :, i:i + h2, j:j + w2].to(out.dtype), filt[:, None, :, :, i, j].to(out.dtype))
+            return out.to(inp.dtype)
     ups.AdaptiveConv = _AC
     _installed = True
 
@@ -98,6 +103,34 @@ def build_ref_clip(cfg: dict, state_dict: dict, precision: str = 'fp32'):
     if precision in ('fp16', 'bf16'):
         convert_weights_to_lp(m, torch.float16 if precision == 'fp16' else torch.bfloat16)
     return m.eval()
+
+
+def build_ref_segmentor_cuda(cfg: dict, state_dict: dict, name_path: str, *, upsampler=None, **kw):
+    """The reference's unmodified ``SegmentorEx`` the way it runs on a GPU: fp16 weights (create_model(...,
+    precision='fp16')), ``.cuda().half()`` upsampler under cuda autocast (segmentor.py:280,370-371).  Only
+    ``create_model`` (no network) and the un-vendored featup ``AdaptiveConv`` op are substituted."""
+    install()
+    import tempfile
+    import segmentor as refseg
+    refseg.create_model = lambda *a, **k: build_ref_clip(cfg, state_dict, 'fp16')
+    extra = {}
+    if upsampler is not None:
+        name, up_sd = upsampler
+        f = tempfile.NamedTemporaryFile(suffix='.ckpt', delete=False)
+        torch.save({'state_dict': {'upsampler.' + k: v for k, v in up_sd.items()}}, f.name)   # k[10:] at segmentor.py:282
+        extra = dict(apply_sim_feat_up=True, sim_feat_up_cfg=dict(model_name=name, model_path=f.name))
+        _orig_load = torch.load
+        torch.load = lambda p, *a, **k: _orig_load(p, *a, **{**k, 'weights_only': False})
+    cwd = os.getcwd()
+    try:
+        seg = refseg.SegmentorEx(clip_type='CLIP', vit_type='ViT-B/16', name_path=name_path,
+                                 device=torch.device('cuda'), **extra, **kw)
+    finally:
+        os.chdir(cwd)
+        if upsampler is not None:
+            torch.load = _orig_load
+            os.unlink(f.name)
+    return seg
 
 
 def build_ref_segmentor(cfg: dict, state_dict: dict, name_path: str, *, precision='fp32',
@@ -123,7 +156,9 @@ def build_ref_segmentor(cfg: dict, state_dict: dict, name_path: str, *, precisio
         seg.apply_sim_feat_up = True
         # segmentor.py:370-371 wraps the call in torch.cuda.amp.autocast() and .half(); on the CPU
         # fp32 harness both must be identities.
-        torch.cuda.amp.autocast = lambda *a, **k: torch.autocast('cpu', enabled=False)
+        # (the bf16 yardstick run keeps autocast on, in bf16: CPU autocast has no fp16 kernels for these ops)
+        low = precision in ('fp16', 'bf16')
+        torch.cuda.amp.autocast = lambda *a, **k: torch.autocast('cpu', dtype=torch.bfloat16, enabled=low)
         _orig = seg.upsampler.forward
         class _NoHalf(torch.Tensor):
             pass

@@ -1,6 +1,7 @@
 """CPU suite (`-m "not gpu"`): the oracle against the golden vectors produced by the unmodified reference,
 the host-side logic, and the C ABI surface (the library must load without a GPU and export every symbol
 declared in include/clipseg.h; no compute calls here)."""
+import ctypes as C
 import os
 import re
 import subprocess
@@ -213,7 +214,23 @@ def test_cabi_exports_every_declared_symbol():
     out = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r' T (cseg_\w+)', out))
     assert declared <= exported, declared - exported
-    assert _lib.lib.cseg_version() == 100
+    assert _lib.lib.cseg_version() == 200
+
+
+def test_cseg_image_struct_layout_matches_ctypes(tmp_path):
+    """include/clipseg.h is valid C and struct cseg_image has the layout the ctypes binding assumes."""
+    from clip_decontamination_b200 import _lib
+    src = tmp_path / 'layout.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "clipseg.h"\nint main(void){'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(cseg_image), offsetof(cseg_image, dtype), '
+                   'offsetof(cseg_image, img_h), offsetof(cseg_image, stride_img), offsetof(cseg_image, stride_x), '
+                   'offsetof(cseg_image, chan), offsetof(cseg_image, mean), offsetof(cseg_image, std)); return 0;}')
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-std=c99', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    CI = _lib.CsegImage
+    assert got == [C.sizeof(CI), CI.dtype.offset, CI.img_h.offset, CI.stride_img.offset, CI.stride_x.offset,
+                   CI.chan.offset, CI.mean.offset, CI.std.offset], got
 
 
 def test_cabi_argument_validation_without_gpu():
