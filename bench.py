@@ -6,12 +6,13 @@
 Workload (BASELINE.json configs[1]): Vaihingen-shaped 512x512 synthetic tiles, ViT-B/16 (synthetic
 "random-init" weights), jbu_one upsampler (C=512, radius 5), cls_vaihingen.txt (Q=K=6), prob_thd 0.1,
 bg_idx 5, slide 224/112 (16 crops per tile), base_config.py extras ON, bf16.  A step = `--tiles` tiles
-through preprocess -> ViT -> JBU -> logits -> accumulate/argmax -> IoU histogram (+ one all-reduce of
+through normalise-on-load -> ViT -> JBU -> logits -> accumulate/argmax -> IoU histogram (+ one all-reduce of
 the [3,K] int64 histogram per step when N > 1).  Every rank processes its own tiles (weak scaling).
 
 value : tiles already resident in HBM as uint8 (device-timed, CUDA events, max over ranks)
-e2e   : the same through SegmentorEx.predict_u8 from pinned HOST uint8 buffers, labels copied back
-roofline / cpu_baseline : see DESIGN.md "Measurement".
+e2e   : the same through the call mmengine's Runner makes, ``SegmentorEx.test_step(dict(inputs=[uint8 CHW ...],
+        data_samples=[...]))`` (eval.py:86-87), from pinned HOST buffers, labels + histogram read back every step
+roofline / rooflines / cpu_baseline : see DESIGN.md "Measurement".
 """
 import argparse
 import json
@@ -49,6 +50,13 @@ def _peaks():
         return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sust=d.get('bf16_tflops_sustained', d['bf16_tflops']),
                     src='measured (MEASURED_PEAKS.json)')
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback (B200_PROFILING.md)')
+
+
+def _traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel class, from the committed
+    `ncu --set full` capture of this command (profiles/r02_traffic.json; absent -> null)."""
+    p = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+    return json.load(open(p)) if os.path.exists(p) else {}
 
 
 # ---- algorithmic work per launch of each kernel class (DESIGN.md "Kernels and their rooflines") -------
@@ -113,49 +121,82 @@ def build_model(device, precision='bf16', wl=None):
                        upsampler_state_dict=synthetic_jbu_state_dict('jbu_one', 512, 1))
 
 
-def cpu_baseline_crop_seconds(threads):
-    """Oracle (CPU restatement of the reference, fp32) on ONE 224 crop of the workload: ViT-B/16 with the
-    extras + jbu_one + cosine logits.  Returns seconds per crop."""
-    from oracle import clipseg_oracle as O
-    from clip_decontamination_b200 import synth
-    from clip_decontamination_b200.open_clip.model_configs import get_model_config
-    from clip_decontamination_b200.open_clip.synthetic import synthetic_clip_state_dict, synthetic_jbu_state_dict
-    torch.set_num_threads(threads)
-    cfg = get_model_config('ViT-B-16')
-    v = cfg['vision_cfg']
-    sd = synthetic_clip_state_dict(cfg, 0, text_tower=False)
-    vis = {k[len('visual.'):]: t for k, t in sd.items() if k.startswith('visual.')}
-    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'bench_text.npz'))
-    orc = O.SegOracle(vis, torch.from_numpy(gold['vaihingen_query_features']), list(range(6)), layers=v['layers'],
-                      heads=v['heads'], patch=16, prob_thd=0.1, bg_idx=5, global_debias_factor=0.2,
-                      upsampler=('jbu_one', synthetic_jbu_state_dict('jbu_one', 512, 1)), sim_cfg={},
-                      outlier_cfg={'top_k': 30})
-    img = torch.from_numpy(synth.preprocess(synth.voronoi_scene(H, W, 100)))[None]
-    crop = img[:, :, :224, :224]
-    with torch.no_grad():
-        t0 = time.time()
-        orc.forward_feature(crop)
-        return time.time() - t0
+# ---- the CPU arm: the reference's algorithm for this path on the host cores ----------------------------
+EXTRAS_REF = dict(global_debias_factor=0.2, apply_outlier_suppression=True, outlier_suppression_cfg=dict(top_k=30),
+                  apply_similarity_enhancement=True,
+                  similarity_enhancement_cfg=dict(similarity_weight=1.0, temperature=1.0, add_self_similarity=True))
+
+
+class CpuTile:
+    """One FULL 512x512 tile of the workload through the CPU implementation of the path: 16 crops (ViT-B/16 + extras
+    + jbu_one + cosine logits) + overlap accumulate + post-process, fp32, all host threads.  kind 'port' = the oracle
+    (oracle/clipseg_oracle.py, pinned against the reference); kind 'reference' = the UNMODIFIED reference staged in
+    baseline/_ref (oracle/stage_ref.py), selected with CLIPSEG_REF_ARM=unmodified -- it is ~5x slower than the port
+    (tap-loop adaptive conv, per-crop Python overhead), so the port is the conservative default."""
+
+    def __init__(self, threads):
+        from clip_decontamination_b200 import synth
+        from clip_decontamination_b200.open_clip.model_configs import get_model_config
+        from clip_decontamination_b200.open_clip.synthetic import synthetic_clip_state_dict, synthetic_jbu_state_dict
+        torch.set_num_threads(threads)
+        self.threads = threads
+        cfg = get_model_config('ViT-B-16')
+        v = cfg['vision_cfg']
+        gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'bench_text.npz'))
+        qf = torch.from_numpy(gold['vaihingen_query_features'])
+        jbu = synthetic_jbu_state_dict('jbu_one', 512, 1)
+        self.img = torch.from_numpy(synth.preprocess(synth.voronoi_scene(H, W, 100)))[None]
+        self.kind = 'port'
+        if os.environ.get('CLIPSEG_REF_ARM', '') == 'unmodified':
+            from oracle import ref_harness as rh
+            if rh.available():
+                sd = synthetic_clip_state_dict(cfg, 0)
+                seg = rh.build_ref_segmentor(cfg, sd, os.path.join(ROOT, 'configs', 'cls_vaihingen.txt'),
+                                             model_type='Experimental', prob_thd=0.1, bg_idx=5,
+                                             upsampler=('jbu_one', jbu), **EXTRAS_REF)
+                seg.query_features = qf
+
+                def run():
+                    lg = seg.forward_slide(self.img, [dict(ori_shape=(H, W))], 112, 224)
+                    return seg.postprocess_result(lg, None)
+                self.run, self.kind = run, 'reference'
+                return
+        from oracle import clipseg_oracle as O
+        sd = synthetic_clip_state_dict(cfg, 0, text_tower=False)
+        vis = {k[len('visual.'):]: t for k, t in sd.items() if k.startswith('visual.')}
+        orc = O.SegOracle(vis, qf, list(range(6)), layers=v['layers'], heads=v['heads'], patch=16, prob_thd=0.1, bg_idx=5,
+                          global_debias_factor=0.2, upsampler=('jbu_one', jbu), sim_cfg={}, outlier_cfg={'top_k': 30})
+        self.run = lambda: orc.predict(self.img)
+
+    def seconds(self):
+        with torch.no_grad():
+            t0 = time.time()
+            self.run()
+            return time.time() - t0
+
+    @property
+    def sample(self):
+        return ('one full 512x512 tile per step: 16 crops (ViT-B/16 + extras + jbu_one + cosine logits) + overlap '
+                'accumulate + post-process, fp32, ' + ('unmodified reference (baseline/_ref)' if self.kind == 'reference'
+                                                       else 'oracle port of the reference'))
 
 
 def run_reference(args, rank):
-    """--impl reference: the CPU implementation of the path on the host cores (the oracle port: the
-    reference is Python and cannot travel to the GPU box).  A step = one crop of one tile, scaled to the
-    tile (16 crops); all host threads."""
+    """--impl reference: the CPU implementation of the path on the host cores, all host threads; a step = one full
+    tile (no extrapolation); exactly --steps timed steps after --warmup warm-up steps."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        cpu_baseline_crop_seconds(threads)
-    ts = [cpu_baseline_crop_seconds(threads) for _ in range(max(1, min(args.steps, 3)))]
-    sec_tile = float(np.mean(ts)) * CROPS
+    cpu = CpuTile(threads)
+    for _ in range(max(0, args.warmup)):
+        cpu.seconds()
+    ts = [cpu.seconds() for _ in range(max(1, args.steps))]
+    sec_tile = float(np.mean(ts))
     mps = H * W / 1e6 / sec_tile
-    line = dict(metric=METRIC, value=mps, unit='MP/s', n_gpus=args.gpus, steps=len(ts), warmup=1,
+    line = dict(metric=METRIC, value=mps, unit='MP/s', n_gpus=args.gpus, steps=len(ts), warmup=max(0, args.warmup),
                 ms_per_step=sec_tile * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
-                data='synthetic', impl='reference', config=dict(workload=WORKLOAD),
-                cpu_baseline=dict(value=mps, unit='MP/s', cores=threads, kind='port',
-                                  sample='1 of the 16 crops of one 512x512 tile per step (ViT-B/16 + extras + '
-                                         'jbu_one + logits), time x16'),
+                data='synthetic', impl='reference', config=dict(workload=WORKLOAD, tiles_per_step=1),
+                cpu_baseline=dict(value=mps, unit='MP/s', cores=threads, kind=cpu.kind, sample=cpu.sample),
                 e2e=dict(value=mps, unit='MP/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -165,7 +206,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--tiles', type=int, default=4, help='tiles per step per GPU')
+    ap.add_argument('--tiles', type=int, default=6, help='tiles per step per GPU')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -181,6 +222,7 @@ def main():
     import torch.distributed as dist
     from clip_decontamination_b200 import ops, synth
     from clip_decontamination_b200 import _lib
+    from clip_decontamination_b200.compat import SegDataSample
     from clip_decontamination_b200.dist import allreduce_hist
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
@@ -199,36 +241,41 @@ def main():
     eng = model.engine
     K = model.num_classes
     T = args.tiles
-    # synthetic tiles (different per rank / tile) + synthetic ground truth for the histogram
-    host_imgs = torch.stack([torch.from_numpy(synth.voronoi_scene(H, W, 1000 + rank * 64 + t)) for t in range(T)]).pin_memory()
+    # synthetic tiles (different per rank / tile) as the dataloader hands them over: uint8 CHW BGR (PackSegInputs),
+    # one pinned host tensor per image; synthetic ground truth for the histogram
+    host_imgs = [torch.from_numpy(np.ascontiguousarray(synth.voronoi_scene(H, W, 1000 + rank * 64 + t).transpose(2, 0, 1))).pin_memory()
+                 for t in range(T)]
     host_gt = torch.stack([torch.from_numpy(synth.synthetic_labels(H, W, K, 2000 + rank * 64 + t)) for t in range(T)])
-    dev_imgs = host_imgs.to(device)                     # [T,H,W,3] uint8 BGR
+    dev_imgs = torch.stack(host_imgs).to(device)        # [T,3,H,W] uint8 BGR
     dev_gt = host_gt.to(device)
     hist = torch.zeros((3, K), dtype=torch.int64, device=device)
     labels = torch.empty((T, H, W), dtype=torch.uint8, device=device)
     host_labels = torch.empty((T, H, W), dtype=torch.uint8).pin_memory()
-    mean, std = synth.MEAN.tolist(), synth.STD.tolist()
-    img_f32 = torch.empty((3, T * H, W), dtype=torch.float32, device=device)
+    host_hist = torch.empty((3, K), dtype=torch.int64).pin_memory()
+    samples = [SegDataSample(dict(ori_shape=(H, W), img_shape=(H, W))) for _ in range(T)]
+    dev_image = ops.Image.u8(dev_imgs, 'chw', eng.mean, eng.std)
 
     # One step = one pass of the hot path over one batch of T tiles: the T images go through every kernel together
     # (T x 16 crops per launch), as the reference's slide_inference does with a batched input.
     def step_eager():          # un-graphed launch sequence (used for the instrumented breakdown)
-        ops.preprocess_u8(dev_imgs.view(T * H, W, 3), mean, std, img_f32)
-        eng.segment(img_f32, None, labels=labels.view(T * H, W), batch=T)
+        eng.segment(dev_image, None, labels=labels.view(T * H, W))
         ops.iou_hist(labels.view(-1), dev_gt.view(-1), K, hist)
         allreduce_hist(hist)
 
     def step_resident():       # the product path: CUDA-graph replay, inputs resident in HBM
-        lab = eng.segment_u8(dev_imgs)
+        lab = eng.segment_batch(dev_imgs, 'u8chw', copy_out=False)
         ops.iou_hist(lab.view(-1), dev_gt.view(-1), K, hist)
         allreduce_hist(hist)
 
-    def step_e2e():
-        lab = model.predict_u8(host_imgs)                                     # H2D inside
+    def step_e2e():            # what mmengine's Runner.test() does per batch (eval.py:86-87) + the metric
+        out = model.test_step(dict(inputs=host_imgs, data_samples=samples))      # H2D of the raw bytes inside
+        lab = model.last_labels                                                    # uint8 [T,H,W] behind pred_sem_seg
         ops.iou_hist(lab.view(-1), dev_gt.view(-1), K, hist)
-        host_labels.copy_(lab, non_blocking=True)                             # D2H of the step's result
         allreduce_hist(hist)
+        host_labels.copy_(lab, non_blocking=True)                                  # D2H of the step's result
+        host_hist.copy_(hist, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        return out
 
     def barrier():
         if world > 1:
@@ -248,19 +295,17 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- warm-up; find the dominant kernel with a fully instrumented step -------------------------
+    # ---- warm-up; find the kernel classes of a step with a fully instrumented eager step ----------------
     for _ in range(args.warmup):
         step_eager()
         step_resident()
     torch.cuda.synchronize()
-    launches_per_tile = None
     l0 = _lib.launch_count()
     step_eager()
     launches_per_step = _lib.launch_count() - l0       # kernels per step (a graph replay issues the same set)
     records = {}
     shape_records = {}
     orig = {}
-    work = {}
 
     def wrap(name, fn, workfn=None):
         def inner(*a, **k):
@@ -272,7 +317,7 @@ def main():
             if name == 'gemm':      # per-shape split of the GEMM class (diagnostic)
                 A, B = a[0], a[1]
                 key = 'gemm[M%dxN%dxK%d]' % (k.get('M') or A.shape[0], k.get('N') or B.shape[0], k.get('K') or A.shape[1])
-                shape_records.setdefault(key, []).append((s, e))
+                shape_records.setdefault(key, []).append((s, e, 2.0 * (k.get('M') or A.shape[0]) * (k.get('N') or B.shape[0]) * (k.get('K') or A.shape[1])))
             return r
         return inner
 
@@ -281,7 +326,7 @@ def main():
     def gemm_work(A, B, out, **k):
         return ('tensor', 2.0 * (k.get('M') or A.shape[0]) * (k.get('N') or B.shape[0]) * (k.get('K') or A.shape[1]))
 
-    def apply_work(src, n, h, w, C, kern, radius, dst, hr):
+    def apply_work(src, n, h, w, C, kern, radius, dst, hr, *a, **k):
         return ('hbm', float(_work_jbu_apply(n, h, w, C, radius, esize)))
 
     def attn_work(qkv, n, L, heads, hd, mode, out, **k):
@@ -291,10 +336,11 @@ def main():
         return ('hbm', float(n * hw * (D * esize + text.shape[0] * 4)))
 
     def accum_work(cl, *a, **k):
-        return ('hbm', float(cl.numel() * 4 + H * W))
+        return ('hbm', float(cl.numel() * 4 + T * H * W))
 
-    def rk_work(proj, guid, n, gh, gw, radius, rt, ss, kern):
-        return ('hbm', float(n * gh * gw * (32 * proj.element_size() + 16 + kern.shape[-1] * esize)))
+    def rk_work(proj, guid, n, gh, gw, radius, rt, ss, kern, *a, **k):
+        rows = k.get('n_rows') or n * gh * gw
+        return ('hbm', float(rows * (32 * proj.element_size() + 16 + kern.shape[-1] * esize)))
 
     def fns_work(y, Wt, n, hw, Cc, bias, alpha, text, logits, cls_logit_bias=None, scratch=None):
         return ('tensor', 2.0 * n * hw * Cc * (Cc + text.shape[0]))
@@ -305,11 +351,19 @@ def main():
     def kfix_work(k, W0, b0, W3s, b3s, out):
         return ('hbm', float(2 * k.shape[0] * k.shape[1] * esize))
 
-    workfns = dict(jbu_kernel_fixup=kfix_work, basis_logits=basis_work, fixup_norm_sim=fns_work, gemm=gemm_work, jbu_apply=apply_work, attention=attn_work, norm_sim=nsim_work,
-                   accum_argmax=accum_work, jbu_range_kernel=rk_work)
+    def ln_work(x, gamma, beta, out, eps=1e-5):
+        return ('hbm', float(x.numel() * (4 + out.element_size())))
+
+    def simmap_work(x, n, L, width, out, *a, **k):
+        return ('hbm', float(n * L * width * 4 + n * (L - 1) * (L - 1) * 4))
+
+    workfns = dict(jbu_kernel_fixup=kfix_work, basis_logits=basis_work, fixup_norm_sim=fns_work, gemm=gemm_work,
+                   jbu_apply=apply_work, attention=attn_work, norm_sim=nsim_work, accum_argmax=accum_work,
+                   jbu_range_kernel=rk_work, layernorm=ln_work, simmap=simmap_work)
     names = ['preprocess_u8', 'patchify', 'embed_tokens', 'layernorm', 'gemm', 'attention', 'simmap', 'outlier_suppress',
-             'cls_debias', 'jbu_guidance', 'jbu_range_proj', 'jbu_guidance_proj', 'jbu_range_kernel', 'jbu_kernel_fixup', 'jbu_apply', 'norm_sim', 'fixup_norm_sim', 'basis_logits',
-             'accum_argmax', 'iou_hist']
+             'cls_debias', 'jbu_guidance', 'jbu_range_proj', 'jbu_guidance_proj', 'jbu_range_kernel', 'jbu_kernel_fixup',
+             'jbu_apply', 'norm_sim', 'fixup_norm_sim', 'basis_logits', 'accum_argmax', 'iou_hist']
+    names = [nm for nm in names if hasattr(ops, nm)]
     for nm in names:
         orig[nm] = getattr(ops, nm)
         setattr(ops, nm, wrap(nm, orig[nm], workfns.get(nm)))
@@ -318,40 +372,50 @@ def main():
     for nm in names:
         setattr(ops, nm, orig[nm])
     totals = {nm: sum(s.elapsed_time(e) for s, e, _ in recs) for nm, recs in records.items()}
+    tot_all = sum(totals.values())
     breakdown = {nm: round(v / T, 4) for nm, v in sorted(totals.items(), key=lambda kv: -kv[1])}
-    gemm_shapes = {k: [len(v) // T, round(sum(s.elapsed_time(e) for s, e in v) / T, 4)] for k, v in shape_records.items()}
     shape_records.clear()
-    dominant = max((nm for nm in totals if nm in workfns), key=lambda nm: totals[nm])
+    classes = [nm for nm in totals if nm in workfns and totals[nm] >= 0.03 * tot_all]     # every class >= 3 % of a step
+    dominant = max(classes, key=lambda nm: totals[nm])
     records.clear()
     # ---- timed region: value (inputs resident in HBM, CUDA-graph replay of the launch sequence) -----
     clk = ClockSampler(local_rank)
     clk.start()
     ms = timed(step_resident, args.steps)
     launches = launches_per_step * args.steps          # a replay issues the kernels counted at capture
-    # ---- same launches issued eagerly with the dominant kernel bracketed by CUDA events (a graph node
-    #      cannot be bracketed): per-launch duration of the dominant kernel for the roofline -------------
-    setattr(ops, dominant, wrap(dominant, orig[dominant], workfns[dominant]))
+    # ---- the same launches issued eagerly with every kernel class >= 3 % of the step bracketed by CUDA events (a graph
+    #      node cannot be bracketed): per-launch durations for the rooflines -------------------------------------------
+    for nm in classes:
+        setattr(ops, nm, wrap(nm, orig[nm], workfns[nm]))
     ms_eager = timed(step_eager, args.steps)
     clocks = clk.stop()
-    setattr(ops, dominant, orig[dominant])
-    dom = records.get(dominant, [])
-    dom_ms = [s.elapsed_time(e) for s, e, _ in dom]
-    dom_work = [w[1] for _, _, w in dom]
-    bound = dom[0][2][0] if dom else 'hbm'
+    for nm in classes:
+        setattr(ops, nm, orig[nm])
     peaks = _peaks()
-    # work-weighted: total algorithmic work / total time of the kernel over the region
-    tot_ms, tot_work = float(np.sum(dom_ms)), float(np.sum(dom_work))
-    if bound == 'hbm':
-        achieved, peak, runit = tot_work / tot_ms / 1e6, peaks['hbm'], 'GB/s'
-    else:
-        achieved, peak, runit = tot_work / tot_ms / 1e9, peaks['tf_sust'], 'TFLOP/s'
-    roofline = dict(kernel=dominant, bound=bound, achieved=achieved, peak=peak, unit=runit, frac=achieved / peak,
-                    traffic=None, launches_timed=len(dom_ms), avg_launch_ms=tot_ms / max(1, len(dom_ms)),
-                    share_of_step=tot_ms / ms_eager, eager_ms_per_step=ms_eager / args.steps,
-                    peak_source=peaks['src'], per_tile_ms_by_kernel=breakdown,
-                    gemm_calls_and_ms_per_tile_by_shape=gemm_shapes)
+    traffic = _traffic()
 
-    # ---- e2e: host buffers in, labels out, through the segmentor API -------------------------------
+    def roofline_of(nm):
+        recs = records.get(nm, [])
+        t_ms = float(sum(s.elapsed_time(e) for s, e, _ in recs))
+        work = float(sum(w[1] for _, _, w in recs))
+        bound = recs[0][2][0] if recs else 'hbm'
+        if bound == 'hbm':
+            achieved, peak, runit = work / t_ms / 1e6, peaks['hbm'], 'GB/s'
+        else:
+            achieved, peak, runit = work / t_ms / 1e9, peaks['tf_sust'], 'TFLOP/s'
+        return dict(kernel=nm, bound=bound, achieved=achieved, peak=peak, unit=runit, frac=achieved / peak,
+                    traffic=traffic.get(nm), launches_timed=len(recs), avg_launch_ms=t_ms / max(1, len(recs)),
+                    share_of_step=t_ms / ms_eager)
+
+    rooflines = sorted((roofline_of(nm) for nm in classes), key=lambda r: -r['share_of_step'])
+    gemm_shapes = {k: dict(calls_per_step=len(v) // args.steps, ms_per_step=round(sum(s.elapsed_time(e) for s, e, _ in v) / args.steps, 4),
+                           tflops=round(sum(w for _, _, w in v) / sum(s.elapsed_time(e) for s, e, _ in v) / 1e9, 1))
+                   for k, v in shape_records.items()}
+    roofline = dict(next(r for r in rooflines if r['kernel'] == dominant))
+    roofline.update(eager_ms_per_step=ms_eager / args.steps, peak_source=peaks['src'], per_tile_ms_by_kernel=breakdown,
+                    gemm_by_shape=gemm_shapes)
+
+    # ---- e2e: host buffers in, labels + histogram out, through SegmentorEx.test_step ----------------
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -366,15 +430,19 @@ def main():
                             l2='working set of a step (JBU stage buffers, ~1.5 GB per 16-crop chunk) far exceeds the 126 MB L2; '
                                'the batch holds %d different tiles' % T, parallelism=f'image-sharded x{world}'),
                 clocks=clocks, gpu_launches=int(launches),
-                e2e=dict(value=e2e, unit='MP/s', h2d_bytes_per_step=T * H * W * 3, d2h_bytes_per_step=T * H * W,
-                         ms_per_step=ms_e2e / args.steps),
-                roofline=roofline)
+                e2e=dict(value=e2e, unit='MP/s', h2d_bytes_per_step=T * H * W * 3, d2h_bytes_per_step=T * H * W + 3 * K * 8,
+                         ms_per_step=ms_e2e / args.steps, api='SegmentorEx.test_step(dict(inputs=[uint8 CHW], data_samples))'),
+                roofline=roofline, rooflines=rooflines)
+    ref_gpu = os.path.join(ROOT, 'profiles', 'r02_reference_on_b200.json')
+    if os.path.exists(ref_gpu):       # measured once with oracle/ref_on_gpu.py on the same kind of box (stated baseline)
+        rg = json.load(open(ref_gpu))
+        line['reference_on_b200'] = {k: dict(mp_per_s=v['mp_per_s'], seconds_per_tile=v['seconds_per_tile'])
+                                     for k, v in rg.items() if isinstance(v, dict) and 'mp_per_s' in v}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sec = cpu_baseline_crop_seconds(threads)
-        line['cpu_baseline'] = dict(value=H * W / 1e6 / (sec * CROPS), unit='MP/s', cores=threads, kind='port',
-                                    sample='1 of the 16 crops of one 512x512 tile (ViT-B/16 + extras + jbu_one + '
-                                           'logits) through the oracle, time x16')
+        cpu = CpuTile(threads)
+        sec = cpu.seconds()
+        line['cpu_baseline'] = dict(value=H * W / 1e6 / sec, unit='MP/s', cores=threads, kind=cpu.kind, sample=cpu.sample)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

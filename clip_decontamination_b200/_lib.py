@@ -34,6 +34,14 @@ class CsegImage(C.Structure):
 
 _img = C.POINTER(CsegImage)
 
+
+class CsegJbuShare(C.Structure):
+    """struct cseg_jbu_share of include/clipseg.h."""
+    _fields_ = [('windows', C.c_void_p), ('shift', C.c_int), ('pitch', C.c_int)]
+
+
+_shr = C.POINTER(CsegJbuShare)
+
 SIGNATURES = {
     'cseg_version': (_i, []),
     'cseg_last_error': (_i, [C.c_char_p, C.c_size_t]),
@@ -53,6 +61,10 @@ SIGNATURES = {
     'cseg_jbu_range_proj': (_i, [_p, _i, _i, _p, _p, _p, _p, _i, _p, _p]),
     'cseg_jbu_range_kernel': (_i, [_i, _p, _p, _i, _i, _i, _i, _i, _f, _f, _i, _p, _i, _i, _p]),
     'cseg_jbu_apply': (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
+    'cseg_jbu_share_rows': (_i, [_i, _i, _i]),
+    'cseg_jbu_range_kernel_border': (_i, [_p, _p, _shr, _i, _i, _i, _i, _f, _f, _p, _i, _i, _p]),
+    'cseg_jbu_composite_image': (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    'cseg_jbu_apply_shared': (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _shr, _i, _i, _p, _p, _p]),
     'cseg_norm_sim': (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
     'cseg_fixup_norm_sim': (_i, [_i, _p, _i, _p, _i, _i, _i, _i, _p, _f, _p, _i, _p, _p, _p, _p]),
     'cseg_jbu_guidance_proj': (_i, [_img, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p]),

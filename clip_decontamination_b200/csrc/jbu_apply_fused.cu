@@ -23,6 +23,7 @@
 //               (2 DO + 1)^2 results are scattered into the double-buffered band tiles.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "jbu_share.cuh"
 #include <cuda_fp16.h>
 
 namespace {
@@ -100,10 +101,17 @@ __global__ void fz_tables_kernel(int W2, int H2, int R, uint4* __restrict__ tabx
 //   stage A  T^T[dx][i]  = sum_j TX^T[x][dx][j] * k[i][j]        (mma.sync fp16, A = table fragment, B = the weight row)
 //   stage B  K'^T[dx][dy] = sum_i T^T[dx][i] * TY^T[y][dy][i]     (the accumulators of stage A are the A fragment)
 // kc[p][dy * (2 DO + 1) + dx] (bf16, row stride 128) is what the banded GEMM scatters into its B tiles.
-template <int R>
+// MODE 0: every pixel of n crops (dense, kern / kc indexed [crop][y][x]).
+// MODE 1: every pixel of the image-level stage canvas (ih x iw): kern_img -> kc_img with the bicubic tables of a
+//         crop-INTERIOR pixel of the same parity (the tables only depend on the parity there: the composite kernel of an
+//         interior pixel is the same for every crop that contains it, jbu_share.cuh).
+// MODE 2: the border frames (fb = CSEG_JBU_FB_COMP) of n crops, compact kc; the fixed-up kernel of a frame pixel comes
+//         from the per-crop border tensor (frame CSEG_JBU_FB_RANGE) or, further inside, from the image-level tensor.
+template <int R, int MODE>
 __global__ void __launch_bounds__(256) fz_composite_kernel(const bf16* __restrict__ kern, int ldk, long long n_px, int H2,
                                                            int W2, const uint4* __restrict__ tabx,
-                                                           const uint4* __restrict__ taby, bf16* __restrict__ kc) {
+                                                           const uint4* __restrict__ taby, bf16* __restrict__ kc,
+                                                           const bf16* __restrict__ kern_img, const ShareGeom sg, int iw) {
   pdl_grid_sync();
   constexpr int D = 2 * R + 1, DO = (R + 3) / 2, DC = 2 * DO + 1;
   const int lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
@@ -120,16 +128,36 @@ __global__ void __launch_bounds__(256) fz_composite_kernel(const bf16* __restric
   // every warp takes a contiguous run of pixels, so (x, y) advance incrementally (no per-pixel divisions)
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long per = (n_px + nwarps - 1) / nwarps, p_begin = warp0 * per, p_end = min(n_px, p_begin + per);
-  int x = (int)(p_begin % W2), y = (int)((p_begin / W2) % H2);
+  const int roww = MODE == 1 ? iw : W2;
+  const int rb_c = border_rows(H2, W2, CSEG_JBU_FB_COMP), rb_r = border_rows(H2, W2, CSEG_JBU_FB_RANGE);
+  int x = (int)(p_begin % roww), y = MODE == 1 ? (int)(p_begin / roww) : (int)((p_begin / roww) % H2);
   for (long long p = p_begin; p < p_end; ++p, ++x) {
-    if (x == W2) {
+    if (MODE != 2 && x == roww) {
       x = 0;
-      if (++y == H2) y = 0;
+      if (++y == H2 && MODE == 0) y = 0;
     }
-    const uint4 txv = __ldg(tabx + (size_t)x * 32 + lane), tyv = __ldg(taby + (size_t)y * 32 + lane);
+    int tx = x, ty = y;
+    const bf16* krow;
+    if (MODE == 0) {
+      krow = kern + p * ldk;
+    } else if (MODE == 1) {
+      tx = 16 + (x & 1);
+      ty = 16 + (y & 1);
+      krow = kern + p * ldk;
+    } else {
+      const int crop = (int)(p / rb_c), r = (int)(p - (long long)crop * rb_c);
+      border_coords(r, H2, W2, CSEG_JBU_FB_COMP, ty, tx);
+      if (border_interior(ty, tx, H2, W2, CSEG_JBU_FB_RANGE)) {
+        const size_t org = (size_t)((sg.wins[crop * 4] >> sg.shift) + ty) * sg.pitch + (sg.wins[crop * 4 + 1] >> sg.shift) + tx;
+        krow = kern_img + org * ldk;
+      } else {
+        krow = kern + ((size_t)crop * rb_r + border_index(ty, tx, H2, W2, CSEG_JBU_FB_RANGE)) * ldk;
+      }
+    }
+    const uint4 txv = __ldg(tabx + (size_t)tx * 32 + lane), tyv = __ldg(taby + (size_t)ty * 32 + lane);
     const uint32_t ta[4] = {txv.x, txv.y, txv.z, txv.w};
     const uint32_t tyb[2][2] = {{tyv.x, tyv.y}, {tyv.z, tyv.w}};
-    const unsigned short* wrow = reinterpret_cast<const unsigned short*>(kern + p * ldk);
+    const unsigned short* wrow = reinterpret_cast<const unsigned short*>(krow);
     float tacc[2][4];
 #pragma unroll
     for (int nb = 0; nb < 2; ++nb) {
@@ -190,7 +218,8 @@ struct FzCfg {
 template <int R, int MH>
 __global__ void __launch_bounds__(FZ_THREADS, 1)
 jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const bf16* __restrict__ kc,
-                       bf16* __restrict__ dst, int nx, int ny, int nslab, int total_tiles) {
+                       bf16* __restrict__ dst, int nx, int ny, int nslab, int total_tiles,
+                       const bf16* __restrict__ kc_img, const ShareGeom sg) {
   using Cf = FzCfg<R, MH>;
   constexpr int DO = Cf::DO, NLR = Cf::NLR;
   const int H2 = 2 * h, W2 = 2 * w;
@@ -358,13 +387,25 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
       tile_coords(tile, x0, y0, crop, c0);
       const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
       uint4 wv[WPT];
+      // shared kernels (jbu_share.cuh): interior pixels read the image-level composite kernels at the crop's origin,
+      // border-frame pixels the crop's compact frame tensor
+      size_t org = 0, cbase = (size_t)crop * H2 * W2;
+      if (kc_img != nullptr) {
+        org = (size_t)(sg.wins[crop * 4] >> sg.shift) * sg.pitch + (sg.wins[crop * 4 + 1] >> sg.shift);
+        cbase = (size_t)crop * border_rows(H2, W2, CSEG_JBU_FB_COMP);
+      }
 #pragma unroll
       for (int k = 0; k < WPT; ++k) {
         const int e = bt + k * 32 * FZ_BB_WARPS, n = e / NCH, v = e - n * NCH;
         const int y = y0 + (n >> 4), x = x0 + (n & 15);
         wv[k] = make_uint4(0, 0, 0, 0);                          // pixels outside the image: zero weights
-        if (n < FZ_NPX && y < H2 && x < W2)
-          wv[k] = __ldg(reinterpret_cast<const uint4*>(kc + (((size_t)crop * H2 + y) * W2 + x) * 128 + v * 8));
+        if (n < FZ_NPX && y < H2 && x < W2) {
+          const bf16* kp;
+          if (kc_img == nullptr) kp = kc + (cbase + (size_t)y * W2 + x) * 128;
+          else if (border_interior(y, x, H2, W2, CSEG_JBU_FB_COMP)) kp = kc_img + (org + (size_t)y * sg.pitch + x) * 128;
+          else kp = kc + (cbase + border_index(y, x, H2, W2, CSEG_JBU_FB_COMP)) * 128;
+          wv[k] = __ldg(reinterpret_cast<const uint4*>(kp + v * 8));
+        }
       }
       mbar_wait(b_empty0 + as * 8, aph ^ 1);
       uint8_t* bbuf = smem + Cf::B_OFF + as * Cf::B_BUF;
@@ -402,9 +443,24 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
 }
 
 template <int R, int MH>
+int launch_apply_kernel(const bf16* src, int n_crops, int h, int w, int C, const bf16* kc, bf16* dst, const bf16* kc_img,
+                        const ShareGeom& sg, cudaStream_t st) {
+  using Cf = FzCfg<R, MH>;
+  const int H2 = 2 * h, W2 = 2 * w;
+  CSEG_SET_SMEM((jbu_apply_fused_kernel<R, MH>), Cf::SMEM_BYTES);
+  const int nx = cdiv(W2, FZ_TX), ny = cdiv(H2, FZ_RW), nslab = C / Cf::CH;
+  const long long total = (long long)nx * ny * n_crops * nslab;
+  CSEG_REQUIRE(total < (1ll << 31), "jbu_apply(bf16): too many tiles");
+  const int grid = (int)std::min<long long>(total, sm_count());
+  cseg_launch(jbu_apply_fused_kernel<R, MH>, dim3(grid), dim3(FZ_THREADS), Cf::SMEM_BYTES, st, src, h, w, C, kc,
+              dst, nx, ny, nslab, (int)total, kc_img, sg);
+  CSEG_LAUNCH_CHECK("jbu_apply_fused");
+  return 0;
+}
+
+template <int R, int MH>
 int launch_fused(const bf16* src, int n_crops, int h, int w, int C, const bf16* kern, int ldk, bf16* dst, uint8_t* scratch,
                  cudaStream_t st) {
-  using Cf = FzCfg<R, MH>;
   const int H2 = 2 * h, W2 = 2 * w;
   const long long n_px = (long long)n_crops * H2 * W2;
   bf16* kc = reinterpret_cast<bf16*>(scratch);                       // composite kernels [n_px, 128]
@@ -413,18 +469,46 @@ int launch_fused(const bf16* src, int n_crops, int h, int w, int C, const bf16* 
   cseg_launch(fz_tables_kernel, dim3(cdiv((W2 + H2) * 32, 256)), dim3(256), 0, st, W2, H2, R, tabx, taby);
   CSEG_LAUNCH_CHECK("jbu_apply_tables");
   const int cblocks = (int)std::min<long long>(cdiv(n_px, 8), (long long)sm_count() * 8);
-  cseg_launch(fz_composite_kernel<R>, dim3(cblocks), dim3(256), 0, st, kern, ldk, n_px, H2, W2, (const uint4*)tabx,
-              (const uint4*)taby, kc);
+  const ShareGeom none = {nullptr, 0, 0};
+  cseg_launch(fz_composite_kernel<R, 0>, dim3(cblocks), dim3(256), 0, st, kern, ldk, n_px, H2, W2, (const uint4*)tabx,
+              (const uint4*)taby, kc, (const bf16*)nullptr, none, 0);
   CSEG_LAUNCH_CHECK("jbu_apply_composite");
-  CSEG_SET_SMEM((jbu_apply_fused_kernel<R, MH>), Cf::SMEM_BYTES);
-  const int nx = cdiv(W2, FZ_TX), ny = cdiv(H2, FZ_RW), nslab = C / Cf::CH;
-  const long long total = (long long)nx * ny * n_crops * nslab;
-  CSEG_REQUIRE(total < (1ll << 31), "jbu_apply(bf16): too many tiles");
-  const int grid = (int)std::min<long long>(total, sm_count());
-  cseg_launch(jbu_apply_fused_kernel<R, MH>, dim3(grid), dim3(FZ_THREADS), Cf::SMEM_BYTES, st, src, h, w, C, (const bf16*)kc,
-              dst, nx, ny, nslab, (int)total);
-  CSEG_LAUNCH_CHECK("jbu_apply_fused");
+  return launch_apply_kernel<R, MH>(src, n_crops, h, w, C, kc, dst, nullptr, none, st);
+}
+
+// image-level composite kernels (MODE 1); tabs: (gh + gw) * 512 bytes
+template <int R>
+int launch_composite_image(const bf16* kern_img, int ldk, int ih, int iw, int gh, int gw, bf16* kc_img, uint8_t* tabs,
+                           cudaStream_t st) {
+  uint4* tabx = reinterpret_cast<uint4*>(tabs);
+  uint4* taby = tabx + (size_t)gw * 32;
+  cseg_launch(fz_tables_kernel, dim3(cdiv((gw + gh) * 32, 256)), dim3(256), 0, st, gw, gh, R, tabx, taby);
+  CSEG_LAUNCH_CHECK("jbu_apply_tables");
+  const long long n_px = (long long)ih * iw;
+  const int cblocks = (int)std::min<long long>(cdiv(n_px, 8), (long long)sm_count() * 8);
+  const ShareGeom none = {nullptr, 0, 0};
+  cseg_launch(fz_composite_kernel<R, 1>, dim3(cblocks), dim3(256), 0, st, kern_img, ldk, n_px, gh, gw, (const uint4*)tabx,
+              (const uint4*)taby, kc_img, (const bf16*)nullptr, none, iw);
+  CSEG_LAUNCH_CHECK("jbu_composite_image");
   return 0;
+}
+
+// shared form of launch_fused: border-frame composites (MODE 2) into `scratch`, then the banded GEMM with indirection
+template <int R, int MH>
+int launch_fused_shared(const bf16* src, int n_crops, int h, int w, int C, const bf16* kern_border, const bf16* kern_img,
+                        const bf16* kc_img, const ShareGeom& sg, int ldk, bf16* dst, uint8_t* scratch, cudaStream_t st) {
+  const int H2 = 2 * h, W2 = 2 * w;
+  const long long n_px = (long long)n_crops * border_rows(H2, W2, CSEG_JBU_FB_COMP);
+  bf16* kc = reinterpret_cast<bf16*>(scratch);                       // compact frame composites [n_px, 128]
+  uint4* tabx = reinterpret_cast<uint4*>(scratch + n_px * 256);
+  uint4* taby = tabx + (size_t)W2 * 32;
+  cseg_launch(fz_tables_kernel, dim3(cdiv((W2 + H2) * 32, 256)), dim3(256), 0, st, W2, H2, R, tabx, taby);
+  CSEG_LAUNCH_CHECK("jbu_apply_tables");
+  const int cblocks = (int)std::min<long long>(cdiv(n_px, 8), (long long)sm_count() * 8);
+  cseg_launch(fz_composite_kernel<R, 2>, dim3(cblocks), dim3(256), 0, st, kern_border, ldk, n_px, H2, W2, (const uint4*)tabx,
+              (const uint4*)taby, kc, kern_img, sg, 0);
+  CSEG_LAUNCH_CHECK("jbu_apply_composite_border");
+  return launch_apply_kernel<R, MH>(src, n_crops, h, w, C, kc, dst, kc_img, sg, st);
 }
 
 }  // namespace
@@ -445,4 +529,31 @@ int cseg_jbu_apply_fused(const bf16* src, int n_crops, int h, int w, int C, cons
   }
   if (radius == 5) return launch_fused<5, 1>(src, n_crops, h, w, C, kern, ldk, dst, tabs, st);
   return launch_fused<3, 1>(src, n_crops, h, w, C, kern, ldk, dst, tabs, st);
+}
+
+// image-level composite kernels; returns 1 when the shape is not covered
+int cseg_jbu_composite_image_tc(const bf16* kern_img, int ldk, int ih, int iw, int gh, int gw, int radius, bf16* kc_img,
+                                void* tabs, cudaStream_t st) {
+  if (ldk % 8 != 0 || (radius != 5 && radius != 3)) return 1;
+  if (((uintptr_t)kern_img & 15) != 0 || ((uintptr_t)kc_img & 15) != 0 || ((uintptr_t)tabs & 15) != 0) return 1;
+  if (radius == 5) return launch_composite_image<5>(kern_img, ldk, ih, iw, gh, gw, kc_img, (uint8_t*)tabs, st);
+  return launch_composite_image<3>(kern_img, ldk, ih, iw, gh, gw, kc_img, (uint8_t*)tabs, st);
+}
+
+// cseg_jbu_apply with kernels shared across crops (include/clipseg.h); returns 1 when the shape is not covered
+int cseg_jbu_apply_shared_tc(const bf16* src, int n_crops, int h, int w, int C, const bf16* kern_border, const bf16* kern_img,
+                             const bf16* kc_img, const ShareGeom& sg, int ldk, int radius, bf16* dst, void* scratch,
+                             cudaStream_t st) {
+  if (C % 128 != 0 || ldk % 8 != 0 || (radius != 5 && radius != 3)) return 1;
+  if (2 * h < 2 * CSEG_JBU_FB_COMP + 2 || 2 * w < 34) return 1;
+  if (((uintptr_t)src & 15) != 0 || ((uintptr_t)kern_border & 15) != 0 || ((uintptr_t)kern_img & 15) != 0 ||
+      ((uintptr_t)kc_img & 15) != 0 || ((uintptr_t)scratch & 15) != 0)
+    return 1;
+  uint8_t* sc = (uint8_t*)scratch;
+  if (C % 256 == 0) {
+    if (radius == 5) return launch_fused_shared<5, 2>(src, n_crops, h, w, C, kern_border, kern_img, kc_img, sg, ldk, dst, sc, st);
+    return launch_fused_shared<3, 2>(src, n_crops, h, w, C, kern_border, kern_img, kc_img, sg, ldk, dst, sc, st);
+  }
+  if (radius == 5) return launch_fused_shared<5, 1>(src, n_crops, h, w, C, kern_border, kern_img, kc_img, sg, ldk, dst, sc, st);
+  return launch_fused_shared<3, 1>(src, n_crops, h, w, C, kern_border, kern_img, kc_img, sg, ldk, dst, sc, st);
 }

@@ -6,6 +6,7 @@
 //   [fixup_proj: two 1x1 convs = two cseg_gemm calls with GELU / residual epilogues, :264]
 //   apply     : bicubic x2 + reflect pad + adaptive conv                   (:268-274, :14-25)
 #include "common.cuh"
+#include "jbu_share.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -338,7 +339,8 @@ int cseg_jbu_guidance_proj_f16(const ImgView& img, const int32_t* windows, int n
 int cseg_jbu_range_proj_f16(const float* guid, int n_pix, const float* w0, const float* b0, const float* w3,
                             const float* b3, void* proj, cudaStream_t st);
 int cseg_jbu_range_kernel_mma(const void* proj_f16, const float* guid, int n_crops, int gh, int gw, int radius,
-                              float pos_temp, float inv2s2, void* kern, int kwidth, int ldk, cudaStream_t st);
+                              float pos_temp, float inv2s2, void* kern, int kwidth, int ldk, cudaStream_t st,
+                              const ShareGeom* sg = nullptr, int fb = 0);
 
 extern "C" {
 
@@ -397,6 +399,11 @@ int cseg_jbu_adaptive_conv_tc(const bf16* hr, int n_crops, int H2, int W2, int C
                               bf16* dst, cudaStream_t st);
 int cseg_jbu_apply_fused(const bf16* src, int n_crops, int h, int w, int C, const bf16* kern, int ldk, int radius,
                          bf16* dst, void* scratch, cudaStream_t st);
+int cseg_jbu_composite_image_tc(const bf16* kern_img, int ldk, int ih, int iw, int gh, int gw, int radius, bf16* kc_img,
+                                void* tabs, cudaStream_t st);
+int cseg_jbu_apply_shared_tc(const bf16* src, int n_crops, int h, int w, int C, const bf16* kern_border, const bf16* kern_img,
+                             const bf16* kc_img, const ShareGeom& sg, int ldk, int radius, bf16* dst, void* scratch,
+                             cudaStream_t st);
 static bool apply_fused_enabled() {  // CSEG_APPLY_FUSED=0 selects bicubic2x + the stand-alone conv (A/B measurements)
   static int on = -1;
   if (on < 0) {
@@ -477,6 +484,52 @@ int cseg_jbu_range_kernel(int proj_dtype, const void* proj_v, const float* guid,
   }
   if (radius == 5) return launch_range_kernel<float, 5>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, kwidth, ldk, st);
   return launch_range_kernel<float, 3>(proj, guid, n_crops, gh, gw, pos_temp, inv2s2, kern, kwidth, ldk, st);
+}
+
+static int share_geom(const cseg_jbu_share* sh, ShareGeom& sg, const char* who) {
+  CSEG_REQUIRE(sh && sh->windows && sh->shift >= 0 && sh->shift <= 4 && sh->pitch > 0, "%s: bad cseg_jbu_share", who);
+  sg.wins = sh->windows;
+  sg.shift = sh->shift;
+  sg.pitch = sh->pitch;
+  return 0;
+}
+
+int cseg_jbu_share_rows(int gh, int gw, int fb) { return border_rows(gh, gw, fb); }
+
+int cseg_jbu_range_kernel_border(const void* proj_img, const float* guid_img, const cseg_jbu_share* share, int n_crops,
+                                 int gh, int gw, int radius, float range_temp, float sigma_spatial, void* kern_border,
+                                 int kwidth, int ldk, void* stream) {
+  ShareGeom sg;
+  if (int rc = share_geom(share, sg, "jbu_range_kernel_border")) return rc;
+  CSEG_REQUIRE(n_crops > 0 && gh > 2 * CSEG_JBU_FB_RANGE && gw >= 32, "jbu_range_kernel_border: region %dx%d too small", gh, gw);
+  const float pos_temp = fminf(fmaxf(expf(range_temp), 1e-4f), 1e4f);
+  const float inv2s2 = 1.0f / (2.0f * sigma_spatial * sigma_spatial);
+  const int rc = cseg_jbu_range_kernel_mma(proj_img, guid_img, n_crops, gh, gw, radius, pos_temp, inv2s2, kern_border, kwidth,
+                                           ldk, (cudaStream_t)stream, &sg, CSEG_JBU_FB_RANGE);
+  if (rc == 1) CSEG_FAIL(CSEG_EUNSUPPORTED, "jbu_range_kernel_border: radius=%d kwidth=%d not covered (5/128, 3/64)", radius, kwidth);
+  return rc;
+}
+
+int cseg_jbu_composite_image(const void* kern_img, int ldk, int ih, int iw, int gh, int gw, int radius, void* kc_img,
+                             void* tabs_scratch, void* stream) {
+  CSEG_REQUIRE(kern_img && kc_img && tabs_scratch && ih > 0 && iw > 0, "jbu_composite_image: null operand / empty image");
+  CSEG_REQUIRE(gh >= 2 * CSEG_JBU_FB_COMP + 2 && gw >= 34, "jbu_composite_image: crop region %dx%d too small", gh, gw);
+  const int rc = cseg_jbu_composite_image_tc((const bf16*)kern_img, ldk, ih, iw, gh, gw, radius, (bf16*)kc_img, tabs_scratch,
+                                             (cudaStream_t)stream);
+  if (rc == 1) CSEG_FAIL(CSEG_EUNSUPPORTED, "jbu_composite_image: radius=%d ldk=%d not covered", radius, ldk);
+  return rc;
+}
+
+int cseg_jbu_apply_shared(const void* src, int n_crops, int h, int w, int C, const void* kern_border, const void* kern_img,
+                          const void* kc_img, const cseg_jbu_share* share, int ldk, int radius, void* dst, void* scratch,
+                          void* stream) {
+  ShareGeom sg;
+  if (int rc = share_geom(share, sg, "jbu_apply_shared")) return rc;
+  CSEG_REQUIRE(src && kern_border && kern_img && kc_img && dst && scratch && n_crops > 0, "jbu_apply_shared: null operand");
+  const int rc = cseg_jbu_apply_shared_tc((const bf16*)src, n_crops, h, w, C, (const bf16*)kern_border, (const bf16*)kern_img,
+                                          (const bf16*)kc_img, sg, ldk, radius, (bf16*)dst, scratch, (cudaStream_t)stream);
+  if (rc == 1) CSEG_FAIL(CSEG_EUNSUPPORTED, "jbu_apply_shared: shape not covered (C %% 128, radius 3/5, 2h > 2*%d+2, 2w >= 34)", CSEG_JBU_FB_COMP);
+  return rc;
 }
 
 int cseg_jbu_apply(int dtype, const void* src, int n_crops, int h, int w, int C, const void* kern, int ldk, int radius,

@@ -12,6 +12,7 @@
 // 2^(m_row - m_final) -- is applied while the staged rows are copied out as full 16-byte vectors of the
 // [pixels, ldk] kernel matrix (taps, then the 3 guidance channels, then zeros).
 #include "common.cuh"
+#include "jbu_share.cuh"
 #include <cuda_fp16.h>
 
 namespace {
@@ -38,11 +39,15 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], u
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int R, int LDK>
+// BORDER = false: every pixel of n regions of gh x gw (one crop each, or the whole canvas as one region), dense output
+// [region][gh][gw].  BORDER = true (jbu_share.cuh): only the border frame of every crop -- top / bottom `fb` rows and
+// the left / right 16 columns -- read from the IMAGE-LEVEL projection / guidance buffers at the crop's origin (reflect
+// padding is relative to the crop), compact output.
+template <int R, int LDK, bool BORDER>
 __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __restrict__ proj,
                                                              const float4* __restrict__ guid, int gh, int gw,
                                                              float pos_temp, float inv2s2, bf16* __restrict__ kern,
-                                                             int ldk) {
+                                                             int ldk, const ShareGeom sg, int fb) {
   pdl_grid_sync();
   constexpr int D = 2 * R + 1, D2 = D * D;
   constexpr int NB = (16 + 2 * R + 7) / 8;       // 8-position blocks per 16-query block
@@ -55,14 +60,41 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
   float* mrow = reinterpret_cast<float*>(rsm + HR * NPOS * PROW + ((D2 * 4 + 15) & ~15) + TYR * 16 * (LDK + SPAD) * 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
-  const int crop = blockIdx.z, y0 = blockIdx.y * TYR, x0 = blockIdx.x * TXR;
-  const __half* pc = proj + (size_t)crop * gh * gw * KD;
+  const int crop = blockIdx.z;
+  int y0, x0, nxb = TXR / 16, ylim = gh, pitch = gw;
+  const __half* pc;
+  const float4* gc;
+  if (!BORDER) {
+    y0 = blockIdx.y * TYR;
+    x0 = blockIdx.x * TXR;
+    pc = proj + (size_t)crop * gh * gw * KD;
+    gc = guid + (size_t)crop * gh * gw;
+  } else {
+    const int ntx = (gw + TXR - 1) / TXR, t1 = (fb / TYR) * ntx, idx = blockIdx.x;
+    if (idx < t1) {                                            // top strip
+      y0 = (idx / ntx) * TYR;
+      x0 = (idx % ntx) * TXR;
+    } else if (idx < 2 * t1) {                                 // bottom strip
+      y0 = gh - fb + ((idx - t1) / ntx) * TYR;
+      x0 = ((idx - t1) % ntx) * TXR;
+    } else {                                                   // left / right 16 columns of the rows in between
+      const int j = idx - 2 * t1;
+      y0 = fb + (j >> 1) * TYR;
+      x0 = (j & 1) ? gw - 16 : 0;
+      nxb = 1;
+      ylim = gh - fb;
+    }
+    pitch = sg.pitch;
+    const size_t org = (size_t)(sg.wins[crop * 4] >> sg.shift) * pitch + (sg.wins[crop * 4 + 1] >> sg.shift);
+    pc = proj + org * KD;
+    gc = guid + org;
+  }
 
   for (int e = tid; e < HR * NPOS * 4; e += TYR * 32) {      // 4 x 16 B per position, all in flight (cp.async)
     const int ch = e & 3, pos = (e >> 2) % NPOS, hy = (e >> 2) / NPOS;
     const int yy = reflect1(min(y0 - R + hy, gh - 1 + R), gh), xx = reflect1(min(x0 - R + pos, gw - 1 + R), gw);
     const uint32_t dst = psm + (uint32_t)((hy * NPOS + pos) * PROW + ch * 16);
-    const __half* src = pc + ((size_t)yy * gw + xx) * KD + ch * 8;
+    const __half* src = pc + ((size_t)yy * pitch + xx) * KD + ch * 8;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -81,7 +113,7 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
 #pragma unroll 1
   for (int xb = 0; xb < TXR / 16; ++xb) {
     const int xq0 = x0 + xb * 16;
-    if (y >= gh || xq0 >= gw) break;                         // warp-uniform
+    if (y >= ylim || xq0 >= gw || xb >= nxb) break;          // warp-uniform
     uint32_t a[2][4];
     {
       const uint32_t base = psm + (uint32_t)(((warp + R) * NPOS + xb * 16 + R + (q & 1) * 8 + rr) * PROW + (q >> 1) * 16);
@@ -197,7 +229,7 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
       }
       if (v == D2 / 8) {                                       // columns D2 .. D2+2: guidance (RGB) of this pixel
         const int x = min(xq0 + px, gw - 1);
-        const float4 gv = guid[((size_t)crop * gh + y) * gw + x];
+        const float4 gv = gc[(size_t)y * pitch + x];
         f[D2 % 8] = gv.x;
         f[D2 % 8 + 1] = gv.y;
         f[D2 % 8 + 2] = gv.z;
@@ -207,7 +239,9 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
         __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
         for (int k = 0; k < 4; ++k) op[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-        *reinterpret_cast<uint4*>(kern + (((size_t)crop * gh + y) * gw + xq0 + px) * ldk + v * 8) = o;
+        const size_t orow = BORDER ? (size_t)crop * border_rows(gh, gw, fb) + border_index(y, xq0 + px, gh, gw, fb)
+                                   : ((size_t)crop * gh + y) * gw + xq0 + px;
+        *reinterpret_cast<uint4*>(kern + orow * ldk + v * 8) = o;
       }
     }
     __syncwarp();
@@ -357,12 +391,22 @@ __global__ void __launch_bounds__(256) range_proj_f16_kernel(const float4* __res
 
 template <int R, int LDK>
 int launch(const __half* proj, const float* guid, int n_crops, int gh, int gw, float pos_temp, float inv2s2, bf16* kern,
-           int ldk, cudaStream_t st) {
+           int ldk, cudaStream_t st, const ShareGeom* sg = nullptr, int fb = 0) {
   constexpr int D2 = (2 * R + 1) * (2 * R + 1), NB = (16 + 2 * R + 7) / 8, HR = TYR + 2 * R, NPOS = 16 + NB * 8;
   const int smem = HR * NPOS * PROW + ((D2 * 4 + 15) & ~15) + TYR * 16 * (LDK + SPAD) * 2 + TYR * 16 * MROWS * 4;
-  CSEG_SET_SMEM((range_kernel_mma<R, LDK>), smem);
-  dim3 grid(cdiv(gw, TXR), cdiv(gh, TYR), n_crops);
-  cseg_launch(range_kernel_mma<R, LDK>, dim3(grid), dim3(TYR * 32), smem, st, proj, (const float4*)guid, gh, gw, pos_temp, inv2s2, kern, ldk);
+  if (sg == nullptr) {
+    CSEG_SET_SMEM((range_kernel_mma<R, LDK, false>), smem);
+    dim3 grid(cdiv(gw, TXR), cdiv(gh, TYR), n_crops);
+    ShareGeom none = {nullptr, 0, 0};
+    cseg_launch(range_kernel_mma<R, LDK, false>, dim3(grid), dim3(TYR * 32), smem, st, proj, (const float4*)guid, gh, gw, pos_temp,
+                inv2s2, kern, ldk, none, 0);
+  } else {
+    CSEG_SET_SMEM((range_kernel_mma<R, LDK, true>), smem);
+    const int tiles = 2 * (fb / TYR) * cdiv(gw, TXR) + 2 * cdiv(gh - 2 * fb, TYR);
+    dim3 grid(tiles, 1, n_crops);
+    cseg_launch(range_kernel_mma<R, LDK, true>, dim3(grid), dim3(TYR * 32), smem, st, proj, (const float4*)guid, gh, gw, pos_temp,
+                inv2s2, kern, ldk, *sg, fb);
+  }
   CSEG_LAUNCH_CHECK("jbu_range_kernel_mma");
   return 0;
 }
@@ -390,13 +434,15 @@ int cseg_jbu_guidance_proj_f16(const ImgView& img, const int32_t* windows, int n
   return 0;
 }
 
-// returns 1 when (radius, ldk) is not covered
+// returns 1 when (radius, ldk) is not covered.  sg != nullptr: border frames only (jbu_share.cuh), fb % 8 == 0.
 int cseg_jbu_range_kernel_mma(const void* proj_f16, const float* guid, int n_crops, int gh, int gw, int radius,
-                              float pos_temp, float inv2s2, void* kern, int kwidth, int ldk, cudaStream_t st) {
+                              float pos_temp, float inv2s2, void* kern, int kwidth, int ldk, cudaStream_t st,
+                              const ShareGeom* sg, int fb) {
   if (ldk % 8 != 0 || ((uintptr_t)kern & 15) != 0) return 1;
+  if (sg != nullptr && (fb <= 0 || fb % TYR != 0 || gh <= 2 * fb || gw < 32)) return 1;
   if (radius == 5 && kwidth == 128)
-    return launch<5, 128>((const __half*)proj_f16, guid, n_crops, gh, gw, pos_temp, inv2s2, (bf16*)kern, ldk, st);
+    return launch<5, 128>((const __half*)proj_f16, guid, n_crops, gh, gw, pos_temp, inv2s2, (bf16*)kern, ldk, st, sg, fb);
   if (radius == 3 && kwidth == 64)
-    return launch<3, 64>((const __half*)proj_f16, guid, n_crops, gh, gw, pos_temp, inv2s2, (bf16*)kern, ldk, st);
+    return launch<3, 64>((const __half*)proj_f16, guid, n_crops, gh, gw, pos_temp, inv2s2, (bf16*)kern, ldk, st, sg, fb);
   return 1;
 }

@@ -182,7 +182,7 @@ __device__ __forceinline__ uint8_t post_process(const AccumParams& p, const int*
 // <= 4..9 candidates instead of all n_crops.  When the crop logits are at crop resolution and no final resize is needed
 // (the JBU path) the PX pixels of a thread read each crop's logits with one 16-byte load per query.
 template <int QT, int PX>
-__global__ void __launch_bounds__(256) accum_argmax_kernel(const AccumParams p) {
+__global__ void __launch_bounds__(256, (QT <= 8) ? 3 : 2) accum_argmax_kernel(const AccumParams p) {
   pdl_grid_sync();
   extern __shared__ int4 s_wins[];                              // [n_crops] candidate windows (compacted)
   int* s_cand = reinterpret_cast<int*>(s_wins + p.n_crops);     // [n_crops] their crop indices

@@ -16,6 +16,7 @@ streams only -- there is no torch compute on the per-image path and no CPU fallb
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -351,9 +352,58 @@ class JBUEngine:
         self.b_fin = f32(sd['fixup_proj.1.bias'])
         self.ws = Workspace(self.device)
 
+    # ---- kernels shared across overlapping crops (csrc/jbu_share.cuh) ----------------------------------------------
+    SHARED_STAGES = (2, 3)        # the 112^2 and 224^2 stages: 94 % of the pixels; the frames of stages 0/1 are most of the crop
+
+    def share_ok(self, wl, n_canvas_px: int, crop_h: int, crop_w: int, pad_top: int, pad_left: int) -> bool:
+        """Guidance pooling -> range projection -> range kernel -> fix-up -> composite kernels depend on the image, not
+        on the crop, away from the crop border.  Sharing needs full-size windows on a 16-pixel lattice (pooling windows
+        and bicubic phases then coincide between crops) and pays when the windows overlap (>= 2x coverage)."""
+        if self.cdt != torch.bfloat16 or os.environ.get('CSEG_JBU_SHARE', '1') == '0':
+            return False
+        if pad_top or pad_left or crop_h % 16 or crop_w % 16 or crop_h < 16 * 4 or crop_w < 16 * 4:
+            return False
+        if any(st['ldk'] not in (64, 128) for st in self.stages):
+            return False
+        if any((y1 % 16) or (x1 % 16) or (h, w) != (crop_h, crop_w) for (y1, x1, h, w) in wl):
+            return False
+        return len(wl) * crop_h * crop_w >= 2 * n_canvas_px
+
+    def prepare_shared(self, img, crop_h: int, crop_w: int, gh: int, gw: int) -> dict:
+        """Image-level tensors of the shared stages for the whole canvas of `img` (one region = all stacked images; the
+        seams between images lie inside every crop's border frame, which is computed per crop)."""
+        ws = self.ws
+        img = ops._image(img)
+        Hc, W = img.H, img.W
+        key = (Hc, W)
+        if getattr(self, '_full_win', None) is None:
+            self._full_win = {}
+        if key not in self._full_win:
+            self._full_win[key] = torch.tensor([(0, 0, Hc, W)], dtype=torch.int32, device=self.device)
+        full = self._full_win[key]
+        out = {}
+        for si in self.SHARED_STAGES:
+            st = self.stages[si]
+            GH, GW = gh << (si + 1), gw << (si + 1)                      # crop region at this stage
+            shift = (crop_h // GH).bit_length() - 1                      # image pixels per stage pixel = 2^shift
+            IH, IW = Hc >> shift, W >> shift
+            npx, kw = IH * IW, st['ldk']
+            guid = ws.get(f'img_guid{si}', (npx, 4), torch.float32)
+            proj = ws.get(f'img_proj{si}', (npx, 32), torch.float16)
+            ops.jbu_guidance_proj(img, full, Hc, W, 0, 0, IH, IW, st['rp_w0'], st['rp_b0'], st['rp_w3'], st['rp_b3'], guid, proj)
+            kraw = ws.get(f'img_kraw{si}', (npx, kw), self.cdt)
+            kern = ws.get(f'img_kern{si}', (npx, kw), self.cdt)
+            ops.jbu_range_kernel(proj, guid, 1, IH, IW, st['radius'], st['range_temp'], st['sigma'], kraw)
+            ops.jbu_kernel_fixup(kraw, st['fx_w0'], st['fx_b0'], st['fx_w3'][:, :kw], st['fx_b3'], kern)
+            kc = ws.get(f'img_kc{si}', (npx, 128), self.cdt)
+            tabs = ws.get('img_tabs', ((GH + GW) * 512,), torch.uint8)
+            ops.jbu_composite_image(kern, IH, IW, GH, GW, st['radius'], kc, tabs)
+            out[si] = dict(guid=guid, proj=proj, kern=kern, kc=kc, shift=shift, pitch=IW)
+        return out
+
     def upsample(self, feats: torch.Tensor, gh: int, gw: int, img: torch.Tensor, windows: torch.Tensor,
                  crop_h: int, crop_w: int, pad_top: int = 0, pad_left: int = 0,
-                 taps: Optional[dict] = None, final_conv: bool = True) -> torch.Tensor:
+                 taps: Optional[dict] = None, final_conv: bool = True, shared: Optional[dict] = None) -> torch.Tensor:
         """feats T [n*gh*gw, C] channel-last; returns T [n*(16gh)*(16gw), C] after the final fix-up
         (upsamplers.py:320-325); with final_conv=False the output of the fourth stage (the caller fuses the
         1x1 conv with the normalise + similarity, ``ops.fixup_norm_sim``)."""
@@ -363,6 +413,21 @@ class JBUEngine:
         for si, st in enumerate(self.stages):
             GH, GW = 2 * h, 2 * w
             npix = n * GH * GW
+            if shared is not None and si in shared:
+                # border frames per crop from the image-level projections; interior pixels read the image-level tensors
+                sh, kw = shared[si], st['ldk']
+                rb = ops.jbu_share_rows(GH, GW, ops.FB_RANGE)
+                kraw_b = ws.get('kraw_b', (n * rb, kw), cdt)
+                kern_b = ws.get('kern_b', (n * rb, kw), cdt)
+                ops.jbu_range_kernel_border(sh['proj'], sh['guid'], windows, sh['shift'], sh['pitch'], n, GH, GW,
+                                            st['radius'], st['range_temp'], st['sigma'], kraw_b)
+                ops.jbu_kernel_fixup(kraw_b, st['fx_w0'], st['fx_b0'], st['fx_w3'][:, :kw], st['fx_b3'], kern_b)
+                hr = ws.get('hr', (npix, C), cdt)
+                dst = ws.get(f'up{si % 2}', (npix, C), cdt)
+                ops.jbu_apply_shared(s, n, h, w, C, kern_b, sh['kern'], sh['kc'], windows, sh['shift'], sh['pitch'],
+                                     st['radius'], dst, hr)
+                s, h, w = dst, GH, GW
+                continue
             guid = ws.get('guid', (npix, 4), f32)
             proj = ws.get('proj', (npix, 32), torch.float16 if cdt == torch.bfloat16 else f32)
             if cdt == torch.bfloat16 and GW >= 16:    # pooling + MLP in one kernel
@@ -432,7 +497,8 @@ class JBUEngine:
 
     def basis_logits(self, feats: torch.Tensor, gh: int, gw: int, img: torch.Tensor, windows: torch.Tensor,
                      crop_h: int, crop_w: int, pad_top: int, pad_left: int, text: torch.Tensor,
-                     logits: torch.Tensor, cls_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     logits: torch.Tensor, cls_bias: Optional[torch.Tensor] = None,
+                     shared: Optional[dict] = None) -> torch.Tensor:
         """Same result as upsample(final_conv=False) + ops.fixup_norm_sim: logits fp32 [n, Q, crop_h*crop_w].
         feats: [n * round_up(P, 8), C], every crop's P tokens followed by zero rows (ops.cls_debias rows_per_crop):
         the per-crop column blocks of gram / aux then start on 16-byte boundaries, which TMA requires."""
@@ -444,7 +510,8 @@ class JBUEngine:
         ops.gemm(feats, self.w_fin, g, residual=feats, alpha=0.1)
         ops.gemm(g, g, gram[:, :n * Tp])          # Gram matrix; one launch, the diagonal blocks are what is used
         ops.gemm(st['tb'], g, aux[:, :n * Tp])                      # <g, text[q]> and <g, b>
-        s = self.upsample(st['eye'], gh, gw, img, windows, crop_h, crop_w, pad_top, pad_left, None, final_conv=False)
+        s = self.upsample(st['eye'], gh, gw, img, windows, crop_h, crop_w, pad_top, pad_left, None, final_conv=False,
+                          shared=shared)
         return ops.basis_logits(s, st['Cb'], n, crop_h * crop_w, P, Tp, gram, aux, st['consts'], Q, logits, cls_bias)
 
 
@@ -472,6 +539,7 @@ class SegEngine:
         self.sim_cfg, self.outlier_cfg = sim_cfg, outlier_cfg
         self.jbu_chunk = jbu_chunk
         self.basis = basis          # bf16: upsample token indicators instead of features when that is cheaper
+        self.share_kernels = True   # bf16: JBU kernel generation once per image pixel + per-crop border frames
         self.ws = Workspace(self.device)
         self._win_cache: Dict[tuple, Tuple[torch.Tensor, list]] = {}
         self._graphs: Dict[tuple, dict] = {}
@@ -544,14 +612,18 @@ class SegEngine:
             if ps != 16:
                 raise ValueError('JBU upsamples x16 and only matches patch size 16 (segmentor.py:372)')
             logits = ws.get('logits', (n, self.Q, crop_h, crop_w), torch.float32)
+            shared = None
+            if self.share_kernels and taps is None and self.crop > 0 and self.up.share_ok(wl, H * W, crop_h, crop_w, pt, pl):
+                shared = self.up.prepare_shared(img, crop_h, crop_w, gh, gw)
             for c0 in range(0, n, self.jbu_chunk):
                 c1 = min(n, c0 + self.jbu_chunk)
                 if basis:
                     self.up.basis_logits(feats[c0 * Pp:c1 * Pp], gh, gw, img, win_dev[c0:c1], crop_h, crop_w, pt, pl,
-                                         self.text, logits[c0:c1], cls_bias[c0:c1] if cls_bias is not None else None)
+                                         self.text, logits[c0:c1], cls_bias[c0:c1] if cls_bias is not None else None,
+                                         shared=shared)
                     continue
                 y = self.up.upsample(feats[c0 * P:c1 * P], gh, gw, img, win_dev[c0:c1], crop_h, crop_w, pt, pl,
-                                     taps if c0 == 0 else None, final_conv=False)
+                                     taps if c0 == 0 else None, final_conv=False, shared=shared)
                 fused = (cdt == torch.bfloat16 and D % 128 == 0 and D <= 512 and self.Q <= 16)
                 scratch = None if fused else self.up.ws.get('fin', ((c1 - c0) * crop_h * crop_w, D), cdt)
                 ops.fixup_norm_sim(y, self.up.w_fin, c1 - c0, crop_h * crop_w, D, self.up.b_fin, 0.1, self.text,
@@ -661,25 +733,35 @@ class SegEngine:
         self._graphs[key] = st
         return st
 
-    def segment_batch(self, x: torch.Tensor, kind: str, ori_shape: Optional[Tuple[int, int]] = None,
+    def segment_batch(self, x, kind: str, ori_shape: Optional[Tuple[int, int]] = None,
                       labels_out: Optional[torch.Tensor] = None, use_graph: bool = True,
                       copy_out: bool = True) -> torch.Tensor:
-        """B equally sized images (host pinned or device tensor laid out as `kind`, see graph()) -> uint8 labels
-        [B,out_h,out_w] on the device.  The batch runs as ONE launch sequence over B times as many crops.
-        With copy_out=False the returned tensor is the graph's static output buffer, overwritten by the next call."""
-        B = x.shape[0]
-        H, W = (x.shape[1], x.shape[2]) if kind == 'u8hwc' else (x.shape[2], x.shape[3])
+        """B equally sized images -> uint8 labels [B,out_h,out_w] on the device.  `x`: one tensor laid out as `kind`
+        (see graph()) or a list of B per-image tensors (what a dataloader hands over), pinned host or device memory.
+        The batch runs as ONE launch sequence over B times as many crops.  With copy_out=False the returned tensor is
+        the graph's static output buffer, overwritten by the next call."""
+        xs = list(x) if isinstance(x, (list, tuple)) else None
+        first = xs[0] if xs is not None else x[0]
+        B = len(xs) if xs is not None else x.shape[0]
+        H, W = (first.shape[0], first.shape[1]) if kind == 'u8hwc' else (first.shape[1], first.shape[2])
         assert B == 1 or ori_shape is None
         with torch.cuda.device(self.device):
             if not use_graph:
-                xd = x.to(self.device, non_blocking=True).contiguous()
+                if xs is not None:
+                    xd = torch.stack([t.to(self.device, non_blocking=True) for t in xs])
+                else:
+                    xd = x.to(self.device, non_blocking=True).contiguous()
                 oh, ow = (H, W) if ori_shape is None else (int(ori_shape[0]), int(ori_shape[1]))
                 if labels_out is None:
                     labels_out = torch.empty((B, oh, ow), dtype=torch.uint8, device=self.device)
                 self.segment(self._image_of(kind, xd), ori_shape, labels=labels_out.view(B * oh, ow))
                 return labels_out
             st = self.graph(H, W, B, kind, ori_shape)
-            st['in'].copy_(x, non_blocking=True)         # H2D (or D2D) into the static input
+            if xs is not None:                           # H2D (or D2D) straight into the static input, image by image
+                for i, t in enumerate(xs):
+                    st['in'][i].copy_(t, non_blocking=True)
+            else:
+                st['in'].copy_(x, non_blocking=True)
             st['graph'].replay()
             if labels_out is not None:
                 labels_out.copy_(st['labels'], non_blocking=True)

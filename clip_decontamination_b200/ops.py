@@ -74,6 +74,23 @@ class Image:
         return cls(t, 'u8chw', B, H, W, (3 * H * W, H * W, W, 1), chan, mean, std)
 
 
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.ClipSegError('libclipseg needs CUDA tensors (there is no CPU path)')
+    if not t.is_contiguous():
+        raise _lib.ClipSegError('libclipseg needs contiguous tensors')
+    return C.c_void_p(t.data_ptr())
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise _lib.ClipSegError(f'unsupported dtype {t.dtype} (float32 / bfloat16)')
+
+
 def preprocess_u8(img_hwc_bgr: torch.Tensor, mean, std, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     H, W, _ = img_hwc_bgr.shape
     assert img_hwc_bgr.dtype == torch.uint8
@@ -196,6 +213,45 @@ def jbu_range_kernel(proj, guid, n_crops, gh, gw, radius, range_temp, sigma_spat
 def jbu_apply(src, n_crops, h, w, Cc, kern, radius, dst, hr_scratch):
     check(lib.cseg_jbu_apply(_dt(src), _ptr(src), n_crops, h, w, Cc, _ptr(kern), kern.shape[-1], radius, _ptr(dst),
                              _ptr(hr_scratch), _stream()))
+    return dst
+
+
+# ---- JBU kernels shared across overlapping crops (include/clipseg.h "shared kernel generation") -------------------------
+FB_RANGE, FB_COMP = 8, 12                  # CSEG_JBU_FB_RANGE / CSEG_JBU_FB_COMP
+
+
+def jbu_share_rows(gh: int, gw: int, fb: int) -> int:
+    return int(lib.cseg_jbu_share_rows(gh, gw, fb))
+
+
+def _share(windows: torch.Tensor, shift: int, pitch: int):
+    assert windows.dtype == torch.int32 and windows.is_contiguous()
+    sh = _lib.CsegJbuShare()
+    sh.windows, sh.shift, sh.pitch = windows.data_ptr(), shift, pitch
+    return sh
+
+
+def jbu_range_kernel_border(proj_img, guid_img, windows, shift, pitch, n_crops, gh, gw, radius, range_temp,
+                            sigma_spatial, kern_border):
+    """Range kernel of the border frames of n crops from the image-level projections (cseg_jbu_range_kernel_border)."""
+    assert kern_border.dim() == 2 and kern_border.stride(1) == 1
+    assert kern_border.shape[0] >= n_crops * jbu_share_rows(gh, gw, FB_RANGE)
+    check(lib.cseg_jbu_range_kernel_border(_ptr(proj_img), _ptr(guid_img), C.byref(_share(windows, shift, pitch)), n_crops,
+                                           gh, gw, radius, range_temp, sigma_spatial, C.c_void_p(kern_border.data_ptr()),
+                                           kern_border.shape[1], kern_border.stride(0), _stream()))
+    return kern_border
+
+
+def jbu_composite_image(kern_img, ih, iw, gh, gw, radius, kc_img, tabs):
+    check(lib.cseg_jbu_composite_image(_ptr(kern_img), kern_img.shape[-1], ih, iw, gh, gw, radius, _ptr(kc_img), _ptr(tabs),
+                                       _stream()))
+    return kc_img
+
+
+def jbu_apply_shared(src, n_crops, h, w, Cc, kern_border, kern_img, kc_img, windows, shift, pitch, radius, dst, scratch):
+    check(lib.cseg_jbu_apply_shared(_ptr(src), n_crops, h, w, Cc, _ptr(kern_border), _ptr(kern_img), _ptr(kc_img),
+                                    C.byref(_share(windows, shift, pitch)), kern_img.shape[-1], radius, _ptr(dst),
+                                    _ptr(scratch), _stream()))
     return dst
 
 

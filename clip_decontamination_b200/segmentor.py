@@ -172,6 +172,7 @@ class SegmentorEx(BaseSegmentor):
         self.result_dir, self.heatmap_dir = result_dir, heatmap_dir
         self.output_seg_logits = output_seg_logits or bool(heatmap_dir)
         self.use_graph = use_graph
+        self.last_labels = None          # uint8 label maps behind the last predict / test_step (native evaluators)
 
         up_engine = None
         if self.apply_sim_feat_up:                                   # segmentor.py:278-284
@@ -283,16 +284,19 @@ class SegmentorEx(BaseSegmentor):
 
     # ---- the fast path shared by predict / test_step / predict_u8 ---------------------------------
     def _labels(self, x, kind, ori_shapes):
-        """x: B equally sized images laid out as `kind` (engine.graph) -> list of B uint8 label maps [oh,ow] on the
-        device.  Images that keep their size go through ONE CUDA-graph replay as a stacked batch; images that are
-        resized to a different ori_shape (Resize in the test pipeline) are replayed one by one."""
-        B = x.shape[0]
-        H, W = (x.shape[1], x.shape[2]) if kind == 'u8hwc' else (x.shape[2], x.shape[3])
+        """x: B equally sized images laid out as `kind` (engine.graph), one tensor or a list of per-image tensors ->
+        uint8 label maps on the device ([B,oh,ow] tensor, or a list when the images are resized to different
+        ori_shapes).  Images that keep their size go through ONE CUDA-graph replay as a stacked batch; images that are
+        resized to ori_shape (Resize in the test pipeline) are replayed one by one."""
+        xs = list(x) if isinstance(x, (list, tuple)) else [x[i] for i in range(x.shape[0])]
+        H, W = (xs[0].shape[0], xs[0].shape[1]) if kind == 'u8hwc' else (xs[0].shape[1], xs[0].shape[2])
         oris = [tuple(int(v) for v in o[:2]) for o in ori_shapes]
         if all(o == (H, W) for o in oris):
-            lab = self.engine.segment_batch(x, kind, None, use_graph=self.use_graph)
-            return [lab[i] for i in range(B)]
-        return [self.engine.segment_batch(x[i:i + 1], kind, oris[i], use_graph=self.use_graph)[0] for i in range(B)]
+            self.last_labels = self.engine.segment_batch(x, kind, None, use_graph=self.use_graph)
+        else:
+            self.last_labels = [self.engine.segment_batch(xs[i].unsqueeze(0), kind, oris[i], use_graph=self.use_graph)[0]
+                                for i in range(len(xs))]
+        return self.last_labels
 
     def _attach(self, data_samples, labels, probs_list=None):
         out = []
@@ -346,12 +350,12 @@ class SegmentorEx(BaseSegmentor):
         if not fast:
             data = self.data_preprocessor(data, False)
             return self.predict(data['inputs'], data['data_samples'])
-        x = inputs[0].unsqueeze(0) if len(inputs) == 1 else torch.stack(list(inputs))
+        shape = tuple(inputs[0].shape[1:])
         if samples is not None:
-            oris = [ds.metainfo.get('ori_shape', x.shape[2:]) for ds in samples]
+            oris = [ds.metainfo.get('ori_shape', shape) for ds in samples]
         else:
-            oris = [x.shape[2:]] * x.shape[0]
-        return self._attach(samples, self._labels(x.contiguous(), 'u8chw', oris))
+            oris = [shape] * len(inputs)
+        return self._attach(samples, self._labels(list(inputs), 'u8chw', oris))
 
     @torch.no_grad()
     def predict_u8(self, img_hwc_bgr_u8, labels_out=None, use_graph=True, copy_out=True):

@@ -177,6 +177,40 @@ CSEG_API int cseg_jbu_range_kernel(int proj_dtype, const void* proj, const float
 CSEG_API int cseg_jbu_apply(int dtype, const void* src, int n_crops, int h, int w, int C, const void* kern,
                    int ldk, int radius, void* dst, void* hr_scratch, void* stream);
 
+/* ---- JBU kernel generation shared across overlapping crops (bf16 path) ---------------------------------------
+ * guidance pooling, range projection, range kernel, kernel fix-up and the bicubic-folded composite kernels depend on
+ * the IMAGE, not the crop, for every pixel further than radius + 6 from the crop border (reflect padding and bicubic
+ * border clamps, upsamplers.py:233,268-269).  With overlapping windows they are therefore computed once per image
+ * pixel ("image level": one region = the whole canvas, through the plain entry points above with n_crops = 1) plus,
+ * per crop, for a border frame: the top / bottom fb rows and the left / right 16 columns, stored compactly
+ * (cseg_jbu_share_rows(gh, gw, fb) rows per crop: top strip, bottom strip, then 32 pixels per remaining row).
+ * Requires full-size windows whose origins are multiples of 16 image pixels.  fb = CSEG_JBU_FB_RANGE for the
+ * range-kernel / fix-up tensors, CSEG_JBU_FB_COMP for the composite kernels (bicubic clamps reach further). */
+#define CSEG_JBU_FB_RANGE 8
+#define CSEG_JBU_FB_COMP 12
+typedef struct cseg_jbu_share {
+  const int32_t* windows; /* device int32 [n_crops][4] = {y1, x1, h, w} (canvas pixels), as for cseg_patchify */
+  int shift;              /* log2(image pixels per pixel of this stage): crop origin at this stage = (y1 >> shift, x1 >> shift) */
+  int pitch;              /* pixels per row of the image-level buffers of this stage (canvas W >> shift) */
+} cseg_jbu_share;
+CSEG_API int cseg_jbu_share_rows(int gh, int gw, int fb);
+/* range kernel (as cseg_jbu_range_kernel, fp16 projections -> bf16) of the border frames only: proj_img CSEG_F16
+ * [ih*iw, 32] and guid_img fp32 [ih*iw, 4] are IMAGE-LEVEL; kern_border bf16 [n_crops * rows(gh, gw, FB_RANGE), ldk]. */
+CSEG_API int cseg_jbu_range_kernel_border(const void* proj_img, const float* guid_img, const cseg_jbu_share* share,
+                                 int n_crops, int gh, int gw, int radius, float range_temp, float sigma_spatial,
+                                 void* kern_border, int kwidth, int ldk, void* stream);
+/* composite (bicubic-folded) kernels of every image-level pixel, valid for crop-interior pixels: kern_img bf16
+ * [ih*iw, ldk] (after the fix-up) -> kc_img bf16 [ih*iw, 128].  gh x gw = the crop region at this stage (selects the
+ * interior bicubic phase tables); tabs_scratch: (gh + gw) * 512 bytes. */
+CSEG_API int cseg_jbu_composite_image(const void* kern_img, int ldk, int ih, int iw, int gh, int gw, int radius,
+                             void* kc_img, void* tabs_scratch, void* stream);
+/* cseg_jbu_apply for n crops with shared kernels: interior pixels read kc_img at the crop's origin, border-frame
+ * pixels get their composite kernels here from kern_border (frame FB_RANGE) / kern_img.  src bf16 [n, h, w, C] ->
+ * dst bf16 [n, 2h, 2w, C].  scratch: n * rows(2h, 2w, FB_COMP) * 256 + (2h + 2w) * 512 bytes. */
+CSEG_API int cseg_jbu_apply_shared(const void* src, int n_crops, int h, int w, int C, const void* kern_border,
+                          const void* kern_img, const void* kc_img, const cseg_jbu_share* share, int ldk, int radius,
+                          void* dst, void* scratch, void* stream);
+
 /* ---- A10: L2-normalise + cosine logits, segmentor.py:374-375,378-379 --------------------------
  * feats T [rows, ldf] (D used) ; text fp32 [Q, D] ; logits fp32 [n_crops, Q, hw] with rows =
  * n_crops*hw.  cls_logit_bias (fp32 [n_crops, Q], may be NULL) is added (cls_token_lambda term). */

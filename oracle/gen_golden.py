@@ -292,9 +292,15 @@ def seg_full(out_name, model_name, cls, H, W, thd, bg, upsampler=None, extras=Tr
         assert agree >= 0.9999
     s = torch.sort(lg[0], dim=0, descending=True)[0]
     margin = (s[0] - s[1])
+    # with random-init text embeddings the configured prob_thd often sends every pixel to bg_idx: also store the
+    # reference's labels with the threshold off, so that label agreement at full size is not vacuous
+    seg.prob_thd = 0.0
+    pred0 = seg.postprocess_result(lg.clone(), None)
+    seg.prob_thd = thd
+    print(f'  label hist without threshold {torch.bincount(pred0.flatten(), minlength=seg.num_classes).tolist()}')
     _save(out_name, query_features=seg.query_features, query_idx=seg.query_idx,
           logits_sub=lg[0][:, ::sub, ::sub].half() if sub > 4 else lg[0][:, ::sub, ::sub],
-          labels=pred[0].to(torch.uint8),
+          labels=pred[0].to(torch.uint8), labels_nothd=pred0[0].to(torch.uint8),
           margin_u8=(margin / MARGIN_Q).clamp(0, 255).to(torch.uint8),
           meta=np.array([H, W, thd, bg, scene_seed, t_ref, crop, stride, ori[0], ori[1], sub, MARGIN_Q,
                          1.0 if extras else 0.0], dtype=np.float64),

@@ -35,6 +35,7 @@ def _stub(name, **attrs):
 
 
 _installed = False
+_CUDA_AUTOCAST = torch.cuda.amp.autocast          # build_ref_segmentor (CPU) substitutes it; the CUDA builder restores it
 
 
 def install():
@@ -112,6 +113,7 @@ def build_ref_segmentor_cuda(cfg: dict, state_dict: dict, name_path: str, *, ups
     install()
     import tempfile
     import segmentor as refseg
+    torch.cuda.amp.autocast = _CUDA_AUTOCAST
     refseg.create_model = lambda *a, **k: build_ref_clip(cfg, state_dict, 'fp16')
     extra = {}
     if upsampler is not None:
@@ -164,7 +166,7 @@ def build_ref_segmentor(cfg: dict, state_dict: dict, name_path: str, *, precisio
             pass
         def fwd(src, g):
             out = _orig(src, g)
-            out.half = lambda: out
+            out.half = (lambda: out.to(torch.bfloat16)) if low else (lambda: out)
             return out
         seg.upsampler.forward = fwd
     return seg

@@ -239,6 +239,34 @@ def test_seg_potsdam_jbu_basis_vs_literal(gold):
     assert torch.isfinite(lb).all() and d < 5e-3
 
 
+@pytest.mark.parametrize('batch', [1, 2])
+def test_jbu_shared_kernels_equal_per_crop(gold, batch):
+    """JBU kernel generation shared across overlapping crops (image-level tensors + per-crop border frames,
+    csrc/jbu_share.cuh) against the per-crop form: the same arithmetic per pixel, so the crop logits are identical."""
+    g = gold('seg_potsdam_jbu')
+    seg = _seg_engine('ViT-B-16', 'potsdam', 'bf16', g, upsampler='jbu_one')
+    H = W = 512
+    img = torch.cat([torch.from_numpy(synth.preprocess(synth.voronoi_scene(H, W, 2 + b))) for b in range(batch)], 1).cuda()
+    assert seg.up.share_ok(seg._windows(H, W, batch)[1], batch * H * W, 224, 224, 0, 0)
+    seg.share_kernels = True
+    a = seg.crop_logits(img, batch=batch)[0].clone()
+    seg.share_kernels = False
+    b = seg.crop_logits(img, batch=batch)[0].clone()
+    torch.cuda.synchronize()
+    d = (a - b).abs().max().item()
+    print(f'[shared vs per-crop JBU kernels, batch {batch}] max|dlogit| = {d:.3e}')
+    assert torch.isfinite(a).all() and d <= 1e-6
+    # literal (non-basis) head too
+    seg.basis = False
+    seg.share_kernels = True
+    a = seg.crop_logits(img, batch=batch)[0].clone()
+    seg.share_kernels = False
+    b = seg.crop_logits(img, batch=batch)[0].clone()
+    assert (a - b).abs().max().item() <= 1e-6
+    # windows off the 16-pixel lattice (snapped last window of a 1300-wide image) take the per-crop path
+    assert not seg.up.share_ok(seg._windows(1300, 1100)[1], 1300 * 1100, 224, 224, 0, 0)
+
+
 @pytest.mark.parametrize('upsampler', [None, 'jbu_one'])
 def test_batched_equals_per_image(gold, upsampler):
     """A batch [B,H,W,3] goes through every kernel as B x 16 crops (stacked canvas); crop-level work is independent,
