@@ -1,0 +1,334 @@
+// Standard multi-head attention of the ViT blocks on tcgen05 (bf16, head_dim 64, L <= 208, no statistics output):
+//   out = softmax(q k^T / 8) v                                (nn.MultiheadAttention, open_clip/transformer.py:204,218-232)
+//
+// One work item = one (crop, head); a persistent CTA per SM walks the items.  L <= 208 keys fit one MMA in N, so there
+// is no online softmax: per 128-query tile
+//   S[128, 208]  = Q_tile . K^T       4 x tcgen05.mma (K = 16) into TMEM (two S buffers: the MMA warp runs a tile ahead)
+//   P            = exp2((S - rowmax) * scale * log2 e)   by 8 warps: row quarter = warp % 4 (the TMEM lane window a warp
+//                  may touch), key half = warp / 4; row max / row sum are exchanged through shared memory; P is written
+//                  as bf16 straight into the K-major SWIZZLE_128B layout the second MMA reads
+//   O[128, 64]   = P . V              13 x tcgen05.mma; V is consumed in its natural [key][dim] layout as an MN-major
+//                  SWIZZLE_128B B operand (no transpose); 1 / rowsum is applied in the epilogue.
+// Q / K / V tiles arrive by TMA from the [rows, 3*width] QKV matrix (the rows of a crop that lie beyond L belong to the
+// next crop: those key columns are masked, those query rows are never stored).
+// Warp roles: 0-7 softmax + epilogue, 8 TMA producer, 9 TMEM allocator + MMA issuer.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace {
+
+constexpr int AT_HD = 64, AT_BM = 128, AT_LP = 208;           // keys padded to 13 K-steps of 16
+constexpr int AT_SMW = 8;                                      // softmax / epilogue warps
+constexpr int AT_THREADS = 32 * (AT_SMW + 2);
+constexpr int AT_Q_BYTES = AT_BM * 128, AT_KV_BYTES = AT_LP * 128, AT_P_BLK = AT_BM * 128, AT_P_BYTES = 4 * AT_P_BLK;
+constexpr int AT_Q_OFF = 0, AT_K_OFF = 2 * AT_Q_BYTES, AT_V_OFF = AT_K_OFF + 2 * AT_KV_BYTES;
+constexpr int AT_P_OFF = AT_V_OFF + 2 * AT_KV_BYTES, AT_RED_OFF = AT_P_OFF + AT_P_BYTES;
+constexpr int AT_RED_BYTES = (2 * 128 + 2 * 2 * 128) * 4;      // smax[2][128], ssum[2 tiles][2][128]
+constexpr int AT_BAR_OFF = AT_RED_OFF + AT_RED_BYTES, AT_NBARS = 15;
+constexpr int AT_SMEM = AT_BAR_OFF + AT_NBARS * 8 + 16 + 1024;
+constexpr int AT_S_COLS = 224, AT_O_COL = 448, AT_TMEM_COLS = 512;
+constexpr int AT_SPLIT = 112;                                  // key half 0: [0, 112), half 1: [112, 208)
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ float at_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t at_pack(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// MN-major SWIZZLE_128B descriptor (V as the B operand of P.V: 8 keys x 64 dims per 1024 B atom)
+__device__ __forceinline__ uint64_t at_mn_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 16;       // LBO: unused (N = 64 is one atom wide)
+  d |= (uint64_t)(1024 >> 4) << 32;       // SBO: stride between 8-key groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16, D = f32, A = B = bf16, A K-major, B MN-major (bit 16)
+__host__ __device__ constexpr uint32_t at_idesc_pv() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(AT_HD >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int L, int heads,
+                    int n_items, bf16* __restrict__ out, float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  float* smax = reinterpret_cast<float*>(smem + AT_RED_OFF);            // [2][128]
+  float* ssum = smax + 2 * 128;                                        // [2][2][128]
+  uint64_t* bars = (uint64_t*)(smem + AT_BAR_OFF);
+  uint32_t* tmem_slot = (uint32_t*)(bars + AT_NBARS);
+  const uint32_t b0 = smem_u32(bars);
+  const uint32_t q_full = b0, q_empty = b0 + 16, kv_full = b0 + 32, kv_empty = b0 + 48, s_full = b0 + 64, s_empty = b0 + 80;
+  const uint32_t p_full = b0 + 96, o_full = b0 + 104, o_empty = b0 + 112;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int width = heads * AT_HD, mt = (L + AT_BM - 1) / AT_BM;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKV) : "memory");
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(q_full + i * 8, 1);
+      mbar_init(q_empty + i * 8, 1);
+      mbar_init(kv_full + i * 8, 1);
+      mbar_init(kv_empty + i * 8, 1);
+      mbar_init(s_full + i * 8, 1);
+      mbar_init(s_empty + i * 8, AT_SMW);
+    }
+    mbar_init(p_full, AT_SMW);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, AT_SMW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == AT_SMW + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)AT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_grid_sync();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == AT_SMW) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      uint32_t qi = 0, ki = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ki) {
+        const int crop = item / heads, head = item - crop * heads;
+        const uint32_t kb = ki & 1, kph = (ki >> 1) & 1;
+        mbar_wait(kv_empty + kb * 8, kph ^ 1);
+        mbar_expect_tx(kv_full + kb * 8, 2 * AT_KV_BYTES);
+        tma_load_2d(sbase + AT_K_OFF + kb * AT_KV_BYTES, &tmKV, kv_full + kb * 8, width + head * AT_HD, crop * L);
+        tma_load_2d(sbase + AT_V_OFF + kb * AT_KV_BYTES, &tmKV, kv_full + kb * 8, 2 * width + head * AT_HD, crop * L);
+        for (int t = 0; t < mt; ++t, ++qi) {
+          const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+          mbar_wait(q_empty + qb * 8, qph ^ 1);
+          mbar_expect_tx(q_full + qb * 8, AT_Q_BYTES);
+          tma_load_2d(sbase + AT_Q_OFF + qb * AT_Q_BYTES, &tmQ, q_full + qb * 8, head * AT_HD, crop * L + t * AT_BM);
+        }
+      }
+    }
+  } else if (warp == AT_SMW + 1) {
+    // ---------------- MMA issuer: S of tile i is issued before P.V of tile i-1 ----------------
+    constexpr uint32_t idesc_s = make_idesc(AT_BM, AT_LP), idesc_pv = at_idesc_pv();
+    uint32_t qi = 0, ki = 0;
+    bool have_prev = false;
+    uint32_t prev_pi = 0, prev_kb = 0;
+    bool prev_last = false;
+    auto issue_pv = [&]() {
+      mbar_wait(p_full, prev_pi & 1);
+      mbar_wait(o_empty, (prev_pi & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < AT_LP / 16; ++j) {
+          const uint64_t adesc = make_sdesc(sbase + AT_P_OFF + (j >> 2) * AT_P_BLK + (j & 3) * 32);
+          const uint64_t bdesc = at_mn_desc(sbase + AT_V_OFF + prev_kb * AT_KV_BYTES + j * 2048);
+          umma_f16(tmem_base + AT_O_COL, adesc, bdesc, idesc_pv, j > 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        if (prev_last) umma_commit(kv_empty + prev_kb * 8);
+      }
+      __syncwarp();
+    };
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ki) {
+      const uint32_t kb = ki & 1, kph = (ki >> 1) & 1;
+      for (int t = 0; t < mt; ++t, ++qi) {
+        const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+        if (t == 0) mbar_wait(kv_full + kb * 8, kph);
+        mbar_wait(q_full + qb * 8, qph);
+        mbar_wait(s_empty + qb * 8, qph ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < AT_HD / 16; ++ks) {
+            const uint64_t adesc = make_sdesc(sbase + AT_Q_OFF + qb * AT_Q_BYTES + ks * 32);
+            const uint64_t bdesc = make_sdesc(sbase + AT_K_OFF + kb * AT_KV_BYTES + ks * 32);
+            umma_f16(tmem_base + qb * AT_S_COLS, adesc, bdesc, idesc_s, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(s_full + qb * 8);
+          umma_commit(q_empty + qb * 8);
+        }
+        __syncwarp();
+        if (have_prev) issue_pv();
+        have_prev = true;
+        prev_pi = qi;
+        prev_kb = kb;
+        prev_last = (t == mt - 1);
+      }
+    }
+    if (have_prev) issue_pv();
+  } else {
+    // ---------------- softmax + epilogue ----------------
+    const int q4 = warp & 3, hh = warp >> 2, row = q4 * 32 + lane;
+    const int c_begin = hh ? AT_SPLIT : 0, c_end = hh ? AT_LP : AT_SPLIT;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    uint8_t* prow = smem + AT_P_OFF + row * 128;
+    uint32_t qi = 0;
+    bool have_prev = false;
+    uint32_t prev_pi = 0;
+    int prev_row0 = 0, prev_head = 0, prev_valid = 0;
+    auto epilogue = [&]() {
+      mbar_wait(o_full, prev_pi & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(tlane + AT_O_COL + hh * 32, r);
+      const float* ss = ssum + (prev_pi & 1) * 256;
+      const float inv = 1.0f / (ss[row] + ss[128 + row]);
+      if (row < prev_valid) {
+        uint4* o = reinterpret_cast<uint4*>(out + (size_t)(prev_row0 + row) * width + prev_head * AT_HD + hh * 32);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint4 w;
+          w.x = at_pack(__uint_as_float(r[8 * v]) * inv, __uint_as_float(r[8 * v + 1]) * inv);
+          w.y = at_pack(__uint_as_float(r[8 * v + 2]) * inv, __uint_as_float(r[8 * v + 3]) * inv);
+          w.z = at_pack(__uint_as_float(r[8 * v + 4]) * inv, __uint_as_float(r[8 * v + 5]) * inv);
+          w.w = at_pack(__uint_as_float(r[8 * v + 6]) * inv, __uint_as_float(r[8 * v + 7]) * inv);
+          o[v] = w;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    };
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int crop = item / heads, head = item - crop * heads;
+      for (int t = 0; t < mt; ++t, ++qi) {
+        const uint32_t sb = qi & 1, sph = (qi >> 1) & 1;
+        mbar_wait(s_full + sb * 8, sph);
+        tc_fence_after();
+        const uint32_t ts = tlane + sb * AT_S_COLS;
+        // pass 1: row maximum over this warp's key half, then across the two halves
+        float m = -INFINITY;
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(ts + c, r);
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (c + e < L) m = fmaxf(m, __uint_as_float(r[e]));
+        }
+        smax[hh * 128 + row] = m;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * AT_SMW) : "memory");
+        m = fmaxf(smax[row], smax[128 + row]);
+        // epilogue of the previous tile: its P.V has completed, so the P buffer is free for this tile
+        if (have_prev) epilogue();
+        // pass 2: exponentials -> bf16 P in the K-major SWIZZLE_128B layout, row sum in fp32
+        const float msc = m * scale_log2e;
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(ts + c, r);
+          float ev[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            ev[e] = (c + e < L) ? at_ex2(fmaf(__uint_as_float(r[e]), scale_log2e, -msc)) : 0.f;
+            sum += ev[e];
+          }
+          uint8_t* pb = prow + (c >> 6) * AT_P_BLK;
+          const int j = (c & 63) >> 3;                                   // 16-byte chunk within the 128-byte row (even)
+          uint4 w0, w1;
+          w0.x = at_pack(ev[0], ev[1]);   w0.y = at_pack(ev[2], ev[3]);   w0.z = at_pack(ev[4], ev[5]);   w0.w = at_pack(ev[6], ev[7]);
+          w1.x = at_pack(ev[8], ev[9]);   w1.y = at_pack(ev[10], ev[11]); w1.z = at_pack(ev[12], ev[13]); w1.w = at_pack(ev[14], ev[15]);
+          *reinterpret_cast<uint4*>(pb + ((j ^ (row & 7)) << 4)) = w0;
+          *reinterpret_cast<uint4*>(pb + (((j + 1) ^ (row & 7)) << 4)) = w1;
+        }
+        ssum[(qi & 1) * 256 + hh * 128 + row] = sum;
+        tc_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(p_full);
+          mbar_arrive(s_empty + sb * 8);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * AT_SMW) : "memory");
+        have_prev = true;
+        prev_pi = qi;
+        prev_row0 = crop * L + t * AT_BM;
+        prev_head = head;
+        prev_valid = min(AT_BM, L - t * AT_BM);
+      }
+    }
+    if (have_prev) epilogue();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == AT_SMW + 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)AT_TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*AtEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+AtEncodeFn at_encode() {
+  static AtEncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (AtEncodeFn)p;
+  }
+  return fn;
+}
+// 2D bf16 map over the [rows, cols] QKV matrix: box {64 columns, box_rows}, SWIZZLE_128B, zero fill beyond the last row
+int at_make_map(CUtensorMap* m, const void* base, long long rows, int cols, int box_rows) {
+  AtEncodeFn enc = at_encode();
+  if (!enc) CSEG_FAIL(CSEG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) CSEG_FAIL(CSEG_ECUDA, "attention: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+bool at_enabled() {   // CSEG_ATTN_TC=0 selects the mma.sync kernel (A/B measurements)
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CSEG_ATTN_TC");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
+}  // namespace
+
+// returns 1 when the case is not covered (the caller falls back to the mma.sync kernel)
+int cseg_attention_tc(const bf16* qkv, int n_crops, int L, int heads, int head_dim, int mode, const float* simmap, bf16* out,
+                      float* stats, cudaStream_t st) {
+  if (!at_enabled() || head_dim != AT_HD || mode != CSEG_ATTN_STD || stats != nullptr || simmap != nullptr) return 1;
+  if (L < 17 || L > AT_LP || ((uintptr_t)qkv & 15) != 0 || ((uintptr_t)out & 15) != 0) return 1;
+  const int width = heads * AT_HD;
+  CUtensorMap tq, tkv;
+  if (int rc = at_make_map(&tq, qkv, (long long)n_crops * L, 3 * width, AT_BM)) return rc;
+  if (int rc = at_make_map(&tkv, qkv, (long long)n_crops * L, 3 * width, AT_LP)) return rc;
+  CSEG_SET_SMEM(attention_tc_kernel, AT_SMEM);
+  const int items = n_crops * heads;
+  const int grid = std::min(items, sm_count());
+  const float scale_log2e = 0.125f * 1.4426950408889634f;     // head_dim^-0.5 * log2(e)
+  cseg_launch(attention_tc_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tq, tkv, L, heads, items, out, scale_log2e);
+  CSEG_LAUNCH_CHECK("attention_tc");
+  return 0;
+}

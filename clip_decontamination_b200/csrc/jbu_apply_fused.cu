@@ -377,16 +377,21 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
     fz_fence_proxy_async();
     for (uint32_t j = (it >= FZ_INFL - 1 ? it - (FZ_INFL - 1) : 0); j < it; ++j) mbar_arrive(a_full0 + (j % FZ_NSTG) * 8);
   } else {
-    // ---------------- band builders: scatter the composite kernels of the tile's 64 pixels ----------------
+    // ---------------- band builders ----------------
+    // For output pixel n and composite-kernel row dy, the band tile holds, in strip row sr = (y >> 1) - (y0 >> 1) + dy,
+    // a 16-position (32-byte) segment that is zero except for the DC weights K'[dy][0..DC) at positions kk0 .. kk0 + DC.
+    // One unit of work = one (pixel, dy): the DC weights are cut out of the composite row with 256-bit shifts in
+    // registers and the WHOLE segment is written with two 16-byte stores (instead of DC scattered 2-byte stores into a
+    // zero background: the scatter was the largest consumer of shared-memory wavefronts of the kernel).
     const int bt = tid - FZ_BB_T0;                               // 0..127
-    constexpr int DC = 2 * DO + 1, NCH = (DC * DC + 7) / 8;      // 16-byte chunks per composite kernel (11 / 7)
-    constexpr int WPT = (FZ_NPX * NCH + 32 * FZ_BB_WARPS - 1) / (32 * FZ_BB_WARPS);
+    constexpr int DC = 2 * DO + 1;
+    constexpr int NU = FZ_NPX * DC;                              // (pixel, dy) units per tile
+    constexpr int UPT = (NU + 32 * FZ_BB_WARPS - 1) / (32 * FZ_BB_WARPS);
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
       int x0, y0, crop, c0;
       tile_coords(tile, x0, y0, crop, c0);
       const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
-      uint4 wv[WPT];
       // shared kernels (jbu_share.cuh): interior pixels read the image-level composite kernels at the crop's origin,
       // border-frame pixels the crop's compact frame tensor
       size_t org = 0, cbase = (size_t)crop * H2 * W2;
@@ -394,17 +399,21 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
         org = (size_t)(sg.wins[crop * 4] >> sg.shift) * sg.pitch + (sg.wins[crop * 4 + 1] >> sg.shift);
         cbase = (size_t)crop * border_rows(H2, W2, CSEG_JBU_FB_COMP);
       }
+      uint4 qa[UPT], qb[UPT];
 #pragma unroll
-      for (int k = 0; k < WPT; ++k) {
-        const int e = bt + k * 32 * FZ_BB_WARPS, n = e / NCH, v = e - n * NCH;
+      for (int k = 0; k < UPT; ++k) {
+        const int u = bt + k * 32 * FZ_BB_WARPS, n = u / DC, dy = u - n * DC;
         const int y = y0 + (n >> 4), x = x0 + (n & 15);
-        wv[k] = make_uint4(0, 0, 0, 0);                          // pixels outside the image: zero weights
-        if (n < FZ_NPX && y < H2 && x < W2) {
+        qa[k] = make_uint4(0, 0, 0, 0);                          // pixels outside the image: zero weights
+        qb[k] = make_uint4(0, 0, 0, 0);
+        if (u < NU && y < H2 && x < W2) {
           const bf16* kp;
           if (kc_img == nullptr) kp = kc + (cbase + (size_t)y * W2 + x) * 128;
           else if (border_interior(y, x, H2, W2, CSEG_JBU_FB_COMP)) kp = kc_img + (org + (size_t)y * sg.pitch + x) * 128;
           else kp = kc + (cbase + border_index(y, x, H2, W2, CSEG_JBU_FB_COMP)) * 128;
-          wv[k] = __ldg(reinterpret_cast<const uint4*>(kp + v * 8));
+          const int ch = (dy * DC) >> 3;                         // 16-byte chunk holding the first weight of this row
+          qa[k] = __ldg(reinterpret_cast<const uint4*>(kp) + ch);
+          if (ch < 15) qb[k] = __ldg(reinterpret_cast<const uint4*>(kp) + ch + 1);
         }
       }
       mbar_wait(b_empty0 + as * 8, aph ^ 1);
@@ -414,22 +423,46 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
         asm volatile("bar.sync 2, %0;" ::"n"(32 * FZ_BB_WARPS) : "memory");
       }
 #pragma unroll
-      for (int k = 0; k < WPT; ++k) {
-        const int e = bt + k * 32 * FZ_BB_WARPS, n = e / NCH, v = e - n * NCH;
-        if (n >= FZ_NPX) continue;
+      for (int k = 0; k < UPT; ++k) {
+        const int u = bt + k * 32 * FZ_BB_WARPS, n = u / DC, dy = u - n * DC;
+        if (u >= NU) continue;
         const int r = n >> 4, m = n & 15;
-        const unsigned short* hv = reinterpret_cast<const unsigned short*>(&wv[k]);
-        uint8_t* rowb = bbuf + (n >> 3) * 1024 + (n & 7) * 128;
-        const int sr0 = r >> 1, kk0 = m >> 1;                    // (y >> 1) - (y0 >> 1), (x >> 1) - (x0 >> 1)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int t = v * 8 + q;
-          if (t >= DC * DC) continue;
-          const int dy = (t * 57) >> 9;                          // t / 9 for t < 128 (DC == 9); exact division below otherwise
-          const int dyy = (DC == 9) ? dy : t / DC, dx = t - dyy * DC;
-          const int sr = sr0 + dyy, col = (sr & 3) * 16 + kk0 + dx;
-          *reinterpret_cast<unsigned short*>(rowb + (sr >> 2) * Cf::B_QUAD + ((((col >> 3) ^ (n & 7)) << 4) | ((col & 7) << 1))) = hv[q];
+        const int sr = (r >> 1) + dy, kk0 = m >> 1;              // strip row, first position of the segment
+        // 256-bit window (16 halfwords): drop the (dy * DC) & 7 halfwords in front of the row, keep DC, move to kk0
+        unsigned long long w0 = ((unsigned long long)qa[k].y << 32) | qa[k].x, w1 = ((unsigned long long)qa[k].w << 32) | qa[k].z;
+        unsigned long long w2 = ((unsigned long long)qb[k].y << 32) | qb[k].x, w3 = ((unsigned long long)qb[k].w << 32) | qb[k].z;
+        {
+          const int bits = ((dy * DC) & 7) * 16;                 // < 128
+          if (bits >= 64) { w0 = w1; w1 = w2; w2 = w3; w3 = 0; }
+          const int rs = bits & 63;
+          if (rs) {
+            w0 = (w0 >> rs) | (w1 << (64 - rs));
+            w1 = (w1 >> rs) | (w2 << (64 - rs));
+            w2 = (w2 >> rs) | (w3 << (64 - rs));
+            w3 >>= rs;
+          }
         }
+        // keep DC halfwords (DC = 9: 144 bits; DC = 7: 112 bits)
+        if (DC * 16 >= 128) { w2 &= (DC * 16 > 128) ? ((1ull << ((DC * 16 - 128) & 63)) - 1ull) : 0ull; }
+        else { w1 &= (1ull << ((DC * 16 - 64) & 63)) - 1ull; w2 = 0; }
+        w3 = 0;
+        {
+          const int bits = kk0 * 16;                             // < 128
+          if (bits >= 64) { w3 = w2; w2 = w1; w1 = w0; w0 = 0; }
+          const int ls = bits & 63;
+          if (ls) {
+            w3 = (w3 << ls) | (w2 >> (64 - ls));
+            w2 = (w2 << ls) | (w1 >> (64 - ls));
+            w1 = (w1 << ls) | (w0 >> (64 - ls));
+            w0 <<= ls;
+          }
+        }
+        uint8_t* rowb = bbuf + (sr >> 2) * Cf::B_QUAD + (n >> 3) * 1024 + (n & 7) * 128;
+        const int cch = (sr & 3) * 2;                            // the segment's two 16-byte chunks within the 128-byte row
+        *reinterpret_cast<uint4*>(rowb + ((cch ^ (n & 7)) << 4)) =
+            make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
+        *reinterpret_cast<uint4*>(rowb + (((cch + 1) ^ (n & 7)) << 4)) =
+            make_uint4((uint32_t)w2, (uint32_t)(w2 >> 32), (uint32_t)w3, (uint32_t)(w3 >> 32));
       }
       fz_fence_proxy_async();
       mbar_arrive(b_full0 + as * 8);

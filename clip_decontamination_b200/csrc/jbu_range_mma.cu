@@ -47,7 +47,7 @@ template <int R, int LDK, bool BORDER>
 __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __restrict__ proj,
                                                              const float4* __restrict__ guid, int gh, int gw,
                                                              float pos_temp, float inv2s2, bf16* __restrict__ kern,
-                                                             int ldk, const ShareGeom sg, int fb) {
+                                                             int ldk, const ShareGeom geom, int frame) {
   pdl_grid_sync();
   constexpr int D = 2 * R + 1, D2 = D * D;
   constexpr int NB = (16 + 2 * R + 7) / 8;       // 8-position blocks per 16-query block
@@ -70,22 +70,22 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
     pc = proj + (size_t)crop * gh * gw * KD;
     gc = guid + (size_t)crop * gh * gw;
   } else {
-    const int ntx = (gw + TXR - 1) / TXR, t1 = (fb / TYR) * ntx, idx = blockIdx.x;
+    const int ntx = (gw + TXR - 1) / TXR, t1 = (frame / TYR) * ntx, idx = blockIdx.x;
     if (idx < t1) {                                            // top strip
       y0 = (idx / ntx) * TYR;
       x0 = (idx % ntx) * TXR;
     } else if (idx < 2 * t1) {                                 // bottom strip
-      y0 = gh - fb + ((idx - t1) / ntx) * TYR;
+      y0 = gh - frame + ((idx - t1) / ntx) * TYR;
       x0 = ((idx - t1) % ntx) * TXR;
     } else {                                                   // left / right 16 columns of the rows in between
       const int j = idx - 2 * t1;
-      y0 = fb + (j >> 1) * TYR;
+      y0 = frame + (j >> 1) * TYR;
       x0 = (j & 1) ? gw - 16 : 0;
       nxb = 1;
-      ylim = gh - fb;
+      ylim = gh - frame;
     }
-    pitch = sg.pitch;
-    const size_t org = (size_t)(sg.wins[crop * 4] >> sg.shift) * pitch + (sg.wins[crop * 4 + 1] >> sg.shift);
+    pitch = geom.pitch;
+    const size_t org = (size_t)(geom.wins[crop * 4] >> geom.shift) * pitch + (geom.wins[crop * 4 + 1] >> geom.shift);
     pc = proj + org * KD;
     gc = guid + org;
   }
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
         __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
         for (int k = 0; k < 4; ++k) op[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-        const size_t orow = BORDER ? (size_t)crop * border_rows(gh, gw, fb) + border_index(y, xq0 + px, gh, gw, fb)
+        const size_t orow = BORDER ? (size_t)crop * border_rows(gh, gw, frame) + border_index(y, xq0 + px, gh, gw, frame)
                                    : ((size_t)crop * gh + y) * gw + xq0 + px;
         *reinterpret_cast<uint4*>(kern + orow * ldk + v * 8) = o;
       }

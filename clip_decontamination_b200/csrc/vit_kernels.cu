@@ -700,6 +700,9 @@ static int launch_attention(const void* qkv, int n_crops, int L, int heads, int 
   return 0;
 }
 
+int cseg_attention_tc(const bf16* qkv, int n_crops, int L, int heads, int head_dim, int mode, const float* simmap, bf16* out,
+                      float* stats, cudaStream_t st);
+
 extern "C" {
 
 int cseg_attention(int dtype, const void* qkv, int n_crops, int L, int heads, int head_dim, int mode,
@@ -709,7 +712,11 @@ int cseg_attention(int dtype, const void* qkv, int n_crops, int L, int heads, in
   CSEG_REQUIRE(mode >= CSEG_ATTN_STD && mode <= CSEG_ATTN_CAUSAL, "attention: unknown mode %d", mode);
   CSEG_REQUIRE(stats == nullptr || mode == CSEG_ATTN_STD, "attention: stats only with CSEG_ATTN_STD");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == CSEG_BF16) {   // tensor-core kernel; returns 1 for shapes it does not cover
+  if (dtype == CSEG_BF16) {   // tcgen05 kernel for the standard layers (head_dim 64, L <= 208, no statistics)
+    const int rc = cseg_attention_tc((const bf16*)qkv, n_crops, L, heads, head_dim, mode, simmap, (bf16*)out, stats, st);
+    if (rc <= 0) return rc;
+  }
+  if (dtype == CSEG_BF16) {   // mma.sync kernel; returns 1 for shapes it does not cover
     const int rc = cseg_attention_mma((const bf16*)qkv, n_crops, L, heads, head_dim, mode, simmap, sim_weight, (bf16*)out,
                                       stats, st);
     if (rc <= 0) return rc;

@@ -221,6 +221,29 @@ def test_attention_modes(ops, mode, dtype, L, hd):
         assert (s[:, :, 1] - torch.diagonal(wgt, dim1=2, dim2=3)[:, :, 1:]).abs().max().item() < 1e-6
 
 
+@pytest.mark.parametrize('n,L,heads', [(2, 197, 3), (5, 197, 12), (3, 128, 2), (2, 77, 4), (150, 197, 12), (1, 208, 1)])
+def test_attention_tcgen05_std(ops, n, L, heads):
+    """Standard attention on tcgen05 (attention_tc.cu: S in TMEM, softmax from tcgen05.ld, P.V as a second MMA) against
+    the torch formula and against the mma.sync kernel (selected by asking for the statistics output)."""
+    from clip_decontamination_b200._lib import ATTN
+    hd, d = 64, heads * 64
+    qkv = (torch.randn(n * L, 3 * d, generator=_g(3)) * 0.8).to(torch.bfloat16)
+    out = torch.full((n * L, d), float('nan'), device='cuda', dtype=torch.bfloat16)
+    ops.attention(qkv.cuda(), n, L, heads, hd, ATTN['STD'], out)
+    out2 = torch.empty_like(out)
+    stats = torch.zeros((n, heads, 2, L - 1), device='cuda')
+    ops.attention(qkv.cuda(), n, L, heads, hd, ATTN['STD'], out2, stats=stats)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    d12 = (out.float() - out2.float()).abs().max().item()
+    if n <= 5:
+        ref, _ = _attn_ref(qkv.float(), n, L, heads, 'STD', None, 0.0)
+        e = (out.float().cpu() - ref).abs().max().item()
+        print(f'[attention tcgen05 n={n} L={L} heads={heads}] vs torch {e:.3e}, vs mma.sync {d12:.3e}')
+        assert e < 2e-2
+    assert d12 < 2e-2
+
+
 def test_simmap(ops):
     n, L, w = 3, 197, 200
     x = torch.randn(n * L, w, generator=_g(1))

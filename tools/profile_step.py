@@ -21,12 +21,17 @@ from clip_decontamination_b200 import ops, synth  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--tiles', type=int, default=6)
 ap.add_argument('--workload', default='vaihingen512')
+ap.add_argument('--layers', type=int, default=0, help='truncate the ViT to this many blocks (0 = all): one launch per GEMM shape for --set full')
 args = ap.parse_args()
 wl = bench.WORKLOADS[args.workload]
 H, W, T = wl['H'], wl['W'], args.tiles
 torch.cuda.set_device(0)
 model = bench.build_model(torch.device('cuda', 0), 'bf16', wl)
 eng, K = model.engine, model.num_classes
+if args.layers:                       # first blocks + the final block (the modified attention lives in the last one)
+    v = eng.v
+    v.blocks = v.blocks[:args.layers - 1] + v.blocks[-1:]
+    v.layers = args.layers
 imgs = torch.stack([torch.from_numpy(np.ascontiguousarray(synth.voronoi_scene(H, W, 1000 + t).transpose(2, 0, 1))) for t in range(T)]).cuda()
 gt = torch.stack([torch.from_numpy(synth.synthetic_labels(H, W, K, 2000 + t)) for t in range(T)]).cuda()
 hist = torch.zeros((3, K), dtype=torch.int64, device='cuda')
