@@ -72,6 +72,8 @@ SIGNATURES = {
     'cseg_basis_logits': (_i, [_i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p, _p]),
     'cseg_accum_argmax': (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _i, _f, _f, _i,
                                _p, _p, _p, _p]),
+    'cseg_colorize': (_i, [_p, _ll, _p, _i, _p, _p]),
+    'cseg_heatmap': (_i, [_p, _i, _ll, _p, _p, _p]),
     'cseg_iou_hist': (_i, [_p, _p, _ll, _i, _i, _p, _p]),
 }
 for _name, (_res, _args) in SIGNATURES.items():

@@ -13,6 +13,9 @@
 // exists: HBM traffic drops from (write + re-read hr, 5 x the source) to the source itself, and the banded GEMM sees
 // 16 instead of 32 positions per source row and NLR = 10 instead of 14 rows per tile.
 //
+// Work unit = a vertical run of `seg` tiles of one (crop, 16-px column, channel slab): consecutive tiles of a run share
+// NLR - 2 of their NLR low-res source rows, so the source strips live in a ring of 16 slots and only the 2 new rows per
+// tile are fetched (the strips were 62 % of the kernel's L2 traffic: 10x halo amplification per 4 x 16 tile).
 // Per tile of 4 rows x 16 px and 128-channel slab, every low-res row s of the (NLR x 16) source patch costs one
 // tcgen05.mma  D[128 ch, 64 px] += A_s[128 ch, 16 pos] . B_s[16 pos, 64 px]  (A: MN-major SWIZZLE_128B straight from
 // the [pos][ch] HBM layout; B: composite band tile, K-major).  Warp roles of the persistent CTA:
@@ -25,12 +28,13 @@
 #include "tc_common.cuh"
 #include "jbu_share.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace {
 
 constexpr int FZ_RW = 4, FZ_TX = 16, FZ_NPX = FZ_RW * FZ_TX;   // 64 pixels per tile = N of the MMA
 constexpr int FZ_NPOS = 16;                                    // low-res positions per strip = K of the MMA
-constexpr int FZ_NSTG = 6, FZ_INFL = 4;                        // strip ring stages / strips in flight per loader thread
+constexpr int FZ_NSTG = 16, FZ_INFL = 4;                       // strip ring slots / strips in flight per loader thread
 constexpr int FZ_EPI_WARPS = 4, FZ_LD_WARPS = 4, FZ_BB_WARPS = 4;
 constexpr int FZ_THREADS = 32 * (FZ_EPI_WARPS + 1 + FZ_LD_WARPS + FZ_BB_WARPS);
 constexpr int FZ_LD_T0 = 32 * (FZ_EPI_WARPS + 1), FZ_BB_T0 = FZ_LD_T0 + 32 * FZ_LD_WARPS;
@@ -218,7 +222,7 @@ struct FzCfg {
 template <int R, int MH>
 __global__ void __launch_bounds__(FZ_THREADS, 1)
 jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const bf16* __restrict__ kc,
-                       bf16* __restrict__ dst, int nx, int ny, int nslab, int total_tiles,
+                       bf16* __restrict__ dst, int nx, int ny, int nslab, int seg, int nseg, int total_units,
                        const bf16* __restrict__ kc_img, const ShareGeom sg) {
   using Cf = FzCfg<R, MH>;
   constexpr int DO = Cf::DO, NLR = Cf::NLR;
@@ -256,21 +260,26 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto tile_coords = [&](int tile, int& x0, int& y0, int& crop, int& c0) {
-    const int xt = tile % nx, rest = tile / nx;
-    const int yt = rest % ny, z = rest / ny;
+  // unit -> column (x tile, crop, channel slab) and the run of y tiles [yt0, yt1)
+  auto unit_coords = [&](int unit, int& x0, int& crop, int& c0, int& yt0, int& yt1) {
+    const int col = unit / nseg, sgi = unit - col * nseg;
+    const int xt = col % nx, z = col / nx;
     x0 = xt * FZ_TX;
-    y0 = yt * FZ_RW;
     crop = z / nslab;
     c0 = (z % nslab) * Cf::CH;
+    yt0 = sgi * seg;
+    yt1 = min(ny, yt0 + seg);
   };
 
   if (warp < FZ_EPI_WARPS) {
     // ---------------- epilogue: lane = channel, 64 pixel columns per channel slab ----------------
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-      int x0, y0, crop, c0;
-      tile_coords(tile, x0, y0, crop, c0);
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x)
+    {
+     int x0, crop, c0, yt0, yt1;
+     unit_coords(unit, x0, crop, c0, yt0, yt1);
+     for (int yt = yt0; yt < yt1; ++yt, ++tl) {
+      const int y0 = yt * FZ_RW;
       const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
       mbar_wait(t_full0 + as * 8, aph);
       tc_fence_after();
@@ -300,39 +309,49 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty0 + as * 8);
+     }
     }
   } else if (warp == FZ_EPI_WARPS) {
     // ---------------- MMA issuer: one MMA per low-res row and channel half ----------------
     // the whole warp runs the loop (warp-uniform control flow); one elected lane issues the MMAs and commits
     {
       constexpr uint32_t idesc = fz_idesc();
-      uint32_t tl = 0, it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-        const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
-        mbar_wait(t_empty0 + as * 8, aph ^ 1);
-        mbar_wait(b_full0 + as * 8, aph);
-        tc_fence_after();
-        const uint32_t bbuf = smem_base + Cf::B_OFF + as * Cf::B_BUF;
-        for (int s = 0; s < NLR; ++s, ++it) {
-          const uint32_t st = it % FZ_NSTG, ph = (it / FZ_NSTG) & 1;
-          mbar_wait(a_full0 + st * 8, ph);
+      uint32_t tl = 0, base_it = 0;                             // base_it: ring fill counter of the unit's first row
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        int x0, crop, c0, yt0, yt1;
+        unit_coords(unit, x0, crop, c0, yt0, yt1);
+        const int ntile = yt1 - yt0;
+        for (int i = 0; i < ntile; ++i, ++tl) {
+          const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+          mbar_wait(t_empty0 + as * 8, aph ^ 1);
+          mbar_wait(b_full0 + as * 8, aph);
           tc_fence_after();
-          const uint32_t a_src = smem_base + Cf::A_OFF + st * Cf::A_STAGE;
-          const uint64_t bdesc = make_sdesc(bbuf + (s >> 2) * Cf::B_QUAD + (s & 3) * 32);
-          if (elect_one()) {
+          const uint32_t bbuf = smem_base + Cf::B_OFF + as * Cf::B_BUF;
+          const bool last = (i == ntile - 1);
+          for (int s = 0; s < NLR; ++s) {
+            const uint32_t g = base_it + (uint32_t)(2 * i + s);     // row s of this tile = row 2i + s of the run
+            const uint32_t st = g % FZ_NSTG, ph = (g / FZ_NSTG) & 1;
+            mbar_wait(a_full0 + st * 8, ph);
+            tc_fence_after();
+            const uint32_t a_src = smem_base + Cf::A_OFF + st * Cf::A_STAGE;
+            const uint64_t bdesc = make_sdesc(bbuf + (s >> 2) * Cf::B_QUAD + (s & 3) * 32);
+            if (elect_one()) {
 #pragma unroll
-            for (int half = 0; half < MH; ++half) {
-              const uint64_t adesc = fz_adesc(a_src + half * 2 * Cf::CHUNK_BYTES, Cf::CHUNK_BYTES);
-              umma_f16(tmem_base + (uint32_t)((as * MH + half) * FZ_NPX), adesc, bdesc, idesc, s > 0 ? 1u : 0u);
+              for (int half = 0; half < MH; ++half) {
+                const uint64_t adesc = fz_adesc(a_src + half * 2 * Cf::CHUNK_BYTES, Cf::CHUNK_BYTES);
+                umma_f16(tmem_base + (uint32_t)((as * MH + half) * FZ_NPX), adesc, bdesc, idesc, s > 0 ? 1u : 0u);
+              }
+              // the two top rows leave the window of the next tile (all rows after the last tile of the run)
+              if (s < FZ_RW / 2 || last) umma_commit(a_empty0 + st * 8);
+              if (s == NLR - 1) {
+                umma_commit(t_full0 + as * 8);
+                umma_commit(b_empty0 + as * 8);
+              }
             }
-            umma_commit(a_empty0 + st * 8);
-            if (s == NLR - 1) {
-              umma_commit(t_full0 + as * 8);
-              umma_commit(b_empty0 + as * 8);
-            }
+            __syncwarp();
           }
-          __syncwarp();
         }
+        base_it += (uint32_t)(NLR + (FZ_RW / 2) * (ntile - 1));
       }
     }
   } else if (warp < FZ_EPI_WARPS + 1 + FZ_LD_WARPS) {
@@ -341,11 +360,12 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
     constexpr int CPR = Cf::CH / 8;                              // 16-byte chunks per position
     constexpr int LPT = FZ_NPOS * CPR / (32 * FZ_LD_WARPS);      // chunks per thread per strip (2 / 4)
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int x0, y0, crop, c0;
-      tile_coords(tile, x0, y0, crop, c0);
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      int x0, crop, c0, yt0, yt1;
+      unit_coords(unit, x0, crop, c0, yt0, yt1);
       const bf16* sc = src + (size_t)crop * h * w * C + c0;
-      const int lx0 = (x0 >> 1) - DO, ly0 = (y0 >> 1) - DO;
+      const int lx0 = (x0 >> 1) - DO, ly0 = ((yt0 * FZ_RW) >> 1) - DO;
+      const int nrows = NLR + (FZ_RW / 2) * (yt1 - yt0 - 1);     // low-res rows of the whole run
       int src_off[LPT];
       uint32_t dst_off[LPT];
 #pragma unroll
@@ -356,7 +376,7 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
         src_off[k] = xx * C + c8 * 8;
         dst_off[k] = (uint32_t)((c8 >> 3) * Cf::CHUNK_BYTES + p * 128 + (((c8 & 7) ^ (p & 7)) << 4));
       }
-      for (int s = 0; s < NLR; ++s, ++it) {
+      for (int s = 0; s < nrows; ++s, ++it) {
         const uint32_t st = it % FZ_NSTG, ph = (it / FZ_NSTG) & 1;
         mbar_wait(a_empty0 + st * 8, ph ^ 1);
         const int yy = min(max(ly0 + s, 0), h - 1);
@@ -377,21 +397,19 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
     fz_fence_proxy_async();
     for (uint32_t j = (it >= FZ_INFL - 1 ? it - (FZ_INFL - 1) : 0); j < it; ++j) mbar_arrive(a_full0 + (j % FZ_NSTG) * 8);
   } else {
-    // ---------------- band builders ----------------
-    // For output pixel n and composite-kernel row dy, the band tile holds, in strip row sr = (y >> 1) - (y0 >> 1) + dy,
-    // a 16-position (32-byte) segment that is zero except for the DC weights K'[dy][0..DC) at positions kk0 .. kk0 + DC.
-    // One unit of work = one (pixel, dy): the DC weights are cut out of the composite row with 256-bit shifts in
-    // registers and the WHOLE segment is written with two 16-byte stores (instead of DC scattered 2-byte stores into a
-    // zero background: the scatter was the largest consumer of shared-memory wavefronts of the kernel).
+    // ---------------- band builders: scatter the composite kernels of the tile's 64 pixels ----------------
     const int bt = tid - FZ_BB_T0;                               // 0..127
-    constexpr int DC = 2 * DO + 1;
-    constexpr int NU = FZ_NPX * DC;                              // (pixel, dy) units per tile
-    constexpr int UPT = (NU + 32 * FZ_BB_WARPS - 1) / (32 * FZ_BB_WARPS);
+    constexpr int DC = 2 * DO + 1, NCH = (DC * DC + 7) / 8;      // 16-byte chunks per composite kernel (11 / 7)
+    constexpr int WPT = (FZ_NPX * NCH + 32 * FZ_BB_WARPS - 1) / (32 * FZ_BB_WARPS);
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-      int x0, y0, crop, c0;
-      tile_coords(tile, x0, y0, crop, c0);
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x)
+    {
+     int x0, crop, c0, yt0, yt1;
+     unit_coords(unit, x0, crop, c0, yt0, yt1);
+     for (int yt = yt0; yt < yt1; ++yt, ++tl) {
+      const int y0 = yt * FZ_RW;
       const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+      uint4 wv[WPT];
       // shared kernels (jbu_share.cuh): interior pixels read the image-level composite kernels at the crop's origin,
       // border-frame pixels the crop's compact frame tensor
       size_t org = 0, cbase = (size_t)crop * H2 * W2;
@@ -399,21 +417,17 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
         org = (size_t)(sg.wins[crop * 4] >> sg.shift) * sg.pitch + (sg.wins[crop * 4 + 1] >> sg.shift);
         cbase = (size_t)crop * border_rows(H2, W2, CSEG_JBU_FB_COMP);
       }
-      uint4 qa[UPT], qb[UPT];
 #pragma unroll
-      for (int k = 0; k < UPT; ++k) {
-        const int u = bt + k * 32 * FZ_BB_WARPS, n = u / DC, dy = u - n * DC;
+      for (int k = 0; k < WPT; ++k) {
+        const int e = bt + k * 32 * FZ_BB_WARPS, n = e / NCH, v = e - n * NCH;
         const int y = y0 + (n >> 4), x = x0 + (n & 15);
-        qa[k] = make_uint4(0, 0, 0, 0);                          // pixels outside the image: zero weights
-        qb[k] = make_uint4(0, 0, 0, 0);
-        if (u < NU && y < H2 && x < W2) {
+        wv[k] = make_uint4(0, 0, 0, 0);                          // pixels outside the image: zero weights
+        if (n < FZ_NPX && y < H2 && x < W2) {
           const bf16* kp;
           if (kc_img == nullptr) kp = kc + (cbase + (size_t)y * W2 + x) * 128;
           else if (border_interior(y, x, H2, W2, CSEG_JBU_FB_COMP)) kp = kc_img + (org + (size_t)y * sg.pitch + x) * 128;
           else kp = kc + (cbase + border_index(y, x, H2, W2, CSEG_JBU_FB_COMP)) * 128;
-          const int ch = (dy * DC) >> 3;                         // 16-byte chunk holding the first weight of this row
-          qa[k] = __ldg(reinterpret_cast<const uint4*>(kp) + ch);
-          if (ch < 15) qb[k] = __ldg(reinterpret_cast<const uint4*>(kp) + ch + 1);
+          wv[k] = __ldg(reinterpret_cast<const uint4*>(kp + v * 8));
         }
       }
       mbar_wait(b_empty0 + as * 8, aph ^ 1);
@@ -423,49 +437,26 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
         asm volatile("bar.sync 2, %0;" ::"n"(32 * FZ_BB_WARPS) : "memory");
       }
 #pragma unroll
-      for (int k = 0; k < UPT; ++k) {
-        const int u = bt + k * 32 * FZ_BB_WARPS, n = u / DC, dy = u - n * DC;
-        if (u >= NU) continue;
+      for (int k = 0; k < WPT; ++k) {
+        const int e = bt + k * 32 * FZ_BB_WARPS, n = e / NCH, v = e - n * NCH;
+        if (n >= FZ_NPX) continue;
         const int r = n >> 4, m = n & 15;
-        const int sr = (r >> 1) + dy, kk0 = m >> 1;              // strip row, first position of the segment
-        // 256-bit window (16 halfwords): drop the (dy * DC) & 7 halfwords in front of the row, keep DC, move to kk0
-        unsigned long long w0 = ((unsigned long long)qa[k].y << 32) | qa[k].x, w1 = ((unsigned long long)qa[k].w << 32) | qa[k].z;
-        unsigned long long w2 = ((unsigned long long)qb[k].y << 32) | qb[k].x, w3 = ((unsigned long long)qb[k].w << 32) | qb[k].z;
-        {
-          const int bits = ((dy * DC) & 7) * 16;                 // < 128
-          if (bits >= 64) { w0 = w1; w1 = w2; w2 = w3; w3 = 0; }
-          const int rs = bits & 63;
-          if (rs) {
-            w0 = (w0 >> rs) | (w1 << (64 - rs));
-            w1 = (w1 >> rs) | (w2 << (64 - rs));
-            w2 = (w2 >> rs) | (w3 << (64 - rs));
-            w3 >>= rs;
-          }
+        const unsigned short* hv = reinterpret_cast<const unsigned short*>(&wv[k]);
+        uint8_t* rowb = bbuf + (n >> 3) * 1024 + (n & 7) * 128;
+        const int sr0 = r >> 1, kk0 = m >> 1;                    // (y >> 1) - (y0 >> 1), (x >> 1) - (x0 >> 1)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int t = v * 8 + q;
+          if (t >= DC * DC) continue;
+          const int dy = (t * 57) >> 9;                          // t / 9 for t < 128 (DC == 9); exact division below otherwise
+          const int dyy = (DC == 9) ? dy : t / DC, dx = t - dyy * DC;
+          const int sr = sr0 + dyy, col = (sr & 3) * 16 + kk0 + dx;
+          *reinterpret_cast<unsigned short*>(rowb + (sr >> 2) * Cf::B_QUAD + ((((col >> 3) ^ (n & 7)) << 4) | ((col & 7) << 1))) = hv[q];
         }
-        // keep DC halfwords (DC = 9: 144 bits; DC = 7: 112 bits)
-        if (DC * 16 >= 128) { w2 &= (DC * 16 > 128) ? ((1ull << ((DC * 16 - 128) & 63)) - 1ull) : 0ull; }
-        else { w1 &= (1ull << ((DC * 16 - 64) & 63)) - 1ull; w2 = 0; }
-        w3 = 0;
-        {
-          const int bits = kk0 * 16;                             // < 128
-          if (bits >= 64) { w3 = w2; w2 = w1; w1 = w0; w0 = 0; }
-          const int ls = bits & 63;
-          if (ls) {
-            w3 = (w3 << ls) | (w2 >> (64 - ls));
-            w2 = (w2 << ls) | (w1 >> (64 - ls));
-            w1 = (w1 << ls) | (w0 >> (64 - ls));
-            w0 <<= ls;
-          }
-        }
-        uint8_t* rowb = bbuf + (sr >> 2) * Cf::B_QUAD + (n >> 3) * 1024 + (n & 7) * 128;
-        const int cch = (sr & 3) * 2;                            // the segment's two 16-byte chunks within the 128-byte row
-        *reinterpret_cast<uint4*>(rowb + ((cch ^ (n & 7)) << 4)) =
-            make_uint4((uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32));
-        *reinterpret_cast<uint4*>(rowb + (((cch + 1) ^ (n & 7)) << 4)) =
-            make_uint4((uint32_t)w2, (uint32_t)(w2 >> 32), (uint32_t)w3, (uint32_t)(w3 >> 32));
       }
       fz_fence_proxy_async();
       mbar_arrive(b_full0 + as * 8);
+     }
     }
   }
   tc_fence_before();
@@ -482,11 +473,27 @@ int launch_apply_kernel(const bf16* src, int n_crops, int h, int w, int C, const
   const int H2 = 2 * h, W2 = 2 * w;
   CSEG_SET_SMEM((jbu_apply_fused_kernel<R, MH>), Cf::SMEM_BYTES);
   const int nx = cdiv(W2, FZ_TX), ny = cdiv(H2, FZ_RW), nslab = C / Cf::CH;
-  const long long total = (long long)nx * ny * n_crops * nslab;
-  CSEG_REQUIRE(total < (1ll << 31), "jbu_apply(bf16): too many tiles");
+  const long long ncols = (long long)nx * n_crops * nslab;
+  CSEG_REQUIRE(ncols * ny < (1ll << 31), "jbu_apply(bf16): too many tiles");
+  // tiles per run: longer runs re-use more source rows (a run of s tiles fetches NLR + 2 (s - 1) strips instead of
+  // NLR s) but leave fewer, coarser units to balance over the SMs.  Cost of a unit in strip-sized L2 transfers: its
+  // strips + 6 per tile (output + composite kernels); pick the run length with the cheapest slowest SM.
+  int seg = 1;
+  {
+    const int sms = sm_count();
+    double best = 1e30;
+    for (int s = 1; s <= std::min(ny, 16); ++s) {
+      const long long units = ncols * cdiv(ny, s);
+      const double cost = (double)cdiv(units, sms) * (Cf::NLR + (FZ_RW / 2) * (s - 1) + 6.0 * s);
+      if (cost < best - 1e-9) { best = cost; seg = s; }
+    }
+    if (const char* e = getenv("CSEG_APPLY_SEG")) seg = std::max(1, std::min(atoi(e), ny));   // A/B measurements
+  }
+  const int nseg = cdiv(ny, seg);
+  const long long total = ncols * nseg;
   const int grid = (int)std::min<long long>(total, sm_count());
   cseg_launch(jbu_apply_fused_kernel<R, MH>, dim3(grid), dim3(FZ_THREADS), Cf::SMEM_BYTES, st, src, h, w, C, kc,
-              dst, nx, ny, nslab, (int)total, kc_img, sg);
+              dst, nx, ny, nslab, seg, nseg, (int)total, kc_img, sg);
   CSEG_LAUNCH_CHECK("jbu_apply_fused");
   return 0;
 }

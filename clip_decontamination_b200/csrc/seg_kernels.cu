@@ -341,6 +341,36 @@ __global__ void __launch_bounds__(256) iou_hist_kernel(const uint8_t* __restrict
     if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// N4 output side: colourised mask and confidence heat-map (segmentor.py:513-531,568-608) as BGR images
+// ready for cv2.imwrite.  lut: uint8 [n_lut][3] (palette rows for the mask; the 256-entry colour map for the heat-map).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colorize_kernel(const uint8_t* __restrict__ labels, long long n,
+                                                       const uint8_t* __restrict__ lut, int n_lut,
+                                                       uint8_t* __restrict__ out) {
+  pdl_grid_sync();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int l = min((int)labels[i], n_lut - 1);          // np.clip(mask, 0, len(palette) - 1)
+    out[3 * i + 0] = lut[3 * l + 0];
+    out[3 * i + 1] = lut[3 * l + 1];
+    out[3 * i + 2] = lut[3 * l + 2];
+  }
+}
+__global__ void __launch_bounds__(256) heatmap_kernel(const float* __restrict__ probs, int K, long long n,
+                                                      const uint8_t* __restrict__ lut, uint8_t* __restrict__ out) {
+  pdl_grid_sync();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float c = -INFINITY;
+    for (int k = 0; k < K; ++k) c = fmaxf(c, probs[(size_t)k * n + i]);     // seg_logits.max(dim=0)
+    if (!(c == c)) c = 0.f;                                                  // nan_to_num
+    c = fminf(fmaxf(c, 0.f), 1.f);
+    const int g = (int)(c * 255.0f);                                         // astype(uint8) truncates
+    out[3 * i + 0] = lut[3 * g + 0];
+    out[3 * i + 1] = lut[3 * g + 1];
+    out[3 * i + 2] = lut[3 * g + 2];
+  }
+}
+
 }  // namespace
 
 template <typename T>
@@ -397,6 +427,22 @@ int cseg_accum_argmax(const float* crop_logits, int n_crops, int Q, int lh, int 
     cseg_launch(accum_argmax_kernel<32, 2>, dim3(cdiv(out_w, 64), cdiv(out_h, 8)), dim3(256), smem, (cudaStream_t)stream, p);
   }
   CSEG_LAUNCH_CHECK("accum_argmax");
+  return 0;
+}
+
+int cseg_colorize(const uint8_t* labels, long long n, const uint8_t* lut, int n_lut, uint8_t* out_bgr, void* stream) {
+  CSEG_REQUIRE(labels && lut && out_bgr && n > 0 && n_lut > 0, "colorize: bad arguments");
+  const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 16);
+  cseg_launch(colorize_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, labels, n, lut, n_lut, out_bgr);
+  CSEG_LAUNCH_CHECK("colorize");
+  return 0;
+}
+
+int cseg_heatmap(const float* probs, int K, long long n, const uint8_t* lut256, uint8_t* out_bgr, void* stream) {
+  CSEG_REQUIRE(probs && lut256 && out_bgr && n > 0 && K > 0, "heatmap: bad arguments");
+  const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 16);
+  cseg_launch(heatmap_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, probs, K, n, lut256, out_bgr);
+  CSEG_LAUNCH_CHECK("heatmap");
   return 0;
 }
 

@@ -757,7 +757,31 @@ class SegEngine:
                 self.segment(self._image_of(kind, xd), ori_shape, labels=labels_out.view(B * oh, ow))
                 return labels_out
             st = self.graph(H, W, B, kind, ori_shape)
-            if xs is not None:                           # H2D (or D2D) straight into the static input, image by image
+            on_host = not (xs[0] if xs is not None else x).is_cuda
+            if on_host:
+                # double-buffered upload on a copy stream: the H2D of this batch overlaps the replay of the previous one
+                # (the caller's pinned buffers must stay valid until the copy has run, as with any non_blocking copy)
+                if 'stage' not in st:
+                    st['stage'] = [torch.empty_like(st['in']) for _ in range(2)]
+                    st['copy_stream'] = torch.cuda.Stream(self.device)
+                    st['ready'] = [torch.cuda.Event() for _ in range(2)]
+                    st['free'] = [torch.cuda.Event() for _ in range(2)]
+                    st['k'] = 0
+                k = st['k'] = st['k'] ^ 1
+                cur = torch.cuda.current_stream(self.device)
+                cs = st['copy_stream']
+                cs.wait_event(st['free'][k])             # staging[k] was last read two calls ago
+                with torch.cuda.stream(cs):
+                    if xs is not None:
+                        for i, t in enumerate(xs):
+                            st['stage'][k][i].copy_(t, non_blocking=True)
+                    else:
+                        st['stage'][k].copy_(x, non_blocking=True)
+                    st['ready'][k].record(cs)
+                cur.wait_event(st['ready'][k])
+                st['in'].copy_(st['stage'][k], non_blocking=True)
+                st['free'][k].record(cur)
+            elif xs is not None:                         # device inputs: D2D straight into the static input
                 for i, t in enumerate(xs):
                     st['in'][i].copy_(t, non_blocking=True)
             else:

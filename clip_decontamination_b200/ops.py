@@ -301,3 +301,22 @@ def iou_hist(pred, label, K, hist, ignore_index=255):
     assert pred.dtype == torch.uint8 and label.dtype == torch.uint8 and hist.dtype == torch.int64
     check(lib.cseg_iou_hist(_ptr(pred), _ptr(label), pred.numel(), K, ignore_index, _ptr(hist), _stream()))
     return hist
+
+
+def colorize(labels: torch.Tensor, palette: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint8 labels [H,W] + uint8 palette [n,3] -> uint8 image [H,W,3] (palette rows in the order to be written)."""
+    assert labels.dtype == torch.uint8 and palette.dtype == torch.uint8 and palette.shape[1] == 3
+    if out is None:
+        out = torch.empty(tuple(labels.shape) + (3,), dtype=torch.uint8, device=labels.device)
+    check(lib.cseg_colorize(_ptr(labels), labels.numel(), _ptr(palette), palette.shape[0], _ptr(out), _stream()))
+    return out
+
+
+def heatmap(probs: torch.Tensor, lut256: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 probabilities [K,H,W] + uint8 colour map [256,3] -> uint8 image [H,W,3] of the per-pixel max probability."""
+    assert probs.dtype == torch.float32 and lut256.dtype == torch.uint8 and tuple(lut256.shape) == (256, 3)
+    K, H, W = probs.shape
+    if out is None:
+        out = torch.empty((H, W, 3), dtype=torch.uint8, device=probs.device)
+    check(lib.cseg_heatmap(_ptr(probs), K, H * W, _ptr(lut256), _ptr(out), _stream()))
+    return out

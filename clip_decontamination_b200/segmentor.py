@@ -388,28 +388,42 @@ class SegmentorEx(BaseSegmentor):
     def compute_padsize(self, H: int, W: int, patch_size: int):
         return _compute_padsize(H, W, patch_size)
 
-    # ---- optional PNG dumps (segmentor.py:501-531,568-608); host-side, off the hot path ---------
+    # ---- optional PNG dumps (segmentor.py:501-531,568-608): colourised on the GPU, one D2H copy + cv2.imwrite -----
+    def _palette_bgr(self):
+        """_generate_palette (segmentor.py:568-579), rows flipped to BGR for cv2.imwrite (:516)."""
+        if getattr(self, '_pal', None) is None:
+            import colorsys
+            n = int(self.num_classes)
+            pal = []
+            for idx in range(n):
+                r, g, b = colorsys.hsv_to_rgb((idx / max(1, n)) % 1.0, 0.75, 1.0 if idx != self.bg_idx else 0.2)
+                pal.append([int(b * 255), int(g * 255), int(r * 255)])
+            self._pal = torch.tensor(pal, dtype=torch.uint8, device=self._device)
+        return self._pal
+
+    def _jet_bgr(self):
+        """cv2.COLORMAP_JET as a 256-entry BGR table (segmentor.py:601-603: the RGB conversion there is undone by the
+        [:, :, ::-1] at :527, so the file holds cv2's own BGR colours)."""
+        if getattr(self, '_jet', None) is None:
+            import cv2
+            lut = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(256, 1), cv2.COLORMAP_JET).reshape(256, 3)
+            self._jet = torch.from_numpy(np.ascontiguousarray(lut)).to(self._device)
+        return self._jet
+
     def _dump(self, i, sample, labels_u8, probs):
-        import colorsys
         import cv2
+        from . import ops
         meta = getattr(sample, 'metainfo', {}) or {}
         stem = next((os.path.splitext(os.path.basename(meta[k]))[0] for k in
                      ('img_path', 'ori_path', 'filename', 'ori_filename') if meta.get(k)), f'sample_{i}')
         if self.result_dir:
             os.makedirs(self.result_dir, exist_ok=True)
-            n = int(self.num_classes)
-            pal = []
-            for idx in range(n):
-                r, g, b = colorsys.hsv_to_rgb((idx / max(1, n)) % 1.0, 0.75, 1.0 if idx != self.bg_idx else 0.2)
-                pal.append([int(r * 255), int(g * 255), int(b * 255)])
-            pal = np.array(pal, dtype=np.uint8)
-            mask = labels_u8.cpu().numpy().astype(np.int32)
-            cv2.imwrite(os.path.join(self.result_dir, f'{stem}.png'), pal[np.clip(mask, 0, n - 1)][:, :, ::-1])
+            img = ops.colorize(labels_u8.contiguous(), self._palette_bgr())
+            cv2.imwrite(os.path.join(self.result_dir, f'{stem}.png'), img.cpu().numpy())
         if self.heatmap_dir and probs is not None:
             os.makedirs(self.heatmap_dir, exist_ok=True)
-            conf = np.clip(np.nan_to_num(probs.max(dim=0)[0].cpu().numpy(), nan=0.0), 0.0, 1.0)
-            heat = cv2.applyColorMap((conf * 255.0).astype(np.uint8), cv2.COLORMAP_JET)
-            cv2.imwrite(os.path.join(self.heatmap_dir, f'{stem}.png'), heat)
+            img = ops.heatmap(probs.contiguous(), self._jet_bgr())
+            cv2.imwrite(os.path.join(self.heatmap_dir, f'{stem}.png'), img.cpu().numpy())
 
     # mmseg abstract methods (unused, as in the reference segmentor.py:548-566)
     def _forward(self, *a, **k):

@@ -266,6 +266,13 @@ CSEG_API int cseg_accum_argmax(const float* crop_logits, int n_crops, int Q, int
                       float prob_thd, int bg_idx, uint8_t* labels, float* probs, float* avg_logits,
                       void* stream);
 
+/* ---- N4 output side: segmentor.py:513-531,568-608 ---------------------------------------------------------
+ * colourised mask: out_bgr[i] = lut[min(labels[i], n_lut-1)] (lut uint8 [n_lut][3], rows already in the channel order
+ * to be written); confidence heat-map: out_bgr[i] = lut256[uint8(clip(nan_to_num(max_k probs[k][i]), 0, 1) * 255)]
+ * (lut256 = the 256-entry colour map, e.g. cv2.COLORMAP_JET).  Both write uint8 [n][3] images ready for cv2.imwrite. */
+CSEG_API int cseg_colorize(const uint8_t* labels, long long n, const uint8_t* lut, int n_lut, uint8_t* out_bgr, void* stream);
+CSEG_API int cseg_heatmap(const float* probs, int K, long long n, const uint8_t* lut256, uint8_t* out_bgr, void* stream);
+
 /* ---- K17: mmseg IoUMetric.intersect_and_union (mmsegmentation 1.2.2, external) -----------------
  * hist int64 [3][K] += {intersect, pred, label} pixel counts; label == ignore_index skipped. */
 CSEG_API int cseg_iou_hist(const uint8_t* pred, const uint8_t* label, long long n, int K, int ignore_index,

@@ -505,3 +505,28 @@ def test_fixup_norm_sim(ops, dtype, C, Q):
     ops.fixup_norm_sim(y.cuda(), W.cuda(), n, hw, C, b.cuda(), 0.1, text.cuda(), lg, cb.cuda(), scratch)
     tol = 2e-5 if dtype == torch.float32 else 3e-3
     assert (lg.cpu() - ref).abs().max().item() < tol
+
+
+def test_colorize_and_heatmap(ops):
+    """N4 output side against the reference's numpy / cv2 arithmetic (segmentor.py:568-608)."""
+    import colorsys
+    import cv2
+    K, H, W, bg = 7, 50, 70, 2
+    labels = torch.randint(0, K + 2, (H, W), generator=_g(1)).to(torch.uint8)        # includes out-of-range labels
+    pal = []
+    for idx in range(K):
+        r, g, b = colorsys.hsv_to_rgb((idx / max(1, K)) % 1.0, 0.75, 1.0 if idx != bg else 0.2)
+        pal.append([int(r * 255), int(g * 255), int(b * 255)])
+    pal = np.array(pal, dtype=np.uint8)
+    ref = pal[np.clip(labels.numpy().astype(np.int32), 0, K - 1)][:, :, ::-1]         # RGB palette, written as BGR
+    out = ops.colorize(labels.cuda(), torch.from_numpy(np.ascontiguousarray(pal[:, ::-1])).cuda())
+    assert np.array_equal(out.cpu().numpy(), ref)
+    probs = torch.rand(K, H, W, generator=_g(2))
+    probs[0, 0, 0] = float('nan')
+    conf = np.clip(np.nan_to_num(probs.max(dim=0)[0].numpy().astype(np.float32), nan=0.0), 0.0, 1.0)
+    heat = cv2.applyColorMap((conf * 255.0).astype(np.uint8), cv2.COLORMAP_JET)
+    lut = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(256, 1), cv2.COLORMAP_JET).reshape(256, 3)
+    out = ops.heatmap(probs.cuda(), torch.from_numpy(np.ascontiguousarray(lut)).cuda())
+    got = out.cpu().numpy()
+    # torch.max propagates NaN exactly like the reference's seg_logits.max(dim=0); everything else must be identical
+    assert np.array_equal(got[1:], heat[1:]) and np.array_equal(got[0, 1:], heat[0, 1:])
