@@ -45,23 +45,6 @@ __device__ __forceinline__ float at_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x for x <= 0 on the FMA pipe (the MUFU/XU pipe is the bottleneck of the softmax: ncu shows it 76 % busy with one
-// MUFU.EX2 per element plus the F2FP packs): round to the nearest integer with the 1.5 * 2^23 trick, degree-3 minimax
-// polynomial of 2^f on [-0.5, 0.5] (max relative error 1.6e-4, 25x below the bf16 rounding of P), exponent added
-// through the integer bits.  Half of the elements take this path, half the MUFU.
-__device__ __forceinline__ float at_ex2_poly(float x) {
-  x = fmaxf(x, -125.f);
-  const float t = x + 12582912.f;
-  const float f = x - (t - 12582912.f);
-  float p = fmaf(f, 0.05360212f, 0.24237292f);
-  p = fmaf(p, f, 0.69350237f);
-  p = fmaf(p, f, 0.99994814f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-// two non-negative finite floats -> bf16x2 with integer rounding (ALU pipe instead of F2FP)
-__device__ __forceinline__ uint32_t at_pack_pos(float a, float b) {
-  return __byte_perm(__float_as_uint(a) + 0x8000u, __float_as_uint(b) + 0x8000u, 0x7632);
-}
 __device__ __forceinline__ uint32_t at_pack(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -257,16 +240,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           float ev[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const float x = fmaf(__uint_as_float(r[e]), scale_log2e, -msc);
-            const float v = (e & 1) ? at_ex2_poly(x) : at_ex2(x);
-            ev[e] = (c + e < L) ? v : 0.f;
+            ev[e] = (c + e < L) ? at_ex2(fmaf(__uint_as_float(r[e]), scale_log2e, -msc)) : 0.f;
             sum += ev[e];
           }
           uint8_t* pb = prow + (c >> 6) * AT_P_BLK;
           const int j = (c & 63) >> 3;                                   // 16-byte chunk within the 128-byte row (even)
           uint4 w0, w1;
-          w0.x = at_pack_pos(ev[0], ev[1]);   w0.y = at_pack_pos(ev[2], ev[3]);   w0.z = at_pack_pos(ev[4], ev[5]);   w0.w = at_pack_pos(ev[6], ev[7]);
-          w1.x = at_pack_pos(ev[8], ev[9]);   w1.y = at_pack_pos(ev[10], ev[11]); w1.z = at_pack_pos(ev[12], ev[13]); w1.w = at_pack_pos(ev[14], ev[15]);
+          w0.x = at_pack(ev[0], ev[1]);   w0.y = at_pack(ev[2], ev[3]);   w0.z = at_pack(ev[4], ev[5]);   w0.w = at_pack(ev[6], ev[7]);
+          w1.x = at_pack(ev[8], ev[9]);   w1.y = at_pack(ev[10], ev[11]); w1.z = at_pack(ev[12], ev[13]); w1.w = at_pack(ev[14], ev[15]);
           *reinterpret_cast<uint4*>(pb + ((j ^ (row & 7)) << 4)) = w0;
           *reinterpret_cast<uint4*>(pb + (((j + 1) ^ (row & 7)) << 4)) = w1;
         }

@@ -43,10 +43,13 @@ extern std::atomic<long long> g_cseg_launches;
 // path, so launch sequences can be captured into CUDA graphs)
 #define CSEG_SET_SMEM(kernel, bytes)                                                                      \
   do {                                                                                                    \
-    static int cur_ = 0;                                                                                  \
-    if ((int)(bytes) > cur_) {                                                                            \
+    static int cur_[16] = {0};                       /* per device: the attribute is per (function, device) */ \
+    int dev_ = 0;                                                                                         \
+    cudaGetDevice(&dev_);                                                                                 \
+    dev_ &= 15;                                                                                           \
+    if ((int)(bytes) > cur_[dev_]) {                                                                      \
       CSEG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
-      cur_ = (int)(bytes);                                                                                \
+      cur_[dev_] = (int)(bytes);                                                                          \
     }                                                                                                     \
   } while (0)
 
@@ -165,12 +168,13 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }

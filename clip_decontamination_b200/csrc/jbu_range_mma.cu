@@ -177,19 +177,29 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
         mrun[h] = mnew;
         if (tig == 0) mrw[(g + h * 8) * MROWS + i] = mnew;
       }
+      // Rows g (e < 2) only reach positions [g, g + D) of the 8 NB-blocks, rows g + 8 (e >= 2) positions [g + 8, g + 8 + D):
+      // the last block can never hold a tap of the top half, the first block never one of the bottom half.  Skipping
+      // those pairs at compile time saves a quarter of the MUFU.EX2 / F2FP work -- ncu shows the XU pipe saturated here.
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (jj[nb][e] >= 0) {
-            const int h = e >> 1;
-            float ex;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(S[nb][e] - mrun[h]));
-            const float w = ex * (gy * gx[nb][e]);
-            se[h] += ex;
-            sg[h] += w;
-            sti[(g + h * 8) * (LDK + SPAD) + jj[nb][e]] = __float2half_rn(w);
-          }
+        for (int hh = 0; hh < 2; ++hh) {
+          if ((hh == 0 && nb * 8 >= 8 + D - 1) || (hh == 1 && nb * 8 + 8 <= 8)) continue;   // compile-time
+          const int e0 = hh * 2;
+          float ex0, ex1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex0) : "f"(S[nb][e0] - mrun[hh]));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex1) : "f"(S[nb][e0 + 1] - mrun[hh]));
+          const bool v0 = jj[nb][e0] >= 0, v1 = jj[nb][e0 + 1] >= 0;
+          ex0 = v0 ? ex0 : 0.f;
+          ex1 = v1 ? ex1 : 0.f;
+          const float w0 = ex0 * (gy * gx[nb][e0]), w1 = ex1 * (gy * gx[nb][e0 + 1]);
+          se[hh] += ex0 + ex1;
+          sg[hh] += w0 + w1;
+          const __half2 wp = __floats2half2_rn(w0, w1);                  // one F2FP for the pair
+          __half* srow = sti + (g + hh * 8) * (LDK + SPAD);
+          if (v0) srow[jj[nb][e0]] = __low2half(wp);
+          if (v1) srow[jj[nb][e0 + 1]] = __high2half(wp);
+        }
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {

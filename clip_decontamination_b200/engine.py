@@ -30,6 +30,18 @@ def _round_up(v: int, m: int) -> int:
     return (v + m - 1) // m * m
 
 
+def _on_device(fn):
+    """Run an engine entry point with the engine's device current: kernels launch on the current device and
+    ops._stream() takes its current stream, whatever device the caller had selected (SegmentorEx(device='cuda:1'))."""
+    import functools
+
+    @functools.wraps(fn)
+    def inner(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return inner
+
+
 class Workspace:
     """Grow-only named device buffers (no allocation on the steady-state path).
 
@@ -147,6 +159,7 @@ class VisualEngine:
             self._pos_cache[key] = torch.cat([self.pos[:1], pp], 0).contiguous()
         return self._pos_cache[key]
 
+    @_on_device
     def encode(self, img: torch.Tensor, windows: torch.Tensor, crop_h: int, crop_w: int, pad_top: int = 0,
                pad_left: int = 0, model_type: str = 'Experimental', ignore_residual: bool = True,
                sim_cfg: Optional[dict] = None, outlier_cfg: Optional[dict] = None,
@@ -369,6 +382,7 @@ class JBUEngine:
             return False
         return len(wl) * crop_h * crop_w >= 2 * n_canvas_px
 
+    @_on_device
     def prepare_shared(self, img, crop_h: int, crop_w: int, gh: int, gw: int) -> dict:
         """Image-level tensors of the shared stages for the whole canvas of `img` (one region = all stacked images; the
         seams between images lie inside every crop's border frame, which is computed per crop)."""
@@ -401,6 +415,7 @@ class JBUEngine:
             out[si] = dict(guid=guid, proj=proj, kern=kern, kc=kc, shift=shift, pitch=IW)
         return out
 
+    @_on_device
     def upsample(self, feats: torch.Tensor, gh: int, gw: int, img: torch.Tensor, windows: torch.Tensor,
                  crop_h: int, crop_w: int, pad_top: int = 0, pad_left: int = 0,
                  taps: Optional[dict] = None, final_conv: bool = True, shared: Optional[dict] = None) -> torch.Tensor:
@@ -495,6 +510,7 @@ class JBUEngine:
             self._basis[key] = st
         return st
 
+    @_on_device
     def basis_logits(self, feats: torch.Tensor, gh: int, gw: int, img: torch.Tensor, windows: torch.Tensor,
                      crop_h: int, crop_w: int, pad_top: int, pad_left: int, text: torch.Tensor,
                      logits: torch.Tensor, cls_bias: Optional[torch.Tensor] = None,
@@ -570,6 +586,7 @@ class SegEngine:
         assert im.H % batch == 0
         return im, batch
 
+    @_on_device
     def crop_logits(self, img, taps: Optional[dict] = None, batch: int = 1):
         """Per-crop cosine logits (forward_feature, segmentor.py:286-392) for every window of `img` (an ops.Image, or
         a normalised fp32 [3,H,W] tensor on the device; with batch = B > 1 the tensor holds B images stacked to

@@ -18,6 +18,8 @@ STD_RGB = (68.501, 66.632, 70.323)
 
 
 def _stream():
+    # the current stream of the CURRENT device: the engines wrap their entry points in torch.cuda.device(engine.device),
+    # so a model built with device='cuda:1' launches on cuda:1 whatever the caller's current device is
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

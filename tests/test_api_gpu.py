@@ -184,3 +184,38 @@ def test_build_from_reference_base_config_and_test_step(gold, tmp_path, monkeypa
     ds = [SegDataSample(dict(ori_shape=(600, 520), img_shape=(H, W)))]
     out = model.test_step(dict(inputs=batch['inputs'][:1], data_samples=ds))
     assert out[0].pred_sem_seg.data.shape == (1, 600, 520)
+
+
+def test_forward_feature_api_matches_oracle(gold):
+    """SegmentorEx.forward_feature (segmentor.py:286-392) as an API: one crop -> cosine logits [1,Q,h,w] at the crop
+    size and at a requested logit_size, against the oracle's forward_feature on the same crop."""
+    seg, g = _segmentor(gold, **EXTRAS)
+    cfg = get_model_config('ViT-tiny-16')
+    v = cfg['vision_cfg']
+    vis = {k[len('visual.'):]: t for k, t in synthetic_clip_state_dict(cfg, 0, text_tower=False).items()
+           if k.startswith('visual.')}
+    orc = O.SegOracle(vis, torch.from_numpy(g['query_features']), g['query_idx'].tolist(), layers=v['layers'],
+                      heads=v['heads'], patch=16, prob_thd=0.1, bg_idx=5, global_debias_factor=0.2,
+                      upsampler=('jbu_one', synthetic_jbu_state_dict('jbu_one', 64, 1)), sim_cfg={}, outlier_cfg={'top_k': 30})
+    x = torch.from_numpy(synth.preprocess(synth.voronoi_scene(224, 224, 13)))[None]
+    with torch.no_grad():
+        ref = orc.forward_feature(x)
+        ref_small = orc.forward_feature(x, logit_size=(100, 120))
+    out = seg.forward_feature(x.cuda())
+    assert out.shape == ref.shape and (out.cpu() - ref).abs().max().item() < 1e-4
+    out2 = seg.forward_feature(x.cuda(), logit_size=(100, 120))
+    assert out2.shape == ref_small.shape and (out2.cpu() - ref_small).abs().max().item() < 1e-4
+    assert seg.engine.crop == 224                                    # the whole-image switch is restored
+
+
+def test_model_on_second_device_if_present(gold):
+    """device= is honoured end to end: a model built for cuda:1 runs there while cuda:0 is the current device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    torch.cuda.set_device(0)
+    seg, g = _segmentor(gold, device=torch.device('cuda', 1), **EXTRAS)
+    H, W, seed = int(g['meta'][0]), int(g['meta'][1]), int(g['meta'][4])
+    u8 = torch.from_numpy(synth.voronoi_scene(H, W, seed))
+    lab = seg.predict_u8(u8)
+    assert lab.device.index == 1 and (lab.cpu().numpy() == g['labels']).mean() >= 0.999
+    assert torch.cuda.current_device() == 0
