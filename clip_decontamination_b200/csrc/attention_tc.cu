@@ -40,6 +40,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float at_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -215,15 +225,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(s_full + sb * 8, sph);
         tc_fence_after();
         const uint32_t ts = tlane + sb * AT_S_COLS;
-        // pass 1: row maximum over this warp's key half, then across the two halves
+        // pass 1: row maximum over this warp's key half, then across the two halves.  The TMEM load of the next 16
+        // columns is in flight while the current 16 are reduced (the softmax warps were latency bound: ncu shows
+        // long-scoreboard stalls on a tcgen05.ld + wait per chunk with only two warps per scheduler)
         float m = -INFINITY;
-#pragma unroll 1
-        for (int c = c_begin; c < c_end; c += 16) {
-          uint32_t r[16];
-          tmem_ld16(ts + c, r);
+        {
+          uint32_t ra[16], rb[16];
+          auto red = [&](const uint32_t (&r)[16], int c) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (c + e < L) m = fmaxf(m, __uint_as_float(r[e]));
+            for (int e = 0; e < 16; ++e)
+              if (c + e < L) m = fmaxf(m, __uint_as_float(r[e]));
+          };
+          tmem_ld16_nowait(ts + c_begin, ra);
+#pragma unroll 1
+          for (int c = c_begin; c < c_end; c += 32) {
+            tmem_wait_ld();
+            if (c + 16 < c_end) tmem_ld16_nowait(ts + c + 16, rb);
+            red(ra, c);
+            if (c + 16 < c_end) {
+              tmem_wait_ld();
+              if (c + 32 < c_end) tmem_ld16_nowait(ts + c + 32, ra);
+              red(rb, c + 16);
+            }
+          }
         }
         smax[hh * 128 + row] = m;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * AT_SMW) : "memory");
@@ -233,23 +257,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // pass 2: exponentials -> bf16 P in the K-major SWIZZLE_128B layout, row sum in fp32
         const float msc = m * scale_log2e;
         float sum = 0.f;
-#pragma unroll 1
-        for (int c = c_begin; c < c_end; c += 16) {
-          uint32_t r[16];
-          tmem_ld16(ts + c, r);
-          float ev[16];
+        {
+          uint32_t ra[16], rb[16];
+          auto expo = [&](const uint32_t (&r)[16], int c) {
+            float ev[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            ev[e] = (c + e < L) ? at_ex2(fmaf(__uint_as_float(r[e]), scale_log2e, -msc)) : 0.f;
-            sum += ev[e];
+            for (int e = 0; e < 16; ++e) {
+              ev[e] = (c + e < L) ? at_ex2(fmaf(__uint_as_float(r[e]), scale_log2e, -msc)) : 0.f;
+              sum += ev[e];
+            }
+            uint8_t* pb = prow + (c >> 6) * AT_P_BLK;
+            const int j = (c & 63) >> 3;                                   // 16-byte chunk within the 128-byte row (even)
+            uint4 w0, w1;
+            w0.x = at_pack(ev[0], ev[1]);   w0.y = at_pack(ev[2], ev[3]);   w0.z = at_pack(ev[4], ev[5]);   w0.w = at_pack(ev[6], ev[7]);
+            w1.x = at_pack(ev[8], ev[9]);   w1.y = at_pack(ev[10], ev[11]); w1.z = at_pack(ev[12], ev[13]); w1.w = at_pack(ev[14], ev[15]);
+            *reinterpret_cast<uint4*>(pb + ((j ^ (row & 7)) << 4)) = w0;
+            *reinterpret_cast<uint4*>(pb + (((j + 1) ^ (row & 7)) << 4)) = w1;
+          };
+          tmem_ld16_nowait(ts + c_begin, ra);
+#pragma unroll 1
+          for (int c = c_begin; c < c_end; c += 32) {
+            tmem_wait_ld();
+            if (c + 16 < c_end) tmem_ld16_nowait(ts + c + 16, rb);
+            expo(ra, c);
+            if (c + 16 < c_end) {
+              tmem_wait_ld();
+              if (c + 32 < c_end) tmem_ld16_nowait(ts + c + 32, ra);
+              expo(rb, c + 16);
+            }
           }
-          uint8_t* pb = prow + (c >> 6) * AT_P_BLK;
-          const int j = (c & 63) >> 3;                                   // 16-byte chunk within the 128-byte row (even)
-          uint4 w0, w1;
-          w0.x = at_pack(ev[0], ev[1]);   w0.y = at_pack(ev[2], ev[3]);   w0.z = at_pack(ev[4], ev[5]);   w0.w = at_pack(ev[6], ev[7]);
-          w1.x = at_pack(ev[8], ev[9]);   w1.y = at_pack(ev[10], ev[11]); w1.z = at_pack(ev[12], ev[13]); w1.w = at_pack(ev[14], ev[15]);
-          *reinterpret_cast<uint4*>(pb + ((j ^ (row & 7)) << 4)) = w0;
-          *reinterpret_cast<uint4*>(pb + (((j + 1) ^ (row & 7)) << 4)) = w1;
         }
         ssum[(qi & 1) * 256 + hh * 128 + row] = sum;
         tc_fence_before();

@@ -181,8 +181,8 @@ __device__ __forceinline__ uint8_t post_process(const AccumParams& p, const int*
 // binned once per CTA (in forward_slide order, so the fp32 sums keep the reference's order): a pixel then visits
 // <= 4..9 candidates instead of all n_crops.  When the crop logits are at crop resolution and no final resize is needed
 // (the JBU path) the PX pixels of a thread read each crop's logits with one 16-byte load per query.
-template <int QT, int PX>
-__global__ void __launch_bounds__(256, (QT <= 8) ? 3 : 2) accum_argmax_kernel(const AccumParams p) {
+template <int QT, int PX, bool DIRECT>
+__global__ void __launch_bounds__(256, 2) accum_argmax_kernel(const AccumParams p) {
   pdl_grid_sync();
   extern __shared__ int4 s_wins[];                              // [n_crops] candidate windows (compacted)
   int* s_cand = reinterpret_cast<int*>(s_wins + p.n_crops);     // [n_crops] their crop indices
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256, (QT <= 8) ? 3 : 2) accum_argmax_kernel(co
   __shared__ int s_qidx[QT];
   const int tid = threadIdx.x;
   const int ox0 = blockIdx.x * (32 * PX), oy0 = blockIdx.y * 8;
-  const bool direct = (p.out_h == p.H && p.out_w == p.W);
+  constexpr bool direct = DIRECT;                              // output size == canvas size (no final resize)
   if (tid < QT) s_qidx[tid] = tid < p.Q ? p.query_idx[tid] : -1;
   if (tid < 32) {
     // canvas rectangle the tile depends on
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256, (QT <= 8) ? 3 : 2) accum_argmax_kernel(co
       int4 w = make_int4(0, 0, 0, 0);
       bool hit = false;
       if (i < p.n_crops) {
-        w = make_int4(p.windows[4 * i], p.windows[4 * i + 1], p.windows[4 * i + 2], p.windows[4 * i + 3]);
+        w = __ldg(reinterpret_cast<const int4*>(p.windows) + i);
         hit = (w.x <= cy1 && w.x + w.z > cy0 && w.y <= cx1 && w.y + w.w > cx0);
       }
       const unsigned mask = __ballot_sync(0xffffffffu, hit);
@@ -245,16 +245,22 @@ __global__ void __launch_bounds__(256, (QT <= 8) ? 3 : 2) accum_argmax_kernel(co
       if (lx0 + PX <= 0 || lx0 >= w.w) continue;
       const int cr = s_cand[ci];
       const int cy = ly + p.pad_top, cx0 = lx0 + p.pad_left;
-      if (PX == 4 && same_res && lx0 >= 0 && lx0 + PX <= w.w && ((cx0 | p.lw) & 3) == 0) {
+      if (PX >= 2 && same_res && lx0 >= 0 && lx0 + PX <= w.w && ((cx0 | p.lw) & (PX - 1)) == 0) {
         const float* base = p.crop_logits + (size_t)cr * p.Q * p.lh * p.lw + (size_t)cy * p.lw + cx0;
 #pragma unroll
         for (int q = 0; q < QT; ++q)
           if (q < p.Q) {
-            const float4 v4 = *reinterpret_cast<const float4*>(base + (size_t)q * p.lh * p.lw);
-            acc[0][q] += v4.x;
-            if (PX > 1) acc[1 % PX][q] += v4.y;
-            if (PX > 2) acc[2 % PX][q] += v4.z;
-            if (PX > 3) acc[3 % PX][q] += v4.w;
+            if (PX == 4) {
+              const float4 v4 = *reinterpret_cast<const float4*>(base + (size_t)q * p.lh * p.lw);
+              acc[0][q] += v4.x;
+              acc[1 % PX][q] += v4.y;
+              acc[2 % PX][q] += v4.z;
+              acc[3 % PX][q] += v4.w;
+            } else {
+              const float2 v2 = *reinterpret_cast<const float2*>(base + (size_t)q * p.lh * p.lw);
+              acc[0][q] += v2.x;
+              acc[1 % PX][q] += v2.y;
+            }
           }
 #pragma unroll
         for (int e = 0; e < PX; ++e) ++cnt[e];
@@ -312,6 +318,8 @@ __global__ void __launch_bounds__(256, (QT <= 8) ? 3 : 2) accum_argmax_kernel(co
   if (PX == 4 && oxb + 4 <= p.out_w && (((size_t)oy * p.out_w + oxb) & 3) == 0 && ((uintptr_t)p.labels & 3) == 0) {
     *reinterpret_cast<uint32_t*>(lrow) = (uint32_t)lab[0] | ((uint32_t)lab[1 % PX] << 8) | ((uint32_t)lab[2 % PX] << 16) |
                                          ((uint32_t)lab[3 % PX] << 24);
+  } else if (PX == 2 && oxb + 2 <= p.out_w && (((size_t)oy * p.out_w + oxb) & 1) == 0 && ((uintptr_t)p.labels & 1) == 0) {
+    *reinterpret_cast<unsigned short*>(lrow) = (unsigned short)((uint32_t)lab[0] | ((uint32_t)lab[1 % PX] << 8));
   } else {
 #pragma unroll
     for (int e = 0; e < PX; ++e)
@@ -416,16 +424,21 @@ int cseg_accum_argmax(const float* crop_logits, int n_crops, int Q, int lh, int 
                 query_idx, K, logit_scale, prob_thd, bg_idx, labels, probs, avg_logits};
   const size_t smem = (size_t)n_crops * (sizeof(int4) + sizeof(int));
   CSEG_REQUIRE(smem <= 200 * 1024, "accum_argmax: %d windows do not fit the window table in shared memory", n_crops);
+  const bool direct = (out_h == H && out_w == W);
+#define CSEG_ACCUM_LAUNCH(QT, PX, D)                                                                                  \
+  do {                                                                                                                \
+    CSEG_SET_SMEM((accum_argmax_kernel<QT, PX, D>), smem);                                                            \
+    cseg_launch(accum_argmax_kernel<QT, PX, D>, dim3(cdiv(out_w, 32 * PX), cdiv(out_h, 8)), dim3(256), smem,          \
+                (cudaStream_t)stream, p);                                                                             \
+  } while (0)
   if (Q <= 8) {
-    CSEG_SET_SMEM((accum_argmax_kernel<8, 4>), smem);
-    cseg_launch(accum_argmax_kernel<8, 4>, dim3(cdiv(out_w, 128), cdiv(out_h, 8)), dim3(256), smem, (cudaStream_t)stream, p);
+    if (direct) CSEG_ACCUM_LAUNCH(8, 4, true); else CSEG_ACCUM_LAUNCH(8, 4, false);
   } else if (Q <= 16) {
-    CSEG_SET_SMEM((accum_argmax_kernel<16, 4>), smem);
-    cseg_launch(accum_argmax_kernel<16, 4>, dim3(cdiv(out_w, 128), cdiv(out_h, 8)), dim3(256), smem, (cudaStream_t)stream, p);
+    if (direct) CSEG_ACCUM_LAUNCH(16, 2, true); else CSEG_ACCUM_LAUNCH(16, 2, false);
   } else {
-    CSEG_SET_SMEM((accum_argmax_kernel<32, 2>), smem);
-    cseg_launch(accum_argmax_kernel<32, 2>, dim3(cdiv(out_w, 64), cdiv(out_h, 8)), dim3(256), smem, (cudaStream_t)stream, p);
+    if (direct) CSEG_ACCUM_LAUNCH(32, 1, true); else CSEG_ACCUM_LAUNCH(32, 1, false);
   }
+#undef CSEG_ACCUM_LAUNCH
   CSEG_LAUNCH_CHECK("accum_argmax");
   return 0;
 }
