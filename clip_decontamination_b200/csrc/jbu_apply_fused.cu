@@ -16,8 +16,8 @@
 // Work unit = a vertical run of `seg` tiles of one (crop, 16-px column, channel slab): consecutive tiles of a run share
 // NLR - 2 of their NLR low-res source rows, so the source strips live in a ring of 16 slots and only the 2 new rows per
 // tile are fetched (the strips were 62 % of the kernel's L2 traffic: 10x halo amplification per 4 x 16 tile).
-// Per tile of 4 rows x 16 px and 128-channel slab, every low-res row s of the (NLR x 16) source patch costs one
-// tcgen05.mma  D[128 ch, 64 px] += A_s[128 ch, 16 pos] . B_s[16 pos, 64 px]  (A: MN-major SWIZZLE_128B straight from
+// Per tile of 8 rows x 16 px and 128-channel slab, every low-res row s of the (NLR x 16) source patch costs one
+// tcgen05.mma  D[128 ch, 128 px] += A_s[128 ch, 16 pos] . B_s[16 pos, 128 px]  (A: MN-major SWIZZLE_128B straight from
 // the [pos][ch] HBM layout; B: composite band tile, K-major).  Warp roles of the persistent CTA:
 //   warps 0-3   epilogue (tcgen05.ld, lane = channel)           warp 4   TMEM allocator + MMA issuer
 //   warps 5-8   strip loaders (cp.async into a 6-stage ring)
@@ -32,10 +32,10 @@
 
 namespace {
 
-constexpr int FZ_RW = 4, FZ_TX = 16, FZ_NPX = FZ_RW * FZ_TX;   // 64 pixels per tile = N of the MMA
+constexpr int FZ_RW = 8, FZ_TX = 16, FZ_NPX = FZ_RW * FZ_TX;   // 128 pixels per tile = N of the MMA
 constexpr int FZ_NPOS = 16;                                    // low-res positions per strip = K of the MMA
 constexpr int FZ_NSTG = 16, FZ_INFL = 4;                       // strip ring slots / strips in flight per loader thread
-constexpr int FZ_EPI_WARPS = 4, FZ_LD_WARPS = 4, FZ_BB_WARPS = 4;
+constexpr int FZ_EPI_WARPS = 4, FZ_LD_WARPS = 4, FZ_BB_WARPS = 8;
 constexpr int FZ_THREADS = 32 * (FZ_EPI_WARPS + 1 + FZ_LD_WARPS + FZ_BB_WARPS);
 constexpr int FZ_LD_T0 = 32 * (FZ_EPI_WARPS + 1), FZ_BB_T0 = FZ_LD_T0 + 32 * FZ_LD_WARPS;
 
@@ -216,14 +216,14 @@ struct FzCfg {
   static constexpr int A_OFF = 0, B_OFF = FZ_NSTG * A_STAGE, BAR_OFF = B_OFF + 2 * B_BUF;
   static constexpr int NBARS = 2 * FZ_NSTG + 8;
   static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
-  static constexpr int TMEM_COLS = (2 * MH * FZ_NPX <= 128) ? 128 : 256;
+  static constexpr int TMEM_COLS = (2 * MH * FZ_NPX <= 128) ? 128 : ((2 * MH * FZ_NPX <= 256) ? 256 : 512);
 };
 
 template <int R, int MH>
 __global__ void __launch_bounds__(FZ_THREADS, 1)
 jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const bf16* __restrict__ kc,
                        bf16* __restrict__ dst, int nx, int ny, int nslab, int seg, int nseg, int total_units,
-                       const bf16* __restrict__ kc_img, const ShareGeom sg) {
+                       const bf16* __restrict__ kc_img, const ShareGeom sg, int diag) {
   using Cf = FzCfg<R, MH>;
   constexpr int DO = Cf::DO, NLR = Cf::NLR;
   const int H2 = 2 * h, W2 = 2 * w;
@@ -295,6 +295,7 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
           const int y = y0 + cb * 2 + rr;
           if (y >= H2) continue;
           bf16* o = obase + ((size_t)y * W2 + x0) * C;
+          if (diag & 4) continue;                                  // diagnostic: no output stores
           const int mmax = min(16, W2 - x0);
           if (mmax == 16) {
 #pragma unroll
@@ -316,7 +317,7 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
     // the whole warp runs the loop (warp-uniform control flow); one elected lane issues the MMAs and commits
     {
       constexpr uint32_t idesc = fz_idesc();
-      uint32_t tl = 0, base_it = 0;                             // base_it: ring fill counter of the unit's first row
+      uint32_t tl = 0, base_it = 0, ready = 0;                  // base_it: ring fill counter of the unit's first row
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
         int x0, crop, c0, yt0, yt1;
         unit_coords(unit, x0, crop, c0, yt0, yt1);
@@ -329,17 +330,21 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
           const uint32_t bbuf = smem_base + Cf::B_OFF + as * Cf::B_BUF;
           const bool last = (i == ntile - 1);
           for (int s = 0; s < NLR; ++s) {
-            const uint32_t g = base_it + (uint32_t)(2 * i + s);     // row s of this tile = row 2i + s of the run
+            const uint32_t g = base_it + (uint32_t)((FZ_RW / 2) * i + s);   // row s of this tile = row (RW/2) i + s of the run
             const uint32_t st = g % FZ_NSTG, ph = (g / FZ_NSTG) & 1;
-            mbar_wait(a_full0 + st * 8, ph);
-            tc_fence_after();
+            if (g >= ready) {                                      // strips land in order: rows below `ready` are known to
+              mbar_wait(a_full0 + st * 8, ph);                     // be resident (NLR - RW/2 rows of every tile after the
+              tc_fence_after();                                    // first one of a run were waited for by the tile above)
+              ready = g + 1;
+            }
             const uint32_t a_src = smem_base + Cf::A_OFF + st * Cf::A_STAGE;
             const uint64_t bdesc = make_sdesc(bbuf + (s >> 2) * Cf::B_QUAD + (s & 3) * 32);
             if (elect_one()) {
 #pragma unroll
               for (int half = 0; half < MH; ++half) {
                 const uint64_t adesc = fz_adesc(a_src + half * 2 * Cf::CHUNK_BYTES, Cf::CHUNK_BYTES);
-                umma_f16(tmem_base + (uint32_t)((as * MH + half) * FZ_NPX), adesc, bdesc, idesc, s > 0 ? 1u : 0u);
+                if (!(diag & 16))                                  // diagnostic bit 16: no MMAs (commits still fire)
+                  umma_f16(tmem_base + (uint32_t)((as * MH + half) * FZ_NPX), adesc, bdesc, idesc, s > 0 ? 1u : 0u);
               }
               // the two top rows leave the window of the next tile (all rows after the last tile of the run)
               if (s < FZ_RW / 2 || last) umma_commit(a_empty0 + st * 8);
@@ -382,9 +387,11 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
         const int yy = min(max(ly0 + s, 0), h - 1);
         const bf16* rowp = sc + (size_t)yy * w * C;
         const uint32_t base = smem_base + Cf::A_OFF + st * Cf::A_STAGE;
+        if (!(diag & 2)) {                                       // diagnostic bit 2: no strip fetches
 #pragma unroll
-        for (int k = 0; k < LPT; ++k)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + dst_off[k]), "l"(rowp + src_off[k]) : "memory");
+          for (int k = 0; k < LPT; ++k)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + dst_off[k]), "l"(rowp + src_off[k]) : "memory");
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (it >= FZ_INFL - 1) {
           asm volatile("cp.async.wait_group %0;" ::"n"(FZ_INFL - 1) : "memory");
@@ -422,7 +429,7 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
         const int e = bt + k * 32 * FZ_BB_WARPS, n = e / NCH, v = e - n * NCH;
         const int y = y0 + (n >> 4), x = x0 + (n & 15);
         wv[k] = make_uint4(0, 0, 0, 0);                          // pixels outside the image: zero weights
-        if (n < FZ_NPX && y < H2 && x < W2) {
+        if (n < FZ_NPX && y < H2 && x < W2 && !(diag & 8)) {     // diagnostic bit 8: no composite-weight loads
           const bf16* kp;
           if (kc_img == nullptr) kp = kc + (cbase + (size_t)y * W2 + x) * 128;
           else if (border_interior(y, x, H2, W2, CSEG_JBU_FB_COMP)) kp = kc_img + (org + (size_t)y * sg.pitch + x) * 128;
@@ -439,7 +446,7 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
 #pragma unroll
       for (int k = 0; k < WPT; ++k) {
         const int e = bt + k * 32 * FZ_BB_WARPS, n = e / NCH, v = e - n * NCH;
-        if (n >= FZ_NPX) continue;
+        if (n >= FZ_NPX || (diag & 1)) continue;                 // diagnostic bit 1: no band scatter
         const int r = n >> 4, m = n & 15;
         const unsigned short* hv = reinterpret_cast<const unsigned short*>(&wv[k]);
         uint8_t* rowb = bbuf + (n >> 3) * 1024 + (n & 7) * 128;
@@ -484,7 +491,7 @@ int launch_apply_kernel(const bf16* src, int n_crops, int h, int w, int C, const
     double best = 1e30;
     for (int s = 1; s <= std::min(ny, 16); ++s) {
       const long long units = ncols * cdiv(ny, s);
-      const double cost = (double)cdiv(units, sms) * (Cf::NLR + (FZ_RW / 2) * (s - 1) + 6.0 * s);
+      const double cost = (double)cdiv(units, sms) * (Cf::NLR + (FZ_RW / 2) * (s - 1) + 12.0 * s);
       if (cost < best - 1e-9) { best = cost; seg = s; }
     }
     if (const char* e = getenv("CSEG_APPLY_SEG")) seg = std::max(1, std::min(atoi(e), ny));   // A/B measurements
@@ -492,8 +499,13 @@ int launch_apply_kernel(const bf16* src, int n_crops, int h, int w, int C, const
   const int nseg = cdiv(ny, seg);
   const long long total = ncols * nseg;
   const int grid = (int)std::min<long long>(total, sm_count());
+  static int diag = -1;                            // CSEG_APPLY_DIAG: role knock-out bits for timing experiments (results invalid)
+  if (diag < 0) {
+    const char* e = getenv("CSEG_APPLY_DIAG");
+    diag = e ? atoi(e) : 0;
+  }
   cseg_launch(jbu_apply_fused_kernel<R, MH>, dim3(grid), dim3(FZ_THREADS), Cf::SMEM_BYTES, st, src, h, w, C, kc,
-              dst, nx, ny, nslab, seg, nseg, (int)total, kc_img, sg);
+              dst, nx, ny, nslab, seg, nseg, (int)total, kc_img, sg, diag);
   CSEG_LAUNCH_CHECK("jbu_apply_fused");
   return 0;
 }

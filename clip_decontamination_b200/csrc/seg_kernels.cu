@@ -147,18 +147,27 @@ __device__ __forceinline__ void canvas_avg(const AccumParams& p, const int4* win
 // (segmentor.py:478-489).  Ordering is decided on the scaled logits (softmax is monotone); probabilities only feed the
 // threshold and the optional probs output.
 template <int QT>
-__device__ __forceinline__ uint8_t post_process(const AccumParams& p, const int* s_qidx, float (&v)[QT], int oy, int ox) {
+__device__ __forceinline__ uint8_t post_process(const AccumParams& p, const int* s_qidx, bool identity, float (&v)[QT], int oy,
+                                                int ox) {
   float m = -INFINITY;
+  int arg = 0;
 #pragma unroll
   for (int q = 0; q < QT; ++q)
     if (q < p.Q) {
       v[q] *= p.logit_scale;
-      m = fmaxf(m, v[q]);
+      if (v[q] > m) {          // strict: the lowest index wins ties
+        m = v[q];
+        arg = q;
+      }
     }
   float sum = 0.f;
 #pragma unroll
   for (int q = 0; q < QT; ++q)
     if (q < p.Q) sum += expf(v[q] - m);
+  if (identity && p.probs == nullptr) {
+    // one query per class (query_idx = 0..Q-1): the class maximum is the query maximum, its probability 1 / sum
+    return (uint8_t)((1.0f / sum < p.prob_thd) ? p.bg_idx : arg);
+  }
   float best = -INFINITY;
   int best_k = 0;
   for (int k = 0; k < p.K; ++k) {
@@ -182,16 +191,22 @@ __device__ __forceinline__ uint8_t post_process(const AccumParams& p, const int*
 // <= 4..9 candidates instead of all n_crops.  When the crop logits are at crop resolution and no final resize is needed
 // (the JBU path) the PX pixels of a thread read each crop's logits with one 16-byte load per query.
 template <int QT, int PX, bool DIRECT>
-__global__ void __launch_bounds__(256, 2) accum_argmax_kernel(const AccumParams p) {
+__global__ void __launch_bounds__(256, (QT <= 8) ? 3 : 2) accum_argmax_kernel(const AccumParams p) {
   pdl_grid_sync();
   extern __shared__ int4 s_wins[];                              // [n_crops] candidate windows (compacted)
   int* s_cand = reinterpret_cast<int*>(s_wins + p.n_crops);     // [n_crops] their crop indices
   __shared__ int s_ncand;
   __shared__ int s_qidx[QT];
+  __shared__ int s_ident;
   const int tid = threadIdx.x;
   const int ox0 = blockIdx.x * (32 * PX), oy0 = blockIdx.y * 8;
   constexpr bool direct = DIRECT;                              // output size == canvas size (no final resize)
   if (tid < QT) s_qidx[tid] = tid < p.Q ? p.query_idx[tid] : -1;
+  if (tid == 32) {
+    int id = (p.K == p.Q);
+    for (int q = 0; q < p.Q; ++q) id &= (p.query_idx[q] == q);
+    s_ident = id;
+  }
   if (tid < 32) {
     // canvas rectangle the tile depends on
     int cy0 = oy0, cy1 = min(oy0 + 7, p.out_h - 1), cx0 = ox0, cx1 = min(ox0 + 32 * PX - 1, p.out_w - 1);
@@ -224,6 +239,7 @@ __global__ void __launch_bounds__(256, 2) accum_argmax_kernel(const AccumParams 
   }
   __syncthreads();
   const int n_cand = s_ncand;
+  const bool identity = s_ident != 0;
   const int oy = oy0 + (tid >> 5), oxb = ox0 + (tid & 31) * PX;
   if (oy >= p.out_h || oxb >= p.out_w) return;
   uint8_t lab[PX];
@@ -287,7 +303,7 @@ __global__ void __launch_bounds__(256, 2) accum_argmax_kernel(const AccumParams 
           acc[e][q] = acc[e][q] / c;
           if (p.avg_logits) p.avg_logits[((size_t)q * p.H + oy) * p.W + ox] = acc[e][q];
         }
-      lab[e] = post_process<QT>(p, s_qidx, acc[e], oy, ox);
+      lab[e] = post_process<QT>(p, s_qidx, identity, acc[e], oy, ox);
     }
   } else {  // bilinear resize of the averaged canvas to ori_shape (segmentor.py:448-449)
     int y0, y1;
@@ -311,7 +327,7 @@ __global__ void __launch_bounds__(256, 2) accum_argmax_kernel(const AccumParams 
       canvas_avg<QT>(p, s_wins, s_cand, n_cand, y1, x1, b);
 #pragma unroll
       for (int q = 0; q < QT; ++q) v[q] += ly * (hx * a[q] + lx * b[q]);
-      lab[e] = post_process<QT>(p, s_qidx, v, oy, ox);
+      lab[e] = post_process<QT>(p, s_qidx, identity, v, oy, ox);
     }
   }
   uint8_t* lrow = p.labels + (size_t)oy * p.out_w + oxb;

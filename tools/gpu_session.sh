@@ -5,13 +5,13 @@ set -u
 OUT=gpurun_out
 TAG=${1:-r02}
 mkdir -p $OUT
-python -m pytest tests -m gpu -q -s --maxfail=10 > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -3 $OUT/${TAG}_tests.log
-python bench.py --steps 10 --warmup 3 --tiles 6 > $OUT/${TAG}_bench_t6.log 2>&1; echo "bench6 rc=$?"
-CSEG_ATTN_TC=0 python bench.py --steps 10 --warmup 3 --tiles 6 --no-cpu-baseline > $OUT/${TAG}_bench_t6_noattntc.log 2>&1; echo "bench6 attn-mma rc=$?"
-CSEG_JBU_SHARE=0 python bench.py --steps 10 --warmup 3 --tiles 6 --no-cpu-baseline > $OUT/${TAG}_bench_t6_noshare.log 2>&1; echo "bench6 noshare rc=$?"
-python bench.py --steps 10 --warmup 3 --tiles 4 --no-cpu-baseline > $OUT/${TAG}_bench_t4.log 2>&1; echo "bench4 rc=$?"
-python bench.py --steps 5 --warmup 3 --tiles 2 --workload road1024 > $OUT/${TAG}_bench_road.log 2>&1; echo "road rc=$?"
-python bench.py --steps 5 --warmup 3 --tiles 2 --workload isaid896 > $OUT/${TAG}_bench_isaid.log 2>&1; echo "isaid rc=$?"
+timeout 600 python -m pytest tests -m gpu -q -s --maxfail=10 > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -3 $OUT/${TAG}_tests.log
+timeout 300 python bench.py --steps 10 --warmup 3 --tiles 6 > $OUT/${TAG}_bench_t6.log 2>&1; echo "bench6 rc=$?"
+CSEG_ATTN_TC=0 timeout 300 python bench.py --steps 10 --warmup 3 --tiles 6 --no-cpu-baseline > $OUT/${TAG}_bench_t6_noattntc.log 2>&1; echo "bench6 attn-mma rc=$?"
+CSEG_JBU_SHARE=0 timeout 300 python bench.py --steps 10 --warmup 3 --tiles 6 --no-cpu-baseline > $OUT/${TAG}_bench_t6_noshare.log 2>&1; echo "bench6 noshare rc=$?"
+timeout 300 python bench.py --steps 10 --warmup 3 --tiles 4 --no-cpu-baseline > $OUT/${TAG}_bench_t4.log 2>&1; echo "bench4 rc=$?"
+timeout 300 python bench.py --steps 5 --warmup 3 --tiles 2 --workload road1024 > $OUT/${TAG}_bench_road.log 2>&1; echo "road rc=$?"
+timeout 300 python bench.py --steps 5 --warmup 3 --tiles 2 --workload isaid896 > $OUT/${TAG}_bench_isaid.log 2>&1; echo "isaid rc=$?"
 if [ "${SKIP_REF:-0}" != "1" ]; then
   python -m oracle.ref_on_gpu --out $OUT/${TAG}_ref_on_gpu.json > $OUT/${TAG}_ref_on_gpu.log 2>&1; echo "ref rc=$?"
 fi
