@@ -19,16 +19,17 @@
 namespace {
 
 constexpr int AT_HD = 64, AT_BM = 128, AT_LP = 208;           // keys padded to 13 K-steps of 16
-constexpr int AT_SMW = 8;                                      // softmax / epilogue warps
+constexpr int AT_SMW = 16;                                     // softmax / epilogue warps: row quarter = warp % 4, key quarter = warp / 4
 constexpr int AT_THREADS = 32 * (AT_SMW + 2);
 constexpr int AT_Q_BYTES = AT_BM * 128, AT_KV_BYTES = AT_LP * 128, AT_P_BLK = AT_BM * 128, AT_P_BYTES = 4 * AT_P_BLK;
 constexpr int AT_Q_OFF = 0, AT_K_OFF = 2 * AT_Q_BYTES, AT_V_OFF = AT_K_OFF + 2 * AT_KV_BYTES;
 constexpr int AT_P_OFF = AT_V_OFF + 2 * AT_KV_BYTES, AT_RED_OFF = AT_P_OFF + AT_P_BYTES;
-constexpr int AT_RED_BYTES = (2 * 128 + 2 * 2 * 128) * 4;      // smax[2][128], ssum[2 tiles][2][128]
+constexpr int AT_RED_BYTES = (4 * 128 + 2 * 4 * 128) * 4;      // smax[4][128], ssum[2 tiles][4][128]
 constexpr int AT_BAR_OFF = AT_RED_OFF + AT_RED_BYTES, AT_NBARS = 15;
 constexpr int AT_SMEM = AT_BAR_OFF + AT_NBARS * 8 + 16 + 1024;
 constexpr int AT_S_COLS = 224, AT_O_COL = 448, AT_TMEM_COLS = 512;
-constexpr int AT_SPLIT = 112;                                  // key half 0: [0, 112), half 1: [112, 208)
+// key quarters: [0, 64), [64, 112), [112, 160), [160, 208)
+__host__ __device__ constexpr int at_qbegin(int k) { return k == 0 ? 0 : (k == 1 ? 64 : (k == 2 ? 112 : (k == 3 ? 160 : AT_LP))); }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -76,12 +77,12 @@ __host__ __device__ constexpr uint32_t at_idesc_pv() {
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int L, int heads,
-                    int n_items, bf16* __restrict__ out, float scale_log2e) {
+                    int n_items, bf16* __restrict__ out, float scale_log2e, int diag) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
-  float* smax = reinterpret_cast<float*>(smem + AT_RED_OFF);            // [2][128]
-  float* ssum = smax + 2 * 128;                                        // [2][2][128]
+  float* smax = reinterpret_cast<float*>(smem + AT_RED_OFF);            // [4][128]
+  float* ssum = smax + 4 * 128;                                        // [2][4][128]
   uint64_t* bars = (uint64_t*)(smem + AT_BAR_OFF);
   uint32_t* tmem_slot = (uint32_t*)(bars + AT_NBARS);
   const uint32_t b0 = smem_u32(bars);
@@ -151,7 +152,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int j = 0; j < AT_LP / 16; ++j) {
           const uint64_t adesc = make_sdesc(sbase + AT_P_OFF + (j >> 2) * AT_P_BLK + (j & 3) * 32);
           const uint64_t bdesc = at_mn_desc(sbase + AT_V_OFF + prev_kb * AT_KV_BYTES + j * 2048);
-          umma_f16(tmem_base + AT_O_COL, adesc, bdesc, idesc_pv, j > 0 ? 1u : 0u);
+          if (!(diag & 2)) umma_f16(tmem_base + AT_O_COL, adesc, bdesc, idesc_pv, j > 0 ? 1u : 0u);
         }
         umma_commit(o_full);
         if (prev_last) umma_commit(kv_empty + prev_kb * 8);
@@ -171,7 +172,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           for (int ks = 0; ks < AT_HD / 16; ++ks) {
             const uint64_t adesc = make_sdesc(sbase + AT_Q_OFF + qb * AT_Q_BYTES + ks * 32);
             const uint64_t bdesc = make_sdesc(sbase + AT_K_OFF + kb * AT_KV_BYTES + ks * 32);
-            umma_f16(tmem_base + qb * AT_S_COLS, adesc, bdesc, idesc_s, ks > 0 ? 1u : 0u);
+            if (!(diag & 4)) umma_f16(tmem_base + qb * AT_S_COLS, adesc, bdesc, idesc_s, ks > 0 ? 1u : 0u);
           }
           umma_commit(s_full + qb * 8);
           umma_commit(q_empty + qb * 8);
@@ -187,8 +188,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (have_prev) issue_pv();
   } else {
     // ---------------- softmax + epilogue ----------------
-    const int q4 = warp & 3, hh = warp >> 2, row = q4 * 32 + lane;
-    const int c_begin = hh ? AT_SPLIT : 0, c_end = hh ? AT_LP : AT_SPLIT;
+    const int q4 = warp & 3, hh = warp >> 2, row = q4 * 32 + lane;         // hh: key quarter
+    const int c_begin = at_qbegin(hh), c_end = at_qbegin(hh + 1);
     const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16);
     uint8_t* prow = smem + AT_P_OFF + row * 128;
     uint32_t qi = 0;
@@ -198,14 +199,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     auto epilogue = [&]() {
       mbar_wait(o_full, prev_pi & 1);
       tc_fence_after();
-      uint32_t r[32];
-      tmem_ld32(tlane + AT_O_COL + hh * 32, r);
-      const float* ss = ssum + (prev_pi & 1) * 256;
-      const float inv = 1.0f / (ss[row] + ss[128 + row]);
-      if (row < prev_valid) {
-        uint4* o = reinterpret_cast<uint4*>(out + (size_t)(prev_row0 + row) * width + prev_head * AT_HD + hh * 32);
+      uint32_t r[16];
+      tmem_ld16(tlane + AT_O_COL + hh * 16, r);
+      const float* ss = ssum + (prev_pi & 1) * 512;
+      const float inv = 1.0f / ((ss[row] + ss[128 + row]) + (ss[256 + row] + ss[384 + row]));
+      if (row < prev_valid && !(diag & 8)) {
+        uint4* o = reinterpret_cast<uint4*>(out + (size_t)(prev_row0 + row) * width + prev_head * AT_HD + hh * 16);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
+        for (int v = 0; v < 2; ++v) {
           uint4 w;
           w.x = at_pack(__uint_as_float(r[8 * v]) * inv, __uint_as_float(r[8 * v + 1]) * inv);
           w.y = at_pack(__uint_as_float(r[8 * v + 2]) * inv, __uint_as_float(r[8 * v + 3]) * inv);
@@ -238,7 +239,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           };
           tmem_ld16_nowait(ts + c_begin, ra);
 #pragma unroll 1
-          for (int c = c_begin; c < c_end; c += 32) {
+          for (int c = c_begin; c < ((diag & 16) ? c_begin + 1 : c_end); c += 32) {
             tmem_wait_ld();
             if (c + 16 < c_end) tmem_ld16_nowait(ts + c + 16, rb);
             red(ra, c);
@@ -251,7 +252,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         smax[hh * 128 + row] = m;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * AT_SMW) : "memory");
-        m = fmaxf(smax[row], smax[128 + row]);
+        m = fmaxf(fmaxf(smax[row], smax[128 + row]), fmaxf(smax[256 + row], smax[384 + row]));
         // epilogue of the previous tile: its P.V has completed, so the P buffer is free for this tile
         if (have_prev) epilogue();
         // pass 2: exponentials -> bf16 P in the K-major SWIZZLE_128B layout, row sum in fp32
@@ -276,7 +277,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           };
           tmem_ld16_nowait(ts + c_begin, ra);
 #pragma unroll 1
-          for (int c = c_begin; c < c_end; c += 32) {
+          for (int c = c_begin; c < ((diag & 1) ? c_begin + 1 : c_end); c += 32) {
             tmem_wait_ld();
             if (c + 16 < c_end) tmem_ld16_nowait(ts + c + 16, rb);
             expo(ra, c);
@@ -287,7 +288,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
           }
         }
-        ssum[(qi & 1) * 256 + hh * 128 + row] = sum;
+        ssum[(qi & 1) * 512 + hh * 128 + row] = sum;
         tc_fence_before();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -364,7 +365,12 @@ int cseg_attention_tc(const bf16* qkv, int n_crops, int L, int heads, int head_d
   const int items = n_crops * heads;
   const int grid = std::min(items, sm_count());
   const float scale_log2e = 0.125f * 1.4426950408889634f;     // head_dim^-0.5 * log2(e)
-  cseg_launch(attention_tc_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tq, tkv, L, heads, items, out, scale_log2e);
+  static int diag = -1;                     // CSEG_ATTN_DIAG: knock-out bits for timing experiments (results invalid)
+  if (diag < 0) {
+    const char* e = getenv("CSEG_ATTN_DIAG");
+    diag = e ? atoi(e) : 0;
+  }
+  cseg_launch(attention_tc_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tq, tkv, L, heads, items, out, scale_log2e, diag);
   CSEG_LAUNCH_CHECK("attention_tc");
   return 0;
 }

@@ -539,7 +539,7 @@ class SegEngine:
                  logit_scale: float = 50.0, slide_stride: int = 112, slide_crop: int = 224,
                  cls_token_lambda: float = 0.0, global_debias_factor: float = 0.0, bg_idx: int = 0,
                  upsampler: Optional[JBUEngine] = None, sim_cfg: Optional[dict] = None,
-                 outlier_cfg: Optional[dict] = None, jbu_chunk: int = 16, basis: bool = True):
+                 outlier_cfg: Optional[dict] = None, jbu_chunk: int = 48, basis: bool = True):
         self.v = visual
         self.device = visual.device
         self.text = query_features.detach().to(self.device, torch.float32).contiguous()
@@ -553,7 +553,7 @@ class SegEngine:
         self.cls_token_lambda, self.debias, self.bg_idx = float(cls_token_lambda), float(global_debias_factor), int(bg_idx)
         self.up = upsampler
         self.sim_cfg, self.outlier_cfg = sim_cfg, outlier_cfg
-        self.jbu_chunk = jbu_chunk
+        self.jbu_chunk = int(os.environ.get('CSEG_JBU_CHUNK', jbu_chunk))     # crops per JBU pass (working set ~95 MB per crop)
         self.basis = basis          # bf16: upsample token indicators instead of features when that is cheaper
         self.share_kernels = True   # bf16: JBU kernel generation once per image pixel + per-crop border frames
         self.ws = Workspace(self.device)
