@@ -556,6 +556,8 @@ class SegEngine:
         self.jbu_chunk = int(os.environ.get('CSEG_JBU_CHUNK', jbu_chunk))     # crops per JBU pass (working set ~95 MB per crop)
         self.basis = basis          # bf16: upsample token indicators instead of features when that is cheaper
         self.share_kernels = True   # bf16: JBU kernel generation once per image pixel + per-crop border frames
+        self.overlap_image_level = os.environ.get('CSEG_OVERLAP', '1') != '0'   # ... on a side stream next to the ViT
+        self._side = None
         self.ws = Workspace(self.device)
         self._win_cache: Dict[tuple, Tuple[torch.Tensor, list]] = {}
         self._graphs: Dict[tuple, dict] = {}
@@ -609,8 +611,26 @@ class SegEngine:
         crop_h, crop_w = wh + pt + pb, ww + pl + pr
         gh, gw = crop_h // ps, crop_w // ps
         P = gh * gw
+        # The image-level JBU tensors (guidance, range projection / kernel, fix-up, composite kernels of the shared stages)
+        # depend on the image only: they run on a side stream next to the ViT (SIMT / MUFU work in the gaps of the
+        # tensor-core GEMMs) and are joined before the upsampler starts.  Inside a graph capture this is a parallel branch.
+        shared, side = None, None
+        if (self.up is not None and ps == 16 and self.share_kernels and taps is None and self.crop > 0
+                and self.up.share_ok(wl, H * W, crop_h, crop_w, pt, pl)):
+            if self.overlap_image_level:
+                cur = torch.cuda.current_stream(self.device)
+                if self._side is None:
+                    self._side = torch.cuda.Stream(self.device)
+                side = self._side
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    shared = self.up.prepare_shared(img, crop_h, crop_w, gh, gw)
+            else:
+                shared = self.up.prepare_shared(img, crop_h, crop_w, gh, gw)
         tok, L = self.v.encode(img, win_dev, crop_h, crop_w, pt, pl, self.model_type, self.ignore_residual,
                                self.sim_cfg, self.outlier_cfg, taps)
+        if side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(side)
         D, cdt, ws = self.v.D, self.v.cdt, self.ws
         basis = (self.up is not None and self.basis and taps is None and ps == 16
                  and self.up.basis_ok(P, crop_h * crop_w, self.Q))
@@ -629,9 +649,6 @@ class SegEngine:
             if ps != 16:
                 raise ValueError('JBU upsamples x16 and only matches patch size 16 (segmentor.py:372)')
             logits = ws.get('logits', (n, self.Q, crop_h, crop_w), torch.float32)
-            shared = None
-            if self.share_kernels and taps is None and self.crop > 0 and self.up.share_ok(wl, H * W, crop_h, crop_w, pt, pl):
-                shared = self.up.prepare_shared(img, crop_h, crop_w, gh, gw)
             for c0 in range(0, n, self.jbu_chunk):
                 c1 = min(n, c0 + self.jbu_chunk)
                 if basis:
