@@ -402,6 +402,10 @@ def main():
     for nm in names:
         orig[nm] = getattr(ops, nm)
         setattr(ops, nm, wrap(nm, orig[nm], workfns.get(nm)))
+    # the instrumented passes run every kernel ALONE on the stream (no side-stream branch next to the ViT): a launch
+    # bracketed by events while another stream shares the SMs would be charged for its neighbour's work
+    overlap = eng.overlap_image_level
+    eng.overlap_image_level = False
     step_eager()
     torch.cuda.synchronize()
     for nm in names:
@@ -417,14 +421,17 @@ def main():
     # ---- timed region: value (inputs resident in HBM, CUDA-graph replay of the launch sequence) -----
     clk = ClockSampler(local_rank)
     clk.start()
+    eng.overlap_image_level = overlap
     ms = timed(step_resident, args.steps)
     launches = launches_per_step * args.steps          # a replay issues the kernels counted at capture
+    eng.overlap_image_level = False
     # ---- the same launches issued eagerly with every kernel class >= 3 % of the step bracketed by CUDA events (a graph
     #      node cannot be bracketed): per-launch durations for the rooflines -------------------------------------------
     for c in classes:
         for nm in members[c]:
             setattr(ops, nm, wrap(nm, orig[nm], workfns[nm]))
     ms_eager = timed(step_eager, args.steps)
+    eng.overlap_image_level = overlap
     clocks = clk.stop()
     for c in classes:
         for nm in members[c]:

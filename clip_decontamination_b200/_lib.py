@@ -52,6 +52,7 @@ SIGNATURES = {
     'cseg_embed_tokens': (_i, [_p, _p, _p, _i, _i, _i, _p, _p]),
     'cseg_layernorm': (_i, [_p, _i, _i, _p, _p, _f, _i, _p, _p]),
     'cseg_gemm': (_i, [_i, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _f, _i, _i, _p, _i, _p]),
+    'cseg_gemm_blockdiag': (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     'cseg_gemm_reference': (_i, [_i, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _f, _i, _i, _p, _i, _p]),
     'cseg_attention': (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _f, _p, _p, _p]),
     'cseg_simmap': (_i, [_p, _i, _i, _i, _f, _i, _p, _p]),

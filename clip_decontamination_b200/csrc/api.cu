@@ -16,7 +16,7 @@ bool cseg_pdl_enabled() {
 
 int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
                       const void* residual, int ldr, int res_dtype, float alpha, int act, int out_dtype, void* C, int ldc,
-                      cudaStream_t st);
+                      cudaStream_t st, int diag_rows = 0);
 int cseg_gemm_simt(int in_dtype, const void* A, int lda, const void* B, int ldb, int M, int N, int K,
                    const float* bias, const void* residual, int ldr, int res_dtype, float alpha, int act, int out_dtype, void* C,
                    int ldc, cudaStream_t st);
@@ -52,6 +52,13 @@ int cseg_gemm(int in_dtype, const void* A, int lda, const void* B, int ldb, int 
   if (in_dtype == CSEG_F32)
     return cseg_gemm_simt(CSEG_F32, A, lda, B, ldb, M, N, K, bias, residual, ldr, res_dtype, alpha, act, out_dtype, C, ldc, st);
   CSEG_FAIL(CSEG_EINVAL, "gemm: unknown dtype %d", in_dtype);
+}
+
+int cseg_gemm_blockdiag(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int block_rows, int out_dtype,
+                        void* C, int ldc, void* stream) {
+  CSEG_REQUIRE(block_rows > 0, "gemm_blockdiag: block_rows=%d", block_rows);
+  return cseg_gemm_bf16_tc(A, lda, B, ldb, M, N, K, nullptr, nullptr, 0, CSEG_F32, 1.0f, CSEG_ACT_NONE, out_dtype, C, ldc,
+                           (cudaStream_t)stream, block_rows);
 }
 
 int cseg_fixup_norm_sim(int dtype, const void* y, int ldy, const void* W, int ldw, int n_crops, int hw, int C,

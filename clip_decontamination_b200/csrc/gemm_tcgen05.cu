@@ -33,6 +33,7 @@ struct EpiParams {
   void* C;
   int ldc;
   int M, N;
+  int diag_rows;   // > 0: only tiles that touch the block diagonal (square blocks of diag_rows rows / columns) are computed
 };
 
 // Persistent, warp-specialised kernel.  One CTA per SM loops over output tiles (tile id -> (m, n) with m
@@ -91,6 +92,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const bool n_fast = m_tiles >= n_tiles;
 #define TILE_M(t) (n_fast ? (t) / n_tiles : (t) % m_tiles)
 #define TILE_N(t) (n_fast ? (t) % n_tiles : (t) / m_tiles)
+  // block-diagonal products (per-crop Gram matrices in one launch): a tile is skipped by every warp role alike when its
+  // row range and its column range share no diagonal block
+  auto tile_skipped = [&](int t) -> bool {
+    if (ep.diag_rows <= 0) return false;
+    const int m0 = TILE_M(t) * BM, n0 = TILE_N(t) * BN;
+    const int r_lo = m0 / ep.diag_rows, r_hi = (min(m0 + BM, ep.M) - 1) / ep.diag_rows;
+    const int c_lo = n0 / ep.diag_rows, c_hi = (min(n0 + BN, ep.N) - 1) / ep.diag_rows;
+    return r_hi < c_lo || c_hi < r_lo;
+  };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -119,6 +129,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        if (tile_skipped(tile)) continue;
         const int m0 = TILE_M(tile) * BM, n0 = TILE_N(tile) * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
@@ -136,8 +147,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       uint32_t it = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        if (tile_skipped(tile)) continue;
         const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
+        ++tl;
         mbar_wait(tempty0 + as * 8, aph ^ 1);      // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN;
@@ -167,9 +180,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr int SST = C::SST, CPW = C::NCHUNK / C::CGROUPS;
     float* stg = reinterpret_cast<float*>(smem + C::STG_OFF) + ew * 32 * SST;
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (tile_skipped(tile)) continue;
       const int m0 = TILE_M(tile) * BM, n0 = TILE_N(tile) * BN;
       const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
+      ++tl;
       const int rbase = m0 + lg * 32;
       const int nrows = min(32, ep.M - rbase);
 #pragma unroll
@@ -1160,7 +1175,7 @@ int cseg_jbu_kernel_fixup_tc(const void* k, int lda, const void* W0, int ldw0, c
 
 int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
                       const void* residual, int ldr, int res_dtype, float alpha, int act, int out_dtype, void* C,
-                      int ldc, cudaStream_t st) {
+                      int ldc, cudaStream_t st, int diag_rows) {
   CSEG_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   CSEG_REQUIRE(K % 8 == 0, "gemm(bf16): K=%d must be a multiple of 8 (16-byte rows for TMA)", K);
   CSEG_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm(bf16): lda=%d, ldb=%d must be multiples of 8", lda, ldb);
@@ -1190,7 +1205,7 @@ int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int
   if (rc) return rc;
   rc = make_map(&tb, B, N, K, ldb, bn);
   if (rc) return rc;
-  EpiParams ep{bias, residual, ldr, res_dtype == CSEG_BF16, alpha, act, out_dtype == CSEG_BF16, C, ldc, M, N};
+  EpiParams ep{bias, residual, ldr, res_dtype == CSEG_BF16, alpha, act, out_dtype == CSEG_BF16, C, ldc, M, N, diag_rows};
   if (bn == 64) return launch<64, 6>(ta, tb, M, N, K, ep, st);
   if (bn == 192) return launch<192, 4>(ta, tb, M, N, K, ep, st);
   if (bn == 256) return launch<256, 3>(ta, tb, M, N, K, ep, st);

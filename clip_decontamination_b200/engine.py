@@ -524,7 +524,7 @@ class JBUEngine:
         assert feats.shape[0] == n * Tp
         # token features after the final 1x1 conv (without its bias): g = x + 0.1 * x . W^T
         ops.gemm(feats, self.w_fin, g, residual=feats, alpha=0.1)
-        ops.gemm(g, g, gram[:, :n * Tp])          # Gram matrix; one launch, the diagonal blocks are what is used
+        ops.gemm_blockdiag(g, g, gram[:, :n * Tp], Tp)     # per-crop Gram matrices: one launch, diagonal tiles only
         ops.gemm(st['tb'], g, aux[:, :n * Tp])                      # <g, text[q]> and <g, b>
         s = self.upsample(st['eye'], gh, gw, img, windows, crop_h, crop_w, pad_top, pad_left, None, final_conv=False,
                           shared=shared)

@@ -157,6 +157,15 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, bias=None, residua
     return out
 
 
+def gemm_blockdiag(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, block_rows: int):
+    """out = A @ B^T on the block diagonal only (square blocks of block_rows); other entries of `out` are not written."""
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.stride(1) == 1 and B.stride(1) == 1 and out.stride(1) == 1
+    check(lib.cseg_gemm_blockdiag(C.c_void_p(A.data_ptr()), A.stride(0), C.c_void_p(B.data_ptr()), B.stride(0), A.shape[0],
+                                  B.shape[0], A.shape[1], block_rows, _dt(out), C.c_void_p(out.data_ptr()), out.stride(0),
+                                  _stream()))
+    return out
+
+
 def attention(qkv: torch.Tensor, n_crops: int, L: int, heads: int, head_dim: int, mode: int, out: torch.Tensor,
               simmap=None, sim_weight: float = 1.0, stats=None):
     check(lib.cseg_attention(_dt(qkv), _ptr(qkv), n_crops, L, heads, head_dim, mode, _ptr(simmap), sim_weight,

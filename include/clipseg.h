@@ -111,6 +111,11 @@ CSEG_API int cseg_layernorm(const float* x, int rows, int width, const float* ga
 CSEG_API int cseg_gemm(int in_dtype, const void* A, int lda, const void* B, int ldb, int M, int N, int K,
               const float* bias, const void* residual, int ldr, int res_dtype, float alpha, int act,
               int out_dtype, void* C, int ldc, void* stream);
+/* bf16 A[M,K] . B[N,K]^T restricted to the block diagonal: only output tiles that touch a square diagonal block of
+ * block_rows rows / columns are computed (the per-crop Gram matrices of cseg_basis_logits in ONE launch: entries that pair
+ * rows of different blocks are left untouched).  Same operand constraints as cseg_gemm(CSEG_BF16). */
+CSEG_API int cseg_gemm_blockdiag(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int block_rows,
+                        int out_dtype, void* C, int ldc, void* stream);
 /* same contract on the CUDA-core kernel for either operand dtype: the on-device cross-check of the
  * tensor-core path used by the tests (never called by the product path). */
 CSEG_API int cseg_gemm_reference(int in_dtype, const void* A, int lda, const void* B, int ldb, int M, int N,

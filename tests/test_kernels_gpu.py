@@ -530,3 +530,19 @@ def test_colorize_and_heatmap(ops):
     got = out.cpu().numpy()
     # torch.max propagates NaN exactly like the reference's seg_logits.max(dim=0); everything else must be identical
     assert np.array_equal(got[1:], heat[1:]) and np.array_equal(got[0, 1:], heat[0, 1:])
+
+
+def test_gemm_blockdiag(ops):
+    """A @ A^T restricted to the diagonal blocks (per-crop Gram matrices in one launch): the blocks equal the full
+    product, tiles off the block diagonal are not written."""
+    n, Tp, K = 13, 200, 512
+    a = (torch.randn(n * Tp, K, generator=_g(5)) * 0.3).to(torch.bfloat16).cuda()
+    out = torch.full((n * Tp, n * Tp + 8), 7.0, device='cuda', dtype=torch.bfloat16)
+    ops.gemm_blockdiag(a, a, out[:, :n * Tp], Tp)
+    ref = torch.empty((n * Tp, n * Tp), device='cuda', dtype=torch.bfloat16)
+    ops.gemm(a, a, ref)
+    torch.cuda.synchronize()
+    for c in range(n):
+        sl = slice(c * Tp, (c + 1) * Tp)
+        assert torch.equal(out[sl, sl], ref[sl, sl])
+    assert (out[:128, 1024:1200] == 7.0).all() and (out[2000:2100, :512] == 7.0).all()       # far off the diagonal: untouched
