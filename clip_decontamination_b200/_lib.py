@@ -50,12 +50,14 @@ SIGNATURES = {
     'cseg_patchify': (_i, [_img, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     'cseg_gather_rows': (_i, [_p, _p, _p, _ll, _i, _i, _p, _p]),
     'cseg_embed_tokens': (_i, [_p, _p, _p, _i, _i, _i, _p, _p]),
+    'cseg_embed_tokens_ln': (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _f, _p, _p]),
     'cseg_layernorm': (_i, [_p, _i, _i, _p, _p, _f, _i, _p, _p]),
     'cseg_gemm': (_i, [_i, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _f, _i, _i, _p, _i, _p]),
     'cseg_gemm_blockdiag': (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     'cseg_gemm_reference': (_i, [_i, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _f, _i, _i, _p, _i, _p]),
     'cseg_attention': (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _f, _p, _p, _p]),
     'cseg_simmap': (_i, [_p, _i, _i, _i, _f, _i, _p, _p]),
+    'cseg_simmap_tc': (_i, [_p, _i, _i, _i, _f, _p, _p, _p]),
     'cseg_outlier_suppress': (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _i, _f, _p, _p, _p]),
     'cseg_cls_debias': (_i, [_p, _i, _i, _i, _f, _i, _p, _i, _i, _p, _p]),
     'cseg_jbu_guidance': (_i, [_img, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),

@@ -34,6 +34,13 @@ struct EpiParams {
   int ldc;
   int M, N;
   int diag_rows;   // > 0: only tiles that touch the block diagonal (square blocks of diag_rows rows / columns) are computed
+  // RES == 3 (compact block-diagonal store, fp32): element (block b, i, j) goes to C[b * cmp_cs + (i - cmp_skip) * cmp_rs +
+  // (j - cmp_skip)] for i, j >= cmp_skip; entries that pair rows of different blocks are dropped
+  long long cmp_cs;
+  int cmp_rs, cmp_skip;
+  // > 0: both operands are [hi | lo] bf16 splits of split_kb k-blocks each and the K loop runs hi.hi + hi.lo + lo.hi
+  // (three segments of split_kb k-blocks): fp32-grade products on the bf16 tensor cores
+  int split_kb;
 };
 
 // Persistent, warp-specialised kernel.  One CTA per SM loops over output tiles (tile id -> (m, n) with m
@@ -136,8 +143,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           mbar_wait(empty0 + s * 8, ph ^ 1);
           mbar_expect_tx(full0 + s * 8, C::STAGE_BYTES);
           const uint32_t a_dst = smem_base + s * C::STAGE_BYTES;
-          tma_load_2d(a_dst, &tmA, full0 + s * 8, kb * BK, m0);
-          tma_load_2d(a_dst + C::A_BYTES, &tmB, full0 + s * 8, kb * BK, n0);
+          int ka = kb, kb_ = kb;
+          if (ep.split_kb > 0) {                     // segments: (A hi, B hi), (A hi, B lo), (A lo, B hi)
+            const int seg = kb / ep.split_kb, r = kb - seg * ep.split_kb;
+            ka = (seg == 2) ? ep.split_kb + r : r;
+            kb_ = (seg == 1) ? ep.split_kb + r : r;
+          }
+          tma_load_2d(a_dst, &tmA, full0 + s * 8, ka * BK, m0);
+          tma_load_2d(a_dst + C::A_BYTES, &tmB, full0 + s * 8, kb_ * BK, n0);
         }
       }
     }
@@ -196,8 +209,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // residual + bias of the chunk are fetched BEFORE the accumulator is read (for the first chunk:
         // before waiting for it), so their latency hides behind the main loop / the previous chunk.
         float res[32];
-        const bool direct = EPI_DIRECT && col0 + 32 <= ep.N && (ep.ldc & 7) == 0 && (RES == 0 || (ep.ldr & 7) == 0);
-        if (RES != 0 && col_ok && nrows > 0 && !direct) {
+        const bool direct = EPI_DIRECT && RES != 3 && col0 + 32 <= ep.N && (ep.ldc & 7) == 0 && (RES == 0 || (ep.ldr & 7) == 0);
+        if ((RES == 1 || RES == 2) && col_ok && nrows > 0 && !direct) {
           if (RES == 2) {
             const bf16* rp = (const bf16*)ep.residual + (size_t)rbase * ep.ldr + col;
 #pragma unroll
@@ -299,9 +312,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             float x = stg[rr * SST + lane] + bv;
             if (ACT == CSEG_ACT_GELU) x = OUTB ? gelu_tanh(x) : gelu_fast(x);
             else if (ACT == CSEG_ACT_QUICKGELU) x = quick_gelu(x);
-            return RES != 0 ? fmaf(x, alpha, res[rr]) : x * alpha;
+            return (RES == 1 || RES == 2) ? fmaf(x, alpha, res[rr]) : x * alpha;
           };
-          if (OUTB) {
+          if (RES == 3) {
+            const int Lb = ep.diag_rows, skip = ep.cmp_skip;
+            int blk = rbase / Lb, i = rbase - blk * Lb;
+            float* cf = (float*)ep.C;
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+              if (rr < nrows) {
+                const int j = col - blk * Lb;
+                if (i >= skip && j >= skip && j < Lb)
+                  cf[(size_t)blk * ep.cmp_cs + (size_t)(i - skip) * ep.cmp_rs + (j - skip)] = stg[rr * SST + lane] * alpha;
+              }
+              if (++i == Lb) { i = 0; ++blk; }
+            }
+          } else if (OUTB) {
             bf16* cp = (bf16*)ep.C + (size_t)rbase * ep.ldc + col;
             if (nrows == 32) {
 #pragma unroll
@@ -1173,6 +1199,25 @@ int cseg_jbu_kernel_fixup_tc(const void* k, int lda, const void* W0, int ldw0, c
   return launch_kernel_fixup<64>(k, lda, W0, ldw0, b0, W3, ldw3, b3, M, out, ldo, st);
 }
 
+// Per-block Gram matrices of fp32-grade accuracy on the bf16 tensor cores: X is the [hi | lo] bf16 split of a row-normalised
+// fp32 matrix ([M, 2 * width], width % 64 == 0); out[b, i - skip, j - skip] = alpha * <x_(b,i), x_(b,j)> for the square diagonal
+// blocks of block_rows rows, compact fp32 [n_blocks, block_rows - skip, block_rows - skip] (the similarity map layout).
+int cseg_gram_split_tc(const void* X, int ldx, int M, int width, int block_rows, int skip, float alpha, float* out,
+                       cudaStream_t st) {
+  CSEG_REQUIRE(M > 0 && width > 0 && width % BK == 0 && ldx % 8 == 0 && ldx >= 2 * width, "gram_split: M=%d width=%d ldx=%d", M,
+               width, ldx);
+  CSEG_REQUIRE(block_rows > skip && skip >= 0 && M % block_rows == 0, "gram_split: M=%d block_rows=%d skip=%d", M, block_rows, skip);
+  CSEG_REQUIRE(((uintptr_t)X & 15) == 0, "gram_split: operand must be 16-byte aligned");
+  CUtensorMap ta, tb;
+  int rc = make_map(&ta, X, M, 2 * width, ldx, BM);
+  if (rc) return rc;
+  rc = make_map(&tb, X, M, 2 * width, ldx, 128);
+  if (rc) return rc;
+  const int P = block_rows - skip;
+  EpiParams ep{nullptr, nullptr, 0, 0, alpha, CSEG_ACT_NONE, 0, out, 0, M, M, block_rows, (long long)P * P, P, skip, width / BK};
+  return launch3<128, 4, CSEG_ACT_NONE, 0, 3>(ta, tb, M, M, 3 * width, ep, st);
+}
+
 int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
                       const void* residual, int ldr, int res_dtype, float alpha, int act, int out_dtype, void* C,
                       int ldc, cudaStream_t st, int diag_rows) {
@@ -1205,7 +1250,7 @@ int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int
   if (rc) return rc;
   rc = make_map(&tb, B, N, K, ldb, bn);
   if (rc) return rc;
-  EpiParams ep{bias, residual, ldr, res_dtype == CSEG_BF16, alpha, act, out_dtype == CSEG_BF16, C, ldc, M, N, diag_rows};
+  EpiParams ep{bias, residual, ldr, res_dtype == CSEG_BF16, alpha, act, out_dtype == CSEG_BF16, C, ldc, M, N, diag_rows, 0, 0, 0, 0};
   if (bn == 64) return launch<64, 6>(ta, tb, M, N, K, ep, st);
   if (bn == 192) return launch<192, 4>(ta, tb, M, N, K, ep, st);
   if (bn == 256) return launch<256, 3>(ta, tb, M, N, K, ep, st);

@@ -47,6 +47,53 @@ __global__ void patchify_kernel(const ImgView img, const int32_t* __restrict__ w
   }
 }
 
+// bf16 form for ps % 8 == 0: a thread produces 8 consecutive columns (= 8 consecutive pixels of one patch row of one
+// channel) and stores them as one 16-byte vector; uint8 inputs are normalised through a 3 x 256 table built per CTA with
+// the same IEEE division as img_at (bit-identical values, no division per element).
+__global__ void __launch_bounds__(256) patchify_vec8_kernel(const ImgView img, const int32_t* __restrict__ wins, int n_crops,
+                                                            int gh, int gw, int pad_top, int pad_left, int ps,
+                                                            bf16* __restrict__ out, int ldo) {
+  __shared__ float lut[3][256];
+  if (img.dtype == CSEG_U8)
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) lut[i >> 8][i & 255] = __fdiv_rn((float)(i & 255) - img.mean[i >> 8], img.std[i >> 8]);
+  __syncthreads();
+  pdl_grid_sync();
+  const int g_per_row = ldo >> 3, kk = 3 * ps * ps, P = gh * gw;
+  const long long total = (long long)n_crops * P * g_per_row;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % g_per_row) * 8;
+    const long long row = idx / g_per_row;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (col < kk) {
+      const int p = (int)(row % P), crop = (int)(row / P);
+      const int c = col / (ps * ps), ky = (col / ps) % ps, kx = col % ps;
+      const int cy = (p / gw) * ps + ky - pad_top, cx = (p % gw) * ps + kx - pad_left;
+      const int4 w = *reinterpret_cast<const int4*>(wins + crop * 4);
+      if (cy >= 0 && cy < w.z) {
+        const long long base = img_row_off(img, w.x + cy) + (long long)img.chan[c] * img.stride_c;
+        if (img.dtype == CSEG_U8) {
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(img.data) + base;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (cx + e >= 0 && cx + e < w.w) v[e] = lut[c][src[(long long)(w.y + cx + e) * img.stride_x]];
+        } else {
+          const float* src = reinterpret_cast<const float*>(img.data) + base;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (cx + e >= 0 && cx + e < w.w) v[e] = src[(long long)(w.y + cx + e) * img.stride_x];
+        }
+      }
+    }
+    uint4 pk;
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+    pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+    pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+    reinterpret_cast<uint4*>(out)[idx] = pk;
+  }
+}
+
 // text tower stem (open_clip/model.py:291-293): out[r] = table[idx[r]] + pos[r % L]; pos == nullptr: plain row gather
 // (the EOT-token pick of model.py:302-304)
 __global__ void gather_rows_kernel(const float* __restrict__ table, const long long* __restrict__ idx,
@@ -77,6 +124,23 @@ __global__ void embed_tokens_kernel(const float* __restrict__ pe, const float* _
     const int crop = (int)(row / L);
     const float v = (t == 0) ? cls[c] : pe[((size_t)crop * (L - 1) + (t - 1)) * width + c];
     x[idx] = v + pos[(size_t)t * width + c];
+  }
+}
+// width % 4 == 0: float4 per thread
+__global__ void embed_tokens_vec4_kernel(const float4* __restrict__ pe, const float4* __restrict__ cls,
+                                         const float4* __restrict__ pos, int n_crops, int L, int w4,
+                                         float4* __restrict__ x) {
+  pdl_grid_sync();
+  const long long total = (long long)n_crops * L * w4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % w4);
+    const long long row = idx / w4;
+    const int t = (int)(row % L);
+    const int crop = (int)(row / L);
+    const float4 v = (t == 0) ? __ldg(cls + c) : pe[((size_t)crop * (L - 1) + (t - 1)) * w4 + c];
+    const float4 q = __ldg(pos + (size_t)t * w4 + c);
+    x[idx] = make_float4(v.x + q.x, v.y + q.y, v.z + q.z, v.w + q.w);
   }
 }
 
@@ -154,6 +218,55 @@ __global__ void __launch_bounds__(256) layernorm_reg_kernel(const float* x, int 
         u.y = *reinterpret_cast<uint32_t*>(&hi);
         reinterpret_cast<uint2*>(orow)[v] = u;
       }
+    }
+  }
+}
+
+// token assembly (transformer.py:565-571) + ln_pre (:574) in one pass: x[crop, t] = LN((t == 0 ? cls : pe[crop, t-1]) + pos[t]).
+// One warp per token row, the row in registers; same arithmetic order as embed_tokens followed by layernorm_reg.
+__global__ void __launch_bounds__(256) embed_ln_kernel(const float4* __restrict__ pe, const float4* __restrict__ cls,
+                                                       const float4* __restrict__ pos, int n_crops, int L, int width,
+                                                       const float4* __restrict__ gamma, const float4* __restrict__ beta,
+                                                       float eps, float4* __restrict__ x) {
+  pdl_grid_sync();
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= (long long)n_crops * L) return;
+  const int nv = width >> 2;
+  const int t = (int)(row % L);
+  const long long crop = row / L;
+  const float4* src = (t == 0) ? cls : pe + ((size_t)crop * (L - 1) + (t - 1)) * nv;
+  const float4* pr = pos + (size_t)t * nv;
+  float4 buf[LNV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < LNV; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nv) {
+      const float4 a = src[v], q = __ldg(pr + v);
+      buf[k] = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+      s += (buf[k].x + buf[k].y) + (buf[k].z + buf[k].w);
+    }
+  }
+  const float mean = warp_sum(s) / width;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < LNV; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nv) {
+      const float a = buf[k].x - mean, b = buf[k].y - mean, c = buf[k].z - mean, d = buf[k].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / width + eps);
+  float4* orow = x + (size_t)row * nv;
+#pragma unroll
+  for (int k = 0; k < LNV; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nv) {
+      const float4 g = __ldg(gamma + v), b = __ldg(beta + v);
+      orow[v] = make_float4((buf[k].x - mean) * rstd * g.x + b.x, (buf[k].y - mean) * rstd * g.y + b.y,
+                            (buf[k].z - mean) * rstd * g.z + b.z, (buf[k].w - mean) * rstd * g.w + b.w);
     }
   }
 }
@@ -419,6 +532,47 @@ __global__ void __launch_bounds__(256) simmap_kernel(const float* __restrict__ x
     }
 }
 
+// Tensor-core form of the similarity map: rows are L2-normalised (F.normalize, eps 1e-12) and written as a [hi | lo] bf16
+// split (hi = bf16(v), lo = bf16(v - hi)): hi.hi + hi.lo + lo.hi reproduces the fp32 dot product to ~2^-17 relative.
+// One warp per row, the row in registers.
+__global__ void __launch_bounds__(256) simmap_split_kernel(const float* __restrict__ x, long long rows, int width,
+                                                           bf16* __restrict__ xs) {
+  pdl_grid_sync();
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nv = width >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * width);
+  float4 buf[LNV];
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < LNV; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nv) {
+      buf[k] = xr[v];
+      q += (buf[k].x * buf[k].x + buf[k].y * buf[k].y) + (buf[k].z * buf[k].z + buf[k].w * buf[k].w);
+    }
+  }
+  const float inv = 1.0f / fmaxf(sqrtf(warp_sum(q)), 1e-12f);
+  uint2* hi = reinterpret_cast<uint2*>(xs + (size_t)row * 2 * width);
+  uint2* lo = reinterpret_cast<uint2*>(xs + (size_t)row * 2 * width + width);
+#pragma unroll
+  for (int k = 0; k < LNV; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nv) {
+      const float a[4] = {buf[k].x * inv, buf[k].y * inv, buf[k].z * inv, buf[k].w * inv};
+      bf16 h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        h[e] = __float2bfloat16_rn(a[e]);
+        l[e] = __float2bfloat16_rn(a[e] - __bfloat162float(h[e]));
+      }
+      hi[v] = *reinterpret_cast<const uint2*>(h);
+      lo[v] = *reinterpret_cast<const uint2*>(l);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // outlier_suppression.py:15-61,115-214, zero host syncs, two kernels:
 //   plan  (one CTA per crop): ratio_i = mean_h P[0,1+i] / (mean_h P[1+i,1+i] + 1e-8); top-k by repeated
@@ -638,7 +792,12 @@ int cseg_patchify(const cseg_image* img_desc, const int32_t* windows, int n_crop
   const int gh = crop_h / ps, gw = crop_w / ps;
   const long long total = (long long)n_crops * gh * gw * ldo;
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
-  if (out_dtype == CSEG_BF16)
+  if (out_dtype == CSEG_BF16 && ps % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)out & 15) == 0) {
+    const long long groups = total / 8;
+    const int vb = (int)std::min<long long>((groups + 255) / 256, (long long)sm_count() * 16);
+    cseg_launch(patchify_vec8_kernel, dim3(vb), dim3(256), 0, (cudaStream_t)stream, img, windows, n_crops, gh, gw, pad_top,
+                                                              pad_left, ps, (bf16*)out, ldo);
+  } else if (out_dtype == CSEG_BF16)
     cseg_launch(patchify_kernel<bf16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, img, windows, n_crops, gh, gw, pad_top,
                                                                     pad_left, ps, (bf16*)out, ldo);
   else
@@ -662,8 +821,28 @@ int cseg_embed_tokens(const float* pe, const float* cls, const float* pos, int n
   CSEG_REQUIRE(n_crops > 0 && L > 1 && width > 0, "embed_tokens: bad shape");
   const long long total = (long long)n_crops * L * width;
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
-  cseg_launch(embed_tokens_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, pe, cls, pos, n_crops, L, width, x);
+  if (width % 4 == 0 && (((uintptr_t)pe | (uintptr_t)cls | (uintptr_t)pos | (uintptr_t)x) & 15) == 0) {
+    const int vb = (int)std::min<long long>((total / 4 + 255) / 256, (long long)sm_count() * 16);
+    cseg_launch(embed_tokens_vec4_kernel, dim3(vb), dim3(256), 0, (cudaStream_t)stream, (const float4*)pe, (const float4*)cls,
+                                                                  (const float4*)pos, n_crops, L, width / 4, (float4*)x);
+  } else {
+    cseg_launch(embed_tokens_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, pe, cls, pos, n_crops, L, width, x);
+  }
   CSEG_LAUNCH_CHECK("embed_tokens");
+  return 0;
+}
+
+int cseg_embed_tokens_ln(const float* pe, const float* cls, const float* pos, int n_crops, int L, int width,
+                         const float* gamma, const float* beta, float eps, float* x, void* stream) {
+  CSEG_REQUIRE(n_crops > 0 && L > 1 && width > 0, "embed_tokens_ln: bad shape");
+  CSEG_REQUIRE(width % 4 == 0 && width <= 128 * LNV, "embed_tokens_ln: width=%d must be a multiple of 4 and <= %d", width, 128 * LNV);
+  CSEG_REQUIRE((((uintptr_t)pe | (uintptr_t)cls | (uintptr_t)pos | (uintptr_t)x | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0,
+               "embed_tokens_ln: pointers must be 16-byte aligned");
+  const long long rows = (long long)n_crops * L;
+  cseg_launch(embed_ln_kernel, dim3(cdiv(rows * 32, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)pe, (const float4*)cls,
+                                                                        (const float4*)pos, n_crops, L, width, (const float4*)gamma,
+                                                                        (const float4*)beta, eps, (float4*)x);
+  CSEG_LAUNCH_CHECK("embed_tokens_ln");
   return 0;
 }
 
@@ -702,6 +881,8 @@ static int launch_attention(const void* qkv, int n_crops, int L, int heads, int 
 
 int cseg_attention_tc(const bf16* qkv, int n_crops, int L, int heads, int head_dim, int mode, const float* simmap, bf16* out,
                       float* stats, cudaStream_t st);
+int cseg_gram_split_tc(const void* X, int ldx, int M, int width, int block_rows, int skip, float alpha, float* out,
+                       cudaStream_t st);
 
 extern "C" {
 
@@ -745,6 +926,18 @@ int cseg_simmap(const float* x, int n_crops, int L, int width, float temperature
   cseg_launch(simmap_kernel, dim3(grid), dim3(256), 0, st, x, L, width, 1.0f / temperature, add_self_similarity, simmap);
   CSEG_LAUNCH_CHECK("simmap");
   return 0;
+}
+
+int cseg_simmap_tc(const float* x, int n_crops, int L, int width, float temperature, void* scratch, float* simmap,
+                   void* stream) {
+  CSEG_REQUIRE(n_crops > 0 && L >= 2 && width > 0 && temperature != 0.f, "simmap_tc: bad arguments");
+  CSEG_REQUIRE(width % 64 == 0 && width <= 128 * LNV, "simmap_tc: width=%d must be a multiple of 64 and <= %d", width, 128 * LNV);
+  CSEG_REQUIRE((((uintptr_t)x | (uintptr_t)scratch) & 15) == 0, "simmap_tc: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long rows = (long long)n_crops * L;
+  cseg_launch(simmap_split_kernel, dim3(cdiv(rows * 32, 256)), dim3(256), 0, st, x, rows, width, (bf16*)scratch);
+  CSEG_LAUNCH_CHECK("simmap_split");
+  return cseg_gram_split_tc(scratch, 2 * width, (int)rows, width, L, 1, 1.0f / temperature, simmap, st);
 }
 
 int cseg_outlier_suppress(const float* y, float* y_out, int n_crops, int L, int width, int grid, const float* stats,

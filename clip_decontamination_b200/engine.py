@@ -180,8 +180,11 @@ class VisualEngine:
         pe = ws.get('pe', (n * P, width), f32)
         ops.gemm(patches, self.w_conv, pe)
         x = ws.get('x', (M, width), f32)
-        ops.embed_tokens(pe, self.cls_emb, self._pos_for(gh, gw, crop_h, crop_w), n, L, width, x)
-        ops.layernorm(x, *self.ln_pre, out=x)
+        if width % 4 == 0 and width <= 1280:
+            ops.embed_tokens_ln(pe, self.cls_emb, self._pos_for(gh, gw, crop_h, crop_w), n, L, width, *self.ln_pre, x)
+        else:
+            ops.embed_tokens(pe, self.cls_emb, self._pos_for(gh, gw, crop_h, crop_w), n, L, width, x)
+            ops.layernorm(x, *self.ln_pre, out=x)
         if taps is not None:
             taps['ln_pre'] = x.clone()
         h = ws.get('h', (M, width), cdt)
@@ -197,8 +200,10 @@ class VisualEngine:
         for idx in range(self.layers - 1):
             b = self.blocks[idx]
             if idx == mid_idx and use_sim:
-                ops.simmap(x, n, L, width, simmap, sim_cfg.get('temperature', 1.0),
-                           sim_cfg.get('add_self_similarity', True))
+                keep_diag = sim_cfg.get('add_self_similarity', True)
+                tc = cdt == torch.bfloat16 and keep_diag and width % 64 == 0 and width <= 1280
+                ops.simmap(x, n, L, width, simmap, sim_cfg.get('temperature', 1.0), keep_diag,
+                           scratch=ws.get('simmap_split', (M, 2 * width), cdt) if tc else None)
                 have_sim = True
             ops.layernorm(x, *b['ln1'], out=h)
             ops.gemm(h, b['w_in'], qkv, bias=b['b_in'])

@@ -127,6 +127,13 @@ def embed_tokens(pe, cls_emb, pos, n_crops, L, width, x):
     return x
 
 
+def embed_tokens_ln(pe, cls_emb, pos, n_crops, L, width, gamma, beta, x, eps: float = 1e-5):
+    """embed_tokens followed by ln_pre in one pass (same values)."""
+    check(lib.cseg_embed_tokens_ln(_ptr(pe), _ptr(cls_emb), _ptr(pos), n_crops, L, width, _ptr(gamma), _ptr(beta), eps,
+                                   _ptr(x), _stream()))
+    return x
+
+
 def layernorm(x: torch.Tensor, gamma, beta, out: torch.Tensor, eps: float = 1e-5):
     assert x.dtype == torch.float32
     rows, width = x.shape
@@ -174,8 +181,13 @@ def attention(qkv: torch.Tensor, n_crops: int, L: int, heads: int, head_dim: int
 
 
 def simmap(x: torch.Tensor, n_crops: int, L: int, width: int, out: torch.Tensor, temperature: float = 1.0,
-           add_self_similarity: bool = True):
+           add_self_similarity: bool = True, scratch: Optional[torch.Tensor] = None):
+    """scratch (bf16 [n_crops*L, 2*width]) selects the tensor-core form (hi/lo bf16 split, fp32-grade products)."""
     assert x.dtype == torch.float32 and out.dtype == torch.float32
+    if scratch is not None:
+        assert add_self_similarity and scratch.dtype == torch.bfloat16 and scratch.numel() >= n_crops * L * 2 * width
+        check(lib.cseg_simmap_tc(_ptr(x), n_crops, L, width, temperature, _ptr(scratch), _ptr(out), _stream()))
+        return out
     check(lib.cseg_simmap(_ptr(x), n_crops, L, width, temperature, int(add_self_similarity), _ptr(out), _stream()))
     return out
 

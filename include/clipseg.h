@@ -97,6 +97,11 @@ CSEG_API int cseg_gather_rows(const float* table, const long long* idx, const fl
 /* x[crop*L + t] = (t == 0 ? class_embedding : patch_embed[crop*P + t-1]) + pos[t]   (:565-571) */
 CSEG_API int cseg_embed_tokens(const float* patch_embed, const float* class_embedding, const float* pos,
                       int n_crops, int L, int width, float* x, void* stream);
+/* the same followed by ln_pre (:574) in one pass over the rows: x = LayerNorm(tokens + pos) with fp32 statistics
+ * (width % 4 == 0, 16-byte aligned pointers); equals cseg_embed_tokens + in-place cseg_layernorm bit for bit. */
+CSEG_API int cseg_embed_tokens_ln(const float* patch_embed, const float* class_embedding, const float* pos,
+                         int n_crops, int L, int width, const float* gamma, const float* beta, float eps,
+                         float* x, void* stream);
 /* LayerNormFp32 (open_clip/transformer.py:17-23): fp32 statistics, output in out_dtype.
  * `x` and `out` may alias when out_dtype == CSEG_F32. */
 CSEG_API int cseg_layernorm(const float* x, int rows, int width, const float* gamma, const float* beta,
@@ -136,6 +141,12 @@ CSEG_API int cseg_attention(int dtype, const void* qkv, int n_crops, int L, int 
  * residual stream x [n_crops*L, width] (CLS row skipped): M [n_crops, L-1, L-1] fp32. */
 CSEG_API int cseg_simmap(const float* x, int n_crops, int L, int width, float temperature,
                 int add_self_similarity, float* simmap, void* stream);
+/* the same map (add_self_similarity = true) on the tensor cores: rows are normalised and split into bf16 [hi | lo]
+ * (scratch: bf16 [n_crops*L, 2*width], 16-byte aligned), then ONE block-diagonal tcgen05 GEMM accumulates
+ * hi.hi + hi.lo + lo.hi in fp32 and stores the per-crop blocks compactly.  |difference to cseg_simmap| <= 2e-5 / temperature.
+ * width % 64 == 0. */
+CSEG_API int cseg_simmap_tc(const float* x, int n_crops, int L, int width, float temperature, void* scratch,
+                   float* simmap, void* stream);
 /* detect_outliers_by_attention + OutlierSuppressionModule.mean_interpolation
  * (outlier_suppression.py:15-61,115-214): y [n_crops*L, width] fp32 -> y_out (same shape, OUT OF PLACE,
  * CLS row copied).  grid x grid patches, stats from cseg_attention.  plan: int32 workspace of

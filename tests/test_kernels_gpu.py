@@ -161,6 +161,33 @@ def test_layernorm_and_embed(ops):
     assert (o16.float().cpu() - refln).abs().max().item() < 3e-2
     ops.layernorm(x, gam.cuda(), bet.cuda(), x)          # in place, fp32: 1e-5
     assert (x.cpu() - refln).abs().max().item() < 1e-5
+    x2 = torch.empty_like(x)                             # token assembly + ln_pre in one pass: bit-identical
+    ops.embed_tokens_ln(pe.cuda(), cls.cuda(), pos.cuda(), n, L, w, gam.cuda(), bet.cuda(), x2)
+    assert torch.equal(x2, x)
+
+
+@pytest.mark.parametrize('layout', ['chw', 'hwc', 'f32'])
+def test_patchify_bf16_vector_path(ops, layout):
+    """The 8-columns-per-thread bf16 kernel (table-normalised uint8 input) equals the scalar fp32 kernel rounded to bf16,
+    including windows that leave the image on the padded side (pad_top / pad_left) and the zero columns up to ldo."""
+    H, W, ps, ch, cw, pt, pl = 300, 280, 16, 208, 160, 4, 3
+    rng = np.random.default_rng(3)
+    u8 = torch.from_numpy(rng.integers(0, 256, (1, H, W, 3), dtype=np.uint8)).cuda()
+    mean, std = [122.771, 116.746, 104.094], [68.501, 66.632, 70.323]
+    if layout == 'hwc':
+        img = ops.Image.u8(u8, 'hwc', mean, std)
+    elif layout == 'chw':
+        img = ops.Image.u8(u8.permute(0, 3, 1, 2).contiguous(), 'chw', mean, std)
+    else:
+        img = ops.Image.normalised(torch.randn(3, H, W, generator=_g(9)).cuda())
+    wh, ww = ch - 2 * pt - 1, cw - 2 * pl
+    wins = torch.tensor([(0, 0, wh, ww), (H - wh, W - ww, wh, ww), (17, 31, wh, ww)], dtype=torch.int32).cuda()
+    rows = 3 * (ch // ps) * (cw // ps)
+    ref = torch.empty((rows, 832), device='cuda')
+    ops.patchify(img, wins, ch, cw, pt, pl, ps, ref)
+    got = torch.full((rows, 832), 7.0, device='cuda', dtype=torch.bfloat16)
+    ops.patchify(img, wins, ch, cw, pt, pl, ps, got)
+    assert torch.equal(got, ref.to(torch.bfloat16))
 
 
 # ------------------------------------------------------------------ attention ---------------------
@@ -254,6 +281,21 @@ def test_simmap(ops):
     ops.simmap(x.cuda(), n, L, w, out, temperature=2.0, add_self_similarity=False)
     ref2 = O.similarity_map(x.view(n, L, w)[:, 1:], 2.0, False)
     assert (out.cpu() - ref2).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize('n,L,w,temp', [(3, 197, 768, 1.0), (7, 197, 192, 2.0), (5, 50, 64, 0.5), (2, 257, 1024, 1.0)])
+def test_simmap_tensor_core(ops, n, L, w, temp):
+    """Tensor-core similarity map (normalised rows split into bf16 hi | lo, one block-diagonal tcgen05 GEMM with fp32
+    accumulation, compact per-crop store) against the fp32 oracle: 2e-5 / temperature; rows with a large common offset
+    (the residual stream's outlier channels) included."""
+    x = torch.randn(n * L, w, generator=_g(11))
+    x[:, 3] += 40.0
+    x[::7] *= 25.0
+    ref = O.similarity_map(x.view(n, L, w)[:, 1:], temp)
+    out = torch.full((n, L - 1, L - 1), 7.0, device='cuda')
+    scratch = torch.empty((n * L, 2 * w), device='cuda', dtype=torch.bfloat16)
+    ops.simmap(x.cuda(), n, L, w, out, temperature=temp, scratch=scratch)
+    assert (out.cpu() - ref).abs().max().item() < 2e-5 / temp
 
 
 @pytest.mark.parametrize('grid,top_k', [(14, 30), (16, 10), (5, 25)])
