@@ -327,7 +327,8 @@ def main():
     orig = {}
 
     # kernel classes: the shared-kernel entry points belong to the class of the op they implement
-    CLASS = dict(jbu_apply_shared='jbu_apply', jbu_composite_image='jbu_apply', jbu_range_kernel_border='jbu_range_kernel')
+    CLASS = dict(jbu_apply_shared='jbu_apply', jbu_composite_image='jbu_apply', jbu_range_kernel_border='jbu_range_kernel',
+                 attention_experimental_tc='attention', gemm_blockdiag='gemm')
 
     def wrap(name, fn, workfn=None):
         cname = CLASS.get(name, name)
@@ -365,6 +366,12 @@ def main():
     def attn_work(qkv, n, L, heads, hd, mode, out, **k):
         return ('tensor', (4.0 if mode == 0 else 6.0) * n * heads * L * L * hd)
 
+    def gemm_bd_work(A, B, out, block_rows):
+        return ('tensor', 2.0 * A.shape[0] * block_rows * A.shape[1])       # the diagonal blocks only
+
+    def attn_exp_work(qkv, n, L, heads, out, *a, **k):
+        return ('tensor', 6.0 * n * heads * L * L * 64)
+
     def nsim_work(feats, ldf, n, hw, D, text, logits, cls_logit_bias=None):
         return ('hbm', float(n * hw * (D * esize + text.shape[0] * 4)))
 
@@ -393,8 +400,10 @@ def main():
     workfns = dict(jbu_kernel_fixup=kfix_work, basis_logits=basis_work, fixup_norm_sim=fns_work, gemm=gemm_work,
                    jbu_apply=apply_work, attention=attn_work, norm_sim=nsim_work, accum_argmax=accum_work,
                    jbu_range_kernel=rk_work, layernorm=ln_work, simmap=simmap_work, jbu_apply_shared=apply_shared_work,
-                   jbu_composite_image=comp_img_work, jbu_range_kernel_border=rkb_work)
-    names = ['preprocess_u8', 'patchify', 'embed_tokens', 'layernorm', 'gemm', 'attention', 'simmap', 'outlier_suppress',
+                   jbu_composite_image=comp_img_work, jbu_range_kernel_border=rkb_work,
+                   attention_experimental_tc=attn_exp_work, gemm_blockdiag=gemm_bd_work)
+    names = ['preprocess_u8', 'patchify', 'embed_tokens', 'embed_tokens_ln', 'layernorm', 'gemm', 'gemm_blockdiag', 'attention',
+             'attention_experimental_tc', 'simmap', 'outlier_suppress',
              'cls_debias', 'jbu_guidance', 'jbu_range_proj', 'jbu_guidance_proj', 'jbu_range_kernel', 'jbu_kernel_fixup',
              'jbu_apply', 'jbu_apply_shared', 'jbu_composite_image', 'jbu_range_kernel_border', 'norm_sim', 'fixup_norm_sim',
              'basis_logits', 'accum_argmax', 'iou_hist']

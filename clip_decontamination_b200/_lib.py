@@ -57,7 +57,8 @@ SIGNATURES = {
     'cseg_gemm_reference': (_i, [_i, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _f, _i, _i, _p, _i, _p]),
     'cseg_attention': (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _f, _p, _p, _p]),
     'cseg_simmap': (_i, [_p, _i, _i, _i, _f, _i, _p, _p]),
-    'cseg_simmap_tc': (_i, [_p, _i, _i, _i, _f, _p, _p, _p]),
+    'cseg_simmap_tc': (_i, [_p, _i, _i, _i, _f, _p, _p, _i, _p]),
+    'cseg_attention_experimental_tc': (_i, [_p, _i, _i, _i, _p, _f, _p, _p]),
     'cseg_outlier_suppress': (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _i, _f, _p, _p, _p]),
     'cseg_cls_debias': (_i, [_p, _i, _i, _i, _f, _i, _p, _i, _i, _p, _p]),
     'cseg_jbu_guidance': (_i, [_img, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),

@@ -233,9 +233,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         {
           uint32_t ra[16], rb[16];
           auto red = [&](const uint32_t (&r)[16], int c) {
+            if (c + 16 <= L) {               // warp-uniform: only the chunk that holds key L needs per-element masks
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (c + e < L) m = fmaxf(m, __uint_as_float(r[e]));
+              for (int e = 0; e < 16; ++e) m = fmaxf(m, __uint_as_float(r[e]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (c + e < L) m = fmaxf(m, __uint_as_float(r[e]));
+            }
           };
           tmem_ld16_nowait(ts + c_begin, ra);
 #pragma unroll 1
@@ -262,10 +267,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           uint32_t ra[16], rb[16];
           auto expo = [&](const uint32_t (&r)[16], int c) {
             float ev[16];
+            if (c + 16 <= L) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              ev[e] = (c + e < L) ? at_ex2(fmaf(__uint_as_float(r[e]), scale_log2e, -msc)) : 0.f;
-              sum += ev[e];
+              for (int e = 0; e < 16; ++e) {
+                ev[e] = at_ex2(fmaf(__uint_as_float(r[e]), scale_log2e, -msc));
+                sum += ev[e];
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                ev[e] = (c + e < L) ? at_ex2(fmaf(__uint_as_float(r[e]), scale_log2e, -msc)) : 0.f;
+                sum += ev[e];
+              }
             }
             uint8_t* pb = prow + (c >> 6) * AT_P_BLK;
             const int j = (c & 63) >> 3;                                   // 16-byte chunk within the 128-byte row (even)
@@ -287,6 +300,281 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               expo(rb, c + 16);
             }
           }
+        }
+        ssum[(qi & 1) * 512 + hh * 128 + row] = sum;
+        tc_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(p_full);
+          mbar_arrive(s_empty + sb * 8);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * AT_SMW) : "memory");
+        have_prev = true;
+        prev_pi = qi;
+        prev_row0 = crop * L + t * AT_BM;
+        prev_head = head;
+        prev_valid = min(AT_BM, L - t * AT_BM);
+      }
+    }
+    if (have_prev) epilogue();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == AT_SMW + 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)AT_TMEM_COLS) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Final block, model_type 'Experimental' (open_clip/transformer.py:897-903) on the same pipeline:
+//   P = softmax(softmax((k k^T + q q^T) / 8) + w * M_pad),  out = P v
+// S: 8 MMAs per 128-query tile (K_tile . K^T, then Q_tile . Q^T into the same accumulator); the A operand of a tile is a
+// row window of the 208-row K / Q buffer that also serves as the B operand.  Three passes over S in TMEM: (1) row max,
+// (2) first-softmax sum + row max of w * M (the similarity map, zero CLS row / column), (3) second softmax numerators
+// exp(p1 + w M - (max(w M, 0) + 1)) -- the offset is within 1 of the true row maximum, so nothing over- or underflows --
+// written as bf16 P.  Row statistics of the four key quarters are exchanged through shared memory.
+// smem: Q-all x2, K-all x2, V x1 (V of the next item is only needed one softmax later), P, reductions.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int AX_QK_OFF = 0, AX_V_OFF = 4 * AT_KV_BYTES, AX_P_OFF = 5 * AT_KV_BYTES, AX_RED_OFF = AX_P_OFF + AT_P_BYTES;
+constexpr int AX_RED_BYTES = (3 * 4 * 128 + 2 * 4 * 128) * 4;   // smax[4][128], ssum1[4][128], smaxm[4][128], ssum[2][4][128]
+constexpr int AX_BAR_OFF = AX_RED_OFF + AX_RED_BYTES, AX_NBARS = 13;
+constexpr int AX_SMEM = AX_BAR_OFF + AX_NBARS * 8 + 16 + 1024;
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_tc_exp_kernel(const __grid_constant__ CUtensorMap tmKV, int L, int heads, int n_items, bf16* __restrict__ out,
+                        float scale_log2e, const float* __restrict__ simmap, float simw) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  float* smax = reinterpret_cast<float*>(smem + AX_RED_OFF);           // [4][128]
+  float* ssum1 = smax + 4 * 128;                                       // [4][128]
+  float* smaxm = ssum1 + 4 * 128;                                      // [4][128]
+  float* ssum = smaxm + 4 * 128;                                       // [2][4][128]
+  uint64_t* bars = (uint64_t*)(smem + AX_BAR_OFF);
+  uint32_t* tmem_slot = (uint32_t*)(bars + AX_NBARS);
+  const uint32_t b0 = smem_u32(bars);
+  const uint32_t qk_full = b0, qk_empty = b0 + 16, v_full = b0 + 32, v_empty = b0 + 40, s_full = b0 + 48, s_empty = b0 + 64;
+  const uint32_t p_full = b0 + 80, o_full = b0 + 88, o_empty = b0 + 96;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int width = heads * AT_HD, mt = (L + AT_BM - 1) / AT_BM;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKV) : "memory");
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(qk_full + i * 8, 1);
+      mbar_init(qk_empty + i * 8, 1);
+      mbar_init(s_full + i * 8, 1);
+      mbar_init(s_empty + i * 8, AT_SMW);
+    }
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    mbar_init(p_full, AT_SMW);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, AT_SMW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == AT_SMW + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)AT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_grid_sync();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == AT_SMW) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      uint32_t ki = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ki) {
+        const int crop = item / heads, head = item - crop * heads;
+        const uint32_t kb = ki & 1, kph = (ki >> 1) & 1;
+        mbar_wait(qk_empty + kb * 8, kph ^ 1);
+        mbar_expect_tx(qk_full + kb * 8, 2 * AT_KV_BYTES);
+        tma_load_2d(sbase + AX_QK_OFF + (2 * kb) * AT_KV_BYTES, &tmKV, qk_full + kb * 8, head * AT_HD, crop * L);
+        tma_load_2d(sbase + AX_QK_OFF + (2 * kb + 1) * AT_KV_BYTES, &tmKV, qk_full + kb * 8, width + head * AT_HD, crop * L);
+        mbar_wait(v_empty, (ki & 1) ^ 1);
+        mbar_expect_tx(v_full, AT_KV_BYTES);
+        tma_load_2d(sbase + AX_V_OFF, &tmKV, v_full, 2 * width + head * AT_HD, crop * L);
+      }
+    }
+  } else if (warp == AT_SMW + 1) {
+    // ---------------- MMA issuer: S of tile i is issued before P.V of tile i-1 ----------------
+    constexpr uint32_t idesc_s = make_idesc(AT_BM, AT_LP), idesc_pv = at_idesc_pv();
+    uint32_t qi = 0, ki = 0;
+    bool have_prev = false;
+    uint32_t prev_pi = 0, prev_ki = 0;
+    bool prev_first = false, prev_last = false;
+    auto issue_pv = [&]() {
+      mbar_wait(p_full, prev_pi & 1);
+      mbar_wait(o_empty, (prev_pi & 1) ^ 1);
+      if (prev_first) mbar_wait(v_full, prev_ki & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < AT_LP / 16; ++j) {
+          const uint64_t adesc = make_sdesc(sbase + AX_P_OFF + (j >> 2) * AT_P_BLK + (j & 3) * 32);
+          const uint64_t bdesc = at_mn_desc(sbase + AX_V_OFF + j * 2048);
+          umma_f16(tmem_base + AT_O_COL, adesc, bdesc, idesc_pv, j > 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        if (prev_last) umma_commit(v_empty);
+      }
+      __syncwarp();
+    };
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ki) {
+      const uint32_t kb = ki & 1, kph = (ki >> 1) & 1;
+      for (int t = 0; t < mt; ++t, ++qi) {
+        const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+        if (t == 0) mbar_wait(qk_full + kb * 8, kph);
+        mbar_wait(s_empty + qb * 8, qph ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int mat = 1; mat >= 0; --mat) {                       // k k^T first, then q q^T (transformer.py:897-899)
+            const uint32_t mbase = sbase + AX_QK_OFF + (2 * kb + mat) * AT_KV_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < AT_HD / 16; ++ks) {
+              const uint64_t adesc = make_sdesc(mbase + t * AT_Q_BYTES + ks * 32);
+              const uint64_t bdesc = make_sdesc(mbase + ks * 32);
+              umma_f16(tmem_base + qb * AT_S_COLS, adesc, bdesc, idesc_s, (mat == 0 || ks > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(s_full + qb * 8);
+          if (t == mt - 1) umma_commit(qk_empty + kb * 8);
+        }
+        __syncwarp();
+        if (have_prev) issue_pv();
+        have_prev = true;
+        prev_pi = qi;
+        prev_ki = ki;
+        prev_first = (t == 0);
+        prev_last = (t == mt - 1);
+      }
+    }
+    if (have_prev) issue_pv();
+  } else {
+    // ---------------- softmax + epilogue ----------------
+    const int q4 = warp & 3, hh = warp >> 2, row = q4 * 32 + lane;         // hh: key quarter
+    const int c_begin = at_qbegin(hh), c_end = at_qbegin(hh + 1);
+    const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    uint8_t* prow = smem + AX_P_OFF + row * 128;
+    const float LOG2E = 1.4426950408889634f;
+    uint32_t qi = 0;
+    bool have_prev = false;
+    uint32_t prev_pi = 0;
+    int prev_row0 = 0, prev_head = 0, prev_valid = 0;
+    auto epilogue = [&]() {
+      mbar_wait(o_full, prev_pi & 1);
+      tc_fence_after();
+      uint32_t r[16];
+      tmem_ld16(tlane + AT_O_COL + hh * 16, r);
+      const float* ss = ssum + (prev_pi & 1) * 512;
+      const float inv = 1.0f / ((ss[row] + ss[128 + row]) + (ss[256 + row] + ss[384 + row]));
+      if (row < prev_valid) {
+        uint4* o = reinterpret_cast<uint4*>(out + (size_t)(prev_row0 + row) * width + prev_head * AT_HD + hh * 16);
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          uint4 w;
+          w.x = at_pack(__uint_as_float(r[8 * v]) * inv, __uint_as_float(r[8 * v + 1]) * inv);
+          w.y = at_pack(__uint_as_float(r[8 * v + 2]) * inv, __uint_as_float(r[8 * v + 3]) * inv);
+          w.z = at_pack(__uint_as_float(r[8 * v + 4]) * inv, __uint_as_float(r[8 * v + 5]) * inv);
+          w.w = at_pack(__uint_as_float(r[8 * v + 6]) * inv, __uint_as_float(r[8 * v + 7]) * inv);
+          o[v] = w;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    };
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int crop = item / heads, head = item - crop * heads;
+      for (int t = 0; t < mt; ++t, ++qi) {
+        const uint32_t sb = qi & 1, sph = (qi >> 1) & 1;
+        const int tok = t * AT_BM + row;                                      // token index of this thread's query row
+        // similarity row of this query: M_pad[tok][j] = M[tok-1][j-1] for tok, j >= 1, else 0 (similarity_enhancement.py:104-107)
+        // (layout 1 of cseg_simmap_tc: [crop][token / 32][key][token % 32]: a warp's 32 rows of one key are one 128-byte line;
+        // the CLS row / column hold zeros, rows beyond L are never used: they read row 0)
+        const bool has_sim = simmap != nullptr;                                  // uniform
+        const int tokc = tok < L ? tok : 0;
+        const float* mrow = has_sim ? simmap + (size_t)crop * CSEG_SIMT_FLOATS + (size_t)(tokc >> 5) * (CSEG_SIMT_COLS * 32) + (tokc & 31)
+                                    : nullptr;
+        mbar_wait(s_full + sb * 8, sph);
+        tc_fence_after();
+        const uint32_t ts = tlane + sb * AT_S_COLS;
+        uint32_t r[16];
+        // pass 1: row maximum of S
+        float m = -INFINITY;
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; c += 16) {
+          tmem_ld16(ts + c, r);
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (c + e < L) m = fmaxf(m, __uint_as_float(r[e]));
+        }
+        smax[hh * 128 + row] = m;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * AT_SMW) : "memory");
+        m = fmaxf(fmaxf(smax[row], smax[128 + row]), fmaxf(smax[256 + row], smax[384 + row]));
+        if (have_prev) epilogue();       // P.V of the previous tile has completed: the P buffer is free
+        // pass 2: sum of the first softmax, row maximum of w * M
+        const float msc = m * scale_log2e;
+        float sum1 = 0.f, mm = 0.f;       // M_pad holds zeros (CLS column): 0 takes part in the maximum
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; c += 16) {
+          float mv[16];                   // all 16 loads in flight before the TMEM wait (one coalesced line per key)
+          if (has_sim) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) mv[e] = __ldg(mrow + (c + e) * 32);
+          }
+          tmem_ld16(ts + c, r);
+          if (c + 16 <= L) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sum1 += at_ex2(fmaf(__uint_as_float(r[e]), scale_log2e, -msc));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (c + e < L) sum1 += at_ex2(fmaf(__uint_as_float(r[e]), scale_log2e, -msc));
+          }
+          if (has_sim) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (c + e < L) mm = fmaxf(mm, simw * mv[e]);
+          }
+        }
+        ssum1[hh * 128 + row] = sum1;
+        smaxm[hh * 128 + row] = mm;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * AT_SMW) : "memory");
+        const float inv1 = 1.0f / ((ssum1[row] + ssum1[128 + row]) + (ssum1[256 + row] + ssum1[384 + row]));
+        const float off = (fmaxf(fmaxf(smaxm[row], smaxm[128 + row]), fmaxf(smaxm[256 + row], smaxm[384 + row])) + 1.0f) * LOG2E;
+        // pass 3: P = exp(p1 + w M - offset) as bf16 in the K-major SWIZZLE_128B layout, row sum in fp32
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; c += 16) {
+          float ev[16];
+          if (has_sim) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) ev[e] = simw * __ldg(mrow + (c + e) * 32);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) ev[e] = 0.f;
+          }
+          tmem_ld16(ts + c, r);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float tt = fmaf(at_ex2(fmaf(__uint_as_float(r[e]), scale_log2e, -msc)), inv1, ev[e]);
+            const float v = at_ex2(fmaf(tt, LOG2E, -off));
+            ev[e] = (c + e < L) ? v : 0.f;
+            sum += ev[e];
+          }
+          uint8_t* pb = prow + (c >> 6) * AT_P_BLK;
+          const int j = (c & 63) >> 3;                                   // 16-byte chunk within the 128-byte row (even)
+          uint4 w0, w1;
+          w0.x = at_pack(ev[0], ev[1]);   w0.y = at_pack(ev[2], ev[3]);   w0.z = at_pack(ev[4], ev[5]);   w0.w = at_pack(ev[6], ev[7]);
+          w1.x = at_pack(ev[8], ev[9]);   w1.y = at_pack(ev[10], ev[11]); w1.z = at_pack(ev[12], ev[13]); w1.w = at_pack(ev[14], ev[15]);
+          *reinterpret_cast<uint4*>(pb + ((j ^ (row & 7)) << 4)) = w0;
+          *reinterpret_cast<uint4*>(pb + (((j + 1) ^ (row & 7)) << 4)) = w1;
         }
         ssum[(qi & 1) * 512 + hh * 128 + row] = sum;
         tc_fence_before();
@@ -353,9 +641,10 @@ bool at_enabled() {   // CSEG_ATTN_TC=0 selects the mma.sync kernel (A/B measure
 }  // namespace
 
 // returns 1 when the case is not covered (the caller falls back to the mma.sync kernel)
-int cseg_attention_tc(const bf16* qkv, int n_crops, int L, int heads, int head_dim, int mode, const float* simmap, bf16* out,
-                      float* stats, cudaStream_t st) {
-  if (!at_enabled() || head_dim != AT_HD || mode != CSEG_ATTN_STD || stats != nullptr || simmap != nullptr) return 1;
+int cseg_attention_tc(const bf16* qkv, int n_crops, int L, int heads, int head_dim, int mode, const float* simmap, float simw,
+                      bf16* out, float* stats, cudaStream_t st) {
+  if (!at_enabled() || head_dim != AT_HD || stats != nullptr) return 1;
+  if (mode != CSEG_ATTN_STD || simmap != nullptr) return 1;
   if (L < 17 || L > AT_LP || ((uintptr_t)qkv & 15) != 0 || ((uintptr_t)out & 15) != 0) return 1;
   const int width = heads * AT_HD;
   CUtensorMap tq, tkv;
@@ -372,5 +661,22 @@ int cseg_attention_tc(const bf16* qkv, int n_crops, int L, int heads, int head_d
   }
   cseg_launch(attention_tc_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tq, tkv, L, heads, items, out, scale_log2e, diag);
   CSEG_LAUNCH_CHECK("attention_tc");
+  return 0;
+}
+
+extern "C" int cseg_attention_experimental_tc(const void* qkv, int n_crops, int L, int heads, const float* simmap_t,
+                                              float sim_weight, void* out, void* stream) {
+  static_assert(AT_LP == CSEG_SIMT_COLS, "the padded key count is the column count of the transposed similarity map");
+  CSEG_REQUIRE(n_crops > 0 && heads > 0 && L >= 17 && L <= AT_LP, "attention_experimental_tc: n_crops=%d heads=%d L=%d", n_crops,
+               heads, L);
+  CSEG_REQUIRE((((uintptr_t)qkv | (uintptr_t)out) & 15) == 0, "attention_experimental_tc: pointers must be 16-byte aligned");
+  const int width = heads * AT_HD;
+  CUtensorMap tkv;
+  if (int rc = at_make_map(&tkv, qkv, (long long)n_crops * L, 3 * width, AT_LP)) return rc;
+  CSEG_SET_SMEM(attention_tc_exp_kernel, AX_SMEM);
+  const int items = n_crops * heads;
+  cseg_launch(attention_tc_exp_kernel, dim3(std::min(items, sm_count())), dim3(AT_THREADS), AX_SMEM, (cudaStream_t)stream, tkv, L, heads,
+              items, (bf16*)out, 0.125f * 1.4426950408889634f, simmap_t, sim_weight);
+  CSEG_LAUNCH_CHECK("attention_tc_exp");
   return 0;
 }

@@ -37,7 +37,7 @@ struct EpiParams {
   // RES == 3 (compact block-diagonal store, fp32): element (block b, i, j) goes to C[b * cmp_cs + (i - cmp_skip) * cmp_rs +
   // (j - cmp_skip)] for i, j >= cmp_skip; entries that pair rows of different blocks are dropped
   long long cmp_cs;
-  int cmp_rs, cmp_skip;
+  int cmp_rs, cmp_skip, cmp_mode;
   // > 0: both operands are [hi | lo] bf16 splits of split_kb k-blocks each and the K loop runs hi.hi + hi.lo + lo.hi
   // (three segments of split_kb k-blocks): fp32-grade products on the bf16 tensor cores
   int split_kb;
@@ -322,8 +322,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             for (int rr = 0; rr < 32; ++rr) {
               if (rr < nrows) {
                 const int j = col - blk * Lb;
-                if (i >= skip && j >= skip && j < Lb)
-                  cf[(size_t)blk * ep.cmp_cs + (size_t)(i - skip) * ep.cmp_rs + (j - skip)] = stg[rr * SST + lane] * alpha;
+                if (i >= skip && j >= skip && j < Lb) {
+                  // cmp_mode 1: row blocks of 32, column-major inside a block ([i / 32][j][i % 32], cmp_rs columns per block)
+                  const size_t o = ep.cmp_mode == 0 ? (size_t)(i - skip) * ep.cmp_rs + (j - skip)
+                                                    : ((size_t)(i >> 5) * ep.cmp_rs + j) * 32 + (i & 31);
+                  cf[(size_t)blk * ep.cmp_cs + o] = stg[rr * SST + lane] * alpha;
+                }
               }
               if (++i == Lb) { i = 0; ++blk; }
             }
@@ -1200,21 +1204,30 @@ int cseg_jbu_kernel_fixup_tc(const void* k, int lda, const void* W0, int ldw0, c
 }
 
 // Per-block Gram matrices of fp32-grade accuracy on the bf16 tensor cores: X is the [hi | lo] bf16 split of a row-normalised
-// fp32 matrix ([M, 2 * width], width % 64 == 0); out[b, i - skip, j - skip] = alpha * <x_(b,i), x_(b,j)> for the square diagonal
-// blocks of block_rows rows, compact fp32 [n_blocks, block_rows - skip, block_rows - skip] (the similarity map layout).
+// fp32 matrix ([M, 2 * width], width % 64 == 0); value(b, i, j) = alpha * <x_(b,i), x_(b,j)> for the square diagonal blocks
+// of block_rows rows and i, j >= skip.
+//   layout 0: compact fp32 [n_blocks, block_rows - skip, block_rows - skip] (the similarity map layout)
+//   layout 1: fp32 [n_blocks, ceil(cols_pad / 32), cols_pad, 32] indexed [b][i / 32][j][i % 32] with UNSHIFTED i, j (entries with
+//             i < skip or j < skip are never written): what a TMEM-row-per-lane consumer reads with coalesced loads
 int cseg_gram_split_tc(const void* X, int ldx, int M, int width, int block_rows, int skip, float alpha, float* out,
-                       cudaStream_t st) {
+                       int layout, int cols_pad, cudaStream_t st) {
   CSEG_REQUIRE(M > 0 && width > 0 && width % BK == 0 && ldx % 8 == 0 && ldx >= 2 * width, "gram_split: M=%d width=%d ldx=%d", M,
                width, ldx);
   CSEG_REQUIRE(block_rows > skip && skip >= 0 && M % block_rows == 0, "gram_split: M=%d block_rows=%d skip=%d", M, block_rows, skip);
   CSEG_REQUIRE(((uintptr_t)X & 15) == 0, "gram_split: operand must be 16-byte aligned");
+  CSEG_REQUIRE(layout == 0 || (layout == 1 && cols_pad >= block_rows), "gram_split: layout=%d cols_pad=%d", layout, cols_pad);
   CUtensorMap ta, tb;
   int rc = make_map(&ta, X, M, 2 * width, ldx, BM);
   if (rc) return rc;
   rc = make_map(&tb, X, M, 2 * width, ldx, 128);
   if (rc) return rc;
   const int P = block_rows - skip;
-  EpiParams ep{nullptr, nullptr, 0, 0, alpha, CSEG_ACT_NONE, 0, out, 0, M, M, block_rows, (long long)P * P, P, skip, width / BK};
+  EpiParams ep{nullptr, nullptr, 0, 0, alpha, CSEG_ACT_NONE, 0, out, 0, M, M, block_rows, (long long)P * P, P, skip, 0, width / BK};
+  if (layout == 1) {
+    ep.cmp_mode = 1;
+    ep.cmp_rs = cols_pad;
+    ep.cmp_cs = (long long)((cols_pad + 31) / 32) * cols_pad * 32;
+  }
   return launch3<128, 4, CSEG_ACT_NONE, 0, 3>(ta, tb, M, M, 3 * width, ep, st);
 }
 
@@ -1250,7 +1263,7 @@ int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int
   if (rc) return rc;
   rc = make_map(&tb, B, N, K, ldb, bn);
   if (rc) return rc;
-  EpiParams ep{bias, residual, ldr, res_dtype == CSEG_BF16, alpha, act, out_dtype == CSEG_BF16, C, ldc, M, N, diag_rows, 0, 0, 0, 0};
+  EpiParams ep{bias, residual, ldr, res_dtype == CSEG_BF16, alpha, act, out_dtype == CSEG_BF16, C, ldc, M, N, diag_rows, 0, 0, 0, 0, 0};
   if (bn == 64) return launch<64, 6>(ta, tb, M, N, K, ep, st);
   if (bn == 192) return launch<192, 4>(ta, tb, M, N, K, ep, st);
   if (bn == 256) return launch<256, 3>(ta, tb, M, N, K, ep, st);

@@ -53,7 +53,8 @@ class Workspace:
         self._bufs: Dict[str, torch.Tensor] = {}
         self.generation = 0
 
-    def get(self, name: str, shape: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
+    def get(self, name: str, shape: Sequence[int], dtype: torch.dtype, zero: bool = False) -> torch.Tensor:
+        """zero: the buffer is zero-filled when it is (re)allocated (never on the steady-state path)."""
         n = 1
         for s in shape:
             n *= int(s)
@@ -62,7 +63,7 @@ class Workspace:
         if buf is None or buf.numel() < nbytes:
             if buf is not None:
                 self.generation += 1              # an existing buffer is replaced: captured graphs are stale
-            buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+            buf = (torch.zeros if zero else torch.empty)(max(nbytes, 256), dtype=torch.uint8, device=self.device)
             self._bufs[name] = buf
         return buf[:nbytes].view(dtype).view(*shape)
 
@@ -194,7 +195,16 @@ class VisualEngine:
         use_sim = sim_cfg is not None
         use_out = outlier_cfg is not None
         mid_idx = (self.layers - 1) // 2                                   # transformer.py:593
-        simmap = ws.get('simmap', (n, P, P), f32) if use_sim else None
+        # bf16, model_type 'Experimental', head_dim 64, L <= 208: the final block runs on tcgen05 and reads the similarity map
+        # in its padded, row-block-transposed layout (ops.simmap(transposed=True)); taps keep the plain [n, P, P] map
+        exp_tc = (cdt == torch.bfloat16 and model_type == 'Experimental' and self.head_dim == 64 and 17 <= L <= ops.SIMT_COLS
+                  and taps is None and os.environ.get('CSEG_ATTN_TC', '1') != '0')
+        sim_w = (sim_cfg or {}).get('similarity_weight', 1.0)
+        sim_t = (use_sim and exp_tc and sim_cfg.get('add_self_similarity', True) and width % 64 == 0 and width <= 1280)
+        if sim_t:
+            simmap = ws.get('simmap_t', (n, ops.SIMT_FLOATS), f32, zero=True)
+        else:
+            simmap = ws.get('simmap', (n, P, P), f32) if use_sim else None
         stats = ws.get('stats', (n, self.heads, 2, P), f32) if use_out else None
         have_sim = False
         for idx in range(self.layers - 1):
@@ -203,7 +213,7 @@ class VisualEngine:
                 keep_diag = sim_cfg.get('add_self_similarity', True)
                 tc = cdt == torch.bfloat16 and keep_diag and width % 64 == 0 and width <= 1280
                 ops.simmap(x, n, L, width, simmap, sim_cfg.get('temperature', 1.0), keep_diag,
-                           scratch=ws.get('simmap_split', (M, 2 * width), cdt) if tc else None)
+                           scratch=ws.get('simmap_split', (M, 2 * width), cdt) if tc else None, transposed=sim_t)
                 have_sim = True
             ops.layernorm(x, *b['ln1'], out=h)
             ops.gemm(h, b['w_in'], qkv, bias=b['b_in'])
@@ -220,9 +230,11 @@ class VisualEngine:
         b = self.blocks[-1]
         ops.layernorm(x, *b['ln1'], out=h)
         ops.gemm(h, b['w_in'], qkv, bias=b['b_in'])
-        ops.attention(qkv, n, L, self.heads, self.head_dim, ATTN[model_type], att,
-                      simmap=simmap if have_sim else None,
-                      sim_weight=(sim_cfg or {}).get('similarity_weight', 1.0))
+        if exp_tc and (sim_t or not have_sim):
+            ops.attention_experimental_tc(qkv, n, L, self.heads, att, simmap if have_sim else None, sim_w)
+        else:
+            ops.attention(qkv, n, L, self.heads, self.head_dim, ATTN[model_type], att,
+                          simmap=simmap if have_sim else None, sim_weight=sim_w)
         y = ws.get('y', (M, width), f32)
         if ignore_residual:                                                # transformer.py:627-628
             ops.gemm(att, b['w_out'], y, bias=b['b_out'])

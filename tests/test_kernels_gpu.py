@@ -271,6 +271,41 @@ def test_attention_tcgen05_std(ops, n, L, heads):
     assert d12 < 2e-2
 
 
+def _pack_simt(ops, sim, L):
+    """[n, L-1, L-1] -> the zero-padded, row-block-transposed layout of cseg_simmap_tc(layout 1): [n][i / 32][j][i % 32]."""
+    n, cols = sim.shape[0], ops.SIMT_COLS
+    nb = (cols + 31) // 32
+    pad = torch.zeros(n, nb * 32, cols)
+    pad[:, 1:L, 1:L] = sim
+    return pad.view(n, nb, 32, cols).permute(0, 1, 3, 2).contiguous().view(n, -1)
+
+
+@pytest.mark.parametrize('n,L,heads,simw,temp', [(2, 197, 3, 0.7, 1.0), (5, 197, 12, 1.0, 1.0), (3, 128, 2, -2.0, 1.0),
+                                                 (2, 77, 4, 1.0, 0.05), (150, 197, 12, 1.0, 1.0), (1, 208, 1, 0.0, 1.0),
+                                                 (3, 197, 2, None, 1.0)])
+def test_attention_tcgen05_experimental(ops, n, L, heads, simw, temp):
+    """Final-block 'Experimental' attention on tcgen05 (k k^T + q q^T in one TMEM accumulator, double softmax with the
+    similarity map added to the probabilities) against the torch formula of custom_attn (transformer.py:897-903);
+    similarity maps of large magnitude (temperature 0.05: |w M| <= 20) and of negative weight included; simw None = no map."""
+    from clip_decontamination_b200._lib import ATTN
+    hd, d = 64, heads * 64
+    qkv = (torch.randn(n * L, 3 * d, generator=_g(3)) * 0.8).to(torch.bfloat16)
+    sim = None
+    if simw is not None:
+        f = F.normalize(torch.randn(n, L - 1, 24, generator=_g(2)), dim=-1)
+        sim = (f @ f.transpose(1, 2)) / temp
+    out = torch.full((n * L, d), float('nan'), device='cuda', dtype=torch.bfloat16)
+    ops.attention_experimental_tc(qkv.cuda(), n, L, heads, out, _pack_simt(ops, sim, L).cuda() if sim is not None else None,
+                                  simw if simw is not None else 1.0)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    if n <= 5:
+        ref, _ = _attn_ref(qkv.float(), n, L, heads, 'Experimental', sim, simw if simw is not None else 1.0)
+        e = (out.float().cpu() - ref).abs().max().item()
+        print(f'[attention tcgen05 experimental n={n} L={L} heads={heads}] vs torch {e:.3e}')
+        assert e < 2e-2
+
+
 def test_simmap(ops):
     n, L, w = 3, 197, 200
     x = torch.randn(n * L, w, generator=_g(1))
@@ -296,6 +331,10 @@ def test_simmap_tensor_core(ops, n, L, w, temp):
     scratch = torch.empty((n * L, 2 * w), device='cuda', dtype=torch.bfloat16)
     ops.simmap(x.cuda(), n, L, w, out, temperature=temp, scratch=scratch)
     assert (out.cpu() - ref).abs().max().item() < 2e-5 / temp
+    if L <= ops.SIMT_COLS:        # padded, row-block-transposed layout for the tcgen05 final-block attention
+        out_t = torch.zeros((n, ops.SIMT_FLOATS), device='cuda')
+        ops.simmap(x.cuda(), n, L, w, out_t, temperature=temp, scratch=scratch, transposed=True)
+        assert torch.equal(out_t.cpu(), _pack_simt(ops, out.cpu(), L))
 
 
 @pytest.mark.parametrize('grid,top_k', [(14, 30), (16, 10), (5, 25)])
