@@ -24,7 +24,7 @@ constexpr int AT_THREADS = 32 * (AT_SMW + 2);
 constexpr int AT_Q_BYTES = AT_BM * 128, AT_KV_BYTES = AT_LP * 128, AT_P_BLK = AT_BM * 128, AT_P_BYTES = 4 * AT_P_BLK;
 constexpr int AT_Q_OFF = 0, AT_K_OFF = 2 * AT_Q_BYTES, AT_V_OFF = AT_K_OFF + 2 * AT_KV_BYTES;
 constexpr int AT_P_OFF = AT_V_OFF + 2 * AT_KV_BYTES, AT_RED_OFF = AT_P_OFF + AT_P_BYTES;
-constexpr int AT_RED_BYTES = (4 * 128 + 2 * 4 * 128) * 4;      // smax[4][128], ssum[2 tiles][4][128]
+constexpr int AT_RED_BYTES = (4 * 128 + 2 * 4 * 128 + AT_LP) * 4;   // smax[4][128], ssum[2 tiles][4][128], scls[AT_LP]
 constexpr int AT_BAR_OFF = AT_RED_OFF + AT_RED_BYTES, AT_NBARS = 15;
 constexpr int AT_SMEM = AT_BAR_OFF + AT_NBARS * 8 + 16 + 1024;
 constexpr int AT_S_COLS = 224, AT_O_COL = 448, AT_TMEM_COLS = 512;
@@ -75,14 +75,19 @@ __host__ __device__ constexpr uint32_t at_idesc_pv() {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(AT_HD >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
 }
 
+// STATS: additionally emits P[0, 1+i] and P[1+i, 1+i] per (crop, head) -- the entries of the need_weights=True matrix that
+// detect_outliers_by_attention reads (outlier_suppression.py:46-53): the diagonal numerator stays in a register of the
+// thread that owns row i, the CLS row's numerators are parked in shared memory; both are normalised in the epilogue.
+template <bool STATS>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int L, int heads,
-                    int n_items, bf16* __restrict__ out, float scale_log2e, int diag) {
+                    int n_items, bf16* __restrict__ out, float scale_log2e, int diag, float* __restrict__ stats) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   float* smax = reinterpret_cast<float*>(smem + AT_RED_OFF);            // [4][128]
   float* ssum = smax + 4 * 128;                                        // [2][4][128]
+  float* scls = ssum + 2 * 4 * 128;                                    // [AT_LP] numerators of the CLS row (STATS)
   uint64_t* bars = (uint64_t*)(smem + AT_BAR_OFF);
   uint32_t* tmem_slot = (uint32_t*)(bars + AT_NBARS);
   const uint32_t b0 = smem_u32(bars);
@@ -195,7 +200,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint32_t qi = 0;
     bool have_prev = false;
     uint32_t prev_pi = 0;
-    int prev_row0 = 0, prev_head = 0, prev_valid = 0;
+    int prev_row0 = 0, prev_head = 0, prev_valid = 0, prev_t = 0, prev_item = 0;
+    float ediag = 0.f;                                                        // STATS: numerator of P[tok, tok]
     auto epilogue = [&]() {
       mbar_wait(o_full, prev_pi & 1);
       tc_fence_after();
@@ -203,6 +209,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tmem_ld16(tlane + AT_O_COL + hh * 16, r);
       const float* ss = ssum + (prev_pi & 1) * 512;
       const float inv = 1.0f / ((ss[row] + ss[128 + row]) + (ss[256 + row] + ss[384 + row]));
+      if (STATS) {
+        const int P = L - 1, ptok = prev_t * AT_BM + row;
+        float* st = stats + (size_t)prev_item * 2 * P;
+        if (ptok >= 1 && ptok < L && ptok >= c_begin && ptok < c_end) st[P + ptok - 1] = ediag * inv;
+        if (prev_t == 0 && q4 == 0) {                                        // CLS row: this warp's key quarter, lane-parallel
+          const float inv0 = __shfl_sync(0xffffffffu, inv, 0);
+          for (int c = c_begin + lane; c < c_end; c += 32)
+            if (c >= 1 && c < L) st[c - 1] = scls[c] * inv0;
+        }
+      }
       if (row < prev_valid && !(diag & 8)) {
         uint4* o = reinterpret_cast<uint4*>(out + (size_t)(prev_row0 + row) * width + prev_head * AT_HD + hh * 16);
 #pragma unroll
@@ -280,6 +296,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 sum += ev[e];
               }
             }
+            if (STATS) {
+              const int tok = t * AT_BM + row;
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (c + e == tok) ediag = ev[e];
+              if (tok == 0) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) scls[c + e] = ev[e];
+              }
+            }
             uint8_t* pb = prow + (c >> 6) * AT_P_BLK;
             const int j = (c & 63) >> 3;                                   // 16-byte chunk within the 128-byte row (even)
             uint4 w0, w1;
@@ -315,6 +341,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         prev_row0 = crop * L + t * AT_BM;
         prev_head = head;
         prev_valid = min(AT_BM, L - t * AT_BM);
+        prev_t = t;
+        prev_item = item;
       }
     }
     if (have_prev) epilogue();
@@ -643,14 +671,15 @@ bool at_enabled() {   // CSEG_ATTN_TC=0 selects the mma.sync kernel (A/B measure
 // returns 1 when the case is not covered (the caller falls back to the mma.sync kernel)
 int cseg_attention_tc(const bf16* qkv, int n_crops, int L, int heads, int head_dim, int mode, const float* simmap, float simw,
                       bf16* out, float* stats, cudaStream_t st) {
-  if (!at_enabled() || head_dim != AT_HD || stats != nullptr) return 1;
+  if (!at_enabled() || head_dim != AT_HD) return 1;
   if (mode != CSEG_ATTN_STD || simmap != nullptr) return 1;
   if (L < 17 || L > AT_LP || ((uintptr_t)qkv & 15) != 0 || ((uintptr_t)out & 15) != 0) return 1;
   const int width = heads * AT_HD;
   CUtensorMap tq, tkv;
   if (int rc = at_make_map(&tq, qkv, (long long)n_crops * L, 3 * width, AT_BM)) return rc;
   if (int rc = at_make_map(&tkv, qkv, (long long)n_crops * L, 3 * width, AT_LP)) return rc;
-  CSEG_SET_SMEM(attention_tc_kernel, AT_SMEM);
+  if (stats != nullptr) CSEG_SET_SMEM(attention_tc_kernel<true>, AT_SMEM);
+  else CSEG_SET_SMEM(attention_tc_kernel<false>, AT_SMEM);
   const int items = n_crops * heads;
   const int grid = std::min(items, sm_count());
   const float scale_log2e = 0.125f * 1.4426950408889634f;     // head_dim^-0.5 * log2(e)
@@ -659,7 +688,11 @@ int cseg_attention_tc(const bf16* qkv, int n_crops, int L, int heads, int head_d
     const char* e = getenv("CSEG_ATTN_DIAG");
     diag = e ? atoi(e) : 0;
   }
-  cseg_launch(attention_tc_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tq, tkv, L, heads, items, out, scale_log2e, diag);
+  if (stats != nullptr)
+    cseg_launch(attention_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tq, tkv, L, heads, items, out, scale_log2e, diag, stats);
+  else
+    cseg_launch(attention_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tq, tkv, L, heads, items, out, scale_log2e, diag,
+                stats);
   CSEG_LAUNCH_CHECK("attention_tc");
   return 0;
 }

@@ -110,6 +110,13 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
   const int y = y0 + warp;
   bf16* st = stage + warp * 16 * (LDK + SPAD);
   const int q = lane >> 3, rr = lane & 7;
+  // the staging columns behind the D2 taps are never written by the tap loop: zero them once, so that the copy-out can
+  // weight them with 0 instead of selecting (uninitialised shared memory may hold NaN patterns)
+  if (lane < 16) {
+    __half* zr = reinterpret_cast<__half*>(st) + lane * (LDK + SPAD);
+    for (int c = D2; c < LDK + SPAD; ++c) zr[c] = __float2half(0.f);
+  }
+  __syncwarp();
 #pragma unroll 1
   for (int xb = 0; xb < TXR / 16; ++xb) {
     const int xq0 = x0 + xb * 16;
@@ -137,16 +144,25 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
       for (int e = 0; e < 4; ++e) gx[nb][e] = jj[nb][e] >= 0 ? gauss[jj[nb][e]] : 0.f;
     const uint32_t rowb0 = psm + (uint32_t)((warp * NPOS + xb * 16 + rr) * PROW + q * 16);
     // ---- single pass over the tap rows with a running maximum (online softmax): exp, both sums, and the unnormalised
-    //      exp * gauss (fp16, <= 1) into the staging rows.  Every tap row i is staged relative to the running maximum at
-    //      that time, which is kept per (pixel, i) and folded into the normalisation when the rows are copied out. ----
-    const float pt2 = pos_temp * 1.4426950408889634f;          // exp(x) = 2^(x log2 e): one FFMA + MUFU.EX2 per tap
+    //      exp * gauss_x (fp16, <= 1) into the staging rows.  Every tap row i is staged relative to the running maximum at
+    //      that time, which is kept per (pixel, i); that factor, the row factor gauss_y[i] of the separable Gaussian and the
+    //      normalisation are folded in when the rows are copied out. ----
+    // exp(pos_temp * s - m) = 2^(s * pt2 - m'): ONE FFMA + MUFU.EX2 per tap, the scale is never applied to S itself.  The
+    // running maximum needs a positive scale: for a negative pos_temp the query fragments change sign (exact in fp16).
+    float pt2 = pos_temp * 1.4426950408889634f;
+    if (pt2 < 0.f) {                                           // uniform
+      pt2 = -pt2;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) a[ks][r4] ^= 0x80008000u;
+    }
     float mrun[2] = {-INFINITY, -INFINITY};                    // running maxima of rows g, g+8 in log2 units
     __half* sth = reinterpret_cast<__half*>(st);
     float* mrw = mrow + warp * 16 * MROWS;
 #pragma unroll 1
     for (int i = 0; i < D; ++i) {
       const uint32_t rowb = rowb0 + (uint32_t)(i * NPOS * PROW);
-      const float gy = gauss[i];
       __half* sti = sth + i * D;
       float S[NB][4];
 #pragma unroll
@@ -157,29 +173,33 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
         mma_f16(S[nb], a[0], b[0], b[1]);
         mma_f16(S[nb], a[1], b[2], b[3]);
       }
+      // band mask once per element: everything after it (maximum, exponent, sums) is unpredicated; 2^(-inf) = 0
       float mi[2] = {-INFINITY, -INFINITY};
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          S[nb][e] *= pt2;
-          if (jj[nb][e] >= 0) mi[e >> 1] = fmaxf(mi[e >> 1], S[nb][e]);
+          if ((e < 2 && nb * 8 >= 8 + D - 1) || (e >= 2 && nb * 8 + 8 <= 8)) continue;     // compile-time: never in the band
+          S[nb][e] = jj[nb][e] >= 0 ? S[nb][e] : -INFINITY;
+          mi[e >> 1] = fmaxf(mi[e >> 1], S[nb][e]);
         }
+      float nm[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         mi[h] = fmaxf(mi[h], __shfl_xor_sync(0xffffffffu, mi[h], 1));
         mi[h] = fmaxf(mi[h], __shfl_xor_sync(0xffffffffu, mi[h], 2));
-        const float mnew = fmaxf(mrun[h], mi[h]);
+        const float mnew = fmaxf(mrun[h], __fmul_rn(mi[h], pt2));
         float corr;
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(corr) : "f"(mrun[h] - mnew));   // 0 on the first row (mrun = -inf)
-        se[h] *= corr;
-        sg[h] *= corr;
+        se[h] = __fmul_rn(se[h], corr);
+        sg[h] = __fmul_rn(sg[h], corr);
         mrun[h] = mnew;
+        nm[h] = -mnew;
         if (tig == 0) mrw[(g + h * 8) * MROWS + i] = mnew;
       }
       // Rows g (e < 2) only reach positions [g, g + D) of the 8 NB-blocks, rows g + 8 (e >= 2) positions [g + 8, g + 8 + D):
-      // the last block can never hold a tap of the top half, the first block never one of the bottom half.  Skipping
-      // those pairs at compile time saves a quarter of the MUFU.EX2 / F2FP work -- ncu shows the XU pipe saturated here.
+      // the last block can never hold a tap of the top half, the first block never one of the bottom half.
+      float sgr[2] = {0.f, 0.f};
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
@@ -187,19 +207,21 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
           if ((hh == 0 && nb * 8 >= 8 + D - 1) || (hh == 1 && nb * 8 + 8 <= 8)) continue;   // compile-time
           const int e0 = hh * 2;
           float ex0, ex1;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex0) : "f"(S[nb][e0] - mrun[hh]));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex1) : "f"(S[nb][e0 + 1] - mrun[hh]));
-          const bool v0 = jj[nb][e0] >= 0, v1 = jj[nb][e0 + 1] >= 0;
-          ex0 = v0 ? ex0 : 0.f;
-          ex1 = v1 ? ex1 : 0.f;
-          const float w0 = ex0 * (gy * gx[nb][e0]), w1 = ex1 * (gy * gx[nb][e0 + 1]);
-          se[hh] += ex0 + ex1;
-          sg[hh] += w0 + w1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex0) : "f"(fmaf(S[nb][e0], pt2, nm[hh])));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex1) : "f"(fmaf(S[nb][e0 + 1], pt2, nm[hh])));
+          // explicit roundings: the BORDER and dense instantiations must not differ in FMA contraction (their results are
+          // required to be bit-identical, tests/test_engine_gpu.py::test_jbu_shared_kernels_equal_per_crop)
+          const float w0 = __fmul_rn(ex0, gx[nb][e0]), w1 = __fmul_rn(ex1, gx[nb][e0 + 1]);
+          se[hh] = __fadd_rn(se[hh], __fadd_rn(ex0, ex1));
+          sgr[hh] = __fadd_rn(sgr[hh], __fadd_rn(w0, w1));
           const __half2 wp = __floats2half2_rn(w0, w1);                  // one F2FP for the pair
           __half* srow = sti + (g + hh * 8) * (LDK + SPAD);
-          if (v0) srow[jj[nb][e0]] = __low2half(wp);
-          if (v1) srow[jj[nb][e0 + 1]] = __high2half(wp);
+          if (jj[nb][e0] >= 0) srow[jj[nb][e0]] = __low2half(wp);
+          if (jj[nb][e0 + 1] >= 0) srow[jj[nb][e0 + 1]] = __high2half(wp);
         }
+      const float gy = gauss[i];
+      sg[0] = fmaf(gy, sgr[0], sg[0]);
+      sg[1] = fmaf(gy, sgr[1], sg[1]);
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -208,50 +230,64 @@ __global__ void __launch_bounds__(TYR * 32) range_kernel_mma(const __half* __res
       sg[h] += __shfl_xor_sync(0xffffffffu, sg[h], 1);
       sg[h] += __shfl_xor_sync(0xffffffffu, sg[h], 2);
       const float ise = 1.0f / se[h];
-      inv[h] = ise / fmaxf(sg[h] * ise, 1e-7f);               // softmax, then / sum(softmax*gauss).clamp(1e-7)
+      inv[h] = ise / fmaxf(__fmul_rn(sg[h], ise), 1e-7f);               // softmax, then / sum(softmax*gauss).clamp(1e-7)
     }
     __syncwarp();
-    // ---- normalise while copying out: taps * inv[row] * 2^(m_i - m_final), then the 3 guidance channels, then zeros;
-    //      coalesced 16-byte row stores of the [pixels, ldk] kernel matrix ----
-#pragma unroll
-    for (int e = lane; e < 16 * (LDK / 8); e += 32) {          // uniform trip count: the shuffles stay convergent
-      const int px = e / (LDK / 8), v = e % (LDK / 8);
-      const float i0 = __shfl_sync(0xffffffffu, inv[0], (px & 7) * 4);
-      const float i1 = __shfl_sync(0xffffffffu, inv[1], (px & 7) * 4);
-      const float m0 = __shfl_sync(0xffffffffu, mrun[0], (px & 7) * 4);
-      const float m1 = __shfl_sync(0xffffffffu, mrun[1], (px & 7) * 4);
-      const float sc = px < 8 ? i0 : i1, mf = px < 8 ? m0 : m1;
-      // the 8 taps of this chunk lie in tap rows ia and (from element bnd on) ia + 1
+    // ---- normalise while copying out: taps * inv[row] * gauss_y[i] * 2^(m_i - m_final), then the 3 guidance channels, then
+    //      zeros; coalesced 16-byte row stores of the [pixels, ldk] kernel matrix.  A lane keeps its 16-byte column chunk v for
+    //      all iterations (32 lanes = 32 / CH pixels x CH chunks), so everything that depends on v only is hoisted. ----
+    {
+      constexpr int CH = LDK / 8;                              // 16-byte chunks per pixel row
+      static_assert(CH == 16 || CH == 8, "copy-out assumes 8 or 16 chunks of 8 taps per pixel");
+      const int v = lane % CH;
+      // the 8 taps of chunk v lie in tap rows ia and (from element bnd on) ia + 1
       const int ia = (v * 8) / D, bnd = (ia + 1) * D - v * 8;
-      float fa, fb;
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(fa) : "f"(mrw[px * MROWS + min(ia, D - 1)] - mf));
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(fb) : "f"(mrw[px * MROWS + min(ia + 1, D - 1)] - mf));
-      fa *= sc;
-      fb *= sc;
-      const uint4 raw = *reinterpret_cast<const uint4*>(sth + px * (LDK + SPAD) + v * 8);
-      const __half2* hp = reinterpret_cast<const __half2*>(&raw);
-      float f[8];
+      const int ra = min(ia, D - 1), rb = min(ia + 1, D - 1);
+      const float ga = gauss[ra], gb = gauss[rb];
+      float wa[8], wb[8];                                      // 0 / 1 selectors: element k takes factor a, b or is padding
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 t2 = __half22float2(hp[k]);
-        f[2 * k] = (v * 8 + 2 * k < D2) ? t2.x * (2 * k < bnd ? fa : fb) : 0.f;
-        f[2 * k + 1] = (v * 8 + 2 * k + 1 < D2) ? t2.y * (2 * k + 1 < bnd ? fa : fb) : 0.f;
+      for (int k = 0; k < 8; ++k) {
+        const bool ok = v * 8 + k < D2;
+        wa[k] = (ok && k < bnd) ? 1.f : 0.f;
+        wb[k] = (ok && k >= bnd) ? 1.f : 0.f;
       }
-      if (v == D2 / 8) {                                       // columns D2 .. D2+2: guidance (RGB) of this pixel
-        const int x = min(xq0 + px, gw - 1);
-        const float4 gv = gc[(size_t)y * pitch + x];
-        f[D2 % 8] = gv.x;
-        f[D2 % 8 + 1] = gv.y;
-        f[D2 % 8 + 2] = gv.z;
-      }
-      if (xq0 + px < gw) {
-        uint4 o;
-        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+      const bool has_guid = v == D2 / 8;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) op[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-        const size_t orow = BORDER ? (size_t)crop * border_rows(gh, gw, frame) + border_index(y, xq0 + px, gh, gw, frame)
-                                   : ((size_t)crop * gh + y) * gw + xq0 + px;
-        *reinterpret_cast<uint4*>(kern + orow * ldk + v * 8) = o;
+      for (int it = 0; it < CH / 2; ++it) {
+        const int px = lane / CH + (32 / CH) * it;             // px < 8 <=> it < CH / 4 (compile time)
+        const int src = (px & 7) * 4;
+        const float sc = __shfl_sync(0xffffffffu, it < CH / 4 ? inv[0] : inv[1], src);
+        const float mf = __shfl_sync(0xffffffffu, it < CH / 4 ? mrun[0] : mrun[1], src);
+        float fa, fb;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(fa) : "f"(mrw[px * MROWS + ra] - mf));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(fb) : "f"(mrw[px * MROWS + rb] - mf));
+        fa = __fmul_rn(fa, __fmul_rn(sc, ga));
+        fb = __fmul_rn(fb, __fmul_rn(sc, gb));
+        const uint4 raw = *reinterpret_cast<const uint4*>(sth + px * (LDK + SPAD) + v * 8);
+        const __half2* hp = reinterpret_cast<const __half2*>(&raw);
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 t2 = __half22float2(hp[k]);
+          f[2 * k] = __fmul_rn(t2.x, fmaf(wa[2 * k], fa, __fmul_rn(wb[2 * k], fb)));
+          f[2 * k + 1] = __fmul_rn(t2.y, fmaf(wa[2 * k + 1], fa, __fmul_rn(wb[2 * k + 1], fb)));
+        }
+        if (has_guid) {                                        // columns D2 .. D2+2: guidance (RGB) of this pixel
+          const int x = min(xq0 + px, gw - 1);
+          const float4 gv = gc[(size_t)y * pitch + x];
+          f[D2 % 8] = gv.x;
+          f[D2 % 8 + 1] = gv.y;
+          f[D2 % 8 + 2] = gv.z;
+        }
+        if (xq0 + px < gw) {
+          uint4 o;
+          __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) op[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+          const size_t orow = BORDER ? (size_t)crop * border_rows(gh, gw, frame) + border_index(y, xq0 + px, gh, gw, frame)
+                                     : ((size_t)crop * gh + y) * gw + xq0 + px;
+          *reinterpret_cast<uint4*>(kern + orow * ldk + v * 8) = o;
+        }
       }
     }
     __syncwarp();

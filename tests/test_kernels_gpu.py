@@ -251,17 +251,21 @@ def test_attention_modes(ops, mode, dtype, L, hd):
 @pytest.mark.parametrize('n,L,heads', [(2, 197, 3), (5, 197, 12), (3, 128, 2), (2, 77, 4), (150, 197, 12), (1, 208, 1)])
 def test_attention_tcgen05_std(ops, n, L, heads):
     """Standard attention on tcgen05 (attention_tc.cu: S in TMEM, softmax from tcgen05.ld, P.V as a second MMA) against
-    the torch formula and against the mma.sync kernel (selected by asking for the statistics output)."""
+    the torch formula and against the mma.sync kernel (selected through mode 'vanilla' without a similarity map: the same
+    formula, a mode only the mma.sync kernel serves); the statistics-emitting variant gives the same output."""
     from clip_decontamination_b200._lib import ATTN
     hd, d = 64, heads * 64
     qkv = (torch.randn(n * L, 3 * d, generator=_g(3)) * 0.8).to(torch.bfloat16)
     out = torch.full((n * L, d), float('nan'), device='cuda', dtype=torch.bfloat16)
     ops.attention(qkv.cuda(), n, L, heads, hd, ATTN['STD'], out)
     out2 = torch.empty_like(out)
+    ops.attention(qkv.cuda(), n, L, heads, hd, ATTN['vanilla'], out2)
+    out3 = torch.empty_like(out)
     stats = torch.zeros((n, heads, 2, L - 1), device='cuda')
-    ops.attention(qkv.cuda(), n, L, heads, hd, ATTN['STD'], out2, stats=stats)
+    ops.attention(qkv.cuda(), n, L, heads, hd, ATTN['STD'], out3, stats=stats)
     torch.cuda.synchronize()
-    assert torch.isfinite(out.float()).all()
+    assert torch.isfinite(out.float()).all() and torch.equal(out3, out)
+    assert (stats > 0).all() and (stats <= 1).all()
     d12 = (out.float() - out2.float()).abs().max().item()
     if n <= 5:
         ref, _ = _attn_ref(qkv.float(), n, L, heads, 'STD', None, 0.0)
