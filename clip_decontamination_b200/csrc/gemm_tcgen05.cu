@@ -306,6 +306,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<uint4*>(stg + lane * SST + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
         __syncwarp();
+        if (RES == 3 && ep.cmp_mode == 1) {
+          // row blocks of 32, column-major inside a block ([i / 32][j][i % 32], cmp_rs columns per block): lane = ROW here, so
+          // the 32 rows of one column are (up to a block change) consecutive floats -- coalesced stores
+          const int Lb = ep.diag_rows, skip = ep.cmp_skip;
+          const int row = rbase + lane, blk = row / Lb, i = row - blk * Lb;
+          float* cb = (float*)ep.C + (size_t)blk * ep.cmp_cs + (size_t)(i >> 5) * ep.cmp_rs * 32 + (i & 31);
+          const int jb = col0 - blk * Lb;
+          const bool row_ok = lane < nrows && i >= skip;
+          const int jmax = min(32, ep.N - col0);
+#pragma unroll 8
+          for (int jj = 0; jj < 32; ++jj) {
+            const int j = jb + jj;
+            if (row_ok && jj < jmax && j >= skip && j < Lb) cb[(size_t)j * 32] = stg[lane * SST + jj] * ep.alpha;
+          }
+        }
         if (col_ok) {
           const float alpha = ep.alpha;
           auto finish = [&](int rr) -> float {
@@ -316,20 +331,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           };
           if (RES == 3) {
             const int Lb = ep.diag_rows, skip = ep.cmp_skip;
-            int blk = rbase / Lb, i = rbase - blk * Lb;
             float* cf = (float*)ep.C;
+            if (ep.cmp_mode == 0) {
+              int blk = rbase / Lb, i = rbase - blk * Lb;
 #pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) {
-              if (rr < nrows) {
-                const int j = col - blk * Lb;
-                if (i >= skip && j >= skip && j < Lb) {
-                  // cmp_mode 1: row blocks of 32, column-major inside a block ([i / 32][j][i % 32], cmp_rs columns per block)
-                  const size_t o = ep.cmp_mode == 0 ? (size_t)(i - skip) * ep.cmp_rs + (j - skip)
-                                                    : ((size_t)(i >> 5) * ep.cmp_rs + j) * 32 + (i & 31);
-                  cf[(size_t)blk * ep.cmp_cs + o] = stg[rr * SST + lane] * alpha;
+              for (int rr = 0; rr < 32; ++rr) {
+                if (rr < nrows) {
+                  const int j = col - blk * Lb;
+                  if (i >= skip && j >= skip && j < Lb)
+                    cf[(size_t)blk * ep.cmp_cs + (size_t)(i - skip) * ep.cmp_rs + (j - skip)] = stg[rr * SST + lane] * alpha;
                 }
+                if (++i == Lb) { i = 0; ++blk; }
               }
-              if (++i == Lb) { i = 0; ++blk; }
             }
           } else if (OUTB) {
             bf16* cp = (bf16*)ep.C + (size_t)rbase * ep.ldc + col;

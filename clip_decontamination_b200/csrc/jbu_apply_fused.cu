@@ -19,11 +19,12 @@
 // Per tile of 8 rows x 16 px and 128-channel slab, every low-res row s of the (NLR x 16) source patch costs one
 // tcgen05.mma  D[128 ch, 128 px] += A_s[128 ch, 16 pos] . B_s[16 pos, 128 px]  (A: MN-major SWIZZLE_128B straight from
 // the [pos][ch] HBM layout; B: composite band tile, K-major).  Warp roles of the persistent CTA:
-//   warps 0-3   epilogue (tcgen05.ld, lane = channel)           warp 4   TMEM allocator + MMA issuer
-//   warps 5-8   strip loaders (cp.async into a 6-stage ring)
-//   warps 9-12  composite builders, one output row each: per pixel two mma.sync (fp16) compute T^T = TX^T . k^T, two
-//               more K'^T = T^T . TY (the accumulator of the first pair is the A fragment of the second), and the
-//               (2 DO + 1)^2 results are scattered into the double-buffered band tiles.
+//   warps 0-7   epilogue (tcgen05.ld, lane = channel; lane quadrant = warp % 4, column half = warp / 4)
+//   warp 8      TMEM allocator + MMA issuer
+//   warps 9-10  strip loaders (cp.async into a 16-slot ring)
+//   warps 11-18 band builders: two threads per pixel scatter its (2 DO + 1)^2 composite weights (computed by the
+//               fz_composite pre-pass, fetched one tile ahead) into the double-buffered band tiles; the swizzled offsets
+//               depend on (pixel, tap) only and are computed once per kernel.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "jbu_share.cuh"
@@ -35,7 +36,7 @@ namespace {
 constexpr int FZ_RW = 8, FZ_TX = 16, FZ_NPX = FZ_RW * FZ_TX;   // 128 pixels per tile = N of the MMA
 constexpr int FZ_NPOS = 16;                                    // low-res positions per strip = K of the MMA
 constexpr int FZ_NSTG = 16, FZ_INFL = 4;                       // strip ring slots / strips in flight per loader thread
-constexpr int FZ_EPI_WARPS = 4, FZ_LD_WARPS = 4, FZ_BB_WARPS = 8;
+constexpr int FZ_EPI_WARPS = 8, FZ_LD_WARPS = 2, FZ_BB_WARPS = 8;   // 19 warps: the same 640-thread register allocation as 17
 constexpr int FZ_THREADS = 32 * (FZ_EPI_WARPS + 1 + FZ_LD_WARPS + FZ_BB_WARPS);
 constexpr int FZ_LD_T0 = 32 * (FZ_EPI_WARPS + 1), FZ_BB_T0 = FZ_LD_T0 + 32 * FZ_LD_WARPS;
 
@@ -283,13 +284,17 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
       const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
       mbar_wait(t_full0 + as * 8, aph);
       tc_fence_after();
+      // 8 warps: TMEM lane quadrant = warp % 4 (32 channels), warp / 4 selects one half of the MH * 4 column steps (with two
+      // channel slabs: one slab each) -- the epilogue was the busiest role of the kernel (94 % of its warps' samples)
+      constexpr int HSTEPS = MH * (FZ_NPX / 32) / (FZ_EPI_WARPS / 4);
+      const int wq = warp & 3, wh = warp >> 2;
 #pragma unroll 1
-      for (int hc = 0; hc < MH * (FZ_NPX / 32); ++hc) {          // 32 pixel columns (two output rows) per step
+      for (int hc = wh * HSTEPS; hc < (wh + 1) * HSTEPS; ++hc) {  // 32 pixel columns (two output rows) per step
         const int half = hc / (FZ_NPX / 32), cb = hc % (FZ_NPX / 32);
         uint32_t r[32];
         __syncwarp();
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((as * MH + half) * FZ_NPX + cb * 32), r);
-        bf16* obase = dst + (size_t)crop * H2 * W2 * C + c0 + half * 128 + warp * 32 + lane;
+        tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((as * MH + half) * FZ_NPX + cb * 32), r);
+        bf16* obase = dst + (size_t)crop * H2 * W2 * C + c0 + half * 128 + wq * 32 + lane;
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
           const int y = y0 + cb * 2 + rr;
@@ -404,66 +409,112 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
     fz_fence_proxy_async();
     for (uint32_t j = (it >= FZ_INFL - 1 ? it - (FZ_INFL - 1) : 0); j < it; ++j) mbar_arrive(a_full0 + (j % FZ_NSTG) * 8);
   } else {
-    // ---------------- band builders: scatter the composite kernels of the tile's 64 pixels ----------------
-    const int bt = tid - FZ_BB_T0;                               // 0..127
+    // ---------------- band builders: scatter the composite kernels of the tile's 128 pixels ----------------
+    // A thread owns ONE pixel of the tile (n = bt % 128) and one half of its composite kernel (the first NC0 or the last
+    // NC1 16-byte chunks; the half is warp-uniform).  Where a weight lands in the band tiles depends on (n, tap) only, not
+    // on the tile: the swizzled offsets are computed once per kernel and kept as 16-bit pairs in registers, so a tile costs
+    // one pointer computation, NC0 16-byte loads and one 2-byte store (+ ~3 integer instructions) per weight.
+    const int bt = tid - FZ_BB_T0;                               // 0..255
     constexpr int DC = 2 * DO + 1, NCH = (DC * DC + 7) / 8;      // 16-byte chunks per composite kernel (11 / 7)
-    constexpr int WPT = (FZ_NPX * NCH + 32 * FZ_BB_WARPS - 1) / (32 * FZ_BB_WARPS);
-    uint32_t tl = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x)
+    constexpr int NC0 = (NCH + 1) / 2, NC1 = NCH - NC0;
+    static_assert(32 * FZ_BB_WARPS == 2 * FZ_NPX, "two builder threads per pixel");
+    static_assert(Cf::B_BUF <= 65536, "band-tile offsets are kept in 16 bits");
+    const int n = bt & (FZ_NPX - 1), half = bt >> 7;
+    const int nck = half ? NC1 : NC0, v0 = half ? NC0 : 0;
+    uint32_t offp[NC0 * 4];
     {
-     int x0, crop, c0, yt0, yt1;
-     unit_coords(unit, x0, crop, c0, yt0, yt1);
-     for (int yt = yt0; yt < yt1; ++yt, ++tl) {
-      const int y0 = yt * FZ_RW;
-      const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
-      uint4 wv[WPT];
+      const int r = n >> 4, m = n & 15;
+      const int sr0 = r >> 1, kk0 = m >> 1;                      // (y >> 1) - (y0 >> 1), (x >> 1) - (x0 >> 1)
+      const uint32_t rowb = (uint32_t)((n >> 3) * 1024 + (n & 7) * 128);
+#pragma unroll
+      for (int k = 0; k < NC0; ++k)
+#pragma unroll
+        for (int q2 = 0; q2 < 4; ++q2) {
+          uint32_t o[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int t = (v0 + k) * 8 + 2 * q2 + e;
+            const int dy = t / DC, dx = t - dy * DC;
+            const int sr = sr0 + dy, col = (sr & 3) * 16 + kk0 + dx;
+            o[e] = (t < DC * DC) ? rowb + (uint32_t)((sr >> 2) * Cf::B_QUAD) + (uint32_t)((((col >> 3) ^ (n & 7)) << 4) | ((col & 7) << 1)) : 0u;
+          }
+          offp[k * 4 + q2] = o[0] | (o[1] << 16);
+        }
+    }
+    // The weights of tile i + 1 are requested before tile i is scattered (registers, one tile ahead): the composite kernels
+    // stream from HBM (616 MB per 48 crops at the last stage) and a tile's loads would otherwise expose a full DRAM round
+    // trip between two scatters.
+    int unit = blockIdx.x, yt = 0, yt1 = 0, x0 = 0, crop = 0, c0 = 0;
+    size_t org = 0, cbase = 0;
+    bool have = unit < total_units;
+    auto enter_unit = [&]() {
+      int yt0;
+      unit_coords(unit, x0, crop, c0, yt0, yt1);
+      yt = yt0;
       // shared kernels (jbu_share.cuh): interior pixels read the image-level composite kernels at the crop's origin,
       // border-frame pixels the crop's compact frame tensor
-      size_t org = 0, cbase = (size_t)crop * H2 * W2;
+      org = 0;
+      cbase = (size_t)crop * H2 * W2;
       if (kc_img != nullptr) {
         org = (size_t)(sg.wins[crop * 4] >> sg.shift) * sg.pitch + (sg.wins[crop * 4 + 1] >> sg.shift);
         cbase = (size_t)crop * border_rows(H2, W2, CSEG_JBU_FB_COMP);
       }
+    };
+    auto fetch = [&](uint4 (&w)[NC0]) {                          // composite weights of this thread's pixel in tile (unit, yt)
+      const int y = yt * FZ_RW + (n >> 4), x = x0 + (n & 15);
 #pragma unroll
-      for (int k = 0; k < WPT; ++k) {
-        const int e = bt + k * 32 * FZ_BB_WARPS, n = e / NCH, v = e - n * NCH;
-        const int y = y0 + (n >> 4), x = x0 + (n & 15);
-        wv[k] = make_uint4(0, 0, 0, 0);                          // pixels outside the image: zero weights
-        if (n < FZ_NPX && y < H2 && x < W2 && !(diag & 8)) {     // diagnostic bit 8: no composite-weight loads
-          const bf16* kp;
-          if (kc_img == nullptr) kp = kc + (cbase + (size_t)y * W2 + x) * 128;
-          else if (border_interior(y, x, H2, W2, CSEG_JBU_FB_COMP)) kp = kc_img + (org + (size_t)y * sg.pitch + x) * 128;
-          else kp = kc + (cbase + border_index(y, x, H2, W2, CSEG_JBU_FB_COMP)) * 128;
-          wv[k] = __ldg(reinterpret_cast<const uint4*>(kp + v * 8));
-        }
+      for (int k = 0; k < NC0; ++k) w[k] = make_uint4(0, 0, 0, 0);    // pixels outside the image: zero weights
+      if (y < H2 && x < W2 && !(diag & 8)) {                     // diagnostic bit 8: no composite-weight loads
+        const bf16* kp;
+        if (kc_img == nullptr) kp = kc + (cbase + (size_t)y * W2 + x) * 128;
+        else if (border_interior(y, x, H2, W2, CSEG_JBU_FB_COMP)) kp = kc_img + (org + (size_t)y * sg.pitch + x) * 128;
+        else kp = kc + (cbase + border_index(y, x, H2, W2, CSEG_JBU_FB_COMP)) * 128;
+        const uint4* kv = reinterpret_cast<const uint4*>(kp) + v0;
+#pragma unroll
+        for (int k = 0; k < NC0; ++k)
+          if (k < nck) w[k] = __ldg(kv + k);
       }
+    };
+    uint4 wn[NC0];
+    if (have) {
+      enter_unit();
+      fetch(wn);
+    }
+    for (uint32_t tl = 0; have; ++tl) {
+      const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+      uint4 wv[NC0];
+#pragma unroll
+      for (int k = 0; k < NC0; ++k) wv[k] = wn[k];
+      if (++yt >= yt1) {                                         // next tile of the run, or the first tile of the next unit
+        unit += gridDim.x;
+        have = unit < total_units;
+        if (have) enter_unit();
+      }
+      if (have) fetch(wn);
       mbar_wait(b_empty0 + as * 8, aph ^ 1);
       uint8_t* bbuf = smem + Cf::B_OFF + as * Cf::B_BUF;
       if (tl < 2) {                                              // zero background, once per buffer
         for (int e = bt; e < Cf::B_BUF / 16; e += 32 * FZ_BB_WARPS) reinterpret_cast<uint4*>(bbuf)[e] = make_uint4(0, 0, 0, 0);
         asm volatile("bar.sync 2, %0;" ::"n"(32 * FZ_BB_WARPS) : "memory");
       }
+      if (!(diag & 1)) {                                         // diagnostic bit 1: no band scatter
 #pragma unroll
-      for (int k = 0; k < WPT; ++k) {
-        const int e = bt + k * 32 * FZ_BB_WARPS, n = e / NCH, v = e - n * NCH;
-        if (n >= FZ_NPX || (diag & 1)) continue;                 // diagnostic bit 1: no band scatter
-        const int r = n >> 4, m = n & 15;
-        const unsigned short* hv = reinterpret_cast<const unsigned short*>(&wv[k]);
-        uint8_t* rowb = bbuf + (n >> 3) * 1024 + (n & 7) * 128;
-        const int sr0 = r >> 1, kk0 = m >> 1;                    // (y >> 1) - (y0 >> 1), (x >> 1) - (x0 >> 1)
+        for (int k = 0; k < NC0; ++k) {
+          if (k >= nck) break;                                   // warp-uniform
+          const uint32_t w4[4] = {wv[k].x, wv[k].y, wv[k].z, wv[k].w};
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int t = v * 8 + q;
-          if (t >= DC * DC) continue;
-          const int dy = (t * 57) >> 9;                          // t / 9 for t < 128 (DC == 9); exact division below otherwise
-          const int dyy = (DC == 9) ? dy : t / DC, dx = t - dyy * DC;
-          const int sr = sr0 + dyy, col = (sr & 3) * 16 + kk0 + dx;
-          *reinterpret_cast<unsigned short*>(rowb + (sr >> 2) * Cf::B_QUAD + ((((col >> 3) ^ (n & 7)) << 4) | ((col & 7) << 1))) = hv[q];
+          for (int q2 = 0; q2 < 4; ++q2) {
+            const uint32_t op = offp[k * 4 + q2];
+            // taps beyond DC * DC only occur in the last chunk of the second half
+            if ((NC0 + k) * 8 + 2 * q2 < DC * DC || !half)
+              *reinterpret_cast<unsigned short*>(bbuf + (op & 0xFFFFu)) = (unsigned short)(w4[q2] & 0xFFFFu);
+            if ((NC0 + k) * 8 + 2 * q2 + 1 < DC * DC || !half)
+              *reinterpret_cast<unsigned short*>(bbuf + (op >> 16)) = (unsigned short)(w4[q2] >> 16);
+          }
         }
       }
       fz_fence_proxy_async();
       mbar_arrive(b_full0 + as * 8);
-     }
     }
   }
   tc_fence_before();
