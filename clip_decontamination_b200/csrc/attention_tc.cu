@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int L, int heads,
                     int n_items, bf16* __restrict__ out, float scale_log2e, int diag, float* __restrict__ stats) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS / STS, not generic LD / ST
   const uint32_t sbase = smem_u32(smem);
   float* smax = reinterpret_cast<float*>(smem + AT_RED_OFF);            // [4][128]
   float* ssum = smax + 4 * 128;                                        // [2][4][128]
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_exp_kernel(const __grid_constant__ CUtensorMap tmKV, int L, int heads, int n_items, bf16* __restrict__ out,
                         float scale_log2e, const float* __restrict__ simmap, float simw) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS / STS, not generic LD / ST
   const uint32_t sbase = smem_u32(smem);
   float* smax = reinterpret_cast<float*>(smem + AX_RED_OFF);           // [4][128]
   float* ssum1 = smax + 4 * 128;                                       // [4][128]

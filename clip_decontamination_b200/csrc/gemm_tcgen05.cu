@@ -84,7 +84,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   using C = Cfg<BN, STAGES>;
   constexpr int ACC = C::ACC;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS / STS, not generic LD / ST
   uint64_t* bars = (uint64_t*)(smem + C::BAR_OFF);
   uint32_t* tmem_slot = (uint32_t*)(bars + C::NBARS);
   const uint32_t smem_base = smem_u32(smem);
@@ -472,7 +472,7 @@ gemm_normsim_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   using Cf = NsCfg<QT>;
   constexpr int BN = Cf::BN, STAGES = Cf::STAGES, ACC = Cf::NT_MAX;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS / STS, not generic LD / ST
   uint64_t* bars = (uint64_t*)(smem + Cf::BAR_OFF);
   uint32_t* tmem_slot = (uint32_t*)(bars + Cf::NBARS);
   float* txt = reinterpret_cast<float*>(smem + Cf::TXT_OFF);
@@ -696,7 +696,7 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int STAGES = Cf::STAGES;
   constexpr uint32_t ACC = 2;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS / STS, not generic LD / ST
   uint64_t* bars = (uint64_t*)(smem + Cf::BAR_OFF);
   uint32_t* tmem_slot = (uint32_t*)(bars + Cf::NBARS);
   float* part = reinterpret_cast<float*>(smem + Cf::PART_OFF);
@@ -924,7 +924,7 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   using Cf = FxCfg<LDK>;
   constexpr int NKB = Cf::NKB;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS / STS, not generic LD / ST
   uint64_t* bars = (uint64_t*)(smem + Cf::BAR_OFF);
   uint32_t* tmem_slot = (uint32_t*)(bars + Cf::NBARS);
   float* bs0 = reinterpret_cast<float*>(smem + Cf::BIAS_OFF);

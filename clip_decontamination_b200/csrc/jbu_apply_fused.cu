@@ -220,7 +220,9 @@ struct FzCfg {
   static constexpr int TMEM_COLS = (2 * MH * FZ_NPX <= 128) ? 128 : ((2 * MH * FZ_NPX <= 256) ? 256 : 512);
 };
 
-template <int R, int MH>
+// CST: compile-time channel count of the output rows (0 = runtime C): the 16 two-byte stores of an output row then take
+// their offsets m * C * 2 as immediates of ONE base address instead of a 64-bit add each.
+template <int R, int MH, int CST>
 __global__ void __launch_bounds__(FZ_THREADS, 1)
 jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const bf16* __restrict__ kc,
                        bf16* __restrict__ dst, int nx, int ny, int nslab, int seg, int nseg, int total_units,
@@ -229,7 +231,7 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
   constexpr int DO = Cf::DO, NLR = Cf::NLR;
   const int H2 = 2 * h, W2 = 2 * w;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS / STS, not generic LD / ST
   uint64_t* bars = (uint64_t*)(smem + Cf::BAR_OFF);
   uint32_t* tmem_slot = (uint32_t*)(bars + Cf::NBARS);
   const uint32_t smem_base = smem_u32(smem);
@@ -294,21 +296,22 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
         uint32_t r[32];
         __syncwarp();
         tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((as * MH + half) * FZ_NPX + cb * 32), r);
-        bf16* obase = dst + (size_t)crop * H2 * W2 * C + c0 + half * 128 + wq * 32 + lane;
+        const int Cs = CST ? CST : C;
+        bf16* obase = dst + (size_t)crop * H2 * W2 * Cs + c0 + half * 128 + wq * 32 + lane;
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
           const int y = y0 + cb * 2 + rr;
           if (y >= H2) continue;
-          bf16* o = obase + ((size_t)y * W2 + x0) * C;
+          bf16* o = obase + ((size_t)y * W2 + x0) * Cs;
           if (diag & 4) continue;                                  // diagnostic: no output stores
           const int mmax = min(16, W2 - x0);
           if (mmax == 16) {
 #pragma unroll
-            for (int m = 0; m < 16; ++m) o[(size_t)m * C] = __float2bfloat16_rn(__uint_as_float(r[rr * 16 + m]));
+            for (int m = 0; m < 16; ++m) o[(size_t)m * Cs] = __float2bfloat16_rn(__uint_as_float(r[rr * 16 + m]));
           } else {
 #pragma unroll
             for (int m = 0; m < 16; ++m)
-              if (m < mmax) o[(size_t)m * C] = __float2bfloat16_rn(__uint_as_float(r[rr * 16 + m]));
+              if (m < mmax) o[(size_t)m * Cs] = __float2bfloat16_rn(__uint_as_float(r[rr * 16 + m]));
           }
         }
       }
@@ -524,12 +527,12 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
   }
 }
 
-template <int R, int MH>
-int launch_apply_kernel(const bf16* src, int n_crops, int h, int w, int C, const bf16* kc, bf16* dst, const bf16* kc_img,
-                        const ShareGeom& sg, cudaStream_t st) {
+template <int R, int MH, int CST>
+int launch_apply_kernel_c(const bf16* src, int n_crops, int h, int w, int C, const bf16* kc, bf16* dst, const bf16* kc_img,
+                          const ShareGeom& sg, cudaStream_t st) {
   using Cf = FzCfg<R, MH>;
   const int H2 = 2 * h, W2 = 2 * w;
-  CSEG_SET_SMEM((jbu_apply_fused_kernel<R, MH>), Cf::SMEM_BYTES);
+  CSEG_SET_SMEM((jbu_apply_fused_kernel<R, MH, CST>), Cf::SMEM_BYTES);
   const int nx = cdiv(W2, FZ_TX), ny = cdiv(H2, FZ_RW), nslab = C / Cf::CH;
   const long long ncols = (long long)nx * n_crops * nslab;
   CSEG_REQUIRE(ncols * ny < (1ll << 31), "jbu_apply(bf16): too many tiles");
@@ -555,10 +558,17 @@ int launch_apply_kernel(const bf16* src, int n_crops, int h, int w, int C, const
     const char* e = getenv("CSEG_APPLY_DIAG");
     diag = e ? atoi(e) : 0;
   }
-  cseg_launch(jbu_apply_fused_kernel<R, MH>, dim3(grid), dim3(FZ_THREADS), Cf::SMEM_BYTES, st, src, h, w, C, kc,
+  cseg_launch(jbu_apply_fused_kernel<R, MH, CST>, dim3(grid), dim3(FZ_THREADS), Cf::SMEM_BYTES, st, src, h, w, C, kc,
               dst, nx, ny, nslab, seg, nseg, (int)total, kc_img, sg, diag);
   CSEG_LAUNCH_CHECK("jbu_apply_fused");
   return 0;
+}
+template <int R, int MH>
+int launch_apply_kernel(const bf16* src, int n_crops, int h, int w, int C, const bf16* kc, bf16* dst, const bf16* kc_img,
+                        const ShareGeom& sg, cudaStream_t st) {
+  if (C == 256) return launch_apply_kernel_c<R, MH, 256>(src, n_crops, h, w, C, kc, dst, kc_img, sg, st);   // basis form (ViT-B/L)
+  if (C == 512) return launch_apply_kernel_c<R, MH, 512>(src, n_crops, h, w, C, kc, dst, kc_img, sg, st);   // literal form
+  return launch_apply_kernel_c<R, MH, 0>(src, n_crops, h, w, C, kc, dst, kc_img, sg, st);
 }
 
 template <int R, int MH>

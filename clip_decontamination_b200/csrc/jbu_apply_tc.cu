@@ -79,7 +79,7 @@ adaptive_conv_tc_kernel(const bf16* __restrict__ hr, int H2, int W2, int C, cons
   using Cf = CvCfg<R, MH>;
   constexpr int D = Cf::D, NSRC = Cf::NSRC;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS / STS, not generic LD / ST
   uint64_t* bars = (uint64_t*)(smem + Cf::BAR_OFF);
   uint32_t* tmem_slot = (uint32_t*)(bars + Cf::NBARS);
   const uint32_t smem_base = smem_u32(smem);
