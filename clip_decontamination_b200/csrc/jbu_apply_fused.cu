@@ -463,58 +463,58 @@ jbu_apply_fused_kernel(const bf16* __restrict__ src, int h, int w, int C, const 
         cbase = (size_t)crop * border_rows(H2, W2, CSEG_JBU_FB_COMP);
       }
     };
-    auto fetch = [&](uint4 (&w)[NC0]) {                          // composite weights of this thread's pixel in tile (unit, yt)
+    auto locate = [&]() -> const uint4* {                        // composite weights of this thread's pixel in tile (unit, yt)
       const int y = yt * FZ_RW + (n >> 4), x = x0 + (n & 15);
-#pragma unroll
-      for (int k = 0; k < NC0; ++k) w[k] = make_uint4(0, 0, 0, 0);    // pixels outside the image: zero weights
-      if (y < H2 && x < W2 && !(diag & 8)) {                     // diagnostic bit 8: no composite-weight loads
-        const bf16* kp;
-        if (kc_img == nullptr) kp = kc + (cbase + (size_t)y * W2 + x) * 128;
-        else if (border_interior(y, x, H2, W2, CSEG_JBU_FB_COMP)) kp = kc_img + (org + (size_t)y * sg.pitch + x) * 128;
-        else kp = kc + (cbase + border_index(y, x, H2, W2, CSEG_JBU_FB_COMP)) * 128;
-        const uint4* kv = reinterpret_cast<const uint4*>(kp) + v0;
-#pragma unroll
-        for (int k = 0; k < NC0; ++k)
-          if (k < nck) w[k] = __ldg(kv + k);
-      }
+      if (y >= H2 || x >= W2 || (diag & 8)) return nullptr;      // outside the image: zero weights (diagnostic bit 8: no loads)
+      const bf16* kp;
+      if (kc_img == nullptr) kp = kc + (cbase + (size_t)y * W2 + x) * 128;
+      else if (border_interior(y, x, H2, W2, CSEG_JBU_FB_COMP)) kp = kc_img + (org + (size_t)y * sg.pitch + x) * 128;
+      else kp = kc + (cbase + border_index(y, x, H2, W2, CSEG_JBU_FB_COMP)) * 128;
+      return reinterpret_cast<const uint4*>(kp) + v0;
     };
     uint4 wn[NC0];
+#pragma unroll
+    for (int k = 0; k < NC0; ++k) wn[k] = make_uint4(0, 0, 0, 0);
     if (have) {
       enter_unit();
-      fetch(wn);
+      const uint4* kv = locate();
+      if (kv != nullptr) {
+#pragma unroll
+        for (int k = 0; k < NC0; ++k)
+          if (k < nck) wn[k] = __ldg(kv + k);
+      }
     }
     for (uint32_t tl = 0; have; ++tl) {
       const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
-      uint4 wv[NC0];
-#pragma unroll
-      for (int k = 0; k < NC0; ++k) wv[k] = wn[k];
       if (++yt >= yt1) {                                         // next tile of the run, or the first tile of the next unit
         unit += gridDim.x;
         have = unit < total_units;
         if (have) enter_unit();
       }
-      if (have) fetch(wn);
-      mbar_wait(b_empty0 + as * 8, aph ^ 1);
-      uint8_t* bbuf = smem + Cf::B_OFF + as * Cf::B_BUF;
+      const uint4* kvn = have ? locate() : nullptr;              // weights of the NEXT tile: requested chunk by chunk as the
+      mbar_wait(b_empty0 + as * 8, aph ^ 1);                     // registers of the current tile are scattered (one tile ahead)
+      const uint32_t bb = smem_base + Cf::B_OFF + as * Cf::B_BUF;
       if (tl < 2) {                                              // zero background, once per buffer
+        uint8_t* bbuf = smem + Cf::B_OFF + as * Cf::B_BUF;
         for (int e = bt; e < Cf::B_BUF / 16; e += 32 * FZ_BB_WARPS) reinterpret_cast<uint4*>(bbuf)[e] = make_uint4(0, 0, 0, 0);
         asm volatile("bar.sync 2, %0;" ::"n"(32 * FZ_BB_WARPS) : "memory");
       }
-      if (!(diag & 1)) {                                         // diagnostic bit 1: no band scatter
 #pragma unroll
-        for (int k = 0; k < NC0; ++k) {
-          if (k >= nck) break;                                   // warp-uniform
-          const uint32_t w4[4] = {wv[k].x, wv[k].y, wv[k].z, wv[k].w};
+      for (int k = 0; k < NC0; ++k) {
+        if (k >= nck) break;                                     // warp-uniform
+        if (!(diag & 1)) {                                       // diagnostic bit 1: no band scatter
+          const uint32_t w4[4] = {wn[k].x, wn[k].y, wn[k].z, wn[k].w};
 #pragma unroll
           for (int q2 = 0; q2 < 4; ++q2) {
             const uint32_t op = offp[k * 4 + q2];
             // taps beyond DC * DC only occur in the last chunk of the second half
             if ((NC0 + k) * 8 + 2 * q2 < DC * DC || !half)
-              *reinterpret_cast<unsigned short*>(bbuf + (op & 0xFFFFu)) = (unsigned short)(w4[q2] & 0xFFFFu);
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(bb + (op & 0xFFFFu)), "h"((unsigned short)(w4[q2] & 0xFFFFu)) : "memory");
             if ((NC0 + k) * 8 + 2 * q2 + 1 < DC * DC || !half)
-              *reinterpret_cast<unsigned short*>(bbuf + (op >> 16)) = (unsigned short)(w4[q2] >> 16);
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(bb + (op >> 16)), "h"((unsigned short)(w4[q2] >> 16)) : "memory");
           }
         }
+        wn[k] = (kvn != nullptr) ? __ldg(kvn + k) : make_uint4(0, 0, 0, 0);
       }
       fz_fence_proxy_async();
       mbar_arrive(b_full0 + as * 8);
