@@ -99,14 +99,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const bool n_fast = m_tiles >= n_tiles;
 #define TILE_M(t) (n_fast ? (t) / n_tiles : (t) % m_tiles)
 #define TILE_N(t) (n_fast ? (t) % n_tiles : (t) / m_tiles)
-  // block-diagonal products (per-crop Gram matrices in one launch): a tile is skipped by every warp role alike when its
-  // row range and its column range share no diagonal block
-  auto tile_skipped = [&](int t) -> bool {
-    if (ep.diag_rows <= 0) return false;
-    const int m0 = TILE_M(t) * BM, n0 = TILE_N(t) * BN;
-    const int r_lo = m0 / ep.diag_rows, r_hi = (min(m0 + BM, ep.M) - 1) / ep.diag_rows;
-    const int c_lo = n0 / ep.diag_rows, c_hi = (min(n0 + BN, ep.N) - 1) / ep.diag_rows;
-    return r_hi < c_lo || c_hi < r_lo;
+  // Tile enumeration, identical in every warp role: v -> (m, n).  Block-diagonal products (per-crop Gram matrices in one
+  // launch, ep.diag_rows > 0) only visit the tiles whose row range shares a diagonal block with their column range: for
+  // column tile n those are the m-tiles m_lo(n) .. m_hi(n); v = n * DM + dm enumerates them with a fixed bound DM per column,
+  // so a CTA evaluates a handful of candidates instead of scanning all m_tiles x n_tiles tile ids.
+  const int DM = ep.diag_rows > 0 ? (BN + 2 * ep.diag_rows + BM - 1) / BM + 1 : 1;
+  const int n_iter = ep.diag_rows > 0 ? n_tiles * DM : num_tiles;
+  auto tile_mn = [&](int v, int& tm, int& tn) -> bool {
+    if (ep.diag_rows <= 0) {
+      tm = TILE_M(v);
+      tn = TILE_N(v);
+      return true;
+    }
+    tn = v / DM;
+    const int dm = v - tn * DM, Lb = ep.diag_rows, n0 = tn * BN;
+    const int c_lo = n0 / Lb, c_hi = (min(n0 + BN, ep.N) - 1) / Lb;
+    const int m_lo = (c_lo * Lb) / BM, m_hi = (min((c_hi + 1) * Lb, ep.M) - 1) / BM;
+    tm = m_lo + dm;
+    return tm <= m_hi;
   };
 
   if (warp == 0 && lane == 0) {
@@ -135,9 +145,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        if (tile_skipped(tile)) continue;
-        const int m0 = TILE_M(tile) * BM, n0 = TILE_N(tile) * BN;
+      for (int tile = blockIdx.x; tile < n_iter; tile += gridDim.x) {
+        int tm, tn;
+        if (!tile_mn(tile, tm, tn)) continue;
+        const int m0 = tm * BM, n0 = tn * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(empty0 + s * 8, ph ^ 1);
@@ -160,8 +171,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       uint32_t it = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        if (tile_skipped(tile)) continue;
+      for (int tile = blockIdx.x; tile < n_iter; tile += gridDim.x) {
+        int tm, tn;
+        if (!tile_mn(tile, tm, tn)) continue;
         const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
         ++tl;
         mbar_wait(tempty0 + as * 8, aph ^ 1);      // epilogue has drained this accumulator stage
@@ -193,9 +205,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr int SST = C::SST, CPW = C::NCHUNK / C::CGROUPS;
     float* stg = reinterpret_cast<float*>(smem + C::STG_OFF) + ew * 32 * SST;
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      if (tile_skipped(tile)) continue;
-      const int m0 = TILE_M(tile) * BM, n0 = TILE_N(tile) * BN;
+    for (int tile = blockIdx.x; tile < n_iter; tile += gridDim.x) {
+      int tm, tn;
+      if (!tile_mn(tile, tm, tn)) continue;
+      const int m0 = tm * BM, n0 = tn * BN;
       const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
       ++tl;
       const int rbase = m0 + lg * 32;
