@@ -191,7 +191,7 @@ __device__ __forceinline__ uint8_t post_process(const AccumParams& p, const int*
 // <= 4..9 candidates instead of all n_crops.  When the crop logits are at crop resolution and no final resize is needed
 // (the JBU path) the PX pixels of a thread read each crop's logits with one 16-byte load per query.
 template <int QT, int PX, bool DIRECT>
-__global__ void __launch_bounds__(256, (QT <= 8) ? 3 : 2) accum_argmax_kernel(const AccumParams p) {
+__global__ void __launch_bounds__(256, 2) accum_argmax_kernel(const AccumParams p) {
   pdl_grid_sync();
   extern __shared__ int4 s_wins[];                              // [n_crops] candidate windows (compacted)
   int* s_cand = reinterpret_cast<int*>(s_wins + p.n_crops);     // [n_crops] their crop indices
@@ -253,7 +253,56 @@ __global__ void __launch_bounds__(256, (QT <= 8) ? 3 : 2) accum_argmax_kernel(co
       for (int q = 0; q < QT; ++q) acc[e][q] = 0.f;
     }
     const bool same_res = (p.lh == p.crop_h && p.lw == p.crop_w);
+    // candidate that covers all PX pixels of this thread with one aligned vector per query: its base pointer (else null)
+    auto vec_base = [&](int ci) -> const float* {
+      const int4 w = s_wins[ci];
+      const int ly = oy - w.x, lx0 = oxb - w.y;
+      if (ly < 0 || ly >= w.z || lx0 < 0 || lx0 + PX > w.w) return nullptr;
+      const int cy = ly + p.pad_top, cx0 = lx0 + p.pad_left;
+      if (((cx0 | p.lw) & (PX - 1)) != 0) return nullptr;
+      return p.crop_logits + (size_t)s_cand[ci] * p.Q * p.lh * p.lw + (size_t)cy * p.lw + cx0;
+    };
+    auto vec_load = [&](const float* base, float (&v)[QT][PX]) {
+#pragma unroll
+      for (int q = 0; q < QT; ++q)
+        if (q < p.Q) {
+          if (PX == 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(base + (size_t)q * p.lh * p.lw);
+            v[q][0] = v4.x; v[q][1 % PX] = v4.y; v[q][2 % PX] = v4.z; v[q][3 % PX] = v4.w;
+          } else {
+            const float2 v2 = *reinterpret_cast<const float2*>(base + (size_t)q * p.lh * p.lw);
+            v[q][0] = v2.x; v[q][1 % PX] = v2.y;
+          }
+        }
+    };
+    auto vec_add = [&](const float (&v)[QT][PX]) {
+#pragma unroll
+      for (int q = 0; q < QT; ++q)
+        if (q < p.Q) {
+#pragma unroll
+          for (int e = 0; e < PX; ++e) acc[e][q] += v[q][e];
+        }
+#pragma unroll
+      for (int e = 0; e < PX; ++e) ++cnt[e];
+    };
     for (int ci = 0; ci < n_cand; ++ci) {
+      if (PX >= 2 && same_res) {
+        // the loads of TWO consecutive vector candidates are in flight together (the kernel was latency bound: one
+        // candidate's 16-byte loads, a DRAM round trip, the next candidate's ...); the sums keep forward_slide's order
+        const float* b0 = vec_base(ci);
+        if (b0 != nullptr) {
+          const float* b1 = (QT <= 8 && ci + 1 < n_cand) ? vec_base(ci + 1) : nullptr;    // (register budget: Q <= 8 only)
+          float v0[QT][PX], v1[QT][PX];
+          vec_load(b0, v0);
+          if (b1 != nullptr) vec_load(b1, v1);
+          vec_add(v0);
+          if (b1 != nullptr) {
+            vec_add(v1);
+            ++ci;
+          }
+          continue;
+        }
+      }
       const int4 w = s_wins[ci];
       const int ly = oy - w.x;
       if (ly < 0 || ly >= w.z) continue;
@@ -261,35 +310,14 @@ __global__ void __launch_bounds__(256, (QT <= 8) ? 3 : 2) accum_argmax_kernel(co
       if (lx0 + PX <= 0 || lx0 >= w.w) continue;
       const int cr = s_cand[ci];
       const int cy = ly + p.pad_top, cx0 = lx0 + p.pad_left;
-      if (PX >= 2 && same_res && lx0 >= 0 && lx0 + PX <= w.w && ((cx0 | p.lw) & (PX - 1)) == 0) {
-        const float* base = p.crop_logits + (size_t)cr * p.Q * p.lh * p.lw + (size_t)cy * p.lw + cx0;
+#pragma unroll
+      for (int e = 0; e < PX; ++e) {
+        const int lx = lx0 + e;
+        if (lx < 0 || lx >= w.w || oxb + e >= p.out_w) continue;
+        ++cnt[e];
 #pragma unroll
         for (int q = 0; q < QT; ++q)
-          if (q < p.Q) {
-            if (PX == 4) {
-              const float4 v4 = *reinterpret_cast<const float4*>(base + (size_t)q * p.lh * p.lw);
-              acc[0][q] += v4.x;
-              acc[1 % PX][q] += v4.y;
-              acc[2 % PX][q] += v4.z;
-              acc[3 % PX][q] += v4.w;
-            } else {
-              const float2 v2 = *reinterpret_cast<const float2*>(base + (size_t)q * p.lh * p.lw);
-              acc[0][q] += v2.x;
-              acc[1 % PX][q] += v2.y;
-            }
-          }
-#pragma unroll
-        for (int e = 0; e < PX; ++e) ++cnt[e];
-      } else {
-#pragma unroll
-        for (int e = 0; e < PX; ++e) {
-          const int lx = lx0 + e;
-          if (lx < 0 || lx >= w.w || oxb + e >= p.out_w) continue;
-          ++cnt[e];
-#pragma unroll
-          for (int q = 0; q < QT; ++q)
-            if (q < p.Q) acc[e][q] += crop_value(p, cr, q, cy, cx0 + e);
-        }
+          if (q < p.Q) acc[e][q] += crop_value(p, cr, q, cy, cx0 + e);
       }
     }
 #pragma unroll
