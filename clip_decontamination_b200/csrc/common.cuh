@@ -106,10 +106,15 @@ __device__ __forceinline__ long long img_row_off(const ImgView& v, int Y) {
   const int b = Y / v.img_h;
   return (long long)b * v.stride_img + (long long)(Y - b * v.img_h) * v.stride_y;
 }
+// per-channel fields are picked with selects on constant indices: indexing the kernel-parameter struct with a runtime channel
+// would copy it to local memory (96-184 bytes of stack and a local load per access in the kernels that read the image)
+__device__ __forceinline__ int img_chan(const ImgView& v, int c) { return c == 0 ? v.chan[0] : (c == 1 ? v.chan[1] : v.chan[2]); }
+__device__ __forceinline__ float img_mean(const ImgView& v, int c) { return c == 0 ? v.mean[0] : (c == 1 ? v.mean[1] : v.mean[2]); }
+__device__ __forceinline__ float img_std(const ImgView& v, int c) { return c == 0 ? v.std[0] : (c == 1 ? v.std[1] : v.std[2]); }
 __device__ __forceinline__ float img_at(const ImgView& v, int c, long long row_off, int x) {
-  const long long off = row_off + (long long)v.chan[c] * v.stride_c + (long long)x * v.stride_x;
+  const long long off = row_off + (long long)img_chan(v, c) * v.stride_c + (long long)x * v.stride_x;
   if (v.dtype == CSEG_U8)      // SegDataPreProcessor: (x.float() - mean) / std, IEEE division (segmentor.py:64-67)
-    return __fdiv_rn((float)reinterpret_cast<const uint8_t*>(v.data)[off] - v.mean[c], v.std[c]);
+    return __fdiv_rn((float)reinterpret_cast<const uint8_t*>(v.data)[off] - img_mean(v, c), img_std(v, c));
   return reinterpret_cast<const float*>(v.data)[off];
 }
 

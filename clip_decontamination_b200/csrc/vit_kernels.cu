@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) patchify_vec8_kernel(const ImgView img, c
                                                             bf16* __restrict__ out, int ldo) {
   __shared__ float lut[3][256];
   if (img.dtype == CSEG_U8)
-    for (int i = threadIdx.x; i < 768; i += blockDim.x) lut[i >> 8][i & 255] = __fdiv_rn((float)(i & 255) - img.mean[i >> 8], img.std[i >> 8]);
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) lut[i >> 8][i & 255] = __fdiv_rn((float)(i & 255) - img_mean(img, i >> 8), img_std(img, i >> 8));
   __syncthreads();
   pdl_grid_sync();
   const int g_per_row = ldo >> 3, kk = 3 * ps * ps, P = gh * gw;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) patchify_vec8_kernel(const ImgView img, c
       const int cy = (p / gw) * ps + ky - pad_top, cx = (p % gw) * ps + kx - pad_left;
       const int4 w = *reinterpret_cast<const int4*>(wins + crop * 4);
       if (cy >= 0 && cy < w.z) {
-        const long long base = img_row_off(img, w.x + cy) + (long long)img.chan[c] * img.stride_c;
+        const long long base = img_row_off(img, w.x + cy) + (long long)img_chan(img, c) * img.stride_c;
         if (img.dtype == CSEG_U8) {
           const uint8_t* src = reinterpret_cast<const uint8_t*>(img.data) + base;
 #pragma unroll
