@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -448,6 +449,228 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
   if (ep.act == CSEG_ACT_GELU) return launch1<BN, STAGES, CSEG_ACT_GELU>(ta, tb, M, N, K, ep, st);
   if (ep.act == CSEG_ACT_QUICKGELU) return launch1<BN, STAGES, CSEG_ACT_QUICKGELU>(ta, tb, M, N, K, ep, st);
   return launch1<BN, STAGES, CSEG_ACT_NONE>(ta, tb, M, N, K, ep, st);
+}
+
+// =====================================================================================================
+// CTA-pair variant (cta_group::2) for the big ViT GEMMs: two CTAs of a cluster (the two SMs of a TPC) compute ONE
+// 256 x BN output tile.  Each CTA stages its own 128 rows of A and HALF of the B tile (BN / 2 rows) per k-block -- 32 KB
+// per stage instead of 48 KB: the single-CTA kernel is bound by the L2 -> SM operand feed on these shapes -- and the
+// leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 (M = 256), which reads both CTAs' shared memory and writes
+// each CTA's 128 accumulator rows into its own TMEM.
+//   full[s]    lives in the leader only: armed by the leader's producer with the bytes of BOTH CTAs; every TMA load
+//              (cp.async.bulk.tensor ... cta_group::2) signals the leader's barrier (peer bit of the address cleared)
+//   empty[s]   one per CTA: the leader's tcgen05.commit is multicast to both
+//   tfull[a]   one per CTA (multicast commit); tempty[a] lives in the leader and counts the epilogue warps of both CTAs
+//              (the peer arrives remotely)
+// The epilogue is the staged one of the single-CTA kernel (RES 0 / 1, fp32 or bf16 output, optional activation).
+// =====================================================================================================
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;       // clears the CTA-pair bit of a shared::cluster address: the even (leader) CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {       // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {    // arrive on the leader CTA's barrier at this offset
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+
+template <int BN, int STAGES>
+struct Cfg2 {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int ACC = 512 / BN;
+  static constexpr int NCHUNK = BN / 32, CGROUPS = 4, EPI_WARPS = 16, THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int SST = 36;
+  static constexpr int STG_OFF = STAGES * STAGE_BYTES;
+  static constexpr int STG_BYTES = EPI_WARPS * 32 * SST * 4;
+  static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
+  static constexpr int NBARS = 2 * STAGES + 2 * ACC;
+  static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
+};
+
+template <int BN, int STAGES, int ACT, int OUTB, int RES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg2<BN, STAGES>::THREADS, 1)
+gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K,
+                              int m2_tiles, int num_tiles, EpiParams ep) {
+  using C = Cfg2<BN, STAGES>;
+  constexpr int ACC = C::ACC;
+  static_assert(RES == 0 || RES == 1, "the pair kernel serves the ViT GEMMs: no residual or an fp32 residual");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = (uint64_t*)(smem + C::BAR_OFF);
+  uint32_t* tmem_slot = (uint32_t*)(bars + C::NBARS);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + STAGES * 8;
+  const uint32_t tfull0 = empty0 + STAGES * 8, tempty0 = tfull0 + ACC * 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int num_kb = (K + BK - 1) / BK;
+  const int n_tiles = num_tiles / m2_tiles;
+  const bool n_fast = m2_tiles >= n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + s * 8, 1);
+      mbar_init(empty0 + s * 8, 1);
+    }
+    for (int s = 0; s < ACC; ++s) {
+      mbar_init(tfull0 + s * 8, 1);
+      mbar_init(tempty0 + s * 8, 2 * C::EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();            // the peer's barriers exist before anything arrives on them remotely
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  pdl_grid_sync();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+        const int tm = n_fast ? tile / n_tiles : tile % m2_tiles, tn = n_fast ? tile % n_tiles : tile / m2_tiles;
+        const int m0 = tm * 2 * BM + (int)rank * BM, n0 = tn * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(empty0 + s * 8, ph ^ 1);
+          if (leader) mbar_expect_tx(full0 + s * 8, 2 * C::STAGE_BYTES);
+          const uint32_t a_dst = smem_base + s * C::STAGE_BYTES;
+          tma_load_2d_2sm(a_dst, &tmA, full0 + s * 8, kb * BK, m0);
+          tma_load_2d_2sm(a_dst + C::A_BYTES, &tmB, full0 + s * 8, kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN);
+      uint32_t it = 0, tl = 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs, ++tl) {
+        const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
+        mbar_wait(tempty0 + as * 8, aph ^ 1);      // the epilogue warps of BOTH CTAs have drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(full0 + s * 8, ph);
+          tc_fence_after();
+          const uint64_t adesc = make_sdesc(smem_base + s * C::STAGE_BYTES);
+          const uint64_t bdesc = make_sdesc(smem_base + s * C::STAGE_BYTES + C::A_BYTES);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma2_f16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma2_commit_mc(empty0 + s * 8);
+            if (kb == num_kb - 1) umma2_commit_mc(tfull0 + as * 8);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int lg = warp & 3;
+    const int cg = ew >> 2;
+    constexpr int SST = C::SST, CPW = C::NCHUNK / C::CGROUPS;
+    float* stg = reinterpret_cast<float*>(smem + C::STG_OFF) + ew * 32 * SST;
+    uint32_t tl = 0;
+    for (int tile = pair; tile < num_tiles; tile += n_pairs, ++tl) {
+      const int tm = n_fast ? tile / n_tiles : tile % m2_tiles, tn = n_fast ? tile % n_tiles : tile / m2_tiles;
+      const int m0 = tm * 2 * BM + (int)rank * BM, n0 = tn * BN;
+      const uint32_t as = tl % ACC, aph = (tl / ACC) & 1;
+      const int rbase = m0 + lg * 32;
+      const int nrows = min(32, ep.M - rbase);
+#pragma unroll
+      for (int ci = 0; ci < CPW; ++ci) {
+        const int cchunk = cg + ci * C::CGROUPS;
+        const int col0 = n0 + cchunk * 32;
+        const int col = col0 + lane;
+        const bool col_ok = col < ep.N;
+        float res[32];
+        if (RES == 1 && col_ok && nrows > 0) {
+          const float* rp = (const float*)ep.residual + (size_t)rbase * ep.ldr + col;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) res[rr] = (rr < nrows) ? rp[(size_t)rr * ep.ldr] : 0.f;
+        }
+        const float bv = (ep.bias != nullptr && col_ok) ? __ldg(ep.bias + col) : 0.f;
+        if (ci == 0) {
+          mbar_wait(tfull0 + as * 8, aph);
+          tc_fence_after();
+        }
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + cchunk * 32), r);
+        if (ci == CPW - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(tempty0 + as * 8);
+        }
+        if (col0 >= ep.N || nrows <= 0) continue;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(stg + lane * SST + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        __syncwarp();
+        if (col_ok) {
+          const float alpha = ep.alpha;
+          auto finish = [&](int rr) -> float {
+            float x = stg[rr * SST + lane] + bv;
+            if (ACT == CSEG_ACT_GELU) x = OUTB ? gelu_tanh(x) : gelu_fast(x);
+            else if (ACT == CSEG_ACT_QUICKGELU) x = quick_gelu(x);
+            return RES == 1 ? fmaf(x, alpha, res[rr]) : x * alpha;
+          };
+          if (OUTB) {
+            bf16* cp = (bf16*)ep.C + (size_t)rbase * ep.ldc + col;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              if (rr < nrows) cp[(size_t)rr * ep.ldc] = __float2bfloat16_rn(finish(rr));
+          } else {
+            float* cp = (float*)ep.C + (size_t)rbase * ep.ldc + col;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              if (rr < nrows) cp[(size_t)rr * ep.ldc] = finish(rr);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();            // neither CTA leaves (or frees TMEM) while the other may still signal it
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
 }
 
 // =====================================================================================================
@@ -1229,6 +1452,32 @@ int cseg_jbu_kernel_fixup_tc(const void* k, int lda, const void* W0, int ldw0, c
   return launch_kernel_fixup<64>(k, lda, W0, ldw0, b0, W3, ldw3, b3, M, out, ldo, st);
 }
 
+template <int ACT, int OUTB, int RES>
+int launch2cta3(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+  constexpr int BN2 = 256, ST2 = 4;
+  using C = Cfg2<BN2, ST2>;
+  CSEG_SET_SMEM((gemm_bf16_tcgen05_2cta_kernel<BN2, ST2, ACT, OUTB, RES>), C::SMEM_BYTES);
+  const int m2_tiles = cdiv(M, 2 * BM), num_tiles = m2_tiles * (N / BN2);
+  const int grid = 2 * std::min(num_tiles, sm_count() / 2);
+  cseg_launch(gemm_bf16_tcgen05_2cta_kernel<BN2, ST2, ACT, OUTB, RES>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, K,
+              m2_tiles, num_tiles, ep);
+  CSEG_LAUNCH_CHECK("gemm_bf16_tcgen05_2cta");
+  return 0;
+}
+template <int ACT>
+int launch2cta1(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+  if (ep.out_bf16) return ep.residual ? launch2cta3<ACT, 1, 1>(ta, tb, M, N, K, ep, st) : launch2cta3<ACT, 1, 0>(ta, tb, M, N, K, ep, st);
+  return ep.residual ? launch2cta3<ACT, 0, 1>(ta, tb, M, N, K, ep, st) : launch2cta3<ACT, 0, 0>(ta, tb, M, N, K, ep, st);
+}
+bool gemm_2cta_enabled() {     // CSEG_GEMM_2CTA=0 selects the single-CTA kernel for every shape (A/B measurements)
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CSEG_GEMM_2CTA");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
 // Per-block Gram matrices of fp32-grade accuracy on the bf16 tensor cores: X is the [hi | lo] bf16 split of a row-normalised
 // fp32 matrix ([M, 2 * width], width % 64 == 0); value(b, i, j) = alpha * <x_(b,i), x_(b,j)> for the square diagonal blocks
 // of block_rows rows and i, j >= skip.
@@ -1287,9 +1536,21 @@ int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int
   CUtensorMap ta, tb;
   int rc = make_map(&ta, A, M, K, lda, BM);
   if (rc) return rc;
+  EpiParams ep{bias, residual, ldr, res_dtype == CSEG_BF16, alpha, act, out_dtype == CSEG_BF16, C, ldc, M, N, diag_rows, 0, 0, 0, 0, 0};
+  // CTA pairs (cta_group::2) for the big N = 256 k GEMMs of the ViT: the pair stages 32 KB per k-block and SM instead of 48
+  // (measured at M = 18 912: QKV 59.5 -> 53.6 us, fc2 82.4 -> 74.6 us; the K = 768 residual GEMM (out-proj) is paced by its
+  // epilogue and loses 8 % to the pair's lock step, the GELU GEMM (fc1) is epilogue bound either way: both stay single-CTA)
+  const bool pair_shape = act == CSEG_ACT_NONE && (residual == nullptr || K >= 1536);
+  if (bn == 256 && N % 256 == 0 && diag_rows == 0 && (residual == nullptr || res_dtype == CSEG_F32) && sms % 2 == 0 && pair_shape &&
+      (long long)cdiv(M, 2 * BM) * (N / 256) >= sms / 2 && gemm_2cta_enabled()) {
+    rc = make_map(&tb, B, N, K, ldb, 128);
+    if (rc) return rc;
+    if (act == CSEG_ACT_GELU) return launch2cta1<CSEG_ACT_GELU>(ta, tb, M, N, K, ep, st);
+    if (act == CSEG_ACT_QUICKGELU) return launch2cta1<CSEG_ACT_QUICKGELU>(ta, tb, M, N, K, ep, st);
+    return launch2cta1<CSEG_ACT_NONE>(ta, tb, M, N, K, ep, st);
+  }
   rc = make_map(&tb, B, N, K, ldb, bn);
   if (rc) return rc;
-  EpiParams ep{bias, residual, ldr, res_dtype == CSEG_BF16, alpha, act, out_dtype == CSEG_BF16, C, ldc, M, N, diag_rows, 0, 0, 0, 0, 0};
   if (bn == 64) return launch<64, 6>(ta, tb, M, N, K, ep, st);
   if (bn == 192) return launch<192, 4>(ta, tb, M, N, K, ep, st);
   if (bn == 256) return launch<256, 3>(ta, tb, M, N, K, ep, st);
