@@ -44,6 +44,46 @@ struct EpiParams {
   int split_kb;
 };
 
+// Vector form of the staged epilogue for full, aligned chunks WITHOUT a residual: a lane owns FOUR consecutive columns of
+// rows r4, r4 + 4, ... (r4 = lane / 8): 8 x LDS.128 from the staging tile and 8 vector stores per chunk instead of 32 + 32
+// scalar ones (8 instead of 11 instructions per element in the GELU epilogue of fc1, which paces that GEMM once the CTA
+// pair has removed the operand-feed limit).  The fp32-residual variants keep the scalar form: with the residual registers
+// on top they spill at the 96-register budget of the 18-warp CTA (measured: out-proj 10 % slower).
+template <int ACT, int OUTB>
+__device__ __forceinline__ void epi_vec_chunk(const float* stg, int SST, const EpiParams& ep, int rbase, int nrows, int col0, int lane) {
+  const int r4 = lane >> 3, c4 = (lane & 7) * 4;
+  const float alpha = ep.alpha;
+  const float4 bv4 = ep.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + r4;
+    if (row >= nrows) continue;
+    const float4 a = *reinterpret_cast<const float4*>(stg + row * SST + c4);
+    float x[4] = {a.x + bv4.x, a.y + bv4.y, a.z + bv4.z, a.w + bv4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (ACT == CSEG_ACT_GELU) x[e] = OUTB ? gelu_tanh(x[e]) : gelu_fast(x[e]);
+      else if (ACT == CSEG_ACT_QUICKGELU) x[e] = quick_gelu(x[e]);
+      x[e] *= alpha;
+    }
+    if (OUTB) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]), hi = __floats2bfloat162_rn(x[2], x[3]);
+      uint2 u;
+      u.x = *reinterpret_cast<const uint32_t*>(&lo);
+      u.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>((bf16*)ep.C + (size_t)(rbase + row) * ep.ldc + col0 + c4) = u;
+    } else {
+      *reinterpret_cast<float4*>((float*)ep.C + (size_t)(rbase + row) * ep.ldc + col0 + c4) = make_float4(x[0], x[1], x[2], x[3]);
+    }
+  }
+}
+__device__ __forceinline__ bool epi_vec_ok(const EpiParams& ep, int col0, bool outb) {
+  if (col0 + 32 > ep.N || (ep.ldc & 3) != 0) return false;
+  if (((uintptr_t)ep.C & (outb ? 7 : 15)) != 0) return false;
+  if (ep.bias != nullptr && ((uintptr_t)ep.bias & 15) != 0) return false;
+  return true;
+}
+
 // Persistent, warp-specialised kernel.  One CTA per SM loops over output tiles (tile id -> (m, n) with m
 // fastest, so concurrently running CTAs share the B tile in L2):
 //   warp 0      TMA producer      smem ring of STAGES x (A 128x64 + B BNx64), full/empty mbarriers
@@ -320,6 +360,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<uint4*>(stg + lane * SST + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
         __syncwarp();
+        if (RES == 0 && !direct && epi_vec_ok(ep, col0, OUTB != 0)) {       // warp-uniform
+          epi_vec_chunk<ACT, OUTB>(stg, SST, ep, rbase, nrows, col0, lane);
+          __syncwarp();
+          continue;
+        }
         if (RES == 3 && ep.cmp_mode == 1) {
           // row blocks of 32, column-major inside a block ([i / 32][j][i % 32], cmp_rs columns per block): lane = ROW here, so
           // the 32 rows of one column are (up to a block change) consecutive floats -- coalesced stores
@@ -642,6 +687,11 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<uint4*>(stg + lane * SST + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
         __syncwarp();
+        if (RES == 0 && epi_vec_ok(ep, col0, OUTB != 0)) {       // warp-uniform
+          epi_vec_chunk<ACT, OUTB>(stg, SST, ep, rbase, nrows, col0, lane);
+          __syncwarp();
+          continue;
+        }
         if (col_ok) {
           const float alpha = ep.alpha;
           auto finish = [&](int rr) -> float {
@@ -1540,7 +1590,7 @@ int cseg_gemm_bf16_tc(const void* A, int lda, const void* B, int ldb, int M, int
   // CTA pairs (cta_group::2) for the big N = 256 k GEMMs of the ViT: the pair stages 32 KB per k-block and SM instead of 48
   // (measured at M = 18 912: QKV 59.5 -> 53.6 us, fc2 82.4 -> 74.6 us; the K = 768 residual GEMM (out-proj) is paced by its
   // epilogue and loses 8 % to the pair's lock step, the GELU GEMM (fc1) is epilogue bound either way: both stay single-CTA)
-  const bool pair_shape = act == CSEG_ACT_NONE && (residual == nullptr || K >= 1536);
+  const bool pair_shape = residual == nullptr || (act == CSEG_ACT_NONE && K >= 1536);
   if (bn == 256 && N % 256 == 0 && diag_rows == 0 && (residual == nullptr || res_dtype == CSEG_F32) && sms % 2 == 0 && pair_shape &&
       (long long)cdiv(M, 2 * BM) * (N / 256) >= sms / 2 && gemm_2cta_enabled()) {
     rc = make_map(&tb, B, N, K, ldb, 128);

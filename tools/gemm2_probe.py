@@ -12,7 +12,8 @@ from clip_decontamination_b200._lib import ACT_GELU, ACT_NONE  # noqa: E402
 
 torch.manual_seed(0)
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 18912
-cases = [('qkv', 2304, 768, None, False, torch.bfloat16), ('out', 768, 768, None, True, torch.float32),
+cases = [('fc1-noact', 3072, 768, None, False, torch.bfloat16), ('fc1-f32out', 3072, 768, None, False, torch.float32),
+         ('qkv', 2304, 768, None, False, torch.bfloat16), ('out', 768, 768, None, True, torch.float32),
          ('fc1', 3072, 768, ACT_GELU, False, torch.bfloat16), ('fc2', 768, 3072, None, True, torch.float32)]
 for name, N, K, act, res, odt in cases:
     A = (torch.randn(M, K, device='cuda') * 0.5).to(torch.bfloat16)
