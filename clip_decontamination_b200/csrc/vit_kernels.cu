@@ -167,56 +167,68 @@ __global__ void layernorm_kernel(const float* x, int rows, int width, const floa
   for (int c = lane; c < width; c += 32) orow[c] = from_f32<T>((xr[c] - mean) * rstd * gamma[c] + beta[c]);
 }
 
-// single pass: the row lives in registers (float4 x LNV per lane), for width % 4 == 0 and width <= 128*LNV
+// single pass: the row lives in registers (float4 x LNV per lane), for width % 4 == 0 and width <= 128*LNV.
+// Grid-stride over rows with the NEXT row of the warp requested before the current one is reduced (the one-row-per-warp form
+// ran at 0.64 of the copy bandwidth: every warp paid a full DRAM round trip and a CTA launch for 3 KB of traffic).
 constexpr int LNV = 10;
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(256) layernorm_reg_kernel(const float* x, int rows, int width,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, T* out) {
   pdl_grid_sync();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  if (warp0 >= rows) return;
   const int nv = width >> 2;
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * width);
-  float4 buf[LNV];
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < LNV; ++k) {
-    const int v = lane + 32 * k;
-    if (v < nv) {
-      buf[k] = xr[v];
-      s += (buf[k].x + buf[k].y) + (buf[k].z + buf[k].w);
-    }
-  }
-  const float mean = warp_sum(s) / width;
-  float q = 0.f;
-#pragma unroll
-  for (int k = 0; k < LNV; ++k) {
-    const int v = lane + 32 * k;
-    if (v < nv) {
-      const float a = buf[k].x - mean, b = buf[k].y - mean, c = buf[k].z - mean, d = buf[k].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / width + eps);
-  T* orow = out + (size_t)warp * width;
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
+  float4 buf[NV], nxt[NV];
+  {
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp0 * width);
 #pragma unroll
-  for (int k = 0; k < LNV; ++k) {
-    const int v = lane + 32 * k;
-    if (v < nv) {
-      const float4 g = __ldg(g4 + v), b = __ldg(b4 + v);
-      const float o0 = (buf[k].x - mean) * rstd * g.x + b.x, o1 = (buf[k].y - mean) * rstd * g.y + b.y;
-      const float o2 = (buf[k].z - mean) * rstd * g.z + b.z, o3 = (buf[k].w - mean) * rstd * g.w + b.w;
-      if (sizeof(T) == 4) {
-        reinterpret_cast<float4*>(orow)[v] = make_float4(o0, o1, o2, o3);
-      } else {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
-        uint2 u;
-        u.x = *reinterpret_cast<uint32_t*>(&lo);
-        u.y = *reinterpret_cast<uint32_t*>(&hi);
-        reinterpret_cast<uint2*>(orow)[v] = u;
+    for (int k = 0; k < NV; ++k)
+      if (lane + 32 * k < nv) nxt[k] = xr[lane + 32 * k];
+  }
+  for (int row = warp0; row < rows; row += nwarps) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) buf[k] = nxt[k];
+    if (row + nwarps < rows) {
+      const float4* xn = reinterpret_cast<const float4*>(x + (size_t)(row + nwarps) * width);
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        if (lane + 32 * k < nv) nxt[k] = xn[lane + 32 * k];
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      if (lane + 32 * k < nv) s += (buf[k].x + buf[k].y) + (buf[k].z + buf[k].w);
+    const float mean = warp_sum(s) / width;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      if (lane + 32 * k < nv) {
+        const float a = buf[k].x - mean, b = buf[k].y - mean, c = buf[k].z - mean, d = buf[k].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / width + eps);
+    T* orow = out + (size_t)row * width;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nv) {
+        const float4 g = __ldg(g4 + v), b = __ldg(b4 + v);
+        const float o0 = (buf[k].x - mean) * rstd * g.x + b.x, o1 = (buf[k].y - mean) * rstd * g.y + b.y;
+        const float o2 = (buf[k].z - mean) * rstd * g.z + b.z, o3 = (buf[k].w - mean) * rstd * g.w + b.w;
+        if (sizeof(T) == 4) {
+          reinterpret_cast<float4*>(orow)[v] = make_float4(o0, o1, o2, o3);
+        } else {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&lo);
+          u.y = *reinterpret_cast<uint32_t*>(&hi);
+          reinterpret_cast<uint2*>(orow)[v] = u;
+        }
       }
     }
   }
@@ -850,12 +862,23 @@ int cseg_layernorm(const float* x, int rows, int width, const float* gamma, cons
                    int out_dtype, void* out, void* stream) {
   CSEG_REQUIRE(rows > 0 && width > 0, "layernorm: bad shape");
   const int blocks = cdiv((long long)rows * 32, 256);
+  const int pblocks = std::min(blocks, sm_count() * 6);        // register kernel: persistent, grid-stride over rows
   const bool reg_path = (width % 4 == 0) && width <= 128 * LNV && (((uintptr_t)x | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0;
   if (reg_path) {
-    if (out_dtype == CSEG_BF16)
-      cseg_launch(layernorm_reg_kernel<bf16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, rows, width, gamma, beta, eps, (bf16*)out);
-    else
-      cseg_launch(layernorm_reg_kernel<float>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, rows, width, gamma, beta, eps, (float*)out);
+    const int need = cdiv(width / 4, 32);          // float4 vectors per lane
+#define CSEG_LN_LAUNCH(NVV)                                                                                                        \
+    do {                                                                                                                           \
+      if (out_dtype == CSEG_BF16)                                                                                                  \
+        cseg_launch(layernorm_reg_kernel<bf16, NVV>, dim3(pblocks), dim3(256), 0, (cudaStream_t)stream, x, rows, width, gamma, beta, eps, (bf16*)out); \
+      else                                                                                                                         \
+        cseg_launch(layernorm_reg_kernel<float, NVV>, dim3(pblocks), dim3(256), 0, (cudaStream_t)stream, x, rows, width, gamma, beta, eps, (float*)out); \
+    } while (0)
+    if (need <= 2) CSEG_LN_LAUNCH(2);
+    else if (need <= 4) CSEG_LN_LAUNCH(4);
+    else if (need <= 6) CSEG_LN_LAUNCH(6);
+    else if (need <= 8) CSEG_LN_LAUNCH(8);
+    else CSEG_LN_LAUNCH(10);
+#undef CSEG_LN_LAUNCH
   } else if (out_dtype == CSEG_BF16)
     cseg_launch(layernorm_kernel<bf16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, rows, width, gamma, beta, eps, (bf16*)out);
   else
