@@ -556,7 +556,7 @@ class SegEngine:
                  logit_scale: float = 50.0, slide_stride: int = 112, slide_crop: int = 224,
                  cls_token_lambda: float = 0.0, global_debias_factor: float = 0.0, bg_idx: int = 0,
                  upsampler: Optional[JBUEngine] = None, sim_cfg: Optional[dict] = None,
-                 outlier_cfg: Optional[dict] = None, jbu_chunk: int = 48, basis: bool = True):
+                 outlier_cfg: Optional[dict] = None, jbu_chunk: int = 192, basis: bool = True):
         self.v = visual
         self.device = visual.device
         self.text = query_features.detach().to(self.device, torch.float32).contiguous()
