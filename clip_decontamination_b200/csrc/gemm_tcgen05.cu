@@ -1186,8 +1186,9 @@ basis_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // Two chained tcgen05 GEMMs per 128-row panel.  The hidden activations never leave the SM: the first epilogue
 // writes gelu(.) as bf16 straight into the SWIZZLE_128B K-major layout the second MMA reads; the residual is read
 // back from the TMA-loaded k tile in shared memory.  HBM traffic = read k once + write out once.
-//   warp 0 TMA producer (W0, W3 once; k panels, 2-stage ring)     warp 1 MMA issuer (MMA1 of panel i+1 before
-//   MMA2 of panel i)     warps 2-5 epilogue 1 (D1 -> gelu -> H tile)     warps 6-9 epilogue 2 (D2 + k + b3 -> out)
+//   warp 0 TMA producer (W0, W3 once; k panels, 3-slot ring)     warp 1 MMA issuer (MMA1 of panel i+1 before
+//   MMA2 of panel i)     warps 2-9 epilogue 1 (D1 -> gelu -> H tile)     warps 10-17 epilogue 2 (D2 + k + b3 -> out);
+//   both epilogues: lane quadrant = warp % 4, two warps per quadrant split the column chunks
 // =====================================================================================================
 template <int LDK>
 struct FxCfg {
@@ -1199,7 +1200,9 @@ struct FxCfg {
   static constexpr int BAR_OFF = BIAS_OFF + 2 * LDK * 4;
   static constexpr int NBARS = 19;
   static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
-  static constexpr int E1W = 4, THREADS = 32 * (2 + E1W + 4), TMEM_COLS = 4 * LDK;
+  // 8 + 8 epilogue warps: with one warp per scheduler the two epilogues were latency bound (source-level samples: issuing
+  // 33 % of the cycles, the rest fixed-latency / shared-memory waits of a single dependent chain)
+  static constexpr int E1W = 8, E2W = 8, THREADS = 32 * (2 + E1W + E2W), TMEM_COLS = 4 * LDK;
 };
 
 template <int LDK>
@@ -1235,11 +1238,11 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(d1_full0 + i * 8, 1);
-      mbar_init(d1_empty0 + i * 8, 4);
-      mbar_init(h_full0 + i * 8, 128);
+      mbar_init(d1_empty0 + i * 8, Cf::E1W);
+      mbar_init(h_full0 + i * 8, 32 * Cf::E1W);
       mbar_init(h_empty0 + i * 8, 1);
       mbar_init(d2_full0 + i * 8, 1);
-      mbar_init(d2_empty0 + i * 8, 4);
+      mbar_init(d2_empty0 + i * 8, Cf::E2W);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1322,9 +1325,12 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mma2(i);
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + Cf::E1W) {
     // ---- epilogue 1: hidden = gelu(D1 + b0) -> bf16 H tile (K-major, SWIZZLE_128B) ----
+    // lane quadrant = warp % 4, column half = (warp - 2) / 4
     const int lg = warp & 3, row = lg * 32 + lane;
+    constexpr int NC1 = (LDK / 32) / (Cf::E1W / 4);
+    const int c1_0 = ((warp - 2) >> 2) * NC1;
     for (int i = 0; i < n_my; ++i) {
       const uint32_t st = i & 1, u = i >> 1;
       mbar_wait(d1_full0 + st * 8, u & 1);
@@ -1332,11 +1338,11 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       uint8_t* hrow = smem + Cf::H_OFF + st * Cf::P_BYTES + row * 128;
 #pragma unroll 1
-      for (int c4 = 0; c4 < LDK / 32; ++c4) {
+      for (int c4 = c1_0; c4 < c1_0 + NC1; ++c4) {
         uint32_t r[32];
         __syncwarp();
         tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(st * 2 * LDK + c4 * 32), r);
-        if (c4 == LDK / 32 - 1) {
+        if (c4 == c1_0 + NC1 - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(d1_empty0 + st * 8);
@@ -1366,6 +1372,8 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     //      swizzled position, every thread owns its row); the finished tile leaves with one TMA store per k-block, so
     //      the global writes are full lines instead of 32 row-strided 16-byte pieces per instruction ----
     const int lg = warp & 3, row = lg * 32 + lane;
+    constexpr int NC2 = (LDK / 32) / (Cf::E2W / 4);
+    const int c2_0 = ((warp - 2 - Cf::E1W) >> 2) * NC2;
     for (int i = 0; i < n_my; ++i) {
       const uint32_t st = i & 1, u = i >> 1;
       const int panel = blockIdx.x + i * gridDim.x;
@@ -1374,11 +1382,11 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t sa = i % Cf::NA;
       uint8_t* arow = smem + Cf::A_OFF + sa * Cf::P_BYTES + row * 128;
 #pragma unroll 1
-      for (int c4 = 0; c4 < LDK / 32; ++c4) {
+      for (int c4 = c2_0; c4 < c2_0 + NC2; ++c4) {
         uint32_t r[32];
         __syncwarp();
         tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(st * 2 * LDK + LDK + c4 * 32), r);
-        if (c4 == LDK / 32 - 1) {                                  // accumulator fully read
+        if (c4 == c2_0 + NC2 - 1) {                                // this warp's part of the accumulator has been read
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(d2_empty0 + st * 8);
@@ -1404,7 +1412,7 @@ kernel_fixup_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> visible to the TMA store
-      asm volatile("bar.sync 3, 128;" ::: "memory");                    // the four epilogue-2 warps
+      asm volatile("bar.sync 3, %0;" ::"n"(32 * Cf::E2W) : "memory");   // the epilogue-2 warps
       if (warp == 2 + Cf::E1W && lane == 0) {
         for (int kb = 0; kb < NKB; ++kb)
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
