@@ -78,6 +78,36 @@ def test_gemm_bf16_matches_cuda_core_reference(ops):
     assert (o1 - o2).abs().max().item() < 5e-3
 
 
+@pytest.mark.parametrize('M,N,K,act,res,odt', [
+    (18912, 2304, 768, 0, False, torch.bfloat16),      # QKV
+    (18912, 3072, 768, 1, False, torch.bfloat16),      # fc1 (GELU, vector epilogue)
+    (18912, 768, 3072, 0, True, torch.float32),        # fc2 (fp32 residual, in place)
+    (18816, 768, 768, 0, False, torch.float32),        # patch embedding: the peer CTA of the last pair is entirely out of range
+    (9500, 512, 200, 0, False, torch.float32),         # M tail inside the peer CTA, K tail (zero-filled by TMA)
+    (3152, 2304, 768, 2, False, torch.bfloat16),       # one image (16 crops), QuickGELU
+])
+def test_gemm_cta_pair_matches_cuda_core_reference(ops, M, N, K, act, res, odt):
+    """CTA-pair GEMM (tcgen05.mma.cta_group::2: each CTA of a 2-CTA cluster stages its 128 A rows and half of the B tile)
+    against the CUDA-core reference kernel on the same operands; shapes chosen so that cseg_gemm takes the pair kernel
+    (N % 256 == 0, enough 256-row tiles, no residual or K >= 1536)."""
+    A = (torch.randn(M, K, generator=_g(21)) * 0.5).bfloat16().cuda()
+    B = (torch.randn(N, K, generator=_g(22)) * 0.05).bfloat16().cuda()
+    bias = torch.randn(N, generator=_g(23)).cuda()
+    x = torch.randn(M, N, generator=_g(24)).cuda() if res else None
+    o1 = x.clone() if res else torch.full((M, N), float('nan'), device='cuda', dtype=odt)
+    o2 = x.clone() if res else torch.empty((M, N), device='cuda', dtype=odt)
+    kw = dict(bias=bias, act=act)
+    ops.gemm(A, B, o1, residual=o1 if res else None, **kw)
+    ops.gemm(A, B, o2, residual=o2 if res else None, reference=True, **kw)
+    torch.cuda.synchronize()
+    assert torch.isfinite(o1.float()).all()
+    d = (o1.float() - o2.float()).abs()
+    if odt == torch.bfloat16:      # the two kernels accumulate in different orders: at most one bf16 ulp (2^-7 relative) apart
+        assert (d <= 0.0079 * o2.float().abs() + 1e-2).all()
+    else:
+        assert d.max().item() < 2e-3
+
+
 def test_gemm_strided_views(ops):
     """operands / outputs that are column-padded views (lda != K, ldc != N)."""
     M, N, K = 200, 121, 128
