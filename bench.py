@@ -482,7 +482,7 @@ def main():
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype=args.precision, data='synthetic',
                 config=dict(workload=WORKLOAD, tiles_per_step_per_gpu=T, crops_per_tile=CROPS,
-                            l2='working set of a step (JBU stage buffers, ~1.5 GB per 16-crop chunk) far exceeds the 126 MB L2; '
+                            l2='working set of a step (JBU stage buffers, ~95 MB per crop: ~9 GB for the 96 crops of a step) far exceeds the 126 MB L2; '
                                'the batch holds %d different tiles' % T, parallelism=f'image-sharded x{world}'),
                 clocks=clocks, gpu_launches=int(launches),
                 e2e=dict(value=e2e, unit='MP/s', h2d_bytes_per_step=T * H * W * 3, d2h_bytes_per_step=T * H * W + 3 * K * 8,
