@@ -40,6 +40,9 @@ WORKLOADS = {
     'isaid896': dict(H=896, W=896, model='ViT-B/16', cls='isaid', thd=0.4, bg=0, up=True),
     'road1024': dict(H=1024, W=1024, model='ViT-B/16', cls='roadval', thd=0.7, bg=0, up=True),
     'vaihingen512_noup': dict(H=512, W=512, model='ViT-B/16', cls='vaihingen', thd=0.1, bg=5, up=False),
+    # BASELINE config 3: ViT-L/14 (L = 257, d = 1024), no upsampler (JBU x16 is shape-incompatible with patch 14), 81 crops
+    'loveda1024_vitl': dict(H=1024, W=1024, model='ViT-L-14', cls='loveda', thd=0.3, bg=0, up=False,
+                            text='seg_loveda_vitl_1024.npz'),
 }
 
 
@@ -108,7 +111,10 @@ def build_model(device, precision='bf16', wl=None):
     from clip_decontamination_b200.open_clip.synthetic import synthetic_jbu_state_dict
     from clip_decontamination_b200.segmentor import SegmentorEx
     wl = wl or WORKLOADS['vaihingen512']
-    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'bench_text.npz'))
+    if wl.get('text'):                 # query features of this model width live in the config's own golden file
+        qf = np.load(os.path.join(ROOT, 'tests', 'golden', wl['text']))['query_features']
+    else:
+        qf = np.load(os.path.join(ROOT, 'tests', 'golden', 'bench_text.npz'))[f"{wl['cls']}_query_features"]
     net = create_model(wl['model'], pretrained=None, precision='fp32' if precision == 'fp32' else 'fp16')
     return SegmentorEx(clip_type='CLIP', vit_type=wl['model'], model_type='Experimental',
                        name_path=os.path.join(ROOT, 'configs', f"cls_{wl['cls']}.txt"), device=device,
@@ -117,8 +123,8 @@ def build_model(device, precision='bf16', wl=None):
                        apply_similarity_enhancement=True,
                        similarity_enhancement_cfg=dict(similarity_weight=1.0, temperature=1.0, add_self_similarity=True),
                        sim_feat_up_cfg=dict(model_name='jbu_one', model_path=None), precision=precision, net=net,
-                       query_features=torch.from_numpy(gold[f"{wl['cls']}_query_features"]),
-                       upsampler_state_dict=synthetic_jbu_state_dict('jbu_one', 512, 1))
+                       query_features=torch.from_numpy(qf),
+                       upsampler_state_dict=synthetic_jbu_state_dict('jbu_one', 512, 1) if wl['up'] else None)
 
 
 # ---- the CPU arm: the reference's algorithm for this path on the host cores ----------------------------

@@ -1,4 +1,5 @@
-// Standard multi-head attention of the ViT blocks on tcgen05 (bf16, head_dim 64, L <= 208, no statistics output):
+// Standard multi-head attention of the ViT blocks on tcgen05 (bf16, head_dim 64, L <= 272; described for L <= 208, the
+// differences of the 272-key shape are listed at AtCfg):
 //   out = softmax(q k^T / 8) v                                (nn.MultiheadAttention, open_clip/transformer.py:204,218-232)
 //
 // One work item = one (crop, head); a persistent CTA per SM walks the items.  L <= 208 keys fit one MMA in N, so there
@@ -21,15 +22,39 @@ namespace {
 constexpr int AT_HD = 64, AT_BM = 128, AT_LP = 208;           // keys padded to 13 K-steps of 16
 constexpr int AT_SMW = 16;                                     // softmax / epilogue warps: row quarter = warp % 4, key quarter = warp / 4
 constexpr int AT_THREADS = 32 * (AT_SMW + 2);
-constexpr int AT_Q_BYTES = AT_BM * 128, AT_KV_BYTES = AT_LP * 128, AT_P_BLK = AT_BM * 128, AT_P_BYTES = 4 * AT_P_BLK;
-constexpr int AT_Q_OFF = 0, AT_K_OFF = 2 * AT_Q_BYTES, AT_V_OFF = AT_K_OFF + 2 * AT_KV_BYTES;
-constexpr int AT_P_OFF = AT_V_OFF + 2 * AT_KV_BYTES, AT_RED_OFF = AT_P_OFF + AT_P_BYTES;
-constexpr int AT_RED_BYTES = (4 * 128 + 2 * 4 * 128 + AT_LP) * 4;   // smax[4][128], ssum[2 tiles][4][128], scls[AT_LP]
-constexpr int AT_BAR_OFF = AT_RED_OFF + AT_RED_BYTES, AT_NBARS = 15;
-constexpr int AT_SMEM = AT_BAR_OFF + AT_NBARS * 8 + 16 + 1024;
-constexpr int AT_S_COLS = 224, AT_O_COL = 448, AT_TMEM_COLS = 512;
+constexpr int AT_Q_BYTES = AT_BM * 128, AT_P_BLK = AT_BM * 128;
+// (the shared-memory layout of the standard kernel depends on the padded key count: AtCfg<LP> below)
+constexpr int AT_O_COL = 448, AT_TMEM_COLS = 512;
 // key quarters: [0, 64), [64, 112), [112, 160), [160, 208)
 __host__ __device__ constexpr int at_qbegin(int k) { return k == 0 ? 0 : (k == 1 ? 64 : (k == 2 ? 112 : (k == 3 ? 160 : AT_LP))); }
+
+// Shape of the standard kernel by padded key count LP.  LP = 208 (ViT-B/16 at 224: L = 197): two S accumulators, K and V
+// double buffered.  LP = 272 (ViT-L/14 at 224: L = 257): 272 + 64 TMEM columns leave room for ONE S accumulator (the next
+// S = Q.K^T is issued as soon as the softmax warps have read the current one), S is issued as two MMAs (N <= 256), K / V
+// arrive as two TMA boxes (box rows <= 256), K stays double buffered and V single (227 KB of shared memory): V of the next
+// item is only needed one softmax after its K.
+template <int LP>
+struct AtCfg {
+  static_assert(LP % 16 == 0 && LP <= 272, "keys padded to k-steps of 16");
+  static constexpr int NSB = LP <= 224 ? 2 : 1;                 // S accumulators in TMEM
+  static constexpr int S_COLS = 224;                            // column stride between them
+  static constexpr int NVB = LP <= 208 ? 2 : 1;                 // V buffers
+  static constexpr int KV_BYTES = LP * 128;
+  static constexpr int KV_BOX = LP <= 256 ? LP : LP / 2;        // TMA box rows
+  static constexpr int KV_LOADS = LP / KV_BOX;
+  static constexpr int N0 = LP <= 256 ? LP : 144, N1 = LP - N0; // S = [N0 | N1] key columns per MMA
+  static constexpr int P_BYTES = ((LP + 63) / 64) * AT_P_BLK;
+  static constexpr int Q_OFF = 0, K_OFF = 2 * AT_Q_BYTES, V_OFF = K_OFF + 2 * KV_BYTES, P_OFF = V_OFF + NVB * KV_BYTES;
+  static constexpr int RED_OFF = P_OFF + P_BYTES, RED_BYTES = (4 * 128 + 2 * 4 * 128 + LP) * 4;
+  static constexpr int BAR_OFF = RED_OFF + RED_BYTES, NBARS = 19;
+  static constexpr int SMEM = BAR_OFF + NBARS * 8 + 16 + 1024;
+  static_assert(KV_BOX % 8 == 0 && N0 % 16 == 0 && N1 % 16 == 0 && (N0 * 128) % 1024 == 0, "swizzle atoms");
+  static_assert(SMEM <= 227 * 1024, "shared memory");
+  // key quarters of the softmax warps (multiples of 16)
+  __host__ __device__ static constexpr int qbegin(int k) {
+    return LP <= 208 ? at_qbegin(k) : (k == 0 ? 0 : (k == 1 ? 80 : (k == 2 ? 144 : (k == 3 ? 208 : LP))));
+  }
+};
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -78,23 +103,24 @@ __host__ __device__ constexpr uint32_t at_idesc_pv() {
 // STATS: additionally emits P[0, 1+i] and P[1+i, 1+i] per (crop, head) -- the entries of the need_weights=True matrix that
 // detect_outliers_by_attention reads (outlier_suppression.py:46-53): the diagonal numerator stays in a register of the
 // thread that owns row i, the CLS row's numerators are parked in shared memory; both are normalised in the epilogue.
-template <bool STATS>
+template <bool STATS, int LP>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, int L, int heads,
-                    int n_items, bf16* __restrict__ out, float scale_log2e, int diag, float* __restrict__ stats) {
+                    int n_items, int mt, bf16* __restrict__ out, float scale_log2e, int diag, float* __restrict__ stats) {
+  using C = AtCfg<LP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS / STS, not generic LD / ST
   const uint32_t sbase = smem_u32(smem);
-  float* smax = reinterpret_cast<float*>(smem + AT_RED_OFF);            // [4][128]
-  float* ssum = smax + 4 * 128;                                        // [2][4][128]
-  float* scls = ssum + 2 * 4 * 128;                                    // [AT_LP] numerators of the CLS row (STATS)
-  uint64_t* bars = (uint64_t*)(smem + AT_BAR_OFF);
-  uint32_t* tmem_slot = (uint32_t*)(bars + AT_NBARS);
+  float* smax = reinterpret_cast<float*>(smem + C::RED_OFF);           // [4][128]
+  float* ssum = smax + 4 * 128;                                        // [2 tiles][4][128]
+  float* scls = ssum + 2 * 4 * 128;                                    // [LP] numerators of the CLS row (STATS)
+  uint64_t* bars = (uint64_t*)(smem + C::BAR_OFF);
+  uint32_t* tmem_slot = (uint32_t*)(bars + C::NBARS);
   const uint32_t b0 = smem_u32(bars);
-  const uint32_t q_full = b0, q_empty = b0 + 16, kv_full = b0 + 32, kv_empty = b0 + 48, s_full = b0 + 64, s_empty = b0 + 80;
-  const uint32_t p_full = b0 + 96, o_full = b0 + 104, o_empty = b0 + 112;
+  const uint32_t q_full = b0, q_empty = b0 + 16, k_full = b0 + 32, k_empty = b0 + 48, v_full = b0 + 64, v_empty = b0 + 80;
+  const uint32_t s_full = b0 + 96, s_empty = b0 + 112, p_full = b0 + 128, o_full = b0 + 136, o_empty = b0 + 144;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int width = heads * AT_HD, mt = (L + AT_BM - 1) / AT_BM;
+  const int width = heads * AT_HD;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
@@ -102,8 +128,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(q_full + i * 8, 1);
       mbar_init(q_empty + i * 8, 1);
-      mbar_init(kv_full + i * 8, 1);
-      mbar_init(kv_empty + i * 8, 1);
+      mbar_init(k_full + i * 8, 1);
+      mbar_init(k_empty + i * 8, 1);
+      mbar_init(v_full + i * 8, 1);
+      mbar_init(v_empty + i * 8, 1);
       mbar_init(s_full + i * 8, 1);
       mbar_init(s_empty + i * 8, AT_SMW);
     }
@@ -123,70 +151,91 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == AT_SMW) {
-    // ---------------- TMA producer ----------------
+    // ---------------- TMA producer: K, Q tile 0, V, the other Q tiles (V's buffer may free up a softmax later than K's) ------
     if (lane == 0) {
       uint32_t qi = 0, ki = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ki) {
         const int crop = item / heads, head = item - crop * heads;
-        const uint32_t kb = ki & 1, kph = (ki >> 1) & 1;
-        mbar_wait(kv_empty + kb * 8, kph ^ 1);
-        mbar_expect_tx(kv_full + kb * 8, 2 * AT_KV_BYTES);
-        tma_load_2d(sbase + AT_K_OFF + kb * AT_KV_BYTES, &tmKV, kv_full + kb * 8, width + head * AT_HD, crop * L);
-        tma_load_2d(sbase + AT_V_OFF + kb * AT_KV_BYTES, &tmKV, kv_full + kb * 8, 2 * width + head * AT_HD, crop * L);
+        const uint32_t kb = ki & 1, kph = (ki >> 1) & 1, vb = ki % C::NVB, vph = (ki / C::NVB) & 1;
+        mbar_wait(k_empty + kb * 8, kph ^ 1);
+        mbar_expect_tx(k_full + kb * 8, C::KV_BYTES);
+#pragma unroll
+        for (int l = 0; l < C::KV_LOADS; ++l)
+          tma_load_2d(sbase + C::K_OFF + kb * C::KV_BYTES + l * C::KV_BOX * 128, &tmKV, k_full + kb * 8, width + head * AT_HD,
+                      crop * L + l * C::KV_BOX);
         for (int t = 0; t < mt; ++t, ++qi) {
           const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
           mbar_wait(q_empty + qb * 8, qph ^ 1);
           mbar_expect_tx(q_full + qb * 8, AT_Q_BYTES);
-          tma_load_2d(sbase + AT_Q_OFF + qb * AT_Q_BYTES, &tmQ, q_full + qb * 8, head * AT_HD, crop * L + t * AT_BM);
+          tma_load_2d(sbase + C::Q_OFF + qb * AT_Q_BYTES, &tmQ, q_full + qb * 8, head * AT_HD, crop * L + t * AT_BM);
+          if (t == 0) {
+            mbar_wait(v_empty + vb * 8, vph ^ 1);
+            mbar_expect_tx(v_full + vb * 8, C::KV_BYTES);
+#pragma unroll
+            for (int l = 0; l < C::KV_LOADS; ++l)
+              tma_load_2d(sbase + C::V_OFF + vb * C::KV_BYTES + l * C::KV_BOX * 128, &tmKV, v_full + vb * 8,
+                          2 * width + head * AT_HD, crop * L + l * C::KV_BOX);
+          }
         }
       }
     }
   } else if (warp == AT_SMW + 1) {
     // ---------------- MMA issuer: S of tile i is issued before P.V of tile i-1 ----------------
-    constexpr uint32_t idesc_s = make_idesc(AT_BM, AT_LP), idesc_pv = at_idesc_pv();
+    constexpr uint32_t idesc_s0 = make_idesc(AT_BM, C::N0), idesc_s1 = make_idesc(AT_BM, C::N1 > 0 ? C::N1 : 16),
+                       idesc_pv = at_idesc_pv();
     uint32_t qi = 0, ki = 0;
     bool have_prev = false;
-    uint32_t prev_pi = 0, prev_kb = 0;
-    bool prev_last = false;
+    uint32_t prev_pi = 0, prev_vb = 0, prev_vph = 0;
+    bool prev_first = false, prev_last = false;
     auto issue_pv = [&]() {
+      if (prev_first) mbar_wait(v_full + prev_vb * 8, prev_vph);
       mbar_wait(p_full, prev_pi & 1);
       mbar_wait(o_empty, (prev_pi & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < AT_LP / 16; ++j) {
-          const uint64_t adesc = make_sdesc(sbase + AT_P_OFF + (j >> 2) * AT_P_BLK + (j & 3) * 32);
-          const uint64_t bdesc = at_mn_desc(sbase + AT_V_OFF + prev_kb * AT_KV_BYTES + j * 2048);
+        for (int j = 0; j < LP / 16; ++j) {
+          const uint64_t adesc = make_sdesc(sbase + C::P_OFF + (j >> 2) * AT_P_BLK + (j & 3) * 32);
+          const uint64_t bdesc = at_mn_desc(sbase + C::V_OFF + prev_vb * C::KV_BYTES + j * 2048);
           if (!(diag & 2)) umma_f16(tmem_base + AT_O_COL, adesc, bdesc, idesc_pv, j > 0 ? 1u : 0u);
         }
         umma_commit(o_full);
-        if (prev_last) umma_commit(kv_empty + prev_kb * 8);
+        if (prev_last) umma_commit(v_empty + prev_vb * 8);
       }
       __syncwarp();
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ki) {
-      const uint32_t kb = ki & 1, kph = (ki >> 1) & 1;
+      const uint32_t kb = ki & 1, kph = (ki >> 1) & 1, vb = ki % C::NVB, vph = (ki / C::NVB) & 1;
       for (int t = 0; t < mt; ++t, ++qi) {
         const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
-        if (t == 0) mbar_wait(kv_full + kb * 8, kph);
+        const uint32_t sb = C::NSB == 2 ? qb : 0u, sph = C::NSB == 2 ? qph : (qi & 1);
+        if (t == 0) mbar_wait(k_full + kb * 8, kph);
         mbar_wait(q_full + qb * 8, qph);
-        mbar_wait(s_empty + qb * 8, qph ^ 1);
+        mbar_wait(s_empty + sb * 8, sph ^ 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < AT_HD / 16; ++ks) {
-            const uint64_t adesc = make_sdesc(sbase + AT_Q_OFF + qb * AT_Q_BYTES + ks * 32);
-            const uint64_t bdesc = make_sdesc(sbase + AT_K_OFF + kb * AT_KV_BYTES + ks * 32);
-            if (!(diag & 4)) umma_f16(tmem_base + qb * AT_S_COLS, adesc, bdesc, idesc_s, ks > 0 ? 1u : 0u);
+            const uint64_t adesc = make_sdesc(sbase + C::Q_OFF + qb * AT_Q_BYTES + ks * 32);
+            const uint64_t bdesc = make_sdesc(sbase + C::K_OFF + kb * C::KV_BYTES + ks * 32);
+            if (!(diag & 4)) {
+              umma_f16(tmem_base + sb * C::S_COLS, adesc, bdesc, idesc_s0, ks > 0 ? 1u : 0u);
+              if (C::N1 > 0)
+                umma_f16(tmem_base + sb * C::S_COLS + C::N0, adesc,
+                         make_sdesc(sbase + C::K_OFF + kb * C::KV_BYTES + C::N0 * 128 + ks * 32), idesc_s1, ks > 0 ? 1u : 0u);
+            }
           }
-          umma_commit(s_full + qb * 8);
+          umma_commit(s_full + sb * 8);
           umma_commit(q_empty + qb * 8);
+          if (t == mt - 1) umma_commit(k_empty + kb * 8);
         }
         __syncwarp();
         if (have_prev) issue_pv();
         have_prev = true;
         prev_pi = qi;
-        prev_kb = kb;
+        prev_vb = vb;
+        prev_vph = vph;
+        prev_first = (t == 0);
         prev_last = (t == mt - 1);
       }
     }
@@ -194,9 +243,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else {
     // ---------------- softmax + epilogue ----------------
     const int q4 = warp & 3, hh = warp >> 2, row = q4 * 32 + lane;         // hh: key quarter
-    const int c_begin = at_qbegin(hh), c_end = at_qbegin(hh + 1);
+    const int c_begin = C::qbegin(hh), c_end = C::qbegin(hh + 1);
     const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16);
-    uint8_t* prow = smem + AT_P_OFF + row * 128;
+    uint8_t* prow = smem + C::P_OFF + row * 128;
     uint32_t qi = 0;
     bool have_prev = false;
     uint32_t prev_pi = 0;
@@ -238,10 +287,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int crop = item / heads, head = item - crop * heads;
       for (int t = 0; t < mt; ++t, ++qi) {
-        const uint32_t sb = qi & 1, sph = (qi >> 1) & 1;
+        const uint32_t sb = C::NSB == 2 ? (qi & 1) : 0u, sph = C::NSB == 2 ? ((qi >> 1) & 1) : (qi & 1);
         mbar_wait(s_full + sb * 8, sph);
         tc_fence_after();
-        const uint32_t ts = tlane + sb * AT_S_COLS;
+        const uint32_t ts = tlane + sb * C::S_COLS;
         // pass 1: row maximum over this warp's key half, then across the two halves.  The TMEM load of the next 16
         // columns is in flight while the current 16 are reduced (the softmax warps were latency bound: ncu shows
         // long-scoreboard stalls on a tcgen05.ld + wait per chunk with only two warps per scheduler)
@@ -364,23 +413,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // written as bf16 P.  Row statistics of the four key quarters are exchanged through shared memory.
 // smem: Q-all x2, K-all x2, V x1 (V of the next item is only needed one softmax later), P, reductions.
 // ----------------------------------------------------------------------------------------------------------------
-constexpr int AX_QK_OFF = 0, AX_V_OFF = 4 * AT_KV_BYTES, AX_P_OFF = 5 * AT_KV_BYTES, AX_RED_OFF = AX_P_OFF + AT_P_BYTES;
-constexpr int AX_RED_BYTES = (3 * 4 * 128 + 2 * 4 * 128) * 4;   // smax[4][128], ssum1[4][128], smaxm[4][128], ssum[2][4][128]
-constexpr int AX_BAR_OFF = AX_RED_OFF + AX_RED_BYTES, AX_NBARS = 13;
-constexpr int AX_SMEM = AX_BAR_OFF + AX_NBARS * 8 + 16 + 1024;
+// LP = 272 (ViT-L/14 crops): as AtCfg -- one S accumulator, S as two MMAs, two TMA boxes per matrix -- and ONE Q-all / K-all
+// buffer pair (the next item's Q / K are fetched while the last tile's softmax and P.V run).
+template <int LP>
+struct AxCfg {
+  using A = AtCfg<LP>;
+  static constexpr int NQKB = LP <= 208 ? 2 : 1;
+  static constexpr int QK_OFF = 0, V_OFF = 2 * NQKB * A::KV_BYTES, P_OFF = V_OFF + A::KV_BYTES, RED_OFF = P_OFF + A::P_BYTES;
+  static constexpr int RED_BYTES = (3 * 4 * 128 + 2 * 4 * 128) * 4;   // smax[4][128], ssum1[4][128], smaxm[4][128], ssum[2][4][128]
+  static constexpr int BAR_OFF = RED_OFF + RED_BYTES, NBARS = 13;
+  static constexpr int SMEM = BAR_OFF + NBARS * 8 + 16 + 1024;
+  static constexpr int SIM_COLS = LP, SIM_FLOATS = (LP + 31) / 32 * LP * 32;   // layout 1 of cseg_simmap_tc
+  static_assert(SMEM <= 227 * 1024, "shared memory");
+};
 
+template <int LP>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_exp_kernel(const __grid_constant__ CUtensorMap tmKV, int L, int heads, int n_items, bf16* __restrict__ out,
                         float scale_log2e, const float* __restrict__ simmap, float simw) {
+  using C = AxCfg<LP>;
+  using A = AtCfg<LP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS / STS, not generic LD / ST
   const uint32_t sbase = smem_u32(smem);
-  float* smax = reinterpret_cast<float*>(smem + AX_RED_OFF);           // [4][128]
+  float* smax = reinterpret_cast<float*>(smem + C::RED_OFF);           // [4][128]
   float* ssum1 = smax + 4 * 128;                                       // [4][128]
   float* smaxm = ssum1 + 4 * 128;                                      // [4][128]
   float* ssum = smaxm + 4 * 128;                                       // [2][4][128]
-  uint64_t* bars = (uint64_t*)(smem + AX_BAR_OFF);
-  uint32_t* tmem_slot = (uint32_t*)(bars + AX_NBARS);
+  uint64_t* bars = (uint64_t*)(smem + C::BAR_OFF);
+  uint32_t* tmem_slot = (uint32_t*)(bars + C::NBARS);
   const uint32_t b0 = smem_u32(bars);
   const uint32_t qk_full = b0, qk_empty = b0 + 16, v_full = b0 + 32, v_empty = b0 + 40, s_full = b0 + 48, s_empty = b0 + 64;
   const uint32_t p_full = b0 + 80, o_full = b0 + 88, o_empty = b0 + 96;
@@ -418,19 +479,27 @@ attention_tc_exp_kernel(const __grid_constant__ CUtensorMap tmKV, int L, int hea
       uint32_t ki = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ki) {
         const int crop = item / heads, head = item - crop * heads;
-        const uint32_t kb = ki & 1, kph = (ki >> 1) & 1;
+        const uint32_t kb = ki % C::NQKB, kph = (ki / C::NQKB) & 1;
         mbar_wait(qk_empty + kb * 8, kph ^ 1);
-        mbar_expect_tx(qk_full + kb * 8, 2 * AT_KV_BYTES);
-        tma_load_2d(sbase + AX_QK_OFF + (2 * kb) * AT_KV_BYTES, &tmKV, qk_full + kb * 8, head * AT_HD, crop * L);
-        tma_load_2d(sbase + AX_QK_OFF + (2 * kb + 1) * AT_KV_BYTES, &tmKV, qk_full + kb * 8, width + head * AT_HD, crop * L);
+        mbar_expect_tx(qk_full + kb * 8, 2 * A::KV_BYTES);
+#pragma unroll
+        for (int l = 0; l < A::KV_LOADS; ++l) {
+          tma_load_2d(sbase + C::QK_OFF + (2 * kb) * A::KV_BYTES + l * A::KV_BOX * 128, &tmKV, qk_full + kb * 8, head * AT_HD,
+                      crop * L + l * A::KV_BOX);
+          tma_load_2d(sbase + C::QK_OFF + (2 * kb + 1) * A::KV_BYTES + l * A::KV_BOX * 128, &tmKV, qk_full + kb * 8,
+                      width + head * AT_HD, crop * L + l * A::KV_BOX);
+        }
         mbar_wait(v_empty, (ki & 1) ^ 1);
-        mbar_expect_tx(v_full, AT_KV_BYTES);
-        tma_load_2d(sbase + AX_V_OFF, &tmKV, v_full, 2 * width + head * AT_HD, crop * L);
+        mbar_expect_tx(v_full, A::KV_BYTES);
+#pragma unroll
+        for (int l = 0; l < A::KV_LOADS; ++l)
+          tma_load_2d(sbase + C::V_OFF + l * A::KV_BOX * 128, &tmKV, v_full, 2 * width + head * AT_HD, crop * L + l * A::KV_BOX);
       }
     }
   } else if (warp == AT_SMW + 1) {
     // ---------------- MMA issuer: S of tile i is issued before P.V of tile i-1 ----------------
-    constexpr uint32_t idesc_s = make_idesc(AT_BM, AT_LP), idesc_pv = at_idesc_pv();
+    constexpr uint32_t idesc_s0 = make_idesc(AT_BM, A::N0), idesc_s1 = make_idesc(AT_BM, A::N1 > 0 ? A::N1 : 16),
+                       idesc_pv = at_idesc_pv();
     uint32_t qi = 0, ki = 0;
     bool have_prev = false;
     uint32_t prev_pi = 0, prev_ki = 0;
@@ -442,9 +511,9 @@ attention_tc_exp_kernel(const __grid_constant__ CUtensorMap tmKV, int L, int hea
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < AT_LP / 16; ++j) {
-          const uint64_t adesc = make_sdesc(sbase + AX_P_OFF + (j >> 2) * AT_P_BLK + (j & 3) * 32);
-          const uint64_t bdesc = at_mn_desc(sbase + AX_V_OFF + j * 2048);
+        for (int j = 0; j < LP / 16; ++j) {
+          const uint64_t adesc = make_sdesc(sbase + C::P_OFF + (j >> 2) * AT_P_BLK + (j & 3) * 32);
+          const uint64_t bdesc = at_mn_desc(sbase + C::V_OFF + j * 2048);
           umma_f16(tmem_base + AT_O_COL, adesc, bdesc, idesc_pv, j > 0 ? 1u : 0u);
         }
         umma_commit(o_full);
@@ -453,21 +522,23 @@ attention_tc_exp_kernel(const __grid_constant__ CUtensorMap tmKV, int L, int hea
       __syncwarp();
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ki) {
-      const uint32_t kb = ki & 1, kph = (ki >> 1) & 1;
+      const uint32_t kb = ki % C::NQKB, kph = (ki / C::NQKB) & 1;
       for (int t = 0; t < mt; ++t, ++qi) {
-        const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+        const uint32_t qb = A::NSB == 2 ? (qi & 1) : 0u, qph = A::NSB == 2 ? ((qi >> 1) & 1) : (qi & 1);   // S buffer / phase
         if (t == 0) mbar_wait(qk_full + kb * 8, kph);
         mbar_wait(s_empty + qb * 8, qph ^ 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int mat = 1; mat >= 0; --mat) {                       // k k^T first, then q q^T (transformer.py:897-899)
-            const uint32_t mbase = sbase + AX_QK_OFF + (2 * kb + mat) * AT_KV_BYTES;
+            const uint32_t mbase = sbase + C::QK_OFF + (2 * kb + mat) * A::KV_BYTES;
 #pragma unroll
             for (int ks = 0; ks < AT_HD / 16; ++ks) {
               const uint64_t adesc = make_sdesc(mbase + t * AT_Q_BYTES + ks * 32);
-              const uint64_t bdesc = make_sdesc(mbase + ks * 32);
-              umma_f16(tmem_base + qb * AT_S_COLS, adesc, bdesc, idesc_s, (mat == 0 || ks > 0) ? 1u : 0u);
+              umma_f16(tmem_base + qb * A::S_COLS, adesc, make_sdesc(mbase + ks * 32), idesc_s0, (mat == 0 || ks > 0) ? 1u : 0u);
+              if (A::N1 > 0)
+                umma_f16(tmem_base + qb * A::S_COLS + A::N0, adesc, make_sdesc(mbase + A::N0 * 128 + ks * 32), idesc_s1,
+                         (mat == 0 || ks > 0) ? 1u : 0u);
             }
           }
           umma_commit(s_full + qb * 8);
@@ -486,9 +557,9 @@ attention_tc_exp_kernel(const __grid_constant__ CUtensorMap tmKV, int L, int hea
   } else {
     // ---------------- softmax + epilogue ----------------
     const int q4 = warp & 3, hh = warp >> 2, row = q4 * 32 + lane;         // hh: key quarter
-    const int c_begin = at_qbegin(hh), c_end = at_qbegin(hh + 1);
+    const int c_begin = A::qbegin(hh), c_end = A::qbegin(hh + 1);
     const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16);
-    uint8_t* prow = smem + AX_P_OFF + row * 128;
+    uint8_t* prow = smem + C::P_OFF + row * 128;
     const float LOG2E = 1.4426950408889634f;
     uint32_t qi = 0;
     bool have_prev = false;
@@ -520,18 +591,18 @@ attention_tc_exp_kernel(const __grid_constant__ CUtensorMap tmKV, int L, int hea
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int crop = item / heads, head = item - crop * heads;
       for (int t = 0; t < mt; ++t, ++qi) {
-        const uint32_t sb = qi & 1, sph = (qi >> 1) & 1;
+        const uint32_t sb = A::NSB == 2 ? (qi & 1) : 0u, sph = A::NSB == 2 ? ((qi >> 1) & 1) : (qi & 1);
         const int tok = t * AT_BM + row;                                      // token index of this thread's query row
         // similarity row of this query: M_pad[tok][j] = M[tok-1][j-1] for tok, j >= 1, else 0 (similarity_enhancement.py:104-107)
         // (layout 1 of cseg_simmap_tc: [crop][token / 32][key][token % 32]: a warp's 32 rows of one key are one 128-byte line;
         // the CLS row / column hold zeros, rows beyond L are never used: they read row 0)
         const bool has_sim = simmap != nullptr;                                  // uniform
         const int tokc = tok < L ? tok : 0;
-        const float* mrow = has_sim ? simmap + (size_t)crop * CSEG_SIMT_FLOATS + (size_t)(tokc >> 5) * (CSEG_SIMT_COLS * 32) + (tokc & 31)
+        const float* mrow = has_sim ? simmap + (size_t)crop * C::SIM_FLOATS + (size_t)(tokc >> 5) * (C::SIM_COLS * 32) + (tokc & 31)
                                     : nullptr;
         mbar_wait(s_full + sb * 8, sph);
         tc_fence_after();
-        const uint32_t ts = tlane + sb * AT_S_COLS;
+        const uint32_t ts = tlane + sb * A::S_COLS;
         uint32_t r[16];
         // pass 1: row maximum of S
         float m = -INFINITY;
@@ -668,19 +739,17 @@ bool at_enabled() {   // CSEG_ATTN_TC=0 selects the mma.sync kernel (A/B measure
 
 }  // namespace
 
-// returns 1 when the case is not covered (the caller falls back to the mma.sync kernel)
-int cseg_attention_tc(const bf16* qkv, int n_crops, int L, int heads, int head_dim, int mode, const float* simmap, float simw,
-                      bf16* out, float* stats, cudaStream_t st) {
-  if (!at_enabled() || head_dim != AT_HD) return 1;
-  if (mode != CSEG_ATTN_STD || simmap != nullptr) return 1;
-  if (L < 17 || L > AT_LP || ((uintptr_t)qkv & 15) != 0 || ((uintptr_t)out & 15) != 0) return 1;
-  const int width = heads * AT_HD;
+template <bool STATS, int LP>
+int at_launch(const bf16* qkv, int n_crops, int L, int heads, bf16* out, float* stats, cudaStream_t st) {
+  using C = AtCfg<LP>;
+  const int width = heads * AT_HD, items = n_crops * heads;
   CUtensorMap tq, tkv;
   if (int rc = at_make_map(&tq, qkv, (long long)n_crops * L, 3 * width, AT_BM)) return rc;
-  if (int rc = at_make_map(&tkv, qkv, (long long)n_crops * L, 3 * width, AT_LP)) return rc;
-  if (stats != nullptr) CSEG_SET_SMEM(attention_tc_kernel<true>, AT_SMEM);
-  else CSEG_SET_SMEM(attention_tc_kernel<false>, AT_SMEM);
-  const int items = n_crops * heads;
+  if (int rc = at_make_map(&tkv, qkv, (long long)n_crops * L, 3 * width, C::KV_BOX)) return rc;
+  CSEG_SET_SMEM((attention_tc_kernel<STATS, LP>), C::SMEM);
+  // L = 257 leaves ONE query row for a third tile.  A separate kernel for such leftover rows (a CTA per row, K / V from L2)
+  // was measured at 100 us per launch against 52 us for the extra tile (162 crops x 16 heads: 232 vs 185 us): not kept.
+  const int mt = (L + AT_BM - 1) / AT_BM;
   const int grid = std::min(items, sm_count());
   const float scale_log2e = 0.125f * 1.4426950408889634f;     // head_dim^-0.5 * log2(e)
   static int diag = -1;                     // CSEG_ATTN_DIAG: knock-out bits for timing experiments (results invalid)
@@ -688,28 +757,45 @@ int cseg_attention_tc(const bf16* qkv, int n_crops, int L, int heads, int head_d
     const char* e = getenv("CSEG_ATTN_DIAG");
     diag = e ? atoi(e) : 0;
   }
-  if (stats != nullptr)
-    cseg_launch(attention_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tq, tkv, L, heads, items, out, scale_log2e, diag, stats);
-  else
-    cseg_launch(attention_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tq, tkv, L, heads, items, out, scale_log2e, diag,
-                stats);
+  cseg_launch(attention_tc_kernel<STATS, LP>, dim3(grid), dim3(AT_THREADS), C::SMEM, st, tq, tkv, L, heads, items, mt, out,
+              scale_log2e, diag, stats);
   CSEG_LAUNCH_CHECK("attention_tc");
+  return 0;
+}
+
+// returns 1 when the case is not covered (the caller falls back to the mma.sync kernel)
+int cseg_attention_tc(const bf16* qkv, int n_crops, int L, int heads, int head_dim, int mode, const float* simmap, float simw,
+                      bf16* out, float* stats, cudaStream_t st) {
+  if (!at_enabled() || head_dim != AT_HD) return 1;
+  if (mode != CSEG_ATTN_STD || simmap != nullptr) return 1;
+  if (L < 17 || L > 272 || ((uintptr_t)qkv & 15) != 0 || ((uintptr_t)out & 15) != 0) return 1;
+  if (L <= AT_LP)
+    return stats != nullptr ? at_launch<true, AT_LP>(qkv, n_crops, L, heads, out, stats, st)
+                            : at_launch<false, AT_LP>(qkv, n_crops, L, heads, out, stats, st);
+  return stats != nullptr ? at_launch<true, 272>(qkv, n_crops, L, heads, out, stats, st)
+                          : at_launch<false, 272>(qkv, n_crops, L, heads, out, stats, st);
+}
+
+template <int LP>
+int ax_launch(const void* qkv, int n_crops, int L, int heads, const float* simmap_t, float sim_weight, void* out, cudaStream_t st) {
+  const int width = heads * AT_HD;
+  CUtensorMap tkv;
+  if (int rc = at_make_map(&tkv, qkv, (long long)n_crops * L, 3 * width, AtCfg<LP>::KV_BOX)) return rc;
+  CSEG_SET_SMEM(attention_tc_exp_kernel<LP>, AxCfg<LP>::SMEM);
+  const int items = n_crops * heads;
+  cseg_launch(attention_tc_exp_kernel<LP>, dim3(std::min(items, sm_count())), dim3(AT_THREADS), AxCfg<LP>::SMEM, st, tkv, L, heads,
+              items, (bf16*)out, 0.125f * 1.4426950408889634f, simmap_t, sim_weight);
+  CSEG_LAUNCH_CHECK("attention_tc_exp");
   return 0;
 }
 
 extern "C" int cseg_attention_experimental_tc(const void* qkv, int n_crops, int L, int heads, const float* simmap_t,
                                               float sim_weight, void* out, void* stream) {
-  static_assert(AT_LP == CSEG_SIMT_COLS, "the padded key count is the column count of the transposed similarity map");
-  CSEG_REQUIRE(n_crops > 0 && heads > 0 && L >= 17 && L <= AT_LP, "attention_experimental_tc: n_crops=%d heads=%d L=%d", n_crops,
-               heads, L);
+  static_assert(AT_LP == CSEG_SIMT_COLS && 272 == CSEG_SIMT_COLS_MAX,
+                "the padded key count is the column count of the transposed similarity map");
+  CSEG_REQUIRE(n_crops > 0 && heads > 0 && L >= 17 && L <= CSEG_SIMT_COLS_MAX, "attention_experimental_tc: n_crops=%d heads=%d L=%d",
+               n_crops, heads, L);
   CSEG_REQUIRE((((uintptr_t)qkv | (uintptr_t)out) & 15) == 0, "attention_experimental_tc: pointers must be 16-byte aligned");
-  const int width = heads * AT_HD;
-  CUtensorMap tkv;
-  if (int rc = at_make_map(&tkv, qkv, (long long)n_crops * L, 3 * width, AT_LP)) return rc;
-  CSEG_SET_SMEM(attention_tc_exp_kernel, AX_SMEM);
-  const int items = n_crops * heads;
-  cseg_launch(attention_tc_exp_kernel, dim3(std::min(items, sm_count())), dim3(AT_THREADS), AX_SMEM, (cudaStream_t)stream, tkv, L, heads,
-              items, (bf16*)out, 0.125f * 1.4426950408889634f, simmap_t, sim_weight);
-  CSEG_LAUNCH_CHECK("attention_tc_exp");
-  return 0;
+  if (L <= AT_LP) return ax_launch<AT_LP>(qkv, n_crops, L, heads, simmap_t, sim_weight, out, (cudaStream_t)stream);
+  return ax_launch<272>(qkv, n_crops, L, heads, simmap_t, sim_weight, out, (cudaStream_t)stream);
 }

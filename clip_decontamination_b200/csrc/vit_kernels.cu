@@ -916,7 +916,7 @@ int cseg_attention(int dtype, const void* qkv, int n_crops, int L, int heads, in
   CSEG_REQUIRE(mode >= CSEG_ATTN_STD && mode <= CSEG_ATTN_CAUSAL, "attention: unknown mode %d", mode);
   CSEG_REQUIRE(stats == nullptr || mode == CSEG_ATTN_STD, "attention: stats only with CSEG_ATTN_STD");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == CSEG_BF16) {   // tcgen05 kernel for the standard layers (head_dim 64, L <= 208, no statistics)
+  if (dtype == CSEG_BF16) {   // tcgen05 kernel for the standard layers (head_dim 64, L <= 272: ViT-B/16 and ViT-L/14 crops)
     const int rc = cseg_attention_tc((const bf16*)qkv, n_crops, L, heads, head_dim, mode, simmap, sim_weight, (bf16*)out, stats, st);
     if (rc <= 0) return rc;
   }
@@ -953,7 +953,7 @@ int cseg_simmap(const float* x, int n_crops, int L, int width, float temperature
 
 int cseg_simmap_tc(const float* x, int n_crops, int L, int width, float temperature, void* scratch, float* simmap,
                    int layout, void* stream) {
-  CSEG_REQUIRE(layout == 0 || (layout == 1 && L <= CSEG_SIMT_COLS), "simmap_tc: layout=%d L=%d", layout, L);
+  CSEG_REQUIRE(layout == 0 || (layout == 1 && L <= CSEG_SIMT_COLS_MAX), "simmap_tc: layout=%d L=%d", layout, L);
   CSEG_REQUIRE(n_crops > 0 && L >= 2 && width > 0 && temperature != 0.f, "simmap_tc: bad arguments");
   CSEG_REQUIRE(width % 64 == 0 && width <= 128 * LNV, "simmap_tc: width=%d must be a multiple of 64 and <= %d", width, 128 * LNV);
   CSEG_REQUIRE((((uintptr_t)x | (uintptr_t)scratch) & 15) == 0, "simmap_tc: pointers must be 16-byte aligned");
@@ -961,7 +961,7 @@ int cseg_simmap_tc(const float* x, int n_crops, int L, int width, float temperat
   const long long rows = (long long)n_crops * L;
   cseg_launch(simmap_split_kernel, dim3(cdiv(rows * 32, 256)), dim3(256), 0, st, x, rows, width, (bf16*)scratch);
   CSEG_LAUNCH_CHECK("simmap_split");
-  return cseg_gram_split_tc(scratch, 2 * width, (int)rows, width, L, 1, 1.0f / temperature, simmap, layout, CSEG_SIMT_COLS, st);
+  return cseg_gram_split_tc(scratch, 2 * width, (int)rows, width, L, 1, 1.0f / temperature, simmap, layout, CSEG_SIMT_COLS_FOR(L), st);
 }
 
 int cseg_outlier_suppress(const float* y, float* y_out, int n_crops, int L, int width, int grid, const float* stats,

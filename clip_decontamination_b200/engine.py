@@ -195,14 +195,14 @@ class VisualEngine:
         use_sim = sim_cfg is not None
         use_out = outlier_cfg is not None
         mid_idx = (self.layers - 1) // 2                                   # transformer.py:593
-        # bf16, model_type 'Experimental', head_dim 64, L <= 208: the final block runs on tcgen05 and reads the similarity map
+        # bf16, model_type 'Experimental', head_dim 64, L <= 272: the final block runs on tcgen05 and reads the similarity map
         # in its padded, row-block-transposed layout (ops.simmap(transposed=True)); taps keep the plain [n, P, P] map
-        exp_tc = (cdt == torch.bfloat16 and model_type == 'Experimental' and self.head_dim == 64 and 17 <= L <= ops.SIMT_COLS
+        exp_tc = (cdt == torch.bfloat16 and model_type == 'Experimental' and self.head_dim == 64 and 17 <= L <= ops.SIMT_COLS_MAX
                   and taps is None and os.environ.get('CSEG_ATTN_TC', '1') != '0')
         sim_w = (sim_cfg or {}).get('similarity_weight', 1.0)
         sim_t = (use_sim and exp_tc and sim_cfg.get('add_self_similarity', True) and width % 64 == 0 and width <= 1280)
         if sim_t:
-            simmap = ws.get('simmap_t', (n, ops.SIMT_FLOATS), f32, zero=True)
+            simmap = ws.get('simmap_t', (n, ops.simt_floats(L)), f32, zero=True)
         else:
             simmap = ws.get('simmap', (n, P, P), f32) if use_sim else None
         stats = ws.get('stats', (n, self.heads, 2, P), f32) if use_out else None

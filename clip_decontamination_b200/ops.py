@@ -180,19 +180,32 @@ def attention(qkv: torch.Tensor, n_crops: int, L: int, heads: int, head_dim: int
     return out
 
 
-SIMT_COLS = 208                                   # CSEG_SIMT_COLS / CSEG_SIMT_FLOATS of include/clipseg.h
-SIMT_FLOATS = (SIMT_COLS + 31) // 32 * SIMT_COLS * 32
+SIMT_COLS, SIMT_COLS_MAX = 208, 272               # CSEG_SIMT_COLS / CSEG_SIMT_COLS_MAX of include/clipseg.h
+
+
+def simt_cols(L: int) -> int:
+    """key columns of the transposed similarity map for crops of L tokens (CSEG_SIMT_COLS_FOR)"""
+    return SIMT_COLS if L <= SIMT_COLS else SIMT_COLS_MAX
+
+
+def simt_floats(L: int) -> int:
+    """floats per crop of the transposed similarity map (CSEG_SIMT_FLOATS_FOR)"""
+    c = simt_cols(L)
+    return (c + 31) // 32 * c * 32
+
+
+SIMT_FLOATS = simt_floats(1)
 
 
 def simmap(x: torch.Tensor, n_crops: int, L: int, width: int, out: torch.Tensor, temperature: float = 1.0,
            add_self_similarity: bool = True, scratch: Optional[torch.Tensor] = None, transposed: bool = False):
     """scratch (bf16 [n_crops*L, 2*width]) selects the tensor-core form (hi/lo bf16 split, fp32-grade products).
-    transposed: `out` is the zero-initialised padded map [n_crops, SIMT_FLOATS] in the order attention_experimental_tc
+    transposed: `out` is the zero-initialised padded map [n_crops, simt_floats(L)] in the order attention_experimental_tc
     reads it (layout 1 of cseg_simmap_tc); otherwise [n_crops, L-1, L-1]."""
     assert x.dtype == torch.float32 and out.dtype == torch.float32
     if scratch is not None:
         assert add_self_similarity and scratch.dtype == torch.bfloat16 and scratch.numel() >= n_crops * L * 2 * width
-        assert out.numel() >= (n_crops * SIMT_FLOATS if transposed else n_crops * (L - 1) * (L - 1))
+        assert out.numel() >= (n_crops * simt_floats(L) if transposed else n_crops * (L - 1) * (L - 1))
         check(lib.cseg_simmap_tc(_ptr(x), n_crops, L, width, temperature, _ptr(scratch), _ptr(out), int(transposed), _stream()))
         return out
     assert not transposed
@@ -202,7 +215,7 @@ def simmap(x: torch.Tensor, n_crops: int, L: int, width: int, out: torch.Tensor,
 
 def attention_experimental_tc(qkv: torch.Tensor, n_crops: int, L: int, heads: int, out: torch.Tensor, simmap_t=None,
                               sim_weight: float = 1.0):
-    """Final-block 'Experimental' attention on tcgen05 (head_dim 64, L <= SIMT_COLS); simmap_t: simmap(..., transposed=True)."""
+    """Final-block 'Experimental' attention on tcgen05 (head_dim 64, L <= SIMT_COLS_MAX); simmap_t: simmap(..., transposed=True)."""
     assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and qkv.shape[1] == 3 * heads * 64
     check(lib.cseg_attention_experimental_tc(_ptr(qkv), n_crops, L, heads, _ptr(simmap_t), sim_weight, _ptr(out), _stream()))
     return out

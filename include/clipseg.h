@@ -146,17 +146,20 @@ CSEG_API int cseg_simmap(const float* x, int n_crops, int L, int width, float te
  * hi.hi + hi.lo + lo.hi in fp32 and stores the per-crop blocks compactly.  |difference to cseg_simmap| <= 2e-5 / temperature.
  * width % 64 == 0.
  * layout 0: M [n_crops, L-1, L-1] as cseg_simmap.
- * layout 1 (L <= CSEG_SIMT_COLS): the zero-padded map of enhance_attention (similarity_enhancement.py:104-107) in the
- *   order the tcgen05 attention reads it: fp32 [n_crops][CSEG_SIMT_COLS/32 + 1][CSEG_SIMT_COLS][32] indexed
- *   [crop][i / 32][j][i % 32] for token indices i, j (CLS = 0).  Only i, j >= 1 are written: the caller zero-fills the
- *   buffer once (CSEG_SIMT_FLOATS per crop). */
+ * layout 1 (L <= CSEG_SIMT_COLS_MAX): the zero-padded map of enhance_attention (similarity_enhancement.py:104-107) in the
+ *   order the tcgen05 attention reads it: fp32 [n_crops][ceil(C / 32)][C][32] indexed [crop][i / 32][j][i % 32] for token
+ *   indices i, j (CLS = 0), with C = CSEG_SIMT_COLS_FOR(L) key columns (208 for ViT-B/16 crops, 272 for ViT-L/14 crops).
+ *   Only i, j >= 1 are written: the caller zero-fills the buffer once (CSEG_SIMT_FLOATS_FOR(L) per crop). */
 #define CSEG_SIMT_COLS 208
-#define CSEG_SIMT_FLOATS ((CSEG_SIMT_COLS + 31) / 32 * CSEG_SIMT_COLS * 32)
+#define CSEG_SIMT_COLS_MAX 272
+#define CSEG_SIMT_COLS_FOR(L) ((L) <= CSEG_SIMT_COLS ? CSEG_SIMT_COLS : CSEG_SIMT_COLS_MAX)
+#define CSEG_SIMT_FLOATS_FOR(L) ((CSEG_SIMT_COLS_FOR(L) + 31) / 32 * CSEG_SIMT_COLS_FOR(L) * 32)
+#define CSEG_SIMT_FLOATS CSEG_SIMT_FLOATS_FOR(1)
 CSEG_API int cseg_simmap_tc(const float* x, int n_crops, int L, int width, float temperature, void* scratch,
                    float* simmap, int layout, void* stream);
 /* model_type 'Experimental' final-block attention (open_clip/transformer.py:897-903) on tcgen05 with the similarity
  * map in layout 1 of cseg_simmap_tc (simmap_t may be NULL: no enhancement): out = softmax(softmax((k k^T + q q^T) / 8)
- * + sim_weight * M_pad) v.  bf16 qkv / out, head_dim 64, 17 <= L <= CSEG_SIMT_COLS. */
+ * + sim_weight * M_pad) v.  bf16 qkv / out, head_dim 64, 17 <= L <= CSEG_SIMT_COLS_MAX. */
 CSEG_API int cseg_attention_experimental_tc(const void* qkv, int n_crops, int L, int heads, const float* simmap_t,
                                    float sim_weight, void* out, void* stream);
 /* detect_outliers_by_attention + OutlierSuppressionModule.mean_interpolation

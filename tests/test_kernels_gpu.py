@@ -278,7 +278,10 @@ def test_attention_modes(ops, mode, dtype, L, hd):
         assert (s[:, :, 1] - torch.diagonal(wgt, dim1=2, dim2=3)[:, :, 1:]).abs().max().item() < 1e-6
 
 
-@pytest.mark.parametrize('n,L,heads', [(2, 197, 3), (5, 197, 12), (3, 128, 2), (2, 77, 4), (150, 197, 12), (1, 208, 1)])
+@pytest.mark.parametrize('n,L,heads', [(2, 197, 3), (5, 197, 12), (3, 128, 2), (2, 77, 4), (150, 197, 12), (1, 208, 1),
+                                       # the 272-key shape (ViT-L/14 crops: L = 257 -> two tiles + one tail row)
+                                       (2, 257, 3), (5, 257, 16), (81, 257, 16), (3, 209, 2), (2, 230, 4), (2, 264, 2),
+                                       (1, 272, 1), (3, 258, 5)])
 def test_attention_tcgen05_std(ops, n, L, heads):
     """Standard attention on tcgen05 (attention_tc.cu: S in TMEM, softmax from tcgen05.ld, P.V as a second MMA) against
     the torch formula and against the mma.sync kernel (selected through mode 'vanilla' without a similarity map: the same
@@ -294,7 +297,13 @@ def test_attention_tcgen05_std(ops, n, L, heads):
     stats = torch.zeros((n, heads, 2, L - 1), device='cuda')
     ops.attention(qkv.cuda(), n, L, heads, hd, ATTN['STD'], out3, stats=stats)
     torch.cuda.synchronize()
-    assert torch.isfinite(out.float()).all() and torch.equal(out3, out)
+    assert torch.isfinite(out.float()).all()
+    full = ((L + 127) // 128 - 1) * 128
+    if L > 128 and L - full <= 8:      # a few leftover query rows: fp32 tail kernel without / tile pipeline with statistics
+        assert torch.equal(out3.view(n, L, d)[:, :full], out.view(n, L, d)[:, :full])
+        assert (out3.float() - out.float()).abs().max().item() < 1e-2
+    else:
+        assert torch.equal(out3, out)
     assert (stats > 0).all() and (stats <= 1).all()
     d12 = (out.float() - out2.float()).abs().max().item()
     if n <= 5:
@@ -307,7 +316,7 @@ def test_attention_tcgen05_std(ops, n, L, heads):
 
 def _pack_simt(ops, sim, L):
     """[n, L-1, L-1] -> the zero-padded, row-block-transposed layout of cseg_simmap_tc(layout 1): [n][i / 32][j][i % 32]."""
-    n, cols = sim.shape[0], ops.SIMT_COLS
+    n, cols = sim.shape[0], ops.simt_cols(L)
     nb = (cols + 31) // 32
     pad = torch.zeros(n, nb * 32, cols)
     pad[:, 1:L, 1:L] = sim
@@ -316,7 +325,10 @@ def _pack_simt(ops, sim, L):
 
 @pytest.mark.parametrize('n,L,heads,simw,temp', [(2, 197, 3, 0.7, 1.0), (5, 197, 12, 1.0, 1.0), (3, 128, 2, -2.0, 1.0),
                                                  (2, 77, 4, 1.0, 0.05), (150, 197, 12, 1.0, 1.0), (1, 208, 1, 0.0, 1.0),
-                                                 (3, 197, 2, None, 1.0)])
+                                                 (3, 197, 2, None, 1.0),
+                                                 # the 272-key shape (ViT-L/14 crops)
+                                                 (2, 257, 3, 0.7, 1.0), (5, 257, 16, 1.0, 1.0), (81, 257, 16, 1.0, 1.0),
+                                                 (2, 209, 2, -2.0, 1.0), (2, 272, 1, 1.0, 0.05), (3, 257, 2, None, 1.0)])
 def test_attention_tcgen05_experimental(ops, n, L, heads, simw, temp):
     """Final-block 'Experimental' attention on tcgen05 (k k^T + q q^T in one TMEM accumulator, double softmax with the
     similarity map added to the probabilities) against the torch formula of custom_attn (transformer.py:897-903);
@@ -365,8 +377,8 @@ def test_simmap_tensor_core(ops, n, L, w, temp):
     scratch = torch.empty((n * L, 2 * w), device='cuda', dtype=torch.bfloat16)
     ops.simmap(x.cuda(), n, L, w, out, temperature=temp, scratch=scratch)
     assert (out.cpu() - ref).abs().max().item() < 2e-5 / temp
-    if L <= ops.SIMT_COLS:        # padded, row-block-transposed layout for the tcgen05 final-block attention
-        out_t = torch.zeros((n, ops.SIMT_FLOATS), device='cuda')
+    if L <= ops.SIMT_COLS_MAX:    # padded, row-block-transposed layout for the tcgen05 final-block attention
+        out_t = torch.zeros((n, ops.simt_floats(L)), device='cuda')
         ops.simmap(x.cuda(), n, L, w, out_t, temperature=temp, scratch=scratch, transposed=True)
         assert torch.equal(out_t.cpu(), _pack_simt(ops, out.cpu(), L))
 
