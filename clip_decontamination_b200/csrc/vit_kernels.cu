@@ -490,6 +490,124 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const T* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+// Attention for long token sequences (whole-image inference, segmentor.py:470-471: L = H W / ps^2 + 1 is unbounded;
+// slide_crop 336 with ViT-L/14: L = 577).  Same formulas as attention_kernel, any L: a warp owns one query row at a
+// time and keeps that row's scores in shared memory (L floats per warp) instead of registers; K / V / Q rows of the
+// keys are read from global memory (the warps of a CTA walk the same rows: L1 / L2 hits).  Every mode is a sum of one
+// to three softmax terms, each over a sum of one or two score products; a term's unnormalised probabilities are
+// contracted with V as soon as they exist, so one score row per warp is enough.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int HD>
+__global__ void __launch_bounds__(256) attention_long_kernel(const T* __restrict__ qkv, int L, int heads, int mode,
+                                                             const float* __restrict__ simmap, float simw, T* __restrict__ out,
+                                                             float* __restrict__ stats, int rows_per_cta) {
+  pdl_grid_sync();
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* sc = reinterpret_cast<float*>(att_smem) + (size_t)warp * L;
+  const int nrb = (L + rows_per_cta - 1) / rows_per_cta;
+  const int item = blockIdx.x / nrb, rb = blockIdx.x - item * nrb;
+  const int crop = item / heads, head = item - crop * heads, width = heads * HD, P = L - 1;
+  const float scale = rsqrtf((float)HD);
+  const T* base = qkv + (size_t)crop * L * 3 * width + head * HD;      // + row * 3 width (+ width: K, + 2 width: V)
+  const size_t rs = (size_t)3 * width;
+  constexpr int DPL = (HD + 31) / 32;                                   // output dimensions per lane: d = lane + 32 u
+  const int i_end = min(L, (rb + 1) * rows_per_cta);
+  for (int i = rb * rows_per_cta + warp; i < i_end; i += nwarps) {
+    float o[DPL];
+#pragma unroll
+    for (int u = 0; u < DPL; ++u) o[u] = 0.f;
+    if (mode == CSEG_ATTN_MASKCLIP) {                                   // identity attention: out_i = v_i
+#pragma unroll
+      for (int u = 0; u < DPL; ++u)
+        if (lane + 32 * u < HD) o[u] = to_f32(base[(size_t)i * rs + 2 * width + lane + 32 * u]);
+    } else {
+      const int nterms = mode == CSEG_ATTN_SCLIP ? 2 : (mode == CSEG_ATTN_SEGEARTH ? 3 : 1);
+      const bool use_m = simmap != nullptr && mode != CSEG_ATTN_STD && mode != CSEG_ATTN_CAUSAL && i >= 1;
+      const float* mrow = use_m ? simmap + ((size_t)crop * P + (i - 1)) * P : nullptr;   // M_pad[i][j] = M[i-1][j-1], j >= 1
+      for (int term = 0; term < nterms; ++term) {
+        // ---- scores of this term into sc[] ----
+        const int nsub = (mode == CSEG_ATTN_SFP || mode == CSEG_ATTN_EXPERIMENTAL) ? 2 : 1;
+        float m = -INFINITY;
+        for (int sub = 0; sub < nsub; ++sub) {
+          // x_i . Y_j: STD / vanilla / causal q.K; ClearCLIP q.Q; SFP, Experimental q.Q then k.K; SCLIP / SegEarth terms q.Q, k.K, v.V
+          int xo, yo;
+          if (mode == CSEG_ATTN_STD || mode == CSEG_ATTN_VANILLA || mode == CSEG_ATTN_CAUSAL) { xo = 0; yo = width; }
+          else if (mode == CSEG_ATTN_SCLIP || mode == CSEG_ATTN_SEGEARTH) { xo = yo = term * width; }
+          else { xo = yo = sub * width; }
+          const float w = mode == CSEG_ATTN_SFP ? 0.5f * scale : scale;
+          float xi[HD];
+          load_row<T, HD>(xi, base + (size_t)i * rs + xo);
+          const bool last = sub == nsub - 1;
+          const bool add_m = last && mode != CSEG_ATTN_EXPERIMENTAL;       // Experimental adds M to the probabilities
+          for (int j = lane; j < L; j += 32) {
+            float v = dot_row<T, HD>(xi, base + (size_t)j * rs + yo) * w;
+            if (sub > 0) v += sc[j];
+            if (add_m && use_m && j >= 1) v += simw * mrow[j - 1];
+            if (mode == CSEG_ATTN_CAUSAL && j > i) v = -INFINITY;
+            sc[j] = v;
+            if (last) m = fmaxf(m, v);
+          }
+        }
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int j = lane; j < L; j += 32) {
+          const float e = __expf(sc[j] - m);
+          sc[j] = e;
+          sum += e;
+        }
+        sum = warp_sum(sum);
+        float inv = 1.0f / sum;
+        if (mode == CSEG_ATTN_EXPERIMENTAL) {                               // second softmax over p1 + w M (transformer.py:901-902)
+          float m2 = -INFINITY;
+          for (int j = lane; j < L; j += 32) {
+            float v = sc[j] * inv;
+            if (use_m && j >= 1) v += simw * mrow[j - 1];
+            sc[j] = v;
+            m2 = fmaxf(m2, v);
+          }
+          m2 = warp_max(m2);
+          sum = 0.f;
+          for (int j = lane; j < L; j += 32) {
+            const float e = __expf(sc[j] - m2);
+            sc[j] = e;
+            sum += e;
+          }
+          sum = warp_sum(sum);
+          inv = 1.0f / sum;
+        }
+        if (stats != nullptr) {   // outlier_suppression.py:46-49: only P[0,1+i] and P[1+i,1+i] are consumed (STD only)
+          float* st = stats + ((size_t)(crop * heads + head) * 2) * P;
+          if (i == 0)
+            for (int j = 1 + lane; j < L; j += 32) st[j - 1] = sc[j] * inv;
+          else if (lane == (i & 31)) st[P + i - 1] = sc[i] * inv;
+        }
+        __syncwarp();
+        // ---- o += (1 / sum) * sum_j e_j v_j ----
+        float a[DPL];
+#pragma unroll
+        for (int u = 0; u < DPL; ++u) a[u] = 0.f;
+        const T* vb = base + 2 * width;
+        const int jn = mode == CSEG_ATTN_CAUSAL ? i + 1 : L;
+#pragma unroll 4
+        for (int j = 0; j < jn; ++j) {
+          const float pj = sc[j];
+#pragma unroll
+          for (int u = 0; u < DPL; ++u)
+            if (lane + 32 * u < HD) a[u] = fmaf(pj, to_f32(vb[(size_t)j * rs + lane + 32 * u]), a[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < DPL; ++u) o[u] = fmaf(a[u], inv, o[u]);
+        __syncwarp();
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < DPL; ++u)
+      if (lane + 32 * u < HD) out[((size_t)crop * L + i) * width + head * HD + lane + 32 * u] = from_f32<T>(o[u]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // similarity_enhancement.py:37-66.  inv_norm then a 32x32-tiled fp32 dot-product kernel.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) simmap_kernel(const float* __restrict__ x, int L, int width, float inv_temp,
@@ -894,7 +1012,17 @@ static int launch_attention(const void* qkv, int n_crops, int L, int heads, int 
                             float simw, void* out, float* stats, cudaStream_t st) {
   constexpr int LDS = HD + (sizeof(T) == 2 ? 2 : 1);
   const size_t smem = (((size_t)3 * L * LDS * sizeof(T) + 15) & ~(size_t)15) + (size_t)ATT_WARPS * ATT_JMAX * 32 * 4;
-  CSEG_REQUIRE(smem <= 227 * 1024, "attention: L=%d head_dim=%d needs %zu B shared memory", L, HD, smem);
+  if (L > ATT_JMAX * 32 || smem > 227 * 1024) {          // long sequences: score rows in shared memory, K / V streamed
+    int warps = (int)std::min<size_t>(8, (size_t)(200 * 1024) / ((size_t)L * 4));
+    CSEG_REQUIRE(warps >= 1, "attention: L=%d exceeds the %d tokens one score row in shared memory allows", L, 200 * 1024 / 4);
+    const size_t sm = (size_t)warps * L * 4;
+    const int rows_per_cta = 8 * warps;
+    CSEG_SET_SMEM((attention_long_kernel<T, HD>), sm);
+    cseg_launch(attention_long_kernel<T, HD>, dim3(n_crops * heads * cdiv(L, rows_per_cta)), dim3(warps * 32), sm, st, (const T*)qkv, L,
+                heads, mode, simmap, simw, (T*)out, stats, rows_per_cta);
+    CSEG_LAUNCH_CHECK("attention_long");
+    return 0;
+  }
   CSEG_SET_SMEM((attention_kernel<T, HD>), smem);
   cseg_launch(attention_kernel<T, HD>, dim3(n_crops * heads), dim3(ATT_WARPS * 32), smem, st, (const T*)qkv, L, heads, mode, simmap, simw,
                                                                          (T*)out, stats);
@@ -912,7 +1040,7 @@ extern "C" {
 int cseg_attention(int dtype, const void* qkv, int n_crops, int L, int heads, int head_dim, int mode,
                    const float* simmap, float sim_weight, void* out, float* stats, void* stream) {
   CSEG_REQUIRE(n_crops > 0 && heads > 0, "attention: bad shape");
-  CSEG_REQUIRE(L >= 2 && L <= ATT_JMAX * 32, "attention: L=%d outside [2, %d]", L, ATT_JMAX * 32);
+  CSEG_REQUIRE(L >= 2, "attention: L=%d", L);
   CSEG_REQUIRE(mode >= CSEG_ATTN_STD && mode <= CSEG_ATTN_CAUSAL, "attention: unknown mode %d", mode);
   CSEG_REQUIRE(stats == nullptr || mode == CSEG_ATTN_STD, "attention: stats only with CSEG_ATTN_STD");
   cudaStream_t st = (cudaStream_t)stream;

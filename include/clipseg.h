@@ -134,7 +134,10 @@ CSEG_API int cseg_gemm_reference(int in_dtype, const void* A, int lda, const voi
  * (similarity_enhancement.py:78-124).  out: T [n_crops*L, width] (before out_proj).
  * stats (may be NULL; CSEG_ATTN_STD only): fp32 [n_crops][heads][2][L-1] receiving P[0,1+i] and
  * P[1+i,1+i] per head -- the only entries of the need_weights=True matrix that
- * detect_outliers_by_attention consumes (outlier_suppression.py:46-53). */
+ * detect_outliers_by_attention consumes (outlier_suppression.py:46-53).
+ * Any L >= 2: bf16, head_dim 64, CSEG_ATTN_STD runs on tcgen05 up to L = 272 (197 / 257 = ViT-B/16 / ViT-L/14 crops),
+ * the other modes on mma.sync up to 272, then the CUDA-core kernels (Q / K / V of a head in shared memory up to
+ * L = 320, a score row per warp with streamed K / V beyond: whole-image inference, segmentor.py:470-471). */
 CSEG_API int cseg_attention(int dtype, const void* qkv, int n_crops, int L, int heads, int head_dim, int mode,
                    const float* simmap, float sim_weight, void* out, float* stats, void* stream);
 /* SimilarityEnhancementModule.compute_similarity_map (similarity_enhancement.py:37-66) on the fp32

@@ -378,6 +378,9 @@ GROUPS = {
                                        extras=False),
     'seg_whole_jbu': lambda: seg_full('seg_whole_240_jbu', 'ViT-B-16', 'potsdam', 240, 240, 0.1, 5, 'jbu_one', crop=0),
     'seg_whole_noup': lambda: seg_full('seg_whole_250_noup', 'ViT-B-16', 'potsdam', 250, 250, 0.1, 5, None, crop=0),
+    # whole image beyond 320 tokens: the long-sequence attention path (L = 626 / 577)
+    'seg_whole_long_noup': lambda: seg_full('seg_whole_400_noup', 'ViT-B-16', 'potsdam', 400, 400, 0.1, 5, None, crop=0),
+    'seg_whole_long_jbu': lambda: seg_full('seg_whole_384_jbu', 'ViT-B-16', 'vaihingen', 384, 384, 0.1, 5, 'jbu_one', crop=0),
     'seg_small_side': lambda: seg_full('seg_small_200_jbu', 'ViT-B-16', 'vaihingen', 200, 200, 0.1, 5, 'jbu_one'),
     'seg_nonsquare_off': lambda: seg_full('seg_nonsquare_200x180_off', 'ViT-B-16', 'potsdam', 200, 180, 0.1, 5, None,
                                           extras=False),

@@ -64,6 +64,8 @@ CASES = [
     ('seg_road_448to1024', 'ViT-B-16', 'jbu_one', None),                    # cfg_deepglobe_road.py:15 Resize path
     ('seg_whole_240_jbu', 'ViT-B-16', 'jbu_one', None),                     # slide_crop = 0 (segmentor.py:470-471), interp. pos-embed
     ('seg_whole_250_noup', 'ViT-B-16', None, None),                         # whole image, H % 16 != 0, one bilinear resize
+    ('seg_whole_400_noup', 'ViT-B-16', None, None),                         # whole image, L = 626 > 320: long-sequence attention
+    ('seg_whole_384_jbu', 'ViT-B-16', 'jbu_one', None),                     # whole image with the upsampler, L = 577
     ('seg_small_200_jbu', 'ViT-B-16', 'jbu_one', None),                     # side < 224: padded window, interp. pos-embed
     ('seg_nonsquare_200x180_off', 'ViT-B-16', None, None),                  # non-square padded window (extras off)
 ]

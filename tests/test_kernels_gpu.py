@@ -251,7 +251,7 @@ def _attn_ref(qkv, n, L, heads, mode, sim, w):
 
 @pytest.mark.parametrize('mode', ['STD', 'Experimental', 'SCLIP', 'ClearCLIP', 'SFP', 'vanilla', 'SegEarth', 'MaskCLIP'])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize('L,hd', [(197, 64), (257, 64), (50, 80)])
+@pytest.mark.parametrize('L,hd', [(197, 64), (257, 64), (50, 80), (577, 64), (401, 80)])   # > 320 tokens: attention_long_kernel
 def test_attention_modes(ops, mode, dtype, L, hd):
     """fp32: 2e-5 abs vs the torch formula of custom_attn; bf16 storage: 2e-2."""
     from clip_decontamination_b200._lib import ATTN
