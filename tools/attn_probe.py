@@ -30,3 +30,9 @@ for name, fn in [('STD', lambda: ops.attention(qkv, n, L, heads, hd, ATTN['STD']
     us = t(fn)
     print(f'n={n} L={L} heads={heads} {name}: {us:.1f} us  {flops / us * 1e-6:.1f} TFLOP/s  '
           f'{(n * L * heads * hd * 2 * 4) / us * 1e-3:.0f} GB/s at the op boundary')
+if L <= ops.SIMT_COLS_MAX:
+    simt = torch.rand(n, ops.simt_floats(L), device='cuda')
+    us = t(lambda: ops.attention_experimental_tc(qkv, n, L, heads, out, simt, 1.0))
+    print(f'n={n} L={L} heads={heads} Experimental (tcgen05, similarity map): {us:.1f} us  {1.5 * flops / us * 1e-6:.1f} TFLOP/s')
+    us = t(lambda: ops.attention_experimental_tc(qkv, n, L, heads, out, None, 1.0))
+    print(f'n={n} L={L} heads={heads} Experimental (tcgen05, no map): {us:.1f} us')
