@@ -235,7 +235,7 @@ def main():
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=device)
-    global H, W, CROPS, WORKLOAD
+    global H, W, CROPS, WORKLOAD, METRIC
     wl = WORKLOADS[args.workload]
     if args.workload != 'vaihingen512':
         from clip_decontamination_b200.engine import slide_windows
@@ -243,6 +243,7 @@ def main():
         CROPS = len(slide_windows(H, W, 112, 224))
         WORKLOAD = f"{args.workload}: {H}x{W} synthetic tile, {wl['model']}, cls_{wl['cls']}.txt, jbu_one={wl['up']}, {CROPS} crops, extras ON"
         args.no_cpu_baseline = True
+        METRIC = f"megapixels/sec segmented ({wl['model']}, {H}x{W} tiles, {'jbu_one' if wl['up'] else 'no upsampler'})"
     model = build_model(device, args.precision, wl)
     eng = model.engine
     K = model.num_classes
@@ -348,7 +349,14 @@ def main():
             if name == 'gemm':      # per-shape split of the GEMM class (diagnostic)
                 A, B = a[0], a[1]
                 key = 'gemm[M%dxN%dxK%d]' % (k.get('M') or A.shape[0], k.get('N') or B.shape[0], k.get('K') or A.shape[1])
-                shape_records.setdefault(key, []).append((s, e, 2.0 * (k.get('M') or A.shape[0]) * (k.get('N') or B.shape[0]) * (k.get('K') or A.shape[1])))
+                Mg, Ng, Kg = k.get('M') or A.shape[0], k.get('N') or B.shape[0], k.get('K') or A.shape[1]
+                # bytes at the op boundary: both operands once, the output, the residual (fp32 for the residual stream)
+                nbytes = Mg * Kg * A.element_size() + Ng * Kg * B.element_size()
+                if len(a) > 2 and torch.is_tensor(a[2]):
+                    nbytes += Mg * Ng * a[2].element_size()
+                if torch.is_tensor(k.get('residual')):
+                    nbytes += Mg * Ng * k['residual'].element_size()
+                shape_records.setdefault(key, []).append((s, e, 2.0 * Mg * Ng * Kg, float(nbytes)))
             return r
         return inner
 
@@ -468,9 +476,16 @@ def main():
                     share_of_step=t_ms / ms_eager)
 
     rooflines = sorted((roofline_of(nm) for nm in classes), key=lambda r: -r['share_of_step'])
-    gemm_shapes = {k: dict(calls_per_step=len(v) // args.steps, ms_per_step=round(sum(s.elapsed_time(e) for s, e, _ in v) / args.steps, 4),
-                           tflops=round(sum(w for _, _, w in v) / sum(s.elapsed_time(e) for s, e, _ in v) / 1e9, 1))
-                   for k, v in shape_records.items()}
+    def shape_row(v):
+        # a GEMM shape is bound by whichever roofline it sits closer to: out-proj (K = width, fp32 residual in and out) moves
+        # 145 MB for 22 GFLOP at the bench batch and is HBM bound, QKV / fc1 / fc2 are tensor bound
+        t_ms = sum(s.elapsed_time(e) for s, e, _, _ in v)
+        tf, gbs = sum(w for _, _, w, _ in v) / t_ms / 1e9, sum(b for _, _, _, b in v) / t_ms / 1e6
+        ft, fh = tf / peaks['tf_sust'], gbs / peaks['hbm']
+        return dict(calls_per_step=len(v) // args.steps, ms_per_step=round(t_ms / args.steps, 4), tflops=round(tf, 1),
+                    gbs_at_op_boundary=round(gbs, 1), bound='tensor' if ft >= fh else 'hbm', frac=round(max(ft, fh), 3))
+
+    gemm_shapes = {k: shape_row(v) for k, v in shape_records.items()}
     roofline = dict(next(r for r in rooflines if r['kernel'] == dominant))
     roofline.update(eager_ms_per_step=ms_eager / args.steps, peak_source=peaks['src'], per_tile_ms_by_kernel=breakdown,
                     gemm_by_shape=gemm_shapes)

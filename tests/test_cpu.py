@@ -239,8 +239,17 @@ def test_cabi_argument_validation_without_gpu():
     rc = _lib.lib.cseg_accum_argmax(None, 0, 4, 1, 1, 1, 1, 0, 0, None, 0, 0, 0, 0, None, 1, 50.0, 0.0, 0, None, None,
                                     None, None)
     assert rc == -1 and 'empty' in _lib.last_error()
-    rc = _lib.lib.cseg_attention(0, None, 1, 1000, 12, 64, 0, None, 1.0, None, None, None)
-    assert rc == -1 and 'L=1000' in _lib.last_error()
+    rc = _lib.lib.cseg_attention(0, None, 1, 1, 12, 64, 0, None, 1.0, None, None, None)
+    assert rc == -1 and 'L=1' in _lib.last_error()
+    # any sequence length is accepted up to the one-score-row-per-warp limit of the long-sequence kernel (51 200 tokens)
+    rc = _lib.lib.cseg_attention(0, None, 1, 60000, 12, 64, 0, None, 1.0, None, None, None)
+    assert rc == -1 and 'L=60000' in _lib.last_error()
+    # the layout-1 similarity map of the header and of the binding agree
+    from clip_decontamination_b200 import ops
+    hdr = open(os.path.join(ROOT, 'include', 'clipseg.h')).read()
+    assert int(re.search(r'#define CSEG_SIMT_COLS (\d+)', hdr).group(1)) == ops.SIMT_COLS
+    assert int(re.search(r'#define CSEG_SIMT_COLS_MAX (\d+)', hdr).group(1)) == ops.SIMT_COLS_MAX
+    assert ops.simt_floats(197) == 7 * 208 * 32 and ops.simt_floats(257) == 9 * 272 * 32
 
 
 # ---------------------------------------------------------------- N > 1 path on CPU (gloo, world 2) --
