@@ -202,7 +202,9 @@ class VisualEngine:
         sim_w = (sim_cfg or {}).get('similarity_weight', 1.0)
         sim_t = (use_sim and exp_tc and sim_cfg.get('add_self_similarity', True) and width % 64 == 0 and width <= 1280)
         if sim_t:
-            simmap = ws.get('simmap_t', (n, ops.simt_floats(L)), f32, zero=True)
+            # one buffer per layout (208 / 272 key columns): only entries i, j >= 1 are ever written, so the zero CLS row /
+            # column of a layout survive any sequence of L and batch sizes -- but not a change of layout
+            simmap = ws.get(f'simmap_t{ops.simt_cols(L)}', (n, ops.simt_floats(L)), f32, zero=True)
         else:
             simmap = ws.get('simmap', (n, P, P), f32) if use_sim else None
         stats = ws.get('stats', (n, self.heads, 2, P), f32) if use_out else None

@@ -205,6 +205,24 @@ def test_seg_tiny_jbu(gold, precision, tol):
     _check_seg('seg_tiny_jbu', seg, g, precision, tol)
 
 
+def test_similarity_map_buffers_survive_layout_changes(gold):
+    """One engine, sequences of different token counts: the transposed similarity map has two layouts (208 / 272 key
+    columns) whose zero CLS row / column are only written at allocation.  Whole-image calls with L = 226 (272 columns), 290
+    (plain map) and 170 (208 columns), then the sliding 512x512 scene (L = 197) must reproduce a fresh engine's result."""
+    g = gold('seg_potsdam_noup')
+    seg = _seg_engine('ViT-B-16', 'potsdam', 'bf16', g)
+    crop = seg.crop
+    for hw in ((240, 240), (272, 272), (208, 208)):        # L = 226 (272 columns), 290 (beyond both: plain map), 170 (208)
+        seg.crop = 0
+        lab = seg.segment(torch.from_numpy(synth.preprocess(synth.voronoi_scene(hw[0], hw[1], 5))).cuda())[0]
+        assert lab.shape == hw
+    seg.crop = crop
+    e, _ = _check_seg('seg_potsdam_noup after whole-image calls', seg, g, 'bf16', 1e-2)
+    fresh = _seg_engine('ViT-B-16', 'potsdam', 'bf16', g)
+    e0, _ = _check_seg('seg_potsdam_noup fresh engine', fresh, g, 'bf16', 1e-2)
+    assert e == e0                                         # bit-identical logits error: nothing stale was read
+
+
 @pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('bf16', 1e-2)])
 def test_seg_potsdam_noup(gold, precision, tol):
     """BASELINE config 1 without the upsampler: 512x512, ViT-B/16, 16 crops, extras ON."""
