@@ -113,7 +113,7 @@ __global__ void fz_tables_kernel(int W2, int H2, int R, uint4* __restrict__ tabx
 // MODE 2: the border frames (fb = CSEG_JBU_FB_COMP) of n crops, compact kc; the fixed-up kernel of a frame pixel comes
 //         from the per-crop border tensor (frame CSEG_JBU_FB_RANGE) or, further inside, from the image-level tensor.
 template <int R, int MODE>
-__global__ void __launch_bounds__(256) fz_composite_kernel(const bf16* __restrict__ kern, int ldk, long long n_px, int H2,
+__global__ void __launch_bounds__(256, MODE == 2 ? 6 : 1) fz_composite_kernel(const bf16* __restrict__ kern, int ldk, long long n_px, int H2,
                                                            int W2, const uint4* __restrict__ tabx,
                                                            const uint4* __restrict__ taby, bf16* __restrict__ kc,
                                                            const bf16* __restrict__ kern_img, const ShareGeom sg, int iw) {
@@ -136,6 +136,18 @@ __global__ void __launch_bounds__(256) fz_composite_kernel(const bf16* __restric
   const int roww = MODE == 1 ? iw : W2;
   const int rb_c = border_rows(H2, W2, CSEG_JBU_FB_COMP), rb_r = border_rows(H2, W2, CSEG_JBU_FB_RANGE);
   int x = (int)(p_begin % roww), y = MODE == 1 ? (int)(p_begin / roww) : (int)((p_begin / roww) % H2);
+  // MODE 2: (crop, compact frame row r) -> (by, bx) also advance incrementally: the divisions of border_coords and the
+  // window look-up happen once per run / per crop, not once per pixel
+  constexpr int FBC = CSEG_JBU_FB_COMP;
+  const int s1 = FBC * W2, s2 = 2 * FBC * W2;
+  int crop = 0, r = 0, bx = 0, by = 0;
+  size_t org0 = 0;
+  if (MODE == 2 && p_begin < p_end) {
+    crop = (int)(p_begin / rb_c);
+    r = (int)(p_begin - (long long)crop * rb_c);
+    border_coords(r, H2, W2, FBC, by, bx);
+    org0 = (size_t)(sg.wins[crop * 4] >> sg.shift) * sg.pitch + (sg.wins[crop * 4 + 1] >> sg.shift);
+  }
   for (long long p = p_begin; p < p_end; ++p, ++x) {
     if (MODE != 2 && x == roww) {
       x = 0;
@@ -150,13 +162,29 @@ __global__ void __launch_bounds__(256) fz_composite_kernel(const bf16* __restric
       ty = 16 + (y & 1);
       krow = kern + p * ldk;
     } else {
-      const int crop = (int)(p / rb_c), r = (int)(p - (long long)crop * rb_c);
-      border_coords(r, H2, W2, CSEG_JBU_FB_COMP, ty, tx);
+      tx = bx;
+      ty = by;
       if (border_interior(ty, tx, H2, W2, CSEG_JBU_FB_RANGE)) {
-        const size_t org = (size_t)((sg.wins[crop * 4] >> sg.shift) + ty) * sg.pitch + (sg.wins[crop * 4 + 1] >> sg.shift) + tx;
-        krow = kern_img + org * ldk;
+        krow = kern_img + (org0 + (size_t)ty * sg.pitch + tx) * ldk;
       } else {
         krow = kern + ((size_t)crop * rb_r + border_index(ty, tx, H2, W2, CSEG_JBU_FB_RANGE)) * ldk;
+      }
+      // next frame pixel (layout of jbu_share.cuh: top strip, bottom strip, then 32-pixel groups of the rows in between)
+      if (++r == rb_c) {
+        r = 0;
+        ++crop;
+        bx = by = 0;
+        if (p + 1 < p_end) org0 = (size_t)(sg.wins[crop * 4] >> sg.shift) * sg.pitch + (sg.wins[crop * 4 + 1] >> sg.shift);
+      } else if (r < s2) {
+        if (++bx == W2) {
+          bx = 0;
+          ++by;
+          if (r == s1) by = H2 - FBC;
+        }
+      } else {
+        const int q = r - s2, c = q & 31;
+        by = FBC + (q >> 5);
+        bx = c < 16 ? c : W2 - 32 + c;
       }
     }
     const uint4 txv = __ldg(tabx + (size_t)tx * 32 + lane), tyv = __ldg(taby + (size_t)ty * 32 + lane);
