@@ -287,3 +287,22 @@ print('ok', r)
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count('ok') == 2
+
+
+def test_bench_workloads_are_runnable_configs():
+    """every --workload of bench.py names an existing class file, a known model and query features of that model's width"""
+    import importlib
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module('bench')
+    from clip_decontamination_b200.open_clip.model_configs import get_model_config
+    assert bench.WORKLOADS['vaihingen512']['H'] == 512 and 'loveda1024_vitl' in bench.WORKLOADS
+    for name, wl in bench.WORKLOADS.items():
+        cfg = get_model_config(wl['model'].replace('/', '-'))
+        assert os.path.exists(os.path.join(ROOT, 'configs', f"cls_{wl['cls']}.txt")), name
+        if wl.get('text'):
+            qf = np.load(os.path.join(ROOT, 'tests', 'golden', wl['text']))['query_features']
+        else:
+            qf = np.load(os.path.join(ROOT, 'tests', 'golden', 'bench_text.npz'))[f"{wl['cls']}_query_features"]
+        assert qf.shape[1] == cfg['embed_dim'], (name, qf.shape)
+        assert wl['up'] is False or cfg['vision_cfg']['patch_size'] == 16, name     # JBU x16 needs patch 16 (segmentor.py:372)
