@@ -111,6 +111,27 @@ def test_oracle_full_segmentor(gold, name, model, ups):
     assert (pred[0].numpy() == g['labels']).mean() >= 0.9999
 
 
+def test_oracle_whole_image_long_sequence(gold):
+    """slide_crop = 0 (segmentor.py:470-471) on a 400x400 image: ONE crop of L = 626 tokens, interpolated positional
+    embedding, a single bilinear resize to ori_shape.  The oracle against the unmodified reference's golden."""
+    g = gold('seg_whole_400_noup')
+    cfg = get_model_config('ViT-B-16')
+    v = cfg['vision_cfg']
+    m = g['meta']
+    H, W, thd, bg, seed, crop = int(m[0]), int(m[1]), float(m[2]), int(m[3]), int(m[4]), int(m[6])
+    assert crop == 0
+    orc = O.SegOracle(_vis(cfg), torch.from_numpy(g['query_features']), g['query_idx'].tolist(), layers=v['layers'],
+                      heads=v['heads'], patch=v['patch_size'], prob_thd=thd, bg_idx=bg, slide_crop=0,
+                      global_debias_factor=0.2, upsampler=None, sim_cfg={}, outlier_cfg={'top_k': 30})
+    img = torch.from_numpy(synth.preprocess(synth.voronoi_scene(H, W, seed)))[None]
+    with torch.no_grad():
+        lg = orc.forward_feature(img, (H, W))
+        _, pred = orc.postprocess(lg[0])
+    sub = int(m[10])
+    assert np.abs(lg[0].numpy()[:, ::sub, ::sub] - g['logits_sub'].astype(np.float32)).max() < 1e-5
+    assert (pred.numpy().reshape(H, W) == g['labels']).mean() >= 0.9999
+
+
 def test_oracle_iou_metrics():
     pred = torch.tensor([0, 1, 1, 2, 2, 2, 0, 255 % 3])
     lab = torch.tensor([0, 1, 2, 2, 2, 255, 1, 0])
