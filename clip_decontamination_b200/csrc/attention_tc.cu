@@ -5,14 +5,14 @@
 // One work item = one (crop, head); a persistent CTA per SM walks the items.  L <= 208 keys fit one MMA in N, so there
 // is no online softmax: per 128-query tile
 //   S[128, 208]  = Q_tile . K^T       4 x tcgen05.mma (K = 16) into TMEM (two S buffers: the MMA warp runs a tile ahead)
-//   P            = exp2((S - rowmax) * scale * log2 e)   by 8 warps: row quarter = warp % 4 (the TMEM lane window a warp
-//                  may touch), key half = warp / 4; row max / row sum are exchanged through shared memory; P is written
+//   P            = exp2((S - rowmax) * scale * log2 e)   by 16 warps: row quarter = warp % 4 (the TMEM lane window a warp
+//                  may touch), key quarter = warp / 4; row max / row sum are exchanged through shared memory; P is written
 //                  as bf16 straight into the K-major SWIZZLE_128B layout the second MMA reads
 //   O[128, 64]   = P . V              13 x tcgen05.mma; V is consumed in its natural [key][dim] layout as an MN-major
 //                  SWIZZLE_128B B operand (no transpose); 1 / rowsum is applied in the epilogue.
 // Q / K / V tiles arrive by TMA from the [rows, 3*width] QKV matrix (the rows of a crop that lie beyond L belong to the
 // next crop: those key columns are masked, those query rows are never stored).
-// Warp roles: 0-7 softmax + epilogue, 8 TMA producer, 9 TMEM allocator + MMA issuer.
+// Warp roles: 0-15 softmax + epilogue, 16 TMA producer, 17 TMEM allocator + MMA issuer.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <stdlib.h>
